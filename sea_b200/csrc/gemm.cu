@@ -1,0 +1,418 @@
+// K1 — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] · B[N,K]^T   (both operands K-major bf16, fp32 accumulation in TMEM)
+//
+// Roles (192 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled A (128x64) and B (BNx64) tiles
+//               into a STAGES-deep shared-memory ring, completion on `full` mbarriers;
+//   warp 1      allocates TMEM (2 accumulator stages x BN columns) and issues tcgen05.mma
+//               (M=128, N=BN, K=16) from lane 0; tcgen05.commit releases ring slots (`empty`)
+//               and publishes finished accumulators (`tfull`);
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (one accumulator row per thread), fused
+//               bias / residual / RoPE / GELU' / GELU / dtype casts, vectorised global stores,
+//               then hand the TMEM stage back (`tempty`) so the next tile's MMAs overlap.
+//
+// Up to 4 same-shape problems share one launch ("groups": the V independent field streams of
+// models/temporal.py:135-146 run their Linear layers side by side).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include "../../include/sea_b200.h"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace sea {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kMaxGroups = 4;
+constexpr int kThreads = 192;
+constexpr int A_BYTES = BM * BK * 2;
+
+struct DevEpilogue {
+  const float* bias;
+  const float* residual;
+  const __nv_bfloat16* gelu_grad_of;
+  const float* rope_table;
+  float* out_f32;
+  __nv_bfloat16* out_pre_bf16;
+  __nv_bfloat16* out_bf16;
+  long long ld_residual, ld_gelu, ld_out_f32, ld_out_pre_bf16, ld_out_bf16;
+  int act, rope_cols, head_dim, seq_len;
+  float rope_sign;
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap tma_a[kMaxGroups];
+  CUtensorMap tma_b[kMaxGroups];
+  DevEpilogue epi[kMaxGroups];
+  int M, N, K;
+  int groups, tiles_m, tiles_n;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint32_t (&r)[32],
+                                               int m, int n0, int M, int N) {
+  // One thread = one output row m, 32 consecutive columns starting at n0.
+  if (m >= M || n0 >= N) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  const int nvalid = min(32, N - n0);  // multiple of 8 (N % 8 == 0 is enforced on the host)
+
+  if (e.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < nvalid) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+  }
+  if (e.residual != nullptr) {
+    const float* rp = e.residual + static_cast<long long>(m) * e.ld_residual + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < nvalid) {
+        const float4 b = *reinterpret_cast<const float4*>(rp + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+  }
+  if (e.rope_table != nullptr && n0 < e.rope_cols) {
+    // models/base_blocks.py:314-324 — interleaved pairs (x[2k], x[2k+1]) times (cos + i sin).
+    const int t = m % e.seq_len;
+    const int d0 = n0 % e.head_dim;
+    const float2* tab = reinterpret_cast<const float2*>(e.rope_table) +
+                        static_cast<long long>(t) * (e.head_dim >> 1) + (d0 >> 1);
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float2 cs = __ldg(tab + (j >> 1));
+      const float s = cs.y * e.rope_sign;
+      const float x0 = v[j], x1 = v[j + 1];
+      v[j] = x0 * cs.x - x1 * s;
+      v[j + 1] = x0 * s + x1 * cs.x;
+    }
+  }
+  if (e.gelu_grad_of != nullptr) {
+    const __nv_bfloat16* gp = e.gelu_grad_of + static_cast<long long>(m) * e.ld_gelu + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < nvalid) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(gp + j);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(h[q]);
+          v[j + 2 * q] *= ptx::gelu_erf_grad(f.x);
+          v[j + 2 * q + 1] *= ptx::gelu_erf_grad(f.y);
+        }
+      }
+    }
+  }
+  if (e.out_f32 != nullptr) {
+    float* op = e.out_f32 + static_cast<long long>(m) * e.ld_out_f32 + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < nvalid) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  if (e.out_pre_bf16 != nullptr) {
+    __nv_bfloat16* op = e.out_pre_bf16 + static_cast<long long>(m) * e.ld_out_pre_bf16 + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < nvalid) {
+        uint4 o;
+        o.x = ptx::pack_bf16(v[j], v[j + 1]);
+        o.y = ptx::pack_bf16(v[j + 2], v[j + 3]);
+        o.z = ptx::pack_bf16(v[j + 4], v[j + 5]);
+        o.w = ptx::pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(op + j) = o;
+      }
+    }
+  }
+  if (e.out_bf16 != nullptr) {
+    if (e.act == SEA_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ptx::gelu_erf(v[j]);
+    }
+    __nv_bfloat16* op = e.out_bf16 + static_cast<long long>(m) * e.ld_out_bf16 + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < nvalid) {
+        uint4 o;
+        o.x = ptx::pack_bf16(v[j], v[j + 1]);
+        o.y = ptx::pack_bf16(v[j + 2], v[j + 3]);
+        o.z = ptx::pack_bf16(v[j + 4], v[j + 5]);
+        o.w = ptx::pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(op + j) = o;
+      }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]       MMA -> epilogue
+  uint64_t* tempty = tfull + 2;          // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int tiles_per_group = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_per_group * p.groups;
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < p.groups; ++g) {
+      ptx::prefetch_tmap(&p.tma_a[g]);
+      ptx::prefetch_tmap(&p.tma_b[g]);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int g = tile / tiles_per_group;
+        const int r = tile - g * tiles_per_group;
+        const int tm = r % p.tiles_m;
+        const int tn = r / p.tiles_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          ptx::tma_load_2d(smem_a + stage * A_BYTES, &p.tma_a[g], &full[stage], kb * BK, tm * BM);
+          ptx::tma_load_2d(smem_b + stage * C::B_BYTES, &p.tma_b[g], &full[stage], kb * BK, tn * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = ptx::smem_u32(smem_a + stage * A_BYTES);
+          const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = ptx::umma_smem_desc(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc = ptx::umma_smem_desc(b_base + k * 32, 16, 1024);
+            ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) ptx::umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // --------------------------------------------------------------- epilogue
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int g = tile / tiles_per_group;
+      const int r = tile - g * tiles_per_group;
+      const int tm = r % p.tiles_m;
+      const int tn = r / p.tiles_m;
+      const DevEpilogue& e = p.epi[g];
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int m = tm * BM + quarter * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t regs[32];
+        ptx::tmem_ld_32x32(t_row + c * 32, regs);
+        ptx::tmem_ld_wait();
+        epilogue_chunk(e, regs, m, tn * BN + c * 32, p.M, p.N);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+int g_force_bn = 0;
+
+template <int BN>
+int launch(const GemmParams& p, int total_tiles, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set[dev] = true;
+  }
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  gemm_bf16_tn_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer,
+                      uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  auto encode = tensor_map_encoder();
+  if (encode == nullptr) return SEA_ERR_NO_DEVICE;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SEA_OK : SEA_ERR_INVALID;
+}
+
+}  // namespace sea
+
+extern "C" void sea_gemm_force_tile_n(int bn) { sea::g_force_bn = bn; }
+
+extern "C" int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* probs, int M, int N,
+                                int K, sea_stream_t stream) {
+  using namespace sea;
+  if (probs == nullptr || num_problems < 1 || num_problems > kMaxGroups) return SEA_ERR_INVALID;
+  if (M <= 0 || N <= 0 || K <= 0) return SEA_ERR_INVALID;
+  if ((N % 8) != 0 || (K % 8) != 0) return SEA_ERR_UNSUPPORTED;
+  int rc = ensure_init();
+  if (rc != SEA_OK) return rc;
+
+  int bn = g_force_bn;
+  if (bn == 0) {
+    // Fill the machine first; prefer the widest tile that still gives >= 1 wave.
+    const long long tm = (M + BM - 1) / BM;
+    const long long t256 = tm * ((N + 255) / 256) * num_problems;
+    const long long t128 = tm * ((N + 127) / 128) * num_problems;
+    if (t256 >= 2LL * num_sms()) bn = 256;
+    else if (t128 >= num_sms()) bn = 128;
+    else bn = 64;
+  }
+  if (bn != 64 && bn != 128 && bn != 256) return SEA_ERR_INVALID;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.groups = num_problems;
+  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_n = (N + bn - 1) / bn;
+  for (int g = 0; g < num_problems; ++g) {
+    const sea_gemm_problem& q = probs[g];
+    const sea_gemm_epilogue& e = q.epi;
+    if (q.a == nullptr || q.b == nullptr) return SEA_ERR_INVALID;
+    if ((q.lda % 8) != 0 || (q.ldb % 8) != 0 || q.lda < K || q.ldb < K) return SEA_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(q.a) & 15) || (reinterpret_cast<uintptr_t>(q.b) & 15))
+      return SEA_ERR_INVALID;
+    if (e.out_f32 == nullptr && e.out_bf16 == nullptr && e.out_pre_bf16 == nullptr)
+      return SEA_ERR_INVALID;
+    if (e.out_f32 && ((e.ld_out_f32 % 4) || (reinterpret_cast<uintptr_t>(e.out_f32) & 15)))
+      return SEA_ERR_INVALID;
+    if (e.out_bf16 && ((e.ld_out_bf16 % 8) || (reinterpret_cast<uintptr_t>(e.out_bf16) & 15)))
+      return SEA_ERR_INVALID;
+    if (e.out_pre_bf16 &&
+        ((e.ld_out_pre_bf16 % 8) || (reinterpret_cast<uintptr_t>(e.out_pre_bf16) & 15)))
+      return SEA_ERR_INVALID;
+    if (e.residual && ((e.ld_residual % 4) || (reinterpret_cast<uintptr_t>(e.residual) & 15)))
+      return SEA_ERR_INVALID;
+    if (e.gelu_grad_of && ((e.ld_gelu % 8) || (reinterpret_cast<uintptr_t>(e.gelu_grad_of) & 15)))
+      return SEA_ERR_INVALID;
+    if (e.bias && (reinterpret_cast<uintptr_t>(e.bias) & 15)) return SEA_ERR_INVALID;
+    if (e.rope_table != nullptr && e.rope_cols > 0) {
+      if (e.head_dim <= 0 || (e.head_dim % 32) || (e.rope_cols % e.head_dim) || e.seq_len <= 0)
+        return SEA_ERR_UNSUPPORTED;
+    }
+    rc = make_tmap_bf16_2d(&p.tma_a[g], q.a, K, M, q.lda, BK, BM);
+    if (rc != SEA_OK) return rc;
+    rc = make_tmap_bf16_2d(&p.tma_b[g], q.b, K, N, q.ldb, BK, bn);
+    if (rc != SEA_OK) return rc;
+    DevEpilogue& d = p.epi[g];
+    d.bias = e.bias;
+    d.residual = e.residual;
+    d.gelu_grad_of = static_cast<const __nv_bfloat16*>(e.gelu_grad_of);
+    d.rope_table = (e.rope_cols > 0) ? e.rope_table : nullptr;
+    d.out_f32 = e.out_f32;
+    d.out_pre_bf16 = static_cast<__nv_bfloat16*>(e.out_pre_bf16);
+    d.out_bf16 = static_cast<__nv_bfloat16*>(e.out_bf16);
+    d.ld_residual = e.ld_residual;
+    d.ld_gelu = e.ld_gelu;
+    d.ld_out_f32 = e.ld_out_f32;
+    d.ld_out_pre_bf16 = e.ld_out_pre_bf16;
+    d.ld_out_bf16 = e.ld_out_bf16;
+    d.act = e.act;
+    d.rope_cols = e.rope_cols;
+    d.head_dim = e.head_dim;
+    d.seq_len = e.seq_len;
+    d.rope_sign = (e.rope_sign == 0.0f) ? 1.0f : e.rope_sign;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.groups;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 256) return launch<256>(p, total, s);
+  if (bn == 128) return launch<128>(p, total, s);
+  return launch<64>(p, total, s);
+}

@@ -1,0 +1,32 @@
+// Internal host-side helpers shared by the translation units of libsea_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sea {
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                      const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int ensure_init();                       // lazily runs sea_init(current device)
+int num_sms();                           // SM count of the initialised device
+TensorMapEncodeFn tensor_map_encoder();  // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
+
+// 2-D bf16 tensor map, 128B swizzle: dims {inner, outer}, row pitch ld_elems, box {bi, bo}.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer,
+                      uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer);
+// 3-D bf16 tensor map {inner, mid, outer} with pitches in elements; box {bi, bm, 1}.
+int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t mid,
+                      uint64_t outer, uint64_t ld_mid, uint64_t ld_outer, uint32_t box_inner,
+                      uint32_t box_mid);
+
+#define SEA_CUDA_OK(expr)                                  \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return static_cast<int>(_e);    \
+  } while (0)
+
+}  // namespace sea

@@ -1,0 +1,111 @@
+"""K1 parity: tcgen05 GEMM + fused epilogues vs torch (fp32 math on bf16-rounded operands)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b):
+    return a.float() @ b.float().t()
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256, 0])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (798, 1024, 1024), (796, 3072, 512),
+                                   (37, 72, 136), (1000, 8192, 1024)])
+def test_gemm_plain(cuda, bn, M, N, K):
+    from sea_b200 import lib, ops
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    b = (torch.randn(N, K, device=cuda, generator=g) * 0.05).bfloat16()
+    out = torch.full((M, N), float("nan"), device=cuda)
+    lib.sea_gemm_force_tile_n(bn)
+    try:
+        ops.gemm_bf16_tn([ops.gemm_problem(a, b, out_f32=out)], M, N, K)
+    finally:
+        lib.sea_gemm_force_tile_n(0)
+    torch.cuda.synchronize()
+    ref = _ref(a, b)
+    err = (out - ref).abs().max().item()
+    assert torch.isfinite(out).all()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-4, err
+
+
+def test_gemm_epilogue_bias_residual_gelu(cuda):
+    from sea_b200 import ops
+    M, N, K = 798, 1024, 512
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    b = (torch.randn(N, K, device=cuda, generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device=cuda, generator=g)
+    res = torch.randn(M, N, device=cuda, generator=g)
+    out = torch.empty(M, N, device=cuda)
+    pre = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    act = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm_bf16_tn([ops.gemm_problem(a, b, bias=bias, residual=res, act=ops.ACT_GELU,
+                                       out_f32=out, out_pre_bf16=pre, out_bf16=act)], M, N, K)
+    torch.cuda.synchronize()
+    ref = _ref(a, b) + bias + res
+    assert (out - ref).abs().max().item() < 5e-3
+    assert (pre.float() - ref).abs().max().item() < 5e-2
+    assert (act.float() - torch.nn.functional.gelu(ref)).abs().max().item() < 5e-2
+
+
+def test_gemm_grouped_and_strided(cuda):
+    from sea_b200 import ops
+    M, N, K = 400, 512, 256
+    g = torch.Generator(device="cuda").manual_seed(2)
+    big = torch.randn(M, 2, K, device=cuda, generator=g).bfloat16()   # two interleaved streams
+    w = [(torch.randn(N, K, device=cuda, generator=g) * 0.05).bfloat16() for _ in range(2)]
+    out = torch.empty(M, 2, N, device=cuda)
+    probs = [ops.gemm_problem(big[:, i], w[i], out_f32=out[:, i]) for i in range(2)]
+    ops.gemm_bf16_tn(probs, M, N, K)
+    torch.cuda.synchronize()
+    for i in range(2):
+        ref = _ref(big[:, i], w[i])
+        assert (out[:, i] - ref).abs().max().item() < 5e-3
+
+
+def test_gemm_rope_epilogue(cuda):
+    from sea_b200 import ops
+    B, T, E, hd = 2, 100, 512, 128
+    M, N, K = B * T, 3 * E, 256
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    b = (torch.randn(N, K, device=cuda, generator=g) * 0.05).bfloat16()
+    freqs = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device=cuda).float() / hd))
+    ang = torch.outer(torch.arange(T, device=cuda).float(), freqs)
+    table = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()    # [T, hd/2, 2]
+    out = torch.empty(M, N, device=cuda)
+    ops.gemm_bf16_tn([ops.gemm_problem(a, b, rope_table=table, rope_cols=2 * E, head_dim=hd,
+                                       seq_len=T, out_f32=out)], M, N, K)
+    torch.cuda.synchronize()
+    ref = _ref(a, b)
+    qk = ref[:, :2 * E].reshape(B, T, 2 * E // hd, hd // 2, 2)
+    c = torch.view_as_complex(qk.contiguous()) * torch.polar(torch.ones_like(ang), ang)[None, :, None, :]
+    ref_rot = torch.cat([torch.view_as_real(c).reshape(M, 2 * E), ref[:, 2 * E:]], dim=1)
+    assert (out - ref_rot).abs().max().item() < 5e-3
+
+
+def test_gemm_throughput_report(cuda):
+    """Not a pass/fail perf gate — prints TFLOP/s so the first GPU run tells us where we are."""
+    from sea_b200 import lib, ops
+    for (M, N, K) in [(8192, 8192, 8192), (12768, 8192, 1024), (12768, 1024, 8192), (798, 8192, 1024)]:
+        a = torch.randn(M, K, device=cuda).bfloat16()
+        b = torch.randn(N, K, device=cuda).bfloat16()
+        out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+        for bn in (128, 256):
+            lib.sea_gemm_force_tile_n(bn)
+            prob = [ops.gemm_problem(a, b, out_bf16=out)]
+            for _ in range(3):
+                ops.gemm_bf16_tn(prob, M, N, K)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(10):
+                ops.gemm_bf16_tn(prob, M, N, K)
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / 10
+            print(f"\n[gemm] M={M} N={N} K={K} BN={bn}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s")
+        lib.sea_gemm_force_tile_n(0)
+        ref = _ref(a[:64], b[:64])
+        assert (out[:64, :64].float() - ref).abs().max().item() < 0.02 * ref.abs().max().item() + 0.5
