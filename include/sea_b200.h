@@ -95,8 +95,180 @@ typedef struct sea_gemm_problem {
 /* `num_problems` (1..4) same-shape problems in ONE launch (the V field streams are independent). */
 int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* host_problems, int M, int N, int K,
                      sea_stream_t stream);
+/* Same, but the K loop is cut into chunks of `k_chunk` elements (multiple of 64; 0 = one chunk):
+ * every chunk gets a fresh TMEM accumulator and the chunk sums are added in fp32 round-to-nearest
+ * by the epilogue through out_f32 (required, must not alias residual).  Used by the fp32-parity
+ * mode: the tensor core's own accumulator does not round to nearest, so long K chains drift. */
+int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem* host_problems, int M, int N,
+                             int K, int k_chunk, sea_stream_t stream);
 /* Test / tuning hook: force the N-tile (64, 128, 256) of the next launches; 0 = heuristic. */
 void sea_gemm_force_tile_n(int bn);
+
+/* ------------------------------------------------------------------ K4: row norms -----------
+ * LayerNorm (custom, weight only: models/base_blocks.py:80-88) or AdaLN (:343-350) over the last
+ * dim of fp32 rows; optional fused TIPI add in front (models/temporal.py:111-116, 140-142):
+ *   x' = x + W3 g[m] + b3   (written to x_out),   y = norm(x')
+ * cond (AdaLN) = output of cond_mlp, [M, 2d]: first half scales, second half shifts.
+ * stats (optional) receives (mean, rstd) per row for the backward pass.  d % 4 == 0, d <= 2048. */
+typedef struct sea_norm_args {
+  const float* x;
+  int64_t ldx;
+  int32_t M, d, kind; /* SEA_NORM_* */
+  const float* weight;
+  const float* bias; /* AdaLN's own bias or NULL */
+  const float* cond;
+  int64_t ldc;
+  const float* tipi_g; /* [M, tipi_hid] from sea_tipi_hidden, or NULL */
+  int32_t tipi_hid;
+  const float* tipi_w; /* [d, tipi_hid] */
+  const float* tipi_b; /* [d] */
+  float* x_out;
+  int64_t ldxo;
+  float* y_f32;
+  int64_t ldy_f32;
+  void* y_bf16;
+  int64_t ldy_bf16;
+  float* stats;
+} sea_norm_args;
+int sea_norm_fwd(const sea_norm_args* args, sea_stream_t stream);
+
+/* AdaLN cond_mlp[0] + SiLU on the scalar condition: h[m,j] = SiLU(w1[j,:]·ib[m,:] + b1[j]), j < n
+ * (models/base_blocks.py:337-339, 344).  Either output may be NULL. */
+int sea_adaln_hidden(const float* ib, int M, int ib_num, const float* w1, const float* b1, int n,
+                     void* out_bf16, float* out_f32, sea_stream_t stream);
+
+/* TIPI hidden layer g = GELU(LayerNorm(W0 ib + b0)), hid <= 64 (models/base_blocks.py:22-25 as
+ * instantiated by models/temporal.py:108).  pre_out / stats_out (optional) are saved for backward. */
+int sea_tipi_hidden(const float* ib, int M, int ib_num, const float* w0, const float* b0,
+                    const float* ln_w, const float* ln_b, int hid, float* g_out, float* pre_out,
+                    float* stats_out, sea_stream_t stream);
+
+/* ------------------------------------------------------------------ K6: LayerNorm(H) + GELU --
+ * The MLP's inner nn.LayerNorm(H) (affine, eps 1e-5) followed by exact-erf GELU
+ * (models/base_blocks.py:23-25).  bf16->bf16 or fp32->fp32.  H % 8 == 0, H <= 16384. */
+typedef struct sea_ln_gelu_args {
+  const void* h_bf16;
+  const float* h_f32;
+  int64_t ldh;
+  int32_t M, H;
+  const float* weight;
+  const float* bias;
+  void* g_bf16;
+  float* g_f32;
+  int64_t ldg;
+  float* stats;
+} sea_ln_gelu_args;
+int sea_ln_gelu_fwd(const sea_ln_gelu_args* args, sea_stream_t stream);
+
+/* ------------------------------------------------------------------ operand packing ----------
+ * src [R,C] (fp32 or bf16) -> bf16 dst, optionally transposed, optionally GELU'd on load,
+ * optionally expanded to the 3-way bf16 split (split=1: A-side pattern, 2: B-side pattern; the
+ * destination then has 6x the columns) that makes sea_gemm_bf16_tn fp32-accurate. */
+typedef struct sea_pack_args {
+  const float* src_f32;
+  const void* src_bf16;
+  int64_t ld;
+  int32_t R, C;
+  int32_t transpose, split, act;
+  int32_t split_inner; /* 0: default (row length of dst / 6); else distance between split segments */
+  void* dst;
+  int64_t ld_dst;
+} sea_pack_args;
+int sea_pack_operand(const sea_pack_args* args, sea_stream_t stream);
+
+/* out[n] += sum_m src[m,n]  (bias gradients). */
+int sea_colsum_accumulate(const float* src_f32, const void* src_bf16, int64_t ld, int M, int N,
+                          float* out, sea_stream_t stream);
+
+/* ------------------------------------------------------------------ K2: attention ------------
+ * softmax(mask(Q K^T * scale)) V per (batch, head), causal with offset: key k is visible to
+ * query q iff k <= q + src_len  (models/base_blocks.py:191-197 and 283-289; Q and K/V come from
+ * different tensors for the state-exchange cross-attention).  Rows of q/k/v/o are (b*T + t),
+ * head h occupies columns [h*head_dim, (h+1)*head_dim).  q,k are expected to be RoPE'd already
+ * (fused into the projection GEMM epilogue).  lse (optional) = log-sum-exp of the scaled scores,
+ * [B, n_heads, T], for the backward pass. */
+typedef struct sea_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  int64_t ldq, ldk, ldv;
+  void* o;
+  int64_t ldo;
+  float* lse;
+  int32_t B, T, n_heads, head_dim;
+  int32_t src_len;
+  float scale;
+  int32_t prec; /* SEA_PREC_BF16: bf16 in/out; SEA_PREC_FP32: fp32 in/out */
+} sea_attn_args;
+int sea_attention_fwd(const sea_attn_args* args, sea_stream_t stream);
+/* Test hook: 1 forces the CUDA-core kernel even where the tcgen05 kernel applies. */
+void sea_attention_force_simt(int on);
+
+/* ------------------------------------------------------------------ temporal model -----------
+ * Whole-model executor for TemporalModel with exchange_mode='sea', ib_scale_mode='mlp',
+ * ib_addition_mode='add', add_info_after_cross=True (the mode both reference configs select):
+ *   TemporalModel.forward                models/temporal.py:405-416
+ *   BaseBlockTemporal.forward            models/temporal.py:126-148
+ *   SEABlockTemporal._apply_exchange     models/temporal.py:176-192
+ * The descriptor mirrors the reference module tree: every field is the fp32 master parameter
+ * (`p`, the nn.Parameter's storage) and, for training, where its gradient goes (`g`, may be NULL).
+ * Dead parameters of the reference do not appear. */
+#define SEA_MAX_STREAMS 4
+
+typedef struct sea_param {
+  const float* p;
+  float* g;
+} sea_param;
+
+typedef struct sea_norm_params { /* LayerNorm(weight) or AdaLN(weight, bias, cond_mlp) */
+  sea_param weight, bias;
+  sea_param c0_w, c0_b; /* cond_mlp.0: [2d, ib_num], [2d] */
+  sea_param c2_w, c2_b; /* cond_mlp.2: [2d, 2d],    [2d] */
+} sea_norm_params;
+
+typedef struct sea_attn_params { /* q,k,v with bias; projection without */
+  sea_param q_w, q_b, k_w, k_b, v_w, v_b, proj_w;
+} sea_attn_params;
+
+typedef struct sea_stream_params {
+  sea_norm_params ln0, ln2, ln_cross;            /* ln.exp.{i}.0, ln.exp.{i}.2, ln_cross.{i} */
+  sea_attn_params self_attn;                     /* attn.self.{i}  */
+  sea_attn_params cross_attn[SEA_MAX_STREAMS];   /* cross_attn.{i}.{j}, j != i */
+  sea_param down_w, down_b, up_w, up_b;          /* cross_down.{i}, cross_up.{i} */
+  sea_param mlp0_w, mlp0_b, mlp_ln_w, mlp_ln_b, mlp3_w, mlp3_b; /* mlp.{i}.layers.{0,1,3} */
+  sea_param proj_w, proj_b;                      /* proj.{i} */
+} sea_stream_params;
+
+typedef struct sea_block_params {
+  sea_stream_params s[SEA_MAX_STREAMS];
+  sea_param ib0_w, ib0_b, ib_ln_w, ib_ln_b, ib3_w, ib3_b; /* ib.layers.{0,1,3} (TIPI) */
+} sea_block_params;
+
+typedef struct sea_temporal_desc {
+  int32_t num_layers, num_streams;
+  int32_t embed_dim, n_heads, hidden_dim /* scale_ratio*E */, down_dim /* E/down_proj */;
+  int32_t ib_num, ib_hidden /* max(1, scale_ratio*ib_num) */;
+  int32_t norm_kind /* SEA_NORM_* */, src_len, max_len;
+  int32_t precision /* SEA_PREC_BF16: bf16 tensor-core operands; SEA_PREC_FP32: 3-way split */;
+  const sea_block_params* blocks; /* host array [num_layers] */
+  sea_norm_params final_ln[SEA_MAX_STREAMS]; /* ln.{i} */
+  const float* rope_self;  /* device [max_len, (E/n_heads)/2, 2] (cos, sin) */
+  const float* rope_cross; /* device [max_len, (down_dim/n_heads)/2, 2] */
+} sea_temporal_desc;
+
+/* Packed low-precision copies of the weights (bf16, fused QKV / KV, optional transposes for the
+ * backward pass) live in a caller-owned cache; refresh after every parameter update. */
+size_t sea_temporal_cache_bytes(const sea_temporal_desc* d, int training);
+int sea_temporal_refresh(const sea_temporal_desc* d, void* cache, size_t cache_bytes, int training,
+                         sea_stream_t stream);
+/* Activations / saved-for-backward tape live in a caller-owned workspace. */
+size_t sea_temporal_workspace_bytes(const sea_temporal_desc* d, int B, int T, int training);
+/* x [B,T,V,E] fp32 contiguous, ib [B,T,ib_num] fp32, y [B,T,V,E] fp32. */
+int sea_temporal_forward(const sea_temporal_desc* d, const void* cache, const float* x,
+                         const float* ib, float* y, int B, int T, void* workspace,
+                         size_t workspace_bytes, int training, sea_stream_t stream);
+/* Number of kernels the last forward / backward call on this thread launched. */
+int sea_last_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -124,3 +124,21 @@ if __name__ == "__main__":
     spatial_case("small", n_inp=16, hidden=48, layers=2, D=8, nh=8, B=3)
     spatial_case("cylinder_flow", n_inp=64, hidden=480, layers=12, D=16, nh=8, B=2)
     spatial_case("multiphase_flow", n_inp=64, hidden=624, layers=12, D=32, nh=8, B=2)
+
+
+def state_dict_manifest():
+    """Names/shapes/dtypes of the reference state_dict (checkpoint-compatibility contract)."""
+    import json
+    out = {}
+    for tag, (E, nh, scale, V, ln) in {"small_adaln": (128, 2, 2, 2, "adaln"), "small_ln": (128, 2, 2, 2, "ln"),
+                                       "small_v3": (128, 2, 2, 3, "ln")}.items():
+        m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln)
+        out["temporal_" + tag] = {k: [list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()}
+    m = SpatialModel([[0, 1], [2]], 16, 48, 2, 8, 8, 2024, 0, 0.0, False)
+    out["spatial_small"] = {k: [list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()}
+    with open(os.path.join(OUT, "state_dict_manifest.json"), "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+
+
+if __name__ == "__main__":
+    state_dict_manifest()

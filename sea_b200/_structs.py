@@ -1,0 +1,77 @@
+"""ctypes mirrors of the descriptor structs in include/sea_b200.h (temporal executor)."""
+from __future__ import annotations
+
+import ctypes as C
+
+MAX_STREAMS = 4
+
+
+class Param(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p)]
+
+
+class NormParams(C.Structure):
+    _fields_ = [("weight", Param), ("bias", Param), ("c0_w", Param), ("c0_b", Param),
+                ("c2_w", Param), ("c2_b", Param)]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [("q_w", Param), ("q_b", Param), ("k_w", Param), ("k_b", Param),
+                ("v_w", Param), ("v_b", Param), ("proj_w", Param)]
+
+
+class StreamParams(C.Structure):
+    _fields_ = [("ln0", NormParams), ("ln2", NormParams), ("ln_cross", NormParams),
+                ("self_attn", AttnParams), ("cross_attn", AttnParams * MAX_STREAMS),
+                ("down_w", Param), ("down_b", Param), ("up_w", Param), ("up_b", Param),
+                ("mlp0_w", Param), ("mlp0_b", Param), ("mlp_ln_w", Param), ("mlp_ln_b", Param),
+                ("mlp3_w", Param), ("mlp3_b", Param), ("proj_w", Param), ("proj_b", Param)]
+
+
+class BlockParams(C.Structure):
+    _fields_ = [("s", StreamParams * MAX_STREAMS),
+                ("ib0_w", Param), ("ib0_b", Param), ("ib_ln_w", Param), ("ib_ln_b", Param),
+                ("ib3_w", Param), ("ib3_b", Param)]
+
+
+class TemporalDesc(C.Structure):
+    _fields_ = [("num_layers", C.c_int32), ("num_streams", C.c_int32),
+                ("embed_dim", C.c_int32), ("n_heads", C.c_int32), ("hidden_dim", C.c_int32),
+                ("down_dim", C.c_int32), ("ib_num", C.c_int32), ("ib_hidden", C.c_int32),
+                ("norm_kind", C.c_int32), ("src_len", C.c_int32), ("max_len", C.c_int32),
+                ("precision", C.c_int32),
+                ("blocks", C.POINTER(BlockParams)),
+                ("final_ln", NormParams * MAX_STREAMS),
+                ("rope_self", C.c_void_p), ("rope_cross", C.c_void_p)]
+
+
+class NormArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ldx", C.c_int64), ("M", C.c_int32), ("d", C.c_int32),
+                ("kind", C.c_int32), ("weight", C.c_void_p), ("bias", C.c_void_p),
+                ("cond", C.c_void_p), ("ldc", C.c_int64), ("tipi_g", C.c_void_p),
+                ("tipi_hid", C.c_int32), ("tipi_w", C.c_void_p), ("tipi_b", C.c_void_p),
+                ("x_out", C.c_void_p), ("ldxo", C.c_int64), ("y_f32", C.c_void_p),
+                ("ldy_f32", C.c_int64), ("y_bf16", C.c_void_p), ("ldy_bf16", C.c_int64),
+                ("stats", C.c_void_p)]
+
+
+class LnGeluArgs(C.Structure):
+    _fields_ = [("h_bf16", C.c_void_p), ("h_f32", C.c_void_p), ("ldh", C.c_int64),
+                ("M", C.c_int32), ("H", C.c_int32), ("weight", C.c_void_p), ("bias", C.c_void_p),
+                ("g_bf16", C.c_void_p), ("g_f32", C.c_void_p), ("ldg", C.c_int64),
+                ("stats", C.c_void_p)]
+
+
+class PackArgs(C.Structure):
+    _fields_ = [("src_f32", C.c_void_p), ("src_bf16", C.c_void_p), ("ld", C.c_int64),
+                ("R", C.c_int32), ("C", C.c_int32), ("transpose", C.c_int32), ("split", C.c_int32),
+                ("act", C.c_int32), ("split_inner", C.c_int32), ("dst", C.c_void_p),
+                ("ld_dst", C.c_int64)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+                ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64),
+                ("o", C.c_void_p), ("ldo", C.c_int64), ("lse", C.c_void_p),
+                ("B", C.c_int32), ("T", C.c_int32), ("n_heads", C.c_int32), ("head_dim", C.c_int32),
+                ("src_len", C.c_int32), ("scale", C.c_float), ("prec", C.c_int32)]

@@ -1,0 +1,322 @@
+// K2 (tcgen05 variant) — fused causal attention forward, bf16 operands, fp32 softmax/accumulate.
+// One kernel serves self-attention (models/base_blocks.py:191-197) and the state-exchange
+// cross-attention (models/base_blocks.py:283-289): Q and K/V are independent tensor maps.
+//
+// CTA = one 128-query tile of one (batch, head); keys/values stream in tiles of BKV.
+//   warp 0      TMA: Q once, then K_j / V_j tiles into a 2-stage ring (128B-swizzled boxes of
+//               64 columns; 3-D tensor maps {col, t, b} so a tile never crosses a batch);
+//   warp 1      TMEM allocation + tcgen05.mma issue:
+//                 S = Q K_j^T          (SS: both operands K-major in smem, N = BKV)
+//                 O (+)= P V_j         (TS: P read from TMEM as packed bf16, V_j MN-major in smem)
+//   warps 2..5  online softmax, one query row per thread: tcgen05.ld S -> scale, causal mask
+//               (k <= q + src_len, no tril buffer), running max / sum in registers, exp2,
+//               P -> bf16 -> tcgen05.st; O is rescaled in TMEM only when the running max grew by
+//               more than 2^8 (lazy rescale); final O / l and log-sum-exp written from registers.
+// TMEM columns: S [0,BKV) | P [128,128+BKV/2) | O [256,256+HD).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/sea_b200.h"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace sea {
+namespace {
+
+constexpr int BQ = 128;
+constexpr int kThreads = 192;
+constexpr uint32_t kColS = 0, kColP = 128, kColO = 256;
+
+struct alignas(64) AttnTcParams {
+  CUtensorMap tq, tk, tv;
+  __nv_bfloat16* o;
+  long long ldo;
+  float* lse;
+  int B, T, n_heads, src_len;
+  float scale_log2;  // scale * log2(e)
+};
+
+template <int HD, int BKV>
+struct ACfg {
+  static constexpr int ATOMS = HD / 64;
+  static constexpr int Q_BYTES = BQ * HD * 2;
+  static constexpr int KV_BYTES = BKV * HD * 2;   // one of K or V
+  static constexpr int STAGES = 2;
+  static constexpr int SMEM = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 128;
+};
+
+template <int HD, int BKV>
+__global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  using C = ACfg<HD, BKV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + C::Q_BYTES;                        // [STAGES][KV_BYTES]
+  uint8_t* sV = sK + C::STAGES * C::KV_BYTES;           // [STAGES][KV_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::STAGES * C::KV_BYTES);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* kv_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;      // 1   MMA -> softmax
+  uint64_t* p_full = bars + 6;      // 1   softmax (128 arrivals) -> MMA
+  uint64_t* o_done = bars + 7;      // 1   MMA -> softmax
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;  // heavy (late) query tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * BQ;
+  const int q_hi = min(p.T - 1, q0 + BQ - 1);
+  const int k_last = min(p.T - 1, q_hi + p.src_len);
+  const int n_kv = k_last / BKV + 1;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&p.tq);
+    ptx::prefetch_tmap(&p.tk);
+    ptx::prefetch_tmap(&p.tv);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(o_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      ptx::mbar_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
+      for (int a = 0; a < C::ATOMS; ++a)
+        ptx::tma_load_3d(sQ + a * (BQ * 128), &p.tq, q_full, h * HD + a * 64, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        ptx::mbar_wait(&kv_empty[s], ph ^ 1);
+        ptx::mbar_expect_tx(&kv_full[s], 2 * C::KV_BYTES);
+#pragma unroll
+        for (int a = 0; a < C::ATOMS; ++a) {
+          ptx::tma_load_3d(sK + s * C::KV_BYTES + a * (BKV * 128), &p.tk, &kv_full[s], h * HD + a * 64, j * BKV, b);
+          ptx::tma_load_3d(sV + s * C::KV_BYTES + a * (BKV * 128), &p.tv, &kv_full[s], h * HD + a * 64, j * BKV, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
+    ptx::mbar_wait(q_full, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1;
+      ptx::mbar_wait(&kv_full[s], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t qb = ptx::smem_u32(sQ);
+        const uint32_t kb = ptx::smem_u32(sK + s * C::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t off = (k >> 2) * (BQ * 128) + (k & 3) * 32;
+          const uint32_t koff = (k >> 2) * (BKV * 128) + (k & 3) * 32;
+          ptx::umma_f16_ss(tmem + kColS, ptx::umma_smem_desc(qb + off, 16, 1024),
+                           ptx::umma_smem_desc(kb + koff, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(s_full);
+      }
+      __syncwarp();
+      ptx::mbar_wait(p_full, j & 1);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t vb = ptx::smem_u32(sV + s * C::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          // 16 keys per step = two 8-row groups (SBO 1024 B); 64-wide head-dim chunks LBO apart
+          const uint64_t vdesc = ptx::umma_smem_desc(vb + k * 2048, BKV * 128, 1024);
+          ptx::umma_f16_ts(tmem + kColO, tmem + kColP + k * 8, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&kv_empty[s]);
+        ptx::umma_commit(o_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warps
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int q = q0 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    float m_ref = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int kv0 = j * BKV;
+      ptx::mbar_wait(s_full, j & 1);
+      ptx::tc_fence_after();
+      const bool need_mask = (kv0 + BKV - 1 > q0 + p.src_len) || (kv0 + BKV > p.T);
+      // pass 1: row max of the scaled, masked scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem + lane_base + kColS + c * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float sv = __uint_as_float(r[e]) * p.scale_log2;
+          if (need_mask) {
+            const int kk = kv0 + c * 32 + e;
+            if (kk > q + p.src_len || kk >= p.T) sv = -INFINITY;
+          }
+          mx = fmaxf(mx, sv);
+        }
+      }
+      const float m_cand = fmaxf(m_ref, mx);
+      const bool grow = (m_cand > m_ref + 8.0f) || (m_ref == -INFINITY && m_cand != -INFINITY);
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      if (j > 0) {  // P and O are owned by the previous P·V until it retires
+        ptx::mbar_wait(o_done, (j - 1) & 1);
+        ptx::tc_fence_after();
+      }
+      if (any_grow) {
+        const float m_new = m_cand;
+        const float alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
+        l_sum *= alpha;
+        m_ref = m_new;
+        if (j > 0) {
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(tmem + lane_base + kColO + c * 32, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+            ptx::tmem_st_32x32(tmem + lane_base + kColO + c * 32, r);
+          }
+        }
+      }
+      // pass 2: p = exp2(s - m_ref), row sum, bf16 pack into TMEM
+      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem + lane_base + kColS + c * 32, r);
+        ptx::tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float s0 = __uint_as_float(r[e]) * p.scale_log2;
+          float s1 = __uint_as_float(r[e + 1]) * p.scale_log2;
+          if (need_mask) {
+            const int kk = kv0 + c * 32 + e;
+            if (kk > q + p.src_len || kk >= p.T) s0 = -INFINITY;
+            if (kk + 1 > q + p.src_len || kk + 1 >= p.T) s1 = -INFINITY;
+          }
+          const float p0 = exp2f(s0 - m_use);
+          const float p1 = exp2f(s1 - m_use);
+          l_sum += p0 + p1;
+          pk[e >> 1] = ptx::pack_bf16(p0, p1);
+        }
+        ptx::tmem_st_32x16(tmem + lane_base + kColP + c * 16, pk);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(p_full);
+    }
+    // epilogue: O / l  -> bf16, log-sum-exp
+    ptx::mbar_wait(o_done, (n_kv - 1) & 1);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l_sum;
+    __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.T + q) * p.ldo + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem + lane_base + kColO + c * 32, r);
+      ptx::tmem_ld_wait();
+      if (q < p.T) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 o;
+          o.x = ptx::pack_bf16(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+          o.y = ptx::pack_bf16(__uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv);
+          o.z = ptx::pack_bf16(__uint_as_float(r[e + 4]) * inv, __uint_as_float(r[e + 5]) * inv);
+          o.w = ptx::pack_bf16(__uint_as_float(r[e + 6]) * inv, __uint_as_float(r[e + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + e) = o;
+        }
+      }
+    }
+    if (p.lse != nullptr && q < p.T)
+      p.lse[(static_cast<long long>(b) * p.n_heads + h) * p.T + q] =
+          (m_ref + log2f(l_sum)) * 0.69314718055994530942f;
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int HD, int BKV>
+int launch_tc(const sea_attn_args* a, cudaStream_t s) {
+  using C = ACfg<HD, BKV>;
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    SEA_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, BKV>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set[dev] = true;
+  }
+  AttnTcParams p;
+  const uint64_t wq = static_cast<uint64_t>(a->n_heads) * HD;
+  int rc = make_tmap_bf16_3d(&p.tq, a->q, wq, a->T, a->B, a->ldq, a->ldq * static_cast<uint64_t>(a->T), 64, BQ);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&p.tk, a->k, wq, a->T, a->B, a->ldk, a->ldk * static_cast<uint64_t>(a->T), 64, BKV);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&p.tv, a->v, wq, a->T, a->B, a->ldv, a->ldv * static_cast<uint64_t>(a->T), 64, BKV);
+  if (rc) return rc;
+  p.o = static_cast<__nv_bfloat16*>(a->o);
+  p.ldo = a->ldo;
+  p.lse = a->lse;
+  p.B = a->B; p.T = a->T; p.n_heads = a->n_heads; p.src_len = a->src_len;
+  p.scale_log2 = a->scale * 1.44269504088896340736f;
+  dim3 grid((a->T + BQ - 1) / BQ, a->n_heads, a->B);
+  attn_fwd_tc_kernel<HD, BKV><<<grid, kThreads, C::SMEM, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+bool attention_tc_supported(const sea_attn_args* a) {
+  if (a->prec != SEA_PREC_BF16) return false;
+  if (a->head_dim != 64 && a->head_dim != 128 && a->head_dim != 256) return false;
+  if (a->src_len < 0) return false;
+  // TMA: 16-byte aligned bases and row pitches
+  if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8)) return false;
+  if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
+       reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->o)) & 15)
+    return false;
+  return true;
+}
+
+int attention_fwd_tc(const sea_attn_args* a, cudaStream_t s) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  switch (a->head_dim) {
+    case 64: return launch_tc<64, 128>(a, s);
+    case 128: return launch_tc<128, 128>(a, s);
+    case 256: return launch_tc<256, 64>(a, s);
+    default: return SEA_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace sea

@@ -1,0 +1,464 @@
+// K4/K5/K6 + operand packing — the HBM-bound kernels of the temporal path.
+// All are one pass over their tensors (each element read once, written once), 16-byte vector
+// accesses, fp32 statistics with warp-shuffle / block reductions.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/sea_b200.h"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace sea {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// ------------------------------------------------------------------ AdaLN cond hidden layer
+// h[m, j] = SiLU(sum_c w1[j, c] * ib[m, c] + b1[j])     models/base_blocks.py:337-339, 344
+__global__ void adaln_hidden_kernel(const float* __restrict__ ib, int M, int ib_num,
+                                    const float* __restrict__ w1, const float* __restrict__ b1,
+                                    int n, __nv_bfloat16* __restrict__ out_bf16,
+                                    float* __restrict__ out_f32) {
+  const long long total = static_cast<long long>(M) * (n / 2);
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(idx / (n / 2));
+    const int j = static_cast<int>(idx - static_cast<long long>(m) * (n / 2)) * 2;
+    float a0 = b1[j], a1 = b1[j + 1];
+    for (int c = 0; c < ib_num; ++c) {
+      const float v = ib[static_cast<long long>(m) * ib_num + c];
+      a0 = fmaf(w1[j * ib_num + c], v, a0);
+      a1 = fmaf(w1[(j + 1) * ib_num + c], v, a1);
+    }
+    a0 = silu(a0);
+    a1 = silu(a1);
+    if (out_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + static_cast<long long>(m) * n + j) = ptx::pack_bf16(a0, a1);
+    if (out_f32) *reinterpret_cast<float2*>(out_f32 + static_cast<long long>(m) * n + j) = make_float2(a0, a1);
+  }
+}
+
+// ------------------------------------------------------------------------- TIPI hidden layer
+// g[m, :] = GELU(LayerNorm_hid(W0 ib[m] + b0))     models/base_blocks.py:22-25 (MLP(ib_num, ...))
+// Also stores the pre-LN values and (mean, rstd) when asked (backward).
+constexpr int kMaxTipiHid = 64;
+__global__ void tipi_hidden_kernel(const float* __restrict__ ib, int M, int ib_num,
+                                   const float* __restrict__ w0, const float* __restrict__ b0,
+                                   const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                   int hid, float* __restrict__ g_out, float* __restrict__ pre_out,
+                                   float* __restrict__ stats_out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float u[kMaxTipiHid];
+  float mean = 0.f;
+  for (int k = 0; k < hid; ++k) {
+    float a = b0[k];
+    for (int c = 0; c < ib_num; ++c) a = fmaf(w0[k * ib_num + c], ib[static_cast<long long>(m) * ib_num + c], a);
+    u[k] = a;
+    mean += a;
+  }
+  mean /= hid;
+  float var = 0.f;
+  for (int k = 0; k < hid; ++k) var += (u[k] - mean) * (u[k] - mean);
+  const float rstd = rsqrtf(var / hid + 1e-5f);
+  for (int k = 0; k < hid; ++k) {
+    const float n = (u[k] - mean) * rstd * ln_w[k] + ln_b[k];
+    g_out[static_cast<long long>(m) * hid + k] = ptx::gelu_erf(n);
+    if (pre_out) pre_out[static_cast<long long>(m) * hid + k] = n;
+  }
+  if (stats_out) {
+    stats_out[2 * m] = mean;
+    stats_out[2 * m + 1] = rstd;
+  }
+}
+
+// ------------------------------------------------------------------ row norm (LN / AdaLN)
+// One warp per row, the row lives in registers (d <= 2048).  Optional fused TIPI add before
+// the norm (models/temporal.py:140-145): x' = x + W3 g[m] + b3, written back, then normalised.
+struct NormDev {
+  const float* x; long long ldx;
+  int M, d, kind;
+  const float* weight; const float* bias;
+  const float* cond; long long ldc;
+  const float* tipi_g; int tipi_hid; const float* tipi_w; const float* tipi_b;
+  float* x_out; long long ldxo;
+  float* y_f32; long long ldy_f32;
+  __nv_bfloat16* y_bf16; long long ldy_bf16;
+  float* stats;
+};
+
+constexpr int kNormMaxChunks = 16;  // 16 chunks x 32 lanes x 4 floats = 2048
+
+__global__ void __launch_bounds__(256) norm_fwd_kernel(const NormDev a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (m >= a.M) return;
+  const float* xr = a.x + static_cast<long long>(m) * a.ldx;
+  float4 v[kNormMaxChunks];
+  float sum = 0.f;
+  float gk[8];
+  if (a.tipi_g) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gk[k] = (k < a.tipi_hid) ? a.tipi_g[static_cast<long long>(m) * a.tipi_hid + k] : 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c) {
+    const int col = c * 128 + lane * 4;
+    if (col < a.d) {
+      float4 t = *reinterpret_cast<const float4*>(xr + col);
+      if (a.tipi_g) {
+        float add[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float s = a.tipi_b[col + e];
+          if (a.tipi_hid == 8) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.tipi_w + (col + e) * 8));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.tipi_w + (col + e) * 8 + 4));
+            s += w0.x * gk[0] + w0.y * gk[1] + w0.z * gk[2] + w0.w * gk[3] + w1.x * gk[4] +
+                 w1.y * gk[5] + w1.z * gk[6] + w1.w * gk[7];
+          } else {
+            for (int k = 0; k < a.tipi_hid; ++k)
+              s = fmaf(a.tipi_w[(col + e) * a.tipi_hid + k],
+                       a.tipi_g[static_cast<long long>(m) * a.tipi_hid + k], s);
+          }
+          add[e] = s;
+        }
+        t.x += add[0]; t.y += add[1]; t.z += add[2]; t.w += add[3];
+        *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(m) * a.ldxo + col) = t;
+      }
+      v[c] = t;
+      sum += t.x + t.y + t.z + t.w;
+    }
+  }
+  const float mean = warp_sum(sum) / a.d;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c) {
+    const int col = c * 128 + lane * 4;
+    if (col < a.d) {
+      const float dx = v[c].x - mean, dy = v[c].y - mean, dz = v[c].z - mean, dw = v[c].w - mean;
+      sq += dx * dx + dy * dy + dz * dz + dw * dw;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / a.d + 1e-5f);
+  if (a.stats && lane == 0) {
+    a.stats[2 * m] = mean;
+    a.stats[2 * m + 1] = rstd;
+  }
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c) {
+    const int col = c * 128 + lane * 4;
+    if (col < a.d) {
+      float4 w = __ldg(reinterpret_cast<const float4*>(a.weight + col));
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.bias) b = __ldg(reinterpret_cast<const float4*>(a.bias + col));
+      if (a.kind == SEA_NORM_ADALN) {
+        // gamma = weight + (w_cond + 1), beta = bias + b_cond   (models/base_blocks.py:345-350)
+        const float* cr = a.cond + static_cast<long long>(m) * a.ldc;
+        const float4 cw = *reinterpret_cast<const float4*>(cr + col);
+        const float4 cb = *reinterpret_cast<const float4*>(cr + a.d + col);
+        w.x += cw.x + 1.f; w.y += cw.y + 1.f; w.z += cw.z + 1.f; w.w += cw.w + 1.f;
+        b.x += cb.x; b.y += cb.y; b.z += cb.z; b.w += cb.w;
+      }
+      float4 y;
+      y.x = (v[c].x - mean) * rstd * w.x + b.x;
+      y.y = (v[c].y - mean) * rstd * w.y + b.y;
+      y.z = (v[c].z - mean) * rstd * w.z + b.z;
+      y.w = (v[c].w - mean) * rstd * w.w + b.w;
+      if (a.y_f32) *reinterpret_cast<float4*>(a.y_f32 + static_cast<long long>(m) * a.ldy_f32 + col) = y;
+      if (a.y_bf16) {
+        uint2 o;
+        o.x = ptx::pack_bf16(y.x, y.y);
+        o.y = ptx::pack_bf16(y.z, y.w);
+        *reinterpret_cast<uint2*>(a.y_bf16 + static_cast<long long>(m) * a.ldy_bf16 + col) = o;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------- MLP inner LayerNorm(H) + GELU (K6)
+// One CTA per row; each thread keeps <= 64 values of the row in registers.
+// models/base_blocks.py:23-25 (nn.LayerNorm(scaled_dim) with affine weight+bias, then nn.GELU()).
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) ln_gelu_fwd_kernel(const TIn* __restrict__ h, long long ldh,
+                                                          int M, int H,
+                                                          const float* __restrict__ weight,
+                                                          const float* __restrict__ bias,
+                                                          TOut* __restrict__ g, long long ldg,
+                                                          float* __restrict__ stats) {
+  constexpr int kMaxChunks = 8;  // 8 chunks x 256 threads x 8 elements = 16384
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const int m = blockIdx.x;
+  const int tid = threadIdx.x;
+  const TIn* hr = h + static_cast<long long>(m) * ldh;
+  float v[kMaxChunks][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (c * 256 + tid) * 8;
+    if (col < H) {
+      if constexpr (sizeof(TIn) == 2) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(hr + col);
+        const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(p[q]);
+          v[c][2 * q] = f.x;
+          v[c][2 * q + 1] = f.y;
+        }
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(hr + col);
+        const float4 b = *reinterpret_cast<const float4*>(hr + col + 4);
+        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+        v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[c][e];
+    }
+  }
+  auto block_sum = [&](float x) -> float {
+    x = warp_sum(x);
+    if ((tid & 31) == 0) red[tid >> 5] = x;
+    __syncthreads();
+    if (tid < 32) {
+      float t = (tid < 8) ? red[tid] : 0.f;
+      t = warp_sum(t);
+      if (tid == 0) bcast = t;
+    }
+    __syncthreads();
+    const float r = bcast;
+    __syncthreads();
+    return r;
+  };
+  const float mean = block_sum(sum) / H;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (c * 256 + tid) * 8;
+    if (col < H) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sq += (v[c][e] - mean) * (v[c][e] - mean);
+    }
+  }
+  const float rstd = rsqrtf(block_sum(sq) / H + 1e-5f);
+  if (stats && tid == 0) {
+    stats[2 * m] = mean;
+    stats[2 * m + 1] = rstd;
+  }
+  TOut* gr = g + static_cast<long long>(m) * ldg;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (c * 256 + tid) * 8;
+    if (col < H) {
+      float y[8];
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = ptx::gelu_erf((v[c][e] - mean) * rstd * ww[e] + bb[e]);
+      if constexpr (sizeof(TOut) == 2) {
+        uint4 o;
+        o.x = ptx::pack_bf16(y[0], y[1]);
+        o.y = ptx::pack_bf16(y[2], y[3]);
+        o.z = ptx::pack_bf16(y[4], y[5]);
+        o.w = ptx::pack_bf16(y[6], y[7]);
+        *reinterpret_cast<uint4*>(gr + col) = o;
+      } else {
+        *reinterpret_cast<float4*>(gr + col) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(gr + col + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- operand packing
+// src [R, C] (fp32 or bf16, pitch ld) -> bf16 dst, plain or transposed, optionally as the
+// 3-way bf16 split used for fp32-accurate products on the bf16 tensor cores:
+//   x = x1 + x2 + x3 (x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2));
+//   A-side pattern along K: [x3 x2 x1 x2 x1 x1], B-side: [y1 y2 y3 y1 y2 y1]  (6 products, all
+//   terms down to 2^-24 relative; the dropped x2*y3, x3*y2, x3*y3 are below fp32 epsilon).
+// dst has (transpose ? C : R) rows of (split ? 6 : 1) * (transpose ? R : C) columns.
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& p1, __nv_bfloat16& p2, __nv_bfloat16& p3) {
+  p1 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(p1);
+  p2 = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(p2);
+  p3 = __float2bfloat16_rn(r2);
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) pack_kernel(const TIn* __restrict__ src, long long ld, int R,
+                                                   int C, int transpose, int split, int act, int split_inner,
+                                                   __nv_bfloat16* __restrict__ dst, long long ldd) {
+  // 32x32 tile through shared memory so both the read and the (possibly transposed) write are
+  // coalesced.
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < C) {
+      if constexpr (sizeof(TIn) == 2) v = __bfloat162float(src[static_cast<long long>(r) * ld + c]);
+      else v = src[static_cast<long long>(r) * ld + c];
+      if (act == SEA_ACT_GELU) v = ptx::gelu_erf(v);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  const int inner = split_inner > 0 ? split_inner : (transpose ? R : C);  // segment pitch
+  for (int i = ty; i < 32; i += 8) {
+    int orow, ocol;
+    float v;
+    if (transpose) {
+      orow = c0 + i; ocol = r0 + tx; v = tile[tx][i];
+      if (orow >= C || ocol >= R) continue;
+    } else {
+      orow = r0 + i; ocol = c0 + tx; v = tile[i][tx];
+      if (orow >= R || ocol >= C) continue;
+    }
+    __nv_bfloat16* drow = dst + static_cast<long long>(orow) * ldd;
+    if (split == 0) {
+      drow[ocol] = __float2bfloat16_rn(v);
+    } else {
+      __nv_bfloat16 p1, p2, p3;
+      split3(v, p1, p2, p3);
+      if (split == 1) {  // A pattern  (smallest products first, x1*y1 last)
+        drow[ocol] = p3; drow[inner + ocol] = p2; drow[2 * inner + ocol] = p1;
+        drow[3 * inner + ocol] = p2; drow[4 * inner + ocol] = p1; drow[5 * inner + ocol] = p1;
+      } else {           // B pattern
+        drow[ocol] = p1; drow[inner + ocol] = p2; drow[2 * inner + ocol] = p3;
+        drow[3 * inner + ocol] = p1; drow[4 * inner + ocol] = p2; drow[5 * inner + ocol] = p1;
+      }
+    }
+  }
+}
+
+// out[n] = sum_m src[m, n] (bias gradients).  One warp per 32 columns x row-slab, atomics into out.
+__global__ void colsum_kernel(const float* __restrict__ src_f32, const __nv_bfloat16* __restrict__ src_bf16,
+                              long long ld, int M, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r_begin = blockIdx.y * rows_per;
+  const int r_end = min(M, r_begin + rows_per);
+  float acc = 0.f;
+  if (n < N) {
+    for (int r = r_begin + (threadIdx.x >> 5); r < r_end; r += (blockDim.x >> 5)) {
+      acc += src_f32 ? src_f32[static_cast<long long>(r) * ld + n]
+                     : __bfloat162float(src_bf16[static_cast<long long>(r) * ld + n]);
+    }
+  }
+  __shared__ float red[8][32];
+  red[threadIdx.x >> 5][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32 && n < N) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + n, t);
+  }
+}
+
+}  // namespace
+}  // namespace sea
+
+using namespace sea;
+
+extern "C" int sea_adaln_hidden(const float* ib, int M, int ib_num, const float* w1, const float* b1,
+                                int n, void* out_bf16, float* out_f32, sea_stream_t stream) {
+  if (!ib || !w1 || !b1 || M <= 0 || n <= 0 || (n % 2) || ib_num <= 0) return SEA_ERR_INVALID;
+  if (!out_bf16 && !out_f32) return SEA_ERR_INVALID;
+  const long long total = static_cast<long long>(M) * (n / 2);
+  long long nblk = (total + 255) / 256;
+  if (nblk > 148LL * 16) nblk = 148LL * 16;
+  const int grid = static_cast<int>(nblk);
+  adaln_hidden_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      ib, M, ib_num, w1, b1, n, static_cast<__nv_bfloat16*>(out_bf16), out_f32);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_tipi_hidden(const float* ib, int M, int ib_num, const float* w0, const float* b0,
+                               const float* ln_w, const float* ln_b, int hid, float* g_out,
+                               float* pre_out, float* stats_out, sea_stream_t stream) {
+  if (!ib || !w0 || !b0 || !ln_w || !ln_b || !g_out || M <= 0 || ib_num <= 0) return SEA_ERR_INVALID;
+  if (hid <= 0 || hid > kMaxTipiHid) return SEA_ERR_UNSUPPORTED;
+  tipi_hidden_kernel<<<(M + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      ib, M, ib_num, w0, b0, ln_w, ln_b, hid, g_out, pre_out, stats_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_norm_fwd(const sea_norm_args* a, sea_stream_t stream) {
+  if (!a || !a->x || !a->weight || a->M <= 0 || a->d <= 0) return SEA_ERR_INVALID;
+  if ((a->d % 4) || a->d > kNormMaxChunks * 128) return SEA_ERR_UNSUPPORTED;
+  if (!a->y_f32 && !a->y_bf16) return SEA_ERR_INVALID;
+  if (a->kind == SEA_NORM_ADALN && !a->cond) return SEA_ERR_INVALID;
+  if ((a->ldx % 4) || (a->y_f32 && (a->ldy_f32 % 4)) || (a->y_bf16 && (a->ldy_bf16 % 4)) ||
+      (a->cond && (a->ldc % 4)))
+    return SEA_ERR_INVALID;
+  if (a->tipi_g && (!a->tipi_w || !a->tipi_b || !a->x_out || a->tipi_hid <= 0 || (a->ldxo % 4)))
+    return SEA_ERR_INVALID;
+  NormDev d;
+  d.x = a->x; d.ldx = a->ldx; d.M = a->M; d.d = a->d; d.kind = a->kind;
+  d.weight = a->weight; d.bias = a->bias; d.cond = a->cond; d.ldc = a->ldc;
+  d.tipi_g = a->tipi_g; d.tipi_hid = a->tipi_hid; d.tipi_w = a->tipi_w; d.tipi_b = a->tipi_b;
+  d.x_out = a->x_out; d.ldxo = a->ldxo;
+  d.y_f32 = a->y_f32; d.ldy_f32 = a->ldy_f32;
+  d.y_bf16 = static_cast<__nv_bfloat16*>(a->y_bf16); d.ldy_bf16 = a->ldy_bf16;
+  d.stats = a->stats;
+  const int rows_per_cta = 8;
+  norm_fwd_kernel<<<(a->M + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0,
+                    reinterpret_cast<cudaStream_t>(stream)>>>(d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_ln_gelu_fwd(const sea_ln_gelu_args* a, sea_stream_t stream) {
+  if (!a || a->M <= 0 || a->H <= 0 || !a->weight || !a->bias) return SEA_ERR_INVALID;
+  if ((a->H % 8) || a->H > 16384 || (a->ldh % 8) || (a->ldg % 8)) return SEA_ERR_UNSUPPORTED;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->h_bf16 && a->g_bf16) {
+    ln_gelu_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<a->M, 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(a->h_bf16), a->ldh, a->M, a->H, a->weight, a->bias,
+        static_cast<__nv_bfloat16*>(a->g_bf16), a->ldg, a->stats);
+  } else if (a->h_f32 && a->g_f32) {
+    ln_gelu_fwd_kernel<float, float><<<a->M, 256, 0, s>>>(a->h_f32, a->ldh, a->M, a->H, a->weight,
+                                                          a->bias, a->g_f32, a->ldg, a->stats);
+  } else {
+    return SEA_ERR_INVALID;
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_pack_operand(const sea_pack_args* a, sea_stream_t stream) {
+  if (!a || !a->dst || a->R <= 0 || a->C <= 0 || (!a->src_f32 && !a->src_bf16)) return SEA_ERR_INVALID;
+  if (a->split < 0 || a->split > 2) return SEA_ERR_INVALID;
+  dim3 grid((a->C + 31) / 32, (a->R + 31) / 32);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->src_f32)
+    pack_kernel<float><<<grid, 256, 0, s>>>(a->src_f32, a->ld, a->R, a->C, a->transpose, a->split,
+                                            a->act, a->split_inner, static_cast<__nv_bfloat16*>(a->dst), a->ld_dst);
+  else
+    pack_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(a->src_bf16),
+                                                    a->ld, a->R, a->C, a->transpose, a->split, a->act, a->split_inner,
+                                                    static_cast<__nv_bfloat16*>(a->dst), a->ld_dst);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_colsum_accumulate(const float* src_f32, const void* src_bf16, int64_t ld, int M,
+                                     int N, float* out, sea_stream_t stream) {
+  if ((!src_f32 && !src_bf16) || !out || M <= 0 || N <= 0) return SEA_ERR_INVALID;
+  int slabs = M / 64;
+  if (slabs < 1) slabs = 1;
+  if (slabs > 64) slabs = 64;
+  dim3 grid((N + 31) / 32, slabs);
+  colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src_f32, static_cast<const __nv_bfloat16*>(src_bf16), ld, M, N, out);
+  return static_cast<int>(cudaGetLastError());
+}

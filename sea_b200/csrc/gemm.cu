@@ -51,6 +51,7 @@ struct alignas(64) GemmParams {
   DevEpilogue epi[kMaxGroups];
   int M, N, K;
   int groups, tiles_m, tiles_n;
+  int chunk_kb;  // k-blocks per accumulation chunk (== num_kb when not chunked)
 };
 
 template <int BN>
@@ -63,7 +64,7 @@ struct Cfg {
 };
 
 __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint32_t (&r)[32],
-                                               int m, int n0, int M, int N) {
+                                               int m, int n0, int M, int N, bool first, bool last) {
   // One thread = one output row m, 32 consecutive columns starting at n0.
   if (m >= M || n0 >= N) return;
   float v[32];
@@ -71,7 +72,48 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   const int nvalid = min(32, N - n0);  // multiple of 8 (N % 8 == 0 is enforced on the host)
 
-  if (e.bias != nullptr) {
+  if (!first) {
+    // chunked accumulation (fp32-parity mode): this thread wrote the running sum itself
+    const float* ap = e.out_f32 + static_cast<long long>(m) * e.ld_out_f32 + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < nvalid) {
+        const float4 b = *reinterpret_cast<const float4*>(ap + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+  }
+  if (!last) {
+    if (first) {
+      if (e.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < nvalid) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+      }
+      if (e.residual != nullptr) {
+        const float* rp = e.residual + static_cast<long long>(m) * e.ld_residual + n0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < nvalid) {
+            const float4 b = *reinterpret_cast<const float4*>(rp + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+      }
+    }
+    float* op = e.out_f32 + static_cast<long long>(m) * e.ld_out_f32 + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < nvalid) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    return;
+  }
+
+  if (first && e.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       if (j < nvalid) {
@@ -80,7 +122,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
       }
     }
   }
-  if (e.residual != nullptr) {
+  if (first && e.residual != nullptr) {
     const float* rp = e.residual + static_cast<long long>(m) * e.ld_residual + n0;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -233,29 +275,32 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(&full[stage], phase);
+      for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
+        const int kb1 = min(num_kb, kb0 + p.chunk_kb);
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_base = ptx::smem_u32(smem_a + stage * A_BYTES);
-          const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::B_BYTES);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_base = ptx::smem_u32(smem_a + stage * A_BYTES);
+            const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = ptx::umma_smem_desc(a_base + k * 32, 16, 1024);
-            const uint64_t bdesc = ptx::umma_smem_desc(b_base + k * 32, 16, 1024);
-            ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adesc = ptx::umma_smem_desc(a_base + k * 32, 16, 1024);
+              const uint64_t bdesc = ptx::umma_smem_desc(b_base + k * 32, 16, 1024);
+              ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+            }
+            ptx::umma_commit(&empty[stage]);
+            if (kb == kb1 - 1) ptx::umma_commit(&tfull[acc]);
           }
-          ptx::umma_commit(&empty[stage]);
-          if (kb == num_kb - 1) ptx::umma_commit(&tfull[acc]);
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // --------------------------------------------------------------- epilogue
@@ -268,23 +313,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       const int tm = r % p.tiles_m;
       const int tn = r / p.tiles_m;
       const DevEpilogue& e = p.epi[g];
-      ptx::mbar_wait(&tfull[acc], acc_phase);
-      ptx::tc_fence_after();
       const int m = tm * BM + quarter * 32 + lane;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(acc * BN);
+      for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
+        const bool first = kb0 == 0, last = kb0 + p.chunk_kb >= num_kb;
+        ptx::mbar_wait(&tfull[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t regs[32];
-        ptx::tmem_ld_32x32(t_row + c * 32, regs);
-        ptx::tmem_ld_wait();
-        epilogue_chunk(e, regs, m, tn * BN + c * 32, p.M, p.N);
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t regs[32];
+          ptx::tmem_ld_32x32(t_row + c * 32, regs);
+          ptx::tmem_ld_wait();
+          epilogue_chunk(e, regs, m, tn * BN + c * 32, p.M, p.N, first, last);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
@@ -338,7 +386,13 @@ extern "C" void sea_gemm_force_tile_n(int bn) { sea::g_force_bn = bn; }
 
 extern "C" int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* probs, int M, int N,
                                 int K, sea_stream_t stream) {
+  return sea_gemm_bf16_tn_chunked(num_problems, probs, M, N, K, 0, stream);
+}
+
+extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem* probs, int M,
+                                        int N, int K, int k_chunk, sea_stream_t stream) {
   using namespace sea;
+  if (k_chunk < 0 || (k_chunk % BK) != 0) return SEA_ERR_INVALID;
   if (probs == nullptr || num_problems < 1 || num_problems > kMaxGroups) return SEA_ERR_INVALID;
   if (M <= 0 || N <= 0 || K <= 0) return SEA_ERR_INVALID;
   if ((N % 8) != 0 || (K % 8) != 0) return SEA_ERR_UNSUPPORTED;
@@ -362,6 +416,8 @@ extern "C" int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* probs,
   p.groups = num_problems;
   p.tiles_m = (M + BM - 1) / BM;
   p.tiles_n = (N + bn - 1) / bn;
+  p.chunk_kb = (k_chunk > 0 && k_chunk < K) ? k_chunk / BK : (K + BK - 1) / BK;
+  const bool chunked = p.chunk_kb < (K + BK - 1) / BK;
   for (int g = 0; g < num_problems; ++g) {
     const sea_gemm_problem& q = probs[g];
     const sea_gemm_epilogue& e = q.epi;
@@ -371,6 +427,7 @@ extern "C" int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* probs,
       return SEA_ERR_INVALID;
     if (e.out_f32 == nullptr && e.out_bf16 == nullptr && e.out_pre_bf16 == nullptr)
       return SEA_ERR_INVALID;
+    if (chunked && (e.out_f32 == nullptr || e.out_f32 == e.residual)) return SEA_ERR_INVALID;
     if (e.out_f32 && ((e.ld_out_f32 % 4) || (reinterpret_cast<uintptr_t>(e.out_f32) & 15)))
       return SEA_ERR_INVALID;
     if (e.out_bf16 && ((e.ld_out_bf16 % 8) || (reinterpret_cast<uintptr_t>(e.out_bf16) & 15)))

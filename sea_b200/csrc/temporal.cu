@@ -1,0 +1,576 @@
+// Whole-model executor for the temporal transformer (host-side orchestration, C++).
+//
+// One call = the complete TemporalModel.forward of the reference (models/temporal.py:405-416):
+// every kernel of the pass is enqueued on the caller's stream from here, so the Python side
+// makes ONE FFI call per forward (and the sequence is CUDA-graph capturable: no allocation, no
+// host sync, descriptors built on the host and passed by value).
+//
+// Data layout in HBM
+//   weights   fp32 masters stay where torch put them; bf16 (or 3-way-split bf16) packed copies,
+//             with q|k|v and k|v fused along N, live in the caller-owned `cache`;
+//   residual  stream x_i is fp32 [M, E] (M = B*T) throughout (bf16 budget: SURVEY.md hard part 2);
+//   operands  every GEMM A-operand is written in bf16 by the kernel that produces it
+//             (norm / attention / GEMM epilogue), never re-read in fp32;
+//   tape      all intermediates sit at fixed offsets of the caller-owned `workspace`, which is
+//             also what the backward pass reads.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/sea_b200.h"
+#include "internal.h"
+#include "temporal_internal.h"
+
+namespace sea {
+
+thread_local int g_launches = 0;
+
+// ------------------------------------------------------------------------------ cache layout
+static PackedLinear take_linear(Arena& ar, int N, int K, int kf, bool training) {
+  PackedLinear p{};
+  p.N = N; p.K = K;
+  p.wT = nullptr; p.ldwT = 0;
+  p.ldw = static_cast<long long>(kf) * K;
+  p.w = static_cast<bf16*>(ar.take(sizeof(bf16) * N * p.ldw));
+  if (training) {
+    p.ldwT = static_cast<long long>(kf) * N;
+    p.wT = static_cast<bf16*>(ar.take(sizeof(bf16) * K * p.ldwT));
+  }
+  return p;
+}
+
+void layout_cache(const sea_temporal_desc* d, bool training, Arena& ar, CacheLayout& c) {
+  const int kf = d->precision == SEA_PREC_FP32 ? 6 : 1;
+  const int E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim, V = d->num_streams;
+  const bool ada = d->norm_kind == SEA_NORM_ADALN;
+  c.blocks.assign(d->num_layers, BlockCache{});
+  for (int l = 0; l < d->num_layers; ++l) {
+    for (int i = 0; i < V; ++i) {
+      StreamCache& s = c.blocks[l].s[i];
+      s.qkv = take_linear(ar, 3 * E, E, kf, training);
+      s.qkv_bias = static_cast<float*>(ar.take(sizeof(float) * 3 * E));
+      s.sproj = take_linear(ar, E, E, kf, training);
+      s.down = take_linear(ar, Dd, E, kf, training);
+      s.up = take_linear(ar, E, Dd, kf, training);
+      s.mlp0 = take_linear(ar, H, E, kf, training);
+      s.mlp3 = take_linear(ar, E, H, kf, training);
+      s.proj = take_linear(ar, E, E, kf, training);
+      for (int j = 0; j < V; ++j) {
+        if (j == i) continue;
+        s.cq[j] = take_linear(ar, Dd, Dd, kf, training);
+        s.ckv[j] = take_linear(ar, 2 * Dd, Dd, kf, training);
+        s.ckv_bias[j] = static_cast<float*>(ar.take(sizeof(float) * 2 * Dd));
+        s.cproj[j] = take_linear(ar, Dd, Dd, kf, training);
+      }
+      if (ada) {
+        s.c2_ln0 = take_linear(ar, 2 * E, 2 * E, kf, training);
+        s.c2_ln2 = take_linear(ar, 2 * E, 2 * E, kf, training);
+        s.c2_lnc = take_linear(ar, 2 * Dd, 2 * Dd, kf, training);
+      }
+    }
+  }
+  for (int i = 0; i < V; ++i)
+    if (ada) c.c2_final[i] = take_linear(ar, 2 * E, 2 * E, kf, training);
+}
+
+static int pack_weight(const float* src, int N, int K, const PackedLinear& dst, int row_off,
+                       int n_total, bool fp32, cudaStream_t s) {
+  // rows [row_off, row_off+N) of the (possibly fused) packed matrix
+  sea_pack_args a{};
+  a.src_f32 = src; a.ld = K; a.R = N; a.C = K;
+  a.split = fp32 ? 2 : 0;
+  a.dst = const_cast<bf16*>(dst.w) + static_cast<long long>(row_off) * dst.ldw;
+  a.ld_dst = dst.ldw;
+  int rc = sea_pack_operand(&a, reinterpret_cast<sea_stream_t>(s));
+  if (rc) return rc;
+  ++g_launches;
+  if (dst.wT) {
+    a.transpose = 1;
+    a.split_inner = n_total;
+    a.dst = const_cast<bf16*>(dst.wT) + row_off;
+    a.ld_dst = dst.ldwT;
+    rc = sea_pack_operand(&a, reinterpret_cast<sea_stream_t>(s));
+    ++g_launches;
+  }
+  return rc;
+}
+
+#define SEA_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != SEA_OK) return _rc; \
+  } while (0)
+
+static int refresh_norm(const sea_norm_params& n, const PackedLinear& c2, int d2, bool fp32,
+                        cudaStream_t s) {
+  return pack_weight(n.c2_w.p, d2, d2, c2, 0, d2, fp32, s);
+}
+
+}  // namespace sea
+
+using namespace sea;
+
+extern "C" int sea_last_launch_count(void) { return g_launches; }
+
+extern "C" size_t sea_temporal_cache_bytes(const sea_temporal_desc* d, int training) {
+  if (!d) return 0;
+  Arena ar{nullptr};
+  CacheLayout c;
+  layout_cache(d, training != 0, ar, c);
+  return ar.off + 256;
+}
+
+static int validate_desc(const sea_temporal_desc* d) {
+  if (!d || !d->blocks) return SEA_ERR_INVALID;
+  if (d->num_layers < 1 || d->num_streams < 1 || d->num_streams > SEA_MAX_STREAMS) return SEA_ERR_UNSUPPORTED;
+  if (d->n_heads < 1 || d->embed_dim % d->n_heads || d->down_dim % d->n_heads) return SEA_ERR_UNSUPPORTED;
+  const int hd = d->embed_dim / d->n_heads, hdc = d->down_dim / d->n_heads;
+  if (hd % 32 || hdc % 32 || hd > 256) return SEA_ERR_UNSUPPORTED;
+  if (d->embed_dim > 2048 || d->hidden_dim > 16384 || d->hidden_dim % 8) return SEA_ERR_UNSUPPORTED;
+  if (d->ib_hidden < 1 || d->ib_hidden > 64 || d->ib_num < 1) return SEA_ERR_UNSUPPORTED;
+  if (!d->rope_self || !d->rope_cross) return SEA_ERR_INVALID;
+  return SEA_OK;
+}
+
+extern "C" int sea_temporal_refresh(const sea_temporal_desc* d, void* cache, size_t cache_bytes,
+                                    int training, sea_stream_t stream) {
+  SEA_TRY(validate_desc(d));
+  if (!cache) return SEA_ERR_INVALID;
+  if (cache_bytes < sea_temporal_cache_bytes(d, training)) return SEA_ERR_WORKSPACE;
+  g_launches = 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  Arena ar{static_cast<char*>(cache)};
+  CacheLayout c;
+  layout_cache(d, training != 0, ar, c);
+  const bool fp32 = d->precision == SEA_PREC_FP32;
+  const int E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim, V = d->num_streams;
+  const bool ada = d->norm_kind == SEA_NORM_ADALN;
+  for (int l = 0; l < d->num_layers; ++l) {
+    for (int i = 0; i < V; ++i) {
+      const sea_stream_params& p = d->blocks[l].s[i];
+      StreamCache& sc = c.blocks[l].s[i];
+      SEA_TRY(pack_weight(p.self_attn.q_w.p, E, E, sc.qkv, 0, 3 * E, fp32, s));
+      SEA_TRY(pack_weight(p.self_attn.k_w.p, E, E, sc.qkv, E, 3 * E, fp32, s));
+      SEA_TRY(pack_weight(p.self_attn.v_w.p, E, E, sc.qkv, 2 * E, 3 * E, fp32, s));
+      SEA_CUDA_OK(cudaMemcpyAsync(sc.qkv_bias, p.self_attn.q_b.p, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
+      SEA_CUDA_OK(cudaMemcpyAsync(sc.qkv_bias + E, p.self_attn.k_b.p, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
+      SEA_CUDA_OK(cudaMemcpyAsync(sc.qkv_bias + 2 * E, p.self_attn.v_b.p, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
+      SEA_TRY(pack_weight(p.self_attn.proj_w.p, E, E, sc.sproj, 0, E, fp32, s));
+      SEA_TRY(pack_weight(p.down_w.p, Dd, E, sc.down, 0, Dd, fp32, s));
+      SEA_TRY(pack_weight(p.up_w.p, E, Dd, sc.up, 0, E, fp32, s));
+      SEA_TRY(pack_weight(p.mlp0_w.p, H, E, sc.mlp0, 0, H, fp32, s));
+      SEA_TRY(pack_weight(p.mlp3_w.p, E, H, sc.mlp3, 0, E, fp32, s));
+      SEA_TRY(pack_weight(p.proj_w.p, E, E, sc.proj, 0, E, fp32, s));
+      for (int j = 0; j < V; ++j) {
+        if (j == i) continue;
+        const sea_attn_params& ca = p.cross_attn[j];
+        SEA_TRY(pack_weight(ca.q_w.p, Dd, Dd, sc.cq[j], 0, Dd, fp32, s));
+        SEA_TRY(pack_weight(ca.k_w.p, Dd, Dd, sc.ckv[j], 0, 2 * Dd, fp32, s));
+        SEA_TRY(pack_weight(ca.v_w.p, Dd, Dd, sc.ckv[j], Dd, 2 * Dd, fp32, s));
+        SEA_CUDA_OK(cudaMemcpyAsync(sc.ckv_bias[j], ca.k_b.p, sizeof(float) * Dd, cudaMemcpyDeviceToDevice, s));
+        SEA_CUDA_OK(cudaMemcpyAsync(sc.ckv_bias[j] + Dd, ca.v_b.p, sizeof(float) * Dd, cudaMemcpyDeviceToDevice, s));
+        SEA_TRY(pack_weight(ca.proj_w.p, Dd, Dd, sc.cproj[j], 0, Dd, fp32, s));
+      }
+      if (ada) {
+        SEA_TRY(refresh_norm(p.ln0, sc.c2_ln0, 2 * E, fp32, s));
+        SEA_TRY(refresh_norm(p.ln2, sc.c2_ln2, 2 * E, fp32, s));
+        SEA_TRY(refresh_norm(p.ln_cross, sc.c2_lnc, 2 * Dd, fp32, s));
+      }
+    }
+  }
+  if (ada)
+    for (int i = 0; i < V; ++i) SEA_TRY(refresh_norm(d->final_ln[i], c.c2_final[i], 2 * E, fp32, s));
+  return SEA_OK;
+}
+
+// ---------------------------------------------------------------------------------- the tape
+namespace sea {
+
+void layout_tape(const sea_temporal_desc* d, int B, int T, bool training, Arena& ar, Tape& t) {
+  (void)training;
+  const bool fp32 = d->precision == SEA_PREC_FP32;
+  const size_t esz = fp32 ? 4 : 2;
+  const size_t M = static_cast<size_t>(B) * T;
+  const size_t E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
+  const int V = d->num_streams;
+  const bool ada = d->norm_kind == SEA_NORM_ADALN;
+  auto act = [&](size_t elems) { return ar.take(elems * esz); };
+  auto f32 = [&](size_t elems) { return static_cast<float*>(ar.take(elems * 4)); };
+  auto b16 = [&](size_t elems) { return fp32 ? nullptr : static_cast<bf16*>(ar.take(elems * 2)); };
+  t.L.assign(d->num_layers, LayerTape{});
+  for (int l = 0; l < d->num_layers; ++l) {
+    LayerTape& lt = t.L[l];
+    lt.tipi_g = f32(M * d->ib_hidden);
+    lt.tipi_pre = f32(M * d->ib_hidden);
+    lt.tipi_st = f32(M * 2);
+    for (int i = 0; i < V; ++i) {
+      StreamTape& s = lt.s[i];
+      if (ada) {
+        s.hid0 = act(M * 2 * E); s.hid2 = act(M * 2 * E); s.hidc = act(M * 2 * Dd);
+        s.cond0 = f32(M * 2 * E); s.cond2 = f32(M * 2 * E); s.condc = f32(M * 2 * Dd);
+      }
+      s.n0 = act(M * E); s.st0 = f32(M * 2);
+      s.qkv = act(M * 3 * E); s.ao = act(M * E);
+      s.lse = f32(static_cast<size_t>(B) * d->n_heads * T);
+      s.x1 = f32(M * E); s.x1b = b16(M * E);
+      s.dpre = f32(M * Dd); s.stc_pre = f32(M * 2); s.npre = act(M * Dd);
+      if (i < V - 1) { s.dpost = f32(M * Dd); s.stc_post = f32(M * 2); s.npost = act(M * Dd); }
+      for (int j = 0; j < V; ++j) {
+        if (j == i) continue;
+        s.q[j] = act(M * Dd); s.kv[j] = act(M * 2 * Dd); s.a[j] = act(M * Dd);
+        s.lse_c[j] = f32(static_cast<size_t>(B) * d->n_heads * T);
+        s.p[j] = act(M * Dd); s.g[j] = b16(M * Dd);
+      }
+      s.xp = f32(M * E); s.xpb = b16(M * E);
+      s.x2 = f32(M * E); s.n2 = act(M * E); s.st2 = f32(M * 2);
+      s.h = act(M * H); s.stH = f32(M * 2); s.gh = act(M * H);
+      s.x3 = act(M * E);
+      s.xout = f32(M * E);
+    }
+  }
+  for (int i = 0; i < V; ++i) {
+    if (ada) { t.hidF[i] = act(M * 2 * E); t.condF[i] = f32(M * 2 * E); }
+    t.stF[i] = f32(M * 2);
+  }
+  if (fp32) {
+    const size_t kmax = H > 2 * E ? H : 2 * E;
+    for (int g = 0; g < SEA_MAX_STREAMS; ++g) t.packA[g] = static_cast<bf16*>(ar.take(M * 6 * kmax * 2));
+  }
+}
+
+// ------------------------------------------------------------------------------ op helpers
+int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, const LinOut* out,
+                 int Mrows) {
+  sea_gemm_problem probs[SEA_MAX_STREAMS];
+  const int N = W[0]->N, K = W[0]->K;
+  for (int g = 0; g < n; ++g) {
+    sea_gemm_problem& p = probs[g];
+    p = sea_gemm_problem{};
+    const LinOut& o = out[g];
+    if (c.fp32) {
+      sea_pack_args pa{};
+      pa.src_f32 = static_cast<const float*>(in[g].a);
+      pa.ld = in[g].lda; pa.R = Mrows; pa.C = K; pa.split = 1; pa.act = in[g].act_on_load;
+      pa.dst = c.tape->packA[g]; pa.ld_dst = 6LL * K;
+      SEA_TRY(sea_pack_operand(&pa, reinterpret_cast<sea_stream_t>(c.s)));
+      ++g_launches;
+      p.a = c.tape->packA[g]; p.lda = 6LL * K;
+    } else {
+      p.a = in[g].a; p.lda = in[g].lda;
+    }
+    p.b = W[g]->w; p.ldb = W[g]->ldw;
+    sea_gemm_epilogue& e = p.epi;
+    e.bias = o.bias;
+    e.residual = o.residual; e.ld_residual = o.ld_res;
+    e.act = o.act;
+    if (o.rope_cols > 0) {
+      e.rope_cols = o.rope_cols; e.head_dim = o.head_dim; e.seq_len = c.T;
+      e.rope_table = o.rope_table; e.rope_sign = 1.f;
+    }
+    if (c.fp32) {
+      // exactly one fp32 destination in the parity mode
+      if (o.f32) { e.out_f32 = o.f32; e.ld_out_f32 = o.ld_f32; }
+      else if (o.pre) { e.out_f32 = static_cast<float*>(o.pre); e.ld_out_f32 = o.ld_pre; }
+      else { e.out_f32 = static_cast<float*>(o.post); e.ld_out_f32 = o.ld_post; }
+    } else {
+      e.out_f32 = o.f32; e.ld_out_f32 = o.ld_f32;
+      e.out_pre_bf16 = o.pre; e.ld_out_pre_bf16 = o.ld_pre;
+      e.out_bf16 = o.post; e.ld_out_bf16 = o.ld_post;
+    }
+  }
+  ++g_launches;
+  if (c.fp32) {
+    // fresh accumulator every 512 columns of K' so the tensor core's non-RN accumulation cannot drift
+    bool can_chunk = true;
+    for (int g = 0; g < n; ++g)
+      if (probs[g].epi.out_f32 == nullptr || probs[g].epi.out_f32 == probs[g].epi.residual) can_chunk = false;
+    return sea_gemm_bf16_tn_chunked(n, probs, Mrows, N, 6 * K, can_chunk ? 512 : 0,
+                                    reinterpret_cast<sea_stream_t>(c.s));
+  }
+  return sea_gemm_bf16_tn(n, probs, Mrows, N, K, reinterpret_cast<sea_stream_t>(c.s));
+}
+
+int norm_op(Ctx& c, int kind, const sea_norm_params& np, const float* cond, const float* x,
+            long long ldx, int dim, void* y_act, float* y_f32, long long ldy_f32, float* stats,
+            const sea_block_params* tipi, const float* tipi_g, float* x_out) {
+  sea_norm_args a{};
+  a.x = x; a.ldx = ldx; a.M = c.M; a.d = dim; a.kind = kind;
+  a.weight = np.weight.p;
+  a.bias = kind == SEA_NORM_ADALN ? np.bias.p : nullptr;
+  a.cond = cond; a.ldc = 2LL * dim;
+  if (tipi) {
+    a.tipi_g = tipi_g; a.tipi_hid = c.d->ib_hidden;
+    a.tipi_w = tipi->ib3_w.p; a.tipi_b = tipi->ib3_b.p;
+    a.x_out = x_out; a.ldxo = dim;
+  }
+  if (y_f32) { a.y_f32 = y_f32; a.ldy_f32 = ldy_f32; }
+  else if (c.fp32) { a.y_f32 = static_cast<float*>(y_act); a.ldy_f32 = dim; }
+  else { a.y_bf16 = y_act; a.ldy_bf16 = dim; }
+  a.stats = stats;
+  ++g_launches;
+  return sea_norm_fwd(&a, reinterpret_cast<sea_stream_t>(c.s));
+}
+
+int attention_op(Ctx& c, const void* q, long long ldq, const void* k, const void* v, long long ldkv,
+                 void* o, long long ldo, float* lse, int head_dim) {
+  sea_attn_args a{};
+  a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldkv; a.ldv = ldkv;
+  a.o = o; a.ldo = ldo; a.lse = lse;
+  a.B = c.B; a.T = c.T; a.n_heads = c.d->n_heads; a.head_dim = head_dim;
+  a.src_len = c.d->src_len;
+  a.scale = 1.0f / sqrtf(static_cast<float>(head_dim));
+  a.prec = c.fp32 ? SEA_PREC_FP32 : SEA_PREC_BF16;
+  ++g_launches;
+  return sea_attention_fwd(&a, reinterpret_cast<sea_stream_t>(c.s));
+}
+
+static int adaln_cond(Ctx& c, int n, const sea_norm_params* const* np, void* const* hid,
+                      const PackedLinear* const* W, float* const* cond, int d2, const float* ib) {
+  // cond = Linear(2d,2d)(SiLU(Linear(ib_num,2d)(ib)))   models/base_blocks.py:337-344
+  LinIn in[SEA_MAX_STREAMS];
+  LinOut out[SEA_MAX_STREAMS];
+  for (int g = 0; g < n; ++g) {
+    SEA_TRY(sea_adaln_hidden(ib, c.M, c.d->ib_num, np[g]->c0_w.p, np[g]->c0_b.p, d2,
+                             c.fp32 ? nullptr : hid[g], c.fp32 ? static_cast<float*>(hid[g]) : nullptr,
+                             reinterpret_cast<sea_stream_t>(c.s)));
+    ++g_launches;
+    in[g] = LinIn{hid[g], d2, 0};
+    out[g] = LinOut{};
+    out[g].bias = np[g]->c2_b.p;
+    out[g].f32 = cond[g]; out[g].ld_f32 = d2;
+  }
+  return linear_group(c, n, in, W, out, c.M);
+}
+
+}  // namespace sea
+
+extern "C" size_t sea_temporal_workspace_bytes(const sea_temporal_desc* d, int B, int T, int training) {
+  if (!d || B <= 0 || T <= 0) return 0;
+  Arena ar{nullptr};
+  Tape t;
+  layout_tape(d, B, T, training != 0, ar, t);
+  return ar.off + 256;
+}
+
+extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cache, const float* x,
+                                    const float* ib, float* y, int B, int T, void* workspace,
+                                    size_t workspace_bytes, int training, sea_stream_t stream) {
+  SEA_TRY(validate_desc(d));
+  if (!cache || !x || !ib || !y || !workspace || B <= 0 || T <= 0) return SEA_ERR_INVALID;
+  if (T > d->max_len) return SEA_ERR_UNSUPPORTED;
+  if (workspace_bytes < sea_temporal_workspace_bytes(d, B, T, training)) return SEA_ERR_WORKSPACE;
+  SEA_TRY(ensure_init());
+  g_launches = 0;
+
+  Arena car{const_cast<char*>(static_cast<const char*>(cache))};
+  CacheLayout cl;
+  layout_cache(d, training != 0, car, cl);
+  Arena war{static_cast<char*>(workspace)};
+  Tape tape;
+  layout_tape(d, B, T, training != 0, war, tape);
+
+  Ctx c{};
+  c.d = d; c.cache = &cl; c.tape = &tape;
+  c.s = reinterpret_cast<cudaStream_t>(stream);
+  c.fp32 = d->precision == SEA_PREC_FP32;
+  c.B = B; c.T = T; c.M = B * T;
+  const int M = c.M, V = d->num_streams, E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
+  const int hd = E / d->n_heads, hdc = Dd / d->n_heads;
+  const bool ada = d->norm_kind == SEA_NORM_ADALN;
+  const int kind = d->norm_kind;
+  const size_t esz = c.fp32 ? 4 : 2;
+  sea_stream_t st = stream;
+
+  // ---- everything that depends on ib only: TIPI hidden + all AdaLN conditions (hoisted) ----
+  for (int l = 0; l < d->num_layers; ++l) {
+    const sea_block_params& bp = d->blocks[l];
+    LayerTape& lt = tape.L[l];
+    SEA_TRY(sea_tipi_hidden(ib, M, d->ib_num, bp.ib0_w.p, bp.ib0_b.p, bp.ib_ln_w.p, bp.ib_ln_b.p,
+                            d->ib_hidden, lt.tipi_g, lt.tipi_pre, lt.tipi_st, st));
+    ++g_launches;
+    if (ada) {
+      const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
+      const PackedLinear* W[SEA_MAX_STREAMS]; float* cond[SEA_MAX_STREAMS];
+      for (int which = 0; which < 2; ++which) {
+        for (int i = 0; i < V; ++i) {
+          np[i] = which ? &bp.s[i].ln2 : &bp.s[i].ln0;
+          hid[i] = which ? lt.s[i].hid2 : lt.s[i].hid0;
+          W[i] = which ? &cl.blocks[l].s[i].c2_ln2 : &cl.blocks[l].s[i].c2_ln0;
+          cond[i] = which ? lt.s[i].cond2 : lt.s[i].cond0;
+        }
+        SEA_TRY(adaln_cond(c, V, np, hid, W, cond, 2 * E, ib));
+      }
+      for (int i = 0; i < V; ++i) {
+        np[i] = &bp.s[i].ln_cross; hid[i] = lt.s[i].hidc;
+        W[i] = &cl.blocks[l].s[i].c2_lnc; cond[i] = lt.s[i].condc;
+      }
+      SEA_TRY(adaln_cond(c, V, np, hid, W, cond, 2 * Dd, ib));
+    }
+  }
+  if (ada) {
+    const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
+    const PackedLinear* W[SEA_MAX_STREAMS]; float* cond[SEA_MAX_STREAMS];
+    for (int i = 0; i < V; ++i) {
+      np[i] = &d->final_ln[i]; hid[i] = tape.hidF[i]; W[i] = &cl.c2_final[i]; cond[i] = tape.condF[i];
+    }
+    SEA_TRY(adaln_cond(c, V, np, hid, W, cond, 2 * E, ib));
+  }
+
+  // ---- layers ----
+  const float* xin[SEA_MAX_STREAMS];
+  long long ldxin = static_cast<long long>(V) * E;
+  for (int i = 0; i < V; ++i) xin[i] = x + static_cast<long long>(i) * E;  // x[:, :, i, :]
+
+  for (int l = 0; l < d->num_layers; ++l) {
+    const sea_block_params& bp = d->blocks[l];
+    LayerTape& lt = tape.L[l];
+    const BlockCache& bc = cl.blocks[l];
+    LinIn in[SEA_MAX_STREAMS];
+    LinOut out[SEA_MAX_STREAMS];
+    const PackedLinear* W[SEA_MAX_STREAMS];
+
+    // (1) x_i += SelfAttn_i(Norm_{i,0}(x_i))          models/temporal.py:135-136
+    for (int i = 0; i < V; ++i)
+      SEA_TRY(norm_op(c, kind, bp.s[i].ln0, lt.s[i].cond0, xin[i], ldxin, E, lt.s[i].n0, nullptr, 0,
+                      lt.s[i].st0, nullptr, nullptr, nullptr));
+    for (int i = 0; i < V; ++i) {
+      in[i] = LinIn{lt.s[i].n0, E, 0};
+      W[i] = &bc.s[i].qkv;
+      out[i] = LinOut{};
+      out[i].bias = bc.s[i].qkv_bias;
+      out[i].post = lt.s[i].qkv; out[i].ld_post = 3 * E;
+      out[i].rope_cols = 2 * E; out[i].head_dim = hd; out[i].rope_table = d->rope_self;
+    }
+    SEA_TRY(linear_group(c, V, in, W, out, M));
+    for (int i = 0; i < V; ++i) {
+      char* base = static_cast<char*>(lt.s[i].qkv);
+      SEA_TRY(attention_op(c, base, 3 * E, base + esz * E, base + esz * 2 * E, 3 * E, lt.s[i].ao, E,
+                           lt.s[i].lse, hd));
+    }
+    for (int i = 0; i < V; ++i) {
+      in[i] = LinIn{lt.s[i].ao, E, 0};
+      W[i] = &bc.s[i].sproj;
+      out[i] = LinOut{};
+      out[i].residual = xin[i]; out[i].ld_res = ldxin;
+      out[i].f32 = lt.s[i].x1; out[i].ld_f32 = E;
+      out[i].pre = lt.s[i].x1b; out[i].ld_pre = E;
+    }
+    SEA_TRY(linear_group(c, V, in, W, out, M));
+
+    // (2) State-Exchange Attention, sequential over i   models/temporal.py:176-192
+    for (int i = 0; i < V; ++i) {
+      in[i] = LinIn{c.fp32 ? static_cast<const void*>(lt.s[i].x1) : lt.s[i].x1b, E, 0};
+      W[i] = &bc.s[i].down;
+      out[i] = LinOut{};
+      out[i].bias = bp.s[i].down_b.p;
+      out[i].f32 = lt.s[i].dpre; out[i].ld_f32 = Dd;
+    }
+    SEA_TRY(linear_group(c, V, in, W, out, M));
+    for (int i = 0; i < V; ++i)
+      SEA_TRY(norm_op(c, kind, bp.s[i].ln_cross, lt.s[i].condc, lt.s[i].dpre, Dd, Dd, lt.s[i].npre,
+                      nullptr, 0, lt.s[i].stc_pre, nullptr, nullptr, nullptr));
+    for (int i = 0; i < V; ++i) {
+      StreamTape& s = lt.s[i];
+      const float* xcur = s.x1;
+      for (int j = 0; j < V; ++j) {
+        if (j == i) continue;
+        const void* src = (j < i) ? lt.s[j].npost : lt.s[j].npre;
+        // q from stream i, (k,v) from stream j        models/base_blocks.py:271-276
+        in[0] = LinIn{s.npre, Dd, 0};
+        W[0] = &bc.s[i].cq[j];
+        out[0] = LinOut{};
+        out[0].bias = bp.s[i].cross_attn[j].q_b.p;
+        out[0].post = s.q[j]; out[0].ld_post = Dd;
+        out[0].rope_cols = Dd; out[0].head_dim = hdc; out[0].rope_table = d->rope_cross;
+        SEA_TRY(linear_group(c, 1, in, W, out, M));
+        in[0] = LinIn{src, Dd, 0};
+        W[0] = &bc.s[i].ckv[j];
+        out[0] = LinOut{};
+        out[0].bias = bc.s[i].ckv_bias[j];
+        out[0].post = s.kv[j]; out[0].ld_post = 2 * Dd;
+        out[0].rope_cols = Dd; out[0].head_dim = hdc; out[0].rope_table = d->rope_cross;
+        SEA_TRY(linear_group(c, 1, in, W, out, M));
+        char* kvb = static_cast<char*>(s.kv[j]);
+        SEA_TRY(attention_op(c, s.q[j], Dd, kvb, kvb + esz * Dd, 2 * Dd, s.a[j], Dd, s.lse_c[j], hdc));
+        // cross_up(GELU(projection(attn)))             models/base_blocks.py:293, temporal.py:185
+        in[0] = LinIn{s.a[j], Dd, 0};
+        W[0] = &bc.s[i].cproj[j];
+        out[0] = LinOut{};
+        out[0].pre = s.p[j]; out[0].ld_pre = Dd;
+        out[0].post = s.g[j]; out[0].ld_post = Dd; out[0].act = SEA_ACT_GELU;
+        SEA_TRY(linear_group(c, 1, in, W, out, M));
+        in[0] = c.fp32 ? LinIn{s.p[j], Dd, SEA_ACT_GELU} : LinIn{s.g[j], Dd, 0};
+        W[0] = &bc.s[i].up;
+        out[0] = LinOut{};
+        out[0].bias = bp.s[i].up_b.p;
+        out[0].residual = xcur; out[0].ld_res = E;
+        out[0].f32 = s.xp; out[0].ld_f32 = E;
+        out[0].pre = s.xpb; out[0].ld_pre = E;
+        SEA_TRY(linear_group(c, 1, in, W, out, M));
+        xcur = s.xp;
+      }
+      if (V == 1) {  // no partner stream: exchange is the identity
+        SEA_CUDA_OK(cudaMemcpyAsync(s.xp, s.x1, sizeof(float) * M * E, cudaMemcpyDeviceToDevice, c.s));
+      }
+      if (i < V - 1) {  // later streams see the UPDATED stream i (Gauss–Seidel)
+        in[0] = LinIn{c.fp32 ? static_cast<const void*>(s.xp) : s.xpb, E, 0};
+        W[0] = &bc.s[i].down;
+        out[0] = LinOut{};
+        out[0].bias = bp.s[i].down_b.p;
+        out[0].f32 = s.dpost; out[0].ld_f32 = Dd;
+        SEA_TRY(linear_group(c, 1, in, W, out, M));
+        SEA_TRY(norm_op(c, kind, bp.s[i].ln_cross, s.condc, s.dpost, Dd, Dd, s.npost, nullptr, 0,
+                        s.stc_post, nullptr, nullptr, nullptr));
+      }
+    }
+
+    // (3) x_i += TIPI(ib) fused with Norm_{i,2}; (4) MLP; (5) proj    models/temporal.py:140-146
+    for (int i = 0; i < V; ++i)
+      SEA_TRY(norm_op(c, kind, bp.s[i].ln2, lt.s[i].cond2, lt.s[i].xp, E, E, lt.s[i].n2, nullptr, 0,
+                      lt.s[i].st2, &bp, lt.tipi_g, lt.s[i].x2));
+    for (int i = 0; i < V; ++i) {
+      in[i] = LinIn{lt.s[i].n2, E, 0};
+      W[i] = &bc.s[i].mlp0;
+      out[i] = LinOut{};
+      out[i].bias = bp.s[i].mlp0_b.p;
+      out[i].post = lt.s[i].h; out[i].ld_post = H;
+    }
+    SEA_TRY(linear_group(c, V, in, W, out, M));
+    for (int i = 0; i < V; ++i) {
+      sea_ln_gelu_args a{};
+      if (c.fp32) { a.h_f32 = static_cast<const float*>(lt.s[i].h); a.g_f32 = static_cast<float*>(lt.s[i].gh); }
+      else { a.h_bf16 = lt.s[i].h; a.g_bf16 = lt.s[i].gh; }
+      a.ldh = H; a.ldg = H; a.M = M; a.H = H;
+      a.weight = bp.s[i].mlp_ln_w.p; a.bias = bp.s[i].mlp_ln_b.p; a.stats = lt.s[i].stH;
+      SEA_TRY(sea_ln_gelu_fwd(&a, st));
+      ++g_launches;
+    }
+    for (int i = 0; i < V; ++i) {
+      in[i] = LinIn{lt.s[i].gh, H, 0};
+      W[i] = &bc.s[i].mlp3;
+      out[i] = LinOut{};
+      out[i].bias = bp.s[i].mlp3_b.p;
+      out[i].residual = lt.s[i].x2; out[i].ld_res = E;
+      out[i].post = lt.s[i].x3; out[i].ld_post = E;
+    }
+    SEA_TRY(linear_group(c, V, in, W, out, M));
+    for (int i = 0; i < V; ++i) {
+      in[i] = LinIn{lt.s[i].x3, E, 0};
+      W[i] = &bc.s[i].proj;
+      out[i] = LinOut{};
+      out[i].bias = bp.s[i].proj_b.p;
+      out[i].f32 = lt.s[i].xout; out[i].ld_f32 = E;
+    }
+    SEA_TRY(linear_group(c, V, in, W, out, M));
+    for (int i = 0; i < V; ++i) xin[i] = lt.s[i].xout;
+    ldxin = E;
+  }
+
+  // ---- final norm per stream, written straight into the strided [B,T,V,E] output ----
+  for (int i = 0; i < V; ++i)
+    SEA_TRY(norm_op(c, kind, d->final_ln[i], tape.condF[i], xin[i], ldxin, E, nullptr,
+                    y + static_cast<long long>(i) * E, static_cast<long long>(V) * E, tape.stF[i],
+                    nullptr, nullptr, nullptr));
+  return SEA_OK;
+}

@@ -1,0 +1,108 @@
+// Internal structures of the temporal executor (shared by forward and backward).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/sea_b200.h"
+
+namespace sea {
+
+using bf16 = __nv_bfloat16;
+
+// Bump allocator over a caller-owned buffer; base == nullptr only measures.
+struct Arena {
+  char* base;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    const size_t a = (off + 255) & ~static_cast<size_t>(255);
+    off = a + bytes;
+    return base ? base + a : nullptr;
+  }
+};
+
+// One nn.Linear (or a fused group of them) in tensor-core layout.
+struct PackedLinear {
+  const bf16* w;   // [N, kf*K]  (kf = 6 in the fp32 split mode)
+  long long ldw;
+  const bf16* wT;  // [K, kf*N]  for dgrad (training only)
+  long long ldwT;
+  int N, K;
+};
+
+struct StreamCache {
+  PackedLinear qkv, sproj, down, up, mlp0, mlp3, proj;
+  float* qkv_bias;
+  PackedLinear cq[SEA_MAX_STREAMS], ckv[SEA_MAX_STREAMS], cproj[SEA_MAX_STREAMS];
+  float* ckv_bias[SEA_MAX_STREAMS];
+  PackedLinear c2_ln0, c2_ln2, c2_lnc;
+};
+struct BlockCache { StreamCache s[SEA_MAX_STREAMS]; };
+struct CacheLayout {
+  std::vector<BlockCache> blocks;
+  PackedLinear c2_final[SEA_MAX_STREAMS];
+};
+
+// "act" buffers are bf16 in SEA_PREC_BF16 and fp32 in SEA_PREC_FP32.
+struct StreamTape {
+  void *hid0, *hid2, *hidc;        // AdaLN SiLU(cond_mlp.0(ib))           [M,2E] [M,2E] [M,2Dd]
+  float *cond0, *cond2, *condc;    // AdaLN cond_mlp outputs (scale|shift)  fp32
+  void* n0; float* st0;            // Norm_{i,0}(x_i), (mean, rstd)
+  void* qkv;                       // [M,3E]  RoPE'd q | RoPE'd k | v
+  void* ao; float* lse;            // attention output [M,E], log-sum-exp [B,nh,T]
+  float* x1; bf16* x1b;            // x_i after self-attention (fp32 + bf16 operand copy)
+  float* dpre; float* stc_pre; void* npre;     // cross_down(x1), stats, ln_cross(...)
+  float* dpost; float* stc_post; void* npost;  // same on the exchanged stream (i < V-1)
+  void* q[SEA_MAX_STREAMS]; void* kv[SEA_MAX_STREAMS]; void* a[SEA_MAX_STREAMS];
+  float* lse_c[SEA_MAX_STREAMS];
+  void* p[SEA_MAX_STREAMS]; bf16* g[SEA_MAX_STREAMS];  // cross projection pre-GELU / GELU
+  float* xp; bf16* xpb;            // x_i after the exchange
+  float* x2; void* n2; float* st2; // x_i + TIPI, Norm_{i,2}
+  void* h; float* stH; void* gh;   // MLP hidden pre-LN [M,H], stats, GELU(LN(h))
+  void* x3;                        // x2 + MLP (operand of proj)
+  float* xout;                     // proj output = block output
+};
+struct LayerTape {
+  StreamTape s[SEA_MAX_STREAMS];
+  float *tipi_g, *tipi_pre, *tipi_st;
+};
+struct Tape {
+  std::vector<LayerTape> L;
+  void* hidF[SEA_MAX_STREAMS];
+  float* condF[SEA_MAX_STREAMS];
+  float* stF[SEA_MAX_STREAMS];
+  bf16* packA[SEA_MAX_STREAMS];  // fp32 mode: split A operands
+};
+
+struct Ctx {
+  const sea_temporal_desc* d;
+  const CacheLayout* cache;
+  Tape* tape;
+  cudaStream_t s;
+  bool fp32;
+  int B, T, M;
+};
+
+struct LinIn {
+  const void* a;  // act dtype [M, K]
+  long long lda;
+  int act_on_load;  // fp32 mode only: GELU applied while packing
+};
+struct LinOut {
+  const float* bias;
+  const float* residual; long long ld_res;
+  float* f32; long long ld_f32;   // fp32 copy of v
+  void* pre; long long ld_pre;    // act-dtype copy of v
+  void* post; long long ld_post;  // act-dtype copy of act(v)
+  int act;
+  int rope_cols, head_dim; const float* rope_table;
+};
+
+void layout_cache(const sea_temporal_desc* d, bool training, Arena& ar, CacheLayout& c);
+void layout_tape(const sea_temporal_desc* d, int B, int T, bool training, Arena& ar, Tape& t);
+int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, const LinOut* out, int Mrows);
+
+extern thread_local int g_launches;
+
+}  // namespace sea

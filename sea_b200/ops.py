@@ -39,6 +39,105 @@ def gemm_problem(a, b, *, bias=None, residual=None, gelu_grad_of=None, act=ACT_N
     return GemmProblem(_ptr(a), a.stride(0), _ptr(b), b.stride(0), e)
 
 
-def gemm_bf16_tn(problems: Sequence[GemmProblem], M: int, N: int, K: int) -> None:
+def gemm_bf16_tn(problems: Sequence[GemmProblem], M: int, N: int, K: int, k_chunk: int = 0) -> None:
     arr = (GemmProblem * len(problems))(*problems)
-    check(lib.sea_gemm_bf16_tn(len(problems), arr, M, N, K, _stream()), "gemm_bf16_tn")
+    check(lib.sea_gemm_bf16_tn_chunked(len(problems), arr, M, N, K, k_chunk, _stream()), "gemm_bf16_tn")
+
+
+# ------------------------------------------------------------------ elementwise / attention ops
+from . import _structs as S  # noqa: E402
+
+
+def norm_fwd(x, weight, *, bias=None, cond=None, kind=0, out_dtype=torch.bfloat16,
+             tipi=None, stats=False):
+    """x [M,d] fp32 (row stride arbitrary) -> (y, x_out or None, stats or None)."""
+    M, d = x.shape
+    y = torch.empty(M, d, device=x.device, dtype=out_dtype)
+    a = S.NormArgs()
+    a.x, a.ldx, a.M, a.d, a.kind = x.data_ptr(), x.stride(0), M, d, kind
+    a.weight = weight.data_ptr()
+    a.bias = None if bias is None else bias.data_ptr()
+    if cond is not None:
+        a.cond, a.ldc = cond.data_ptr(), cond.stride(0)
+    x_out = None
+    if tipi is not None:
+        g, w3, b3 = tipi
+        x_out = torch.empty(M, d, device=x.device, dtype=torch.float32)
+        a.tipi_g, a.tipi_hid, a.tipi_w, a.tipi_b = g.data_ptr(), g.shape[1], w3.data_ptr(), b3.data_ptr()
+        a.x_out, a.ldxo = x_out.data_ptr(), d
+    if out_dtype == torch.float32:
+        a.y_f32, a.ldy_f32 = y.data_ptr(), d
+    else:
+        a.y_bf16, a.ldy_bf16 = y.data_ptr(), d
+    st = torch.empty(M, 2, device=x.device) if stats else None
+    a.stats = None if st is None else st.data_ptr()
+    check(lib.sea_norm_fwd(C.byref(a), _stream()), "norm_fwd")
+    return y, x_out, st
+
+
+def adaln_hidden(ib, w1, b1, out_dtype=torch.bfloat16):
+    M, ib_num = ib.shape
+    n = w1.shape[0]
+    out = torch.empty(M, n, device=ib.device, dtype=out_dtype)
+    ob = _ptr(out) if out_dtype == torch.bfloat16 else None
+    of = _ptr(out) if out_dtype == torch.float32 else None
+    check(lib.sea_adaln_hidden(_ptr(ib), M, ib_num, _ptr(w1), _ptr(b1), n, ob, of, _stream()), "adaln_hidden")
+    return out
+
+
+def tipi_hidden(ib, w0, b0, ln_w, ln_b):
+    M, ib_num = ib.shape
+    hid = w0.shape[0]
+    g = torch.empty(M, hid, device=ib.device)
+    check(lib.sea_tipi_hidden(_ptr(ib), M, ib_num, _ptr(w0), _ptr(b0), _ptr(ln_w), _ptr(ln_b), hid,
+                              _ptr(g), None, None, _stream()), "tipi_hidden")
+    return g
+
+
+def ln_gelu_fwd(h, weight, bias):
+    M, H = h.shape
+    g = torch.empty_like(h)
+    a = S.LnGeluArgs()
+    if h.dtype == torch.bfloat16:
+        a.h_bf16, a.g_bf16 = h.data_ptr(), g.data_ptr()
+    else:
+        a.h_f32, a.g_f32 = h.data_ptr(), g.data_ptr()
+    a.ldh, a.ldg, a.M, a.H = h.stride(0), g.stride(0), M, H
+    a.weight, a.bias = weight.data_ptr(), bias.data_ptr()
+    check(lib.sea_ln_gelu_fwd(C.byref(a), _stream()), "ln_gelu_fwd")
+    return g
+
+
+def pack_operand(src, *, transpose=False, split=0, act=ACT_NONE):
+    R, Cc = src.shape
+    rows, cols = (Cc, R) if transpose else (R, Cc)
+    dst = torch.empty(rows, cols * (6 if split else 1), device=src.device, dtype=torch.bfloat16)
+    a = S.PackArgs()
+    if src.dtype == torch.float32:
+        a.src_f32 = src.data_ptr()
+    else:
+        a.src_bf16 = src.data_ptr()
+    a.ld, a.R, a.C = src.stride(0), R, Cc
+    a.transpose, a.split, a.act, a.split_inner = int(transpose), split, act, 0
+    a.dst, a.ld_dst = dst.data_ptr(), dst.stride(0)
+    check(lib.sea_pack_operand(C.byref(a), _stream()), "pack_operand")
+    return dst
+
+
+def attention_fwd(q, k, v, n_heads, *, src_len=0, B=1, want_lse=False):
+    """q,k,v: [B*T, n_heads*hd] views (row stride arbitrary), bf16 or fp32."""
+    M, Cdim = q.shape
+    T = M // B
+    hd = Cdim // n_heads
+    o = torch.empty(M, Cdim, device=q.device, dtype=q.dtype)
+    lse = torch.empty(B, n_heads, T, device=q.device) if want_lse else None
+    a = S.AttnArgs()
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.ldq, a.ldk, a.ldv = q.stride(0), k.stride(0), v.stride(0)
+    a.o, a.ldo = o.data_ptr(), o.stride(0)
+    a.lse = None if lse is None else lse.data_ptr()
+    a.B, a.T, a.n_heads, a.head_dim, a.src_len = B, T, n_heads, hd, src_len
+    a.scale = hd ** -0.5
+    a.prec = 0 if q.dtype == torch.bfloat16 else 1
+    check(lib.sea_attention_fwd(C.byref(a), _stream()), "attention_fwd")
+    return (o, lse) if want_lse else o

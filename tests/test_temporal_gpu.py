@@ -1,0 +1,84 @@
+"""Whole-model parity of the CUDA temporal path against the reference (golden outputs of the
+unmodified reference + the oracle), through the public module interface."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sea_oracle as so
+from tests.helpers import TEMPORAL_CASES, rel_l2, temporal_case
+
+pytestmark = pytest.mark.gpu
+
+# north_star tolerances: fp32 <= 1e-4 relative, bf16 <= 2e-2 relative (after a 10-step rollout)
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def build(tag, ln, precision, device):
+    from sea_b200.temporal import TemporalModel
+    g, sd, cfg, x, ib, tgt, steps = temporal_case(tag, ln)
+    E, nh, scale, V, B, T, _ = [int(v) for v in g["meta"]]
+    m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln,
+                      precision=precision)
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    live_missing = [k for k in missing.missing_keys if not k.endswith((".tril", ".freqs_cis", ".pe"))]
+    # only the reference's dead parameters may be absent from the recipe
+    assert all(("ln.exp" in k and ".1." in k) or "ln.cross" in k or "residual_projection" in k
+               or any(f"cross_attn.{i}.{i}." in k for i in range(4)) for k in live_missing), live_missing
+    return g, sd, cfg, m.to(device).eval(), x.to(device), ib.to(device), tgt.to(device), steps
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag,ln", TEMPORAL_CASES)
+def test_forward_matches_reference_golden(cuda, tag, ln, precision):
+    g, sd, cfg, m, x, ib, _, _ = build(tag, ln, precision, cuda)
+    with torch.no_grad():
+        y = m(x, ib)
+    torch.cuda.synchronize()
+    assert y.shape == x.shape and y.dtype == torch.float32
+    err = rel_l2(y.cpu(), g["y"])
+    print(f"\n[temporal fwd] {tag} {precision}: rel_l2 = {err:.3e}")
+    assert err < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag,ln", [c for c in TEMPORAL_CASES if c[0] != "small_v3"])
+def test_rollout_matches_reference_golden(cuda, tag, ln, precision):
+    """The loop of utils/train_utils.py:202-209 (prefix recompute) driven through module.forward."""
+    g, sd, cfg, m, x, ib, _, steps = build(tag, ln, precision, cuda)
+    T = x.shape[1]
+    ibr = ib[:1].repeat(1, (steps + T - 1) // T + 1, 1)[:, :steps]
+    seq = x[:1, :1]
+    with torch.no_grad():
+        for i in range(steps):
+            out = m(seq, ibr[:, : i + 1])
+            seq = torch.cat((seq, out[:, -1:]), dim=1)
+    r = seq[:, 1:].cpu()
+    err_all = rel_l2(r, g["rollout"])
+    err_last = rel_l2(r[:, -1], g["rollout"][:, -1])
+    print(f"\n[temporal rollout] {tag} {precision}: {steps} steps rel_l2 all={err_all:.3e} last={err_last:.3e}")
+    assert err_last < TOL[precision] and err_all < TOL[precision]
+
+
+def test_forward_matches_oracle_at_config_shape(cuda):
+    """Full multiphase train shape [4,199,2,2048] vs the oracle on the same seeded inputs."""
+    from sea_b200.temporal import TemporalModel
+    from oracle import golden_recipe as gr
+    shapes = gr.temporal_shapes(embed_dim=2048, n_heads=8, scale_ratio=8, num_variables=2, ln_type="ln")
+    sd = gr.fill_state(shapes, 7)
+    x, ib, _ = gr.temporal_inputs(4, 199, 2, 2048, 7)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    with torch.no_grad():
+        ref = so.temporal_forward(x, ib, sd, num_layers=1, n_heads=8, ln_type="ln")
+    for precision in ("fp32", "bf16"):
+        m = TemporalModel(1, 2048, 8, 256, 8, 0, 2, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True,
+                          "ln", precision=precision)
+        m.load_state_dict(sd, strict=False)
+        m = m.to(cuda).eval()
+        with torch.no_grad():
+            y = m(x.to(cuda), ib.to(cuda))
+        err = rel_l2(y.cpu(), ref)
+        print(f"\n[temporal fwd] multiphase [4,199,2,2048] {precision}: rel_l2 = {err:.3e}, "
+              f"launches = {m.engine().last_launches}")
+        assert err < TOL[precision]
+        del m
