@@ -39,6 +39,7 @@ enum {
 enum { SEA_ACT_NONE = 0, SEA_ACT_GELU = 1 };
 enum { SEA_PREC_BF16 = 0, SEA_PREC_FP32 = 1 };
 enum { SEA_NORM_LN = 0, SEA_NORM_ADALN = 1 };
+#define SEA_MAX_STREAMS 4
 
 /* ------------------------------------------------------------------ library ---------------- */
 int sea_init(int device);              /* caches SM count + driver entry points for `device`  */
@@ -180,6 +181,71 @@ int sea_pack_operand(const sea_pack_args* args, sea_stream_t stream);
 int sea_colsum_accumulate(const float* src_f32, const void* src_bf16, int64_t ld, int M, int N,
                           float* out, sea_stream_t stream);
 
+/* ------------------------------------------------------------------ backward of K4/K5/K6 ----
+ * The reference differentiates these with autograd; here they are explicit kernels.  Parameter
+ * gradients ACCUMULATE (+=) into the given fp32 buffers (atomics). */
+typedef struct sea_norm_bwd_args {
+  const float* dy;      /* [M,d] upstream gradient */
+  int64_t lddy;
+  const float* x;       /* forward input rows */
+  int64_t ldx;
+  const float* stats;   /* (mean, rstd) from forward */
+  int32_t M, d, kind;
+  const float* weight;
+  const float* cond;    /* AdaLN cond used in forward */
+  int64_t ldc;
+  const float* dres;    /* optional gradient of the skip connection, added to dx */
+  int64_t lddres;
+  float* dx;            /* optional fp32 output */
+  int64_t lddx;
+  void* dx_bf16;        /* optional bf16 copy (operand of the following GEMMs) */
+  int64_t lddx_bf16;
+  float* dweight;       /* [d] +=  (may be NULL) */
+  float* dbias;         /* [d] +=  (AdaLN's own bias; may be NULL) */
+  float* dcond;         /* AdaLN: [M,2d] gradient wrt cond (scale | shift) */
+  int64_t lddcond;
+  int32_t dcond_accumulate; /* 1: += into dcond (module applied twice in the exchange) */
+} sea_norm_bwd_args;
+int sea_norm_bwd(const sea_norm_bwd_args* args, sea_stream_t stream);
+
+typedef struct sea_ln_gelu_bwd_args {
+  const void* dg;   /* bf16 [M,H] gradient wrt GELU output */
+  int64_t lddg;
+  const void* h;    /* bf16 [M,H] pre-LayerNorm activations saved by forward */
+  int64_t ldh;
+  const float* stats;
+  int32_t M, H;
+  const float* weight;
+  const float* bias;
+  void* dh;         /* bf16 [M,H] */
+  int64_t lddh;
+  float* dweight;   /* [H] += */
+  float* dbias;     /* [H] += */
+} sea_ln_gelu_bwd_args;
+int sea_ln_gelu_bwd(const sea_ln_gelu_bwd_args* args, sea_stream_t stream);
+
+/* Backward of sea_adaln_hidden: dh [M,n] -> dw1 [n, ib_num] +=, db1 [n] +=  (ib_num <= 4). */
+int sea_adaln_hidden_bwd(const float* dh, int64_t lddh, const float* ib, int M, int ib_num,
+                         const float* w1, const float* b1, int n, float* dw1, float* db1,
+                         sea_stream_t stream);
+
+/* Backward of the TIPI branch x_i += W3 GELU(LN(W0 ib + b0)) + b3 shared by all streams:
+ * dx[i] are the per-stream gradients at the add; everything accumulates. hid <= 8, ib_num <= 4. */
+typedef struct sea_tipi_bwd_args {
+  const float* dx[SEA_MAX_STREAMS];
+  int64_t lddx;
+  int32_t n_streams, M, E, hid, ib_num;
+  const float* g;     /* [M,hid] forward hidden (after GELU) */
+  const float* u;     /* [M,hid] pre-LayerNorm */
+  const float* stats; /* [M,2] */
+  const float* ib;
+  const float* w3;    /* [E,hid] */
+  const float* ln_w;
+  const float* ln_b;
+  float *dw3, *db3, *dlnw, *dlnb, *dw0, *db0;
+} sea_tipi_bwd_args;
+int sea_tipi_bwd(const sea_tipi_bwd_args* args, sea_stream_t stream);
+
 /* ------------------------------------------------------------------ K2: attention ------------
  * softmax(mask(Q K^T * scale)) V per (batch, head), causal with offset: key k is visible to
  * query q iff k <= q + src_len  (models/base_blocks.py:191-197 and 283-289; Q and K/V come from
@@ -201,6 +267,30 @@ typedef struct sea_attn_args {
   int32_t prec; /* SEA_PREC_BF16: bf16 in/out; SEA_PREC_FP32: fp32 in/out */
 } sea_attn_args;
 int sea_attention_fwd(const sea_attn_args* args, sea_stream_t stream);
+/* K3: backward of sea_attention_fwd.  d_o is the gradient of o; delta [B,n_heads,T] is scratch.
+ * dq/dk/dv use the same row/head layout.  If rope_table is given, dq and dk are rotated back by
+ * -theta (the forward RoPE lives in the projection GEMM epilogue), so they are gradients with
+ * respect to the PRE-RoPE projections. */
+typedef struct sea_attn_bwd_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* o;
+  const void* d_o;
+  int64_t ldq, ldk, ldv, ldo, lddo;
+  const float* lse;
+  float* delta;
+  void* dq;
+  void* dk;
+  void* dv;
+  int64_t lddq, lddk, lddv;
+  int32_t B, T, n_heads, head_dim;
+  int32_t src_len;
+  float scale;
+  int32_t prec;
+  const float* rope_table; /* [>=T, head_dim/2, 2] or NULL */
+} sea_attn_bwd_args;
+int sea_attention_bwd(const sea_attn_bwd_args* args, sea_stream_t stream);
 /* Test hook: 1 forces the CUDA-core kernel even where the tcgen05 kernel applies. */
 void sea_attention_force_simt(int on);
 
@@ -213,8 +303,6 @@ void sea_attention_force_simt(int on);
  * The descriptor mirrors the reference module tree: every field is the fp32 master parameter
  * (`p`, the nn.Parameter's storage) and, for training, where its gradient goes (`g`, may be NULL).
  * Dead parameters of the reference do not appear. */
-#define SEA_MAX_STREAMS 4
-
 typedef struct sea_param {
   const float* p;
   float* g;
@@ -267,8 +355,29 @@ size_t sea_temporal_workspace_bytes(const sea_temporal_desc* d, int B, int T, in
 int sea_temporal_forward(const sea_temporal_desc* d, const void* cache, const float* x,
                          const float* ib, float* y, int B, int T, void* workspace,
                          size_t workspace_bytes, int training, sea_stream_t stream);
+/* Backward of the last sea_temporal_forward(..., training=1) that used this `workspace`
+ * (autograd in the reference, train/train_temporal.py:257).  dy [B,T,V,E] fp32 contiguous.
+ * Parameter gradients ACCUMULATE (+=) into the `g` pointers of the descriptor (NULL = frozen);
+ * dx (optional) receives dL/dx.  SEA_PREC_BF16 only; the cache must have been refreshed with
+ * training=1 (it then holds the transposed weights for dgrad). */
+int sea_temporal_backward(const sea_temporal_desc* d, const void* cache, const float* x,
+                          const float* ib, const float* dy, float* dx, int B, int T,
+                          void* workspace, size_t workspace_bytes, sea_stream_t stream);
 /* Number of kernels the last forward / backward call on this thread launched. */
 int sea_last_launch_count(void);
+
+/* Optional per-launch timing (CUDA events on the launching stream) for roofline accounting.
+ * Between begin and end every executor launch is bracketed by an event pair; end synchronises on
+ * the events and returns, per category, total device milliseconds, algorithmic work (FLOPs for
+ * GEMM / attention, bytes for the HBM-bound kernels) and launch counts. */
+enum { SEA_PROF_GEMM = 0, SEA_PROF_ATTN = 1, SEA_PROF_ELEMWISE = 2, SEA_PROF_NUM = 3 };
+typedef struct sea_profile_summary {
+  double ms[SEA_PROF_NUM];
+  double work[SEA_PROF_NUM];
+  int64_t launches[SEA_PROF_NUM];
+} sea_profile_summary;
+void sea_profile_begin(void);
+int sea_profile_end(sea_profile_summary* out);
 
 #ifdef __cplusplus
 }

@@ -75,3 +75,39 @@ class AttnArgs(C.Structure):
                 ("o", C.c_void_p), ("ldo", C.c_int64), ("lse", C.c_void_p),
                 ("B", C.c_int32), ("T", C.c_int32), ("n_heads", C.c_int32), ("head_dim", C.c_int32),
                 ("src_len", C.c_int32), ("scale", C.c_float), ("prec", C.c_int32)]
+
+
+class NormBwdArgs(C.Structure):
+    _fields_ = [("dy", C.c_void_p), ("lddy", C.c_int64), ("x", C.c_void_p), ("ldx", C.c_int64),
+                ("stats", C.c_void_p), ("M", C.c_int32), ("d", C.c_int32), ("kind", C.c_int32),
+                ("weight", C.c_void_p), ("cond", C.c_void_p), ("ldc", C.c_int64),
+                ("dres", C.c_void_p), ("lddres", C.c_int64), ("dx", C.c_void_p), ("lddx", C.c_int64),
+                ("dx_bf16", C.c_void_p), ("lddx_bf16", C.c_int64), ("dweight", C.c_void_p),
+                ("dbias", C.c_void_p), ("dcond", C.c_void_p), ("lddcond", C.c_int64),
+                ("dcond_accumulate", C.c_int32)]
+
+
+class LnGeluBwdArgs(C.Structure):
+    _fields_ = [("dg", C.c_void_p), ("lddg", C.c_int64), ("h", C.c_void_p), ("ldh", C.c_int64),
+                ("stats", C.c_void_p), ("M", C.c_int32), ("H", C.c_int32), ("weight", C.c_void_p),
+                ("bias", C.c_void_p), ("dh", C.c_void_p), ("lddh", C.c_int64),
+                ("dweight", C.c_void_p), ("dbias", C.c_void_p)]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+                ("d_o", C.c_void_p), ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64),
+                ("ldo", C.c_int64), ("lddo", C.c_int64), ("lse", C.c_void_p), ("delta", C.c_void_p),
+                ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddq", C.c_int64),
+                ("lddk", C.c_int64), ("lddv", C.c_int64), ("B", C.c_int32), ("T", C.c_int32),
+                ("n_heads", C.c_int32), ("head_dim", C.c_int32), ("src_len", C.c_int32),
+                ("scale", C.c_float), ("prec", C.c_int32), ("rope_table", C.c_void_p)]
+
+
+class TipiBwdArgs(C.Structure):
+    _fields_ = [("dx", C.c_void_p * MAX_STREAMS), ("lddx", C.c_int64), ("n_streams", C.c_int32),
+                ("M", C.c_int32), ("E", C.c_int32), ("hid", C.c_int32), ("ib_num", C.c_int32),
+                ("g", C.c_void_p), ("u", C.c_void_p), ("stats", C.c_void_p), ("ib", C.c_void_p),
+                ("w3", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
+                ("dw3", C.c_void_p), ("db3", C.c_void_p), ("dlnw", C.c_void_p), ("dlnb", C.c_void_p),
+                ("dw0", C.c_void_p), ("db0", C.c_void_p)]

@@ -1,0 +1,40 @@
+"""Autograd bridge for the temporal engine.
+
+The whole model is ONE autograd node: forward = one FFI call that leaves its tape in a workspace,
+backward = one FFI call that reads it.  Parameter gradients are accumulated by the CUDA kernels
+straight into ``param.grad`` (views of one flat fp32 buffer owned by the engine — the same buffer
+the data-parallel all-reduce runs on), with torch's own semantics: ``grad is None`` -> fresh zeros,
+otherwise ``+=``; the reference's dead parameters keep ``grad = None``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib
+
+
+class _TemporalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ib, anchor, engine):
+        B, T = x.shape[0], x.shape[1]
+        ws = engine.acquire_training_workspace(B, T)
+        y = engine.forward_nograd(x, ib, training=True, ws=ws)
+        ctx.engine, ctx.ws, ctx.shape = engine, ws, (B, T)
+        ctx.save_for_backward(x, ib)
+        ctx.need_dx = x.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng = ctx.engine
+        x, ib = ctx.saved_tensors
+        dx = eng.backward(x, ib, dy, ctx.ws, ctx.need_dx)
+        eng.release_training_workspace(ctx.shape, ctx.ws)
+        return dx, None, None, None
+
+
+def temporal_apply(engine, x, ib):
+    anchor = engine.anchor_param()
+    return _TemporalFn.apply(x, ib, anchor, engine)

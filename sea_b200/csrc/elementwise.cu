@@ -69,7 +69,7 @@ __global__ void tipi_hidden_kernel(const float* __restrict__ ib, int M, int ib_n
   for (int k = 0; k < hid; ++k) {
     const float n = (u[k] - mean) * rstd * ln_w[k] + ln_b[k];
     g_out[static_cast<long long>(m) * hid + k] = ptx::gelu_erf(n);
-    if (pre_out) pre_out[static_cast<long long>(m) * hid + k] = n;
+    if (pre_out) pre_out[static_cast<long long>(m) * hid + k] = u[k];  // pre-LayerNorm, for backward
   }
   if (stats_out) {
     stats_out[2 * m] = mean;

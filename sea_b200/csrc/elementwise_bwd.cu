@@ -1,0 +1,445 @@
+// Backward of the HBM-bound kernels (the reference relies on autograd for all of these).
+// Row-wise quantities are recomputed from the saved fp32 inputs + (mean, rstd); parameter
+// gradients are column reductions over M, accumulated per CTA in registers / shared memory and
+// flushed with one atomicAdd per column per CTA.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/sea_b200.h"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace sea {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------ LN / AdaLN backward
+struct NormBwdDev {
+  const float* dy; long long lddy;
+  const float* x; long long ldx;
+  const float* stats;
+  const float* weight;
+  const float* cond; long long ldc;
+  const float* dres; long long lddres;
+  float* dx; long long lddx;
+  __nv_bfloat16* dx_bf16; long long lddxb;
+  float* dweight; float* dbias;
+  float* dcond; long long lddc; int dcond_accumulate;
+  int M, d, kind, rows_per_cta;
+};
+
+constexpr int kNormMaxChunks = 16;
+
+template <int CH>
+__global__ void __launch_bounds__(256) norm_bwd_kernel(const NormBwdDev a) {
+  extern __shared__ float red[];  // [8 warps][d] x2 (dweight, dbias partials; each lane owns its columns)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* rw = red;
+  float* rb = red + 8 * a.d;
+  const bool want_param = (a.dweight != nullptr) || (a.dbias != nullptr);
+  if (want_param) {
+    for (int i = threadIdx.x; i < 16 * a.d; i += 256) red[i] = 0.f;
+    __syncthreads();
+  }
+  const int row_begin = blockIdx.x * a.rows_per_cta;
+  const int row_end = min(a.M, row_begin + a.rows_per_cta);
+  const float inv_d = 1.0f / a.d;
+  for (int m = row_begin + warp; m < row_end; m += 8) {
+    const float mean = a.stats[2 * m], rstd = a.stats[2 * m + 1];
+    const float* xr = a.x + static_cast<long long>(m) * a.ldx;
+    const float* dyr = a.dy + static_cast<long long>(m) * a.lddy;
+    float4 xh[CH], g[CH];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = c * 128 + lane * 4;
+      if (col < a.d) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + col);
+        const float4 dv = *reinterpret_cast<const float4*>(dyr + col);
+        float4 w = __ldg(reinterpret_cast<const float4*>(a.weight + col));
+        if (a.kind == SEA_NORM_ADALN) {
+          const float4 cw = *reinterpret_cast<const float4*>(a.cond + static_cast<long long>(m) * a.ldc + col);
+          w.x += cw.x + 1.f; w.y += cw.y + 1.f; w.z += cw.z + 1.f; w.w += cw.w + 1.f;
+        }
+        float4 h;
+        h.x = (xv.x - mean) * rstd; h.y = (xv.y - mean) * rstd;
+        h.z = (xv.z - mean) * rstd; h.w = (xv.w - mean) * rstd;
+        float4 gg;
+        gg.x = dv.x * w.x; gg.y = dv.y * w.y; gg.z = dv.z * w.z; gg.w = dv.w * w.w;
+        xh[c] = h; g[c] = gg;
+        s1 += gg.x + gg.y + gg.z + gg.w;
+        s2 += gg.x * h.x + gg.y * h.y + gg.z * h.z + gg.w * h.w;
+        // d gamma_eff = dy * xhat, d beta_eff = dy
+        const float4 dgam = make_float4(dv.x * h.x, dv.y * h.y, dv.z * h.z, dv.w * h.w);
+        if (want_param) {
+          float4* pw = reinterpret_cast<float4*>(rw + warp * a.d + col);
+          float4* pb = reinterpret_cast<float4*>(rb + warp * a.d + col);
+          float4 t = *pw;
+          t.x += dgam.x; t.y += dgam.y; t.z += dgam.z; t.w += dgam.w;
+          *pw = t;
+          t = *pb;
+          t.x += dv.x; t.y += dv.y; t.z += dv.z; t.w += dv.w;
+          *pb = t;
+        }
+        if (a.dcond) {
+          float* dc = a.dcond + static_cast<long long>(m) * a.lddc;
+          float4 o1 = dgam, o2 = dv;
+          if (a.dcond_accumulate) {
+            const float4 p1 = *reinterpret_cast<const float4*>(dc + col);
+            const float4 p2 = *reinterpret_cast<const float4*>(dc + a.d + col);
+            o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+            o2.x += p2.x; o2.y += p2.y; o2.z += p2.z; o2.w += p2.w;
+          }
+          *reinterpret_cast<float4*>(dc + col) = o1;
+          *reinterpret_cast<float4*>(dc + a.d + col) = o2;
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = c * 128 + lane * 4;
+      if (col < a.d) {
+        float4 o;
+        o.x = rstd * (g[c].x - c1 - xh[c].x * c2);
+        o.y = rstd * (g[c].y - c1 - xh[c].y * c2);
+        o.z = rstd * (g[c].z - c1 - xh[c].z * c2);
+        o.w = rstd * (g[c].w - c1 - xh[c].w * c2);
+        if (a.dres) {
+          const float4 r = *reinterpret_cast<const float4*>(a.dres + static_cast<long long>(m) * a.lddres + col);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (a.dx) *reinterpret_cast<float4*>(a.dx + static_cast<long long>(m) * a.lddx + col) = o;
+        if (a.dx_bf16) {
+          uint2 pk;
+          pk.x = ptx::pack_bf16(o.x, o.y);
+          pk.y = ptx::pack_bf16(o.z, o.w);
+          *reinterpret_cast<uint2*>(a.dx_bf16 + static_cast<long long>(m) * a.lddxb + col) = pk;
+        }
+      }
+    }
+  }
+  // cross-warp reduction of the column partials, then one atomic per column per CTA
+  if (!want_param) return;
+  __syncthreads();
+  for (int col = threadIdx.x; col < a.d; col += blockDim.x) {
+    float sw = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      sw += rw[w * a.d + col];
+      sb += rb[w * a.d + col];
+    }
+    if (a.dweight) atomicAdd(a.dweight + col, sw);
+    if (a.dbias) atomicAdd(a.dbias + col, sb);
+  }
+}
+
+// ------------------------------------------------------------- LayerNorm(H)+GELU backward (K6)
+// dh = LN'(GELU'(u) * dg);  dweight/dbias of the inner nn.LayerNorm accumulate in shared memory.
+template <int kDummy>
+__global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, long long lddg,
+                                                          const __nv_bfloat16* __restrict__ h, long long ldh,
+                                                          const float* __restrict__ stats,
+                                                          const float* __restrict__ weight,
+                                                          const float* __restrict__ bias,
+                                                          __nv_bfloat16* __restrict__ dh, long long lddh,
+                                                          float* __restrict__ dweight, float* __restrict__ dbias,
+                                                          int M, int H, int rows_per_cta) {
+  constexpr int kMaxChunks = 8;
+  extern __shared__ float acc[];  // [2][H]
+  __shared__ float red[2][8];
+  __shared__ float bc[2];
+  const int tid = threadIdx.x;
+  float* aw = acc;
+  float* ab = acc + H;
+  for (int i = tid; i < 2 * H; i += 256) acc[i] = 0.f;
+  __syncthreads();
+  const int row_begin = blockIdx.x * rows_per_cta;
+  const int row_end = min(M, row_begin + rows_per_cta);
+  const float inv_h = 1.0f / H;
+  for (int m = row_begin; m < row_end; ++m) {
+    const float mean = stats[2 * m], rstd = stats[2 * m + 1];
+    float hh[kMaxChunks][8], dhh[kMaxChunks][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 256 + tid) * 8;
+      if (col < H) {
+        const uint4 hr = *reinterpret_cast<const uint4*>(h + static_cast<long long>(m) * ldh + col);
+        const uint4 gr = *reinterpret_cast<const uint4*>(dg + static_cast<long long>(m) * lddg + col);
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&hr);
+        const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&gr);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 hv = __bfloat1622float2(hp[q]);
+          const float2 gv = __bfloat1622float2(gp[q]);
+          const float hv2[2] = {hv.x, hv.y}, gv2[2] = {gv.x, gv.y};
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = 2 * q + e;
+            const float xhat = (hv2[e] - mean) * rstd;
+            const float u = xhat * ww[k] + bb[k];
+            const float dgu = gv2[e] * ptx::gelu_erf_grad(u);
+            aw[col + k] += dgu * xhat;   // this thread is the only writer of these columns
+            ab[col + k] += dgu;
+            const float dxh = dgu * ww[k];
+            hh[c][k] = xhat;
+            dhh[c][k] = dxh;
+            s1 += dxh;
+            s2 += dxh * xhat;
+          }
+        }
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = s2; }
+    __syncthreads();
+    if (tid < 32) {
+      float t1 = tid < 8 ? red[0][tid] : 0.f, t2 = tid < 8 ? red[1][tid] : 0.f;
+      t1 = warp_sum(t1); t2 = warp_sum(t2);
+      if (tid == 0) { bc[0] = t1 * inv_h; bc[1] = t2 * inv_h; }
+    }
+    __syncthreads();
+    const float c1 = bc[0], c2 = bc[1];
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 256 + tid) * 8;
+      if (col < H) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = rstd * (dhh[c][k] - c1 - hh[c][k] * c2);
+        uint4 pk;
+        pk.x = ptx::pack_bf16(o[0], o[1]); pk.y = ptx::pack_bf16(o[2], o[3]);
+        pk.z = ptx::pack_bf16(o[4], o[5]); pk.w = ptx::pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dh + static_cast<long long>(m) * lddh + col) = pk;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < H; i += 256) {
+    atomicAdd(dweight + i, aw[i]);
+    atomicAdd(dbias + i, ab[i]);
+  }
+}
+
+// --------------------------------------------------------- AdaLN cond_mlp.0 + SiLU backward
+// dpre = dh * silu'(w1*ib + b1);  dw1[j,c] += sum_m dpre*ib[m,c];  db1[j] += sum_m dpre
+__global__ void __launch_bounds__(256) adaln_hidden_bwd_kernel(const float* __restrict__ dh, long long lddh,
+                                                               const float* __restrict__ ib, int M, int ib_num,
+                                                               const float* __restrict__ w1,
+                                                               const float* __restrict__ b1, int n,
+                                                               float* __restrict__ dw1, float* __restrict__ db1,
+                                                               int rows_per_cta) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float wj[4], aw[4] = {0.f, 0.f, 0.f, 0.f}, ab = 0.f;
+  for (int c = 0; c < ib_num && c < 4; ++c) wj[c] = w1[j * ib_num + c];
+  const float bj = b1[j];
+  for (int m = r0; m < r1; ++m) {
+    float pre = bj;
+    for (int c = 0; c < ib_num && c < 4; ++c) pre = fmaf(wj[c], ib[static_cast<long long>(m) * ib_num + c], pre);
+    const float sig = 1.0f / (1.0f + __expf(-pre));
+    const float dsilu = sig * (1.0f + pre * (1.0f - sig));
+    const float dp = dh[static_cast<long long>(m) * lddh + j] * dsilu;
+    ab += dp;
+    for (int c = 0; c < ib_num && c < 4; ++c) aw[c] = fmaf(dp, ib[static_cast<long long>(m) * ib_num + c], aw[c]);
+  }
+  atomicAdd(db1 + j, ab);
+  for (int c = 0; c < ib_num && c < 4; ++c) atomicAdd(dw1 + j * ib_num + c, aw[c]);
+}
+
+// ------------------------------------------------------------------------------ TIPI backward
+// (A) dW3[n,k] += sum_m dx[m,n] g[m,k];  db3[n] += sum_m dx[m,n]        (thread per column n)
+__global__ void __launch_bounds__(256) tipi_bwd_w_kernel(const float* __restrict__ dx, long long lddx,
+                                                         const float* __restrict__ g, int M, int E, int hid,
+                                                         float* __restrict__ dw3, float* __restrict__ db3,
+                                                         int rows_per_cta) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= E) return;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float aw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ab = 0.f;
+  for (int m = r0; m < r1; ++m) {
+    const float v = dx[static_cast<long long>(m) * lddx + n];
+    ab += v;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < hid) aw[k] = fmaf(v, g[static_cast<long long>(m) * hid + k], aw[k]);
+  }
+  atomicAdd(db3 + n, ab);
+  for (int k = 0; k < hid && k < 8; ++k) atomicAdd(dw3 + n * hid + k, aw[k]);
+}
+
+// (B) dg[m,k] = sum_streams sum_n dx_s[m,n] W3[n,k]; then GELU'/LayerNorm' over hid (<= 8) and
+//     the gradients of Linear(ib_num, hid) + LayerNorm(hid).  One warp per row; `u` is the saved
+//     pre-LayerNorm activation, `stats` its (mean, rstd).
+struct TipiBwdDev {
+  const float* dx[SEA_MAX_STREAMS]; long long lddx; int n_streams;
+  const float* w3; const float* u; const float* stats; const float* ib;
+  const float* ln_w; const float* ln_b;
+  float *dw0, *db0, *dlnw, *dlnb;
+  int M, E, hid, ib_num;
+};
+__global__ void __launch_bounds__(256) tipi_bwd_g_kernel(const TipiBwdDev a) {
+  // CTA-level accumulators: db0[8] | dlnw[8] | dlnb[8] | dw0[8][4]
+  __shared__ float acc[24 + 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (threadIdx.x < 56) acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  if (m < a.M) {
+    float dg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < a.n_streams; ++s) {
+      const float* dxr = a.dx[s] + static_cast<long long>(m) * a.lddx;
+      for (int n = lane; n < a.E; n += 32) {
+        const float v = dxr[n];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < a.hid) dg[k] = fmaf(v, __ldg(a.w3 + n * a.hid + k), dg[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dg[k] = warp_sum(dg[k]);
+    if (lane == 0) {
+      const float mean = a.stats[2 * m], rstd = a.stats[2 * m + 1];
+      float xh[8], dxh[8], s1 = 0.f, s2 = 0.f;
+      for (int k = 0; k < a.hid; ++k) {
+        xh[k] = (a.u[static_cast<long long>(m) * a.hid + k] - mean) * rstd;
+        const float nrm = xh[k] * a.ln_w[k] + a.ln_b[k];
+        const float dgu = dg[k] * ptx::gelu_erf_grad(nrm);
+        atomicAdd(&acc[8 + k], dgu * xh[k]);
+        atomicAdd(&acc[16 + k], dgu);
+        dxh[k] = dgu * a.ln_w[k];
+        s1 += dxh[k];
+        s2 += dxh[k] * xh[k];
+      }
+      const float c1 = s1 / a.hid, c2 = s2 / a.hid;
+      for (int k = 0; k < a.hid; ++k) {
+        const float du = rstd * (dxh[k] - c1 - xh[k] * c2);
+        atomicAdd(&acc[k], du);
+        for (int c = 0; c < a.ib_num && c < 4; ++c)
+          atomicAdd(&acc[24 + k * 4 + c], du * a.ib[static_cast<long long>(m) * a.ib_num + c]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < a.hid) {
+    const int k = threadIdx.x;
+    atomicAdd(a.db0 + k, acc[k]);
+    atomicAdd(a.dlnw + k, acc[8 + k]);
+    atomicAdd(a.dlnb + k, acc[16 + k]);
+    for (int c = 0; c < a.ib_num && c < 4; ++c) atomicAdd(a.dw0 + k * a.ib_num + c, acc[24 + k * 4 + c]);
+  }
+}
+
+}  // namespace
+}  // namespace sea
+
+using namespace sea;
+
+static int rows_per_cta_for(int M, int granule) {
+  int r = (M + 2 * 148 - 1) / (2 * 148);
+  r = ((r + granule - 1) / granule) * granule;
+  return r < granule ? granule : r;
+}
+
+extern "C" int sea_norm_bwd(const sea_norm_bwd_args* a, sea_stream_t stream) {
+  if (!a || !a->dy || !a->x || !a->stats || !a->weight || a->M <= 0 || a->d <= 0) return SEA_ERR_INVALID;
+  if ((a->d % 4) || a->d > kNormMaxChunks * 128) return SEA_ERR_UNSUPPORTED;
+  if (a->kind == SEA_NORM_ADALN && !a->cond) return SEA_ERR_INVALID;
+  if (!a->dx && !a->dx_bf16) return SEA_ERR_INVALID;
+  if ((a->lddy % 4) || (a->ldx % 4) || (a->dx && (a->lddx % 4)) || (a->dres && (a->lddres % 4)))
+    return SEA_ERR_INVALID;
+  NormBwdDev d;
+  d.dy = a->dy; d.lddy = a->lddy; d.x = a->x; d.ldx = a->ldx; d.stats = a->stats;
+  d.weight = a->weight; d.cond = a->cond; d.ldc = a->ldc;
+  d.dres = a->dres; d.lddres = a->lddres;
+  d.dx = a->dx; d.lddx = a->lddx;
+  d.dx_bf16 = static_cast<__nv_bfloat16*>(a->dx_bf16); d.lddxb = a->lddx_bf16;
+  d.dweight = a->dweight; d.dbias = a->dbias;
+  d.dcond = a->dcond; d.lddc = a->lddcond; d.dcond_accumulate = a->dcond_accumulate;
+  d.M = a->M; d.d = a->d; d.kind = a->kind;
+  d.rows_per_cta = rows_per_cta_for(a->M, 8);
+  const int grid = (a->M + d.rows_per_cta - 1) / d.rows_per_cta;
+  const size_t smem = sizeof(float) * 16 * a->d;
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    SEA_CUDA_OK(cudaFuncSetAttribute(norm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4));
+    SEA_CUDA_OK(cudaFuncSetAttribute(norm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4));
+    SEA_CUDA_OK(cudaFuncSetAttribute(norm_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4));
+    attr_set[dev] = true;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->d <= 512) norm_bwd_kernel<4><<<grid, 256, smem, s>>>(d);
+  else if (a->d <= 1024) norm_bwd_kernel<8><<<grid, 256, smem, s>>>(d);
+  else norm_bwd_kernel<16><<<grid, 256, smem, s>>>(d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_ln_gelu_bwd(const sea_ln_gelu_bwd_args* a, sea_stream_t stream) {
+  if (!a || !a->dg || !a->h || !a->stats || !a->weight || !a->bias || !a->dh || !a->dweight || !a->dbias)
+    return SEA_ERR_INVALID;
+  if (a->M <= 0 || a->H <= 0 || (a->H % 8) || a->H > 16384) return SEA_ERR_UNSUPPORTED;
+  if ((a->lddg % 8) || (a->ldh % 8) || (a->lddh % 8)) return SEA_ERR_INVALID;
+  const int rows = rows_per_cta_for(a->M, 1);
+  const int grid = (a->M + rows - 1) / rows;
+  const size_t smem = sizeof(float) * 2 * a->H;
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    SEA_CUDA_OK(cudaFuncSetAttribute(ln_gelu_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
+    attr_set[dev] = true;
+  }
+  ln_gelu_bwd_kernel<0><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a->dg), a->lddg, static_cast<const __nv_bfloat16*>(a->h), a->ldh,
+      a->stats, a->weight, a->bias, static_cast<__nv_bfloat16*>(a->dh), a->lddh, a->dweight, a->dbias,
+      a->M, a->H, rows);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_adaln_hidden_bwd(const float* dh, int64_t lddh, const float* ib, int M, int ib_num,
+                                    const float* w1, const float* b1, int n, float* dw1, float* db1,
+                                    sea_stream_t stream) {
+  if (!dh || !ib || !w1 || !b1 || !dw1 || !db1 || M <= 0 || n <= 0) return SEA_ERR_INVALID;
+  if (ib_num < 1 || ib_num > 4) return SEA_ERR_UNSUPPORTED;
+  const int rows = rows_per_cta_for(M, 8) * 4;
+  dim3 grid((n + 255) / 256, (M + rows - 1) / rows);
+  adaln_hidden_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      dh, lddh, ib, M, ib_num, w1, b1, n, dw1, db1, rows);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_tipi_bwd(const sea_tipi_bwd_args* a, sea_stream_t stream) {
+  if (!a || a->n_streams < 1 || a->n_streams > SEA_MAX_STREAMS || a->M <= 0 || a->E <= 0) return SEA_ERR_INVALID;
+  if (a->hid < 1 || a->hid > 8 || a->ib_num < 1 || a->ib_num > 4) return SEA_ERR_UNSUPPORTED;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int rows = rows_per_cta_for(a->M, 8) * 4;
+  dim3 grid((a->E + 255) / 256, (a->M + rows - 1) / rows);
+  TipiBwdDev d{};
+  for (int i = 0; i < a->n_streams; ++i) {
+    if (!a->dx[i]) return SEA_ERR_INVALID;
+    d.dx[i] = a->dx[i];
+    tipi_bwd_w_kernel<<<grid, 256, 0, s>>>(a->dx[i], a->lddx, a->g, a->M, a->E, a->hid, a->dw3, a->db3, rows);
+  }
+  d.lddx = a->lddx; d.n_streams = a->n_streams;
+  d.w3 = a->w3; d.u = a->u; d.stats = a->stats; d.ib = a->ib; d.ln_w = a->ln_w; d.ln_b = a->ln_b;
+  d.dw0 = a->dw0; d.db0 = a->db0; d.dlnw = a->dlnw; d.dlnb = a->dlnb;
+  d.M = a->M; d.E = a->E; d.hid = a->hid; d.ib_num = a->ib_num;
+  tipi_bwd_g_kernel<<<(a->M + 7) / 8, 256, 0, s>>>(d);
+  return static_cast<int>(cudaGetLastError());
+}

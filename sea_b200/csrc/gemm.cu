@@ -395,7 +395,7 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   if (k_chunk < 0 || (k_chunk % BK) != 0) return SEA_ERR_INVALID;
   if (probs == nullptr || num_problems < 1 || num_problems > kMaxGroups) return SEA_ERR_INVALID;
   if (M <= 0 || N <= 0 || K <= 0) return SEA_ERR_INVALID;
-  if ((N % 8) != 0 || (K % 8) != 0) return SEA_ERR_UNSUPPORTED;
+  if ((N % 8) != 0) return SEA_ERR_UNSUPPORTED;  // K may be ragged: TMA zero-fills the tail
   int rc = ensure_init();
   if (rc != SEA_OK) return rc;
 

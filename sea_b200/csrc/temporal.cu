@@ -26,6 +26,30 @@ namespace sea {
 
 thread_local int g_launches = 0;
 
+// ---------------------------------------------------------------------------------- profiler
+// Optional per-launch CUDA-event timing on the launching stream (bench.py's roofline leg).
+namespace {
+struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+
+ProfScope::ProfScope(cudaStream_t s, int cat, double work) : s_(s), idx_(-1) {
+  if (!g_prof_on) return;
+  ProfRec r{prof_event(), prof_event(), cat, work};
+  cudaEventRecord(r.a, s_);
+  g_prof.push_back(r);
+  idx_ = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, s_);
+}
+
 // ------------------------------------------------------------------------------ cache layout
 static PackedLinear take_linear(Arena& ar, int N, int K, int kf, bool training) {
   PackedLinear p{};
@@ -112,6 +136,27 @@ static int refresh_norm(const sea_norm_params& n, const PackedLinear& c2, int d2
 using namespace sea;
 
 extern "C" int sea_last_launch_count(void) { return g_launches; }
+
+extern "C" void sea_profile_begin(void) {
+  for (auto& r : g_prof) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+}
+
+extern "C" int sea_profile_end(sea_profile_summary* out) {
+  g_prof_on = false;
+  if (!out) return SEA_ERR_INVALID;
+  for (int c = 0; c < SEA_PROF_NUM; ++c) { out->ms[c] = 0; out->work[c] = 0; out->launches[c] = 0; }
+  for (auto& r : g_prof) {
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, r.a, r.b);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    out->ms[r.cat] += ms; out->work[r.cat] += r.work; out->launches[r.cat] += 1;
+  }
+  return SEA_OK;
+}
 
 extern "C" size_t sea_temporal_cache_bytes(const sea_temporal_desc* d, int training) {
   if (!d) return 0;
@@ -253,7 +298,10 @@ int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, c
       pa.src_f32 = static_cast<const float*>(in[g].a);
       pa.ld = in[g].lda; pa.R = Mrows; pa.C = K; pa.split = 1; pa.act = in[g].act_on_load;
       pa.dst = c.tape->packA[g]; pa.ld_dst = 6LL * K;
-      SEA_TRY(sea_pack_operand(&pa, reinterpret_cast<sea_stream_t>(c.s)));
+      {
+        ProfScope prof(c.s, SEA_PROF_ELEMWISE, 4.0 * Mrows * K + 12.0 * Mrows * K);
+        SEA_TRY(sea_pack_operand(&pa, reinterpret_cast<sea_stream_t>(c.s)));
+      }
       ++g_launches;
       p.a = c.tape->packA[g]; p.lda = 6LL * K;
     } else {
@@ -280,6 +328,7 @@ int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, c
     }
   }
   ++g_launches;
+  ProfScope prof(c.s, SEA_PROF_GEMM, 2.0 * Mrows * static_cast<double>(N) * K * n);
   if (c.fp32) {
     // fresh accumulator every 512 columns of K' so the tensor core's non-RN accumulation cannot drift
     bool can_chunk = true;
@@ -309,6 +358,10 @@ int norm_op(Ctx& c, int kind, const sea_norm_params& np, const float* cond, cons
   else { a.y_bf16 = y_act; a.ldy_bf16 = dim; }
   a.stats = stats;
   ++g_launches;
+  const double esz = c.fp32 ? 4.0 : 2.0;
+  ProfScope prof(c.s, SEA_PROF_ELEMWISE,
+                 static_cast<double>(c.M) * dim * (4.0 + (y_f32 ? 4.0 : esz) + (tipi ? 4.0 : 0.0) +
+                                                   (kind == SEA_NORM_ADALN ? 8.0 : 0.0)));
   return sea_norm_fwd(&a, reinterpret_cast<sea_stream_t>(c.s));
 }
 
@@ -322,6 +375,8 @@ int attention_op(Ctx& c, const void* q, long long ldq, const void* k, const void
   a.scale = 1.0f / sqrtf(static_cast<float>(head_dim));
   a.prec = c.fp32 ? SEA_PREC_FP32 : SEA_PREC_BF16;
   ++g_launches;
+  ProfScope prof(c.s, SEA_PROF_ATTN,
+                 2.0 * c.B * c.d->n_heads * static_cast<double>(c.T) * c.T * head_dim);
   return sea_attention_fwd(&a, reinterpret_cast<sea_stream_t>(c.s));
 }
 
@@ -350,6 +405,10 @@ extern "C" size_t sea_temporal_workspace_bytes(const sea_temporal_desc* d, int B
   Arena ar{nullptr};
   Tape t;
   layout_tape(d, B, T, training != 0, ar, t);
+  if (training) {
+    BwdTape bt;
+    layout_bwd_tape(d, B, T, ar, bt);
+  }
   return ar.off + 256;
 }
 
@@ -543,7 +602,10 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
       else { a.h_bf16 = lt.s[i].h; a.g_bf16 = lt.s[i].gh; }
       a.ldh = H; a.ldg = H; a.M = M; a.H = H;
       a.weight = bp.s[i].mlp_ln_w.p; a.bias = bp.s[i].mlp_ln_b.p; a.stats = lt.s[i].stH;
-      SEA_TRY(sea_ln_gelu_fwd(&a, st));
+      {
+        ProfScope prof(c.s, SEA_PROF_ELEMWISE, 2.0 * esz * M * static_cast<double>(H));
+        SEA_TRY(sea_ln_gelu_fwd(&a, st));
+      }
       ++g_launches;
     }
     for (int i = 0; i < V; ++i) {

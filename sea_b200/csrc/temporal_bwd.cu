@@ -1,0 +1,474 @@
+// Backward pass of the temporal executor (the reference gets it from autograd,
+// train/train_temporal.py:257).  Reads the tape the forward left in `workspace`, accumulates (+=)
+// parameter gradients into the `g` pointers of the descriptor and optionally writes dL/dx.
+//
+// Every nn.Linear y = a W^T + b contributes three tensor-core GEMMs / reductions:
+//   dgrad  da = dy · W          gemm_tn(A = dy [M,N],     B = W^T [K,N])   (W^T cached at refresh)
+//   wgrad  dW += dy^T · a       gemm_tn(A = dy^T [N,M],   B = a^T [K,M])   (operands transposed
+//                                                                            by the packing kernel)
+//   dbias  db += colsum(dy)
+// GELU' of the exchange branch is fused into the dgrad epilogue; RoPE is undone inside the
+// attention backward; LN / AdaLN / LN+GELU / TIPI have dedicated backward kernels.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/sea_b200.h"
+#include "internal.h"
+#include "temporal_internal.h"
+
+namespace sea {
+namespace {
+
+#define SEA_TRY(expr)              \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != SEA_OK) return _rc; \
+  } while (0)
+
+struct BCtx {
+  Ctx c;
+  const float* ib;
+  BwdTape* bt;
+  long long Mp;  // M rounded up to 8 (pitch of transposed operands)
+  sea_stream_t st() const { return reinterpret_cast<sea_stream_t>(c.s); }
+};
+
+int transpose_bf16(BCtx& b, const bf16* src, long long ld, int R, int Ccols, bf16* dst) {
+  sea_pack_args a{};
+  a.src_bf16 = src; a.ld = ld; a.R = R; a.C = Ccols; a.transpose = 1;
+  a.dst = dst; a.ld_dst = b.Mp;
+  ++g_launches;
+  ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, 4.0 * R * Ccols);
+  return sea_pack_operand(&a, b.st());
+}
+
+int cast_f32(BCtx& b, const float* src, long long ld, int R, int Ccols, bf16* dst, long long ldd, int transpose) {
+  sea_pack_args a{};
+  a.src_f32 = src; a.ld = ld; a.R = R; a.C = Ccols; a.transpose = transpose;
+  a.dst = dst; a.ld_dst = ldd;
+  ++g_launches;
+  ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, 6.0 * R * Ccols);
+  return sea_pack_operand(&a, b.st());
+}
+
+int colsum(BCtx& b, const float* f32, const bf16* b16, long long ld, int M, int N, float* out) {
+  if (!out) return SEA_OK;
+  ++g_launches;
+  ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, (f32 ? 4.0 : 2.0) * M * N);
+  return sea_colsum_accumulate(f32, b16, ld, M, N, out, b.st());
+}
+
+int gemm(BCtx& b, int n, sea_gemm_problem* probs, int M, int N, int K) {
+  ++g_launches;
+  ProfScope prof(b.c.s, SEA_PROF_GEMM, 2.0 * M * static_cast<double>(N) * K * n);
+  return sea_gemm_bf16_tn(n, probs, M, N, K, b.st());
+}
+
+// One Linear's backward for up to V streams at once (same shapes).
+struct LinB {
+  const bf16* dy; long long lddy;   // [M,N] gradient wrt the Linear's output
+  const bf16* a; long long lda;     // [M,K] saved input
+  const PackedLinear* W;
+  float* dW; float* db;             // accumulate; may be NULL (frozen)
+  int n_split;                      // fused Linear: N is n_split blocks with separate dW/db
+  float* dW_split[3]; float* db_split[3];
+  bool dgrad;
+  float* da_f32; long long ld_da;
+  const float* da_res; long long ld_res;   // added to da (skip connections / accumulation)
+  bf16* da_b16; long long ld_dab;
+  const bf16* gelu_of; long long ld_gelu;  // dgrad epilogue multiplies by gelu'(gelu_of)
+};
+
+int linear_bwd(BCtx& b, int n, LinB* L) {
+  const int M = b.c.M;
+  const int N = L[0].W->N, K = L[0].W->K;
+  sea_gemm_problem probs[SEA_MAX_STREAMS];
+  // ---- wgrad + dbias
+  bool any_w = false;
+  for (int g = 0; g < n; ++g) any_w |= (L[g].dW != nullptr) || (L[g].n_split > 0 && L[g].dW_split[0] != nullptr);
+  if (any_w) {
+    for (int g = 0; g < n; ++g) {
+      SEA_TRY(transpose_bf16(b, L[g].dy, L[g].lddy, M, N, b.bt->tr_dy[g]));
+      SEA_TRY(transpose_bf16(b, L[g].a, L[g].lda, M, K, b.bt->tr_a[g]));
+    }
+    const int parts = L[0].n_split > 0 ? L[0].n_split : 1;
+    const int Np = N / parts;
+    for (int part = 0; part < parts; ++part) {
+      for (int g = 0; g < n; ++g) {
+        sea_gemm_problem& p = probs[g];
+        p = sea_gemm_problem{};
+        p.a = b.bt->tr_dy[g] + static_cast<long long>(part) * Np * b.Mp; p.lda = b.Mp;
+        p.b = b.bt->tr_a[g]; p.ldb = b.Mp;
+        float* dW = parts > 1 ? L[g].dW_split[part] : L[g].dW;
+        p.epi.out_f32 = dW; p.epi.ld_out_f32 = K;
+        p.epi.residual = dW; p.epi.ld_residual = K;
+      }
+      SEA_TRY(gemm(b, n, probs, Np, K, M));
+      for (int g = 0; g < n; ++g) {
+        float* db = parts > 1 ? L[g].db_split[part] : L[g].db;
+        SEA_TRY(colsum(b, nullptr, L[g].dy + part * Np, L[g].lddy, M, Np, db));
+      }
+    }
+  }
+  // ---- dgrad
+  if (L[0].dgrad) {
+    for (int g = 0; g < n; ++g) {
+      sea_gemm_problem& p = probs[g];
+      p = sea_gemm_problem{};
+      p.a = L[g].dy; p.lda = L[g].lddy;
+      p.b = L[g].W->wT; p.ldb = L[g].W->ldwT;
+      p.epi.residual = L[g].da_res; p.epi.ld_residual = L[g].ld_res;
+      p.epi.gelu_grad_of = L[g].gelu_of; p.epi.ld_gelu = L[g].ld_gelu;
+      p.epi.out_f32 = L[g].da_f32; p.epi.ld_out_f32 = L[g].ld_da;
+      p.epi.out_pre_bf16 = L[g].da_b16; p.epi.ld_out_pre_bf16 = L[g].ld_dab;
+    }
+    SEA_TRY(gemm(b, n, probs, M, K, N));
+  }
+  return SEA_OK;
+}
+
+int norm_bwd(BCtx& b, int kind, const sea_norm_params& np, const float* cond, const float* dy,
+             long long lddy, const float* x, long long ldx, const float* stats, int dim,
+             const float* dres, long long lddres, float* dx, long long lddx, bf16* dxb, float* dcond,
+             int dcond_acc) {
+  sea_norm_bwd_args a{};
+  a.dy = dy; a.lddy = lddy; a.x = x; a.ldx = ldx; a.stats = stats;
+  a.M = b.c.M; a.d = dim; a.kind = kind;
+  a.weight = np.weight.p; a.cond = cond; a.ldc = 2LL * dim;
+  a.dres = dres; a.lddres = lddres;
+  a.dx = dx; a.lddx = lddx; a.dx_bf16 = dxb; a.lddx_bf16 = dim;
+  a.dweight = np.weight.g;
+  a.dbias = kind == SEA_NORM_ADALN ? np.bias.g : nullptr;
+  a.dcond = kind == SEA_NORM_ADALN ? dcond : nullptr; a.lddcond = 2LL * dim; a.dcond_accumulate = dcond_acc;
+  ++g_launches;
+  ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, 16.0 * b.c.M * dim);
+  return sea_norm_bwd(&a, b.st());
+}
+
+// AdaLN cond_mlp backward for n modules of width d2 = 2*dim (grouped across streams).
+int cond_bwd(BCtx& b, int n, const sea_norm_params* const* np, void* const* hid, float* const* dcond,
+             const PackedLinear* const* W, int d2) {
+  const int M = b.c.M;
+  LinB L[SEA_MAX_STREAMS];
+  for (int g = 0; g < n; ++g) {
+    SEA_TRY(cast_f32(b, dcond[g], d2, M, d2, b.bt->dcb[g], d2, 0));
+    LinB& l = L[g];
+    l = LinB{};
+    l.dy = b.bt->dcb[g]; l.lddy = d2;
+    l.a = static_cast<const bf16*>(hid[g]); l.lda = d2;
+    l.W = W[g];
+    l.dW = np[g]->c2_w.g; l.db = nullptr;  // bias from the fp32 dcond below
+    l.dgrad = true;
+    l.da_f32 = b.bt->dhid[g]; l.ld_da = d2;
+  }
+  SEA_TRY(linear_bwd(b, n, L));
+  for (int g = 0; g < n; ++g) {
+    SEA_TRY(colsum(b, dcond[g], nullptr, d2, M, d2, np[g]->c2_b.g));
+    if (np[g]->c0_w.g && np[g]->c0_b.g) {
+      ++g_launches;
+      SEA_TRY(sea_adaln_hidden_bwd(b.bt->dhid[g], d2, b.ib, M, b.c.d->ib_num, np[g]->c0_w.p, np[g]->c0_b.p,
+                                   d2, np[g]->c0_w.g, np[g]->c0_b.g, b.st()));
+    }
+  }
+  return SEA_OK;
+}
+
+int attention_bwd(BCtx& b, const bf16* q, long long ldq, const bf16* k, const bf16* v, long long ldkv,
+                  const bf16* o, const bf16* d_o, long long ldo, const float* lse, bf16* dq, long long lddq,
+                  bf16* dk, bf16* dv, long long lddkv, int hd, const float* rope) {
+  sea_attn_bwd_args a{};
+  a.q = q; a.k = k; a.v = v; a.o = o; a.d_o = d_o;
+  a.ldq = ldq; a.ldk = ldkv; a.ldv = ldkv; a.ldo = ldo; a.lddo = ldo;
+  a.lse = lse; a.delta = b.bt->delta;
+  a.dq = dq; a.dk = dk; a.dv = dv; a.lddq = lddq; a.lddk = lddkv; a.lddv = lddkv;
+  a.B = b.c.B; a.T = b.c.T; a.n_heads = b.c.d->n_heads; a.head_dim = hd; a.src_len = b.c.d->src_len;
+  a.scale = 1.0f / sqrtf(static_cast<float>(hd));
+  a.prec = SEA_PREC_BF16;
+  a.rope_table = rope;
+  g_launches += 3;
+  ProfScope prof(b.c.s, SEA_PROF_ATTN, 5.0 * b.c.B * b.c.d->n_heads * static_cast<double>(b.c.T) * b.c.T * hd);
+  return sea_attention_bwd(&a, b.st());
+}
+
+}  // namespace
+
+void layout_bwd_tape(const sea_temporal_desc* d, int B, int T, Arena& ar, BwdTape& t) {
+  const size_t M = static_cast<size_t>(B) * T, Mp = (M + 7) & ~static_cast<size_t>(7);
+  const size_t E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
+  const int V = d->num_streams;
+  const bool ada = d->norm_kind == SEA_NORM_ADALN;
+  auto f32 = [&](size_t n) { return static_cast<float*>(ar.take(n * 4)); };
+  auto b16 = [&](size_t n) { return static_cast<bf16*>(ar.take(n * 2)); };
+  const size_t wide = H > 3 * E ? H : 3 * E;
+  for (int i = 0; i < V; ++i) {
+    BwdStream& s = t.s[i];
+    s.dxout = f32(M * E); s.dxoutb = b16(M * E);
+    s.dx3 = f32(M * E); s.dx3b = b16(M * E);
+    s.dg = b16(M * H); s.dh = b16(M * H);
+    s.dn2 = f32(M * E);
+    s.dx2 = f32(M * E); s.dx2b = b16(M * E);
+    s.dxp = f32(M * E); s.dxpb = b16(M * E);
+    s.dp = b16(M * Dd); s.da = b16(M * Dd); s.dq = b16(M * Dd); s.dkv = b16(M * 2 * Dd);
+    s.dnpre = f32(M * Dd); s.dnpost = f32(M * Dd);
+    s.ddn = f32(M * Dd); s.ddnb = b16(M * Dd);
+    s.dx1 = f32(M * E); s.dx1b = b16(M * E);
+    s.dao = b16(M * E); s.dqkv = b16(M * 3 * E);
+    s.dn0 = f32(M * E);
+    if (ada) {
+      s.dcond0 = f32(M * 2 * E); s.dcond2 = f32(M * 2 * E); s.dcondc = f32(M * 2 * Dd);
+      s.dcondF = f32(M * 2 * E);
+    }
+    t.tr_dy[i] = b16(wide * Mp);
+    t.tr_a[i] = b16(wide * Mp);
+    if (ada) { t.dcb[i] = b16(M * 2 * E); t.dhid[i] = f32(M * 2 * E); }
+  }
+  t.delta = f32(static_cast<size_t>(B) * d->n_heads * T);
+}
+
+}  // namespace sea
+
+using namespace sea;
+
+extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cache, const float* x,
+                                     const float* ib, const float* dy, float* dx, int B, int T,
+                                     void* workspace, size_t workspace_bytes, sea_stream_t stream) {
+  if (!d || !d->blocks || !cache || !x || !ib || !dy || !workspace || B <= 0 || T <= 0) return SEA_ERR_INVALID;
+  if (d->precision != SEA_PREC_BF16) return SEA_ERR_UNSUPPORTED;  // fp32 split mode is forward-only
+  if (d->ib_hidden > 8 || d->ib_num > 4) return SEA_ERR_UNSUPPORTED;
+  if (workspace_bytes < sea_temporal_workspace_bytes(d, B, T, 1)) return SEA_ERR_WORKSPACE;
+  SEA_TRY(ensure_init());
+  g_launches = 0;
+
+  Arena car{const_cast<char*>(static_cast<const char*>(cache))};
+  CacheLayout cl;
+  layout_cache(d, true, car, cl);
+  Arena war{static_cast<char*>(workspace)};
+  Tape tape;
+  layout_tape(d, B, T, true, war, tape);
+  BwdTape bt;
+  layout_bwd_tape(d, B, T, war, bt);
+
+  BCtx b{};
+  b.c.d = d; b.c.cache = &cl; b.c.tape = &tape;
+  b.c.s = reinterpret_cast<cudaStream_t>(stream);
+  b.c.fp32 = false; b.c.B = B; b.c.T = T; b.c.M = B * T;
+  b.ib = ib; b.bt = &bt;
+  b.Mp = (static_cast<long long>(b.c.M) + 7) & ~7LL;
+  const int M = b.c.M, V = d->num_streams, E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
+  const int hd = E / d->n_heads, hdc = Dd / d->n_heads;
+  const int kind = d->norm_kind;
+  const bool ada = kind == SEA_NORM_ADALN;
+  const long long ldY = static_cast<long long>(V) * E;
+  LinB L[SEA_MAX_STREAMS];
+
+  // ---- final norm --------------------------------------------------------------------------
+  {
+    const LayerTape& last = tape.L[d->num_layers - 1];
+    for (int i = 0; i < V; ++i)
+      SEA_TRY(norm_bwd(b, kind, d->final_ln[i], tape.condF[i], dy + static_cast<long long>(i) * E, ldY,
+                       last.s[i].xout, E, tape.stF[i], E, nullptr, 0, bt.s[i].dxout, E, bt.s[i].dxoutb,
+                       bt.s[i].dcondF, 0));
+    if (ada) {
+      const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
+      float* dc[SEA_MAX_STREAMS]; const PackedLinear* W[SEA_MAX_STREAMS];
+      for (int i = 0; i < V; ++i) { np[i] = &d->final_ln[i]; hid[i] = tape.hidF[i]; dc[i] = bt.s[i].dcondF; W[i] = &cl.c2_final[i]; }
+      SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E));
+    }
+  }
+
+  for (int l = d->num_layers - 1; l >= 0; --l) {
+    const sea_block_params& bp = d->blocks[l];
+    LayerTape& lt = tape.L[l];
+    const BlockCache& bc = cl.blocks[l];
+    const float* xin[SEA_MAX_STREAMS];
+    long long ldxin;
+    if (l == 0) { for (int i = 0; i < V; ++i) xin[i] = x + static_cast<long long>(i) * E; ldxin = ldY; }
+    else { for (int i = 0; i < V; ++i) xin[i] = tape.L[l - 1].s[i].xout; ldxin = E; }
+
+    // (5) proj
+    for (int i = 0; i < V; ++i) {
+      LinB& q = L[i]; q = LinB{};
+      q.dy = bt.s[i].dxoutb; q.lddy = E; q.a = static_cast<const bf16*>(lt.s[i].x3); q.lda = E;
+      q.W = &bc.s[i].proj; q.dW = bp.s[i].proj_w.g; q.db = bp.s[i].proj_b.g;
+      q.dgrad = true; q.da_f32 = bt.s[i].dx3; q.ld_da = E; q.da_b16 = bt.s[i].dx3b; q.ld_dab = E;
+    }
+    SEA_TRY(linear_bwd(b, V, L));
+    // (4) MLP: Linear2, LN+GELU, Linear1
+    for (int i = 0; i < V; ++i) {
+      LinB& q = L[i]; q = LinB{};
+      q.dy = bt.s[i].dx3b; q.lddy = E; q.a = static_cast<const bf16*>(lt.s[i].gh); q.lda = H;
+      q.W = &bc.s[i].mlp3; q.dW = bp.s[i].mlp3_w.g; q.db = bp.s[i].mlp3_b.g;
+      q.dgrad = true; q.da_b16 = bt.s[i].dg; q.ld_dab = H;
+    }
+    SEA_TRY(linear_bwd(b, V, L));
+    for (int i = 0; i < V; ++i) {
+      sea_ln_gelu_bwd_args a{};
+      a.dg = bt.s[i].dg; a.lddg = H; a.h = lt.s[i].h; a.ldh = H; a.stats = lt.s[i].stH;
+      a.M = M; a.H = H; a.weight = bp.s[i].mlp_ln_w.p; a.bias = bp.s[i].mlp_ln_b.p;
+      a.dh = bt.s[i].dh; a.lddh = H; a.dweight = bp.s[i].mlp_ln_w.g; a.dbias = bp.s[i].mlp_ln_b.g;
+      ++g_launches;
+      ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, 6.0 * M * static_cast<double>(H));
+      SEA_TRY(sea_ln_gelu_bwd(&a, b.st()));
+    }
+    for (int i = 0; i < V; ++i) {
+      LinB& q = L[i]; q = LinB{};
+      q.dy = bt.s[i].dh; q.lddy = H; q.a = static_cast<const bf16*>(lt.s[i].n2); q.lda = E;
+      q.W = &bc.s[i].mlp0; q.dW = bp.s[i].mlp0_w.g; q.db = bp.s[i].mlp0_b.g;
+      q.dgrad = true; q.da_f32 = bt.s[i].dn2; q.ld_da = E;
+    }
+    SEA_TRY(linear_bwd(b, V, L));
+    // Norm_{i,2} (+ skip) -> gradient at x2 = x_post + TIPI
+    for (int i = 0; i < V; ++i)
+      SEA_TRY(norm_bwd(b, kind, bp.s[i].ln2, lt.s[i].cond2, bt.s[i].dn2, E, lt.s[i].x2, E, lt.s[i].st2, E,
+                       bt.s[i].dx3, E, bt.s[i].dx2, E, bt.s[i].dx2b, bt.s[i].dcond2, 0));
+    if (ada) {
+      const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
+      float* dc[SEA_MAX_STREAMS]; const PackedLinear* W[SEA_MAX_STREAMS];
+      for (int i = 0; i < V; ++i) { np[i] = &bp.s[i].ln2; hid[i] = lt.s[i].hid2; dc[i] = bt.s[i].dcond2; W[i] = &bc.s[i].c2_ln2; }
+      SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E));
+    }
+    // (3) TIPI (shared module: gradients of all streams add up)
+    if (bp.ib3_w.g) {
+      sea_tipi_bwd_args a{};
+      for (int i = 0; i < V; ++i) a.dx[i] = bt.s[i].dx2;
+      a.lddx = E; a.n_streams = V; a.M = M; a.E = E; a.hid = d->ib_hidden; a.ib_num = d->ib_num;
+      a.g = lt.tipi_g; a.u = lt.tipi_pre; a.stats = lt.tipi_st; a.ib = ib;
+      a.w3 = bp.ib3_w.p; a.ln_w = bp.ib_ln_w.p; a.ln_b = bp.ib_ln_b.p;
+      a.dw3 = bp.ib3_w.g; a.db3 = bp.ib3_b.g; a.dlnw = bp.ib_ln_w.g; a.dlnb = bp.ib_ln_b.g;
+      a.dw0 = bp.ib0_w.g; a.db0 = bp.ib0_b.g;
+      g_launches += V + 1;
+      SEA_TRY(sea_tipi_bwd(&a, b.st()));
+    }
+
+    // (2) state exchange, reverse order
+    bool pre_written[SEA_MAX_STREAMS] = {}, post_written[SEA_MAX_STREAMS] = {};
+    const float* dxp[SEA_MAX_STREAMS]; const bf16* dxpb[SEA_MAX_STREAMS];
+    for (int i = V - 1; i >= 0; --i) {
+      StreamTape& s = lt.s[i];
+      BwdStream& g = bt.s[i];
+      if (i < V - 1 && post_written[i]) {
+        SEA_TRY(norm_bwd(b, kind, bp.s[i].ln_cross, s.condc, g.dnpost, Dd, s.dpost, Dd, s.stc_post, Dd,
+                         nullptr, 0, g.ddn, Dd, g.ddnb, g.dcondc, 0));
+        LinB& q = L[0]; q = LinB{};
+        q.dy = g.ddnb; q.lddy = Dd; q.a = s.xpb; q.lda = E;
+        q.W = &bc.s[i].down; q.dW = bp.s[i].down_w.g; q.db = bp.s[i].down_b.g;
+        q.dgrad = true; q.da_f32 = g.dxp; q.ld_da = E; q.da_res = g.dx2; q.ld_res = E;
+        q.da_b16 = g.dxpb; q.ld_dab = E;
+        SEA_TRY(linear_bwd(b, 1, L));
+        dxp[i] = g.dxp; dxpb[i] = g.dxpb;
+      } else {
+        dxp[i] = g.dx2; dxpb[i] = g.dx2b;
+      }
+      for (int j = 0; j < V; ++j) {
+        if (j == i) continue;
+        // cross_up (+ GELU' fused)
+        { LinB& q = L[0]; q = LinB{};
+          q.dy = dxpb[i]; q.lddy = E; q.a = s.g[j]; q.lda = Dd;
+          q.W = &bc.s[i].up; q.dW = bp.s[i].up_w.g; q.db = bp.s[i].up_b.g;
+          q.dgrad = true; q.da_b16 = g.dp; q.ld_dab = Dd;
+          q.gelu_of = static_cast<const bf16*>(s.p[j]); q.ld_gelu = Dd;
+          SEA_TRY(linear_bwd(b, 1, L)); }
+        // attention output projection
+        { LinB& q = L[0]; q = LinB{};
+          q.dy = g.dp; q.lddy = Dd; q.a = static_cast<const bf16*>(s.a[j]); q.lda = Dd;
+          q.W = &bc.s[i].cproj[j]; q.dW = bp.s[i].cross_attn[j].proj_w.g;
+          q.dgrad = true; q.da_b16 = g.da; q.ld_dab = Dd;
+          SEA_TRY(linear_bwd(b, 1, L)); }
+        const bf16* kv = static_cast<const bf16*>(s.kv[j]);
+        SEA_TRY(attention_bwd(b, static_cast<const bf16*>(s.q[j]), Dd, kv, kv + Dd, 2 * Dd,
+                              static_cast<const bf16*>(s.a[j]), g.da, Dd, s.lse_c[j], g.dq, Dd, g.dkv,
+                              g.dkv + Dd, 2 * Dd, hdc, d->rope_cross));
+        // q projection (input: ln_cross_i(down_i(x1_i)))
+        { LinB& q = L[0]; q = LinB{};
+          q.dy = g.dq; q.lddy = Dd; q.a = static_cast<const bf16*>(s.npre); q.lda = Dd;
+          q.W = &bc.s[i].cq[j]; q.dW = bp.s[i].cross_attn[j].q_w.g; q.db = bp.s[i].cross_attn[j].q_b.g;
+          q.dgrad = true; q.da_f32 = g.dnpre; q.ld_da = Dd;
+          if (pre_written[i]) { q.da_res = g.dnpre; q.ld_res = Dd; }
+          SEA_TRY(linear_bwd(b, 1, L));
+          pre_written[i] = true; }
+        // fused k|v projection (input: stream j, exchanged if j < i)
+        { LinB& q = L[0]; q = LinB{};
+          const bool from_post = j < i;
+          float* dst = from_post ? bt.s[j].dnpost : bt.s[j].dnpre;
+          bool& written = from_post ? post_written[j] : pre_written[j];
+          q.dy = g.dkv; q.lddy = 2 * Dd;
+          q.a = static_cast<const bf16*>(from_post ? lt.s[j].npost : lt.s[j].npre); q.lda = Dd;
+          q.W = &bc.s[i].ckv[j];
+          q.n_split = 2;
+          q.dW_split[0] = bp.s[i].cross_attn[j].k_w.g; q.dW_split[1] = bp.s[i].cross_attn[j].v_w.g;
+          q.db_split[0] = bp.s[i].cross_attn[j].k_b.g; q.db_split[1] = bp.s[i].cross_attn[j].v_b.g;
+          q.dgrad = true; q.da_f32 = dst; q.ld_da = Dd;
+          if (written) { q.da_res = dst; q.ld_res = Dd; }
+          SEA_TRY(linear_bwd(b, 1, L));
+          written = true; }
+      }
+    }
+    // pre-exchange branch of every stream: ln_cross + cross_down on x1
+    for (int i = 0; i < V; ++i) {
+      StreamTape& s = lt.s[i];
+      BwdStream& g = bt.s[i];
+      if (!pre_written[i]) {  // V == 1: the exchange is the identity
+        SEA_CUDA_OK(cudaMemcpyAsync(g.dx1, dxp[i], sizeof(float) * M * E, cudaMemcpyDeviceToDevice, b.c.s));
+        SEA_CUDA_OK(cudaMemcpyAsync(g.dx1b, dxpb[i], sizeof(bf16) * M * E, cudaMemcpyDeviceToDevice, b.c.s));
+        continue;
+      }
+      SEA_TRY(norm_bwd(b, kind, bp.s[i].ln_cross, s.condc, g.dnpre, Dd, s.dpre, Dd, s.stc_pre, Dd, nullptr, 0,
+                       g.ddn, Dd, g.ddnb, g.dcondc, (i < V - 1 && post_written[i]) ? 1 : 0));
+      LinB& q = L[0]; q = LinB{};
+      q.dy = g.ddnb; q.lddy = Dd; q.a = s.x1b; q.lda = E;
+      q.W = &bc.s[i].down; q.dW = bp.s[i].down_w.g; q.db = bp.s[i].down_b.g;
+      q.dgrad = true; q.da_f32 = g.dx1; q.ld_da = E; q.da_res = dxp[i]; q.ld_res = E;
+      q.da_b16 = g.dx1b; q.ld_dab = E;
+      SEA_TRY(linear_bwd(b, 1, L));
+    }
+    if (ada && V > 1) {
+      const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
+      float* dc[SEA_MAX_STREAMS]; const PackedLinear* W[SEA_MAX_STREAMS];
+      for (int i = 0; i < V; ++i) { np[i] = &bp.s[i].ln_cross; hid[i] = lt.s[i].hidc; dc[i] = bt.s[i].dcondc; W[i] = &bc.s[i].c2_lnc; }
+      SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * Dd));
+    }
+
+    // (1) self-attention
+    for (int i = 0; i < V; ++i) {
+      LinB& q = L[i]; q = LinB{};
+      q.dy = bt.s[i].dx1b; q.lddy = E; q.a = static_cast<const bf16*>(lt.s[i].ao); q.lda = E;
+      q.W = &bc.s[i].sproj; q.dW = bp.s[i].self_attn.proj_w.g;
+      q.dgrad = true; q.da_b16 = bt.s[i].dao; q.ld_dab = E;
+    }
+    SEA_TRY(linear_bwd(b, V, L));
+    for (int i = 0; i < V; ++i) {
+      const bf16* qkv = static_cast<const bf16*>(lt.s[i].qkv);
+      bf16* dqkv = bt.s[i].dqkv;
+      SEA_TRY(attention_bwd(b, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, static_cast<const bf16*>(lt.s[i].ao),
+                            bt.s[i].dao, E, lt.s[i].lse, dqkv, 3 * E, dqkv + E, dqkv + 2 * E, 3 * E, hd,
+                            d->rope_self));
+    }
+    for (int i = 0; i < V; ++i) {
+      LinB& q = L[i]; q = LinB{};
+      q.dy = bt.s[i].dqkv; q.lddy = 3 * E; q.a = static_cast<const bf16*>(lt.s[i].n0); q.lda = E;
+      q.W = &bc.s[i].qkv; q.n_split = 3;
+      q.dW_split[0] = bp.s[i].self_attn.q_w.g; q.dW_split[1] = bp.s[i].self_attn.k_w.g; q.dW_split[2] = bp.s[i].self_attn.v_w.g;
+      q.db_split[0] = bp.s[i].self_attn.q_b.g; q.db_split[1] = bp.s[i].self_attn.k_b.g; q.db_split[2] = bp.s[i].self_attn.v_b.g;
+      q.dgrad = true; q.da_f32 = bt.s[i].dn0; q.ld_da = E;
+    }
+    SEA_TRY(linear_bwd(b, V, L));
+    // Norm_{i,0} (+ skip) -> gradient at the layer input
+    for (int i = 0; i < V; ++i) {
+      float* dst = nullptr; long long ldd = E; bf16* dstb = nullptr;
+      if (l > 0) { dst = bt.s[i].dxout; dstb = bt.s[i].dxoutb; }
+      else if (dx) { dst = dx + static_cast<long long>(i) * E; ldd = ldY; }
+      else { dst = bt.s[i].dxout; }  // not requested: still needed for the parameter gradients
+      SEA_TRY(norm_bwd(b, kind, bp.s[i].ln0, lt.s[i].cond0, bt.s[i].dn0, E, xin[i], ldxin, lt.s[i].st0, E,
+                       bt.s[i].dx1, E, dst, ldd, dstb, bt.s[i].dcond0, 0));
+    }
+    if (ada) {
+      const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
+      float* dc[SEA_MAX_STREAMS]; const PackedLinear* W[SEA_MAX_STREAMS];
+      for (int i = 0; i < V; ++i) { np[i] = &bp.s[i].ln0; hid[i] = lt.s[i].hid0; dc[i] = bt.s[i].dcond0; W[i] = &bc.s[i].c2_ln0; }
+      SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E));
+    }
+  }
+  return SEA_OK;
+}

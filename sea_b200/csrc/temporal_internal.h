@@ -75,6 +75,32 @@ struct Tape {
   bf16* packA[SEA_MAX_STREAMS];  // fp32 mode: split A operands
 };
 
+// Gradient buffers of the backward pass (one set, reused across layers; bf16 mode only).
+struct BwdStream {
+  float* dxout; bf16* dxoutb;   // gradient at the block output / previous layer's input
+  float* dx3; bf16* dx3b;       // at x3 = x2 + MLP
+  bf16* dg; bf16* dh;           // at GELU output / at the MLP hidden pre-LN   [M,H]
+  float* dn2;                   // at Norm_{i,2} output
+  float* dx2; bf16* dx2b;       // at x2 = x_post + TIPI
+  float* dxp; bf16* dxpb;       // at x_post when the exchanged stream feeds later streams
+  bf16 *dp, *da, *dq, *dkv;     // exchange branch: pre-GELU, attention out, q, k|v
+  float *dnpre, *dnpost;        // at ln_cross outputs (accumulated over consumers)
+  float* ddn; bf16* ddnb;       // at cross_down outputs
+  float* dx1; bf16* dx1b;       // at x1 (after self-attention)
+  bf16* dao; bf16* dqkv;        // self-attention: at attention output, at q|k|v (RoPE undone)
+  float* dn0;                   // at Norm_{i,0} output
+  float *dcond0, *dcond2, *dcondc, *dcondF;  // AdaLN: at the cond_mlp outputs
+};
+struct BwdTape {
+  BwdStream s[SEA_MAX_STREAMS];
+  bf16* tr_dy[SEA_MAX_STREAMS];  // dy^T  [N, Mp]
+  bf16* tr_a[SEA_MAX_STREAMS];   // a^T   [K, Mp]
+  bf16* dcb[SEA_MAX_STREAMS];    // bf16 copy of dcond
+  float* dhid[SEA_MAX_STREAMS];  // gradient at SiLU output
+  float* delta;                  // attention backward scratch
+};
+void layout_bwd_tape(const sea_temporal_desc* d, int B, int T, Arena& ar, BwdTape& t);
+
 struct Ctx {
   const sea_temporal_desc* d;
   const CacheLayout* cache;
@@ -104,5 +130,16 @@ void layout_tape(const sea_temporal_desc* d, int B, int T, bool training, Arena&
 int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, const LinOut* out, int Mrows);
 
 extern thread_local int g_launches;
+
+// RAII CUDA-event pair around one launch when profiling is on (no-op otherwise).
+// `work` is the launch's algorithmic work: FLOPs for GEMM / attention, bytes for HBM-bound kernels.
+class ProfScope {
+ public:
+  ProfScope(cudaStream_t s, int cat, double work);
+  ~ProfScope();
+ private:
+  cudaStream_t s_;
+  int idx_;
+};
 
 }  // namespace sea

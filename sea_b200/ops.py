@@ -141,3 +141,73 @@ def attention_fwd(q, k, v, n_heads, *, src_len=0, B=1, want_lse=False):
     a.prec = 0 if q.dtype == torch.bfloat16 else 1
     check(lib.sea_attention_fwd(C.byref(a), _stream()), "attention_fwd")
     return (o, lse) if want_lse else o
+
+
+# ------------------------------------------------------------------------------ backward ops
+def norm_bwd(dy, x, stats, weight, *, cond=None, kind=0, dres=None, want_bf16=False):
+    """Returns (dx, dx_bf16|None, dweight, dbias|None, dcond|None)."""
+    M, d = x.shape
+    dx = torch.empty(M, d, device=x.device)
+    dxb = torch.empty(M, d, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    dw = torch.zeros(d, device=x.device)
+    db = torch.zeros(d, device=x.device) if kind == 1 else None
+    dc = torch.empty(M, 2 * d, device=x.device) if kind == 1 else None
+    a = S.NormBwdArgs()
+    a.dy, a.lddy, a.x, a.ldx, a.stats = dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), stats.data_ptr()
+    a.M, a.d, a.kind, a.weight = M, d, kind, weight.data_ptr()
+    if cond is not None:
+        a.cond, a.ldc = cond.data_ptr(), cond.stride(0)
+    if dres is not None:
+        a.dres, a.lddres = dres.data_ptr(), dres.stride(0)
+    a.dx, a.lddx = dx.data_ptr(), d
+    if dxb is not None:
+        a.dx_bf16, a.lddx_bf16 = dxb.data_ptr(), d
+    a.dweight = dw.data_ptr()
+    a.dbias = None if db is None else db.data_ptr()
+    if dc is not None:
+        a.dcond, a.lddcond, a.dcond_accumulate = dc.data_ptr(), 2 * d, 0
+    check(lib.sea_norm_bwd(C.byref(a), _stream()), "norm_bwd")
+    return dx, dxb, dw, db, dc
+
+
+def ln_gelu_bwd(dg, h, stats, weight, bias):
+    M, H = h.shape
+    dh = torch.empty_like(h)
+    dw, db = torch.zeros(H, device=h.device), torch.zeros(H, device=h.device)
+    a = S.LnGeluBwdArgs()
+    a.dg, a.lddg, a.h, a.ldh, a.stats = dg.data_ptr(), dg.stride(0), h.data_ptr(), h.stride(0), stats.data_ptr()
+    a.M, a.H, a.weight, a.bias = M, H, weight.data_ptr(), bias.data_ptr()
+    a.dh, a.lddh, a.dweight, a.dbias = dh.data_ptr(), H, dw.data_ptr(), db.data_ptr()
+    check(lib.sea_ln_gelu_bwd(C.byref(a), _stream()), "ln_gelu_bwd")
+    return dh, dw, db
+
+
+def ln_gelu_fwd_with_stats(h, weight, bias):
+    M, H = h.shape
+    g = torch.empty_like(h)
+    st = torch.empty(M, 2, device=h.device)
+    a = S.LnGeluArgs()
+    a.h_bf16, a.g_bf16 = h.data_ptr(), g.data_ptr()
+    a.ldh, a.ldg, a.M, a.H = h.stride(0), g.stride(0), M, H
+    a.weight, a.bias, a.stats = weight.data_ptr(), bias.data_ptr(), st.data_ptr()
+    check(lib.sea_ln_gelu_fwd(C.byref(a), _stream()), "ln_gelu_fwd")
+    return g, st
+
+
+def attention_bwd(q, k, v, o, d_o, lse, n_heads, *, B=1, src_len=0, rope_table=None):
+    M, Cd = q.shape
+    T, hd = M // B, Cd // n_heads
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    delta = torch.empty(B, n_heads, T, device=q.device)
+    a = S.AttnBwdArgs()
+    a.q, a.k, a.v, a.o, a.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr()
+    a.ldq, a.ldk, a.ldv, a.ldo, a.lddo = q.stride(0), k.stride(0), v.stride(0), o.stride(0), d_o.stride(0)
+    a.lse, a.delta = lse.data_ptr(), delta.data_ptr()
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.lddq, a.lddk, a.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+    a.B, a.T, a.n_heads, a.head_dim, a.src_len = B, T, n_heads, hd, src_len
+    a.scale = hd ** -0.5
+    a.prec = 0 if q.dtype == torch.bfloat16 else 1
+    a.rope_table = None if rope_table is None else rope_table.data_ptr()
+    check(lib.sea_attention_bwd(C.byref(a), _stream()), "attention_bwd")
+    return dq, dk, dv

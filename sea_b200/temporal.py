@@ -170,6 +170,23 @@ def _P(t: Optional[torch.Tensor], g: Optional[torch.Tensor] = None) -> S.Param:
     return S.Param(None if t is None else t.data_ptr(), None if g is None else g.data_ptr())
 
 
+class _GradLookup:
+    """Maps a parameter tensor to its flat-gradient view (training) or nothing (inference)."""
+
+    def __init__(self, module, views):
+        self.by_ptr = {}
+        if views:
+            for n, p in module.named_parameters():
+                if n in views:
+                    self.by_ptr[p.data_ptr()] = views[n]
+
+    def __call__(self, t):
+        if t is None:
+            return S.Param(None, None)
+        g = self.by_ptr.get(t.data_ptr())
+        return S.Param(t.data_ptr(), None if g is None else g.data_ptr())
+
+
 class TemporalEngine:
     """Owns the packed-weight cache and workspaces for one module instance."""
 
@@ -182,7 +199,11 @@ class TemporalEngine:
         self._desc = None
         self._keep = None
         self._ws: Dict[tuple, torch.Tensor] = {}
+        self._train_ws: Dict[tuple, list] = {}
+        self._flat_grad = None
+        self._grad_views = {}
         self.last_launches = 0
+        self.total_launches = 0
 
     # -- hyper-parameters are read off the module tree (works for the mirror and the reference) --
     def _hyper(self):
@@ -212,6 +233,49 @@ class TemporalEngine:
             out.append((name, p))
         return out
 
+    # ---- flat gradient buffer: param.grad are views into it (also the DP all-reduce bucket) ----
+    def _ensure_flat_grads(self):
+        live = [(n, p) for n, p in self._live_params() if p.requires_grad]
+        total = sum((p.numel() + 63) // 64 * 64 for _, p in live)
+        dev = live[0][1].device
+        if getattr(self, "_flat_grad", None) is None or self._flat_grad.numel() != total or self._flat_grad.device != dev:
+            self._flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+            self._grad_views = {}
+            off = 0
+            for n, p in live:
+                self._grad_views[n] = self._flat_grad[off:off + p.numel()].view_as(p)
+                off += (p.numel() + 63) // 64 * 64
+            self._desc = None  # pointers changed
+        return live
+
+    def flat_grad(self) -> torch.Tensor:
+        self._ensure_flat_grads()
+        return self._flat_grad
+
+    def anchor_param(self):
+        for _, p in self._live_params():
+            if p.requires_grad:
+                return p
+        raise RuntimeError("no trainable parameter")
+
+    def _bind_grads(self):
+        """torch semantics: grad None -> zeros; else keep accumulating.  All-None (the state after
+        optimizer.zero_grad()) costs a single memset."""
+        live = self._ensure_flat_grads()
+        if all(p.grad is None for _, p in live):
+            self._flat_grad.zero_()
+            for n, p in live:
+                p.grad = self._grad_views[n]
+            return
+        for n, p in live:
+            v = self._grad_views[n]
+            if p.grad is None:
+                v.zero_()
+                p.grad = v
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+
     def _build(self, training: bool):
         h = self._hyper()
         m = self.module
@@ -221,6 +285,9 @@ class TemporalEngine:
         for name, p in self._live_params():
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError(f"parameter {name} must be contiguous fp32")
+        if training:
+            self._ensure_flat_grads()
+        _P = _GradLookup(m, getattr(self, "_grad_views", None) if training else None)  # noqa: N806
         V, L = h["V"], h["L"]
         if V > S.MAX_STREAMS:
             raise NotImplementedError(f"at most {S.MAX_STREAMS} field streams")
@@ -314,6 +381,42 @@ class TemporalEngine:
             self._ws[k] = ws
         return ws
 
+    def acquire_training_workspace(self, B: int, T: int) -> torch.Tensor:
+        self._ensure(True)
+        pool = self._train_ws.setdefault((B, T), [])
+        if pool:
+            return pool.pop()
+        n = lib.sea_temporal_workspace_bytes(C.byref(self._desc), B, T, 1)
+        return torch.empty(n, dtype=torch.uint8, device=self._dev)
+
+    def release_training_workspace(self, key, ws):
+        pool = self._train_ws.setdefault(tuple(key), [])
+        if len(pool) < 2:
+            pool.append(ws)
+
+    @torch.no_grad()
+    def backward(self, x, ib, dy, ws, need_dx: bool):
+        if self.precision != "bf16":
+            raise NotImplementedError("sea_b200 backward runs in bf16 mode (fp32 split mode is forward-only)")
+        self._ensure(True)
+        self._bind_grads()
+        B, T, V, E = x.shape
+        x = x.contiguous().float()
+        ib = ib.contiguous().float()
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(x) if need_dx else None
+        with torch.cuda.device(x.device):
+            check(lib.sea_temporal_backward(C.byref(self._desc), C.c_void_p(self._cache.data_ptr()),
+                                            C.c_void_p(x.data_ptr()), C.c_void_p(ib.data_ptr()),
+                                            C.c_void_p(dy.data_ptr()),
+                                            None if dx is None else C.c_void_p(dx.data_ptr()), B, T,
+                                            C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                  "temporal_backward")
+        self.last_launches = lib.sea_last_launch_count()
+        self.total_launches += self.last_launches
+        return dx
+
     @torch.no_grad()
     def forward_nograd(self, x: torch.Tensor, ib: torch.Tensor, training: bool = False,
                        ws: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -337,6 +440,7 @@ class TemporalEngine:
                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                   "temporal_forward")
         self.last_launches = lib.sea_last_launch_count()
+        self.total_launches += self.last_launches
         return y
 
     def __call__(self, x, ib):

@@ -1,0 +1,179 @@
+"""Backward parity: per-kernel against torch autograd on the same data, whole model against the
+oracle's gradients (goldens from the unmodified reference), and a 100-step training-loss curve."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import golden_recipe as gr
+from oracle import sea_oracle as so
+from tests.helpers import SEED, rel_l2, temporal_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("d", [512, 1024, 2048])
+@pytest.mark.parametrize("kind", [0, 1])
+def test_norm_bwd(cuda, d, kind):
+    from sea_b200 import ops
+    M = 301
+    g = torch.Generator(device="cuda").manual_seed(d + kind)
+    x = (torch.randn(M, d, device=cuda, generator=g) * 1.5 + 0.3).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(d, device=cuda, generator=g)).requires_grad_(True)
+    b = (0.1 * torch.randn(d, device=cuda, generator=g)).requires_grad_(True)
+    cond = (torch.randn(M, 2 * d, device=cuda, generator=g) * 0.3).requires_grad_(True)
+    dy = torch.randn(M, d, device=cuda, generator=g)
+    dres = torch.randn(M, d, device=cuda, generator=g)
+    if kind == 1:
+        mu, var = x.mean(-1, keepdim=True), x.var(-1, keepdim=True, unbiased=False)
+        y = (x - mu) / (var + 1e-5).sqrt() * (w + cond[:, :d] + 1) + (b + cond[:, d:])
+    else:
+        y = F.layer_norm(x, (d,), w, None, 1e-5)
+    (y * dy).sum().backward()
+    _, _, st = ops.norm_fwd(x.detach(), w.detach(), bias=b.detach() if kind else None,
+                            cond=cond.detach() if kind else None, kind=kind, out_dtype=torch.float32, stats=True)
+    dx, dxb, dw, db, dc = ops.norm_bwd(dy, x.detach(), st, w.detach(), cond=cond.detach() if kind else None,
+                                       kind=kind, dres=dres, want_bf16=True)
+    assert _rel(dx, x.grad + dres) < 1e-5
+    assert _rel(dxb.float(), x.grad + dres) < 5e-3
+    assert _rel(dw, w.grad) < 1e-4
+    if kind:
+        assert _rel(db, b.grad) < 1e-4 and _rel(dc, cond.grad) < 1e-5
+
+
+@pytest.mark.parametrize("H", [256, 8192, 16384])
+def test_ln_gelu_bwd(cuda, H):
+    from sea_b200 import ops
+    M = 77
+    g = torch.Generator(device="cuda").manual_seed(H)
+    h = (torch.randn(M, H, device=cuda, generator=g) * 1.5).bfloat16()
+    w = (1 + 0.1 * torch.randn(H, device=cuda, generator=g)).requires_grad_(True)
+    b = (0.1 * torch.randn(H, device=cuda, generator=g)).requires_grad_(True)
+    dg = torch.randn(M, H, device=cuda, generator=g).bfloat16()
+    hf = h.float().requires_grad_(True)
+    y = F.gelu(F.layer_norm(hf, (H,), w, b, 1e-5))
+    (y * dg.float()).sum().backward()
+    _, st = ops.ln_gelu_fwd_with_stats(h, w.detach(), b.detach())
+    dh, dw, db = ops.ln_gelu_bwd(dg, h, st, w.detach(), b.detach())
+    assert _rel(dh.float(), hf.grad) < 6e-3
+    assert _rel(dw, w.grad) < 1e-3 and _rel(db, b.grad) < 1e-3
+
+
+@pytest.mark.parametrize("hd", [32, 64, 128, 256])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,src_len", [(2, 77, 0), (1, 200, 0), (2, 33, 2)])
+def test_attention_bwd(cuda, hd, dt, B, T, src_len):
+    from sea_b200 import lib, ops
+    nh = 2
+    g = torch.Generator(device="cuda").manual_seed(hd + T)
+    qkv = torch.randn(B * T, 3 * nh * hd, device=cuda, generator=g).to(dt)
+    q, k, v = qkv[:, :nh * hd], qkv[:, nh * hd:2 * nh * hd], qkv[:, 2 * nh * hd:]
+    d_o = torch.randn(B * T, nh * hd, device=cuda, generator=g).to(dt)
+    qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+    qh = qf.view(B, T, nh, hd).transpose(1, 2)
+    kh = kf.view(B, T, nh, hd).transpose(1, 2)
+    vh = vf.view(B, T, nh, hd).transpose(1, 2)
+    att = (qh @ kh.transpose(-2, -1)) * hd ** -0.5
+    att = att.masked_fill(torch.ones(T, T, device=cuda).tril(diagonal=src_len) == 0, float("-inf"))
+    o_ref = (torch.softmax(att, -1) @ vh).transpose(1, 2).reshape(B * T, nh * hd)
+    (o_ref * d_o.float()).sum().backward()
+    lib.sea_attention_force_simt(1)
+    try:
+        o, lse = ops.attention_fwd(q, k, v, nh, src_len=src_len, B=B, want_lse=True)
+    finally:
+        lib.sea_attention_force_simt(0)
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, d_o, lse, nh, B=B, src_len=src_len)
+    tol = 2e-5 if dt == torch.float32 else 1.5e-2
+    assert _rel(dq.float(), qf.grad) < tol
+    assert _rel(dk.float(), kf.grad) < tol
+    assert _rel(dv.float(), vf.grad) < tol
+
+
+def _mirror(tag, ln, cuda):
+    from sea_b200.temporal import TemporalModel
+    g, sd, cfg, x, ib, tgt, _ = temporal_case(tag, ln, requires_grad=True)
+    E, nh, scale, V, B, T, _ = [int(v) for v in g["meta"]]
+    m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln)
+    m.load_state_dict({k: v.detach() for k, v in sd.items()}, strict=False)
+    return g, sd, cfg, m.to(cuda).train(), x, ib, tgt
+
+
+@pytest.mark.parametrize("tag,ln", [("small_adaln", "adaln"), ("small_ln", "ln"), ("small_v3", "ln")])
+def test_model_gradients_match_reference(cuda, tag, ln):
+    g, sd, cfg, m, x, ib, tgt = _mirror(tag, ln, cuda)
+    # oracle gradients (fp32 autograd on CPU; pinned to the reference by tests/test_oracle_golden.py)
+    x = x.detach().clone().requires_grad_(True)
+    loss_ref = F.mse_loss(so.temporal_forward(x, ib, sd, **cfg), tgt)
+    loss_ref.backward()
+    xg = x.detach().to(cuda).requires_grad_(True)
+    y = m(xg, ib.to(cuda))
+    loss = F.mse_loss(y, tgt.to(cuda))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    params = dict(m.named_parameters())
+    worst = 0.0
+    for name in [str(n) for n in g["grad_names"]]:
+        got, ref = params[name].grad, sd[name].grad
+        assert got is not None, name
+        ref_norm = ref.double().norm().item()
+        if ref_norm < 2e-5:   # e.g. the TIPI input layer: LayerNorm over 2-8 values, pure cancellation
+            continue
+        err = _rel(got.cpu(), ref)
+        cos = F.cosine_similarity(got.cpu().flatten().double(), ref.flatten().double(), dim=0).item()
+        worst = max(worst, err)
+        assert cos > 0.995 and err < 8e-2, (name, err, cos)
+    for name in [str(n) for n in g["dead_params"]]:
+        assert params[name].grad is None, name
+    assert _rel(xg.grad.cpu(), x.grad) < 5e-2
+    print(f"\n[temporal bwd] {tag}: loss {loss.item():.6f} vs {loss_ref.item():.6f}; worst param-grad rel err {worst:.3e}")
+
+
+def test_gradient_accumulation_semantics(cuda):
+    g, sd, cfg, m, x, ib, tgt = _mirror("small_ln", "ln", cuda)
+    xc, ic, tc = x.detach().to(cuda), ib.to(cuda), tgt.to(cuda)
+    F.mse_loss(m(xc, ic), tc).backward()
+    g1 = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    F.mse_loss(m(xc, ic), tc).backward()          # no zero_grad: must accumulate
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            assert _rel(p.grad, 2 * g1[n]) < 1e-3, n
+    m.zero_grad(set_to_none=True)
+    F.mse_loss(m(xc, ic), tc).backward()
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            assert _rel(p.grad, g1[n]) < 1e-3, n
+
+
+@pytest.mark.parametrize("tag,ln", [("small_adaln", "adaln"), ("small_ln", "ln")])
+def test_training_loss_curve_100_steps(cuda, tag, ln):
+    """train/train_temporal.py:252-260 semantics (AdamW lr 1e-4, MSE, dropout 0): per-step loss of the
+    CUDA path vs the fp32 oracle trained on CPU from the same init and data."""
+    g, sd, cfg, m, x, ib, tgt = _mirror(tag, ln, cuda)
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    opt_ref = torch.optim.AdamW(list(leaves.values()), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    xd, ibd, td = x.detach(), ib, tgt
+    xc, ic, tc = xd.to(cuda), ibd.to(cuda), td.to(cuda)
+    ref_losses, losses = [], []
+    for step in range(100):
+        opt_ref.zero_grad()
+        lr_ = F.mse_loss(so.temporal_forward(xd, ibd, leaves, **cfg), td)
+        lr_.backward()
+        opt_ref.step()
+        ref_losses.append(lr_.item())
+        opt.zero_grad()
+        lo = F.mse_loss(m(xc, ic), tc)
+        lo.backward()
+        opt.step()
+        losses.append(lo.item())
+    ref_losses, losses = np.array(ref_losses), np.array(losses)
+    rel = np.abs(losses - ref_losses) / np.abs(ref_losses)
+    print(f"\n[train 100 steps] {tag}: loss {ref_losses[0]:.4f} -> {ref_losses[-1]:.4f} (oracle), "
+          f"{losses[0]:.4f} -> {losses[-1]:.4f} (cuda); max per-step rel diff {rel.max():.3e}")
+    assert ref_losses[-1] < 0.9 * ref_losses[0]          # it actually trains
+    assert rel.max() < 2e-2

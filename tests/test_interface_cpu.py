@@ -79,7 +79,9 @@ def test_ctypes_struct_sizes_match_header():
              "sea_norm_args": S.NormArgs, "sea_ln_gelu_args": S.LnGeluArgs, "sea_pack_args": S.PackArgs,
              "sea_attn_args": S.AttnArgs, "sea_param": S.Param, "sea_norm_params": S.NormParams,
              "sea_attn_params": S.AttnParams, "sea_stream_params": S.StreamParams,
-             "sea_block_params": S.BlockParams, "sea_temporal_desc": S.TemporalDesc}
+             "sea_block_params": S.BlockParams, "sea_temporal_desc": S.TemporalDesc,
+             "sea_norm_bwd_args": S.NormBwdArgs, "sea_ln_gelu_bwd_args": S.LnGeluBwdArgs,
+             "sea_attn_bwd_args": S.AttnBwdArgs, "sea_tipi_bwd_args": S.TipiBwdArgs}
     src = '#include <stdio.h>\n#include "sea_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:
