@@ -119,6 +119,10 @@ typedef struct sea_norm_args {
   const float* bias; /* AdaLN's own bias or NULL */
   const float* cond;
   int64_t ldc;
+  int32_t cond_div;    /* row m uses cond row m / cond_div (0/1: one cond row per row; T: one per trajectory) */
+  const float* add_rows; /* optional [ceil(M/add_div), d]: x' = x + add_rows[m / add_div] (written to x_out) */
+  int64_t ld_add;
+  int32_t add_div;
   const float* tipi_g; /* [M, tipi_hid] from sea_tipi_hidden, or NULL */
   int32_t tipi_hid;
   const float* tipi_w; /* [d, tipi_hid] */
@@ -135,12 +139,23 @@ int sea_norm_fwd(const sea_norm_args* args, sea_stream_t stream);
 
 /* AdaLN cond_mlp[0] + SiLU on the scalar condition: h[m,j] = SiLU(w1[j,:]·ib[m,:] + b1[j]), j < n
  * (models/base_blocks.py:337-339, 344).  Either output may be NULL. */
-int sea_adaln_hidden(const float* ib, int M, int ib_num, const float* w1, const float* b1, int n,
-                     void* out_bf16, float* out_f32, sea_stream_t stream);
+int sea_adaln_hidden(const float* ib, int64_t ld_ib /* row pitch of ib, 0 = ib_num */, int M, int ib_num,
+                     const float* w1, const float* b1, int n, void* out_bf16, float* out_f32,
+                     sea_stream_t stream);
+
+/* Same for up to 8 modules of equal width in ONE launch (out_bf16 / out_f32: arrays, entries may be NULL). */
+int sea_adaln_hidden_group(int items, const float* const* w1, const float* const* b1,
+                           void* const* out_bf16, float* const* out_f32, const float* ib, int64_t ld_ib,
+                           int M, int ib_num, int n, sea_stream_t stream);
+
+/* rows[r, :] = W3 g[r, :] + b3 for R distinct conditions (TIPI output per trajectory when the
+ * condition is time-invariant; consumed through sea_norm_args.add_rows). */
+int sea_tipi_rows(const float* g, int64_t ldg, int R, int E, int hid, const float* w3, const float* b3,
+                  float* out, sea_stream_t stream);
 
 /* TIPI hidden layer g = GELU(LayerNorm(W0 ib + b0)), hid <= 64 (models/base_blocks.py:22-25 as
  * instantiated by models/temporal.py:108).  pre_out / stats_out (optional) are saved for backward. */
-int sea_tipi_hidden(const float* ib, int M, int ib_num, const float* w0, const float* b0,
+int sea_tipi_hidden(const float* ib, int64_t ld_ib, int M, int ib_num, const float* w0, const float* b0,
                     const float* ln_w, const float* ln_b, int hid, float* g_out, float* pre_out,
                     float* stats_out, sea_stream_t stream);
 
@@ -338,6 +353,13 @@ typedef struct sea_temporal_desc {
   int32_t ib_num, ib_hidden /* max(1, scale_ratio*ib_num) */;
   int32_t norm_kind /* SEA_NORM_* */, src_len, max_len;
   int32_t precision /* SEA_PREC_BF16: bf16 tensor-core operands; SEA_PREC_FP32: 3-way split */;
+  int32_t ib_time_invariant /* caller asserts ib[b,t,:] == ib[b,0,:] for all t (inference only):
+                               AdaLN cond_mlp and the TIPI MLP are evaluated once per trajectory */;
+  int32_t cond_cache_valid /* 1: cond_cache already holds the results for these B trajectories and the
+                              current weights (set by the caller after a first call) -> skip that path */;
+  void* cond_cache;        /* optional persistent device buffer (sea_temporal_cond_cache_bytes) used
+                              only with ib_time_invariant; NULL = keep everything in the workspace */
+  size_t cond_cache_bytes;
   const sea_block_params* blocks; /* host array [num_layers] */
   sea_norm_params final_ln[SEA_MAX_STREAMS]; /* ln.{i} */
   const float* rope_self;  /* device [max_len, (E/n_heads)/2, 2] (cos, sin) */
@@ -347,6 +369,7 @@ typedef struct sea_temporal_desc {
 /* Packed low-precision copies of the weights (bf16, fused QKV / KV, optional transposes for the
  * backward pass) live in a caller-owned cache; refresh after every parameter update. */
 size_t sea_temporal_cache_bytes(const sea_temporal_desc* d, int training);
+size_t sea_temporal_cond_cache_bytes(const sea_temporal_desc* d, int B);
 int sea_temporal_refresh(const sea_temporal_desc* d, void* cache, size_t cache_bytes, int training,
                          sea_stream_t stream);
 /* Activations / saved-for-backward tape live in a caller-owned workspace. */

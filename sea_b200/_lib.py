@@ -64,7 +64,7 @@ class _Lazy:
             dll = C.CDLL(LIB_PATH)
             dll.sea_strerror.restype = C.c_char_p
             dll.sea_strerror.argtypes = [C.c_int]
-            for fn in ("sea_temporal_cache_bytes", "sea_temporal_workspace_bytes"):
+            for fn in ("sea_temporal_cache_bytes", "sea_temporal_workspace_bytes", "sea_temporal_cond_cache_bytes"):
                 if hasattr(dll, fn):
                     getattr(dll, fn).restype = C.c_size_t
             self._dll = dll

@@ -39,7 +39,8 @@ class TemporalDesc(C.Structure):
                 ("embed_dim", C.c_int32), ("n_heads", C.c_int32), ("hidden_dim", C.c_int32),
                 ("down_dim", C.c_int32), ("ib_num", C.c_int32), ("ib_hidden", C.c_int32),
                 ("norm_kind", C.c_int32), ("src_len", C.c_int32), ("max_len", C.c_int32),
-                ("precision", C.c_int32),
+                ("precision", C.c_int32), ("ib_time_invariant", C.c_int32), ("cond_cache_valid", C.c_int32),
+                ("cond_cache", C.c_void_p), ("cond_cache_bytes", C.c_size_t),
                 ("blocks", C.POINTER(BlockParams)),
                 ("final_ln", NormParams * MAX_STREAMS),
                 ("rope_self", C.c_void_p), ("rope_cross", C.c_void_p)]
@@ -48,7 +49,9 @@ class TemporalDesc(C.Structure):
 class NormArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("ldx", C.c_int64), ("M", C.c_int32), ("d", C.c_int32),
                 ("kind", C.c_int32), ("weight", C.c_void_p), ("bias", C.c_void_p),
-                ("cond", C.c_void_p), ("ldc", C.c_int64), ("tipi_g", C.c_void_p),
+                ("cond", C.c_void_p), ("ldc", C.c_int64), ("cond_div", C.c_int32),
+                ("add_rows", C.c_void_p), ("ld_add", C.c_int64), ("add_div", C.c_int32),
+                ("tipi_g", C.c_void_p),
                 ("tipi_hid", C.c_int32), ("tipi_w", C.c_void_p), ("tipi_b", C.c_void_p),
                 ("x_out", C.c_void_p), ("ldxo", C.c_int64), ("y_f32", C.c_void_p),
                 ("ldy_f32", C.c_int64), ("y_bf16", C.c_void_p), ("ldy_bf16", C.c_int64),

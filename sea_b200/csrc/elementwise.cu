@@ -21,7 +21,7 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 
 // ------------------------------------------------------------------ AdaLN cond hidden layer
 // h[m, j] = SiLU(sum_c w1[j, c] * ib[m, c] + b1[j])     models/base_blocks.py:337-339, 344
-__global__ void adaln_hidden_kernel(const float* __restrict__ ib, int M, int ib_num,
+__global__ void adaln_hidden_kernel(const float* __restrict__ ib, long long ld_ib, int M, int ib_num,
                                     const float* __restrict__ w1, const float* __restrict__ b1,
                                     int n, __nv_bfloat16* __restrict__ out_bf16,
                                     float* __restrict__ out_f32) {
@@ -32,7 +32,7 @@ __global__ void adaln_hidden_kernel(const float* __restrict__ ib, int M, int ib_
     const int j = static_cast<int>(idx - static_cast<long long>(m) * (n / 2)) * 2;
     float a0 = b1[j], a1 = b1[j + 1];
     for (int c = 0; c < ib_num; ++c) {
-      const float v = ib[static_cast<long long>(m) * ib_num + c];
+      const float v = ib[static_cast<long long>(m) * ld_ib + c];
       a0 = fmaf(w1[j * ib_num + c], v, a0);
       a1 = fmaf(w1[(j + 1) * ib_num + c], v, a1);
     }
@@ -47,7 +47,7 @@ __global__ void adaln_hidden_kernel(const float* __restrict__ ib, int M, int ib_
 // g[m, :] = GELU(LayerNorm_hid(W0 ib[m] + b0))     models/base_blocks.py:22-25 (MLP(ib_num, ...))
 // Also stores the pre-LN values and (mean, rstd) when asked (backward).
 constexpr int kMaxTipiHid = 64;
-__global__ void tipi_hidden_kernel(const float* __restrict__ ib, int M, int ib_num,
+__global__ void tipi_hidden_kernel(const float* __restrict__ ib, long long ld_ib, int M, int ib_num,
                                    const float* __restrict__ w0, const float* __restrict__ b0,
                                    const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                    int hid, float* __restrict__ g_out, float* __restrict__ pre_out,
@@ -58,7 +58,7 @@ __global__ void tipi_hidden_kernel(const float* __restrict__ ib, int M, int ib_n
   float mean = 0.f;
   for (int k = 0; k < hid; ++k) {
     float a = b0[k];
-    for (int c = 0; c < ib_num; ++c) a = fmaf(w0[k * ib_num + c], ib[static_cast<long long>(m) * ib_num + c], a);
+    for (int c = 0; c < ib_num; ++c) a = fmaf(w0[k * ib_num + c], ib[static_cast<long long>(m) * ld_ib + c], a);
     u[k] = a;
     mean += a;
   }
@@ -78,13 +78,18 @@ __global__ void tipi_hidden_kernel(const float* __restrict__ ib, int M, int ib_n
 }
 
 // ------------------------------------------------------------------ row norm (LN / AdaLN)
-// One warp per row, the row lives in registers (d <= 2048).  Optional fused TIPI add before
-// the norm (models/temporal.py:140-145): x' = x + W3 g[m] + b3, written back, then normalised.
+// One warp per row, the row lives in registers (CH chunks of 128 columns, d <= 2048).  Every
+// global load of a row (x, the AdaLN condition row, the per-trajectory TIPI row) is issued before
+// the first use so one DRAM round trip covers them; statistics are two-pass in registers.
+//   x' = x + add_rows[m / add_div]            (optional; TIPI precomputed per trajectory)
+//   x' = x + W3 g[m] + b3                     (optional; general TIPI, models/temporal.py:140-142)
+//   y  = (x' - mean) * rstd * gamma + beta    gamma/beta from weight/bias (+ cond row m / cond_div)
 struct NormDev {
   const float* x; long long ldx;
   int M, d, kind;
   const float* weight; const float* bias;
-  const float* cond; long long ldc;
+  const float* cond; long long ldc; int cond_div;
+  const float* add_rows; long long ld_add; int add_div;
   const float* tipi_g; int tipi_hid; const float* tipi_w; const float* tipi_b;
   float* x_out; long long ldxo;
   float* y_f32; long long ldy_f32;
@@ -94,24 +99,41 @@ struct NormDev {
 
 constexpr int kNormMaxChunks = 16;  // 16 chunks x 32 lanes x 4 floats = 2048
 
-__global__ void __launch_bounds__(256) norm_fwd_kernel(const NormDev a) {
+template <int CH, bool ADALN>
+__global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const NormDev a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * (blockDim.x >> 5) + warp;
   if (m >= a.M) return;
   const float* xr = a.x + static_cast<long long>(m) * a.ldx;
-  float4 v[kNormMaxChunks];
-  float sum = 0.f;
-  float gk[8];
-  if (a.tipi_g) {
+  const float* cr = ADALN ? a.cond + static_cast<long long>(m / a.cond_div) * a.ldc : nullptr;
+  const float* ar = a.add_rows ? a.add_rows + static_cast<long long>(m / a.add_div) * a.ld_add : nullptr;
+  // Occupancy over prefetch: the grid of these small kernels should be resident in ONE wave
+  // (<= 64 registers -> 32 warps / SM), so only x is staged in registers; the condition row and
+  // the affine vectors are L2 hits consumed in the last loop.
+  float4 v[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = c * 128 + lane * 4;
+    if (col < a.d) v[c] = *reinterpret_cast<const float4*>(xr + col);
+  }
+  if (ar != nullptr) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = c * 128 + lane * 4;
+      if (col < a.d) {
+        const float4 t = *reinterpret_cast<const float4*>(ar + col);
+        v[c].x += t.x; v[c].y += t.y; v[c].z += t.z; v[c].w += t.w;
+        *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(m) * a.ldxo + col) = v[c];
+      }
+    }
+  } else if (a.tipi_g != nullptr) {
+    float gk[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) gk[k] = (k < a.tipi_hid) ? a.tipi_g[static_cast<long long>(m) * a.tipi_hid + k] : 0.f;
-  }
 #pragma unroll
-  for (int c = 0; c < kNormMaxChunks; ++c) {
-    const int col = c * 128 + lane * 4;
-    if (col < a.d) {
-      float4 t = *reinterpret_cast<const float4*>(xr + col);
-      if (a.tipi_g) {
+    for (int c = 0; c < CH; ++c) {
+      const int col = c * 128 + lane * 4;
+      if (col < a.d) {
         float add[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -128,19 +150,20 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(const NormDev a) {
           }
           add[e] = s;
         }
-        t.x += add[0]; t.y += add[1]; t.z += add[2]; t.w += add[3];
-        *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(m) * a.ldxo + col) = t;
+        v[c].x += add[0]; v[c].y += add[1]; v[c].z += add[2]; v[c].w += add[3];
+        *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(m) * a.ldxo + col) = v[c];
       }
-      v[c] = t;
-      sum += t.x + t.y + t.z + t.w;
     }
   }
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    if (c * 128 + lane * 4 < a.d) sum += v[c].x + v[c].y + v[c].z + v[c].w;
   const float mean = warp_sum(sum) / a.d;
   float sq = 0.f;
 #pragma unroll
-  for (int c = 0; c < kNormMaxChunks; ++c) {
-    const int col = c * 128 + lane * 4;
-    if (col < a.d) {
+  for (int c = 0; c < CH; ++c) {
+    if (c * 128 + lane * 4 < a.d) {
       const float dx = v[c].x - mean, dy = v[c].y - mean, dz = v[c].z - mean, dw = v[c].w - mean;
       sq += dx * dx + dy * dy + dz * dz + dw * dw;
     }
@@ -151,15 +174,14 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(const NormDev a) {
     a.stats[2 * m + 1] = rstd;
   }
 #pragma unroll
-  for (int c = 0; c < kNormMaxChunks; ++c) {
+  for (int c = 0; c < CH; ++c) {
     const int col = c * 128 + lane * 4;
     if (col < a.d) {
       float4 w = __ldg(reinterpret_cast<const float4*>(a.weight + col));
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.bias) b = __ldg(reinterpret_cast<const float4*>(a.bias + col));
-      if (a.kind == SEA_NORM_ADALN) {
+      if (ADALN) {
         // gamma = weight + (w_cond + 1), beta = bias + b_cond   (models/base_blocks.py:345-350)
-        const float* cr = a.cond + static_cast<long long>(m) * a.ldc;
         const float4 cw = *reinterpret_cast<const float4*>(cr + col);
         const float4 cb = *reinterpret_cast<const float4*>(cr + a.d + col);
         w.x += cw.x + 1.f; w.y += cw.y + 1.f; w.z += cw.z + 1.f; w.w += cw.w + 1.f;
@@ -181,45 +203,48 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(const NormDev a) {
   }
 }
 
+// rows[r, n] = W3[n, :] . g[r, :] + b3[n]   — the TIPI term for `R` distinct conditions
+__global__ void __launch_bounds__(256) tipi_rows_kernel(const float* __restrict__ g, long long ldg, int R, int E,
+                                                        int hid, const float* __restrict__ w3,
+                                                        const float* __restrict__ b3, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (n >= E || r >= R) return;
+  float s = b3[n];
+  for (int k = 0; k < hid; ++k) s = fmaf(w3[n * hid + k], g[static_cast<long long>(r) * ldg + k], s);
+  out[static_cast<long long>(r) * E + n] = s;
+}
+
 // --------------------------------------------------------- MLP inner LayerNorm(H) + GELU (K6)
-// One CTA per row; each thread keeps <= 64 values of the row in registers.
+// Each CTA owns a group of rows; a thread keeps the LayerNorm weight/bias of ITS columns in
+// registers for the whole group (the fp32 affine vectors are 4x the bytes of a bf16 row, so
+// re-reading them per row would dominate L2 traffic) and prefetches the next row while it works.
 // models/base_blocks.py:23-25 (nn.LayerNorm(scaled_dim) with affine weight+bias, then nn.GELU()).
-template <typename TIn, typename TOut>
+template <typename TIn, typename TOut, int CH>
 __global__ void __launch_bounds__(256) ln_gelu_fwd_kernel(const TIn* __restrict__ h, long long ldh,
                                                           int M, int H,
                                                           const float* __restrict__ weight,
                                                           const float* __restrict__ bias,
                                                           TOut* __restrict__ g, long long ldg,
-                                                          float* __restrict__ stats) {
-  constexpr int kMaxChunks = 8;  // 8 chunks x 256 threads x 8 elements = 16384
+                                                          float* __restrict__ stats, int rows_per_cta) {
   __shared__ float red[8];
   __shared__ float bcast;
-  const int m = blockIdx.x;
   const int tid = threadIdx.x;
-  const TIn* hr = h + static_cast<long long>(m) * ldh;
-  float v[kMaxChunks][8];
-  float sum = 0.f;
+  const int row_begin = blockIdx.x * rows_per_cta;
+  const int row_end = min(M, row_begin + rows_per_cta);
+  float ww[CH][8], bb[CH][8];
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < CH; ++c) {
     const int col = (c * 256 + tid) * 8;
     if (col < H) {
-      if constexpr (sizeof(TIn) == 2) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(hr + col);
-        const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = __bfloat1622float2(p[q]);
-          v[c][2 * q] = f.x;
-          v[c][2 * q + 1] = f.y;
-        }
-      } else {
-        const float4 a = *reinterpret_cast<const float4*>(hr + col);
-        const float4 b = *reinterpret_cast<const float4*>(hr + col + 4);
-        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
-        v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sum += v[c][e];
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+      ww[c][0] = w0.x; ww[c][1] = w0.y; ww[c][2] = w0.z; ww[c][3] = w0.w;
+      ww[c][4] = w1.x; ww[c][5] = w1.y; ww[c][6] = w1.z; ww[c][7] = w1.w;
+      bb[c][0] = b0.x; bb[c][1] = b0.y; bb[c][2] = b0.z; bb[c][3] = b0.w;
+      bb[c][4] = b1.x; bb[c][5] = b1.y; bb[c][6] = b1.z; bb[c][7] = b1.w;
     }
   }
   auto block_sum = [&](float x) -> float {
@@ -236,47 +261,238 @@ __global__ void __launch_bounds__(256) ln_gelu_fwd_kernel(const TIn* __restrict_
     __syncthreads();
     return r;
   };
-  const float mean = block_sum(sum) / H;
-  float sq = 0.f;
+  auto load_row = [&](int m, float (&v)[CH][8]) {
+    const TIn* hr = h + static_cast<long long>(m) * ldh;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int col = (c * 256 + tid) * 8;
-    if (col < H) {
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 256 + tid) * 8;
+      if (col < H) {
+        if constexpr (sizeof(TIn) == 2) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(hr + col);
+          const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sq += (v[c][e] - mean) * (v[c][e] - mean);
-    }
-  }
-  const float rstd = rsqrtf(block_sum(sq) / H + 1e-5f);
-  if (stats && tid == 0) {
-    stats[2 * m] = mean;
-    stats[2 * m + 1] = rstd;
-  }
-  TOut* gr = g + static_cast<long long>(m) * ldg;
-#pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int col = (c * 256 + tid) * 8;
-    if (col < H) {
-      float y[8];
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
-      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = ptx::gelu_erf((v[c][e] - mean) * rstd * ww[e] + bb[e]);
-      if constexpr (sizeof(TOut) == 2) {
-        uint4 o;
-        o.x = ptx::pack_bf16(y[0], y[1]);
-        o.y = ptx::pack_bf16(y[2], y[3]);
-        o.z = ptx::pack_bf16(y[4], y[5]);
-        o.w = ptx::pack_bf16(y[6], y[7]);
-        *reinterpret_cast<uint4*>(gr + col) = o;
-      } else {
-        *reinterpret_cast<float4*>(gr + col) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(gr + col + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(p[q]);
+            v[c][2 * q] = f.x;
+            v[c][2 * q + 1] = f.y;
+          }
+        } else {
+          const float4 a = *reinterpret_cast<const float4*>(hr + col);
+          const float4 b = *reinterpret_cast<const float4*>(hr + col + 4);
+          v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+          v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+        }
       }
     }
+  };
+  float v[CH][8], nxt[CH][8];
+  if (row_begin < row_end) load_row(row_begin, nxt);
+  for (int m = row_begin; m < row_end; ++m) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[c][e] = nxt[c][e];
+    if (m + 1 < row_end) load_row(m + 1, nxt);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      if ((c * 256 + tid) * 8 < H)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[c][e];
+    const float mean = block_sum(sum) / H;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      if ((c * 256 + tid) * 8 < H)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sq += (v[c][e] - mean) * (v[c][e] - mean);
+    const float rstd = rsqrtf(block_sum(sq) / H + 1e-5f);
+    if (stats && tid == 0) {
+      stats[2 * m] = mean;
+      stats[2 * m + 1] = rstd;
+    }
+    TOut* gr = g + static_cast<long long>(m) * ldg;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 256 + tid) * 8;
+      if (col < H) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = ptx::gelu_erf((v[c][e] - mean) * rstd * ww[c][e] + bb[c][e]);
+        if constexpr (sizeof(TOut) == 2) {
+          uint4 o;
+          o.x = ptx::pack_bf16(y[0], y[1]);
+          o.y = ptx::pack_bf16(y[2], y[3]);
+          o.z = ptx::pack_bf16(y[4], y[5]);
+          o.w = ptx::pack_bf16(y[6], y[7]);
+          *reinterpret_cast<uint4*>(gr + col) = o;
+        } else {
+          *reinterpret_cast<float4*>(gr + col) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(gr + col + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        }
+      }
+    }
+  }
+}
+
+// Shared-memory-staged variant (the one that is launched): a CTA pulls R whole rows into smem with
+// 1-D bulk copies (cp.async.bulk + mbarrier: no registers tied up, up to 64 KB in flight per CTA,
+// 3 CTAs / SM), takes the statistics with a warp-pair per row, then sweeps column-wise so each
+// thread loads the fp32 affine vectors of its 8 columns ONCE for all R rows.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) ln_gelu_fwd_smem_kernel(const TIn* __restrict__ h, long long ldh,
+                                                               int M, int H,
+                                                               const float* __restrict__ weight,
+                                                               const float* __restrict__ bias,
+                                                               TOut* __restrict__ g, long long ldg,
+                                                               float* __restrict__ stats, int R) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  __shared__ uint64_t bar;
+  __shared__ float red[8];
+  __shared__ float mean_s[8], rstd_s[8];
+  TIn* rows = reinterpret_cast<TIn*>(ln_smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * R;
+  const int nrows = min(R, M - m0);
+  if (tid == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    ptx::mbar_expect_tx(&bar, static_cast<uint32_t>(nrows * H * sizeof(TIn)));
+    for (int r = 0; r < nrows; ++r)
+      ptx::bulk_load_1d(rows + static_cast<size_t>(r) * H, h + static_cast<long long>(m0 + r) * ldh,
+                        static_cast<uint32_t>(H * sizeof(TIn)), &bar);
+  }
+  ptx::mbar_wait(&bar, 0);
+  // statistics: warp w handles row (w % R), slice (w / R) of 8/R equal column slices
+  const int parts = 8 / R;
+  const int r_mine = warp % R, part = warp / R;
+  const int c0 = part * (H / parts), c1 = c0 + H / parts;
+  const TIn* myrow = rows + static_cast<size_t>(r_mine) * H;
+  auto ldv = [&](int col, float (&o)[8]) {
+    if constexpr (sizeof(TIn) == 2) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(myrow + col);
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(p[q]);
+        o[2 * q] = f.x; o[2 * q + 1] = f.y;
+      }
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(myrow + col);
+      const float4 b = *reinterpret_cast<const float4*>(myrow + col + 4);
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    }
+  };
+  float acc = 0.f;
+  if (r_mine < nrows)
+    for (int col = c0 + lane * 8; col < c1; col += 256) {
+      float o[8];
+      ldv(col, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc += o[e];
+    }
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid < R) {
+    float t = 0.f;
+    for (int p2 = 0; p2 < parts; ++p2) t += red[p2 * R + tid];
+    mean_s[tid] = t / H;
+  }
+  __syncthreads();
+  const float mu = mean_s[r_mine];
+  acc = 0.f;
+  if (r_mine < nrows)
+    for (int col = c0 + lane * 8; col < c1; col += 256) {
+      float o[8];
+      ldv(col, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc += (o[e] - mu) * (o[e] - mu);
+    }
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid < R) {
+    float t = 0.f;
+    for (int p2 = 0; p2 < parts; ++p2) t += red[p2 * R + tid];
+    const float rs = rsqrtf(t / H + 1e-5f);
+    rstd_s[tid] = rs;
+    if (stats && tid < nrows) {
+      stats[2 * (m0 + tid)] = mean_s[tid];
+      stats[2 * (m0 + tid) + 1] = rs;
+    }
+  }
+  __syncthreads();
+  // normalise + affine + GELU, column-wise
+  for (int col = tid * 8; col < H; col += 2048) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+    const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int r = 0; r < nrows; ++r) {
+      const float m_r = mean_s[r], rs = rstd_s[r];
+      float o[8], y[8];
+      const TIn* rp = rows + static_cast<size_t>(r) * H + col;
+      if constexpr (sizeof(TIn) == 2) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(rp);
+        const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(p[q]);
+          o[2 * q] = f.x; o[2 * q + 1] = f.y;
+        }
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(rp);
+        const float4 b = *reinterpret_cast<const float4*>(rp + 4);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+      }
+      TOut* gr = g + static_cast<long long>(m0 + r) * ldg + col;
+      if constexpr (sizeof(TOut) == 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = ptx::gelu_fast((o[e] - m_r) * rs * ww[e] + bb[e]);
+        uint4 pk;
+        pk.x = ptx::pack_bf16(y[0], y[1]); pk.y = ptx::pack_bf16(y[2], y[3]);
+        pk.z = ptx::pack_bf16(y[4], y[5]); pk.w = ptx::pack_bf16(y[6], y[7]);
+        *reinterpret_cast<uint4*>(gr) = pk;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = ptx::gelu_erf((o[e] - m_r) * rs * ww[e] + bb[e]);
+        *reinterpret_cast<float4*>(gr) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(gr + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+    }
+  }
+}
+
+// Grouped AdaLN hidden layers: up to 8 (w1, b1, out) items of the same width in one launch.
+struct AdalnGroupDev {
+  const float* w1[8]; const float* b1[8]; __nv_bfloat16* out_bf16[8]; float* out_f32[8];
+  const float* ib; long long ld_ib; int M, ib_num, n, items;
+};
+__global__ void __launch_bounds__(256) adaln_hidden_group_kernel(const AdalnGroupDev a) {
+  const int it = blockIdx.y;
+  const long long total = static_cast<long long>(a.M) * (a.n / 2);
+  const float* w1 = a.w1[it];
+  const float* b1 = a.b1[it];
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(idx / (a.n / 2));
+    const int j = static_cast<int>(idx - static_cast<long long>(m) * (a.n / 2)) * 2;
+    float a0 = b1[j], a1 = b1[j + 1];
+    for (int c = 0; c < a.ib_num; ++c) {
+      const float v = a.ib[static_cast<long long>(m) * a.ld_ib + c];
+      a0 = fmaf(w1[j * a.ib_num + c], v, a0);
+      a1 = fmaf(w1[(j + 1) * a.ib_num + c], v, a1);
+    }
+    a0 = silu(a0);
+    a1 = silu(a1);
+    if (a.out_bf16[it]) *reinterpret_cast<uint32_t*>(a.out_bf16[it] + static_cast<long long>(m) * a.n + j) = ptx::pack_bf16(a0, a1);
+    if (a.out_f32[it]) *reinterpret_cast<float2*>(a.out_f32[it] + static_cast<long long>(m) * a.n + j) = make_float2(a0, a1);
   }
 }
 
@@ -372,8 +588,9 @@ __global__ void colsum_kernel(const float* __restrict__ src_f32, const __nv_bflo
 
 using namespace sea;
 
-extern "C" int sea_adaln_hidden(const float* ib, int M, int ib_num, const float* w1, const float* b1,
-                                int n, void* out_bf16, float* out_f32, sea_stream_t stream) {
+extern "C" int sea_adaln_hidden(const float* ib, int64_t ld_ib, int M, int ib_num, const float* w1,
+                                const float* b1, int n, void* out_bf16, float* out_f32,
+                                sea_stream_t stream) {
   if (!ib || !w1 || !b1 || M <= 0 || n <= 0 || (n % 2) || ib_num <= 0) return SEA_ERR_INVALID;
   if (!out_bf16 && !out_f32) return SEA_ERR_INVALID;
   const long long total = static_cast<long long>(M) * (n / 2);
@@ -381,17 +598,46 @@ extern "C" int sea_adaln_hidden(const float* ib, int M, int ib_num, const float*
   if (nblk > 148LL * 16) nblk = 148LL * 16;
   const int grid = static_cast<int>(nblk);
   adaln_hidden_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      ib, M, ib_num, w1, b1, n, static_cast<__nv_bfloat16*>(out_bf16), out_f32);
+      ib, ld_ib > 0 ? ld_ib : ib_num, M, ib_num, w1, b1, n, static_cast<__nv_bfloat16*>(out_bf16), out_f32);
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int sea_tipi_hidden(const float* ib, int M, int ib_num, const float* w0, const float* b0,
+extern "C" int sea_adaln_hidden_group(int items, const float* const* w1, const float* const* b1,
+                                      void* const* out_bf16, float* const* out_f32, const float* ib,
+                                      int64_t ld_ib, int M, int ib_num, int n, sea_stream_t stream) {
+  if (items < 1 || items > 8 || !w1 || !b1 || !ib || M <= 0 || n <= 0 || (n % 2) || ib_num <= 0) return SEA_ERR_INVALID;
+  AdalnGroupDev d{};
+  for (int i = 0; i < items; ++i) {
+    d.w1[i] = w1[i]; d.b1[i] = b1[i];
+    d.out_bf16[i] = out_bf16 ? static_cast<__nv_bfloat16*>(out_bf16[i]) : nullptr;
+    d.out_f32[i] = out_f32 ? out_f32[i] : nullptr;
+    if (!d.w1[i] || !d.b1[i] || (!d.out_bf16[i] && !d.out_f32[i])) return SEA_ERR_INVALID;
+  }
+  d.ib = ib; d.ld_ib = ld_ib > 0 ? ld_ib : ib_num; d.M = M; d.ib_num = ib_num; d.n = n; d.items = items;
+  const long long total = static_cast<long long>(M) * (n / 2);
+  long long nblk = (total + 255) / 256;
+  if (nblk > 148LL * 8) nblk = 148LL * 8;
+  dim3 grid(static_cast<unsigned>(nblk), items);
+  adaln_hidden_group_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_tipi_hidden(const float* ib, int64_t ld_ib, int M, int ib_num, const float* w0, const float* b0,
                                const float* ln_w, const float* ln_b, int hid, float* g_out,
                                float* pre_out, float* stats_out, sea_stream_t stream) {
   if (!ib || !w0 || !b0 || !ln_w || !ln_b || !g_out || M <= 0 || ib_num <= 0) return SEA_ERR_INVALID;
   if (hid <= 0 || hid > kMaxTipiHid) return SEA_ERR_UNSUPPORTED;
   tipi_hidden_kernel<<<(M + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      ib, M, ib_num, w0, b0, ln_w, ln_b, hid, g_out, pre_out, stats_out);
+      ib, ld_ib > 0 ? ld_ib : ib_num, M, ib_num, w0, b0, ln_w, ln_b, hid, g_out, pre_out, stats_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <int CH>
+static int launch_norm(const NormDev& d, cudaStream_t s) {
+  const int rows_per_cta = 8;
+  const int grid = (d.M + rows_per_cta - 1) / rows_per_cta;
+  if (d.kind == SEA_NORM_ADALN) norm_fwd_kernel<CH, true><<<grid, rows_per_cta * 32, 0, s>>>(d);
+  else norm_fwd_kernel<CH, false><<<grid, rows_per_cta * 32, 0, s>>>(d);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -405,17 +651,66 @@ extern "C" int sea_norm_fwd(const sea_norm_args* a, sea_stream_t stream) {
     return SEA_ERR_INVALID;
   if (a->tipi_g && (!a->tipi_w || !a->tipi_b || !a->x_out || a->tipi_hid <= 0 || (a->ldxo % 4)))
     return SEA_ERR_INVALID;
+  if (a->add_rows && (!a->x_out || (a->ld_add % 4) || (a->ldxo % 4))) return SEA_ERR_INVALID;
   NormDev d;
   d.x = a->x; d.ldx = a->ldx; d.M = a->M; d.d = a->d; d.kind = a->kind;
   d.weight = a->weight; d.bias = a->bias; d.cond = a->cond; d.ldc = a->ldc;
+  d.cond_div = a->cond_div > 0 ? a->cond_div : 1;
+  d.add_rows = a->add_rows; d.ld_add = a->ld_add; d.add_div = a->add_div > 0 ? a->add_div : 1;
   d.tipi_g = a->tipi_g; d.tipi_hid = a->tipi_hid; d.tipi_w = a->tipi_w; d.tipi_b = a->tipi_b;
   d.x_out = a->x_out; d.ldxo = a->ldxo;
   d.y_f32 = a->y_f32; d.ldy_f32 = a->ldy_f32;
   d.y_bf16 = static_cast<__nv_bfloat16*>(a->y_bf16); d.ldy_bf16 = a->ldy_bf16;
   d.stats = a->stats;
-  const int rows_per_cta = 8;
-  norm_fwd_kernel<<<(a->M + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0,
-                    reinterpret_cast<cudaStream_t>(stream)>>>(d);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->d <= 512) return launch_norm<4>(d, s);
+  if (a->d <= 1024) return launch_norm<8>(d, s);
+  return launch_norm<16>(d, s);
+}
+
+extern "C" int sea_tipi_rows(const float* g, int64_t ldg, int R, int E, int hid, const float* w3,
+                             const float* b3, float* out, sea_stream_t stream) {
+  if (!g || !w3 || !b3 || !out || R <= 0 || E <= 0 || hid <= 0) return SEA_ERR_INVALID;
+  dim3 grid((E + 255) / 256, R);
+  tipi_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, ldg, R, E, hid, w3, b3, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <typename TIn, typename TOut>
+static int launch_ln_gelu_smem(const sea_ln_gelu_args* a, const TIn* h, TOut* g, cudaStream_t s) {
+  // R rows per CTA, power of two <= 8, at most 64 KB of rows in shared memory
+  int R = 8;
+  while (R > 1 && static_cast<size_t>(R) * a->H * sizeof(TIn) > 64 * 1024) R >>= 1;
+  while (R > 1 && (a->M + R - 1) / R < 2 * 148) R >>= 1;   // keep the machine full for small M
+  if ((a->H % (8 * (8 / R) )) != 0) R = 1;
+  const size_t smem = static_cast<size_t>(R) * a->H * sizeof(TIn);
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    SEA_CUDA_OK(cudaFuncSetAttribute(ln_gelu_fwd_smem_kernel<TIn, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set[dev] = true;
+  }
+  ln_gelu_fwd_smem_kernel<TIn, TOut><<<(a->M + R - 1) / R, 256, smem, s>>>(h, a->ldh, a->M, a->H, a->weight, a->bias,
+                                                                          g, a->ldg, a->stats, R);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <typename TIn, typename TOut>
+static int launch_ln_gelu(const sea_ln_gelu_args* a, const TIn* h, TOut* g, cudaStream_t s) {
+  if (static_cast<size_t>(a->H) * sizeof(TIn) <= 64 * 1024 && (a->H % 64) == 0 &&
+      (reinterpret_cast<uintptr_t>(h) % 16) == 0 && ((a->ldh * sizeof(TIn)) % 16) == 0)
+    return launch_ln_gelu_smem(a, h, g, s);
+  // rows per CTA: amortise the affine vectors, but keep >= ~2 CTAs per SM in flight
+  int rows = a->M / (2 * 148);
+  rows = rows < 1 ? 1 : (rows > 8 ? 8 : rows);
+  const int grid = (a->M + rows - 1) / rows;
+  if (a->H <= 4096)
+    ln_gelu_fwd_kernel<TIn, TOut, 2><<<grid, 256, 0, s>>>(h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, rows);
+  else if (a->H <= 8192)
+    ln_gelu_fwd_kernel<TIn, TOut, 4><<<grid, 256, 0, s>>>(h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, rows);
+  else
+    ln_gelu_fwd_kernel<TIn, TOut, 8><<<grid, 256, 0, s>>>(h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, rows);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -423,17 +718,10 @@ extern "C" int sea_ln_gelu_fwd(const sea_ln_gelu_args* a, sea_stream_t stream) {
   if (!a || a->M <= 0 || a->H <= 0 || !a->weight || !a->bias) return SEA_ERR_INVALID;
   if ((a->H % 8) || a->H > 16384 || (a->ldh % 8) || (a->ldg % 8)) return SEA_ERR_UNSUPPORTED;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a->h_bf16 && a->g_bf16) {
-    ln_gelu_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<a->M, 256, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(a->h_bf16), a->ldh, a->M, a->H, a->weight, a->bias,
-        static_cast<__nv_bfloat16*>(a->g_bf16), a->ldg, a->stats);
-  } else if (a->h_f32 && a->g_f32) {
-    ln_gelu_fwd_kernel<float, float><<<a->M, 256, 0, s>>>(a->h_f32, a->ldh, a->M, a->H, a->weight,
-                                                          a->bias, a->g_f32, a->ldg, a->stats);
-  } else {
-    return SEA_ERR_INVALID;
-  }
-  return static_cast<int>(cudaGetLastError());
+  if (a->h_bf16 && a->g_bf16)
+    return launch_ln_gelu(a, static_cast<const __nv_bfloat16*>(a->h_bf16), static_cast<__nv_bfloat16*>(a->g_bf16), s);
+  if (a->h_f32 && a->g_f32) return launch_ln_gelu(a, a->h_f32, a->g_f32, s);
+  return SEA_ERR_INVALID;
 }
 
 extern "C" int sea_pack_operand(const sea_pack_args* a, sea_stream_t stream) {

@@ -2,13 +2,14 @@
 //
 //   C[M,N] = A[M,K] · B[N,K]^T   (both operands K-major bf16, fp32 accumulation in TMEM)
 //
-// Roles (192 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+// Roles (320 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
 //   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled A (128x64) and B (BNx64) tiles
 //               into a STAGES-deep shared-memory ring, completion on `full` mbarriers;
 //   warp 1      allocates TMEM (2 accumulator stages x BN columns) and issues tcgen05.mma
 //               (M=128, N=BN, K=16) from lane 0; tcgen05.commit releases ring slots (`empty`)
 //               and publishes finished accumulators (`tfull`);
-//   warps 2..5  epilogue: tcgen05.ld 32x32b (one accumulator row per thread), fused
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, alternating 32-column chunks):
+//               tcgen05.ld 32x32b (one accumulator row per thread), fused
 //               bias / residual / RoPE / GELU' / GELU / dtype casts, vectorised global stores,
 //               then hand the TMEM stage back (`tempty`) so the next tile's MMAs overlap.
 //
@@ -29,7 +30,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kMaxGroups = 4;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_BYTES = BM * BK * 2;
 
 struct DevEpilogue {
@@ -187,7 +188,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
   if (e.out_bf16 != nullptr) {
     if (e.act == SEA_ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = ptx::gelu_erf(v[j]);
+      for (int j = 0; j < 32; ++j) v[j] = ptx::gelu_fast(v[j]);
     }
     __nv_bfloat16* op = e.out_bf16 + static_cast<long long>(m) * e.ld_out_bf16 + n0;
 #pragma unroll
@@ -238,7 +239,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tempty[a], 8);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -305,6 +306,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   } else {
     // --------------------------------------------------------------- epilogue
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    const int half = (warp - 2) >> 2;  // two warps share a lane quarter and split the column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -321,7 +323,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           uint32_t regs[32];
           ptx::tmem_ld_32x32(t_row + c * 32, regs);
           ptx::tmem_ld_wait();

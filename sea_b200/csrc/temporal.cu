@@ -249,6 +249,7 @@ void layout_tape(const sea_temporal_desc* d, int B, int T, bool training, Arena&
     lt.tipi_g = f32(M * d->ib_hidden);
     lt.tipi_pre = f32(M * d->ib_hidden);
     lt.tipi_st = f32(M * 2);
+    lt.tipi_rows = f32(static_cast<size_t>(B) * E);
     for (int i = 0; i < V; ++i) {
       StreamTape& s = lt.s[i];
       if (ada) {
@@ -282,6 +283,25 @@ void layout_tape(const sea_temporal_desc* d, int B, int T, bool training, Arena&
     const size_t kmax = H > 2 * E ? H : 2 * E;
     for (int g = 0; g < SEA_MAX_STREAMS; ++g) t.packA[g] = static_cast<bf16*>(ar.take(M * 6 * kmax * 2));
   }
+}
+
+// Outputs of the condition path that later kernels read, placed in a persistent caller-owned
+// buffer (one row per trajectory) so a rollout can reuse them across forward calls.
+void layout_cond_cache(const sea_temporal_desc* d, int B, Arena& ar, Tape& t) {
+  const size_t E = d->embed_dim, Dd = d->down_dim, R = static_cast<size_t>(B);
+  const bool ada = d->norm_kind == SEA_NORM_ADALN;
+  auto f32 = [&](size_t n) { return static_cast<float*>(ar.take(n * 4)); };
+  for (int l = 0; l < d->num_layers; ++l) {
+    float* rows = f32(R * E);
+    if (!t.L.empty()) t.L[l].tipi_rows = rows;
+    for (int i = 0; i < d->num_streams; ++i) {
+      if (!ada) continue;
+      float* c0 = f32(R * 2 * E); float* c2 = f32(R * 2 * E); float* cc = f32(R * 2 * Dd);
+      if (!t.L.empty()) { t.L[l].s[i].cond0 = c0; t.L[l].s[i].cond2 = c2; t.L[l].s[i].condc = cc; }
+    }
+  }
+  for (int i = 0; i < d->num_streams; ++i)
+    if (ada) { float* cf = f32(R * 2 * E); t.condF[i] = cf; }
 }
 
 // ------------------------------------------------------------------------------ op helpers
@@ -347,8 +367,11 @@ int norm_op(Ctx& c, int kind, const sea_norm_params& np, const float* cond, cons
   a.x = x; a.ldx = ldx; a.M = c.M; a.d = dim; a.kind = kind;
   a.weight = np.weight.p;
   a.bias = kind == SEA_NORM_ADALN ? np.bias.p : nullptr;
-  a.cond = cond; a.ldc = 2LL * dim;
-  if (tipi) {
+  a.cond = cond; a.ldc = 2LL * dim; a.cond_div = c.cond_div;
+  if (tipi && c.cond_div > 1) {
+    a.add_rows = tipi_g; a.ld_add = dim; a.add_div = c.cond_div;  // tipi_g = per-trajectory TIPI rows
+    a.x_out = x_out; a.ldxo = dim;
+  } else if (tipi) {
     a.tipi_g = tipi_g; a.tipi_hid = c.d->ib_hidden;
     a.tipi_w = tipi->ib3_w.p; a.tipi_b = tipi->ib3_b.p;
     a.x_out = x_out; a.ldxo = dim;
@@ -385,20 +408,34 @@ static int adaln_cond(Ctx& c, int n, const sea_norm_params* const* np, void* con
   // cond = Linear(2d,2d)(SiLU(Linear(ib_num,2d)(ib)))   models/base_blocks.py:337-344
   LinIn in[SEA_MAX_STREAMS];
   LinOut out[SEA_MAX_STREAMS];
+  const float* w1[SEA_MAX_STREAMS]; const float* b1[SEA_MAX_STREAMS];
+  void* ob[SEA_MAX_STREAMS]; float* of[SEA_MAX_STREAMS];
   for (int g = 0; g < n; ++g) {
-    SEA_TRY(sea_adaln_hidden(ib, c.M, c.d->ib_num, np[g]->c0_w.p, np[g]->c0_b.p, d2,
-                             c.fp32 ? nullptr : hid[g], c.fp32 ? static_cast<float*>(hid[g]) : nullptr,
-                             reinterpret_cast<sea_stream_t>(c.s)));
-    ++g_launches;
+    w1[g] = np[g]->c0_w.p; b1[g] = np[g]->c0_b.p;
+    ob[g] = c.fp32 ? nullptr : hid[g];
+    of[g] = c.fp32 ? static_cast<float*>(hid[g]) : nullptr;
+  }
+  SEA_TRY(sea_adaln_hidden_group(n, w1, b1, ob, of, ib, c.ld_ib, c.Mc, c.d->ib_num, d2,
+                                 reinterpret_cast<sea_stream_t>(c.s)));
+  ++g_launches;
+  for (int g = 0; g < n; ++g) {
     in[g] = LinIn{hid[g], d2, 0};
     out[g] = LinOut{};
     out[g].bias = np[g]->c2_b.p;
     out[g].f32 = cond[g]; out[g].ld_f32 = d2;
   }
-  return linear_group(c, n, in, W, out, c.M);
+  return linear_group(c, n, in, W, out, c.Mc);
 }
 
 }  // namespace sea
+
+extern "C" size_t sea_temporal_cond_cache_bytes(const sea_temporal_desc* d, int B) {
+  if (!d || B <= 0) return 0;
+  Arena ar{nullptr};
+  Tape t;
+  layout_cond_cache(d, B, ar, t);
+  return ar.off + 256;
+}
 
 extern "C" size_t sea_temporal_workspace_bytes(const sea_temporal_desc* d, int B, int T, int training) {
   if (!d || B <= 0 || T <= 0) return 0;
@@ -434,6 +471,11 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
   c.s = reinterpret_cast<cudaStream_t>(stream);
   c.fp32 = d->precision == SEA_PREC_FP32;
   c.B = B; c.T = T; c.M = B * T;
+  // time-invariant condition (inference): one cond / TIPI row per trajectory instead of per token
+  const bool inv = d->ib_time_invariant != 0 && training == 0 && T > 1;
+  c.Mc = inv ? B : c.M;
+  c.ld_ib = inv ? static_cast<long long>(T) * d->ib_num : d->ib_num;
+  c.cond_div = inv ? T : 1;
   const int M = c.M, V = d->num_streams, E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
   const int hd = E / d->n_heads, hdc = Dd / d->n_heads;
   const bool ada = d->norm_kind == SEA_NORM_ADALN;
@@ -442,38 +484,61 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
   sea_stream_t st = stream;
 
   // ---- everything that depends on ib only: TIPI hidden + all AdaLN conditions (hoisted) ----
-  for (int l = 0; l < d->num_layers; ++l) {
-    const sea_block_params& bp = d->blocks[l];
-    LayerTape& lt = tape.L[l];
-    SEA_TRY(sea_tipi_hidden(ib, M, d->ib_num, bp.ib0_w.p, bp.ib0_b.p, bp.ib_ln_w.p, bp.ib_ln_b.p,
-                            d->ib_hidden, lt.tipi_g, lt.tipi_pre, lt.tipi_st, st));
-    ++g_launches;
+  // With a time-invariant condition the results live in the caller's persistent cond cache and
+  // are reused by later calls on the same trajectories (the rollout loop) while it stays valid.
+  bool reuse = false;
+  if (inv && d->cond_cache != nullptr) {
+    if (d->cond_cache_bytes < sea_temporal_cond_cache_bytes(d, B)) return SEA_ERR_WORKSPACE;
+    Arena cca{static_cast<char*>(d->cond_cache)};
+    layout_cond_cache(d, B, cca, tape);
+    reuse = d->cond_cache_valid != 0;
+  }
+  if (!reuse) {
+    for (int l = 0; l < d->num_layers; ++l) {
+      const sea_block_params& bp = d->blocks[l];
+      LayerTape& lt = tape.L[l];
+      SEA_TRY(sea_tipi_hidden(ib, c.ld_ib, c.Mc, d->ib_num, bp.ib0_w.p, bp.ib0_b.p, bp.ib_ln_w.p, bp.ib_ln_b.p,
+                              d->ib_hidden, lt.tipi_g, lt.tipi_pre, lt.tipi_st, st));
+      ++g_launches;
+      if (inv) {
+        SEA_TRY(sea_tipi_rows(lt.tipi_g, d->ib_hidden, B, E, d->ib_hidden, bp.ib3_w.p, bp.ib3_b.p, lt.tipi_rows, st));
+        ++g_launches;
+      }
+      if (ada) {
+        const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
+        const PackedLinear* W[SEA_MAX_STREAMS]; float* cond[SEA_MAX_STREAMS];
+        if (2 * V <= SEA_MAX_STREAMS) {  // ln0 and ln2 of every stream in one grouped launch
+          for (int i = 0; i < V; ++i) {
+            np[i] = &bp.s[i].ln0; hid[i] = lt.s[i].hid0; W[i] = &cl.blocks[l].s[i].c2_ln0; cond[i] = lt.s[i].cond0;
+            np[V + i] = &bp.s[i].ln2; hid[V + i] = lt.s[i].hid2; W[V + i] = &cl.blocks[l].s[i].c2_ln2; cond[V + i] = lt.s[i].cond2;
+          }
+          SEA_TRY(adaln_cond(c, 2 * V, np, hid, W, cond, 2 * E, ib));
+        } else {
+          for (int which = 0; which < 2; ++which) {
+            for (int i = 0; i < V; ++i) {
+              np[i] = which ? &bp.s[i].ln2 : &bp.s[i].ln0;
+              hid[i] = which ? lt.s[i].hid2 : lt.s[i].hid0;
+              W[i] = which ? &cl.blocks[l].s[i].c2_ln2 : &cl.blocks[l].s[i].c2_ln0;
+              cond[i] = which ? lt.s[i].cond2 : lt.s[i].cond0;
+            }
+            SEA_TRY(adaln_cond(c, V, np, hid, W, cond, 2 * E, ib));
+          }
+        }
+        for (int i = 0; i < V; ++i) {
+          np[i] = &bp.s[i].ln_cross; hid[i] = lt.s[i].hidc;
+          W[i] = &cl.blocks[l].s[i].c2_lnc; cond[i] = lt.s[i].condc;
+        }
+        SEA_TRY(adaln_cond(c, V, np, hid, W, cond, 2 * Dd, ib));
+      }
+    }
     if (ada) {
       const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
       const PackedLinear* W[SEA_MAX_STREAMS]; float* cond[SEA_MAX_STREAMS];
-      for (int which = 0; which < 2; ++which) {
-        for (int i = 0; i < V; ++i) {
-          np[i] = which ? &bp.s[i].ln2 : &bp.s[i].ln0;
-          hid[i] = which ? lt.s[i].hid2 : lt.s[i].hid0;
-          W[i] = which ? &cl.blocks[l].s[i].c2_ln2 : &cl.blocks[l].s[i].c2_ln0;
-          cond[i] = which ? lt.s[i].cond2 : lt.s[i].cond0;
-        }
-        SEA_TRY(adaln_cond(c, V, np, hid, W, cond, 2 * E, ib));
-      }
       for (int i = 0; i < V; ++i) {
-        np[i] = &bp.s[i].ln_cross; hid[i] = lt.s[i].hidc;
-        W[i] = &cl.blocks[l].s[i].c2_lnc; cond[i] = lt.s[i].condc;
+        np[i] = &d->final_ln[i]; hid[i] = tape.hidF[i]; W[i] = &cl.c2_final[i]; cond[i] = tape.condF[i];
       }
-      SEA_TRY(adaln_cond(c, V, np, hid, W, cond, 2 * Dd, ib));
+      SEA_TRY(adaln_cond(c, V, np, hid, W, cond, 2 * E, ib));
     }
-  }
-  if (ada) {
-    const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
-    const PackedLinear* W[SEA_MAX_STREAMS]; float* cond[SEA_MAX_STREAMS];
-    for (int i = 0; i < V; ++i) {
-      np[i] = &d->final_ln[i]; hid[i] = tape.hidF[i]; W[i] = &cl.c2_final[i]; cond[i] = tape.condF[i];
-    }
-    SEA_TRY(adaln_cond(c, V, np, hid, W, cond, 2 * E, ib));
   }
 
   // ---- layers ----
@@ -587,7 +652,7 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
     // (3) x_i += TIPI(ib) fused with Norm_{i,2}; (4) MLP; (5) proj    models/temporal.py:140-146
     for (int i = 0; i < V; ++i)
       SEA_TRY(norm_op(c, kind, bp.s[i].ln2, lt.s[i].cond2, lt.s[i].xp, E, E, lt.s[i].n2, nullptr, 0,
-                      lt.s[i].st2, &bp, lt.tipi_g, lt.s[i].x2));
+                      lt.s[i].st2, &bp, inv ? lt.tipi_rows : lt.tipi_g, lt.s[i].x2));
     for (int i = 0; i < V; ++i) {
       in[i] = LinIn{lt.s[i].n2, E, 0};
       W[i] = &bc.s[i].mlp0;

@@ -254,6 +254,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
   b.c.d = d; b.c.cache = &cl; b.c.tape = &tape;
   b.c.s = reinterpret_cast<cudaStream_t>(stream);
   b.c.fp32 = false; b.c.B = B; b.c.T = T; b.c.M = B * T;
+  b.c.Mc = b.c.M; b.c.ld_ib = d->ib_num; b.c.cond_div = 1;
   b.ib = ib; b.bt = &bt;
   b.Mp = (static_cast<long long>(b.c.M) + 7) & ~7LL;
   const int M = b.c.M, V = d->num_streams, E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;

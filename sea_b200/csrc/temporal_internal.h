@@ -66,6 +66,7 @@ struct StreamTape {
 struct LayerTape {
   StreamTape s[SEA_MAX_STREAMS];
   float *tipi_g, *tipi_pre, *tipi_st;
+  float* tipi_rows;  // [B,E] TIPI output per trajectory (time-invariant condition)
 };
 struct Tape {
   std::vector<LayerTape> L;
@@ -108,6 +109,9 @@ struct Ctx {
   cudaStream_t s;
   bool fp32;
   int B, T, M;
+  int Mc;            // rows of the condition path (M, or B when ib is time-invariant)
+  long long ld_ib;   // row pitch of ib for the condition path
+  int cond_div;      // token row m uses condition row m / cond_div
 };
 
 struct LinIn {
@@ -127,6 +131,7 @@ struct LinOut {
 
 void layout_cache(const sea_temporal_desc* d, bool training, Arena& ar, CacheLayout& c);
 void layout_tape(const sea_temporal_desc* d, int B, int T, bool training, Arena& ar, Tape& t);
+void layout_cond_cache(const sea_temporal_desc* d, int B, Arena& ar, Tape& t);
 int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, const LinOut* out, int Mrows);
 
 extern thread_local int g_launches;

@@ -81,7 +81,7 @@ def adaln_hidden(ib, w1, b1, out_dtype=torch.bfloat16):
     out = torch.empty(M, n, device=ib.device, dtype=out_dtype)
     ob = _ptr(out) if out_dtype == torch.bfloat16 else None
     of = _ptr(out) if out_dtype == torch.float32 else None
-    check(lib.sea_adaln_hidden(_ptr(ib), M, ib_num, _ptr(w1), _ptr(b1), n, ob, of, _stream()), "adaln_hidden")
+    check(lib.sea_adaln_hidden(_ptr(ib), C.c_int64(ib.stride(0)), M, ib_num, _ptr(w1), _ptr(b1), n, ob, of, _stream()), "adaln_hidden")
     return out
 
 
@@ -89,7 +89,7 @@ def tipi_hidden(ib, w0, b0, ln_w, ln_b):
     M, ib_num = ib.shape
     hid = w0.shape[0]
     g = torch.empty(M, hid, device=ib.device)
-    check(lib.sea_tipi_hidden(_ptr(ib), M, ib_num, _ptr(w0), _ptr(b0), _ptr(ln_w), _ptr(ln_b), hid,
+    check(lib.sea_tipi_hidden(_ptr(ib), C.c_int64(ib.stride(0)), M, ib_num, _ptr(w0), _ptr(b0), _ptr(ln_w), _ptr(ln_b), hid,
                               _ptr(g), None, None, _stream()), "tipi_hidden")
     return g
 

@@ -16,13 +16,40 @@ class ProfileSummary(C.Structure):
     _fields_ = [("ms", C.c_double * 3), ("work", C.c_double * 3), ("launches", C.c_int64 * 3)]
 
 
+def _engine_of(model):
+    eng = getattr(model, "_sea_engine", None)
+    if eng is None and hasattr(model, "engine"):
+        eng = model.engine()
+    return eng
+
+
 @torch.no_grad()
-def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int) -> torch.Tensor:
-    """x0 [B,1,V,E], ib [B,>=steps,ib_num] -> predicted latents [B,steps,V,E]."""
-    seq = x0
-    for i in range(steps):
-        out = model(seq, ib[:, : i + 1])
-        seq = torch.cat((seq, out[:, -1:]), dim=1)
+def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
+            ib_time_invariant: bool | None = None) -> torch.Tensor:
+    """x0 [B,1,V,E], ib [B,>=steps,ib_num] -> predicted latents [B,steps,V,E].
+
+    ``ib`` is the time-invariant physical parameter of a trajectory in the reference's data
+    (models/temporal.py:111-120 "TIPI").  When every ib[b, t] equals ib[b, 0] (checked once here on
+    the device unless the caller passes the answer), the AdaLN cond_mlp and the TIPI MLP are
+    evaluated once per trajectory instead of once per token; the result is the same function of
+    the same inputs."""
+    eng = _engine_of(model)
+    if ib_time_invariant is None:
+        ib_time_invariant = bool((ib[:, :steps] == ib[:, :1]).all().item())
+    prev = None
+    if eng is not None:
+        prev, eng.ib_time_invariant = eng.ib_time_invariant, ib_time_invariant
+        # same trajectories, same weights, same ib for every step of this loop
+        eng.cond_reuse, eng._cond_valid = bool(ib_time_invariant), False
+    try:
+        seq = x0
+        for i in range(steps):
+            out = model(seq, ib[:, : i + 1])
+            seq = torch.cat((seq, out[:, -1:]), dim=1)
+    finally:
+        if eng is not None:
+            eng.ib_time_invariant = prev
+            eng.cond_reuse, eng._cond_valid = False, False
     return seq[:, 1:]
 
 

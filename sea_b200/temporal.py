@@ -204,6 +204,13 @@ class TemporalEngine:
         self._grad_views = {}
         self.last_launches = 0
         self.total_launches = 0
+        # caller-asserted: ib[b,t] == ib[b,0] for all t (set by sea_b200.rollout after checking it)
+        self.ib_time_invariant = False
+        # rollout(): the condition path's outputs are kept across calls while (B, weights, ib) are fixed
+        self.cond_reuse = False
+        self._cond_valid = False
+        self._cond_buf = None
+        self._cond_key = None
 
     # -- hyper-parameters are read off the module tree (works for the mirror and the reference) --
     def _hyper(self):
@@ -432,6 +439,19 @@ class TemporalEngine:
         y = torch.empty_like(x)
         if ws is None:
             ws = self.workspace(B, T, training)
+        inv = bool(self.ib_time_invariant) and not training
+        self._desc.ib_time_invariant = int(inv)
+        self._desc.cond_cache, self._desc.cond_cache_bytes, self._desc.cond_cache_valid = None, 0, 0
+        use_cc = inv and self.cond_reuse and T > 1
+        if use_cc:
+            key = (B, self._cache_key)
+            if self._cond_key != key or self._cond_buf is None:
+                n = lib.sea_temporal_cond_cache_bytes(C.byref(self._desc), B)
+                self._cond_buf = torch.empty(n, dtype=torch.uint8, device=self._dev)
+                self._cond_key, self._cond_valid = key, False
+            self._desc.cond_cache = self._cond_buf.data_ptr()
+            self._desc.cond_cache_bytes = self._cond_buf.numel()
+            self._desc.cond_cache_valid = int(self._cond_valid)
         with torch.cuda.device(x.device):
             check(lib.sea_temporal_forward(C.byref(self._desc), C.c_void_p(self._cache.data_ptr()),
                                            C.c_void_p(x.data_ptr()), C.c_void_p(ib.data_ptr()),
@@ -439,6 +459,8 @@ class TemporalEngine:
                                            C.c_size_t(ws.numel()), int(training),
                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                   "temporal_forward")
+        if use_cc:
+            self._cond_valid = True
         self.last_launches = lib.sea_last_launch_count()
         self.total_launches += self.last_launches
         return y

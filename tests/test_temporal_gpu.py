@@ -82,3 +82,28 @@ def test_forward_matches_oracle_at_config_shape(cuda):
               f"launches = {m.engine().last_launches}")
         assert err < TOL[precision]
         del m
+
+
+@pytest.mark.parametrize("tag,ln", [("small_adaln", "adaln"), ("small_ln", "ln"), ("cylinder_flow", "adaln")])
+def test_time_invariant_condition_path_is_equivalent(cuda, tag, ln):
+    """rollout() with a per-trajectory-constant ib takes the deduplicated cond/TIPI path; it must
+    match the generic path and the oracle."""
+    from sea_b200.rollout import rollout
+    g, sd, cfg, m, x, ib, _, _ = build(tag, ln, "bf16", cuda)
+    B = x.shape[0]
+    steps = 6
+    ibc = ib[:, :1].expand(B, steps, 1).contiguous()
+    r_fast = rollout(m, x[:, :1], ibc, steps)                       # detects invariance
+    assert m.engine().ib_time_invariant is False                      # restored afterwards
+    r_gen = rollout(m, x[:, :1], ibc, steps, ib_time_invariant=False)
+    with torch.no_grad():
+        ref = so.rollout(x[:, :1].cpu(), ibc.cpu(), steps, sd, **cfg)
+    e_fast, e_gen = rel_l2(r_fast.cpu(), ref), rel_l2(r_gen.cpu(), ref)
+    print(f"\n[ib-invariant path] {tag}: fast {e_fast:.3e}  generic {e_gen:.3e}")
+    assert e_fast < TOL["bf16"] and e_gen < TOL["bf16"]
+    assert rel_l2(r_fast, r_gen) < 1e-2
+    # a time-varying ib must NOT take the fast path
+    r_var = rollout(m, x[:, :1], ib[:, :steps], steps)
+    with torch.no_grad():
+        ref_var = so.rollout(x[:, :1].cpu(), ib[:, :steps].cpu(), steps, sd, **cfg)
+    assert rel_l2(r_var.cpu(), ref_var) < TOL["bf16"]
