@@ -76,7 +76,8 @@ typedef struct sea_gemm_epilogue {
   int32_t head_dim;         /* multiple of 32 */
   int32_t seq_len;          /* position of row m is (m % seq_len); rope_sign=-1 rotates back */
   float rope_sign;          /* +1 forward, -1 inverse rotation (backward) */
-  const float* rope_table;  /* [>=seq_len, head_dim/2, 2] fp32 (cos, sin) */
+  int32_t rope_ld;          /* positions per table row (>= seq_len) */
+  const float* rope_table;  /* PAIR-MAJOR [head_dim/2, rope_ld, 2] fp32 (cos, sin): coalesced across rows */
   float* out_f32;
   int64_t ld_out_f32;
   void* out_pre_bf16;
@@ -303,7 +304,8 @@ typedef struct sea_attn_bwd_args {
   int32_t src_len;
   float scale;
   int32_t prec;
-  const float* rope_table; /* [>=T, head_dim/2, 2] or NULL */
+  const float* rope_table; /* pair-major [head_dim/2, rope_ld, 2] or NULL */
+  int32_t rope_ld;
 } sea_attn_bwd_args;
 int sea_attention_bwd(const sea_attn_bwd_args* args, sea_stream_t stream);
 /* Test hook: 1 forces the CUDA-core kernel even where the tcgen05 kernel applies. */
@@ -362,8 +364,8 @@ typedef struct sea_temporal_desc {
   size_t cond_cache_bytes;
   const sea_block_params* blocks; /* host array [num_layers] */
   sea_norm_params final_ln[SEA_MAX_STREAMS]; /* ln.{i} */
-  const float* rope_self;  /* device [max_len, (E/n_heads)/2, 2] (cos, sin) */
-  const float* rope_cross; /* device [max_len, (down_dim/n_heads)/2, 2] */
+  const float* rope_self;  /* device, pair-major [(E/n_heads)/2, max_len, 2] (cos, sin) */
+  const float* rope_cross; /* device, pair-major [(down_dim/n_heads)/2, max_len, 2] */
 } sea_temporal_desc;
 
 /* Packed low-precision copies of the weights (bf16, fused QKV / KV, optional transposes for the

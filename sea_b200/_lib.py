@@ -28,6 +28,7 @@ class GemmEpilogue(C.Structure):
         ("head_dim", C.c_int32),
         ("seq_len", C.c_int32),
         ("rope_sign", C.c_float),
+        ("rope_ld", C.c_int32),
         ("rope_table", C.c_void_p),
         ("out_f32", C.c_void_p),
         ("ld_out_f32", C.c_int64),

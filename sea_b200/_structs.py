@@ -104,7 +104,7 @@ class AttnBwdArgs(C.Structure):
                 ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddq", C.c_int64),
                 ("lddk", C.c_int64), ("lddv", C.c_int64), ("B", C.c_int32), ("T", C.c_int32),
                 ("n_heads", C.c_int32), ("head_dim", C.c_int32), ("src_len", C.c_int32),
-                ("scale", C.c_float), ("prec", C.c_int32), ("rope_table", C.c_void_p)]
+                ("scale", C.c_float), ("prec", C.c_int32), ("rope_table", C.c_void_p), ("rope_ld", C.c_int32)]
 
 
 class TipiBwdArgs(C.Structure):

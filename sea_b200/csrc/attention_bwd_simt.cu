@@ -40,6 +40,7 @@ struct BwdDev {
   int B, T, n_heads, hd, src_len;
   float scale;
   const float* rope;
+  int rope_ld;
 };
 
 template <typename T>
@@ -62,10 +63,10 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const BwdDev a) {
 }
 
 // value of column d = lane + 32c, rotated back:  d even: y*c + partner*s ; d odd: y*c - partner*s
-__device__ __forceinline__ float unrope(float y, int d, int t, int hd, const float* rope, int lane) {
+__device__ __forceinline__ float unrope(float y, int d, int t, int rope_ld, const float* rope, int lane) {
   const float partner = __shfl_xor_sync(0xffffffffu, y, 1);
   if (rope == nullptr) return y;
-  const float2 cs = *reinterpret_cast<const float2*>(rope + (static_cast<long long>(t) * (hd >> 1) + (d >> 1)) * 2);
+  const float2 cs = *reinterpret_cast<const float2*>(rope + (static_cast<long long>(d >> 1) * rope_ld + t) * 2);
   return (lane & 1) ? (y * cs.x - partner * cs.y) : (y * cs.x + partner * cs.y);
 }
 
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_bwd_dq_kernel(const BwdDev a
     for (int c = 0; c < 8; ++c) {
       if (c < dpl) {
         const int d = lane + 32 * c;
-        const float v = unrope(acc[i][c], d, min(q, a.T - 1), hd, a.rope, lane);
+        const float v = unrope(acc[i][c], d, min(q, a.T - 1), a.rope_ld, a.rope, lane);
         if (q < a.T) stf(DQ + (row0 + q) * a.lddq + h * hd + d, v);
       }
     }
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_bwd_dkdv_kernel(const BwdDev
     for (int c = 0; c < 8; ++c) {
       if (c < dpl) {
         const int d = lane + 32 * c;
-        const float kv = unrope(dk[i][c], d, min(key, a.T - 1), hd, a.rope, lane);
+        const float kv = unrope(dk[i][c], d, min(key, a.T - 1), a.rope_ld, a.rope, lane);
         if (key < a.T) {
           stf(DK + (row0 + key) * a.lddk + h * hd + d, kv);
           stf(DV + (row0 + key) * a.lddv + h * hd + d, dv[i][c]);
@@ -320,7 +321,7 @@ extern "C" int sea_attention_bwd(const sea_attn_bwd_args* a, sea_stream_t stream
   d.lse = a->lse; d.delta = a->delta;
   d.dq = a->dq; d.dk = a->dk; d.dv = a->dv; d.lddq = a->lddq; d.lddk = a->lddk; d.lddv = a->lddv;
   d.B = a->B; d.T = a->T; d.n_heads = a->n_heads; d.hd = a->head_dim; d.src_len = a->src_len;
-  d.scale = a->scale; d.rope = a->rope_table;
+  d.scale = a->scale; d.rope = a->rope_table; d.rope_ld = a->rope_ld;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a->prec == SEA_PREC_FP32) return launch_bwd<float>(d, s);
   if (a->prec == SEA_PREC_BF16) return launch_bwd<__nv_bfloat16>(d, s);

@@ -453,8 +453,9 @@ __global__ void __launch_bounds__(256) ln_gelu_fwd_smem_kernel(const TIn* __rest
       }
       TOut* gr = g + static_cast<long long>(m0 + r) * ldg + col;
       if constexpr (sizeof(TOut) == 2) {
+const float a1 = rs, c1 = -m_r * rs;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = ptx::gelu_fast((o[e] - m_r) * rs * ww[e] + bb[e]);
+        for (int e = 0; e < 8; ++e) y[e] = ptx::gelu_bf16(fmaf(fmaf(o[e], a1, c1), ww[e], bb[e]));
         uint4 pk;
         pk.x = ptx::pack_bf16(y[0], y[1]); pk.y = ptx::pack_bf16(y[2], y[3]);
         pk.z = ptx::pack_bf16(y[4], y[5]); pk.w = ptx::pack_bf16(y[6], y[7]);

@@ -42,7 +42,7 @@ struct DevEpilogue {
   __nv_bfloat16* out_pre_bf16;
   __nv_bfloat16* out_bf16;
   long long ld_residual, ld_gelu, ld_out_f32, ld_out_pre_bf16, ld_out_bf16;
-  int act, rope_cols, head_dim, seq_len;
+  int act, rope_cols, head_dim, seq_len, rope_ld;
   float rope_sign;
 };
 
@@ -135,13 +135,15 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
   }
   if (e.rope_table != nullptr && n0 < e.rope_cols) {
     // models/base_blocks.py:314-324 — interleaved pairs (x[2k], x[2k+1]) times (cos + i sin).
+    // table is pair-major: tab[pair][t]; the 32 lanes of a warp hold consecutive rows, i.e.
+    // consecutive t, so every load instruction reads one contiguous 256-byte run
     const int t = m % e.seq_len;
     const int d0 = n0 % e.head_dim;
     const float2* tab = reinterpret_cast<const float2*>(e.rope_table) +
-                        static_cast<long long>(t) * (e.head_dim >> 1) + (d0 >> 1);
+                        static_cast<long long>(d0 >> 1) * e.rope_ld + t;
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      const float2 cs = __ldg(tab + (j >> 1));
+      const float2 cs = __ldg(tab + static_cast<long long>(j >> 1) * e.rope_ld);
       const float s = cs.y * e.rope_sign;
       const float x0 = v[j], x1 = v[j + 1];
       v[j] = x0 * cs.x - x1 * s;
@@ -443,7 +445,8 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
       return SEA_ERR_INVALID;
     if (e.bias && (reinterpret_cast<uintptr_t>(e.bias) & 15)) return SEA_ERR_INVALID;
     if (e.rope_table != nullptr && e.rope_cols > 0) {
-      if (e.head_dim <= 0 || (e.head_dim % 32) || (e.rope_cols % e.head_dim) || e.seq_len <= 0)
+      if (e.head_dim <= 0 || (e.head_dim % 32) || (e.rope_cols % e.head_dim) || e.seq_len <= 0 ||
+          e.rope_ld < e.seq_len)
         return SEA_ERR_UNSUPPORTED;
     }
     rc = make_tmap_bf16_2d(&p.tma_a[g], q.a, K, M, q.lda, BK, BM);
@@ -467,6 +470,7 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
     d.rope_cols = e.rope_cols;
     d.head_dim = e.head_dim;
     d.seq_len = e.seq_len;
+    d.rope_ld = e.rope_ld;
     d.rope_sign = (e.rope_sign == 0.0f) ? 1.0f : e.rope_sign;
   }
   const int total = p.tiles_m * p.tiles_n * p.groups;

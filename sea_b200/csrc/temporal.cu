@@ -334,7 +334,7 @@ int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, c
     e.act = o.act;
     if (o.rope_cols > 0) {
       e.rope_cols = o.rope_cols; e.head_dim = o.head_dim; e.seq_len = c.T;
-      e.rope_table = o.rope_table; e.rope_sign = 1.f;
+      e.rope_table = o.rope_table; e.rope_sign = 1.f; e.rope_ld = c.d->max_len;
     }
     if (c.fp32) {
       // exactly one fp32 destination in the parity mode

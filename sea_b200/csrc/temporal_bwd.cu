@@ -186,7 +186,7 @@ int attention_bwd(BCtx& b, const bf16* q, long long ldq, const bf16* k, const bf
   a.B = b.c.B; a.T = b.c.T; a.n_heads = b.c.d->n_heads; a.head_dim = hd; a.src_len = b.c.d->src_len;
   a.scale = 1.0f / sqrtf(static_cast<float>(hd));
   a.prec = SEA_PREC_BF16;
-  a.rope_table = rope;
+  a.rope_table = rope; a.rope_ld = b.c.d->max_len;
   g_launches += 3;
   ProfScope prof(b.c.s, SEA_PROF_ATTN, 5.0 * b.c.B * b.c.d->n_heads * static_cast<double>(b.c.T) * b.c.T * hd);
   return sea_attention_bwd(&a, b.st());

@@ -31,9 +31,11 @@ def gemm_problem(a, b, *, bias=None, residual=None, gelu_grad_of=None, act=ACT_N
                  out_f32=None, out_pre_bf16=None, out_bf16=None) -> GemmProblem:
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.stride(1) == 1 and b.stride(1) == 1
+    # rope_table: pair-major [head_dim/2, rope_ld, 2]
+    rope_ld = 0 if rope_table is None else int(rope_table.shape[1])
     e = GemmEpilogue(
         _ptr(bias), _ptr(residual), _ld(residual), _ptr(gelu_grad_of), _ld(gelu_grad_of), act,
-        rope_cols, head_dim, seq_len, float(rope_sign), _ptr(rope_table),
+        rope_cols, head_dim, seq_len, float(rope_sign), rope_ld, _ptr(rope_table),
         _ptr(out_f32), _ld(out_f32), _ptr(out_pre_bf16), _ld(out_pre_bf16),
         _ptr(out_bf16), _ld(out_bf16))
     return GemmProblem(_ptr(a), a.stride(0), _ptr(b), b.stride(0), e)
@@ -209,5 +211,6 @@ def attention_bwd(q, k, v, o, d_o, lse, n_heads, *, B=1, src_len=0, rope_table=N
     a.scale = hd ** -0.5
     a.prec = 0 if q.dtype == torch.bfloat16 else 1
     a.rope_table = None if rope_table is None else rope_table.data_ptr()
+    a.rope_ld = 0 if rope_table is None else int(rope_table.shape[1])
     check(lib.sea_attention_bwd(C.byref(a), _stream()), "attention_bwd")
     return dq, dk, dv

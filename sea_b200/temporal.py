@@ -341,8 +341,9 @@ class TemporalEngine:
 
         b0 = m.blocks[0]
         j0 = 1 if V > 1 else 0
-        rope_self = torch.view_as_real(b0.attn["self"][0].freqs_cis).contiguous().float()
-        rope_cross = torch.view_as_real(b0.cross_attn[0][j0].freqs_cis).contiguous().float()
+        # pair-major [hd/2, max_len, 2]: consecutive positions are contiguous (coalesced epilogue reads)
+        rope_self = torch.view_as_real(b0.attn["self"][0].freqs_cis).float().transpose(0, 1).contiguous()
+        rope_cross = torch.view_as_real(b0.cross_attn[0][j0].freqs_cis).float().transpose(0, 1).contiguous()
         d = S.TemporalDesc()
         d.num_layers, d.num_streams = L, V
         d.embed_dim, d.n_heads, d.hidden_dim, d.down_dim = h["E"], h["nh"], h["H"], h["Dd"]

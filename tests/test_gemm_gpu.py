@@ -74,7 +74,7 @@ def test_gemm_rope_epilogue(cuda):
     b = (torch.randn(N, K, device=cuda, generator=g) * 0.05).bfloat16()
     freqs = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device=cuda).float() / hd))
     ang = torch.outer(torch.arange(T, device=cuda).float(), freqs)
-    table = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()    # [T, hd/2, 2]
+    table = torch.stack([ang.cos(), ang.sin()], dim=-1).transpose(0, 1).contiguous()    # pair-major [hd/2, T, 2]
     out = torch.empty(M, N, device=cuda)
     ops.gemm_bf16_tn([ops.gemm_problem(a, b, rope_table=table, rope_cols=2 * E, head_dim=hd,
                                        seq_len=T, out_f32=out)], M, N, K)
