@@ -404,6 +404,41 @@ typedef struct sea_profile_summary {
 void sea_profile_begin(void);
 int sea_profile_end(sea_profile_summary* out);
 
+/* ------------------------------------------------------------------ K7 / K8: ViT-mesh codec ---
+ * Fused SpatialModel halves, one CTA per snapshot (models/encoder_decoder.py):
+ *   sea_spatial_encode = generate_padding_mask (:173-176, in place on x) + PointwiseEncode.forward
+ *                        (:105-123): per-group patch MLP, + positional encoding, num_layers x
+ *                        EncoderBlock (base_blocks.py:123-138), final nn.LayerNorm;
+ *   sea_spatial_decode = Decode.forward (:137-146).
+ * x / out: [B, 64, n_fields, n_inp] fp32; z: [B, 64, G, D] (latent_layout 0) or the temporal
+ * model's [B, G, 64*D] (latent_layout 1 = transform_processed_data, utils/train_utils.py:315-337,
+ * fused into the store / load).  All parameters fp32, reference layouts.  n_patches must be 64,
+ * n_inp / embed_dim / mlp_hidden multiples of 4, head_dim = G*D/n_heads in {2,4,8,16}, <= 16 layers. */
+typedef struct sea_spatial_layer {
+  const float *ln1_w, *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *proj_w, *ln2_w;
+  const float *mlp0_w, *mlp0_b, *mlp_ln_w, *mlp_ln_b, *mlp3_w, *mlp3_b;
+} sea_spatial_layer;
+
+typedef struct sea_spatial_desc {
+  int32_t n_groups, n_fields, n_inp, n_patches, mlp_hidden, embed_dim, n_heads, num_layers;
+  int32_t group_first_field[4], group_num_fields[4]; /* field groups must be contiguous runs */
+  const float* enc_w1[4]; /* encode.encoders.{g}.layer1.weight [Hs, n_inp*|g|] */
+  const float* enc_w2[4]; /* .layer2.weight [D, Hs] */
+  const float* enc_b2[4]; /* .layer2.bias   [D]     */
+  const float* dec_w1[4]; /* decode.decoders.{g}.layer1.weight [Hs, D] */
+  const float* dec_w2[4]; /* .layer2.weight [n_inp*|g|, Hs] */
+  const float* dec_b2[4];
+  const sea_spatial_layer* layers; /* host array [num_layers]: encode.blocks.{l}.* */
+  const float* ln_w;               /* encode.ln */
+  const float* ln_b;
+  const float* pe;                 /* encode.spatial_pos_encoder.pe[0, :64, :]  [64, G*D] */
+} sea_spatial_desc;
+
+int sea_spatial_encode(const sea_spatial_desc* d, float* x, float* z, int B, int latent_layout,
+                       float pad_idx, int fix_pad, sea_stream_t stream);
+int sea_spatial_decode(const sea_spatial_desc* d, const float* z, float* out, int B, int latent_layout,
+                       sea_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,3 +114,19 @@ class TipiBwdArgs(C.Structure):
                 ("w3", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
                 ("dw3", C.c_void_p), ("db3", C.c_void_p), ("dlnw", C.c_void_p), ("dlnb", C.c_void_p),
                 ("dw0", C.c_void_p), ("db0", C.c_void_p)]
+
+
+class SpatialLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "proj_w", "ln2_w",
+                                          "mlp0_w", "mlp0_b", "mlp_ln_w", "mlp_ln_b", "mlp3_w", "mlp3_b")]
+
+
+class SpatialDesc(C.Structure):
+    _fields_ = [("n_groups", C.c_int32), ("n_fields", C.c_int32), ("n_inp", C.c_int32),
+                ("n_patches", C.c_int32), ("mlp_hidden", C.c_int32), ("embed_dim", C.c_int32),
+                ("n_heads", C.c_int32), ("num_layers", C.c_int32),
+                ("group_first_field", C.c_int32 * 4), ("group_num_fields", C.c_int32 * 4),
+                ("enc_w1", C.c_void_p * 4), ("enc_w2", C.c_void_p * 4), ("enc_b2", C.c_void_p * 4),
+                ("dec_w1", C.c_void_p * 4), ("dec_w2", C.c_void_p * 4), ("dec_b2", C.c_void_p * 4),
+                ("layers", C.POINTER(SpatialLayer)), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
+                ("pe", C.c_void_p)]

@@ -26,6 +26,15 @@ def test_temporal_state_dict_matches_reference(tag, V, ln):
     assert ours == _manifest()["temporal_" + tag]
 
 
+def test_spatial_state_dict_matches_reference():
+    from sea_b200.spatial import SpatialModel
+    m = SpatialModel([[0, 1], [2]], 16, 48, 2, 8, 8, 2024, 0, 0.0, False)
+    ours = {k: [list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()}
+    assert ours == _manifest()["spatial_small"]
+    with pytest.raises(NotImplementedError):
+        SpatialModel([[0, 1], [2]], 16, 48, 2, 8, 8, 2024, 0, 0.0, True)
+
+
 def test_temporal_init_distribution():
     from sea_b200.temporal import TemporalModel
     torch.manual_seed(0)
@@ -81,7 +90,8 @@ def test_ctypes_struct_sizes_match_header():
              "sea_attn_params": S.AttnParams, "sea_stream_params": S.StreamParams,
              "sea_block_params": S.BlockParams, "sea_temporal_desc": S.TemporalDesc,
              "sea_norm_bwd_args": S.NormBwdArgs, "sea_ln_gelu_bwd_args": S.LnGeluBwdArgs,
-             "sea_attn_bwd_args": S.AttnBwdArgs, "sea_tipi_bwd_args": S.TipiBwdArgs}
+             "sea_attn_bwd_args": S.AttnBwdArgs, "sea_tipi_bwd_args": S.TipiBwdArgs,
+             "sea_spatial_layer": S.SpatialLayer, "sea_spatial_desc": S.SpatialDesc}
     src = '#include <stdio.h>\n#include "sea_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:

@@ -1,0 +1,86 @@
+"""ViT-mesh encoder / decoder parity against goldens of the unmodified reference SpatialModel."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sea_oracle as so
+from tests.helpers import rel_l2, spatial_case
+
+pytestmark = pytest.mark.gpu
+
+
+def build(tag, cuda):
+    from sea_b200.spatial import SpatialModel
+    g, sd, cfg, x = spatial_case(tag)
+    n_inp, hidden, layers, D, nh, B = [int(v) for v in g["meta"]]
+    m = SpatialModel(cfg["field_groups"], n_inp, hidden, layers, D, nh, 2024, 0, 0.0, False)
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all(k.endswith(".pe") for k in missing.missing_keys)
+    return g, sd, cfg, m.to(cuda).eval(), x
+
+
+@pytest.mark.parametrize("tag", ["small", "cylinder_flow", "multiphase_flow"])
+def test_spatial_matches_reference_golden(cuda, tag):
+    g, sd, cfg, m, x = build(tag, cuda)
+    xin = x.clone().to(cuda)
+    with torch.no_grad():
+        y = m(xin)                       # forward: pad rewrite (in place) + encode + decode
+        z = m.encode(xin)
+        y2 = m.decode(z)
+    torch.cuda.synchronize()
+    ez, ey = rel_l2(z.cpu(), g["z"]), rel_l2(y.cpu(), g["y"])
+    print(f"\n[spatial] {tag}: latent rel {ez:.2e}, reconstruction rel {ey:.2e}")
+    assert z.shape == g["z"].shape and y.shape == g["y"].shape
+    assert ez < 1e-4 and ey < 1e-4            # fp32 bar of north_star
+    assert rel_l2(y2.cpu(), g["y"]) < 1e-4
+    assert np.array_equal(xin.cpu().numpy()[0, 0, 0, -4:], g["x_after"])   # -9999 rewritten in place
+
+
+def test_latent_layout_fused_store_and_load(cuda):
+    """latent_layout=1 == transform_processed_data(encode(x)) (utils/train_utils.py:315-337) and
+    decode(latent_layout=1) inverts it."""
+    g, sd, cfg, m, x = build("cylinder_flow", cuda)
+    xin = x.clone().to(cuda)
+    xin[xin == -9999] = 0
+    codec = m._codec()
+    lat = codec.encode(xin, latent_layout=1)
+    B = x.shape[0]
+    assert lat.shape == (B, 2, 64 * 16)
+    assert rel_l2(lat.cpu().reshape(1, B, 2, -1), g["latent"]) < 1e-4
+    y = codec.decode(lat, latent_layout=1)
+    assert rel_l2(y.cpu(), g["y"]) < 1e-4
+
+
+def test_spatial_ragged_batch_and_oracle(cuda):
+    """Batch sizes that do not divide anything + comparison with the oracle on fresh inputs."""
+    g, sd, cfg, m, x = build("small", cuda)
+    gen = torch.Generator().manual_seed(5)
+    xb = torch.randn(37, 64, 3, 16, generator=gen)
+    with torch.no_grad():
+        ref_z = so.spatial_encode(xb, sd, **cfg)
+        ref_y = so.spatial_decode(ref_z, sd, field_groups=cfg["field_groups"])
+        z = m.encode(xb.to(cuda))
+        y = m.decode(z)
+    assert rel_l2(z.cpu(), ref_z) < 1e-4 and rel_l2(y.cpu(), ref_y) < 1e-4
+
+
+def test_spatial_throughput_report(cuda):
+    from oracle import golden_recipe as gr
+    g, sd, cfg, m, x = build("cylinder_flow", cuda)
+    B = 4096
+    xb = torch.randn(B, 64, 3, 64, device=cuda)
+    for _ in range(2):
+        z = m.encode(xb)
+        y = m.decode(z)
+    s, e, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    s.record()
+    z = m.encode(xb)
+    e.record()
+    y = m.decode(z)
+    e2.record()
+    torch.cuda.synchronize()
+    te, td = s.elapsed_time(e), e.elapsed_time(e2)
+    flops_enc = 2 * 64 * (128 * 480 + 480 * 16 + 64 * 480 + 480 * 16) + 12 * (24 * 64 * 32 * 32 + 4 * 64 * 64 * 32)
+    print(f"\n[spatial perf] cylinder B={B}: encode {te:.2f} ms ({B/te*1e3:.0f} snapshots/s, "
+          f"{flops_enc*B/te/1e9:.1f} TFLOP/s fp32, {B*(49152+8192)/te/1e6:.1f} GB/s algorithmic), "
+          f"decode {td:.2f} ms ({B/td*1e3:.0f} snapshots/s)")
