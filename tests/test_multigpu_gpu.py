@@ -1,0 +1,39 @@
+"""N>1 on real GPUs (skipped on a 1-GPU box): data-parallel training parity and sharded rollout bench."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(n, script_args, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port)] + script_args
+    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+
+
+@pytest.mark.parametrize("ln", ["adaln", "ln"])
+def test_dp_training_matches_oracle_global_batch(cuda, ln):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    env = dict(os.environ, SEA_LN=ln)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", "scripts/dp_train_check.py"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "DP_TRAIN_OK" in r.stdout
+
+
+def test_bench_two_gpus_weak_scaling_line(cuda):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = _torchrun(2, ["bench.py", "--gpus", "2", "--steps", "2", "--warmup", "3", "--rollout", "40"], 29519)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["value"] > 0
