@@ -46,6 +46,7 @@ int sea_init(int device);              /* caches SM count + driver entry points 
 const char* sea_strerror(int code);    /* static string for SEA_ERR_* / cudaError_t           */
 int sea_version(void);
 int sea_num_sms(void);
+void sea_set_pdl(int on);           /* programmatic dependent launch between library kernels (default on) */
 
 /* ------------------------------------------------------------------ K1: GEMM ----------------
  * C[M,N] = A[M,K] * B[N,K]^T with fused epilogue.  Replaces every nn.Linear on the path:

@@ -68,6 +68,8 @@ class _Lazy:
             for fn in ("sea_temporal_cache_bytes", "sea_temporal_workspace_bytes", "sea_temporal_cond_cache_bytes"):
                 if hasattr(dll, fn):
                     getattr(dll, fn).restype = C.c_size_t
+            if os.environ.get("SEA_B200_PDL", "1") == "0":   # A/B switch for programmatic dependent launch
+                dll.sea_set_pdl(0)
             self._dll = dll
         return self._dll
 

@@ -12,6 +12,7 @@
 
 #include "../../include/sea_b200.h"
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace sea {
 namespace {
@@ -45,6 +46,8 @@ struct BwdDev {
 
 template <typename T>
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const BwdDev a) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int total = a.B * a.T * a.n_heads;
   if (warp >= total) return;
@@ -72,6 +75,8 @@ __device__ __forceinline__ float unrope(float y, int d, int t, int rope_ld, cons
 
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32) attn_bwd_dq_kernel(const BwdDev a) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   extern __shared__ float smem[];
   const int hd = a.hd, dpl = hd >> 5;
   float* Ks = smem;                          // [32][hd+1]
@@ -174,6 +179,8 @@ __global__ void __launch_bounds__(kWarps * 32) attn_bwd_dq_kernel(const BwdDev a
 
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32) attn_bwd_dkdv_kernel(const BwdDev a) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   extern __shared__ float smem[];
   const int hd = a.hd, dpl = hd >> 5;
   float* Qs = smem;                          // [32][hd+1]
@@ -299,10 +306,10 @@ int launch_bwd(const BwdDev& d, cudaStream_t s) {
     attr_set[dev] = true;
   }
   const int total_warps = d.B * d.T * d.n_heads;
-  attn_bwd_prep_kernel<T><<<(total_warps + 7) / 8, 256, 0, s>>>(d);
+  SEA_LAUNCH((attn_bwd_prep_kernel<T>), (total_warps + 7) / 8, 256, 0, s, d);
   dim3 grid((d.T + kPerCta - 1) / kPerCta, d.n_heads, d.B);
-  attn_bwd_dq_kernel<T><<<grid, kWarps * 32, smem_dq, s>>>(d);
-  attn_bwd_dkdv_kernel<T><<<grid, kWarps * 32, smem_kv, s>>>(d);
+  SEA_LAUNCH((attn_bwd_dq_kernel<T>), grid, kWarps * 32, smem_dq, s, d);
+  SEA_LAUNCH((attn_bwd_dkdv_kernel<T>), grid, kWarps * 32, smem_kv, s, d);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -11,6 +11,7 @@
 
 #include "../../include/sea_b200.h"
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace sea {
 namespace {
@@ -34,6 +35,8 @@ __global__ void __launch_bounds__(kWarps * 32)
 attn_fwd_simt_kernel(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict__ V,
                      long long ldq, long long ldk, long long ldv, T* __restrict__ O, long long ldo,
                      float* __restrict__ lse, int Tlen, int n_heads, int hd, int src_len, float scale) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   extern __shared__ float smem[];
   const int dpl = hd >> 5;
   float* Ks = smem;                         // [32][hd + 1]
@@ -157,9 +160,7 @@ int launch_simt(const sea_attn_args* a, cudaStream_t s) {
     attr_set[dev] = true;
   }
   dim3 grid((a->T + kQPerCta - 1) / kQPerCta, a->n_heads, a->B);
-  attn_fwd_simt_kernel<T><<<grid, kWarps * 32, smem, s>>>(
-      static_cast<const T*>(a->q), static_cast<const T*>(a->k), static_cast<const T*>(a->v), a->ldq,
-      a->ldk, a->ldv, static_cast<T*>(a->o), a->ldo, a->lse, a->T, a->n_heads, hd, a->src_len, a->scale);
+  SEA_LAUNCH((attn_fwd_simt_kernel<T>), grid, kWarps * 32, smem, s, static_cast<const T*>(a->q), static_cast<const T*>(a->k), static_cast<const T*>(a->v), a->ldq, a->ldk, a->ldv, static_cast<T*>(a->o), a->ldo, a->lse, a->T, a->n_heads, hd, a->src_len, a->scale);
   return static_cast<int>(cudaGetLastError());
 }
 

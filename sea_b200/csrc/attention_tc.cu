@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -290,7 +292,7 @@ int launch_tc(const sea_attn_args* a, cudaStream_t s) {
   p.B = a->B; p.T = a->T; p.n_heads = a->n_heads; p.src_len = a->src_len;
   p.scale_log2 = a->scale * 1.44269504088896340736f;
   dim3 grid((a->T + BQ - 1) / BQ, a->n_heads, a->B);
-  attn_fwd_tc_kernel<HD, BKV><<<grid, kThreads, C::SMEM, s>>>(p);
+  SEA_LAUNCH((attn_fwd_tc_kernel<HD, BKV>), grid, kThreads, C::SMEM, s, p);
   return static_cast<int>(cudaGetLastError());
 }
 

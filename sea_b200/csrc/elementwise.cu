@@ -25,6 +25,8 @@ __global__ void adaln_hidden_kernel(const float* __restrict__ ib, long long ld_i
                                     const float* __restrict__ w1, const float* __restrict__ b1,
                                     int n, __nv_bfloat16* __restrict__ out_bf16,
                                     float* __restrict__ out_f32) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const long long total = static_cast<long long>(M) * (n / 2);
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -52,6 +54,8 @@ __global__ void tipi_hidden_kernel(const float* __restrict__ ib, long long ld_ib
                                    const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                    int hid, float* __restrict__ g_out, float* __restrict__ pre_out,
                                    float* __restrict__ stats_out) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float u[kMaxTipiHid];
@@ -101,6 +105,8 @@ constexpr int kNormMaxChunks = 16;  // 16 chunks x 32 lanes x 4 floats = 2048
 
 template <int CH, bool ADALN>
 __global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const NormDev a) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * (blockDim.x >> 5) + warp;
   if (m >= a.M) return;
@@ -207,6 +213,8 @@ __global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const 
 __global__ void __launch_bounds__(256) tipi_rows_kernel(const float* __restrict__ g, long long ldg, int R, int E,
                                                         int hid, const float* __restrict__ w3,
                                                         const float* __restrict__ b3, float* __restrict__ out) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   if (n >= E || r >= R) return;
@@ -227,6 +235,8 @@ __global__ void __launch_bounds__(256) ln_gelu_fwd_kernel(const TIn* __restrict_
                                                           const float* __restrict__ bias,
                                                           TOut* __restrict__ g, long long ldg,
                                                           float* __restrict__ stats, int rows_per_cta) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   __shared__ float red[8];
   __shared__ float bcast;
   const int tid = threadIdx.x;
@@ -346,6 +356,8 @@ __global__ void __launch_bounds__(256) ln_gelu_fwd_smem_kernel(const TIn* __rest
                                                                const float* __restrict__ bias,
                                                                TOut* __restrict__ g, long long ldg,
                                                                float* __restrict__ stats, int R) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   extern __shared__ __align__(128) uint8_t ln_smem[];
   __shared__ uint64_t bar;
   __shared__ float red[8];
@@ -476,6 +488,8 @@ struct AdalnGroupDev {
   const float* ib; long long ld_ib; int M, ib_num, n, items;
 };
 __global__ void __launch_bounds__(256) adaln_hidden_group_kernel(const AdalnGroupDev a) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int it = blockIdx.y;
   const long long total = static_cast<long long>(a.M) * (a.n / 2);
   const float* w1 = a.w1[it];
@@ -516,6 +530,8 @@ template <typename TIn>
 __global__ void __launch_bounds__(256) pack_kernel(const TIn* __restrict__ src, long long ld, int R,
                                                    int C, int transpose, int split, int act, int split_inner,
                                                    __nv_bfloat16* __restrict__ dst, long long ldd) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   // 32x32 tile through shared memory so both the read and the (possibly transposed) write are
   // coalesced.
   __shared__ float tile[32][33];
@@ -563,6 +579,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const TIn* __restrict__ src, 
 // out[n] = sum_m src[m, n] (bias gradients).  One warp per 32 columns x row-slab, atomics into out.
 __global__ void colsum_kernel(const float* __restrict__ src_f32, const __nv_bfloat16* __restrict__ src_bf16,
                               long long ld, int M, int N, float* __restrict__ out) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int r_begin = blockIdx.y * rows_per;
@@ -598,8 +616,7 @@ extern "C" int sea_adaln_hidden(const float* ib, int64_t ld_ib, int M, int ib_nu
   long long nblk = (total + 255) / 256;
   if (nblk > 148LL * 16) nblk = 148LL * 16;
   const int grid = static_cast<int>(nblk);
-  adaln_hidden_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      ib, ld_ib > 0 ? ld_ib : ib_num, M, ib_num, w1, b1, n, static_cast<__nv_bfloat16*>(out_bf16), out_f32);
+  SEA_LAUNCH(adaln_hidden_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), ib, ld_ib > 0 ? ld_ib : ib_num, M, ib_num, w1, b1, n, static_cast<__nv_bfloat16*>(out_bf16), out_f32);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -619,7 +636,7 @@ extern "C" int sea_adaln_hidden_group(int items, const float* const* w1, const f
   long long nblk = (total + 255) / 256;
   if (nblk > 148LL * 8) nblk = 148LL * 8;
   dim3 grid(static_cast<unsigned>(nblk), items);
-  adaln_hidden_group_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d);
+  SEA_LAUNCH(adaln_hidden_group_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), d);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -628,8 +645,7 @@ extern "C" int sea_tipi_hidden(const float* ib, int64_t ld_ib, int M, int ib_num
                                float* pre_out, float* stats_out, sea_stream_t stream) {
   if (!ib || !w0 || !b0 || !ln_w || !ln_b || !g_out || M <= 0 || ib_num <= 0) return SEA_ERR_INVALID;
   if (hid <= 0 || hid > kMaxTipiHid) return SEA_ERR_UNSUPPORTED;
-  tipi_hidden_kernel<<<(M + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      ib, ld_ib > 0 ? ld_ib : ib_num, M, ib_num, w0, b0, ln_w, ln_b, hid, g_out, pre_out, stats_out);
+  SEA_LAUNCH(tipi_hidden_kernel, (M + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream), ib, ld_ib > 0 ? ld_ib : ib_num, M, ib_num, w0, b0, ln_w, ln_b, hid, g_out, pre_out, stats_out);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -637,8 +653,8 @@ template <int CH>
 static int launch_norm(const NormDev& d, cudaStream_t s) {
   const int rows_per_cta = 8;
   const int grid = (d.M + rows_per_cta - 1) / rows_per_cta;
-  if (d.kind == SEA_NORM_ADALN) norm_fwd_kernel<CH, true><<<grid, rows_per_cta * 32, 0, s>>>(d);
-  else norm_fwd_kernel<CH, false><<<grid, rows_per_cta * 32, 0, s>>>(d);
+  if (d.kind == SEA_NORM_ADALN) SEA_LAUNCH((norm_fwd_kernel<CH, true>), grid, rows_per_cta * 32, 0, s, d);
+  else SEA_LAUNCH((norm_fwd_kernel<CH, false>), grid, rows_per_cta * 32, 0, s, d);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -673,7 +689,7 @@ extern "C" int sea_tipi_rows(const float* g, int64_t ldg, int R, int E, int hid,
                              const float* b3, float* out, sea_stream_t stream) {
   if (!g || !w3 || !b3 || !out || R <= 0 || E <= 0 || hid <= 0) return SEA_ERR_INVALID;
   dim3 grid((E + 255) / 256, R);
-  tipi_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, ldg, R, E, hid, w3, b3, out);
+  SEA_LAUNCH(tipi_rows_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), g, ldg, R, E, hid, w3, b3, out);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -692,8 +708,7 @@ static int launch_ln_gelu_smem(const sea_ln_gelu_args* a, const TIn* h, TOut* g,
     SEA_CUDA_OK(cudaFuncSetAttribute(ln_gelu_fwd_smem_kernel<TIn, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set[dev] = true;
   }
-  ln_gelu_fwd_smem_kernel<TIn, TOut><<<(a->M + R - 1) / R, 256, smem, s>>>(h, a->ldh, a->M, a->H, a->weight, a->bias,
-                                                                          g, a->ldg, a->stats, R);
+  SEA_LAUNCH((ln_gelu_fwd_smem_kernel<TIn, TOut>), (a->M + R - 1) / R, 256, smem, s, h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, R);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -707,11 +722,11 @@ static int launch_ln_gelu(const sea_ln_gelu_args* a, const TIn* h, TOut* g, cuda
   rows = rows < 1 ? 1 : (rows > 8 ? 8 : rows);
   const int grid = (a->M + rows - 1) / rows;
   if (a->H <= 4096)
-    ln_gelu_fwd_kernel<TIn, TOut, 2><<<grid, 256, 0, s>>>(h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, rows);
+    SEA_LAUNCH((ln_gelu_fwd_kernel<TIn, TOut, 2>), grid, 256, 0, s, h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, rows);
   else if (a->H <= 8192)
-    ln_gelu_fwd_kernel<TIn, TOut, 4><<<grid, 256, 0, s>>>(h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, rows);
+    SEA_LAUNCH((ln_gelu_fwd_kernel<TIn, TOut, 4>), grid, 256, 0, s, h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, rows);
   else
-    ln_gelu_fwd_kernel<TIn, TOut, 8><<<grid, 256, 0, s>>>(h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, rows);
+    SEA_LAUNCH((ln_gelu_fwd_kernel<TIn, TOut, 8>), grid, 256, 0, s, h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, rows);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -731,12 +746,9 @@ extern "C" int sea_pack_operand(const sea_pack_args* a, sea_stream_t stream) {
   dim3 grid((a->C + 31) / 32, (a->R + 31) / 32);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a->src_f32)
-    pack_kernel<float><<<grid, 256, 0, s>>>(a->src_f32, a->ld, a->R, a->C, a->transpose, a->split,
-                                            a->act, a->split_inner, static_cast<__nv_bfloat16*>(a->dst), a->ld_dst);
+    SEA_LAUNCH((pack_kernel<float>), grid, 256, 0, s, a->src_f32, a->ld, a->R, a->C, a->transpose, a->split, a->act, a->split_inner, static_cast<__nv_bfloat16*>(a->dst), a->ld_dst);
   else
-    pack_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(a->src_bf16),
-                                                    a->ld, a->R, a->C, a->transpose, a->split, a->act, a->split_inner,
-                                                    static_cast<__nv_bfloat16*>(a->dst), a->ld_dst);
+    SEA_LAUNCH((pack_kernel<__nv_bfloat16>), grid, 256, 0, s, static_cast<const __nv_bfloat16*>(a->src_bf16), a->ld, a->R, a->C, a->transpose, a->split, a->act, a->split_inner, static_cast<__nv_bfloat16*>(a->dst), a->ld_dst);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -747,7 +759,6 @@ extern "C" int sea_colsum_accumulate(const float* src_f32, const void* src_bf16,
   if (slabs < 1) slabs = 1;
   if (slabs > 64) slabs = 64;
   dim3 grid((N + 31) / 32, slabs);
-  colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src_f32, static_cast<const __nv_bfloat16*>(src_bf16), ld, M, N, out);
+  SEA_LAUNCH(colsum_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), src_f32, static_cast<const __nv_bfloat16*>(src_bf16), ld, M, N, out);
   return static_cast<int>(cudaGetLastError());
 }

@@ -37,6 +37,8 @@ constexpr int kNormMaxChunks = 16;
 
 template <int CH>
 __global__ void __launch_bounds__(256) norm_bwd_kernel(const NormBwdDev a) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   extern __shared__ float red[];  // [8 warps][d] x2 (dweight, dbias partials; each lane owns its columns)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* rw = red;
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const __nv_bfloat16* _
                                                           __nv_bfloat16* __restrict__ dh, long long lddh,
                                                           float* __restrict__ dweight, float* __restrict__ dbias,
                                                           int M, int H, int rows_per_cta) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   constexpr int kMaxChunks = 8;
   extern __shared__ float acc[];  // [2][H]
   __shared__ float red[2][8];
@@ -242,6 +246,8 @@ __global__ void __launch_bounds__(256) adaln_hidden_bwd_kernel(const float* __re
                                                                const float* __restrict__ b1, int n,
                                                                float* __restrict__ dw1, float* __restrict__ db1,
                                                                int rows_per_cta) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
@@ -267,6 +273,8 @@ __global__ void __launch_bounds__(256) tipi_bwd_w_kernel(const float* __restrict
                                                          const float* __restrict__ g, int M, int E, int hid,
                                                          float* __restrict__ dw3, float* __restrict__ db3,
                                                          int rows_per_cta) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= E) return;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
@@ -293,6 +301,8 @@ struct TipiBwdDev {
   int M, E, hid, ib_num;
 };
 __global__ void __launch_bounds__(256) tipi_bwd_g_kernel(const TipiBwdDev a) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   // CTA-level accumulators: db0[8] | dlnw[8] | dlnb[8] | dw0[8][4]
   __shared__ float acc[24 + 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -384,9 +394,9 @@ extern "C" int sea_norm_bwd(const sea_norm_bwd_args* a, sea_stream_t stream) {
     attr_set[dev] = true;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a->d <= 512) norm_bwd_kernel<4><<<grid, 256, smem, s>>>(d);
-  else if (a->d <= 1024) norm_bwd_kernel<8><<<grid, 256, smem, s>>>(d);
-  else norm_bwd_kernel<16><<<grid, 256, smem, s>>>(d);
+  if (a->d <= 512) SEA_LAUNCH((norm_bwd_kernel<4>), grid, 256, smem, s, d);
+  else if (a->d <= 1024) SEA_LAUNCH((norm_bwd_kernel<8>), grid, 256, smem, s, d);
+  else SEA_LAUNCH((norm_bwd_kernel<16>), grid, 256, smem, s, d);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -405,10 +415,7 @@ extern "C" int sea_ln_gelu_bwd(const sea_ln_gelu_bwd_args* a, sea_stream_t strea
     SEA_CUDA_OK(cudaFuncSetAttribute(ln_gelu_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
     attr_set[dev] = true;
   }
-  ln_gelu_bwd_kernel<0><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(a->dg), a->lddg, static_cast<const __nv_bfloat16*>(a->h), a->ldh,
-      a->stats, a->weight, a->bias, static_cast<__nv_bfloat16*>(a->dh), a->lddh, a->dweight, a->dbias,
-      a->M, a->H, rows);
+  SEA_LAUNCH((ln_gelu_bwd_kernel<0>), grid, 256, smem, reinterpret_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a->dg), a->lddg, static_cast<const __nv_bfloat16*>(a->h), a->ldh, a->stats, a->weight, a->bias, static_cast<__nv_bfloat16*>(a->dh), a->lddh, a->dweight, a->dbias, a->M, a->H, rows);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -419,8 +426,7 @@ extern "C" int sea_adaln_hidden_bwd(const float* dh, int64_t lddh, const float* 
   if (ib_num < 1 || ib_num > 4) return SEA_ERR_UNSUPPORTED;
   const int rows = rows_per_cta_for(M, 8) * 4;
   dim3 grid((n + 255) / 256, (M + rows - 1) / rows);
-  adaln_hidden_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      dh, lddh, ib, M, ib_num, w1, b1, n, dw1, db1, rows);
+  SEA_LAUNCH(adaln_hidden_bwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), dh, lddh, ib, M, ib_num, w1, b1, n, dw1, db1, rows);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -434,12 +440,12 @@ extern "C" int sea_tipi_bwd(const sea_tipi_bwd_args* a, sea_stream_t stream) {
   for (int i = 0; i < a->n_streams; ++i) {
     if (!a->dx[i]) return SEA_ERR_INVALID;
     d.dx[i] = a->dx[i];
-    tipi_bwd_w_kernel<<<grid, 256, 0, s>>>(a->dx[i], a->lddx, a->g, a->M, a->E, a->hid, a->dw3, a->db3, rows);
+    SEA_LAUNCH(tipi_bwd_w_kernel, grid, 256, 0, s, a->dx[i], a->lddx, a->g, a->M, a->E, a->hid, a->dw3, a->db3, rows);
   }
   d.lddx = a->lddx; d.n_streams = a->n_streams;
   d.w3 = a->w3; d.u = a->u; d.stats = a->stats; d.ib = a->ib; d.ln_w = a->ln_w; d.ln_b = a->ln_b;
   d.dw0 = a->dw0; d.db0 = a->db0; d.dlnw = a->dlnw; d.dlnb = a->dlnb;
   d.M = a->M; d.E = a->E; d.hid = a->hid; d.ib_num = a->ib_num;
-  tipi_bwd_g_kernel<<<(a->M + 7) / 8, 256, 0, s>>>(d);
+  SEA_LAUNCH(tipi_bwd_g_kernel, (a->M + 7) / 8, 256, 0, s, d);
   return static_cast<int>(cudaGetLastError());
 }

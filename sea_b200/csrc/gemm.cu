@@ -44,6 +44,7 @@ struct DevEpilogue {
   long long ld_residual, ld_gelu, ld_out_f32, ld_out_pre_bf16, ld_out_bf16;
   int act, rope_cols, head_dim, seq_len, rope_ld;
   float rope_sign;
+  int vec8;  // every row base / pitch is 32-byte aligned: use 256-bit global accesses
 };
 
 struct alignas(64) GemmParams {
@@ -125,11 +126,23 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
   }
   if (first && e.residual != nullptr) {
     const float* rp = e.residual + static_cast<long long>(m) * e.ld_residual + n0;
+    if (e.vec8) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < nvalid) {
-        const float4 b = *reinterpret_cast<const float4*>(rp + j);
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      for (int j = 0; j < 32; j += 8) {
+        if (j < nvalid) {
+          uint32_t t[8];
+          ptx::ldg256(rp + j, t);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[j + q] += __uint_as_float(t[q]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (j < nvalid) {
+          const float4 b = *reinterpret_cast<const float4*>(rp + j);
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
       }
     }
   }
@@ -168,22 +181,46 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
   }
   if (e.out_f32 != nullptr) {
     float* op = e.out_f32 + static_cast<long long>(m) * e.ld_out_f32 + n0;
+    if (e.vec8) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < nvalid) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int j = 0; j < 32; j += 8) {
+        if (j < nvalid) {
+          uint32_t t[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) t[q] = __float_as_uint(v[j + q]);
+          ptx::stg256(op + j, t);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (j < nvalid) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
     }
   }
   if (e.out_pre_bf16 != nullptr) {
     __nv_bfloat16* op = e.out_pre_bf16 + static_cast<long long>(m) * e.ld_out_pre_bf16 + n0;
+    if (e.vec8) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (j < nvalid) {
-        uint4 o;
-        o.x = ptx::pack_bf16(v[j], v[j + 1]);
-        o.y = ptx::pack_bf16(v[j + 2], v[j + 3]);
-        o.z = ptx::pack_bf16(v[j + 4], v[j + 5]);
-        o.w = ptx::pack_bf16(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(op + j) = o;
+      for (int j = 0; j < 32; j += 16) {
+        if (j < nvalid) {
+          uint32_t t[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) t[q] = ptx::pack_bf16(v[j + 2 * q], v[j + 2 * q + 1]);
+          ptx::stg256(op + j, t);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (j < nvalid) {
+          uint4 o;
+          o.x = ptx::pack_bf16(v[j], v[j + 1]);
+          o.y = ptx::pack_bf16(v[j + 2], v[j + 3]);
+          o.z = ptx::pack_bf16(v[j + 4], v[j + 5]);
+          o.w = ptx::pack_bf16(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(op + j) = o;
+        }
       }
     }
   }
@@ -193,15 +230,27 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
       for (int j = 0; j < 32; ++j) v[j] = ptx::gelu_fast(v[j]);
     }
     __nv_bfloat16* op = e.out_bf16 + static_cast<long long>(m) * e.ld_out_bf16 + n0;
+    if (e.vec8) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (j < nvalid) {
-        uint4 o;
-        o.x = ptx::pack_bf16(v[j], v[j + 1]);
-        o.y = ptx::pack_bf16(v[j + 2], v[j + 3]);
-        o.z = ptx::pack_bf16(v[j + 4], v[j + 5]);
-        o.w = ptx::pack_bf16(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(op + j) = o;
+      for (int j = 0; j < 32; j += 16) {
+        if (j < nvalid) {
+          uint32_t t[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) t[q] = ptx::pack_bf16(v[j + 2 * q], v[j + 2 * q + 1]);
+          ptx::stg256(op + j, t);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (j < nvalid) {
+          uint4 o;
+          o.x = ptx::pack_bf16(v[j], v[j + 1]);
+          o.y = ptx::pack_bf16(v[j + 2], v[j + 3]);
+          o.z = ptx::pack_bf16(v[j + 4], v[j + 5]);
+          o.w = ptx::pack_bf16(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(op + j) = o;
+        }
       }
     }
   }
@@ -250,6 +299,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // prologue done (barriers, TMEM, descriptor prefetch): now wait for the producer kernel
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -363,7 +415,7 @@ int launch(const GemmParams& p, int total_tiles, cudaStream_t stream) {
     attr_set[dev] = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  gemm_bf16_tn_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
+  SEA_LAUNCH((gemm_bf16_tn_kernel<BN>), grid, kThreads, C::SMEM_BYTES, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -472,6 +524,11 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
     d.seq_len = e.seq_len;
     d.rope_ld = e.rope_ld;
     d.rope_sign = (e.rope_sign == 0.0f) ? 1.0f : e.rope_sign;
+    auto al32 = [](const void* ptr, long long ld_elems, int esz) {
+      return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr) & 31) == 0) && ((ld_elems * esz) % 32 == 0));
+    };
+    d.vec8 = (N % 16 == 0) && al32(e.residual, e.ld_residual, 4) && al32(e.out_f32, e.ld_out_f32, 4) &&
+             al32(e.out_pre_bf16, e.ld_out_pre_bf16, 2) && al32(e.out_bf16, e.ld_out_bf16, 2);
   }
   const int total = p.tiles_m * p.tiles_n * p.groups;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

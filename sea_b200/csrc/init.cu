@@ -11,10 +11,15 @@ namespace sea {
 namespace {
 std::mutex g_mu;
 bool g_ready = false;
+}  // namespace
+extern bool g_pdl;
+namespace {
 int g_sms = 0;
 TensorMapEncodeFn g_encode = nullptr;
 }  // namespace
 
+bool g_pdl = true;
+bool pdl_enabled() { return g_pdl; }
 int num_sms() { return g_sms; }
 TensorMapEncodeFn tensor_map_encoder() { return g_encode; }
 
@@ -63,6 +68,7 @@ extern "C" int sea_init(int device) {
 }
 
 extern "C" int sea_version(void) { return 100; }
+extern "C" void sea_set_pdl(int on) { sea::g_pdl = on != 0; }
 extern "C" int sea_num_sms(void) { return sea::g_sms; }
 
 extern "C" const char* sea_strerror(int code) {

@@ -23,6 +23,24 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
                       uint64_t outer, uint64_t ld_mid, uint64_t ld_outer, uint32_t box_inner,
                       uint32_t box_mid);
 
+// Kernel launch with the programmatic-stream-serialization attribute (PDL).  All kernels of this
+// library call griddepcontrol.wait before touching global memory, so they may be launched early.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define SEA_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)::sea::launch_pdl(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+
 #define SEA_CUDA_OK(expr)                                  \
   do {                                                     \
     cudaError_t _e = (expr);                               \

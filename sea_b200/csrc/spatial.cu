@@ -155,6 +155,8 @@ __device__ __forceinline__ long long latent_index(int b, int p, int g, int d, in
 __global__ void __launch_bounds__(kThreads) spatial_encode_kernel(const SpatialDev a, float* __restrict__ x,
                                                                   float* __restrict__ z, int layout,
                                                                   float pad_idx, int fix_pad) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int FC = a.n_fields * a.C, Es = a.n_groups * a.D;
   const int big_w = max(4 * Es, kChunk);
@@ -228,6 +230,8 @@ __global__ void __launch_bounds__(kThreads) spatial_encode_kernel(const SpatialD
 // ------------------------------------------------------------------------------------ decoder
 __global__ void __launch_bounds__(kThreads) spatial_decode_kernel(const SpatialDev a, const float* __restrict__ z,
                                                                   float* __restrict__ out, int layout) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int FC = a.n_fields * a.C, Es = a.n_groups * a.D;
   float* Zin = sm;                 // [64][Es]
@@ -301,7 +305,7 @@ extern "C" int sea_spatial_encode(const sea_spatial_desc* d, float* x, float* z,
   const size_t smem = sizeof(float) * (static_cast<size_t>(P) * FC + 2 * P * Es + static_cast<size_t>(P) * big_w);
   if (smem > 220 * 1024) return SEA_ERR_UNSUPPORTED;
   SEA_CUDA_OK(cudaFuncSetAttribute(spatial_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  spatial_encode_kernel<<<B, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a, x, z, latent_layout, pad_idx, fix_pad);
+  SEA_LAUNCH(spatial_encode_kernel, B, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), a, x, z, latent_layout, pad_idx, fix_pad);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -317,6 +321,6 @@ extern "C" int sea_spatial_decode(const sea_spatial_desc* d, const float* z, flo
   const size_t smem = sizeof(float) * (static_cast<size_t>(P) * Es + static_cast<size_t>(P) * kChunk + static_cast<size_t>(P) * FC);
   if (smem > 220 * 1024) return SEA_ERR_UNSUPPORTED;
   SEA_CUDA_OK(cudaFuncSetAttribute(spatial_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  spatial_decode_kernel<<<B, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a, z, out, latent_layout);
+  SEA_LAUNCH(spatial_decode_kernel, B, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), a, z, out, latent_layout);
   return static_cast<int>(cudaGetLastError());
 }
