@@ -60,8 +60,8 @@ template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+  static constexpr int TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // allocation must be a power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -457,15 +457,22 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
 
   int bn = g_force_bn;
   if (bn == 0) {
-    // Fill the machine first; prefer the widest tile that still gives >= 1 wave.
+    // Cost model: waves x tile width / mainloop efficiency of that width (single-CTA SS-MMA is
+    // shared-memory-bandwidth bound below N = 256: measured ~0.5 / 0.66 / 0.8 / 0.9 of the MMA rate
+    // at N = 64 / 128 / 192 / 256), plus a per-wave epilogue/latency term.
     const long long tm = (M + BM - 1) / BM;
-    const long long t256 = tm * ((N + 255) / 256) * num_problems;
-    const long long t128 = tm * ((N + 127) / 128) * num_problems;
-    if (t256 >= 2LL * num_sms()) bn = 256;
-    else if (t128 >= num_sms()) bn = 128;
-    else bn = 64;
+    const int cand[4] = {64, 128, 192, 256};
+    const double eff[4] = {0.5, 0.66, 0.8, 0.9};
+    double best = 1e30;
+    for (int i = 0; i < 4; ++i) {
+      const long long tiles = tm * ((N + cand[i] - 1) / cand[i]) * num_problems;
+      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      const double kb = (K + BK - 1) / BK;
+      const double cost = waves * (cand[i] / eff[i] * kb + 6.0 * cand[i] + 400.0);
+      if (cost < best) { best = cost; bn = cand[i]; }
+    }
   }
-  if (bn != 64 && bn != 128 && bn != 256) return SEA_ERR_INVALID;
+  if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return SEA_ERR_INVALID;
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -533,6 +540,7 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   const int total = p.tiles_m * p.tiles_n * p.groups;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (bn == 256) return launch<256>(p, total, s);
+  if (bn == 192) return launch<192>(p, total, s);
   if (bn == 128) return launch<128>(p, total, s);
   return launch<64>(p, total, s);
 }

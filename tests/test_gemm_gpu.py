@@ -9,7 +9,7 @@ def _ref(a, b):
     return a.float() @ b.float().t()
 
 
-@pytest.mark.parametrize("bn", [64, 128, 256, 0])
+@pytest.mark.parametrize("bn", [64, 128, 192, 256, 0])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (798, 1024, 1024), (796, 3072, 512),
                                    (37, 72, 136), (1000, 8192, 1024)])
 def test_gemm_plain(cuda, bn, M, N, K):
