@@ -1,0 +1,137 @@
+"""Per-shape microbenchmarks of the kernels on the temporal hot path (CUDA events, L2-cold inputs
+rotated through a pool larger than L2).  Prints one line per shape.
+
+    python scripts/shape_bench.py gemm            # every Linear shape of both configs at several M
+    python scripts/shape_bench.py attn            # attention fwd / bwd at several (B, T, hd)
+    python scripts/shape_bench.py train           # fwd+bwd train step of both configs + breakdown
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from sea_b200 import ops  # noqa: E402
+from sea_b200._lib import lib  # noqa: E402
+
+dev = torch.device("cuda")
+
+
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3  # us
+
+
+def gemm_case(M, N, K, groups, bn=0, pool=6):
+    As = [[torch.randn(M, K, device=dev).bfloat16() for _ in range(groups)] for _ in range(pool)]
+    Ws = [[torch.randn(N, K, device=dev).bfloat16() * 0.02 for _ in range(groups)] for _ in range(pool)]
+    Os = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(groups)]
+    it = [0]
+
+    def fn():
+        k = it[0] % pool
+        it[0] += 1
+        probs = [ops.gemm_problem(As[k][g], Ws[k][g], out_bf16=Os[g]) for g in range(groups)]
+        ops.gemm_bf16_tn(probs, M, N, K)
+
+    lib.sea_gemm_force_tile_n(bn)
+    us = timeit(fn)
+    lib.sea_gemm_force_tile_n(0)
+    return us
+
+
+def run_gemm():
+    for cfg, E, H, Dd in (("cyl", 1024, 8192, 512), ("mp", 2048, 16384, 1024)):
+        shapes = [("qkv", 3 * E, E, 2), ("sproj", E, E, 2), ("down", Dd, E, 2), ("cq", Dd, Dd, 1),
+                  ("ckv", 2 * Dd, Dd, 1), ("cproj", Dd, Dd, 1), ("up", E, Dd, 1), ("mlp0", H, E, 2),
+                  ("mlp3", E, H, 2), ("proj", E, E, 2)]
+        if cfg == "cyl":
+            shapes.append(("cond2E", 2 * E, 2 * E, 4))
+        for M in (32, 256, 800, 1600, 3200):
+            tot_us, tot_fl = 0.0, 0.0
+            for name, N, K, g in shapes:
+                best = None
+                res = []
+                for bn in (0, 64, 128, 192, 256):
+                    us = gemm_case(M, N, K, g, bn)
+                    res.append((bn, us))
+                auto = res[0][1]
+                bn_b, us_b = min(res[1:], key=lambda r: r[1])
+                fl = 2.0 * M * N * K * g
+                print(f"{cfg} M={M:5d} {name:7s} N={N:5d} K={K:5d} g={g} auto {auto:7.1f} us {fl/auto/1e6:7.1f} TF/s | "
+                      f"best bn={bn_b} {us_b:7.1f} us {fl/us_b/1e6:7.1f} TF/s | " +
+                      " ".join(f"{bn}:{us:.1f}" for bn, us in res[1:]), flush=True)
+                tot_us += auto
+                tot_fl += fl
+            print(f"== {cfg} M={M}: sum {tot_us:.1f} us, {tot_fl/tot_us/1e6:.1f} TF/s", flush=True)
+
+
+def run_attn():
+    for (B, T, nh, hd) in ((32, 100, 8, 128), (32, 100, 8, 64), (2, 399, 8, 128), (4, 199, 8, 256), (16, 399, 8, 128),
+                           (8, 1024, 8, 128), (4, 2024, 8, 128), (4, 2024, 8, 64), (2, 2024, 8, 256)):
+        M = B * T
+        qkv = torch.randn(M, 3 * nh * hd, device=dev).bfloat16()
+        q, k, v = qkv[:, : nh * hd], qkv[:, nh * hd: 2 * nh * hd], qkv[:, 2 * nh * hd:]
+        us_f = timeit(lambda: ops.attention_fwd(q, k, v, nh, B=B, want_lse=True))
+        o, lse = ops.attention_fwd(q, k, v, nh, B=B, want_lse=True)
+        do = torch.randn_like(o)
+        us_b = timeit(lambda: ops.attention_bwd(q, k, v, o, do, lse, nh, B=B), reps=5, warm=1)
+        fl = 2.0 * B * nh * T * T * hd  # causal-useful fwd FLOPs (c = 1/2 of 4*T^2*hd)
+        print(f"attn B={B} T={T} nh={nh} hd={hd}: fwd {us_f:8.1f} us {fl/us_f/1e6:7.1f} TF/s | "
+              f"bwd {us_b:8.1f} us {2.5*fl/us_b/1e6:7.1f} TF/s", flush=True)
+
+
+def run_train():
+    from sea_b200.rollout import profile
+    from sea_b200.temporal import TemporalModel
+    for cfg, E, ln, B, T in (("cylinder_flow", 1024, "adaln", 2, 399), ("multiphase_flow", 2048, "ln", 4, 199),
+                             ("cylinder_flow", 1024, "adaln", 16, 399), ("multiphase_flow", 2048, "ln", 16, 199)):
+        torch.manual_seed(42)
+        m = TemporalModel(1, E, 8, 2024, 8, 0, 2, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln).to(dev)
+        m.train()
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0.0)
+        x = torch.randn(B, T, 2, E, device=dev)
+        ib = torch.rand(B, 1, 1, device=dev).expand(B, T, 1).contiguous()
+        tgt = torch.randn_like(x)
+
+        def step(with_opt=True):
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.mse_loss(m(x, ib), tgt)
+            loss.backward()
+            if with_opt:
+                opt.step()
+
+        us_fb = timeit(lambda: step(False), reps=5, warm=2)
+        us_all = timeit(lambda: step(True), reps=5, warm=2)
+        with torch.no_grad():
+            m.eval()
+            us_f = timeit(lambda: m(x, ib), reps=5, warm=2)
+            m.train()
+        with profile() as prof:
+            step(False)
+            torch.cuda.synchronize()
+        ps = prof.summary
+        M = B * T
+        from bench import fwd_flops  # noqa
+        Hh, Dd = 8 * E, E // 2
+        fl = fwd_flops(B, T, E=E, H=Hh, Dd=Dd, adaln=(ln == "adaln"))
+        print(f"train {cfg} B={B} T={T} M={M}: fwd {us_f:.0f} us ({fl/us_f/1e6:.0f} TF/s) fwd+bwd {us_fb:.0f} us "
+              f"({3*fl/us_fb/1e6:.0f} TF/s) +AdamW {us_all:.0f} us | breakdown ms " +
+              " ".join(f"{k}:{v['ms']:.2f}/{v['launches']}" for k, v in ps.items()) +
+              f" | gemm {ps['gemm']['work']/max(ps['gemm']['ms'],1e-9)/1e9:.0f} TF/s "
+              f"attn {ps['attention']['work']/max(ps['attention']['ms'],1e-9)/1e9:.1f} TF/s "
+              f"elem {ps['elementwise']['work']/max(ps['elementwise']['ms'],1e-9)/1e6:.0f} GB/s", flush=True)
+        del m, opt
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+    {"gemm": run_gemm, "attn": run_attn, "train": run_train}[what]()

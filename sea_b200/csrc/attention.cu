@@ -8,9 +8,7 @@ namespace sea {
 int attention_fwd_simt(const sea_attn_args* a, cudaStream_t s);
 int attention_fwd_tc(const sea_attn_args* a, cudaStream_t s);  // attention_tc.cu
 bool attention_tc_supported(const sea_attn_args* a);
-namespace {
-int g_force_simt = 0;
-}
+int g_force_simt = 0;  // test hook: route bf16 attention (fwd and bwd) to the CUDA-core kernels
 }  // namespace sea
 
 extern "C" void sea_attention_force_simt(int on) { sea::g_force_simt = on; }

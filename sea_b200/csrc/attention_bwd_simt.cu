@@ -314,6 +314,9 @@ int launch_bwd(const BwdDev& d, cudaStream_t s) {
 }
 
 }  // namespace
+extern int g_force_simt;                                                  // attention.cu
+bool attention_bwd_tc_supported(const sea_attn_bwd_args* a);              // attention_bwd_tc.cu
+int attention_bwd_tc(const sea_attn_bwd_args* a, cudaStream_t s);
 }  // namespace sea
 
 extern "C" int sea_attention_bwd(const sea_attn_bwd_args* a, sea_stream_t stream) {
@@ -330,6 +333,7 @@ extern "C" int sea_attention_bwd(const sea_attn_bwd_args* a, sea_stream_t stream
   d.B = a->B; d.T = a->T; d.n_heads = a->n_heads; d.hd = a->head_dim; d.src_len = a->src_len;
   d.scale = a->scale; d.rope = a->rope_table; d.rope_ld = a->rope_ld;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!g_force_simt && attention_bwd_tc_supported(a)) return attention_bwd_tc(a, s);
   if (a->prec == SEA_PREC_FP32) return launch_bwd<float>(d, s);
   if (a->prec == SEA_PREC_BF16) return launch_bwd<__nv_bfloat16>(d, s);
   return SEA_ERR_INVALID;

@@ -93,6 +93,54 @@ def test_attention_bwd(cuda, hd, dt, B, T, src_len):
     assert _rel(dv.float(), vf.grad) < tol
 
 
+def _rope_tables(hd, T):
+    """freqs (models/base_blocks.py:300-306) as complex [T, hd/2] and as the pair-major real table."""
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2)[: hd // 2].float() / hd))
+    ang = torch.outer(torch.arange(T, dtype=torch.float32), inv)
+    fc = torch.polar(torch.ones_like(ang), ang)
+    return fc, torch.view_as_real(fc).float().transpose(0, 1).contiguous()
+
+
+@pytest.mark.parametrize("hd", [64, 128, 256])
+@pytest.mark.parametrize("B,T,src_len,rope", [(2, 128, 0, False), (1, 399, 0, True), (3, 199, 0, True),
+                                             (1, 521, 3, False), (2, 1030, 0, True)])
+def test_attention_bwd_tensor_core(cuda, hd, B, T, src_len, rope):
+    """tcgen05 backward (multi-tile, ragged tails, both roles, RoPE undone in the epilogue) against
+    torch autograd through the same attention incl. the rotation (models/base_blocks.py:184-197)."""
+    from sea_b200 import ops
+    nh = 2
+    g = torch.Generator(device="cuda").manual_seed(hd + T)
+    pre = (torch.randn(B * T, 3 * nh * hd, device=cuda, generator=g) * 0.8).bfloat16()
+    d_o = torch.randn(B * T, nh * hd, device=cuda, generator=g).bfloat16()
+    fc, tab = _rope_tables(hd, T)
+    fc, tab = fc.to(cuda), tab.to(cuda)
+    xf = pre.float().detach().clone().requires_grad_(True)
+    q0, k0, v0 = (xf[:, i * nh * hd:(i + 1) * nh * hd].view(B, T, nh, hd) for i in range(3))
+
+    def rot(x):
+        xc = torch.view_as_complex(x.float().reshape(B, T, nh, hd // 2, 2))
+        return torch.view_as_real(xc * fc[None, :, None, :]).flatten(3)
+
+    qr, kr = (rot(q0), rot(k0)) if rope else (q0, k0)
+    # the kernels see bf16 rotated q/k (what the projection GEMM epilogue stores)
+    qkv_dev = torch.cat([qr.detach().reshape(B * T, -1), kr.detach().reshape(B * T, -1),
+                         v0.detach().reshape(B * T, -1)], dim=1).bfloat16()
+    qd, kd, vd = (qkv_dev[:, i * nh * hd:(i + 1) * nh * hd] for i in range(3))
+    qh, kh, vh = (t.transpose(1, 2) for t in (qr, kr, v0))
+    att = (qh @ kh.transpose(-2, -1)) * hd ** -0.5
+    att = att.masked_fill(torch.ones(T, T, device=cuda).tril(diagonal=src_len) == 0, float("-inf"))
+    o_ref = (torch.softmax(att, -1) @ vh).transpose(1, 2).reshape(B * T, nh * hd)
+    (o_ref * d_o.float()).sum().backward()
+    gq, gk, gv = (xf.grad[:, i * nh * hd:(i + 1) * nh * hd] for i in range(3))
+    o, lse = ops.attention_fwd(qd, kd, vd, nh, src_len=src_len, B=B, want_lse=True)
+    dq, dk, dv = ops.attention_bwd(qd, kd, vd, o, d_o, lse, nh, B=B, src_len=src_len,
+                                   rope_table=tab if rope else None)
+    torch.cuda.synchronize()
+    errs = (_rel(dq.float(), gq), _rel(dk.float(), gk), _rel(dv.float(), gv))
+    print(f"\n[attn bwd tc] hd={hd} B={B} T={T} src_len={src_len} rope={rope}: dq {errs[0]:.2e} dk {errs[1]:.2e} dv {errs[2]:.2e}")
+    assert max(errs) < 1.5e-2
+
+
 def _mirror(tag, ln, cuda):
     from sea_b200.temporal import TemporalModel
     g, sd, cfg, x, ib, tgt, _ = temporal_case(tag, ln, requires_grad=True)
