@@ -312,6 +312,35 @@ int sea_attention_bwd(const sea_attn_bwd_args* args, sea_stream_t stream);
 /* Test hook: 1 forces the CUDA-core kernel even where the tcgen05 kernel applies. */
 void sea_attention_force_simt(int on);
 
+/* ------------------------------------------------------------------ fused AdamW --------------
+ * torch.optim.AdamW.step as the reference configures it (utils/train_utils.py:33-39; called at
+ * train/train_temporal.py:258), for a list of fp32 tensors in ONE launch:
+ *   g' = g * grad_scale ; p *= 1 - lr*wd ; m = b1 m + (1-b1) g' ; v = b2 v + (1-b2) g'^2 ;
+ *   p -= lr/bias_corr1 * m / (sqrt(v)/bias_corr2_sqrt + eps)
+ * `chunks_dev` is a DEVICE array (built once by the caller while pointers are stable): every entry
+ * covers <= 2^31 consecutive elements of one tensor; all four pointers 16-byte aligned.  p_bf16
+ * (optional) receives the bf16 rounding of the updated values (the tensor-core copy of a weight,
+ * see sea_temporal_cache_slot). */
+typedef struct sea_adamw_chunk {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  void* p_bf16;
+  int32_t n;
+  int32_t reserved;
+} sea_adamw_chunk;
+typedef struct sea_adamw_hyper {
+  float lr, beta1, beta2, eps, weight_decay;
+  float bias_corr1;      /* 1 - beta1^t */
+  float bias_corr2_sqrt; /* sqrt(1 - beta2^t) */
+  float grad_scale;      /* 1, or 1/world to fold the data-parallel mean into the step */
+  float one_minus_beta1; /* (1 - beta) evaluated in double by the caller, as torch does */
+  float one_minus_beta2;
+} sea_adamw_hyper;
+int sea_adamw_step(const sea_adamw_chunk* chunks_dev, int num_chunks, const sea_adamw_hyper* hp,
+                   sea_stream_t stream);
+
 /* ------------------------------------------------------------------ temporal model -----------
  * Whole-model executor for TemporalModel with exchange_mode='sea', ib_scale_mode='mlp',
  * ib_addition_mode='add', add_info_after_cross=True (the mode both reference configs select):
@@ -375,6 +404,15 @@ size_t sea_temporal_cache_bytes(const sea_temporal_desc* d, int training);
 size_t sea_temporal_cond_cache_bytes(const sea_temporal_desc* d, int B);
 int sea_temporal_refresh(const sea_temporal_desc* d, void* cache, size_t cache_bytes, int training,
                          sea_stream_t stream);
+/* Partial refresh after an optimizer step that already wrote the straight bf16 copies itself
+ * (sea_adamw_step with p_bf16 from sea_temporal_cache_slot): `what` is a mask of SEA_REFRESH_*. */
+enum { SEA_REFRESH_STRAIGHT = 1, SEA_REFRESH_TRANSPOSED = 2, SEA_REFRESH_BIASES = 4, SEA_REFRESH_ALL = 7 };
+int sea_temporal_refresh_ex(const sea_temporal_desc* d, void* cache, size_t cache_bytes, int training,
+                            int what, sea_stream_t stream);
+/* Where the straight bf16 copy [N,K] (contiguous) of the fp32 master `master` lives inside `cache`
+ * (SEA_PREC_BF16 only); *dst = NULL when that parameter has no tensor-core copy (biases, norms). */
+int sea_temporal_cache_slot(const sea_temporal_desc* d, void* cache, int training, const float* master,
+                            void** dst);
 /* Activations / saved-for-backward tape live in a caller-owned workspace. */
 size_t sea_temporal_workspace_bytes(const sea_temporal_desc* d, int B, int T, int training);
 /* x [B,T,V,E] fp32 contiguous, ib [B,T,ib_num] fp32, y [B,T,V,E] fp32. */

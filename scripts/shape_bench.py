@@ -111,6 +111,9 @@ def run_train():
 
         us_fb = timeit(lambda: step(False), reps=5, warm=2)
         us_all = timeit(lambda: step(True), reps=5, warm=2)
+        from sea_b200.optim import AdamW as FusedAdamW
+        opt = FusedAdamW(m.parameters(), lr=1e-4, weight_decay=0.0, engine=m.engine())
+        us_fused = timeit(lambda: step(True), reps=5, warm=2)
         with torch.no_grad():
             m.eval()
             us_f = timeit(lambda: m(x, ib), reps=5, warm=2)
@@ -124,7 +127,7 @@ def run_train():
         Hh, Dd = 8 * E, E // 2
         fl = fwd_flops(B, T, E=E, H=Hh, Dd=Dd, adaln=(ln == "adaln"))
         print(f"train {cfg} B={B} T={T} M={M}: fwd {us_f:.0f} us ({fl/us_f/1e6:.0f} TF/s) fwd+bwd {us_fb:.0f} us "
-              f"({3*fl/us_fb/1e6:.0f} TF/s) +AdamW {us_all:.0f} us | breakdown ms " +
+              f"({3*fl/us_fb/1e6:.0f} TF/s) +torch AdamW {us_all:.0f} us / +fused AdamW {us_fused:.0f} us | breakdown ms " +
               " ".join(f"{k}:{v['ms']:.2f}/{v['launches']}" for k, v in ps.items()) +
               f" | gemm {ps['gemm']['work']/max(ps['gemm']['ms'],1e-9)/1e9:.0f} TF/s "
               f"attn {ps['attention']['work']/max(ps['attention']['ms'],1e-9)/1e9:.1f} TF/s "
@@ -132,6 +135,41 @@ def run_train():
         del m, opt
 
 
+def run_rollout():
+    """Per-step device time of the headline rollout (cylinder, B=32) as a function of the prefix length."""
+    from bench import build_model, make_inputs
+    B, R = 32, 100
+    m = build_model("bf16").to(dev).eval()
+    x0, ib = make_inputs(B, R, 1024, 2, 1234)
+    x0, ib = x0.to(dev), ib.to(dev)
+    eng = m.engine()
+    from sea_b200.rollout import rollout
+    for _ in range(2):
+        rollout(m, x0, ib, R)
+    torch.cuda.synchronize()
+    eng.ib_time_invariant, eng.cond_reuse, eng._cond_valid = True, True, False
+    seq = x0
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+    import time
+    host = []
+    with torch.no_grad():
+        evs[0].record()
+        for i in range(R):
+            t0 = time.perf_counter()
+            out = m(seq, ib[:, : i + 1])
+            seq = torch.cat((seq, out[:, -1:]), dim=1)
+            host.append((time.perf_counter() - t0) * 1e6)
+            evs[i + 1].record()
+            if i % 10 == 9:
+                torch.cuda.synchronize()   # keep the host from running ahead: host[] = pure issue time
+    torch.cuda.synchronize()
+    eng.ib_time_invariant, eng.cond_reuse, eng._cond_valid = False, False, False
+    devt = [evs[i].elapsed_time(evs[i + 1]) * 1e3 for i in range(R)]
+    for i in range(0, R, 5):
+        print(f"rollout t={i+1:3d} M={B*(i+1):5d}: device {devt[i]:7.1f} us  host-issue {host[i]:7.1f} us  launches {eng.last_launches}")
+    print(f"sum device {sum(devt)/1e3:.2f} ms, sum host {sum(host)/1e3:.2f} ms")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gemm"
-    {"gemm": run_gemm, "attn": run_attn, "train": run_train}[what]()
+    {"gemm": run_gemm, "attn": run_attn, "train": run_train, "rollout": run_rollout}[what]()

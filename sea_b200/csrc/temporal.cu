@@ -99,17 +99,20 @@ void layout_cache(const sea_temporal_desc* d, bool training, Arena& ar, CacheLay
 }
 
 static int pack_weight(const float* src, int N, int K, const PackedLinear& dst, int row_off,
-                       int n_total, bool fp32, cudaStream_t s) {
+                       int n_total, bool fp32, int what, cudaStream_t s) {
   // rows [row_off, row_off+N) of the (possibly fused) packed matrix
   sea_pack_args a{};
   a.src_f32 = src; a.ld = K; a.R = N; a.C = K;
   a.split = fp32 ? 2 : 0;
-  a.dst = const_cast<bf16*>(dst.w) + static_cast<long long>(row_off) * dst.ldw;
-  a.ld_dst = dst.ldw;
-  int rc = sea_pack_operand(&a, reinterpret_cast<sea_stream_t>(s));
-  if (rc) return rc;
-  ++g_launches;
-  if (dst.wT) {
+  int rc = SEA_OK;
+  if (what & SEA_REFRESH_STRAIGHT) {
+    a.dst = const_cast<bf16*>(dst.w) + static_cast<long long>(row_off) * dst.ldw;
+    a.ld_dst = dst.ldw;
+    rc = sea_pack_operand(&a, reinterpret_cast<sea_stream_t>(s));
+    if (rc) return rc;
+    ++g_launches;
+  }
+  if (dst.wT && (what & SEA_REFRESH_TRANSPOSED)) {
     a.transpose = 1;
     a.split_inner = n_total;
     a.dst = const_cast<bf16*>(dst.wT) + row_off;
@@ -126,9 +129,43 @@ static int pack_weight(const float* src, int N, int K, const PackedLinear& dst, 
     if (_rc != SEA_OK) return _rc; \
   } while (0)
 
-static int refresh_norm(const sea_norm_params& n, const PackedLinear& c2, int d2, bool fp32,
-                        cudaStream_t s) {
-  return pack_weight(n.c2_w.p, d2, d2, c2, 0, d2, fp32, s);
+// Every (fp32 master -> rows of a packed matrix) pair of the model, in one place: the refresh
+// walks it to pack, sea_temporal_cache_slot walks it to answer "where does this master's copy live".
+template <typename F>
+static int for_each_weight(const sea_temporal_desc* d, CacheLayout& c, F&& f) {
+  const int E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim, V = d->num_streams;
+  const bool ada = d->norm_kind == SEA_NORM_ADALN;
+  for (int l = 0; l < d->num_layers; ++l) {
+    for (int i = 0; i < V; ++i) {
+      const sea_stream_params& p = d->blocks[l].s[i];
+      StreamCache& sc = c.blocks[l].s[i];
+      SEA_TRY(f(p.self_attn.q_w.p, E, E, sc.qkv, 0, 3 * E));
+      SEA_TRY(f(p.self_attn.k_w.p, E, E, sc.qkv, E, 3 * E));
+      SEA_TRY(f(p.self_attn.v_w.p, E, E, sc.qkv, 2 * E, 3 * E));
+      SEA_TRY(f(p.self_attn.proj_w.p, E, E, sc.sproj, 0, E));
+      SEA_TRY(f(p.down_w.p, Dd, E, sc.down, 0, Dd));
+      SEA_TRY(f(p.up_w.p, E, Dd, sc.up, 0, E));
+      SEA_TRY(f(p.mlp0_w.p, H, E, sc.mlp0, 0, H));
+      SEA_TRY(f(p.mlp3_w.p, E, H, sc.mlp3, 0, E));
+      SEA_TRY(f(p.proj_w.p, E, E, sc.proj, 0, E));
+      for (int j = 0; j < V; ++j) {
+        if (j == i) continue;
+        const sea_attn_params& ca = p.cross_attn[j];
+        SEA_TRY(f(ca.q_w.p, Dd, Dd, sc.cq[j], 0, Dd));
+        SEA_TRY(f(ca.k_w.p, Dd, Dd, sc.ckv[j], 0, 2 * Dd));
+        SEA_TRY(f(ca.v_w.p, Dd, Dd, sc.ckv[j], Dd, 2 * Dd));
+        SEA_TRY(f(ca.proj_w.p, Dd, Dd, sc.cproj[j], 0, Dd));
+      }
+      if (ada) {
+        SEA_TRY(f(p.ln0.c2_w.p, 2 * E, 2 * E, sc.c2_ln0, 0, 2 * E));
+        SEA_TRY(f(p.ln2.c2_w.p, 2 * E, 2 * E, sc.c2_ln2, 0, 2 * E));
+        SEA_TRY(f(p.ln_cross.c2_w.p, 2 * Dd, 2 * Dd, sc.c2_lnc, 0, 2 * Dd));
+      }
+    }
+  }
+  if (ada)
+    for (int i = 0; i < V; ++i) SEA_TRY(f(d->final_ln[i].c2_w.p, 2 * E, 2 * E, c.c2_final[i], 0, 2 * E));
+  return SEA_OK;
 }
 
 }  // namespace sea
@@ -178,8 +215,8 @@ static int validate_desc(const sea_temporal_desc* d) {
   return SEA_OK;
 }
 
-extern "C" int sea_temporal_refresh(const sea_temporal_desc* d, void* cache, size_t cache_bytes,
-                                    int training, sea_stream_t stream) {
+extern "C" int sea_temporal_refresh_ex(const sea_temporal_desc* d, void* cache, size_t cache_bytes,
+                                       int training, int what, sea_stream_t stream) {
   SEA_TRY(validate_desc(d));
   if (!cache) return SEA_ERR_INVALID;
   if (cache_bytes < sea_temporal_cache_bytes(d, training)) return SEA_ERR_WORKSPACE;
@@ -189,44 +226,48 @@ extern "C" int sea_temporal_refresh(const sea_temporal_desc* d, void* cache, siz
   CacheLayout c;
   layout_cache(d, training != 0, ar, c);
   const bool fp32 = d->precision == SEA_PREC_FP32;
-  const int E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim, V = d->num_streams;
-  const bool ada = d->norm_kind == SEA_NORM_ADALN;
-  for (int l = 0; l < d->num_layers; ++l) {
-    for (int i = 0; i < V; ++i) {
-      const sea_stream_params& p = d->blocks[l].s[i];
-      StreamCache& sc = c.blocks[l].s[i];
-      SEA_TRY(pack_weight(p.self_attn.q_w.p, E, E, sc.qkv, 0, 3 * E, fp32, s));
-      SEA_TRY(pack_weight(p.self_attn.k_w.p, E, E, sc.qkv, E, 3 * E, fp32, s));
-      SEA_TRY(pack_weight(p.self_attn.v_w.p, E, E, sc.qkv, 2 * E, 3 * E, fp32, s));
-      SEA_CUDA_OK(cudaMemcpyAsync(sc.qkv_bias, p.self_attn.q_b.p, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
-      SEA_CUDA_OK(cudaMemcpyAsync(sc.qkv_bias + E, p.self_attn.k_b.p, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
-      SEA_CUDA_OK(cudaMemcpyAsync(sc.qkv_bias + 2 * E, p.self_attn.v_b.p, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
-      SEA_TRY(pack_weight(p.self_attn.proj_w.p, E, E, sc.sproj, 0, E, fp32, s));
-      SEA_TRY(pack_weight(p.down_w.p, Dd, E, sc.down, 0, Dd, fp32, s));
-      SEA_TRY(pack_weight(p.up_w.p, E, Dd, sc.up, 0, E, fp32, s));
-      SEA_TRY(pack_weight(p.mlp0_w.p, H, E, sc.mlp0, 0, H, fp32, s));
-      SEA_TRY(pack_weight(p.mlp3_w.p, E, H, sc.mlp3, 0, E, fp32, s));
-      SEA_TRY(pack_weight(p.proj_w.p, E, E, sc.proj, 0, E, fp32, s));
-      for (int j = 0; j < V; ++j) {
-        if (j == i) continue;
-        const sea_attn_params& ca = p.cross_attn[j];
-        SEA_TRY(pack_weight(ca.q_w.p, Dd, Dd, sc.cq[j], 0, Dd, fp32, s));
-        SEA_TRY(pack_weight(ca.k_w.p, Dd, Dd, sc.ckv[j], 0, 2 * Dd, fp32, s));
-        SEA_TRY(pack_weight(ca.v_w.p, Dd, Dd, sc.ckv[j], Dd, 2 * Dd, fp32, s));
-        SEA_CUDA_OK(cudaMemcpyAsync(sc.ckv_bias[j], ca.k_b.p, sizeof(float) * Dd, cudaMemcpyDeviceToDevice, s));
-        SEA_CUDA_OK(cudaMemcpyAsync(sc.ckv_bias[j] + Dd, ca.v_b.p, sizeof(float) * Dd, cudaMemcpyDeviceToDevice, s));
-        SEA_TRY(pack_weight(ca.proj_w.p, Dd, Dd, sc.cproj[j], 0, Dd, fp32, s));
-      }
-      if (ada) {
-        SEA_TRY(refresh_norm(p.ln0, sc.c2_ln0, 2 * E, fp32, s));
-        SEA_TRY(refresh_norm(p.ln2, sc.c2_ln2, 2 * E, fp32, s));
-        SEA_TRY(refresh_norm(p.ln_cross, sc.c2_lnc, 2 * Dd, fp32, s));
+  const int E = d->embed_dim, Dd = d->down_dim, V = d->num_streams;
+  SEA_TRY(for_each_weight(d, c, [&](const float* src, int N, int K, const PackedLinear& dst, int row_off, int n_total) {
+    return pack_weight(src, N, K, dst, row_off, n_total, fp32, what, s);
+  }));
+  if (what & SEA_REFRESH_BIASES) {
+    for (int l = 0; l < d->num_layers; ++l) {
+      for (int i = 0; i < V; ++i) {
+        const sea_stream_params& p = d->blocks[l].s[i];
+        StreamCache& sc = c.blocks[l].s[i];
+        SEA_CUDA_OK(cudaMemcpyAsync(sc.qkv_bias, p.self_attn.q_b.p, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
+        SEA_CUDA_OK(cudaMemcpyAsync(sc.qkv_bias + E, p.self_attn.k_b.p, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
+        SEA_CUDA_OK(cudaMemcpyAsync(sc.qkv_bias + 2 * E, p.self_attn.v_b.p, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
+        for (int j = 0; j < V; ++j) {
+          if (j == i) continue;
+          const sea_attn_params& ca = p.cross_attn[j];
+          SEA_CUDA_OK(cudaMemcpyAsync(sc.ckv_bias[j], ca.k_b.p, sizeof(float) * Dd, cudaMemcpyDeviceToDevice, s));
+          SEA_CUDA_OK(cudaMemcpyAsync(sc.ckv_bias[j] + Dd, ca.v_b.p, sizeof(float) * Dd, cudaMemcpyDeviceToDevice, s));
+        }
       }
     }
   }
-  if (ada)
-    for (int i = 0; i < V; ++i) SEA_TRY(refresh_norm(d->final_ln[i], c.c2_final[i], 2 * E, fp32, s));
   return SEA_OK;
+}
+
+extern "C" int sea_temporal_refresh(const sea_temporal_desc* d, void* cache, size_t cache_bytes,
+                                    int training, sea_stream_t stream) {
+  return sea_temporal_refresh_ex(d, cache, cache_bytes, training, SEA_REFRESH_ALL, stream);
+}
+
+extern "C" int sea_temporal_cache_slot(const sea_temporal_desc* d, void* cache, int training,
+                                       const float* master, void** dst) {
+  SEA_TRY(validate_desc(d));
+  if (!cache || !master || !dst) return SEA_ERR_INVALID;
+  *dst = nullptr;
+  if (d->precision != SEA_PREC_BF16) return SEA_OK;  // split copies are not a plain rounding of the master
+  Arena ar{static_cast<char*>(cache)};
+  CacheLayout c;
+  layout_cache(d, training != 0, ar, c);
+  return for_each_weight(d, c, [&](const float* src, int, int, const PackedLinear& pl, int row_off, int) {
+    if (src == master) *dst = const_cast<bf16*>(pl.w) + static_cast<long long>(row_off) * pl.ldw;
+    return static_cast<int>(SEA_OK);
+  });
 }
 
 // ---------------------------------------------------------------------------------- the tape

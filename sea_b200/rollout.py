@@ -46,10 +46,13 @@ def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
         for i in range(steps):
             out = model(seq, ib[:, : i + 1])
             seq = torch.cat((seq, out[:, -1:]), dim=1)
+            if eng is not None:
+                eng.weights_frozen = True   # checked once by the first call of this loop
     finally:
         if eng is not None:
             eng.ib_time_invariant = prev
             eng.cond_reuse, eng._cond_valid = False, False
+            eng.weights_frozen = False
     return seq[:, 1:]
 
 

@@ -211,6 +211,8 @@ class TemporalEngine:
         self._cond_valid = False
         self._cond_buf = None
         self._cond_key = None
+        # rollout(): weights cannot change inside the no_grad loop -> skip the per-call freshness scan
+        self.weights_frozen = False
 
     # -- hyper-parameters are read off the module tree (works for the mirror and the reference) --
     def _hyper(self):
@@ -363,6 +365,8 @@ class TemporalEngine:
         return (training, tuple(p.data_ptr() for _, p in live), sum(p._version for _, p in live))
 
     def _ensure(self, training: bool):
+        if self.weights_frozen and self._cache_key is not None and self._cache_key[0] == training:
+            return  # rollout(): same weights for every step of the loop, skip the per-call version scan
         key = self._key(training)
         if self._desc is None or self._cache_key is None or key[:2] != self._cache_key[:2]:
             self._build(training)
@@ -377,6 +381,22 @@ class TemporalEngine:
                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                       "temporal_refresh")
             self._cache_key = key
+
+    def after_optimizer_step(self, straight_copies_fresh: bool) -> None:
+        """Called by sea_b200.optim.AdamW.step(): the masters changed through raw pointers (no
+        ``_version`` bump).  If the optimizer already wrote the straight bf16 copies, only the dgrad
+        transposes and the fused bias vectors are rebuilt; otherwise everything is."""
+        if self._cache is None or self._cache_key is None or self._desc is None:
+            return
+        training = bool(self._cache_key[0])
+        what = 6 if straight_copies_fresh else 7   # SEA_REFRESH_TRANSPOSED | SEA_REFRESH_BIASES, or ALL
+        with torch.cuda.device(self._dev):
+            check(lib.sea_temporal_refresh_ex(C.byref(self._desc), C.c_void_p(self._cache.data_ptr()),
+                                              C.c_size_t(self._cache.numel()), int(training), what,
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                  "temporal_refresh_ex")
+        self._cache_key = self._key(training)
+        self._cond_valid = False
 
     def workspace(self, B: int, T: int, training: bool) -> torch.Tensor:
         k = (B, T, training)

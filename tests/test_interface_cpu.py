@@ -91,7 +91,8 @@ def test_ctypes_struct_sizes_match_header():
              "sea_block_params": S.BlockParams, "sea_temporal_desc": S.TemporalDesc,
              "sea_norm_bwd_args": S.NormBwdArgs, "sea_ln_gelu_bwd_args": S.LnGeluBwdArgs,
              "sea_attn_bwd_args": S.AttnBwdArgs, "sea_tipi_bwd_args": S.TipiBwdArgs,
-             "sea_spatial_layer": S.SpatialLayer, "sea_spatial_desc": S.SpatialDesc}
+             "sea_spatial_layer": S.SpatialLayer, "sea_spatial_desc": S.SpatialDesc,
+             "sea_adamw_hyper": __import__("sea_b200.optim", fromlist=["AdamWHyper"]).AdamWHyper}
     src = '#include <stdio.h>\n#include "sea_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:
@@ -103,3 +104,5 @@ def test_ctypes_struct_sizes_match_header():
     sizes = dict(zip(out[::2], map(int, out[1::2])))
     for n, cls in pairs.items():
         assert ctypes.sizeof(cls) == sizes[n], (n, ctypes.sizeof(cls), sizes[n])
+    from sea_b200.optim import _CHUNK_DT
+    assert _CHUNK_DT.itemsize == 48  # sea_adamw_chunk: 5 pointers + 2 int32
