@@ -93,6 +93,11 @@ typedef struct sea_gemm_problem {
   const void* b; /* bf16 [N,K], ldb  (nn.Linear weight layout) */
   int64_t ldb;
   sea_gemm_epilogue epi;
+  int32_t b_is_static; /* promise: B was completely written before the last NON-overlapped kernel
+                          boundary of the stream (a weight matrix).  The TMA producer then requests its
+                          first ring of B tiles before griddepcontrol.wait, so the weight fetch overlaps
+                          the upstream kernel's tail.  0 = B may come from a kernel still in flight. */
+  int32_t reserved;
 } sea_gemm_problem;
 
 /* `num_problems` (1..4) same-shape problems in ONE launch (the V field streams are independent). */
@@ -138,6 +143,8 @@ typedef struct sea_norm_args {
   float* stats;
 } sea_norm_args;
 int sea_norm_fwd(const sea_norm_args* args, sea_stream_t stream);
+/* `n` (1..SEA_MAX_STREAMS) norms of equal (M, d, kind) in ONE launch (the V field streams). */
+int sea_norm_fwd_group(int n, const sea_norm_args* host_args, sea_stream_t stream);
 
 /* AdaLN cond_mlp[0] + SiLU on the scalar condition: h[m,j] = SiLU(w1[j,:]·ib[m,:] + b1[j]), j < n
  * (models/base_blocks.py:337-339, 344).  Either output may be NULL. */
@@ -177,6 +184,8 @@ typedef struct sea_ln_gelu_args {
   float* stats;
 } sea_ln_gelu_args;
 int sea_ln_gelu_fwd(const sea_ln_gelu_args* args, sea_stream_t stream);
+/* `n` (1..SEA_MAX_STREAMS) problems of equal (M, H, ldh, ldg, dtype) in ONE launch. */
+int sea_ln_gelu_fwd_group(int n, const sea_ln_gelu_args* host_args, sea_stream_t stream);
 
 /* ------------------------------------------------------------------ operand packing ----------
  * src [R,C] (fp32 or bf16) -> bf16 dst, optionally transposed, optionally GELU'd on load,
@@ -284,6 +293,10 @@ typedef struct sea_attn_args {
   int32_t prec; /* SEA_PREC_BF16: bf16 in/out; SEA_PREC_FP32: fp32 in/out */
 } sea_attn_args;
 int sea_attention_fwd(const sea_attn_args* args, sea_stream_t stream);
+/* `n` (1..SEA_MAX_STREAMS) problems of identical shape (B, T, n_heads, head_dim, src_len, scale,
+ * prec, ldo) in ONE launch: the self-attention of the V independent field streams
+ * (models/temporal.py:135-136 runs them one after the other). */
+int sea_attention_fwd_group(int n, const sea_attn_args* host_args, sea_stream_t stream);
 /* K3: backward of sea_attention_fwd.  d_o is the gradient of o; delta [B,n_heads,T] is scratch.
  * dq/dk/dv use the same row/head layout.  If rope_table is given, dq and dk are rotated back by
  * -theta (the forward RoPE lives in the projection GEMM epilogue), so they are gradients with

@@ -168,6 +168,20 @@ def run_rollout():
     for i in range(0, R, 5):
         print(f"rollout t={i+1:3d} M={B*(i+1):5d}: device {devt[i]:7.1f} us  host-issue {host[i]:7.1f} us  launches {eng.last_launches}")
     print(f"sum device {sum(devt)/1e3:.2f} ms, sum host {sum(host)/1e3:.2f} ms")
+    # graph replays
+    from sea_b200.rollout import RolloutPlan
+    plan = RolloutPlan(m, B, R, dev)
+    plan.run(x0, ib)
+    torch.cuda.synchronize()
+    evs[0].record()
+    for i, g in enumerate(plan.graphs):
+        g.replay()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    devg = [evs[i].elapsed_time(evs[i + 1]) * 1e3 for i in range(R)]
+    for i in range(0, R, 5):
+        print(f"graph   t={i+1:3d} M={B*(i+1):5d}: device {devg[i]:7.1f} us  nodes {plan.launches[i]}")
+    print(f"sum graph device {sum(devg)/1e3:.2f} ms")
 
 
 if __name__ == "__main__":

@@ -46,6 +46,8 @@ class GemmProblem(C.Structure):
         ("b", C.c_void_p),
         ("ldb", C.c_int64),
         ("epi", GemmEpilogue),
+        ("b_is_static", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

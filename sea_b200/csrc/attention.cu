@@ -6,19 +6,41 @@
 
 namespace sea {
 int attention_fwd_simt(const sea_attn_args* a, cudaStream_t s);
-int attention_fwd_tc(const sea_attn_args* a, cudaStream_t s);  // attention_tc.cu
+int attention_fwd_tc(int n, const sea_attn_args* a, cudaStream_t s);  // attention_tc.cu
 bool attention_tc_supported(const sea_attn_args* a);
 int g_force_simt = 0;  // test hook: route bf16 attention (fwd and bwd) to the CUDA-core kernels
+
+static int validate(const sea_attn_args* a) {
+  if (!a->q || !a->k || !a->v || !a->o) return SEA_ERR_INVALID;
+  if (a->B <= 0 || a->T <= 0 || a->n_heads <= 0 || a->head_dim <= 0) return SEA_ERR_INVALID;
+  if (a->prec != SEA_PREC_BF16 && a->prec != SEA_PREC_FP32) return SEA_ERR_INVALID;
+  return SEA_OK;
+}
 }  // namespace sea
 
 extern "C" void sea_attention_force_simt(int on) { sea::g_force_simt = on; }
 
 extern "C" int sea_attention_fwd(const sea_attn_args* a, sea_stream_t stream) {
+  return sea_attention_fwd_group(1, a, stream);
+}
+
+extern "C" int sea_attention_fwd_group(int n, const sea_attn_args* a, sea_stream_t stream) {
   using namespace sea;
-  if (!a || !a->q || !a->k || !a->v || !a->o) return SEA_ERR_INVALID;
-  if (a->B <= 0 || a->T <= 0 || a->n_heads <= 0 || a->head_dim <= 0) return SEA_ERR_INVALID;
-  if (a->prec != SEA_PREC_BF16 && a->prec != SEA_PREC_FP32) return SEA_ERR_INVALID;
+  if (!a || n < 1 || n > SEA_MAX_STREAMS) return SEA_ERR_INVALID;
+  bool tc = !g_force_simt;
+  for (int i = 0; i < n; ++i) {
+    int rc = validate(&a[i]);
+    if (rc) return rc;
+    if (a[i].B != a[0].B || a[i].T != a[0].T || a[i].n_heads != a[0].n_heads || a[i].head_dim != a[0].head_dim ||
+        a[i].src_len != a[0].src_len || a[i].scale != a[0].scale || a[i].prec != a[0].prec || a[i].ldo != a[0].ldo)
+      return SEA_ERR_INVALID;
+    tc = tc && attention_tc_supported(&a[i]);
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (!g_force_simt && attention_tc_supported(a)) return attention_fwd_tc(a, s);
-  return attention_fwd_simt(a, s);
+  if (tc) return attention_fwd_tc(n, a, s);
+  for (int i = 0; i < n; ++i) {
+    int rc = attention_fwd_simt(&a[i], s);
+    if (rc) return rc;
+  }
+  return SEA_OK;
 }

@@ -12,7 +12,12 @@
 //               (k <= q + src_len, no tril buffer), running max / sum in registers, exp2,
 //               P -> bf16 -> tcgen05.st; O is rescaled in TMEM only when the running max grew by
 //               more than 2^8 (lazy rescale); final O / l and log-sum-exp written from registers.
-// TMEM columns: S [0,BKV) | P [128,128+BKV/2) | O [256,256+HD).
+// TMEM columns: S [0,BKV), P (packed bf16) overwrites S in place [0,BKV/2) — tcgen05.mma executes
+// in issue order, so the next tile's S cannot overtake the P·V that reads P — and O [128,128+HD)
+// (256 columns allocated) or, for HD = 256, O [256,512) (512 allocated).
+// STAGES = 1 (the whole key range fits one tile: short prefixes of a rollout) halves the shared
+// memory, so two CTAs share an SM and B x heads = 256 CTAs run as a single wave.
+// Up to SEA_MAX_STREAMS same-shape problems (the V field streams) share one launch (blockIdx.z).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -27,29 +32,38 @@ namespace {
 
 constexpr int BQ = 128;
 constexpr int kThreads = 192;
-constexpr uint32_t kColS = 0, kColP = 128, kColO = 256;
+constexpr uint32_t kColS = 0, kColP = 0;
 
-struct alignas(64) AttnTcParams {
+struct AttnTcItem {
   CUtensorMap tq, tk, tv;
   __nv_bfloat16* o;
-  long long ldo;
   float* lse;
+};
+struct alignas(64) AttnTcParams {
+  AttnTcItem it[SEA_MAX_STREAMS];
+  long long ldo;
   int B, T, n_heads, src_len;
   float scale_log2;  // scale * log2(e)
 };
 
-template <int HD, int BKV>
+template <int HD, int BKV, int STAGES_>
 struct ACfg {
   static constexpr int ATOMS = HD / 64;
   static constexpr int Q_BYTES = BQ * HD * 2;
   static constexpr int KV_BYTES = BKV * HD * 2;   // one of K or V
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = STAGES_;
   static constexpr int SMEM = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 128;
+  static constexpr uint32_t COL_O = HD <= 128 ? 128 : 256;
+  static constexpr uint32_t TMEM_COLS = HD <= 128 ? 256 : 512;
+  static constexpr int MIN_CTAS = (SMEM <= 110 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
 };
 
-template <int HD, int BKV>
-__global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
-  using C = ACfg<HD, BKV>;
+template <int HD, int BKV, int STAGES_>
+__global__ void __launch_bounds__(kThreads, (ACfg<HD, BKV, STAGES_>::MIN_CTAS))
+attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
+  using C = ACfg<HD, BKV, STAGES_>;
+  constexpr uint32_t kColO = C::COL_O;
+  const AttnTcItem& p = pp.it[blockIdx.z / pp.B];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -67,10 +81,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;  // heavy (late) query tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.y, b = blockIdx.z % pp.B;
   const int q0 = qt * BQ;
-  const int q_hi = min(p.T - 1, q0 + BQ - 1);
-  const int k_last = min(p.T - 1, q_hi + p.src_len);
+  const int q_hi = min(pp.T - 1, q0 + BQ - 1);
+  const int k_last = min(pp.T - 1, q_hi + pp.src_len);
   const int n_kv = k_last / BKV + 1;
 
   if (threadIdx.x == 0) {
@@ -87,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
     ptx::mbar_init(o_done, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -103,8 +117,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       for (int a = 0; a < C::ATOMS; ++a)
         ptx::tma_load_3d(sQ + a * (BQ * 128), &p.tq, q_full, h * HD + a * 64, q0, b);
       for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int s = j % C::STAGES;
+        const uint32_t ph = (j / C::STAGES) & 1;
         ptx::mbar_wait(&kv_empty[s], ph ^ 1);
         ptx::mbar_expect_tx(&kv_full[s], 2 * C::KV_BYTES);
 #pragma unroll
@@ -120,8 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
     constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
     ptx::mbar_wait(q_full, 0);
     for (int j = 0; j < n_kv; ++j) {
-      const int s = j & 1;
-      ptx::mbar_wait(&kv_full[s], (j >> 1) & 1);
+      const int s = j % C::STAGES;
+      ptx::mbar_wait(&kv_full[s], (j / C::STAGES) & 1);
       ptx::tc_fence_after();
       if (lane == 0) {
         const uint32_t qb = ptx::smem_u32(sQ);
@@ -162,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
       const int kv0 = j * BKV;
       ptx::mbar_wait(s_full, j & 1);
       ptx::tc_fence_after();
-      const bool need_mask = (kv0 + BKV - 1 > q0 + p.src_len) || (kv0 + BKV > p.T);
+      const bool need_mask = (kv0 + BKV - 1 > q0 + pp.src_len) || (kv0 + BKV > pp.T);
       // pass 1: row max of the scaled, masked scores
       float mx = -INFINITY;
 #pragma unroll
@@ -172,10 +186,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          float sv = __uint_as_float(r[e]) * p.scale_log2;
+          float sv = __uint_as_float(r[e]) * pp.scale_log2;
           if (need_mask) {
             const int kk = kv0 + c * 32 + e;
-            if (kk > q + p.src_len || kk >= p.T) sv = -INFINITY;
+            if (kk > q + pp.src_len || kk >= pp.T) sv = -INFINITY;
           }
           mx = fmaxf(mx, sv);
         }
@@ -214,12 +228,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          float s0 = __uint_as_float(r[e]) * p.scale_log2;
-          float s1 = __uint_as_float(r[e + 1]) * p.scale_log2;
+          float s0 = __uint_as_float(r[e]) * pp.scale_log2;
+          float s1 = __uint_as_float(r[e + 1]) * pp.scale_log2;
           if (need_mask) {
             const int kk = kv0 + c * 32 + e;
-            if (kk > q + p.src_len || kk >= p.T) s0 = -INFINITY;
-            if (kk + 1 > q + p.src_len || kk + 1 >= p.T) s1 = -INFINITY;
+            if (kk > q + pp.src_len || kk >= pp.T) s0 = -INFINITY;
+            if (kk + 1 > q + pp.src_len || kk + 1 >= pp.T) s1 = -INFINITY;
           }
           const float p0 = exp2f(s0 - m_use);
           const float p1 = exp2f(s1 - m_use);
@@ -236,13 +250,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
     ptx::mbar_wait(o_done, (n_kv - 1) & 1);
     ptx::tc_fence_after();
     const float inv = 1.f / l_sum;
-    __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.T + q) * p.ldo + h * HD;
+    __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * pp.T + q) * pp.ldo + h * HD;
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) {
       uint32_t r[32];
       ptx::tmem_ld_32x32(tmem + lane_base + kColO + c * 32, r);
       ptx::tmem_ld_wait();
-      if (q < p.T) {
+      if (q < pp.T) {
 #pragma unroll
         for (int e = 0; e < 32; e += 8) {
           uint4 o;
@@ -254,8 +268,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
         }
       }
     }
-    if (p.lse != nullptr && q < p.T)
-      p.lse[(static_cast<long long>(b) * p.n_heads + h) * p.T + q] =
+    if (p.lse != nullptr && q < pp.T)
+      p.lse[(static_cast<long long>(b) * pp.n_heads + h) * pp.T + q] =
           (m_ref + log2f(l_sum)) * 0.69314718055994530942f;
   }
 
@@ -263,36 +277,39 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_tc_kernel(const __grid_c
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, 512);
+    ptx::tmem_dealloc(tmem, C::TMEM_COLS);
   }
 }
 
-template <int HD, int BKV>
-int launch_tc(const sea_attn_args* a, cudaStream_t s) {
-  using C = ACfg<HD, BKV>;
+template <int HD, int BKV, int STAGES_>
+int launch_tc(int n, const sea_attn_args* a, cudaStream_t s) {
+  using C = ACfg<HD, BKV, STAGES_>;
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    SEA_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, BKV>,
+    SEA_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, BKV, STAGES_>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set[dev] = true;
   }
   AttnTcParams p;
   const uint64_t wq = static_cast<uint64_t>(a->n_heads) * HD;
-  int rc = make_tmap_bf16_3d(&p.tq, a->q, wq, a->T, a->B, a->ldq, a->ldq * static_cast<uint64_t>(a->T), 64, BQ);
-  if (rc) return rc;
-  rc = make_tmap_bf16_3d(&p.tk, a->k, wq, a->T, a->B, a->ldk, a->ldk * static_cast<uint64_t>(a->T), 64, BKV);
-  if (rc) return rc;
-  rc = make_tmap_bf16_3d(&p.tv, a->v, wq, a->T, a->B, a->ldv, a->ldv * static_cast<uint64_t>(a->T), 64, BKV);
-  if (rc) return rc;
-  p.o = static_cast<__nv_bfloat16*>(a->o);
+  for (int i = 0; i < n; ++i) {
+    const sea_attn_args& x = a[i];
+    int rc = make_tmap_bf16_3d(&p.it[i].tq, x.q, wq, x.T, x.B, x.ldq, x.ldq * static_cast<uint64_t>(x.T), 64, BQ);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&p.it[i].tk, x.k, wq, x.T, x.B, x.ldk, x.ldk * static_cast<uint64_t>(x.T), 64, BKV);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&p.it[i].tv, x.v, wq, x.T, x.B, x.ldv, x.ldv * static_cast<uint64_t>(x.T), 64, BKV);
+    if (rc) return rc;
+    p.it[i].o = static_cast<__nv_bfloat16*>(x.o);
+    p.it[i].lse = x.lse;
+  }
   p.ldo = a->ldo;
-  p.lse = a->lse;
   p.B = a->B; p.T = a->T; p.n_heads = a->n_heads; p.src_len = a->src_len;
   p.scale_log2 = a->scale * 1.44269504088896340736f;
-  dim3 grid((a->T + BQ - 1) / BQ, a->n_heads, a->B);
-  SEA_LAUNCH((attn_fwd_tc_kernel<HD, BKV>), grid, kThreads, C::SMEM, s, p);
+  dim3 grid((a->T + BQ - 1) / BQ, a->n_heads, a->B * n);
+  SEA_LAUNCH((attn_fwd_tc_kernel<HD, BKV, STAGES_>), grid, kThreads, C::SMEM, s, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -310,13 +327,15 @@ bool attention_tc_supported(const sea_attn_args* a) {
   return true;
 }
 
-int attention_fwd_tc(const sea_attn_args* a, cudaStream_t s) {
+// n same-shape problems (B, T, n_heads, head_dim, src_len, scale, ldo equal; checked by the caller)
+int attention_fwd_tc(int n, const sea_attn_args* a, cudaStream_t s) {
   int rc = ensure_init();
   if (rc) return rc;
+  const int k_last = (a->T - 1 + a->src_len < a->T - 1) ? a->T - 1 + a->src_len : a->T - 1;
   switch (a->head_dim) {
-    case 64: return launch_tc<64, 128>(a, s);
-    case 128: return launch_tc<128, 128>(a, s);
-    case 256: return launch_tc<256, 64>(a, s);
+    case 64: return k_last < 128 ? launch_tc<64, 128, 1>(n, a, s) : launch_tc<64, 128, 2>(n, a, s);
+    case 128: return k_last < 128 ? launch_tc<128, 128, 1>(n, a, s) : launch_tc<128, 128, 2>(n, a, s);
+    case 256: return k_last < 64 ? launch_tc<256, 64, 1>(n, a, s) : launch_tc<256, 64, 2>(n, a, s);
     default: return SEA_ERR_UNSUPPORTED;
   }
 }

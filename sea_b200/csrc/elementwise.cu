@@ -103,10 +103,14 @@ struct NormDev {
 
 constexpr int kNormMaxChunks = 16;  // 16 chunks x 32 lanes x 4 floats = 2048
 
+// Up to SEA_MAX_STREAMS same-shape rows-norms (the V field streams) share a launch: blockIdx.y.
+struct NormGroup { NormDev it[SEA_MAX_STREAMS]; };
+
 template <int CH, bool ADALN>
-__global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const NormDev a) {
+__global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const __grid_constant__ NormGroup grp) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
+  const NormDev& a = grp.it[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * (blockDim.x >> 5) + warp;
   if (m >= a.M) return;
@@ -349,15 +353,20 @@ __global__ void __launch_bounds__(256) ln_gelu_fwd_kernel(const TIn* __restrict_
 // 1-D bulk copies (cp.async.bulk + mbarrier: no registers tied up, up to 64 KB in flight per CTA,
 // 3 CTAs / SM), takes the statistics with a warp-pair per row, then sweeps column-wise so each
 // thread loads the fp32 affine vectors of its 8 columns ONCE for all R rows.
+struct LnGeluItem { const void* h; const float* weight; const float* bias; void* g; float* stats; };
+struct LnGeluGroup { LnGeluItem it[SEA_MAX_STREAMS]; };
+
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(256) ln_gelu_fwd_smem_kernel(const TIn* __restrict__ h, long long ldh,
-                                                               int M, int H,
-                                                               const float* __restrict__ weight,
-                                                               const float* __restrict__ bias,
-                                                               TOut* __restrict__ g, long long ldg,
-                                                               float* __restrict__ stats, int R) {
+__global__ void __launch_bounds__(256) ln_gelu_fwd_smem_kernel(const __grid_constant__ LnGeluGroup grp, long long ldh,
+                                                               int M, int H, long long ldg, int R) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
+  const LnGeluItem& item = grp.it[blockIdx.y];
+  const TIn* __restrict__ h = static_cast<const TIn*>(item.h);
+  const float* __restrict__ weight = item.weight;
+  const float* __restrict__ bias = item.bias;
+  TOut* __restrict__ g = static_cast<TOut*>(item.g);
+  float* __restrict__ stats = item.stats;
   extern __shared__ __align__(128) uint8_t ln_smem[];
   __shared__ uint64_t bar;
   __shared__ float red[8];
@@ -650,16 +659,17 @@ extern "C" int sea_tipi_hidden(const float* ib, int64_t ld_ib, int M, int ib_num
 }
 
 template <int CH>
-static int launch_norm(const NormDev& d, cudaStream_t s) {
+static int launch_norm(const NormGroup& g, int n, cudaStream_t s) {
+  const NormDev& d = g.it[0];
   const int rows_per_cta = 8;
-  const int grid = (d.M + rows_per_cta - 1) / rows_per_cta;
-  if (d.kind == SEA_NORM_ADALN) SEA_LAUNCH((norm_fwd_kernel<CH, true>), grid, rows_per_cta * 32, 0, s, d);
-  else SEA_LAUNCH((norm_fwd_kernel<CH, false>), grid, rows_per_cta * 32, 0, s, d);
+  const dim3 grid((d.M + rows_per_cta - 1) / rows_per_cta, n);
+  if (d.kind == SEA_NORM_ADALN) SEA_LAUNCH((norm_fwd_kernel<CH, true>), grid, rows_per_cta * 32, 0, s, g);
+  else SEA_LAUNCH((norm_fwd_kernel<CH, false>), grid, rows_per_cta * 32, 0, s, g);
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int sea_norm_fwd(const sea_norm_args* a, sea_stream_t stream) {
-  if (!a || !a->x || !a->weight || a->M <= 0 || a->d <= 0) return SEA_ERR_INVALID;
+static int fill_norm(const sea_norm_args* a, NormDev& d) {
+  if (!a->x || !a->weight || a->M <= 0 || a->d <= 0) return SEA_ERR_INVALID;
   if ((a->d % 4) || a->d > kNormMaxChunks * 128) return SEA_ERR_UNSUPPORTED;
   if (!a->y_f32 && !a->y_bf16) return SEA_ERR_INVALID;
   if (a->kind == SEA_NORM_ADALN && !a->cond) return SEA_ERR_INVALID;
@@ -669,7 +679,6 @@ extern "C" int sea_norm_fwd(const sea_norm_args* a, sea_stream_t stream) {
   if (a->tipi_g && (!a->tipi_w || !a->tipi_b || !a->x_out || a->tipi_hid <= 0 || (a->ldxo % 4)))
     return SEA_ERR_INVALID;
   if (a->add_rows && (!a->x_out || (a->ld_add % 4) || (a->ldxo % 4))) return SEA_ERR_INVALID;
-  NormDev d;
   d.x = a->x; d.ldx = a->ldx; d.M = a->M; d.d = a->d; d.kind = a->kind;
   d.weight = a->weight; d.bias = a->bias; d.cond = a->cond; d.ldc = a->ldc;
   d.cond_div = a->cond_div > 0 ? a->cond_div : 1;
@@ -679,10 +688,25 @@ extern "C" int sea_norm_fwd(const sea_norm_args* a, sea_stream_t stream) {
   d.y_f32 = a->y_f32; d.ldy_f32 = a->ldy_f32;
   d.y_bf16 = static_cast<__nv_bfloat16*>(a->y_bf16); d.ldy_bf16 = a->ldy_bf16;
   d.stats = a->stats;
+  return SEA_OK;
+}
+
+extern "C" int sea_norm_fwd_group(int n, const sea_norm_args* a, sea_stream_t stream) {
+  if (!a || n < 1 || n > SEA_MAX_STREAMS) return SEA_ERR_INVALID;
+  NormGroup g;
+  for (int i = 0; i < n; ++i) {
+    int rc = fill_norm(&a[i], g.it[i]);
+    if (rc) return rc;
+    if (a[i].M != a[0].M || a[i].d != a[0].d || a[i].kind != a[0].kind) return SEA_ERR_INVALID;
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a->d <= 512) return launch_norm<4>(d, s);
-  if (a->d <= 1024) return launch_norm<8>(d, s);
-  return launch_norm<16>(d, s);
+  if (a->d <= 512) return launch_norm<4>(g, n, s);
+  if (a->d <= 1024) return launch_norm<8>(g, n, s);
+  return launch_norm<16>(g, n, s);
+}
+
+extern "C" int sea_norm_fwd(const sea_norm_args* a, sea_stream_t stream) {
+  return sea_norm_fwd_group(1, a, stream);
 }
 
 extern "C" int sea_tipi_rows(const float* g, int64_t ldg, int R, int E, int hid, const float* w3,
@@ -694,11 +718,11 @@ extern "C" int sea_tipi_rows(const float* g, int64_t ldg, int R, int E, int hid,
 }
 
 template <typename TIn, typename TOut>
-static int launch_ln_gelu_smem(const sea_ln_gelu_args* a, const TIn* h, TOut* g, cudaStream_t s) {
+static int launch_ln_gelu_smem(int n, const sea_ln_gelu_args* a, cudaStream_t s) {
   // R rows per CTA, power of two <= 8, at most 64 KB of rows in shared memory
   int R = 8;
   while (R > 1 && static_cast<size_t>(R) * a->H * sizeof(TIn) > 64 * 1024) R >>= 1;
-  while (R > 1 && (a->M + R - 1) / R < 2 * 148) R >>= 1;   // keep the machine full for small M
+  while (R > 1 && static_cast<long long>((a->M + R - 1) / R) * n < 2 * 148) R >>= 1;   // keep the machine full for small M
   if ((a->H % (8 * (8 / R) )) != 0) R = 1;
   const size_t smem = static_cast<size_t>(R) * a->H * sizeof(TIn);
   static bool attr_set[16] = {};
@@ -708,15 +732,19 @@ static int launch_ln_gelu_smem(const sea_ln_gelu_args* a, const TIn* h, TOut* g,
     SEA_CUDA_OK(cudaFuncSetAttribute(ln_gelu_fwd_smem_kernel<TIn, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set[dev] = true;
   }
-  SEA_LAUNCH((ln_gelu_fwd_smem_kernel<TIn, TOut>), (a->M + R - 1) / R, 256, smem, s, h, a->ldh, a->M, a->H, a->weight, a->bias, g, a->ldg, a->stats, R);
+  LnGeluGroup grp;
+  for (int i = 0; i < n; ++i) {
+    const bool bf = sizeof(TIn) == 2;
+    grp.it[i] = LnGeluItem{bf ? a[i].h_bf16 : static_cast<const void*>(a[i].h_f32), a[i].weight, a[i].bias,
+                           bf ? a[i].g_bf16 : static_cast<void*>(a[i].g_f32), a[i].stats};
+  }
+  const dim3 grid((a->M + R - 1) / R, n);
+  SEA_LAUNCH((ln_gelu_fwd_smem_kernel<TIn, TOut>), grid, 256, smem, s, grp, a->ldh, a->M, a->H, a->ldg, R);
   return static_cast<int>(cudaGetLastError());
 }
 
 template <typename TIn, typename TOut>
 static int launch_ln_gelu(const sea_ln_gelu_args* a, const TIn* h, TOut* g, cudaStream_t s) {
-  if (static_cast<size_t>(a->H) * sizeof(TIn) <= 64 * 1024 && (a->H % 64) == 0 &&
-      (reinterpret_cast<uintptr_t>(h) % 16) == 0 && ((a->ldh * sizeof(TIn)) % 16) == 0)
-    return launch_ln_gelu_smem(a, h, g, s);
   // rows per CTA: amortise the affine vectors, but keep >= ~2 CTAs per SM in flight
   int rows = a->M / (2 * 148);
   rows = rows < 1 ? 1 : (rows > 8 ? 8 : rows);
@@ -730,14 +758,42 @@ static int launch_ln_gelu(const sea_ln_gelu_args* a, const TIn* h, TOut* g, cuda
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int sea_ln_gelu_fwd(const sea_ln_gelu_args* a, sea_stream_t stream) {
-  if (!a || a->M <= 0 || a->H <= 0 || !a->weight || !a->bias) return SEA_ERR_INVALID;
-  if ((a->H % 8) || a->H > 16384 || (a->ldh % 8) || (a->ldg % 8)) return SEA_ERR_UNSUPPORTED;
+template <typename T>
+static bool ln_gelu_smem_ok(const sea_ln_gelu_args* a, const void* h) {
+  return static_cast<size_t>(a->H) * sizeof(T) <= 64 * 1024 && (a->H % 64) == 0 &&
+         (reinterpret_cast<uintptr_t>(h) % 16) == 0 && ((a->ldh * sizeof(T)) % 16) == 0;
+}
+
+extern "C" int sea_ln_gelu_fwd_group(int n, const sea_ln_gelu_args* a, sea_stream_t stream) {
+  if (!a || n < 1 || n > SEA_MAX_STREAMS) return SEA_ERR_INVALID;
+  bool all_bf = true, all_f32 = true, smem_ok = true;
+  for (int i = 0; i < n; ++i) {
+    const sea_ln_gelu_args* x = &a[i];
+    if (x->M <= 0 || x->H <= 0 || !x->weight || !x->bias) return SEA_ERR_INVALID;
+    if ((x->H % 8) || x->H > 16384 || (x->ldh % 8) || (x->ldg % 8)) return SEA_ERR_UNSUPPORTED;
+    if (x->M != a->M || x->H != a->H || x->ldh != a->ldh || x->ldg != a->ldg) return SEA_ERR_INVALID;
+    const bool bf = x->h_bf16 && x->g_bf16, f32 = x->h_f32 && x->g_f32;
+    if (!bf && !f32) return SEA_ERR_INVALID;
+    all_bf = all_bf && bf; all_f32 = all_f32 && !bf && f32;
+    smem_ok = smem_ok && (bf ? ln_gelu_smem_ok<__nv_bfloat16>(x, x->h_bf16) : ln_gelu_smem_ok<float>(x, x->h_f32));
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a->h_bf16 && a->g_bf16)
-    return launch_ln_gelu(a, static_cast<const __nv_bfloat16*>(a->h_bf16), static_cast<__nv_bfloat16*>(a->g_bf16), s);
-  if (a->h_f32 && a->g_f32) return launch_ln_gelu(a, a->h_f32, a->g_f32, s);
-  return SEA_ERR_INVALID;
+  if (smem_ok && all_bf) return launch_ln_gelu_smem<__nv_bfloat16, __nv_bfloat16>(n, a, s);
+  if (smem_ok && all_f32) return launch_ln_gelu_smem<float, float>(n, a, s);
+  for (int i = 0; i < n; ++i) {
+    const sea_ln_gelu_args* x = &a[i];
+    int rc;
+    if (x->h_bf16 && x->g_bf16)
+      rc = launch_ln_gelu(x, static_cast<const __nv_bfloat16*>(x->h_bf16), static_cast<__nv_bfloat16*>(x->g_bf16), s);
+    else
+      rc = launch_ln_gelu(x, x->h_f32, x->g_f32, s);
+    if (rc) return rc;
+  }
+  return SEA_OK;
+}
+
+extern "C" int sea_ln_gelu_fwd(const sea_ln_gelu_args* a, sea_stream_t stream) {
+  return sea_ln_gelu_fwd_group(1, a, stream);
 }
 
 extern "C" int sea_pack_operand(const sea_pack_args* a, sea_stream_t stream) {

@@ -54,6 +54,7 @@ struct alignas(64) GemmParams {
   int M, N, K;
   int groups, tiles_m, tiles_n;
   int chunk_kb;  // k-blocks per accumulation chunk (== num_kb when not chunked)
+  int b_is_static;  // B was written before the previous kernel in the stream started (weights)
 };
 
 template <int BN>
@@ -299,27 +300,45 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // prologue done (barriers, TMEM, descriptor prefetch): now wait for the producer kernel
+  // prologue done (barriers, TMEM, descriptor prefetch): let the next kernel start its own
   ptx::pdl_trigger();
-  ptx::pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // The B operand is a weight matrix: it does not depend on the kernel running before this one,
+      // so the first ring-full of weight tiles is requested BEFORE griddepcontrol.wait and streams
+      // in from HBM while the upstream kernel drains.  Only the A tiles (activations) wait.
+      const int pre = (p.b_is_static && blockIdx.x < total_tiles) ? min(num_kb, STAGES) : 0;
+      if (pre > 0) {
+        const int g = blockIdx.x / tiles_per_group;
+        const int tn = (blockIdx.x - g * tiles_per_group) / p.tiles_m;
+        for (int kb = 0; kb < pre; ++kb) {
+          ptx::mbar_expect_tx(&full[kb], C::STAGE_BYTES);
+          ptx::tma_load_2d(smem_b + kb * C::B_BYTES, &p.tma_b[g], &full[kb], kb * BK, tn * BN);
+        }
+      }
+      ptx::pdl_wait();
+      bool first = true;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int g = tile / tiles_per_group;
         const int r = tile - g * tiles_per_group;
         const int tm = r % p.tiles_m;
         const int tn = r / p.tiles_m;
         for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-          ptx::tma_load_2d(smem_a + stage * A_BYTES, &p.tma_a[g], &full[stage], kb * BK, tm * BM);
-          ptx::tma_load_2d(smem_b + stage * C::B_BYTES, &p.tma_b[g], &full[stage], kb * BK, tn * BN);
+          if (first && kb < pre) {
+            ptx::tma_load_2d(smem_a + stage * A_BYTES, &p.tma_a[g], &full[stage], kb * BK, tm * BM);
+          } else {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+            ptx::tma_load_2d(smem_a + stage * A_BYTES, &p.tma_a[g], &full[stage], kb * BK, tm * BM);
+            ptx::tma_load_2d(smem_b + stage * C::B_BYTES, &p.tma_b[g], &full[stage], kb * BK, tn * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        first = false;
       }
     }
   } else if (warp == 1) {
@@ -359,6 +378,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
     }
   } else {
     // --------------------------------------------------------------- epilogue
+    ptx::pdl_wait();               // residual / gelu_grad_of / out_f32 (chunked) come from upstream kernels
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
     const int half = (warp - 2) >> 2;  // two warps share a lane quarter and split the column chunks
     int acc = 0;
@@ -440,6 +460,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
 
 extern "C" void sea_gemm_force_tile_n(int bn) { sea::g_force_bn = bn; }
 
+
 extern "C" int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* probs, int M, int N,
                                 int K, sea_stream_t stream) {
   return sea_gemm_bf16_tn_chunked(num_problems, probs, M, N, K, 0, stream);
@@ -481,6 +502,8 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   p.tiles_n = (N + bn - 1) / bn;
   p.chunk_kb = (k_chunk > 0 && k_chunk < K) ? k_chunk / BK : (K + BK - 1) / BK;
   const bool chunked = p.chunk_kb < (K + BK - 1) / BK;
+  p.b_is_static = 1;
+  for (int g = 0; g < num_problems; ++g) p.b_is_static &= probs[g].b_is_static != 0;
   for (int g = 0; g < num_problems; ++g) {
     const sea_gemm_problem& q = probs[g];
     const sea_gemm_epilogue& e = q.epi;

@@ -20,6 +20,9 @@ TensorMapEncodeFn g_encode = nullptr;
 
 bool g_pdl = true;
 bool pdl_enabled() { return g_pdl; }
+namespace { thread_local bool g_fence_next = false; }
+void pdl_fence_next() { g_fence_next = true; }
+bool pdl_take_fence() { const bool f = g_fence_next; g_fence_next = false; return f; }
 int num_sms() { return g_sms; }
 TensorMapEncodeFn tensor_map_encoder() { return g_encode; }
 

@@ -26,6 +26,11 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
 // Kernel launch with the programmatic-stream-serialization attribute (PDL).  All kernels of this
 // library call griddepcontrol.wait before touching global memory, so they may be launched early.
 bool pdl_enabled();
+// The next SEA_LAUNCH on this thread is issued WITHOUT the PDL attribute (ordinary stream order):
+// nothing launched after it can overlap anything launched before it.  Executors call this on entry
+// so that weights packed by an earlier call are "static" for every kernel of this call.
+void pdl_fence_next();
+bool pdl_take_fence();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                               Args&&... args) {
@@ -35,7 +40,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_enabled() && !pdl_take_fence()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #define SEA_LAUNCH(kernel, grid, block, smem, stream, ...) \

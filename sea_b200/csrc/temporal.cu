@@ -369,6 +369,7 @@ int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, c
       p.a = in[g].a; p.lda = in[g].lda;
     }
     p.b = W[g]->w; p.ldb = W[g]->ldw;
+    p.b_is_static = 1;  // packed weights: written before this call's launch fence
     sea_gemm_epilogue& e = p.epi;
     e.bias = o.bias;
     e.residual = o.residual; e.ld_residual = o.ld_res;
@@ -401,10 +402,14 @@ int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, c
   return sea_gemm_bf16_tn(n, probs, Mrows, N, K, reinterpret_cast<sea_stream_t>(c.s));
 }
 
-int norm_op(Ctx& c, int kind, const sea_norm_params& np, const float* cond, const float* x,
-            long long ldx, int dim, void* y_act, float* y_f32, long long ldy_f32, float* stats,
-            const sea_block_params* tipi, const float* tipi_g, float* x_out) {
-  sea_norm_args a{};
+// One row-norm of the model as launch arguments (+ its algorithmic bytes for the profiler).
+struct NormCall { sea_norm_args a; double bytes; };
+
+NormCall norm_call(Ctx& c, int kind, const sea_norm_params& np, const float* cond, const float* x,
+                   long long ldx, int dim, void* y_act, float* y_f32, long long ldy_f32, float* stats,
+                   const sea_block_params* tipi, const float* tipi_g, float* x_out) {
+  NormCall nc{};
+  sea_norm_args& a = nc.a;
   a.x = x; a.ldx = ldx; a.M = c.M; a.d = dim; a.kind = kind;
   a.weight = np.weight.p;
   a.bias = kind == SEA_NORM_ADALN ? np.bias.p : nullptr;
@@ -421,16 +426,24 @@ int norm_op(Ctx& c, int kind, const sea_norm_params& np, const float* cond, cons
   else if (c.fp32) { a.y_f32 = static_cast<float*>(y_act); a.ldy_f32 = dim; }
   else { a.y_bf16 = y_act; a.ldy_bf16 = dim; }
   a.stats = stats;
-  ++g_launches;
   const double esz = c.fp32 ? 4.0 : 2.0;
-  ProfScope prof(c.s, SEA_PROF_ELEMWISE,
-                 static_cast<double>(c.M) * dim * (4.0 + (y_f32 ? 4.0 : esz) + (tipi ? 4.0 : 0.0) +
-                                                   (kind == SEA_NORM_ADALN ? 8.0 : 0.0)));
-  return sea_norm_fwd(&a, reinterpret_cast<sea_stream_t>(c.s));
+  nc.bytes = static_cast<double>(c.M) * dim * (4.0 + (y_f32 ? 4.0 : esz) + (tipi ? 4.0 : 0.0) +
+                                               (kind == SEA_NORM_ADALN ? 8.0 : 0.0));
+  return nc;
 }
 
-int attention_op(Ctx& c, const void* q, long long ldq, const void* k, const void* v, long long ldkv,
-                 void* o, long long ldo, float* lse, int head_dim) {
+// The V field streams' norms are independent: one launch for all of them.
+int norm_group(Ctx& c, int n, const NormCall* calls) {
+  sea_norm_args args[SEA_MAX_STREAMS];
+  double bytes = 0;
+  for (int i = 0; i < n; ++i) { args[i] = calls[i].a; bytes += calls[i].bytes; }
+  ++g_launches;
+  ProfScope prof(c.s, SEA_PROF_ELEMWISE, bytes);
+  return sea_norm_fwd_group(n, args, reinterpret_cast<sea_stream_t>(c.s));
+}
+
+sea_attn_args attn_call(Ctx& c, const void* q, long long ldq, const void* k, const void* v, long long ldkv,
+                        void* o, long long ldo, float* lse, int head_dim) {
   sea_attn_args a{};
   a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldkv; a.ldv = ldkv;
   a.o = o; a.ldo = ldo; a.lse = lse;
@@ -438,10 +451,14 @@ int attention_op(Ctx& c, const void* q, long long ldq, const void* k, const void
   a.src_len = c.d->src_len;
   a.scale = 1.0f / sqrtf(static_cast<float>(head_dim));
   a.prec = c.fp32 ? SEA_PREC_FP32 : SEA_PREC_BF16;
+  return a;
+}
+
+int attention_group(Ctx& c, int n, const sea_attn_args* a) {
   ++g_launches;
   ProfScope prof(c.s, SEA_PROF_ATTN,
-                 2.0 * c.B * c.d->n_heads * static_cast<double>(c.T) * c.T * head_dim);
-  return sea_attention_fwd(&a, reinterpret_cast<sea_stream_t>(c.s));
+                 2.0 * n * c.B * c.d->n_heads * static_cast<double>(c.T) * c.T * a[0].head_dim);
+  return sea_attention_fwd_group(n, a, reinterpret_cast<sea_stream_t>(c.s));
 }
 
 static int adaln_cond(Ctx& c, int n, const sea_norm_params* const* np, void* const* hid,
@@ -499,6 +516,7 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
   if (workspace_bytes < sea_temporal_workspace_bytes(d, B, T, training)) return SEA_ERR_WORKSPACE;
   SEA_TRY(ensure_init());
   g_launches = 0;
+  pdl_fence_next();
 
   Arena car{const_cast<char*>(static_cast<const char*>(cache))};
   CacheLayout cl;
@@ -596,9 +614,12 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
     const PackedLinear* W[SEA_MAX_STREAMS];
 
     // (1) x_i += SelfAttn_i(Norm_{i,0}(x_i))          models/temporal.py:135-136
+    NormCall ncall[SEA_MAX_STREAMS];
+    sea_attn_args acall[SEA_MAX_STREAMS];
     for (int i = 0; i < V; ++i)
-      SEA_TRY(norm_op(c, kind, bp.s[i].ln0, lt.s[i].cond0, xin[i], ldxin, E, lt.s[i].n0, nullptr, 0,
-                      lt.s[i].st0, nullptr, nullptr, nullptr));
+      ncall[i] = norm_call(c, kind, bp.s[i].ln0, lt.s[i].cond0, xin[i], ldxin, E, lt.s[i].n0, nullptr, 0,
+                           lt.s[i].st0, nullptr, nullptr, nullptr);
+    SEA_TRY(norm_group(c, V, ncall));
     for (int i = 0; i < V; ++i) {
       in[i] = LinIn{lt.s[i].n0, E, 0};
       W[i] = &bc.s[i].qkv;
@@ -610,9 +631,10 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
     SEA_TRY(linear_group(c, V, in, W, out, M));
     for (int i = 0; i < V; ++i) {
       char* base = static_cast<char*>(lt.s[i].qkv);
-      SEA_TRY(attention_op(c, base, 3 * E, base + esz * E, base + esz * 2 * E, 3 * E, lt.s[i].ao, E,
-                           lt.s[i].lse, hd));
+      acall[i] = attn_call(c, base, 3 * E, base + esz * E, base + esz * 2 * E, 3 * E, lt.s[i].ao, E,
+                           lt.s[i].lse, hd);
     }
+    SEA_TRY(attention_group(c, V, acall));
     for (int i = 0; i < V; ++i) {
       in[i] = LinIn{lt.s[i].ao, E, 0};
       W[i] = &bc.s[i].sproj;
@@ -633,31 +655,68 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
     }
     SEA_TRY(linear_group(c, V, in, W, out, M));
     for (int i = 0; i < V; ++i)
-      SEA_TRY(norm_op(c, kind, bp.s[i].ln_cross, lt.s[i].condc, lt.s[i].dpre, Dd, Dd, lt.s[i].npre,
-                      nullptr, 0, lt.s[i].stc_pre, nullptr, nullptr, nullptr));
+      ncall[i] = norm_call(c, kind, bp.s[i].ln_cross, lt.s[i].condc, lt.s[i].dpre, Dd, Dd, lt.s[i].npre,
+                           nullptr, 0, lt.s[i].stc_pre, nullptr, nullptr, nullptr);
+    SEA_TRY(norm_group(c, V, ncall));
+    // Every q projection, and the k / v projections whose source stream has not been exchanged yet
+    // (j > i), read only the pre-exchange ln_cross outputs: same shape [M, Dd] x [Dd, Dd], so they
+    // go out together, up to four per launch (models/base_blocks.py:271-276).
+    {
+      LinIn gin[SEA_MAX_STREAMS]; LinOut gout[SEA_MAX_STREAMS];
+      PackedLinear gw[SEA_MAX_STREAMS]; const PackedLinear* gW[SEA_MAX_STREAMS];
+      int ng = 0;
+      auto flush = [&]() -> int {
+        if (ng == 0) return SEA_OK;
+        for (int g = 0; g < ng; ++g) gW[g] = &gw[g];
+        const int rc = linear_group(c, ng, gin, gW, gout, M);
+        ng = 0;
+        return rc;
+      };
+      auto push = [&](const void* a_src, const PackedLinear& w, int row_off, const float* bias, void* dst,
+                      long long ld_dst, bool rope) -> int {
+        gin[ng] = LinIn{a_src, Dd, 0};
+        gw[ng] = w;
+        gw[ng].N = Dd;
+        gw[ng].w = w.w + static_cast<long long>(row_off) * w.ldw;
+        gout[ng] = LinOut{};
+        gout[ng].bias = bias;
+        gout[ng].post = dst; gout[ng].ld_post = ld_dst;
+        if (rope) { gout[ng].rope_cols = Dd; gout[ng].head_dim = hdc; gout[ng].rope_table = d->rope_cross; }
+        if (++ng == SEA_MAX_STREAMS) return flush();
+        return SEA_OK;
+      };
+      for (int i = 0; i < V; ++i) {
+        StreamTape& s = lt.s[i];
+        for (int j = 0; j < V; ++j) {
+          if (j == i) continue;
+          SEA_TRY(push(s.npre, bc.s[i].cq[j], 0, bp.s[i].cross_attn[j].q_b.p, s.q[j], Dd, true));
+          if (j > i) {
+            char* kvb = static_cast<char*>(s.kv[j]);
+            SEA_TRY(push(lt.s[j].npre, bc.s[i].ckv[j], 0, bc.s[i].ckv_bias[j], kvb, 2 * Dd, true));
+            SEA_TRY(push(lt.s[j].npre, bc.s[i].ckv[j], Dd, bc.s[i].ckv_bias[j] + Dd, kvb + esz * Dd, 2 * Dd, false));
+          }
+        }
+      }
+      SEA_TRY(flush());
+    }
     for (int i = 0; i < V; ++i) {
       StreamTape& s = lt.s[i];
       const float* xcur = s.x1;
       for (int j = 0; j < V; ++j) {
         if (j == i) continue;
-        const void* src = (j < i) ? lt.s[j].npost : lt.s[j].npre;
-        // q from stream i, (k,v) from stream j        models/base_blocks.py:271-276
-        in[0] = LinIn{s.npre, Dd, 0};
-        W[0] = &bc.s[i].cq[j];
-        out[0] = LinOut{};
-        out[0].bias = bp.s[i].cross_attn[j].q_b.p;
-        out[0].post = s.q[j]; out[0].ld_post = Dd;
-        out[0].rope_cols = Dd; out[0].head_dim = hdc; out[0].rope_table = d->rope_cross;
-        SEA_TRY(linear_group(c, 1, in, W, out, M));
-        in[0] = LinIn{src, Dd, 0};
-        W[0] = &bc.s[i].ckv[j];
-        out[0] = LinOut{};
-        out[0].bias = bc.s[i].ckv_bias[j];
-        out[0].post = s.kv[j]; out[0].ld_post = 2 * Dd;
-        out[0].rope_cols = Dd; out[0].head_dim = hdc; out[0].rope_table = d->rope_cross;
-        SEA_TRY(linear_group(c, 1, in, W, out, M));
+        if (j < i) {
+          // (k,v) from the already exchanged stream j     models/temporal.py:189-191
+          in[0] = LinIn{lt.s[j].npost, Dd, 0};
+          W[0] = &bc.s[i].ckv[j];
+          out[0] = LinOut{};
+          out[0].bias = bc.s[i].ckv_bias[j];
+          out[0].post = s.kv[j]; out[0].ld_post = 2 * Dd;
+          out[0].rope_cols = Dd; out[0].head_dim = hdc; out[0].rope_table = d->rope_cross;
+          SEA_TRY(linear_group(c, 1, in, W, out, M));
+        }
         char* kvb = static_cast<char*>(s.kv[j]);
-        SEA_TRY(attention_op(c, s.q[j], Dd, kvb, kvb + esz * Dd, 2 * Dd, s.a[j], Dd, s.lse_c[j], hdc));
+        acall[0] = attn_call(c, s.q[j], Dd, kvb, kvb + esz * Dd, 2 * Dd, s.a[j], Dd, s.lse_c[j], hdc);
+        SEA_TRY(attention_group(c, 1, acall));
         // cross_up(GELU(projection(attn)))             models/base_blocks.py:293, temporal.py:185
         in[0] = LinIn{s.a[j], Dd, 0};
         W[0] = &bc.s[i].cproj[j];
@@ -685,15 +744,17 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
         out[0].bias = bp.s[i].down_b.p;
         out[0].f32 = s.dpost; out[0].ld_f32 = Dd;
         SEA_TRY(linear_group(c, 1, in, W, out, M));
-        SEA_TRY(norm_op(c, kind, bp.s[i].ln_cross, s.condc, s.dpost, Dd, Dd, s.npost, nullptr, 0,
-                        s.stc_post, nullptr, nullptr, nullptr));
+        ncall[0] = norm_call(c, kind, bp.s[i].ln_cross, s.condc, s.dpost, Dd, Dd, s.npost, nullptr, 0,
+                             s.stc_post, nullptr, nullptr, nullptr);
+        SEA_TRY(norm_group(c, 1, ncall));
       }
     }
 
     // (3) x_i += TIPI(ib) fused with Norm_{i,2}; (4) MLP; (5) proj    models/temporal.py:140-146
     for (int i = 0; i < V; ++i)
-      SEA_TRY(norm_op(c, kind, bp.s[i].ln2, lt.s[i].cond2, lt.s[i].xp, E, E, lt.s[i].n2, nullptr, 0,
-                      lt.s[i].st2, &bp, inv ? lt.tipi_rows : lt.tipi_g, lt.s[i].x2));
+      ncall[i] = norm_call(c, kind, bp.s[i].ln2, lt.s[i].cond2, lt.s[i].xp, E, E, lt.s[i].n2, nullptr, 0,
+                           lt.s[i].st2, &bp, inv ? lt.tipi_rows : lt.tipi_g, lt.s[i].x2);
+    SEA_TRY(norm_group(c, V, ncall));
     for (int i = 0; i < V; ++i) {
       in[i] = LinIn{lt.s[i].n2, E, 0};
       W[i] = &bc.s[i].mlp0;
@@ -702,16 +763,18 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
       out[i].post = lt.s[i].h; out[i].ld_post = H;
     }
     SEA_TRY(linear_group(c, V, in, W, out, M));
-    for (int i = 0; i < V; ++i) {
-      sea_ln_gelu_args a{};
-      if (c.fp32) { a.h_f32 = static_cast<const float*>(lt.s[i].h); a.g_f32 = static_cast<float*>(lt.s[i].gh); }
-      else { a.h_bf16 = lt.s[i].h; a.g_bf16 = lt.s[i].gh; }
-      a.ldh = H; a.ldg = H; a.M = M; a.H = H;
-      a.weight = bp.s[i].mlp_ln_w.p; a.bias = bp.s[i].mlp_ln_b.p; a.stats = lt.s[i].stH;
-      {
-        ProfScope prof(c.s, SEA_PROF_ELEMWISE, 2.0 * esz * M * static_cast<double>(H));
-        SEA_TRY(sea_ln_gelu_fwd(&a, st));
+    {
+      sea_ln_gelu_args la[SEA_MAX_STREAMS];
+      for (int i = 0; i < V; ++i) {
+        sea_ln_gelu_args& a = la[i];
+        a = sea_ln_gelu_args{};
+        if (c.fp32) { a.h_f32 = static_cast<const float*>(lt.s[i].h); a.g_f32 = static_cast<float*>(lt.s[i].gh); }
+        else { a.h_bf16 = lt.s[i].h; a.g_bf16 = lt.s[i].gh; }
+        a.ldh = H; a.ldg = H; a.M = M; a.H = H;
+        a.weight = bp.s[i].mlp_ln_w.p; a.bias = bp.s[i].mlp_ln_b.p; a.stats = lt.s[i].stH;
       }
+      ProfScope prof(c.s, SEA_PROF_ELEMWISE, 2.0 * esz * M * static_cast<double>(H) * V);
+      SEA_TRY(sea_ln_gelu_fwd_group(V, la, st));
       ++g_launches;
     }
     for (int i = 0; i < V; ++i) {
@@ -736,9 +799,13 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
   }
 
   // ---- final norm per stream, written straight into the strided [B,T,V,E] output ----
-  for (int i = 0; i < V; ++i)
-    SEA_TRY(norm_op(c, kind, d->final_ln[i], tape.condF[i], xin[i], ldxin, E, nullptr,
-                    y + static_cast<long long>(i) * E, static_cast<long long>(V) * E, tape.stF[i],
-                    nullptr, nullptr, nullptr));
+  {
+    NormCall ncall[SEA_MAX_STREAMS];
+    for (int i = 0; i < V; ++i)
+      ncall[i] = norm_call(c, kind, d->final_ln[i], tape.condF[i], xin[i], ldxin, E, nullptr,
+                           y + static_cast<long long>(i) * E, static_cast<long long>(V) * E, tape.stF[i],
+                           nullptr, nullptr, nullptr);
+    SEA_TRY(norm_group(c, V, ncall));
+  }
   return SEA_OK;
 }

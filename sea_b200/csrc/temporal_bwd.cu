@@ -119,6 +119,7 @@ int linear_bwd(BCtx& b, int n, LinB* L) {
       p = sea_gemm_problem{};
       p.a = L[g].dy; p.lda = L[g].lddy;
       p.b = L[g].W->wT; p.ldb = L[g].W->ldwT;
+      p.b_is_static = 1;  // transposed weight copy from the cache: older than this call's launch fence
       p.epi.residual = L[g].da_res; p.epi.ld_residual = L[g].ld_res;
       p.epi.gelu_grad_of = L[g].gelu_of; p.epi.ld_gelu = L[g].ld_gelu;
       p.epi.out_f32 = L[g].da_f32; p.epi.ld_out_f32 = L[g].ld_da;
@@ -240,6 +241,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
   if (workspace_bytes < sea_temporal_workspace_bytes(d, B, T, 1)) return SEA_ERR_WORKSPACE;
   SEA_TRY(ensure_init());
   g_launches = 0;
+  pdl_fence_next();
 
   Arena car{const_cast<char*>(static_cast<const char*>(cache))};
   CacheLayout cl;

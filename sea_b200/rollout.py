@@ -23,9 +23,93 @@ def _engine_of(model):
     return eng
 
 
+class RolloutPlan:
+    """The same loop with every step pre-recorded as a CUDA graph.
+
+    Step t (prefix length t) of the reference loop is: forward over the whole prefix, append the
+    last output.  Both are recorded once per (B, steps): graph t = [gather prefix seq[:, :t] into
+    the contiguous forward input] -> [the ~30 kernels of sea_temporal_forward at T = t] ->
+    [scatter y[:, -1] into seq[:, t]].  Replaying costs one cudaGraphLaunch per step instead of
+    ~30 kernel launches + tensor-map encodes + torch.cat on the host, which is what bounds the short
+    prefixes.  Arithmetic, kernels and per-step work are exactly those of the eager loop (the full
+    prefix is still recomputed every step); requires a time-invariant ib (checked by the caller)."""
+
+    def __init__(self, model, B: int, steps: int, device):
+        eng = _engine_of(model)
+        if eng is None:
+            raise RuntimeError("RolloutPlan needs a sea_b200 temporal engine (mirror model or accelerate())")
+        self.eng, self.B, self.steps = eng, B, steps
+        eng._ensure(False)
+        h = eng._h
+        V, E, nib = h["V"], h["E"], h["ib_num"]
+        self.V, self.E = V, E
+        f32 = dict(dtype=torch.float32, device=device)
+        self.seq = torch.zeros(B, steps + 1, V, E, **f32)
+        self.xin = torch.empty(B * steps * V * E, **f32)
+        self.y = torch.empty(B * steps * V * E, **f32)
+        self.ib1 = torch.zeros(B, 1, nib, **f32)      # step 1 reads ib as [B,1,nib]
+        self.ib2 = torch.zeros(B, 2, nib, **f32)      # step 2 (first time-invariant call) as [B,2,nib]
+        nws = lib.sea_temporal_workspace_bytes(C.byref(eng._desc), B, steps, 0)
+        self.ws = torch.empty(nws, dtype=torch.uint8, device=device)
+        ncc = lib.sea_temporal_cond_cache_bytes(C.byref(eng._desc), B)
+        self.cond = torch.empty(ncc, dtype=torch.uint8, device=device)
+        self.graphs, self.launches = [], []
+        self.key = (eng._cache.data_ptr(), eng._cache_key[:2])
+        self._record()
+
+    def _step(self, t: int) -> int:
+        B, V, E = self.B, self.V, self.E
+        x = self.xin[: B * t * V * E].view(B, t, V, E)
+        y = self.y[: B * t * V * E].view(B, t, V, E)
+        x.copy_(self.seq[:, :t])
+        ib = self.ib1 if t == 1 else self.ib2   # only read while the condition cache is not valid (t <= 2)
+        n = self.eng.forward_into(x, ib, y, self.ws, time_invariant=True, cond_buf=self.cond, cond_valid=t > 2)
+        self.seq[:, t].copy_(y[:, t - 1])
+        return n
+
+    def _record(self):
+        # one eager pass first: every kernel variant sets its launch attributes outside a capture
+        for t in range(1, self.steps + 1):
+            self._step(t)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        pool = None
+        for t in range(1, self.steps + 1):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode="relaxed"):
+                n = self._step(t)
+            pool = g.pool()
+            self.graphs.append(g)
+            self.launches.append(n + 2)
+        torch.cuda.current_stream().wait_stream(side)
+
+    def valid_for(self, eng) -> bool:
+        return eng._cache is not None and self.key == (eng._cache.data_ptr(), eng._cache_key[:2])
+
+    @torch.no_grad()
+    def run(self, x0: torch.Tensor, ib: torch.Tensor) -> torch.Tensor:
+        """x0 [B,1,V,E], ib [B,>=1,ib_num] (time-invariant) -> view [B,steps,V,E] of the plan's own
+        sequence buffer (overwritten by the next run)."""
+        self.eng._ensure(False)
+        self.seq[:, 0].copy_(x0[:, 0])
+        self.ib1.copy_(ib[:, :1])
+        self.ib2.copy_(ib[:, :1].expand(-1, 2, -1))
+        for g in self.graphs:
+            g.replay()
+        n = sum(self.launches)
+        self.eng.last_launches = self.launches[-1]
+        self.eng.total_launches += n
+        return self.seq[:, 1:]
+
+
+def _profiling() -> bool:
+    return bool(getattr(profile, "active", False))
+
+
 @torch.no_grad()
 def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
-            ib_time_invariant: bool | None = None) -> torch.Tensor:
+            ib_time_invariant: bool | None = None, graphs: bool = True, _view_ok: bool = False) -> torch.Tensor:
     """x0 [B,1,V,E], ib [B,>=steps,ib_num] -> predicted latents [B,steps,V,E].
 
     ``ib`` is the time-invariant physical parameter of a trajectory in the reference's data
@@ -36,6 +120,17 @@ def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
     eng = _engine_of(model)
     if ib_time_invariant is None:
         ib_time_invariant = bool((ib[:, :steps] == ib[:, :1]).all().item())
+    if graphs and eng is not None and ib_time_invariant and x0.is_cuda and not _profiling():
+        eng._ensure(False)
+        plans = eng.__dict__.setdefault("_rollout_plans", {})
+        key = (x0.shape[0], steps, x0.device.index)
+        plan = plans.get(key)
+        if plan is None or not plan.valid_for(eng):
+            if len(plans) >= 4:
+                plans.clear()
+            plan = plans[key] = RolloutPlan(model, x0.shape[0], steps, x0.device)
+        out = plan.run(x0, ib)
+        return out if _view_ok else out.clone()   # the plan's buffer is overwritten by the next run
     prev = None
     if eng is not None:
         prev, eng.ib_time_invariant = eng.ib_time_invariant, ib_time_invariant
@@ -61,7 +156,7 @@ def rollout_from_host(model, x0_host: torch.Tensor, ib_host: torch.Tensor, steps
     """End-to-end variant: pinned host inputs -> device, rollout, predicted latents -> pinned host."""
     x0 = x0_host.to(device, non_blocking=True)
     ib = ib_host.to(device, non_blocking=True)
-    pred = rollout(model, x0, ib, steps)
+    pred = rollout(model, x0, ib, steps, _view_ok=True)
     out_host.copy_(pred, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return out_host
@@ -71,11 +166,15 @@ class profile:
     """Context manager around lib.sea_profile_begin/end; ``.summary`` holds per-category totals."""
     CATS = ("gemm", "attention", "elementwise")
 
+    active = False
+
     def __enter__(self):
         lib.sea_profile_begin()
+        profile.active = True
         return self
 
     def __exit__(self, *exc):
+        profile.active = False
         s = ProfileSummary()
         check(lib.sea_profile_end(C.byref(s)), "profile_end")
         self.summary = {c: dict(ms=s.ms[i], work=s.work[i], launches=int(s.launches[i]))

@@ -486,6 +486,29 @@ class TemporalEngine:
         self.total_launches += self.last_launches
         return y
 
+    @torch.no_grad()
+    def forward_into(self, x: torch.Tensor, ib: torch.Tensor, y: torch.Tensor, ws: torch.Tensor, *,
+                     time_invariant: bool, cond_buf: Optional[torch.Tensor] = None,
+                     cond_valid: bool = False) -> int:
+        """Allocation-free inference forward (CUDA-graph capturable): contiguous fp32 x [B,T,V,E],
+        ib [B,T,ib_num] -> y, activations in the caller's workspace ``ws``; the caller has already
+        run ``_ensure(False)``.  Returns the number of kernels enqueued."""
+        B, T, V, E = x.shape
+        d = self._desc
+        d.ib_time_invariant = int(time_invariant)
+        if cond_buf is not None and time_invariant and T > 1:
+            d.cond_cache, d.cond_cache_bytes, d.cond_cache_valid = cond_buf.data_ptr(), cond_buf.numel(), int(cond_valid)
+        else:
+            d.cond_cache, d.cond_cache_bytes, d.cond_cache_valid = None, 0, 0
+        with torch.cuda.device(x.device):
+            check(lib.sea_temporal_forward(C.byref(d), C.c_void_p(self._cache.data_ptr()),
+                                           C.c_void_p(x.data_ptr()), C.c_void_p(ib.data_ptr()),
+                                           C.c_void_p(y.data_ptr()), B, T, C.c_void_p(ws.data_ptr()),
+                                           C.c_size_t(ws.numel()), 0,
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                  "temporal_forward")
+        return int(lib.sea_last_launch_count())
+
     def __call__(self, x, ib):
         needs_grad = torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in self.module.parameters()))

@@ -107,3 +107,40 @@ def test_time_invariant_condition_path_is_equivalent(cuda, tag, ln):
     with torch.no_grad():
         ref_var = so.rollout(x[:, :1].cpu(), ib[:, :steps].cpu(), steps, sd, **cfg)
     assert rel_l2(r_var.cpu(), ref_var) < TOL["bf16"]
+
+
+@pytest.mark.parametrize("tag,ln", [("small_adaln", "adaln"), ("small_ln", "ln")])
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_graphed_rollout_equals_eager_loop(cuda, tag, ln, prec):
+    """RolloutPlan (one CUDA graph per prefix length) replays exactly the kernels of the eager loop
+    through module.forward: bit-identical results, also on a second run with other trajectories and
+    after the weights changed (the plan must re-pack, not reuse stale conditions)."""
+    from sea_b200.rollout import rollout
+    from sea_b200.temporal import TemporalModel
+    g, sd, cfg, x, ib, _, steps = temporal_case(tag, ln)
+    E, nh, scale, V, B, T, _ = [int(v) for v in g["meta"]]
+    m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln,
+                      precision=prec)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(cuda).eval()
+    x, ib = x.to(cuda), ib.to(cuda)
+    steps = 12
+    ibc = ib[:, :1].expand(B, steps, 1).contiguous()
+    for trial in range(3):
+        x0 = x[:, trial:trial + 1].contiguous()
+        ibt = (ibc + 0.1 * trial).contiguous()
+        if trial == 2:
+            with torch.no_grad():
+                for p in m.parameters():
+                    p.mul_(1.01)
+        r_graph = rollout(m, x0, ibt, steps, graphs=True)
+        r_eager = rollout(m, x0, ibt, steps, graphs=False)
+        assert torch.equal(r_graph, r_eager), (trial, rel_l2(r_graph, r_eager))
+    assert len(m.engine()._rollout_plans) == 1
+    with torch.no_grad():
+        ref = so.rollout(x[:, 2:3].cpu(), (ibc + 0.2).cpu(), steps,
+                         {k: v * 1.01 if v.dtype.is_floating_point and k in dict(m.named_parameters()) else v
+                          for k, v in sd.items()}, **cfg)
+    err = rel_l2(r_graph.cpu(), ref)
+    print(f"\n[graphed rollout] {tag} {prec}: vs oracle {err:.3e}")
+    assert err < TOL[prec]
