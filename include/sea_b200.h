@@ -111,6 +111,8 @@ int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem* host_prob
                              int K, int k_chunk, sea_stream_t stream);
 /* Test / tuning hook: force the N-tile (64, 128, 256) of the next launches; 0 = heuristic. */
 void sea_gemm_force_tile_n(int bn);
+/* Tuning probe (results are garbage): 1 = skip the TMA traffic, 2 = skip the MMAs; 0 = normal. */
+void sea_gemm_debug_probe(int mode);
 
 /* ------------------------------------------------------------------ K4: row norms -----------
  * LayerNorm (custom, weight only: models/base_blocks.py:80-88) or AdaLN (:343-350) over the last

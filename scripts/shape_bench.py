@@ -184,6 +184,95 @@ def run_rollout():
     print(f"sum graph device {sum(devg)/1e3:.2f} ms")
 
 
+
+
+def run_floor():
+    """Per-node device time of CUDA-graph chains of identical small kernels (latency floor)."""
+    def chain(fn, n=48, reps=20):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
+            for _ in range(n):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps / n * 1e3
+
+    x = torch.randn(160, 1024, device=dev)
+    w = torch.ones(1024, device=dev)
+    y = torch.empty(160, 1024, device=dev)
+    print(f"torch add_ [160x1024]           : {chain(lambda: y.add_(1.0)):6.2f} us/node")
+    print(f"norm_fwd LN [160x1024]          : {chain(lambda: ops.norm_fwd(x, w, kind=0)):6.2f} us/node")
+    g8 = torch.randn(32, 8, device=dev)
+    for (M, N, K) in ((160, 512, 512), (160, 1024, 1024), (160, 3072, 1024), (160, 8192, 1024), (160, 1024, 8192),
+                      (1600, 512, 512), (1600, 1024, 1024)):
+        a = torch.randn(M, K, device=dev).bfloat16()
+        b = (torch.randn(N, K, device=dev) * 0.02).bfloat16()
+        o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for st in (False, True):
+            pr = [ops.gemm_problem(a, b, out_bf16=o, b_is_static=st)]
+            print(f"gemm M={M} N={N} K={K} static={int(st)}: {chain(lambda: ops.gemm_bf16_tn(pr, M, N, K)):6.2f} us/node")
+    for (B, T, nh, hd) in ((32, 5, 8, 128), (32, 5, 8, 64), (32, 100, 8, 128)):
+        qkv = torch.randn(B * T, 3 * nh * hd, device=dev).bfloat16()
+        q, k, v = qkv[:, : nh * hd], qkv[:, nh * hd: 2 * nh * hd], qkv[:, 2 * nh * hd:]
+        print(f"attn B={B} T={T} hd={hd}: {chain(lambda: ops.attention_fwd(q, k, v, nh, B=B)):6.2f} us/node")
+    for pdl in (0, 1):
+        lib.sea_set_pdl(pdl)
+        a = torch.randn(160, 512, device=dev).bfloat16()
+        b = (torch.randn(512, 512, device=dev) * 0.02).bfloat16()
+        o = torch.empty(160, 512, device=dev, dtype=torch.bfloat16)
+        pr = [ops.gemm_problem(a, b, out_bf16=o, b_is_static=True)]
+        print(f"pdl={pdl} gemm 160x512x512 chain: {chain(lambda: ops.gemm_bf16_tn(pr, 160, 512, 512)):6.2f} us/node")
+    lib.sea_set_pdl(1)
+
+
+
+def run_kblock():
+    """Per-k-block time of one CTA column: graph chain of a K-heavy GEMM at forced tile widths."""
+    import itertools
+    def chain(fn, n=16, reps=10):
+        fn(); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph(); side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
+            for _ in range(n):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps / n * 1e3
+    for (M, N, K) in ((128, 256, 8192), (128, 8192, 8192)):
+        a = torch.randn(M, K, device=dev).bfloat16()
+        b = (torch.randn(N, K, device=dev) * 0.02).bfloat16()
+        o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        pr = [ops.gemm_problem(a, b, out_bf16=o, b_is_static=True)]
+        for bn, dbg in itertools.product((64, 128, 256), (0, 1, 2)):
+            if bn > N:
+                continue
+            lib.sea_gemm_force_tile_n(bn)
+            lib.sea_gemm_debug_probe(dbg)
+            us = chain(lambda: ops.gemm_bf16_tn(pr, M, N, K))
+            lib.sea_gemm_force_tile_n(0)
+            lib.sea_gemm_debug_probe(0)
+            ctas = ((M + 127) // 128) * ((N + bn - 1) // bn)
+            kb = K // 64
+            print(f"M={M} N={N} K={K} bn={bn} probe={dbg}: {us:7.2f} us, {ctas} CTAs, {us/kb*1e3:6.1f} ns/k-block, "
+                  f"{(128+bn)*128/ (us/kb*1e3):6.1f} GB/s per CTA", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gemm"
-    {"gemm": run_gemm, "attn": run_attn, "train": run_train, "rollout": run_rollout}[what]()
+    {"gemm": run_gemm, "attn": run_attn, "train": run_train, "rollout": run_rollout, "floor": run_floor, "kblock": run_kblock}[what]()

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
   float* lse_s = reinterpret_cast<float*>(bars + 32);  // [2][BS]  (MODE 1: per-column lse*log2e)
   float* dl_s = lse_s + 2 * BS;                        // [2][BS]  (MODE 1: per-column delta)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform role index + elect.sync regions (see gemm.cu): no waterfall loops around UTMALDG / UTCHMMA
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
   int tile, half = 0;
   if (MODE == 0) {
@@ -124,17 +125,20 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(a_full, 2 * C::STAT_BYTES);
 #pragma unroll
       for (int a = 0; a < C::ATOMS; ++a) {
         ptx::tma_load_3d(sA1 + a * (BR * 128), &p.ta1, a_full, h * HD + a * 64, r0, b);
         ptx::tma_load_3d(sA2 + a * (BR * 128), &p.ta2, a_full, h * HD + a * 64, r0, b);
       }
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(&b_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      ptx::mbar_wait(&b_empty[s], ph ^ 1);
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&b_full[s], 2 * C::STR_BYTES);
         const int row = (it0 + it) * BS;
 #pragma unroll
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
           ptx::tma_load_3d(sB2 + s * C::STR_BYTES + a * (BS * 128), &p.tb2, &b_full[s], h * HD + a * 64, row, b);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------- MMA issuer
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       ptx::tc_fence_after();
       const uint32_t a1 = ptx::smem_u32(sA1), a2 = ptx::smem_u32(sA2);
       const uint32_t b1 = ptx::smem_u32(sB1 + s * C::STR_BYTES), b2 = ptx::smem_u32(sB2 + s * C::STR_BYTES);
-      if (lane == 0) {
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           const uint32_t aoff = (k >> 2) * (BR * 128) + (k & 3) * 32;
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       __syncwarp();
       ptx::mbar_wait(p_full, it & 1);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         const uint32_t hoff = half * (C::DH / 64) * (BS * 128);
 #pragma unroll
         for (int k = 0; k < BS / 16; ++k) {

@@ -79,7 +79,9 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
   uint64_t* o_done = bars + 7;      // 1   MMA -> softmax
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform role index + elect.sync regions: see the note in gemm.cu (no waterfall loops
+  // around UTMALDG / UTCHMMA)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;  // heavy (late) query tiles first
   const int h = blockIdx.y, b = blockIdx.z % pp.B;
   const int q0 = qt * BQ;
@@ -111,15 +113,18 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
       for (int a = 0; a < C::ATOMS; ++a)
         ptx::tma_load_3d(sQ + a * (BQ * 128), &p.tq, q_full, h * HD + a * 64, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % C::STAGES;
-        const uint32_t ph = (j / C::STAGES) & 1;
-        ptx::mbar_wait(&kv_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j % C::STAGES;
+      const uint32_t ph = (j / C::STAGES) & 1;
+      ptx::mbar_wait(&kv_empty[s], ph ^ 1);
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&kv_full[s], 2 * C::KV_BYTES);
 #pragma unroll
         for (int a = 0; a < C::ATOMS; ++a) {
@@ -127,6 +132,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
           ptx::tma_load_3d(sV + s * C::KV_BYTES + a * (BKV * 128), &p.tv, &kv_full[s], h * HD + a * 64, j * BKV, b);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------- MMA issuer
@@ -137,7 +143,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
       const int s = j % C::STAGES;
       ptx::mbar_wait(&kv_full[s], (j / C::STAGES) & 1);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         const uint32_t qb = ptx::smem_u32(sQ);
         const uint32_t kb = ptx::smem_u32(sK + s * C::KV_BYTES);
 #pragma unroll
@@ -152,7 +158,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
       __syncwarp();
       ptx::mbar_wait(p_full, j & 1);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         const uint32_t vb = ptx::smem_u32(sV + s * C::KV_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {

@@ -28,10 +28,9 @@ namespace sea {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int KA = 64;  // one swizzle atom along K: 64 bf16 = 128 B
 constexpr int kMaxGroups = 4;
 constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
-constexpr int A_BYTES = BM * BK * 2;
 
 struct DevEpilogue {
   const float* bias;
@@ -55,13 +54,21 @@ struct alignas(64) GemmParams {
   int groups, tiles_m, tiles_n;
   int chunk_kb;  // k-blocks per accumulation chunk (== num_kb when not chunked)
   int b_is_static;  // B was written before the previous kernel in the stream started (weights)
+  int debug;        // tuning probe: 1 = no TMA traffic (MMA pacing only), 2 = no MMA (TMA pacing only)
 };
 
+// BK = K extent of one pipeline stage.  The issuing thread pays a fixed ~390 cycles per stage
+// (mbarrier wait, fence, tcgen05.commit, loop), independent of the tile; a stage must therefore
+// carry at least that much tensor-pipe work: BK = 64 is enough for N = 256 / 192 (4 x 128 / 96
+// cycles), the narrower tiles take two swizzle atoms per stage (BK = 128).
 template <int BN>
 struct Cfg {
+  static constexpr int BK = (BN <= 128) ? 128 : 64;
+  static constexpr int KATOMS = BK / KA;
+  static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 3 : 4));
   static constexpr int TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // allocation must be a power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -262,6 +269,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
+  constexpr int BK = C::BK;
+  constexpr int A_BYTES = C::A_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -274,7 +283,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   uint64_t* tempty = tfull + 2;          // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // shfl-broadcast makes the warp index provably warp-uniform for the compiler: the role branches
+  // below are then uniform, and the single-thread regions are entered through elect.sync, so the
+  // uniform-datapath instructions (UTMALDG, UTCHMMA, UTCBAR) are issued directly.  With a plain
+  // `lane == 0` test ptxas wraps EVERY such instruction in a divergence ("waterfall") loop that
+  // costs ~130 cycles per tcgen05.mma and paces the whole mainloop.
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
   const int tiles_per_group = p.tiles_m * p.tiles_n;
@@ -305,41 +319,55 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      // The B operand is a weight matrix: it does not depend on the kernel running before this one,
-      // so the first ring-full of weight tiles is requested BEFORE griddepcontrol.wait and streams
-      // in from HBM while the upstream kernel drains.  Only the A tiles (activations) wait.
-      const int pre = (p.b_is_static && blockIdx.x < total_tiles) ? min(num_kb, STAGES) : 0;
-      if (pre > 0) {
-        const int g = blockIdx.x / tiles_per_group;
-        const int tn = (blockIdx.x - g * tiles_per_group) / p.tiles_m;
+    int stage = 0;
+    uint32_t phase = 0;
+    // The B operand is a weight matrix: it does not depend on the kernel running before this one,
+    // so the first ring-full of weight tiles is requested BEFORE griddepcontrol.wait and streams
+    // in from HBM while the upstream kernel drains.  Only the A tiles (activations) wait.
+    const int pre = p.b_is_static ? min(num_kb, STAGES) : 0;
+    if (pre > 0) {
+      const int g = blockIdx.x / tiles_per_group;
+      const int tn = (blockIdx.x - g * tiles_per_group) / p.tiles_m;
+      if (ptx::elect_one()) {
         for (int kb = 0; kb < pre; ++kb) {
           ptx::mbar_expect_tx(&full[kb], C::STAGE_BYTES);
-          ptx::tma_load_2d(smem_b + kb * C::B_BYTES, &p.tma_b[g], &full[kb], kb * BK, tn * BN);
+#pragma unroll
+          for (int a = 0; a < C::KATOMS; ++a)
+            ptx::tma_load_2d(smem_b + kb * C::B_BYTES + a * (BN * 128), &p.tma_b[g], &full[kb], kb * BK + a * KA, tn * BN);
         }
       }
-      ptx::pdl_wait();
-      bool first = true;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int g = tile / tiles_per_group;
-        const int r = tile - g * tiles_per_group;
-        const int tm = r % p.tiles_m;
-        const int tn = r / p.tiles_m;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (first && kb < pre) {
-            ptx::tma_load_2d(smem_a + stage * A_BYTES, &p.tma_a[g], &full[stage], kb * BK, tm * BM);
+      __syncwarp();
+    }
+    ptx::pdl_wait();
+    bool first = true;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int g = tile / tiles_per_group;
+      const int r = tile - g * tiles_per_group;
+      const int tm = r % p.tiles_m;
+      const int tn = r / p.tiles_m;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const bool prefetched = first && kb < pre;
+        if (!prefetched) ptx::mbar_wait(&empty[stage], phase ^ 1);
+        if (ptx::elect_one()) {
+          if (prefetched) {
+#pragma unroll
+            for (int a = 0; a < C::KATOMS; ++a)
+              ptx::tma_load_2d(smem_a + stage * A_BYTES + a * (BM * 128), &p.tma_a[g], &full[stage], kb * BK + a * KA, tm * BM);
+          } else if (p.debug == 1) {
+            ptx::mbar_arrive(&full[stage]);
           } else {
-            ptx::mbar_wait(&empty[stage], phase ^ 1);
             ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-            ptx::tma_load_2d(smem_a + stage * A_BYTES, &p.tma_a[g], &full[stage], kb * BK, tm * BM);
-            ptx::tma_load_2d(smem_b + stage * C::B_BYTES, &p.tma_b[g], &full[stage], kb * BK, tn * BN);
+#pragma unroll
+            for (int a = 0; a < C::KATOMS; ++a) {
+              ptx::tma_load_2d(smem_a + stage * A_BYTES + a * (BM * 128), &p.tma_a[g], &full[stage], kb * BK + a * KA, tm * BM);
+              ptx::tma_load_2d(smem_b + stage * C::B_BYTES + a * (BN * 128), &p.tma_b[g], &full[stage], kb * BK + a * KA, tn * BN);
+            }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        first = false;
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      first = false;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
@@ -357,14 +385,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
-          if (lane == 0) {
+          if (ptx::elect_one()) {
             const uint32_t a_base = ptx::smem_u32(smem_a + stage * A_BYTES);
             const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::B_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t adesc = ptx::umma_smem_desc(a_base + k * 32, 16, 1024);
-              const uint64_t bdesc = ptx::umma_smem_desc(b_base + k * 32, 16, 1024);
-              ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+              const uint64_t adesc = ptx::umma_smem_desc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32, 16, 1024);
+              const uint64_t bdesc = ptx::umma_smem_desc(b_base + (k >> 2) * (BN * 128) + (k & 3) * 32, 16, 1024);
+              if (p.debug != 2) ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
             }
             ptx::umma_commit(&empty[stage]);
             if (kb == kb1 - 1) ptx::umma_commit(&tfull[acc]);
@@ -421,6 +449,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
 }
 
 int g_force_bn = 0;
+int g_debug = 0;
 
 template <int BN>
 int launch(const GemmParams& p, int total_tiles, cudaStream_t stream) {
@@ -459,6 +488,8 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
 }  // namespace sea
 
 extern "C" void sea_gemm_force_tile_n(int bn) { sea::g_force_bn = bn; }
+extern "C" void sea_gemm_debug_probe(int mode) { sea::g_debug = mode; }
+
 
 
 extern "C" int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* probs, int M, int N,
@@ -469,7 +500,7 @@ extern "C" int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* probs,
 extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem* probs, int M,
                                         int N, int K, int k_chunk, sea_stream_t stream) {
   using namespace sea;
-  if (k_chunk < 0 || (k_chunk % BK) != 0) return SEA_ERR_INVALID;
+  if (k_chunk < 0 || (k_chunk % 128) != 0) return SEA_ERR_INVALID;
   if (probs == nullptr || num_problems < 1 || num_problems > kMaxGroups) return SEA_ERR_INVALID;
   if (M <= 0 || N <= 0 || K <= 0) return SEA_ERR_INVALID;
   if ((N % 8) != 0) return SEA_ERR_UNSUPPORTED;  // K may be ragged: TMA zero-fills the tail
@@ -478,17 +509,18 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
 
   int bn = g_force_bn;
   if (bn == 0) {
-    // Cost model: waves x tile width / mainloop efficiency of that width (single-CTA SS-MMA is
-    // shared-memory-bandwidth bound below N = 256: measured ~0.5 / 0.66 / 0.8 / 0.9 of the MMA rate
-    // at N = 64 / 128 / 192 / 256), plus a per-wave epilogue/latency term.
+    // Cost model: waves x tile width / mainloop efficiency of that width, plus a per-wave
+    // epilogue/latency term.  Efficiencies are measured (scripts/shape_bench.py gemm): the issuing
+    // thread's fixed per-stage cost is amortised over N x BK, so narrow tiles stay below the MMA rate
+    // (0.6 / 0.8 / 0.87 / 0.9 of it at N = 64 / 128 / 192 / 256).
     const long long tm = (M + BM - 1) / BM;
     const int cand[4] = {64, 128, 192, 256};
-    const double eff[4] = {0.5, 0.66, 0.8, 0.9};
+    const double eff[4] = {0.6, 0.8, 0.87, 0.9};
     double best = 1e30;
     for (int i = 0; i < 4; ++i) {
       const long long tiles = tm * ((N + cand[i] - 1) / cand[i]) * num_problems;
       const long long waves = (tiles + num_sms() - 1) / num_sms();
-      const double kb = (K + BK - 1) / BK;
+      const double kb = (K + KA - 1) / KA;
       const double cost = waves * (cand[i] / eff[i] * kb + 6.0 * cand[i] + 400.0);
       if (cost < best) { best = cost; bn = cand[i]; }
     }
@@ -500,8 +532,10 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   p.groups = num_problems;
   p.tiles_m = (M + BM - 1) / BM;
   p.tiles_n = (N + bn - 1) / bn;
-  p.chunk_kb = (k_chunk > 0 && k_chunk < K) ? k_chunk / BK : (K + BK - 1) / BK;
-  const bool chunked = p.chunk_kb < (K + BK - 1) / BK;
+  const int bk = bn <= 128 ? 128 : 64;   // Cfg<BN>::BK
+  p.chunk_kb = (k_chunk > 0 && k_chunk < K) ? k_chunk / bk : (K + bk - 1) / bk;
+  const bool chunked = p.chunk_kb < (K + bk - 1) / bk;
+  p.debug = g_debug;
   p.b_is_static = 1;
   for (int g = 0; g < num_problems; ++g) p.b_is_static &= probs[g].b_is_static != 0;
   for (int g = 0; g < num_problems; ++g) {
@@ -531,9 +565,9 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
           e.rope_ld < e.seq_len)
         return SEA_ERR_UNSUPPORTED;
     }
-    rc = make_tmap_bf16_2d(&p.tma_a[g], q.a, K, M, q.lda, BK, BM);
+    rc = make_tmap_bf16_2d(&p.tma_a[g], q.a, K, M, q.lda, KA, BM);
     if (rc != SEA_OK) return rc;
-    rc = make_tmap_bf16_2d(&p.tma_b[g], q.b, K, N, q.ldb, BK, bn);
+    rc = make_tmap_bf16_2d(&p.tma_b[g], q.b, K, N, q.ldb, KA, bn);
     if (rc != SEA_OK) return rc;
     DevEpilogue& d = p.epi[g];
     d.bias = e.bias;
