@@ -65,6 +65,16 @@ def peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
+def gemm_traffic():
+    """DRAM bytes per GEMM launch from the committed `ncu --set full` capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def make_inputs(B, R, E, V, seed):
     g = torch.Generator().manual_seed(seed)
     x0 = torch.randn(B, 1, V, E, generator=g)
@@ -295,10 +305,15 @@ def main():
                    "l2": "no flush: per-step working set (174 MB bf16 weights + activations up to "
                          ">1 GB) exceeds the 126 MB L2",
                    "bench_step": f"one {R}-step rollout of {B} trajectories per GPU",
+                   "execution": "sea_b200.rollout.RolloutPlan: one CUDA graph per prefix length (gather prefix, "
+                                "full forward over the prefix, append last step); the roofline leg replays the "
+                                "same kernels eagerly with per-launch CUDA events",
                    "algorithmic_tflop_per_step_per_gpu": flops / 1e12,
                    "model_tflops_per_gpu": flops / (ms_step * 1e-3) / 1e12},
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["sustained"],
-                     "unit": "TFLOP/s", "frac": gemm_tflops / pk["sustained"], "traffic": None,
+                     "unit": "TFLOP/s", "frac": gemm_tflops / pk["sustained"], "traffic": gemm_traffic(),
+                     "traffic_note": "DRAM bytes per GEMM launch of the T=100 forward, ncu --set full "
+                                     "(profiles/r1b_summary.md section 2); not measured in this run",
                      "kernel": "gemm_bf16_tn_kernel (tcgen05)", "peak_source": pk["src"] + ", sustained",
                      "gemm_share_of_kernel_time": ps["gemm"]["ms"] / total_kernel_ms if total_kernel_ms else None,
                      "attention_tflops": attn_tflops, "attention_frac": attn_tflops / pk["sustained"],
