@@ -37,6 +37,7 @@ enum {
 };
 
 enum { SEA_ACT_NONE = 0, SEA_ACT_GELU = 1 };
+enum { SEA_GEMM_A_MN = 1, SEA_GEMM_B_MN = 2 };
 enum { SEA_PREC_BF16 = 0, SEA_PREC_FP32 = 1 };
 enum { SEA_NORM_LN = 0, SEA_NORM_ADALN = 1 };
 #define SEA_MAX_STREAMS 4
@@ -97,7 +98,13 @@ typedef struct sea_gemm_problem {
                           boundary of the stream (a weight matrix).  The TMA producer then requests its
                           first ring of B tiles before griddepcontrol.wait, so the weight fetch overlaps
                           the upstream kernel's tail.  0 = B may come from a kernel still in flight. */
-  int32_t reserved;
+  int32_t mn_major;    /* mask of SEA_GEMM_A_MN / SEA_GEMM_B_MN.  0: A [M,K], B [N,K] (K contiguous).
+                          SEA_GEMM_B_MN: B is stored [K,N] (N contiguous, ldb = its row pitch) — the input
+                          gradient dx = dy W reads the nn.Linear weight W [N_out, K_in] as it is.
+                          A_MN | B_MN: A stored [K,M] and B [K,N]: C = A^T B — the weight gradient
+                          dW = dy^T x (autograd of every nn.Linear on the path, train/train_temporal.py:257).
+                          No transpose is materialised in either case (MN-major UMMA descriptors).
+                          All problems of a launch must agree; A_MN needs M % 8 == 0. */
 } sea_gemm_problem;
 
 /* `num_problems` (1..4) same-shape problems in ONE launch (the V field streams are independent). */

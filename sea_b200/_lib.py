@@ -47,7 +47,7 @@ class GemmProblem(C.Structure):
         ("ldb", C.c_int64),
         ("epi", GemmEpilogue),
         ("b_is_static", C.c_int32),
-        ("reserved", C.c_int32),
+        ("mn_major", C.c_int32),
     ]
 
 

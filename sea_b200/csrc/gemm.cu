@@ -264,7 +264,15 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
   }
 }
 
-template <int BN>
+// AMN / BMN = false: the operand is stored [M,K] / [N,K], K contiguous (the nn.Linear forward case).
+// AMN / BMN = true : the operand is stored [K,M] / [K,N] (M / N contiguous) and is consumed through
+//   MN-major UMMA descriptors, so no transpose is ever materialised:
+//     forward   y  = x W^T        A = x  [M,K]            B = W  [N,K]            (false, false)
+//     dgrad     dx = dy W         A = dy [M,N] K-major    B = W  [N,K] = [Kc, N'] (false, true)
+//     wgrad     dW = dy^T x       A = dy [M,N] = [Kc, M'] B = x  [M,K] = [Kc, N'] (true,  true)
+//   Stage layout of an MN-major operand, per 64-wide M/N chunk: [BK k-rows][128 B]; descriptors step
+//   16 k-rows (2048 B) per MMA, LBO = chunk stride, SBO = 1024 B (8 k-rows).
+template <int BN, bool AMN, bool BMN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
@@ -331,9 +339,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       if (ptx::elect_one()) {
         for (int kb = 0; kb < pre; ++kb) {
           ptx::mbar_expect_tx(&full[kb], C::STAGE_BYTES);
+          if (BMN) {
 #pragma unroll
-          for (int a = 0; a < C::KATOMS; ++a)
-            ptx::tma_load_2d(smem_b + kb * C::B_BYTES + a * (BN * 128), &p.tma_b[g], &full[kb], kb * BK + a * KA, tn * BN);
+            for (int a = 0; a < BN / 64; ++a)
+              ptx::tma_load_2d(smem_b + kb * C::B_BYTES + a * (BK * 128), &p.tma_b[g], &full[kb], tn * BN + a * 64, kb * BK);
+          } else {
+#pragma unroll
+            for (int a = 0; a < C::KATOMS; ++a)
+              ptx::tma_load_2d(smem_b + kb * C::B_BYTES + a * (BN * 128), &p.tma_b[g], &full[kb], kb * BK + a * KA, tn * BN);
+          }
         }
       }
       __syncwarp();
@@ -349,19 +363,36 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
         const bool prefetched = first && kb < pre;
         if (!prefetched) ptx::mbar_wait(&empty[stage], phase ^ 1);
         if (ptx::elect_one()) {
-          if (prefetched) {
+          auto load_a = [&]() {
+            if (AMN) {
 #pragma unroll
-            for (int a = 0; a < C::KATOMS; ++a)
-              ptx::tma_load_2d(smem_a + stage * A_BYTES + a * (BM * 128), &p.tma_a[g], &full[stage], kb * BK + a * KA, tm * BM);
+              for (int a = 0; a < BM / 64; ++a)
+                ptx::tma_load_2d(smem_a + stage * A_BYTES + a * (BK * 128), &p.tma_a[g], &full[stage], tm * BM + a * 64, kb * BK);
+            } else {
+#pragma unroll
+              for (int a = 0; a < C::KATOMS; ++a)
+                ptx::tma_load_2d(smem_a + stage * A_BYTES + a * (BM * 128), &p.tma_a[g], &full[stage], kb * BK + a * KA, tm * BM);
+            }
+          };
+          auto load_b = [&]() {
+            if (BMN) {
+#pragma unroll
+              for (int a = 0; a < BN / 64; ++a)
+                ptx::tma_load_2d(smem_b + stage * C::B_BYTES + a * (BK * 128), &p.tma_b[g], &full[stage], tn * BN + a * 64, kb * BK);
+            } else {
+#pragma unroll
+              for (int a = 0; a < C::KATOMS; ++a)
+                ptx::tma_load_2d(smem_b + stage * C::B_BYTES + a * (BN * 128), &p.tma_b[g], &full[stage], kb * BK + a * KA, tn * BN);
+            }
+          };
+          if (prefetched) {
+            load_a();
           } else if (p.debug == 1) {
             ptx::mbar_arrive(&full[stage]);
           } else {
             ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-#pragma unroll
-            for (int a = 0; a < C::KATOMS; ++a) {
-              ptx::tma_load_2d(smem_a + stage * A_BYTES + a * (BM * 128), &p.tma_a[g], &full[stage], kb * BK + a * KA, tm * BM);
-              ptx::tma_load_2d(smem_b + stage * C::B_BYTES + a * (BN * 128), &p.tma_b[g], &full[stage], kb * BK + a * KA, tn * BN);
-            }
+            load_a();
+            load_b();
           }
         }
         __syncwarp();
@@ -371,7 +402,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, AMN ? 1 : 0, BMN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -390,8 +421,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
             const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::B_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t adesc = ptx::umma_smem_desc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32, 16, 1024);
-              const uint64_t bdesc = ptx::umma_smem_desc(b_base + (k >> 2) * (BN * 128) + (k & 3) * 32, 16, 1024);
+              const uint64_t adesc = AMN ? ptx::umma_smem_desc(a_base + k * 2048, BK * 128, 1024)
+                                        : ptx::umma_smem_desc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32, 16, 1024);
+              const uint64_t bdesc = BMN ? ptx::umma_smem_desc(b_base + k * 2048, BK * 128, 1024)
+                                        : ptx::umma_smem_desc(b_base + (k >> 2) * (BN * 128) + (k & 3) * 32, 16, 1024);
               if (p.debug != 2) ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
             }
             ptx::umma_commit(&empty[stage]);
@@ -451,20 +484,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
 int g_force_bn = 0;
 int g_debug = 0;
 
-template <int BN>
+template <int BN, bool AMN, bool BMN>
 int launch(const GemmParams& p, int total_tiles, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, AMN, BMN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set[dev] = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  SEA_LAUNCH((gemm_bf16_tn_kernel<BN>), grid, kThreads, C::SMEM_BYTES, stream, p);
+  SEA_LAUNCH((gemm_bf16_tn_kernel<BN, AMN, BMN>), grid, kThreads, C::SMEM_BYTES, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -504,6 +537,12 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   if (probs == nullptr || num_problems < 1 || num_problems > kMaxGroups) return SEA_ERR_INVALID;
   if (M <= 0 || N <= 0 || K <= 0) return SEA_ERR_INVALID;
   if ((N % 8) != 0) return SEA_ERR_UNSUPPORTED;  // K may be ragged: TMA zero-fills the tail
+  const int mnm = probs[0].mn_major;
+  for (int g = 0; g < num_problems; ++g)
+    if (probs[g].mn_major != mnm) return SEA_ERR_INVALID;
+  if (mnm != 0 && mnm != SEA_GEMM_B_MN && mnm != (SEA_GEMM_A_MN | SEA_GEMM_B_MN)) return SEA_ERR_UNSUPPORTED;
+  const bool amn = (mnm & SEA_GEMM_A_MN) != 0, bmn = (mnm & SEA_GEMM_B_MN) != 0;
+  if (amn && (M % 8) != 0) return SEA_ERR_UNSUPPORTED;
   int rc = ensure_init();
   if (rc != SEA_OK) return rc;
 
@@ -542,7 +581,8 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
     const sea_gemm_problem& q = probs[g];
     const sea_gemm_epilogue& e = q.epi;
     if (q.a == nullptr || q.b == nullptr) return SEA_ERR_INVALID;
-    if ((q.lda % 8) != 0 || (q.ldb % 8) != 0 || q.lda < K || q.ldb < K) return SEA_ERR_INVALID;
+    if ((q.lda % 8) != 0 || (q.ldb % 8) != 0) return SEA_ERR_INVALID;
+    if (q.lda < (amn ? M : K) || q.ldb < (bmn ? N : K)) return SEA_ERR_INVALID;
     if ((reinterpret_cast<uintptr_t>(q.a) & 15) || (reinterpret_cast<uintptr_t>(q.b) & 15))
       return SEA_ERR_INVALID;
     if (e.out_f32 == nullptr && e.out_bf16 == nullptr && e.out_pre_bf16 == nullptr)
@@ -565,9 +605,12 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
           e.rope_ld < e.seq_len)
         return SEA_ERR_UNSUPPORTED;
     }
-    rc = make_tmap_bf16_2d(&p.tma_a[g], q.a, K, M, q.lda, KA, BM);
+    // K-major operand: boxes of 64 k-columns x BM / BN rows; MN-major: 64 M/N-columns x BK k-rows
+    rc = amn ? make_tmap_bf16_2d(&p.tma_a[g], q.a, M, K, q.lda, 64, bk)
+             : make_tmap_bf16_2d(&p.tma_a[g], q.a, K, M, q.lda, KA, BM);
     if (rc != SEA_OK) return rc;
-    rc = make_tmap_bf16_2d(&p.tma_b[g], q.b, K, N, q.ldb, KA, bn);
+    rc = bmn ? make_tmap_bf16_2d(&p.tma_b[g], q.b, N, K, q.ldb, 64, bk)
+             : make_tmap_bf16_2d(&p.tma_b[g], q.b, K, N, q.ldb, KA, bn);
     if (rc != SEA_OK) return rc;
     DevEpilogue& d = p.epi[g];
     d.bias = e.bias;
@@ -596,8 +639,15 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   }
   const int total = p.tiles_m * p.tiles_n * p.groups;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch<256>(p, total, s);
-  if (bn == 192) return launch<192>(p, total, s);
-  if (bn == 128) return launch<128>(p, total, s);
-  return launch<64>(p, total, s);
+#define SEA_GEMM_DISPATCH(AMN_, BMN_)                                   \
+  do {                                                                  \
+    if (bn == 256) return launch<256, AMN_, BMN_>(p, total, s);         \
+    if (bn == 192) return launch<192, AMN_, BMN_>(p, total, s);         \
+    if (bn == 128) return launch<128, AMN_, BMN_>(p, total, s);         \
+    return launch<64, AMN_, BMN_>(p, total, s);                         \
+  } while (0)
+  if (amn && bmn) SEA_GEMM_DISPATCH(true, true);
+  if (bmn) SEA_GEMM_DISPATCH(false, true);
+  SEA_GEMM_DISPATCH(false, false);
+#undef SEA_GEMM_DISPATCH
 }

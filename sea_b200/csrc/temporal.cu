@@ -53,14 +53,10 @@ ProfScope::~ProfScope() {
 // ------------------------------------------------------------------------------ cache layout
 static PackedLinear take_linear(Arena& ar, int N, int K, int kf, bool training) {
   PackedLinear p{};
+  (void)training;  // one layout for inference and training: dgrad needs no transposed copies
   p.N = N; p.K = K;
-  p.wT = nullptr; p.ldwT = 0;
   p.ldw = static_cast<long long>(kf) * K;
   p.w = static_cast<bf16*>(ar.take(sizeof(bf16) * N * p.ldw));
-  if (training) {
-    p.ldwT = static_cast<long long>(kf) * N;
-    p.wT = static_cast<bf16*>(ar.take(sizeof(bf16) * K * p.ldwT));
-  }
   return p;
 }
 
@@ -112,14 +108,7 @@ static int pack_weight(const float* src, int N, int K, const PackedLinear& dst, 
     if (rc) return rc;
     ++g_launches;
   }
-  if (dst.wT && (what & SEA_REFRESH_TRANSPOSED)) {
-    a.transpose = 1;
-    a.split_inner = n_total;
-    a.dst = const_cast<bf16*>(dst.wT) + row_off;
-    a.ld_dst = dst.ldwT;
-    rc = sea_pack_operand(&a, reinterpret_cast<sea_stream_t>(s));
-    ++g_launches;
-  }
+  (void)n_total;
   return rc;
 }
 

@@ -31,18 +31,8 @@ struct BCtx {
   Ctx c;
   const float* ib;
   BwdTape* bt;
-  long long Mp;  // M rounded up to 8 (pitch of transposed operands)
   sea_stream_t st() const { return reinterpret_cast<sea_stream_t>(c.s); }
 };
-
-int transpose_bf16(BCtx& b, const bf16* src, long long ld, int R, int Ccols, bf16* dst) {
-  sea_pack_args a{};
-  a.src_bf16 = src; a.ld = ld; a.R = R; a.C = Ccols; a.transpose = 1;
-  a.dst = dst; a.ld_dst = b.Mp;
-  ++g_launches;
-  ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, 4.0 * R * Ccols);
-  return sea_pack_operand(&a, b.st());
-}
 
 int cast_f32(BCtx& b, const float* src, long long ld, int R, int Ccols, bf16* dst, long long ldd, int transpose) {
   sea_pack_args a{};
@@ -89,18 +79,17 @@ int linear_bwd(BCtx& b, int n, LinB* L) {
   bool any_w = false;
   for (int g = 0; g < n; ++g) any_w |= (L[g].dW != nullptr) || (L[g].n_split > 0 && L[g].dW_split[0] != nullptr);
   if (any_w) {
-    for (int g = 0; g < n; ++g) {
-      SEA_TRY(transpose_bf16(b, L[g].dy, L[g].lddy, M, N, b.bt->tr_dy[g]));
-      SEA_TRY(transpose_bf16(b, L[g].a, L[g].lda, M, K, b.bt->tr_a[g]));
-    }
+    // dW[N,K] += dY[M,N]^T X[M,K]: both operands are read as they lie in memory (MN-major UMMA
+    // descriptors) — no transpose pass.
     const int parts = L[0].n_split > 0 ? L[0].n_split : 1;
     const int Np = N / parts;
     for (int part = 0; part < parts; ++part) {
       for (int g = 0; g < n; ++g) {
         sea_gemm_problem& p = probs[g];
         p = sea_gemm_problem{};
-        p.a = b.bt->tr_dy[g] + static_cast<long long>(part) * Np * b.Mp; p.lda = b.Mp;
-        p.b = b.bt->tr_a[g]; p.ldb = b.Mp;
+        p.a = L[g].dy + static_cast<long long>(part) * Np; p.lda = L[g].lddy;
+        p.b = L[g].a; p.ldb = L[g].lda;
+        p.mn_major = SEA_GEMM_A_MN | SEA_GEMM_B_MN;
         float* dW = parts > 1 ? L[g].dW_split[part] : L[g].dW;
         p.epi.out_f32 = dW; p.epi.ld_out_f32 = K;
         p.epi.residual = dW; p.epi.ld_residual = K;
@@ -118,8 +107,9 @@ int linear_bwd(BCtx& b, int n, LinB* L) {
       sea_gemm_problem& p = probs[g];
       p = sea_gemm_problem{};
       p.a = L[g].dy; p.lda = L[g].lddy;
-      p.b = L[g].W->wT; p.ldb = L[g].W->ldwT;
-      p.b_is_static = 1;  // transposed weight copy from the cache: older than this call's launch fence
+      p.b = L[g].W->w; p.ldb = L[g].W->ldw;   // W [N_out, K_in] read as the MN-major B operand: no transposed copy
+      p.mn_major = SEA_GEMM_B_MN;
+      p.b_is_static = 1;  // packed weights are older than this call's launch fence
       p.epi.residual = L[g].da_res; p.epi.ld_residual = L[g].ld_res;
       p.epi.gelu_grad_of = L[g].gelu_of; p.epi.ld_gelu = L[g].ld_gelu;
       p.epi.out_f32 = L[g].da_f32; p.epi.ld_out_f32 = L[g].ld_da;
@@ -196,13 +186,12 @@ int attention_bwd(BCtx& b, const bf16* q, long long ldq, const bf16* k, const bf
 }  // namespace
 
 void layout_bwd_tape(const sea_temporal_desc* d, int B, int T, Arena& ar, BwdTape& t) {
-  const size_t M = static_cast<size_t>(B) * T, Mp = (M + 7) & ~static_cast<size_t>(7);
+  const size_t M = static_cast<size_t>(B) * T;
   const size_t E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
   const int V = d->num_streams;
   const bool ada = d->norm_kind == SEA_NORM_ADALN;
   auto f32 = [&](size_t n) { return static_cast<float*>(ar.take(n * 4)); };
   auto b16 = [&](size_t n) { return static_cast<bf16*>(ar.take(n * 2)); };
-  const size_t wide = H > 3 * E ? H : 3 * E;
   for (int i = 0; i < V; ++i) {
     BwdStream& s = t.s[i];
     s.dxout = f32(M * E); s.dxoutb = b16(M * E);
@@ -221,8 +210,6 @@ void layout_bwd_tape(const sea_temporal_desc* d, int B, int T, Arena& ar, BwdTap
       s.dcond0 = f32(M * 2 * E); s.dcond2 = f32(M * 2 * E); s.dcondc = f32(M * 2 * Dd);
       s.dcondF = f32(M * 2 * E);
     }
-    t.tr_dy[i] = b16(wide * Mp);
-    t.tr_a[i] = b16(wide * Mp);
     if (ada) { t.dcb[i] = b16(M * 2 * E); t.dhid[i] = f32(M * 2 * E); }
   }
   t.delta = f32(static_cast<size_t>(B) * d->n_heads * T);
@@ -258,7 +245,6 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
   b.c.fp32 = false; b.c.B = B; b.c.T = T; b.c.M = B * T;
   b.c.Mc = b.c.M; b.c.ld_ib = d->ib_num; b.c.cond_div = 1;
   b.ib = ib; b.bt = &bt;
-  b.Mp = (static_cast<long long>(b.c.M) + 7) & ~7LL;
   const int M = b.c.M, V = d->num_streams, E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
   const int hd = E / d->n_heads, hdc = Dd / d->n_heads;
   const int kind = d->norm_kind;

@@ -24,10 +24,8 @@ struct Arena {
 
 // One nn.Linear (or a fused group of them) in tensor-core layout.
 struct PackedLinear {
-  const bf16* w;   // [N, kf*K]  (kf = 6 in the fp32 split mode)
+  const bf16* w;   // [N, kf*K]  (kf = 6 in the fp32 split mode); dgrad reads it as an MN-major operand
   long long ldw;
-  const bf16* wT;  // [K, kf*N]  for dgrad (training only)
-  long long ldwT;
   int N, K;
 };
 
@@ -94,8 +92,6 @@ struct BwdStream {
 };
 struct BwdTape {
   BwdStream s[SEA_MAX_STREAMS];
-  bf16* tr_dy[SEA_MAX_STREAMS];  // dy^T  [N, Mp]
-  bf16* tr_a[SEA_MAX_STREAMS];   // a^T   [K, Mp]
   bf16* dcb[SEA_MAX_STREAMS];    // bf16 copy of dcond
   float* dhid[SEA_MAX_STREAMS];  // gradient at SiLU output
   float* delta;                  // attention backward scratch

@@ -384,12 +384,13 @@ class TemporalEngine:
 
     def after_optimizer_step(self, straight_copies_fresh: bool) -> None:
         """Called by sea_b200.optim.AdamW.step(): the masters changed through raw pointers (no
-        ``_version`` bump).  If the optimizer already wrote the straight bf16 copies, only the dgrad
-        transposes and the fused bias vectors are rebuilt; otherwise everything is."""
+        ``_version`` bump).  If the optimizer already wrote the bf16 copies, only the fused bias
+        vectors (q|k|v, k|v) are re-gathered; otherwise everything is re-packed.  (dgrad reads the same
+        [N,K] copy as an MN-major operand, so there are no transposed copies to rebuild.)"""
         if self._cache is None or self._cache_key is None or self._desc is None:
             return
         training = bool(self._cache_key[0])
-        what = 6 if straight_copies_fresh else 7   # SEA_REFRESH_TRANSPOSED | SEA_REFRESH_BIASES, or ALL
+        what = 4 if straight_copies_fresh else 7   # SEA_REFRESH_BIASES, or SEA_REFRESH_ALL
         with torch.cuda.device(self._dev):
             check(lib.sea_temporal_refresh_ex(C.byref(self._desc), C.c_void_p(self._cache.data_ptr()),
                                               C.c_size_t(self._cache.numel()), int(training), what,

@@ -109,3 +109,48 @@ def test_gemm_throughput_report(cuda):
         lib.sea_gemm_force_tile_n(0)
         ref = _ref(a[:64], b[:64])
         assert (out[:64, :64].float() - ref).abs().max().item() < 0.02 * ref.abs().max().item() + 0.5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1024, 512, 798), (3072, 1024, 796), (520, 8192, 333), (64, 2048, 1600)])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
+def test_gemm_mn_major_operands(cuda, M, N, K, bn):
+    """mn_major = 1: C[M,N] = A^T B with A stored [K,M], B stored [K,N] (the wgrad layout
+    dW = dY^T X), accumulated onto an fp32 residual, for every tile width."""
+    from sea_b200 import lib, ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(K, M, device=cuda, generator=g).bfloat16()
+    b = torch.randn(K, N, device=cuda, generator=g).bfloat16()
+    acc = torch.randn(M, N, device=cuda, generator=g)
+    ref = acc.double() + a.double().t() @ b.double()
+    out = acc.clone()
+    lib.sea_gemm_force_tile_n(bn)
+    try:
+        ops.gemm_bf16_tn([ops.gemm_problem(a, b, residual=out, out_f32=out, mn_major=3)], M, N, K)
+    finally:
+        lib.sea_gemm_force_tile_n(0)
+    torch.cuda.synchronize()
+    err = ((out.double() - ref).norm() / ref.norm()).item()
+    assert err < 2e-6, err
+
+
+@pytest.mark.parametrize("M,N,K", [(798, 1024, 3072), (796, 2048, 16384), (100, 512, 1024), (3200, 8192, 1024)])
+def test_gemm_b_mn_major(cuda, M, N, K):
+    """mn_major = SEA_GEMM_B_MN: C[M,N] = A[M,K] B[K,N] with B stored [K,N] — dgrad reads W [N_out,K_in]
+    directly (here K plays N_out and N plays K_in)."""
+    from sea_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    b = (torch.randn(K, N, device=cuda, generator=g) * 0.05).bfloat16()
+    out = torch.empty(M, N, device=cuda)
+    ops.gemm_bf16_tn([ops.gemm_problem(a, b, out_f32=out, mn_major=2, b_is_static=True)], M, N, K)
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double()
+    err = ((out.double() - ref).norm() / ref.norm()).item()
+    # K-major reference run of the same product: the tensor core's fp32 accumulator is not round-to-nearest
+    # (drift grows with K, DESIGN.md), so the bar is "same as the K-major path", not fp32 epsilon
+    out2 = torch.empty(M, N, device=cuda)
+    ops.gemm_bf16_tn([ops.gemm_problem(a, b.t().contiguous(), out_f32=out2)], M, N, K)
+    err2 = ((out2.double() - ref).norm() / ref.norm()).item()
+    print(f"\n[gemm B MN-major] M={M} N={N} K={K}: rel err {err:.2e} (K-major path {err2:.2e})")
+    assert err < max(2e-6, 1.5 * err2), (err, err2)
+    assert torch.equal(out, out2)   # same MMA sequence along K -> bit-identical
