@@ -333,6 +333,8 @@ typedef struct sea_attn_bwd_args {
 int sea_attention_bwd(const sea_attn_bwd_args* args, sea_stream_t stream);
 /* Test hook: 1 forces the CUDA-core kernel even where the tcgen05 kernel applies. */
 void sea_attention_force_simt(int on);
+/* Tuning hook: 0 = one 128-query tile per CTA for every T (default 1: two tiles per CTA, overlapped, when T > 128). */
+void sea_attention_two_tiles(int on);
 
 /* ------------------------------------------------------------------ fused AdamW --------------
  * torch.optim.AdamW.step as the reference configures it (utils/train_utils.py:33-39; called at

@@ -18,7 +18,9 @@ static int validate(const sea_attn_args* a) {
 }
 }  // namespace sea
 
+namespace sea { extern int g_attn_two_tiles; }
 extern "C" void sea_attention_force_simt(int on) { sea::g_force_simt = on; }
+extern "C" void sea_attention_two_tiles(int on) { sea::g_attn_two_tiles = on; }
 
 extern "C" int sea_attention_fwd(const sea_attn_args* a, sea_stream_t stream) {
   return sea_attention_fwd_group(1, a, stream);

@@ -231,23 +231,25 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       const float* drow = dl_s + (it & 1) * BS;
       ptx::mbar_wait(s_full, it & 1);
       ptx::tc_fence_after();
+      // 64 columns of S and dP per TMEM round trip (four loads in flight), results written back in place
 #pragma unroll
-      for (int c = 0; c < BS / 32; ++c) {
-        uint32_t rs[32], rd[32];
-        ptx::tmem_ld_32x32(tmem + lane_base + kColS + c * 32, rs);
-        ptx::tmem_ld_32x32(tmem + lane_base + kColDP + c * 32, rd);
+      for (int c2 = 0; c2 < BS / 64; ++c2) {
+        uint32_t rs[64], rd[64];
+        ptx::tmem_ld_32x32p(tmem + lane_base + kColS + c2 * 64, rs);
+        ptx::tmem_ld_32x32p(tmem + lane_base + kColS + c2 * 64 + 32, rs + 32);
+        ptx::tmem_ld_32x32p(tmem + lane_base + kColDP + c2 * 64, rd);
+        ptx::tmem_ld_32x32p(tmem + lane_base + kColDP + c2 * 64 + 32, rd + 32);
         ptx::tmem_ld_wait();
-        uint32_t pk_p[16], pk_d[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
+        for (int e = 0; e < 64; e += 2) {
           float pv[2], dv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int cpos = c0 + c * 32 + e + u;
+            const int cpos = c0 + c2 * 64 + e + u;
             float l2, dl;
             if (MODE == 0) { l2 = my_lse2; dl = my_dl; }
-            else { l2 = lrow[c * 32 + e + u]; dl = drow[c * 32 + e + u]; }
-            float pe = exp2f(__uint_as_float(rs[e + u]) * p.scale_log2 - l2);
+            else { l2 = lrow[c2 * 64 + e + u]; dl = drow[c2 * 64 + e + u]; }
+            float pe = ptx::ex2(fmaf(__uint_as_float(rs[e + u]), p.scale_log2, -l2));
             if (need_mask) {
               const int qq = MODE == 0 ? rpos : cpos;
               const int kk = MODE == 0 ? cpos : rpos;
@@ -255,13 +257,16 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
             }
             pv[u] = pe;
             dv[u] = pe * (__uint_as_float(rd[e + u]) - dl) * p.scale;
-            if (need_mask && pe == 0.f) dv[u] = 0.f;  // padded rows may hold garbage * 0
           }
-          pk_p[e >> 1] = ptx::pack_bf16(pv[0], pv[1]);
-          pk_d[e >> 1] = ptx::pack_bf16(dv[0], dv[1]);
+          rs[e >> 1] = ptx::pack_bf16(pv[0], pv[1]);
+          rd[e >> 1] = ptx::pack_bf16(dv[0], dv[1]);
         }
-        if (MODE == 1) ptx::tmem_st_32x16(tmem + lane_base + kColS + c * 16, pk_p);
-        ptx::tmem_st_32x16(tmem + lane_base + kColDP + c * 16, pk_d);
+        if (MODE == 1) {
+          ptx::tmem_st_32x16p(tmem + lane_base + kColS + c2 * 32, rs);
+          ptx::tmem_st_32x16p(tmem + lane_base + kColS + c2 * 32 + 16, rs + 16);
+        }
+        ptx::tmem_st_32x16p(tmem + lane_base + kColDP + c2 * 32, rd);
+        ptx::tmem_st_32x16p(tmem + lane_base + kColDP + c2 * 32 + 16, rd + 16);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();

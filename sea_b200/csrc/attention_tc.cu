@@ -183,71 +183,59 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
       ptx::mbar_wait(s_full, j & 1);
       ptx::tc_fence_after();
       const bool need_mask = (kv0 + BKV - 1 > q0 + pp.src_len) || (kv0 + BKV > pp.T);
-      // pass 1: row max of the scaled, masked scores
-      float mx = -INFINITY;
+      // the whole score row of this tile in registers: ONE TMEM round trip (all loads in flight)
+      uint32_t r[BKV];
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem + lane_base + kColS + c * 32, r);
-        ptx::tmem_ld_wait();
+      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld_32x32p(tmem + lane_base + kColS + c * 32, r + c * 32);
+      ptx::tmem_ld_wait();
+      float mx = -INFINITY;   // max of the RAW scores (scale > 0 commutes with max)
+      if (need_mask) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float sv = __uint_as_float(r[e]) * pp.scale_log2;
-          if (need_mask) {
-            const int kk = kv0 + c * 32 + e;
-            if (kk > q + pp.src_len || kk >= pp.T) sv = -INFINITY;
-          }
-          mx = fmaxf(mx, sv);
+        for (int e = 0; e < BKV; ++e) {
+          const int kk = kv0 + e;
+          if (kk > q + pp.src_len || kk >= pp.T) r[e] = 0xff800000u;  // -inf
+          mx = fmaxf(mx, __uint_as_float(r[e]));
         }
+      } else {
+#pragma unroll
+        for (int e = 0; e < BKV; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
       }
-      const float m_cand = fmaxf(m_ref, mx);
+      const float m_cand = fmaxf(m_ref, mx * pp.scale_log2);
       const bool grow = (m_cand > m_ref + 8.0f) || (m_ref == -INFINITY && m_cand != -INFINITY);
       const bool any_grow = __any_sync(0xffffffffu, grow);
-      if (j > 0) {  // P and O are owned by the previous P·V until it retires
+      if (j > 0) {  // O is owned by the previous P·V until it retires
         ptx::mbar_wait(o_done, (j - 1) & 1);
         ptx::tc_fence_after();
       }
       if (any_grow) {
-        const float m_new = m_cand;
-        const float alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
+        const float alpha = (m_ref == -INFINITY) ? 0.f : ptx::ex2(m_ref - m_cand);
         l_sum *= alpha;
-        m_ref = m_new;
+        m_ref = m_cand;
         if (j > 0) {
 #pragma unroll
           for (int c = 0; c < HD / 32; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(tmem + lane_base + kColO + c * 32, r);
+            uint32_t o[32];
+            ptx::tmem_ld_32x32(tmem + lane_base + kColO + c * 32, o);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-            ptx::tmem_st_32x32(tmem + lane_base + kColO + c * 32, r);
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            ptx::tmem_st_32x32(tmem + lane_base + kColO + c * 32, o);
           }
         }
       }
-      // pass 2: p = exp2(s - m_ref), row sum, bf16 pack into TMEM
-      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+      // p = 2^(s * scale_log2 - m): one FFMA + one MUFU per score; packed bf16 pairs overwrite S
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem + lane_base + kColS + c * 32, r);
-        ptx::tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float s0 = __uint_as_float(r[e]) * pp.scale_log2;
-          float s1 = __uint_as_float(r[e + 1]) * pp.scale_log2;
-          if (need_mask) {
-            const int kk = kv0 + c * 32 + e;
-            if (kk > q + pp.src_len || kk >= pp.T) s0 = -INFINITY;
-            if (kk + 1 > q + pp.src_len || kk + 1 >= pp.T) s1 = -INFINITY;
-          }
-          const float p0 = exp2f(s0 - m_use);
-          const float p1 = exp2f(s1 - m_use);
-          l_sum += p0 + p1;
-          pk[e >> 1] = ptx::pack_bf16(p0, p1);
-        }
-        ptx::tmem_st_32x16(tmem + lane_base + kColP + c * 16, pk);
+      for (int e = 0; e < BKV; e += 2) {
+        const float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), pp.scale_log2, neg_m));
+        const float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), pp.scale_log2, neg_m));
+        l0 += p0; l1 += p1;
+        r[e >> 1] = ptx::pack_bf16(p0, p1);
       }
+      l_sum += l0 + l1;
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_st_32x16p(tmem + lane_base + kColP + c * 16, r + c * 16);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
@@ -285,6 +273,293 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, C::TMEM_COLS);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two query tiles per CTA (T > 128, HD <= 128): the tensor pipe and the softmax warps overlap.
+//   warp 0      TMA (Q for 256 query rows once, K_j / V_j ring of 2 stages)
+//   warp 1      tcgen05.mma issue, interleaved so each softmax group always has its next S ready:
+//                 S0_0, S1_0, then per key tile j:  [P0_j ready] PV0_j, S0_{j+1}   [P1_j ready] PV1_j, S1_{j+1}
+//   warps 2..5  softmax group 0 (query rows q0 .. q0+127),  warps 6..9  group 1 (q0+128 .. q0+255)
+// While group 0 exponentiates tile j the pipe computes S1_j / PV1_{j-1}, and vice versa.  Because the
+// MMAs execute in issue order, "S_g(j) complete" implies "PV_g(j-1) complete": a group may rescale its
+// O accumulator as soon as it sees its next S, no extra barrier.
+// TMEM columns: S0|P0 [0,128)  S1|P1 [128,256)  O0 [256,256+HD)  O1 [384,384+HD).
+constexpr int kThreads2 = 320;
+
+template <int HD>
+struct ACfg2 {
+  static constexpr int BKV = 128;
+  static constexpr int ATOMS = HD / 64;
+  static constexpr int Q_BYTES = 2 * BQ * HD * 2;
+  static constexpr int KV_BYTES = BKV * HD * 2;
+  static constexpr int SMEM = Q_BYTES + 2 * 2 * KV_BYTES + 1024 + 128;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid_constant__ AttnTcParams pp) {
+  using C = ACfg2<HD>;
+  constexpr int BKV = C::BKV;
+  const AttnTcItem& p = pp.it[blockIdx.z / pp.B];
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                                   // [ATOMS][256 rows][128 B]
+  uint8_t* sK = sQ + C::Q_BYTES;                        // [2][KV_BYTES]
+  uint8_t* sV = sK + 2 * C::KV_BYTES;                   // [2][KV_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * C::KV_BYTES);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* kv_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;      // [2] per group: MMA -> softmax
+  uint64_t* p_full = bars + 7;      // [2] per group: softmax (128 arrivals) -> MMA
+  uint64_t* o_done = bars + 9;      // [2] per group: MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int qb = gridDim.x - 1 - blockIdx.x;  // heavy (late) query blocks first
+  const int h = blockIdx.y, b = blockIdx.z % pp.B;
+  const int q0 = qb * 2 * BQ;
+  int n_kv[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int qg0 = q0 + g * BQ;
+    n_kv[g] = qg0 < pp.T ? min(pp.T - 1, min(pp.T - 1, qg0 + BQ - 1) + pp.src_len) / BKV + 1 : 0;
+  }
+  const int n_tot = max(n_kv[0], n_kv[1]);
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&p.tq);
+    ptx::prefetch_tmap(&p.tk);
+    ptx::prefetch_tmap(&p.tv);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], 1);
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&p_full[s], 128);
+      ptx::mbar_init(&o_done[s], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
+      for (int a = 0; a < C::ATOMS; ++a) {
+        ptx::tma_load_3d(sQ + a * (2 * BQ * 128), &p.tq, q_full, h * HD + a * 64, q0, b);
+        ptx::tma_load_3d(sQ + a * (2 * BQ * 128) + BQ * 128, &p.tq, q_full, h * HD + a * 64, q0 + BQ, b);
+      }
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tot; ++j) {
+      const int s = j & 1;
+      ptx::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(&kv_full[s], 2 * C::KV_BYTES);
+#pragma unroll
+        for (int a = 0; a < C::ATOMS; ++a) {
+          ptx::tma_load_3d(sK + s * C::KV_BYTES + a * (BKV * 128), &p.tk, &kv_full[s], h * HD + a * 64, j * BKV, b);
+          ptx::tma_load_3d(sV + s * C::KV_BYTES + a * (BKV * 128), &p.tv, &kv_full[s], h * HD + a * 64, j * BKV, b);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
+    const uint32_t qbase = ptx::smem_u32(sQ);
+    auto issue_s = [&](int g, int s) {   // S_g = Q_g K^T into columns [g*128, g*128+128)
+      const uint32_t kb = ptx::smem_u32(sK + s * C::KV_BYTES);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) {
+        const uint32_t qoff = (k >> 2) * (2 * BQ * 128) + g * (BQ * 128) + (k & 3) * 32;
+        const uint32_t koff = (k >> 2) * (BKV * 128) + (k & 3) * 32;
+        ptx::umma_f16_ss(tmem + g * 128, ptx::umma_smem_desc(qbase + qoff, 16, 1024),
+                         ptx::umma_smem_desc(kb + koff, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+      }
+      ptx::umma_commit(&s_full[g]);
+    };
+    auto issue_pv = [&](int g, int s, int j) {   // O_g (+)= P_g V
+      const uint32_t vb = ptx::smem_u32(sV + s * C::KV_BYTES);
+#pragma unroll
+      for (int k = 0; k < BKV / 16; ++k)
+        ptx::umma_f16_ts(tmem + 256 + g * 128, tmem + g * 128 + k * 8,
+                         ptx::umma_smem_desc(vb + k * 2048, BKV * 128, 1024), idesc_o, (j | k) != 0 ? 1u : 0u);
+    };
+    ptx::mbar_wait(q_full, 0);
+    ptx::mbar_wait(&kv_full[0], 0);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
+      if (n_kv[0] > 0) issue_s(0, 0);
+      if (n_kv[1] > 0) issue_s(1, 0);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tot; ++j) {
+      const int s = j & 1, sn = (j + 1) & 1;
+      const bool more = j + 1 < n_tot;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (j < n_kv[g]) {
+          ptx::mbar_wait(&p_full[g], j & 1);
+          if (j + 1 < n_kv[g]) ptx::mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            issue_pv(g, s, j);
+            if (j + 1 < n_kv[g]) issue_s(g, sn);
+            else ptx::umma_commit(&o_done[g]);
+          }
+          __syncwarp();
+        }
+      }
+      (void)more;
+      if (ptx::elect_one()) ptx::umma_commit(&kv_empty[s]);
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax groups
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int qg0 = q0 + g * BQ;
+    const int q = qg0 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t colS = g * 128, colO = 256 + g * 128;
+    const int n_mine = n_kv[g];
+    float m_ref = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < n_mine; ++j) {
+      const int kv0 = j * BKV;
+      ptx::mbar_wait(&s_full[g], j & 1);
+      ptx::tc_fence_after();
+      const bool need_mask = (kv0 + BKV - 1 > qg0 + pp.src_len) || (kv0 + BKV > pp.T);
+      // the whole score row of this tile in registers: ONE TMEM round trip (four loads in flight)
+      uint32_t r[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld_32x32p(tmem + lane_base + colS + c * 32, r + c * 32);
+      ptx::tmem_ld_wait();
+      float mx = -INFINITY;   // max of the RAW scores (scale > 0 commutes with max)
+      if (need_mask) {
+#pragma unroll
+        for (int e = 0; e < BKV; ++e) {
+          const int kk = kv0 + e;
+          if (kk > q + pp.src_len || kk >= pp.T) r[e] = 0xff800000u;  // -inf
+          mx = fmaxf(mx, __uint_as_float(r[e]));
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < BKV; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+      }
+      const float m_cand = fmaxf(m_ref, mx * pp.scale_log2);
+      const bool grow = (m_cand > m_ref + 8.0f) || (m_ref == -INFINITY && m_cand != -INFINITY);
+      if (__any_sync(0xffffffffu, grow)) {
+        // S_g(j) complete => PV_g(j-1) complete (issue order): O_g may be rescaled right here
+        const float alpha = (m_ref == -INFINITY) ? 0.f : ptx::ex2(m_ref - m_cand);
+        l_sum *= alpha;
+        m_ref = m_cand;
+        if (j > 0) {
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o[32];
+            ptx::tmem_ld_32x32(tmem + lane_base + colO + c * 32, o);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            ptx::tmem_st_32x32(tmem + lane_base + colO + c * 32, o);
+          }
+        }
+      }
+      // p = 2^(s * scale_log2 - m): one FFMA + one MUFU per score; packed bf16 pairs overwrite S
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < BKV; e += 2) {
+        const float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), pp.scale_log2, neg_m));
+        const float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), pp.scale_log2, neg_m));
+        l0 += p0; l1 += p1;
+        r[e >> 1] = ptx::pack_bf16(p0, p1);
+      }
+      l_sum += l0 + l1;
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_st_32x16p(tmem + lane_base + colS + c * 16, r + c * 16);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&p_full[g]);
+    }
+    if (n_mine > 0) {
+      ptx::mbar_wait(&o_done[g], 0);
+      ptx::tc_fence_after();
+      const float inv = 1.f / l_sum;
+      __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * pp.T + q) * pp.ldo + h * HD;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem + lane_base + colO + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (q < pp.T) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            uint4 o;
+            o.x = ptx::pack_bf16(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+            o.y = ptx::pack_bf16(__uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv);
+            o.z = ptx::pack_bf16(__uint_as_float(r[e + 4]) * inv, __uint_as_float(r[e + 5]) * inv);
+            o.w = ptx::pack_bf16(__uint_as_float(r[e + 6]) * inv, __uint_as_float(r[e + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 32 + e) = o;
+          }
+        }
+      }
+      if (p.lse != nullptr && q < pp.T)
+        p.lse[(static_cast<long long>(b) * pp.n_heads + h) * pp.T + q] =
+            (m_ref + log2f(l_sum)) * 0.69314718055994530942f;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int HD>
+int launch_tc2(int n, const sea_attn_args* a, cudaStream_t s) {
+  using C = ACfg2<HD>;
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    SEA_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set[dev] = true;
+  }
+  AttnTcParams p;
+  const uint64_t wq = static_cast<uint64_t>(a->n_heads) * HD;
+  for (int i = 0; i < n; ++i) {
+    const sea_attn_args& x = a[i];
+    int rc = make_tmap_bf16_3d(&p.it[i].tq, x.q, wq, x.T, x.B, x.ldq, x.ldq * static_cast<uint64_t>(x.T), 64, BQ);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&p.it[i].tk, x.k, wq, x.T, x.B, x.ldk, x.ldk * static_cast<uint64_t>(x.T), 64, C::BKV);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d(&p.it[i].tv, x.v, wq, x.T, x.B, x.ldv, x.ldv * static_cast<uint64_t>(x.T), 64, C::BKV);
+    if (rc) return rc;
+    p.it[i].o = static_cast<__nv_bfloat16*>(x.o);
+    p.it[i].lse = x.lse;
+  }
+  p.ldo = a->ldo;
+  p.B = a->B; p.T = a->T; p.n_heads = a->n_heads; p.src_len = a->src_len;
+  p.scale_log2 = a->scale * 1.44269504088896340736f;
+  dim3 grid((a->T + 2 * BQ - 1) / (2 * BQ), a->n_heads, a->B * n);
+  SEA_LAUNCH((attn_fwd_tc2_kernel<HD>), grid, kThreads2, C::SMEM, s, p);
+  return static_cast<int>(cudaGetLastError());
 }
 
 template <int HD, int BKV, int STAGES_>
@@ -333,14 +608,18 @@ bool attention_tc_supported(const sea_attn_args* a) {
   return true;
 }
 
+int g_attn_two_tiles = 1;  // tuning hook: 0 = one query tile per CTA also for long sequences
+
 // n same-shape problems (B, T, n_heads, head_dim, src_len, scale, ldo equal; checked by the caller)
 int attention_fwd_tc(int n, const sea_attn_args* a, cudaStream_t s) {
   int rc = ensure_init();
   if (rc) return rc;
   const int k_last = (a->T - 1 + a->src_len < a->T - 1) ? a->T - 1 + a->src_len : a->T - 1;
   switch (a->head_dim) {
-    case 64: return k_last < 128 ? launch_tc<64, 128, 1>(n, a, s) : launch_tc<64, 128, 2>(n, a, s);
-    case 128: return k_last < 128 ? launch_tc<128, 128, 1>(n, a, s) : launch_tc<128, 128, 2>(n, a, s);
+    case 64: return k_last < 128 ? launch_tc<64, 128, 1>(n, a, s)
+                                 : (g_attn_two_tiles ? launch_tc2<64>(n, a, s) : launch_tc<64, 128, 2>(n, a, s));
+    case 128: return k_last < 128 ? launch_tc<128, 128, 1>(n, a, s)
+                                  : (g_attn_two_tiles ? launch_tc2<128>(n, a, s) : launch_tc<128, 128, 2>(n, a, s));
     case 256: return k_last < 64 ? launch_tc<256, 64, 1>(n, a, s) : launch_tc<256, 64, 2>(n, a, s);
     default: return SEA_ERR_UNSUPPORTED;
   }
