@@ -271,6 +271,14 @@ def main():
     h2d = x0_h.numel() * 4 + ib_h.numel() * 4
     d2h = out_h.numel() * 4
 
+    # ---- KV-cached incremental engine (opt-in, NOT the headline): same trajectories ----
+    pred_prefix = rollout(model, x0, ib, R)
+    for _ in range(2):
+        pred_cached = rollout(model, x0, ib, R, cached=True)
+    cached_rel = ((pred_cached - pred_prefix).norm() / pred_prefix.norm()).item()
+    ms_cached = timed(lambda: rollout(model, x0, ib, R, cached=True, _view_ok=True), args.steps)
+    del pred_prefix, pred_cached
+
     # ---- roofline leg: one more rollout with per-launch CUDA events on the launch stream ----
     pk = peaks()
     with profile() as prof:
@@ -323,6 +331,11 @@ def main():
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
+        "cached_rollout": {"value": world * B * R / (ms_cached / 1e3), "unit": UNIT, "ms_per_step": ms_cached,
+                           "rel_l2_vs_prefix_loop": cached_rel,
+                           "note": "opt-in KV-cached engine (sea_temporal_step): O(1) work per step instead of "
+                                   "the reference loop's prefix recompute; same outputs up to rounding; "
+                                   "not the headline value"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
     }

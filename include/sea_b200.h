@@ -86,6 +86,9 @@ typedef struct sea_gemm_epilogue {
   int64_t ld_out_pre_bf16;
   void* out_bf16;
   int64_t ld_out_bf16;
+  int32_t rope_pos0;        /* position of row m is rope_pos0 + (m % seq_len): the incremental (KV-cached)
+                               step rotates its single new token by its absolute position */
+  int32_t reserved0;
 } sea_gemm_epilogue;
 
 typedef struct sea_gemm_problem {
@@ -306,6 +309,21 @@ int sea_attention_fwd(const sea_attn_args* args, sea_stream_t stream);
  * prec, ldo) in ONE launch: the self-attention of the V independent field streams
  * (models/temporal.py:135-136 runs them one after the other). */
 int sea_attention_fwd_group(int n, const sea_attn_args* host_args, sea_stream_t stream);
+/* Decode attention for the KV-cached incremental step: ONE new query per (trajectory, head) against
+ * the cached keys / values 0 .. n_keys-1 (the last row of the causal attention above).  q, o: one row
+ * per trajectory (pitch ldq / ldo); k, v: [B, *, cols] caches with position pitch ldk / ldv and
+ * trajectory pitch k/v_batch_stride.  `n` same-shape problems per launch. */
+typedef struct sea_attn_decode_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  int64_t ldq, ldo, ldk, ldv, k_batch_stride, v_batch_stride;
+  int32_t B, n_keys, n_heads, head_dim;
+  float scale;
+  int32_t prec;
+} sea_attn_decode_args;
+int sea_attention_decode_group(int n, const sea_attn_decode_args* host_args, sea_stream_t stream);
 /* K3: backward of sea_attention_fwd.  d_o is the gradient of o; delta [B,n_heads,T] is scratch.
  * dq/dk/dv use the same row/head layout.  If rope_table is given, dq and dk are rotated back by
  * -theta (the forward RoPE lives in the projection GEMM epilogue), so they are gradients with
@@ -443,6 +461,20 @@ size_t sea_temporal_workspace_bytes(const sea_temporal_desc* d, int B, int T, in
 int sea_temporal_forward(const sea_temporal_desc* d, const void* cache, const float* x,
                          const float* ib, float* y, int B, int T, void* workspace,
                          size_t workspace_bytes, int training, sea_stream_t stream);
+/* KV-cached incremental step (the rollout loop of utils/train_utils.py:202-209 without the O(n^2)
+ * prefix recompute): feeds ONE new token per trajectory, x_t [B,V,E] at absolute position `pos`, and
+ * returns y_t = TemporalModel.forward(x[:, :pos+1])[:, pos].  Exact for a causal model: positions
+ * 0..pos-1 must have been fed before with the same kv_cache (sea_temporal_kv_cache_bytes(d, B, max_len)
+ * bytes, caller-owned; holds the RoPE'd q|k|v rows of the self-attention and the k|v rows of every
+ * state-exchange pair).  x_t / ib_t / y_t are addressed with a pitch between trajectories, so they can
+ * be slices of a [B, T, ...] sequence buffer.  Workspace: sea_temporal_workspace_bytes(d, B, 1, 0).
+ * With d->ib_time_invariant and a cond_cache the AdaLN / TIPI condition path is evaluated once per
+ * trajectory (cond_cache_valid as for sea_temporal_forward). */
+size_t sea_temporal_kv_cache_bytes(const sea_temporal_desc* d, int B, int max_len);
+int sea_temporal_step(const sea_temporal_desc* d, const void* cache, void* kv_cache, size_t kv_cache_bytes,
+                      int max_len, const float* x_t, int64_t x_batch_stride, const float* ib_t,
+                      int64_t ib_batch_stride, float* y_t, int64_t y_batch_stride, int B, int pos,
+                      void* workspace, size_t workspace_bytes, sea_stream_t stream);
 /* Backward of the last sea_temporal_forward(..., training=1) that used this `workspace`
  * (autograd in the reference, train/train_temporal.py:257).  dy [B,T,V,E] fp32 contiguous.
  * Parameter gradients ACCUMULATE (+=) into the `g` pointers of the descriptor (NULL = frozen);

@@ -182,6 +182,20 @@ def run_rollout():
     for i in range(0, R, 5):
         print(f"graph   t={i+1:3d} M={B*(i+1):5d}: device {devg[i]:7.1f} us  nodes {plan.launches[i]}")
     print(f"sum graph device {sum(devg)/1e3:.2f} ms")
+    # KV-cached incremental engine
+    from sea_b200.rollout import CachedRolloutPlan
+    cp = CachedRolloutPlan(m, B, R, dev, True)
+    cp.run(x0, ib)
+    torch.cuda.synchronize()
+    evs[0].record()
+    for i, g in enumerate(cp.graphs):
+        g.replay()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    devc = [evs[i].elapsed_time(evs[i + 1]) * 1e3 for i in range(R)]
+    for i in range(0, R, 10):
+        print(f"cached  t={i+1:3d}: device {devc[i]:7.1f} us  nodes {cp.launches[i]}")
+    print(f"sum cached device {sum(devc)/1e3:.2f} ms")
 
 
 

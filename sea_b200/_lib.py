@@ -36,6 +36,8 @@ class GemmEpilogue(C.Structure):
         ("ld_out_pre_bf16", C.c_int64),
         ("out_bf16", C.c_void_p),
         ("ld_out_bf16", C.c_int64),
+        ("rope_pos0", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -67,7 +69,8 @@ class _Lazy:
             dll = C.CDLL(LIB_PATH)
             dll.sea_strerror.restype = C.c_char_p
             dll.sea_strerror.argtypes = [C.c_int]
-            for fn in ("sea_temporal_cache_bytes", "sea_temporal_workspace_bytes", "sea_temporal_cond_cache_bytes"):
+            for fn in ("sea_temporal_cache_bytes", "sea_temporal_workspace_bytes", "sea_temporal_cond_cache_bytes",
+                       "sea_temporal_kv_cache_bytes"):
                 if hasattr(dll, fn):
                     getattr(dll, fn).restype = C.c_size_t
             if os.environ.get("SEA_B200_PDL", "1") == "0":   # A/B switch for programmatic dependent launch

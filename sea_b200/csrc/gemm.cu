@@ -41,7 +41,7 @@ struct DevEpilogue {
   __nv_bfloat16* out_pre_bf16;
   __nv_bfloat16* out_bf16;
   long long ld_residual, ld_gelu, ld_out_f32, ld_out_pre_bf16, ld_out_bf16;
-  int act, rope_cols, head_dim, seq_len, rope_ld;
+  int act, rope_cols, head_dim, seq_len, rope_ld, rope_pos0;
   float rope_sign;
   int vec8;  // every row base / pitch is 32-byte aligned: use 256-bit global accesses
 };
@@ -158,7 +158,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
     // models/base_blocks.py:314-324 — interleaved pairs (x[2k], x[2k+1]) times (cos + i sin).
     // table is pair-major: tab[pair][t]; the 32 lanes of a warp hold consecutive rows, i.e.
     // consecutive t, so every load instruction reads one contiguous 256-byte run
-    const int t = m % e.seq_len;
+    const int t = e.rope_pos0 + m % e.seq_len;
     const int d0 = n0 % e.head_dim;
     const float2* tab = reinterpret_cast<const float2*>(e.rope_table) +
                         static_cast<long long>(d0 >> 1) * e.rope_ld + t;
@@ -602,7 +602,7 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
     if (e.bias && (reinterpret_cast<uintptr_t>(e.bias) & 15)) return SEA_ERR_INVALID;
     if (e.rope_table != nullptr && e.rope_cols > 0) {
       if (e.head_dim <= 0 || (e.head_dim % 32) || (e.rope_cols % e.head_dim) || e.seq_len <= 0 ||
-          e.rope_ld < e.seq_len)
+          e.rope_pos0 < 0 || e.rope_ld < e.rope_pos0 + e.seq_len)
         return SEA_ERR_UNSUPPORTED;
     }
     // K-major operand: boxes of 64 k-columns x BM / BN rows; MN-major: 64 M/N-columns x BK k-rows
@@ -630,6 +630,7 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
     d.head_dim = e.head_dim;
     d.seq_len = e.seq_len;
     d.rope_ld = e.rope_ld;
+    d.rope_pos0 = e.rope_pos0;
     d.rope_sign = (e.rope_sign == 0.0f) ? 1.0f : e.rope_sign;
     auto al32 = [](const void* ptr, long long ld_elems, int esz) {
       return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr) & 31) == 0) && ((ld_elems * esz) % 32 == 0));

@@ -366,6 +366,7 @@ int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, c
     if (o.rope_cols > 0) {
       e.rope_cols = o.rope_cols; e.head_dim = o.head_dim; e.seq_len = c.T;
       e.rope_table = o.rope_table; e.rope_sign = 1.f; e.rope_ld = c.d->max_len;
+      e.rope_pos0 = c.pos0;
     }
     if (c.fp32) {
       // exactly one fp32 destination in the parity mode
@@ -403,7 +404,7 @@ NormCall norm_call(Ctx& c, int kind, const sea_norm_params& np, const float* con
   a.weight = np.weight.p;
   a.bias = kind == SEA_NORM_ADALN ? np.bias.p : nullptr;
   a.cond = cond; a.ldc = 2LL * dim; a.cond_div = c.cond_div;
-  if (tipi && c.cond_div > 1) {
+  if (tipi && c.inv) {
     a.add_rows = tipi_g; a.ld_add = dim; a.add_div = c.cond_div;  // tipi_g = per-trajectory TIPI rows
     a.x_out = x_out; a.ldxo = dim;
   } else if (tipi) {
@@ -441,6 +442,23 @@ sea_attn_args attn_call(Ctx& c, const void* q, long long ldq, const void* k, con
   a.scale = 1.0f / sqrtf(static_cast<float>(head_dim));
   a.prec = c.fp32 ? SEA_PREC_FP32 : SEA_PREC_BF16;
   return a;
+}
+
+sea_attn_decode_args decode_call(Ctx& c, const void* q, long long ldq, const void* k, const void* v, long long ldkv,
+                                 long long kv_bs, void* o, long long ldo, int n_keys, int head_dim) {
+  sea_attn_decode_args a{};
+  a.q = q; a.k = k; a.v = v; a.o = o;
+  a.ldq = ldq; a.ldo = ldo; a.ldk = ldkv; a.ldv = ldkv; a.k_batch_stride = kv_bs; a.v_batch_stride = kv_bs;
+  a.B = c.B; a.n_keys = n_keys; a.n_heads = c.d->n_heads; a.head_dim = head_dim;
+  a.scale = 1.0f / sqrtf(static_cast<float>(head_dim));
+  a.prec = c.fp32 ? SEA_PREC_FP32 : SEA_PREC_BF16;
+  return a;
+}
+
+int decode_group(Ctx& c, int n, const sea_attn_decode_args* a) {
+  ++g_launches;
+  ProfScope prof(c.s, SEA_PROF_ATTN, 4.0 * n * c.B * c.d->n_heads * static_cast<double>(a[0].n_keys) * a[0].head_dim);
+  return sea_attention_decode_group(n, a, reinterpret_cast<sea_stream_t>(c.s));
 }
 
 int attention_group(Ctx& c, int n, const sea_attn_args* a) {
@@ -496,9 +514,76 @@ extern "C" size_t sea_temporal_workspace_bytes(const sea_temporal_desc* d, int B
   return ar.off + 256;
 }
 
+// ------------------------------------------------------------------ KV-cached incremental step
+// What a later position needs from earlier ones (everything else on the path is per token):
+//   self-attention   q|k|v rows of every stream           [B, max_len, 3E]   (RoPE'd q, k)
+//   exchange         k|v rows of every ordered pair (i,j)  [B, max_len, 2Dd]
+// in the activation dtype of the precision mode.  Position t of trajectory b is row b*max_len + t.
+namespace sea {
+struct KvLayout {
+  struct S { void* qkv; void* kvc[SEA_MAX_STREAMS]; };
+  std::vector<S> L;  // [num_layers * num_streams]
+};
+static void layout_kv(const sea_temporal_desc* d, int B, int max_len, Arena& ar, KvLayout& kv) {
+  const size_t esz = d->precision == SEA_PREC_FP32 ? 4 : 2;
+  const size_t rows = static_cast<size_t>(B) * max_len;
+  const int V = d->num_streams;
+  kv.L.assign(static_cast<size_t>(d->num_layers) * V, KvLayout::S{});
+  for (int l = 0; l < d->num_layers; ++l)
+    for (int i = 0; i < V; ++i) {
+      KvLayout::S& s = kv.L[static_cast<size_t>(l) * V + i];
+      s.qkv = ar.take(rows * 3 * d->embed_dim * esz);
+      for (int j = 0; j < V; ++j)
+        if (j != i) s.kvc[j] = ar.take(rows * 2 * d->down_dim * esz);
+    }
+}
+struct StepCtx {
+  const KvLayout* kv;
+  int pos;       // absolute position of the single new token
+  int max_len;   // positions per trajectory in the caches
+  long long x_bs, ib_bs, y_bs;  // pitches between trajectories of x_t / ib_t / y_t (elements)
+};
+}  // namespace sea
+
+extern "C" size_t sea_temporal_kv_cache_bytes(const sea_temporal_desc* d, int B, int max_len) {
+  if (!d || B <= 0 || max_len <= 0) return 0;
+  Arena ar{nullptr};
+  KvLayout kv;
+  layout_kv(d, B, max_len, ar, kv);
+  return ar.off + 256;
+}
+
+static int forward_impl(const sea_temporal_desc* d, const void* cache, const float* x, const float* ib, float* y,
+                        int B, int T, void* workspace, size_t workspace_bytes, int training,
+                        const StepCtx* step, sea_stream_t stream);
+
 extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cache, const float* x,
                                     const float* ib, float* y, int B, int T, void* workspace,
                                     size_t workspace_bytes, int training, sea_stream_t stream) {
+  return forward_impl(d, cache, x, ib, y, B, T, workspace, workspace_bytes, training, nullptr, stream);
+}
+
+extern "C" int sea_temporal_step(const sea_temporal_desc* d, const void* cache, void* kv_cache,
+                                 size_t kv_cache_bytes, int max_len, const float* x_t, int64_t x_batch_stride,
+                                 const float* ib_t, int64_t ib_batch_stride, float* y_t, int64_t y_batch_stride,
+                                 int B, int pos, void* workspace, size_t workspace_bytes, sea_stream_t stream) {
+  if (!d || !kv_cache || max_len <= 0 || pos < 0 || pos >= max_len) return SEA_ERR_INVALID;
+  if (max_len > d->max_len) return SEA_ERR_UNSUPPORTED;
+  if (kv_cache_bytes < sea_temporal_kv_cache_bytes(d, B, max_len)) return SEA_ERR_WORKSPACE;
+  const int V = d->num_streams;
+  if (x_batch_stride < static_cast<int64_t>(V) * d->embed_dim || (x_batch_stride % 4) ||
+      y_batch_stride < static_cast<int64_t>(V) * d->embed_dim || (y_batch_stride % 4) || ib_batch_stride < d->ib_num)
+    return SEA_ERR_INVALID;
+  Arena ar{static_cast<char*>(kv_cache)};
+  KvLayout kv;
+  layout_kv(d, B, max_len, ar, kv);
+  StepCtx sc{&kv, pos, max_len, x_batch_stride, ib_batch_stride, y_batch_stride};
+  return forward_impl(d, cache, x_t, ib_t, y_t, B, 1, workspace, workspace_bytes, 0, &sc, stream);
+}
+
+static int forward_impl(const sea_temporal_desc* d, const void* cache, const float* x, const float* ib, float* y,
+                        int B, int T, void* workspace, size_t workspace_bytes, int training,
+                        const StepCtx* step, sea_stream_t stream) {
   SEA_TRY(validate_desc(d));
   if (!cache || !x || !ib || !y || !workspace || B <= 0 || T <= 0) return SEA_ERR_INVALID;
   if (T > d->max_len) return SEA_ERR_UNSUPPORTED;
@@ -519,10 +604,12 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
   c.s = reinterpret_cast<cudaStream_t>(stream);
   c.fp32 = d->precision == SEA_PREC_FP32;
   c.B = B; c.T = T; c.M = B * T;
+  c.pos0 = step ? step->pos : 0;
   // time-invariant condition (inference): one cond / TIPI row per trajectory instead of per token
-  const bool inv = d->ib_time_invariant != 0 && training == 0 && T > 1;
+  const bool inv = d->ib_time_invariant != 0 && training == 0 && (T > 1 || step != nullptr);
+  c.inv = inv;
   c.Mc = inv ? B : c.M;
-  c.ld_ib = inv ? static_cast<long long>(T) * d->ib_num : d->ib_num;
+  c.ld_ib = step ? step->ib_bs : (inv ? static_cast<long long>(T) * d->ib_num : d->ib_num);
   c.cond_div = inv ? T : 1;
   const int M = c.M, V = d->num_streams, E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
   const int hd = E / d->n_heads, hdc = Dd / d->n_heads;
@@ -591,7 +678,7 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
 
   // ---- layers ----
   const float* xin[SEA_MAX_STREAMS];
-  long long ldxin = static_cast<long long>(V) * E;
+  long long ldxin = step ? step->x_bs : static_cast<long long>(V) * E;   // step mode: one row per trajectory
   for (int i = 0; i < V; ++i) xin[i] = x + static_cast<long long>(i) * E;  // x[:, :, i, :]
 
   for (int l = 0; l < d->num_layers; ++l) {
@@ -614,16 +701,31 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
       W[i] = &bc.s[i].qkv;
       out[i] = LinOut{};
       out[i].bias = bc.s[i].qkv_bias;
-      out[i].post = lt.s[i].qkv; out[i].ld_post = 3 * E;
+      if (step) {  // the new row goes straight into the cache: [b, pos, :]
+        char* row = static_cast<char*>(step->kv->L[static_cast<size_t>(l) * V + i].qkv) + esz * 3 * E * step->pos;
+        out[i].post = row; out[i].ld_post = 3LL * E * step->max_len;
+      } else {
+        out[i].post = lt.s[i].qkv; out[i].ld_post = 3 * E;
+      }
       out[i].rope_cols = 2 * E; out[i].head_dim = hd; out[i].rope_table = d->rope_self;
     }
     SEA_TRY(linear_group(c, V, in, W, out, M));
-    for (int i = 0; i < V; ++i) {
-      char* base = static_cast<char*>(lt.s[i].qkv);
-      acall[i] = attn_call(c, base, 3 * E, base + esz * E, base + esz * 2 * E, 3 * E, lt.s[i].ao, E,
-                           lt.s[i].lse, hd);
+    if (step) {
+      sea_attn_decode_args dc[SEA_MAX_STREAMS];
+      for (int i = 0; i < V; ++i) {
+        char* base = static_cast<char*>(step->kv->L[static_cast<size_t>(l) * V + i].qkv);
+        dc[i] = decode_call(c, base + esz * 3 * E * step->pos, 3LL * E * step->max_len, base + esz * E,
+                            base + esz * 2 * E, 3 * E, 3LL * E * step->max_len, lt.s[i].ao, E, step->pos + 1, hd);
+      }
+      SEA_TRY(decode_group(c, V, dc));
+    } else {
+      for (int i = 0; i < V; ++i) {
+        char* base = static_cast<char*>(lt.s[i].qkv);
+        acall[i] = attn_call(c, base, 3 * E, base + esz * E, base + esz * 2 * E, 3 * E, lt.s[i].ao, E,
+                             lt.s[i].lse, hd);
+      }
+      SEA_TRY(attention_group(c, V, acall));
     }
-    SEA_TRY(attention_group(c, V, acall));
     for (int i = 0; i < V; ++i) {
       in[i] = LinIn{lt.s[i].ao, E, 0};
       W[i] = &bc.s[i].sproj;
@@ -681,8 +783,13 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
           SEA_TRY(push(s.npre, bc.s[i].cq[j], 0, bp.s[i].cross_attn[j].q_b.p, s.q[j], Dd, true));
           if (j > i) {
             char* kvb = static_cast<char*>(s.kv[j]);
-            SEA_TRY(push(lt.s[j].npre, bc.s[i].ckv[j], 0, bc.s[i].ckv_bias[j], kvb, 2 * Dd, true));
-            SEA_TRY(push(lt.s[j].npre, bc.s[i].ckv[j], Dd, bc.s[i].ckv_bias[j] + Dd, kvb + esz * Dd, 2 * Dd, false));
+            long long ldkv = 2 * Dd;
+            if (step) {
+              kvb = static_cast<char*>(step->kv->L[static_cast<size_t>(l) * V + i].kvc[j]) + esz * 2 * Dd * step->pos;
+              ldkv = 2LL * Dd * step->max_len;
+            }
+            SEA_TRY(push(lt.s[j].npre, bc.s[i].ckv[j], 0, bc.s[i].ckv_bias[j], kvb, ldkv, true));
+            SEA_TRY(push(lt.s[j].npre, bc.s[i].ckv[j], Dd, bc.s[i].ckv_bias[j] + Dd, kvb + esz * Dd, ldkv, false));
           }
         }
       }
@@ -699,13 +806,25 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
           W[0] = &bc.s[i].ckv[j];
           out[0] = LinOut{};
           out[0].bias = bc.s[i].ckv_bias[j];
-          out[0].post = s.kv[j]; out[0].ld_post = 2 * Dd;
+          if (step) {
+            out[0].post = static_cast<char*>(step->kv->L[static_cast<size_t>(l) * V + i].kvc[j]) + esz * 2 * Dd * step->pos;
+            out[0].ld_post = 2LL * Dd * step->max_len;
+          } else {
+            out[0].post = s.kv[j]; out[0].ld_post = 2 * Dd;
+          }
           out[0].rope_cols = Dd; out[0].head_dim = hdc; out[0].rope_table = d->rope_cross;
           SEA_TRY(linear_group(c, 1, in, W, out, M));
         }
-        char* kvb = static_cast<char*>(s.kv[j]);
-        acall[0] = attn_call(c, s.q[j], Dd, kvb, kvb + esz * Dd, 2 * Dd, s.a[j], Dd, s.lse_c[j], hdc);
-        SEA_TRY(attention_group(c, 1, acall));
+        if (step) {
+          char* kvb = static_cast<char*>(step->kv->L[static_cast<size_t>(l) * V + i].kvc[j]);
+          sea_attn_decode_args dc = decode_call(c, s.q[j], Dd, kvb, kvb + esz * Dd, 2 * Dd, 2LL * Dd * step->max_len,
+                                                s.a[j], Dd, step->pos + 1, hdc);
+          SEA_TRY(decode_group(c, 1, &dc));
+        } else {
+          char* kvb = static_cast<char*>(s.kv[j]);
+          acall[0] = attn_call(c, s.q[j], Dd, kvb, kvb + esz * Dd, 2 * Dd, s.a[j], Dd, s.lse_c[j], hdc);
+          SEA_TRY(attention_group(c, 1, acall));
+        }
         // cross_up(GELU(projection(attn)))             models/base_blocks.py:293, temporal.py:185
         in[0] = LinIn{s.a[j], Dd, 0};
         W[0] = &bc.s[i].cproj[j];
@@ -792,7 +911,7 @@ extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cach
     NormCall ncall[SEA_MAX_STREAMS];
     for (int i = 0; i < V; ++i)
       ncall[i] = norm_call(c, kind, d->final_ln[i], tape.condF[i], xin[i], ldxin, E, nullptr,
-                           y + static_cast<long long>(i) * E, static_cast<long long>(V) * E, tape.stF[i],
+                           y + static_cast<long long>(i) * E, step ? step->y_bs : static_cast<long long>(V) * E, tape.stF[i],
                            nullptr, nullptr, nullptr);
     SEA_TRY(norm_group(c, V, ncall));
   }

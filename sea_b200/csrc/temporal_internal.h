@@ -108,6 +108,8 @@ struct Ctx {
   int Mc;            // rows of the condition path (M, or B when ib is time-invariant)
   long long ld_ib;   // row pitch of ib for the condition path
   int cond_div;      // token row m uses condition row m / cond_div
+  bool inv;          // condition path evaluated once per trajectory (time-invariant ib)
+  int pos0;          // absolute position of row 0 of every trajectory (KV-cached step: the new token's)
 };
 
 struct LinIn {

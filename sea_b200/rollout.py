@@ -103,23 +103,103 @@ class RolloutPlan:
         return self.seq[:, 1:]
 
 
+class CachedRolloutPlan:
+    """KV-cached rollout: every step feeds only the newest token of each
+    trajectory through ``sea_temporal_step``; keys / values of earlier positions come from a cache, so
+    a step costs O(1) forward work instead of the reference loop's O(t) prefix recompute.  The model is
+    causal, hence the outputs equal the prefix loop's up to rounding (different reduction order in the
+    attention).  One CUDA graph per step (the cached length is baked into each launch); the step reads
+    x_t from and writes y_t into one [B, steps+1, V, E] sequence buffer, so a step has no copy kernels.
+    Works for time-invariant and time-varying ib."""
+
+    def __init__(self, model, B: int, steps: int, device, time_invariant: bool):
+        eng = _engine_of(model)
+        if eng is None:
+            raise RuntimeError("CachedRolloutPlan needs a sea_b200 temporal engine")
+        self.eng, self.B, self.steps, self.inv = eng, B, steps, bool(time_invariant)
+        eng._ensure(False)
+        h = eng._h
+        V, E, nib = h["V"], h["E"], h["ib_num"]
+        f32 = dict(dtype=torch.float32, device=device)
+        self.seq = torch.zeros(B, steps + 1, V, E, **f32)
+        self.ib = torch.zeros(B, steps, nib, **f32)
+        d = C.byref(eng._desc)
+        self.kv = torch.empty(lib.sea_temporal_kv_cache_bytes(d, B, steps), dtype=torch.uint8, device=device)
+        self.ws = torch.empty(lib.sea_temporal_workspace_bytes(d, B, 1, 0), dtype=torch.uint8, device=device)
+        self.cond = torch.empty(lib.sea_temporal_cond_cache_bytes(d, B), dtype=torch.uint8, device=device)
+        self.graphs, self.launches = [], []
+        self.key = (eng._cache.data_ptr(), eng._cache_key[:2])
+        self._record()
+
+    def _step(self, t: int) -> int:
+        return self.eng.step_into(self.seq[:, t], self.ib[:, t], self.seq[:, t + 1], t, self.kv, self.steps,
+                                  self.ws, time_invariant=self.inv, cond_buf=self.cond, cond_valid=t > 0)
+
+    def _record(self):
+        for t in range(self.steps):      # eager pass: launch attributes are set outside any capture
+            self._step(t)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        pool = None
+        for t in range(self.steps):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode="relaxed"):
+                n = self._step(t)
+            pool = g.pool()
+            self.graphs.append(g)
+            self.launches.append(n)
+        torch.cuda.current_stream().wait_stream(side)
+
+    def valid_for(self, eng) -> bool:
+        return eng._cache is not None and self.key == (eng._cache.data_ptr(), eng._cache_key[:2])
+
+    @torch.no_grad()
+    def run(self, x0: torch.Tensor, ib: torch.Tensor) -> torch.Tensor:
+        self.eng._ensure(False)
+        self.seq[:, 0].copy_(x0[:, 0])
+        self.ib.copy_(ib[:, : self.steps])
+        for g in self.graphs:
+            g.replay()
+        self.eng.last_launches = self.launches[-1]
+        self.eng.total_launches += sum(self.launches)
+        return self.seq[:, 1:]
+
+
 def _profiling() -> bool:
     return bool(getattr(profile, "active", False))
 
 
 @torch.no_grad()
 def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
-            ib_time_invariant: bool | None = None, graphs: bool = True, _view_ok: bool = False) -> torch.Tensor:
+            ib_time_invariant: bool | None = None, graphs: bool = True, cached: bool = False,
+            _view_ok: bool = False) -> torch.Tensor:
     """x0 [B,1,V,E], ib [B,>=steps,ib_num] -> predicted latents [B,steps,V,E].
 
     ``ib`` is the time-invariant physical parameter of a trajectory in the reference's data
     (models/temporal.py:111-120 "TIPI").  When every ib[b, t] equals ib[b, 0] (checked once here on
     the device unless the caller passes the answer), the AdaLN cond_mlp and the TIPI MLP are
     evaluated once per trajectory instead of once per token; the result is the same function of
-    the same inputs."""
+    the same inputs.
+
+    ``cached=True`` (opt-in) runs the KV-cached incremental engine instead of recomputing the prefix:
+    same outputs up to rounding, O(1) instead of O(t) work per step (``CachedRolloutPlan``)."""
     eng = _engine_of(model)
     if ib_time_invariant is None:
         ib_time_invariant = bool((ib[:, :steps] == ib[:, :1]).all().item())
+    if cached:
+        if eng is None or not x0.is_cuda:
+            raise RuntimeError("cached rollout needs a sea_b200 temporal engine on a CUDA device")
+        eng._ensure(False)
+        plans = eng.__dict__.setdefault("_cached_plans", {})
+        key = (x0.shape[0], steps, x0.device.index, bool(ib_time_invariant))
+        plan = plans.get(key)
+        if plan is None or not plan.valid_for(eng):
+            if len(plans) >= 4:
+                plans.clear()
+            plan = plans[key] = CachedRolloutPlan(model, x0.shape[0], steps, x0.device, bool(ib_time_invariant))
+        out = plan.run(x0, ib)
+        return out if _view_ok else out.clone()
     if graphs and eng is not None and ib_time_invariant and x0.is_cuda and not _profiling():
         eng._ensure(False)
         plans = eng.__dict__.setdefault("_rollout_plans", {})

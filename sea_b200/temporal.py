@@ -510,6 +510,34 @@ class TemporalEngine:
                   "temporal_forward")
         return int(lib.sea_last_launch_count())
 
+    @torch.no_grad()
+    def step_into(self, x_t: torch.Tensor, ib_t: torch.Tensor, y_t: torch.Tensor, pos: int,
+                  kv: torch.Tensor, max_len: int, ws: torch.Tensor, *, time_invariant: bool,
+                  cond_buf: Optional[torch.Tensor] = None, cond_valid: bool = False) -> int:
+        """KV-cached incremental step (sea_temporal_step): x_t [B,V,E] (new token at position ``pos``),
+        ib_t [B,ib_num], y_t [B,V,E]; all three may be slices of [B,T,...] buffers (only the batch
+        stride may be non-contiguous).  Allocation-free / graph-capturable; caller ran ``_ensure(False)``."""
+        B = x_t.shape[0]
+        for t_ in (x_t, y_t):
+            if t_.dtype != torch.float32 or t_.stride(-1) != 1 or t_.stride(-2) != t_.shape[-1]:
+                raise RuntimeError("sea_b200 step: x_t / y_t must be fp32 with contiguous [V,E] rows")
+        d = self._desc
+        d.ib_time_invariant = int(time_invariant)
+        if cond_buf is not None and time_invariant:
+            d.cond_cache, d.cond_cache_bytes, d.cond_cache_valid = cond_buf.data_ptr(), cond_buf.numel(), int(cond_valid)
+        else:
+            d.cond_cache, d.cond_cache_bytes, d.cond_cache_valid = None, 0, 0
+        with torch.cuda.device(x_t.device):
+            check(lib.sea_temporal_step(C.byref(d), C.c_void_p(self._cache.data_ptr()), C.c_void_p(kv.data_ptr()),
+                                        C.c_size_t(kv.numel()), int(max_len),
+                                        C.c_void_p(x_t.data_ptr()), C.c_int64(x_t.stride(0)),
+                                        C.c_void_p(ib_t.data_ptr()), C.c_int64(ib_t.stride(0)),
+                                        C.c_void_p(y_t.data_ptr()), C.c_int64(y_t.stride(0)), B, int(pos),
+                                        C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                  "temporal_step")
+        return int(lib.sea_last_launch_count())
+
     def __call__(self, x, ib):
         needs_grad = torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in self.module.parameters()))

@@ -144,3 +144,32 @@ def test_graphed_rollout_equals_eager_loop(cuda, tag, ln, prec):
     err = rel_l2(r_graph.cpu(), ref)
     print(f"\n[graphed rollout] {tag} {prec}: vs oracle {err:.3e}")
     assert err < TOL[prec]
+
+
+@pytest.mark.parametrize("tag,ln", [("small_adaln", "adaln"), ("small_ln", "ln"), ("small_v3", "ln")])
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+@pytest.mark.parametrize("varying_ib", [False, True])
+def test_kv_cached_rollout_matches_prefix_loop(cuda, tag, ln, prec, varying_ib):
+    """sea_temporal_step (KV-cached, one new token per step) against the prefix-recompute loop and the
+    oracle: the model is causal, so both must agree to rounding."""
+    from sea_b200.rollout import rollout
+    from sea_b200.temporal import TemporalModel
+    g, sd, cfg, x, ib, _, _ = temporal_case(tag, ln)
+    E, nh, scale, V, B, T, _ = [int(v) for v in g["meta"]]
+    m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln,
+                      precision=prec)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(cuda).eval()
+    x, ib = x.to(cuda), ib.to(cuda)
+    steps = min(14, ib.shape[1]) if varying_ib else 14
+    ibs = ib[:, :steps].contiguous() if varying_ib else ib[:, :1].expand(B, steps, 1).contiguous()
+    x0 = x[:, :1].contiguous()
+    r_pref = rollout(m, x0, ibs, steps)
+    for trial in range(2):   # second run replays the recorded graphs on a cache that already holds data
+        r_kv = rollout(m, x0, ibs, steps, cached=True)
+    with torch.no_grad():
+        ref = so.rollout(x0.cpu(), ibs.cpu(), steps, sd, **cfg)
+    e_kv, e_pref, d = rel_l2(r_kv.cpu(), ref), rel_l2(r_pref.cpu(), ref), rel_l2(r_kv, r_pref)
+    print(f"\n[kv-cached rollout] {tag} {prec} varying_ib={varying_ib}: cached {e_kv:.3e} prefix {e_pref:.3e} "
+          f"(vs oracle); cached vs prefix {d:.3e}")
+    assert e_kv < TOL[prec] and d < (1e-5 if prec == "fp32" else 1e-2)
