@@ -119,6 +119,15 @@ int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* host_problems, in
  * mode: the tensor core's own accumulator does not round to nearest, so long K chains drift. */
 int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem* host_problems, int M, int N,
                              int K, int k_chunk, sea_stream_t stream);
+/* Stream-K workspace of the calling thread's later GEMM launches (caller-owned device memory, 256-byte
+ * aligned; NULL = none).  The first 64 KB are per-tile arrival counters and MUST be zero when handed
+ * over (the kernels leave them zero); the rest parks fp32 partial tiles: 2 x 128 x BN x 4 bytes per CTA,
+ * about 39 MB makes every shape eligible.  With a workspace, launches whose tile count leaves SMs idle or
+ * whose last wave is ragged split the flattened (tile, k-block) space evenly over the SMs; the CTA that
+ * arrives last at a shared tile sums the partials in CTA order (deterministic) and runs the epilogue. */
+int sea_gemm_set_workspace(void* workspace, size_t bytes);
+/* Tuning hook: 0 = never stream-K, 1 = when the cost model prefers it (default), 2 = whenever legal. */
+void sea_gemm_stream_k(int mode);
 /* Test / tuning hook: force the N-tile (64, 128, 256) of the next launches; 0 = heuristic. */
 void sea_gemm_force_tile_n(int bn);
 /* Tuning probe (results are garbage): 1 = skip the TMA traffic, 2 = skip the MMAs; 0 = normal. */

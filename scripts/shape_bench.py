@@ -287,6 +287,45 @@ def run_kblock():
                   f"{(128+bn)*128/ (us/kb*1e3):6.1f} GB/s per CTA", flush=True)
 
 
+def run_sk():
+    """Stream-K vs data-parallel schedule of the same GEMM (graph chains of 8 launches, warm)."""
+    import ctypes as C
+    ws = torch.zeros(65536 + 148 * 2 * 128 * 256 * 4, dtype=torch.uint8, device=dev)
+
+    def chain(fn, n=8, reps=10):
+        fn(); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph(); side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
+            for _ in range(n):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps / n * 1e3
+    lib.sea_gemm_set_workspace(C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()))
+    for (M, N, K, G) in ((32, 1024, 8192, 2), (800, 1024, 8192, 2), (1600, 1024, 8192, 2), (3200, 1024, 8192, 2),
+                         (3200, 8192, 1024, 2), (800, 3072, 1024, 2), (3200, 1024, 1024, 2), (796, 2048, 16384, 2)):
+        a = [torch.randn(M, K, device=dev).bfloat16() for _ in range(G)]
+        b = [(torch.randn(N, K, device=dev) * 0.02).bfloat16() for _ in range(G)]
+        o = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(G)]
+        pr = [ops.gemm_problem(a[i], b[i], out_bf16=o[i], b_is_static=True) for i in range(G)]
+        fl = 2.0 * M * N * K * G
+        row = []
+        for bn in (0, 64, 128, 192, 256):
+            for mode in (0, 2):
+                lib.sea_gemm_force_tile_n(bn); lib.sea_gemm_stream_k(mode)
+                us = chain(lambda: ops.gemm_bf16_tn(pr, M, N, K))
+                row.append(f"bn{bn}/{'sk' if mode else 'dp'} {us:6.1f}us {fl/us/1e6:5.0f}TF")
+        lib.sea_gemm_force_tile_n(0); lib.sea_gemm_stream_k(1)
+        us = chain(lambda: ops.gemm_bf16_tn(pr, M, N, K))
+        print(f"M={M} N={N} K={K} g={G}: auto {us:6.1f}us {fl/us/1e6:5.0f}TF | " + " | ".join(row), flush=True)
+    lib.sea_gemm_set_workspace(None, C.c_size_t(0))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gemm"
-    {"gemm": run_gemm, "attn": run_attn, "train": run_train, "rollout": run_rollout, "floor": run_floor, "kblock": run_kblock}[what]()
+    {"gemm": run_gemm, "attn": run_attn, "train": run_train, "rollout": run_rollout, "floor": run_floor, "kblock": run_kblock, "sk": run_sk}[what]()

@@ -53,6 +53,11 @@ struct alignas(64) GemmParams {
   int M, N, K;
   int groups, tiles_m, tiles_n;
   int chunk_kb;  // k-blocks per accumulation chunk (== num_kb when not chunked)
+  int sk_grid;              // CTAs of a launch with a stream-K tail
+  int dp_tiles;             // tiles [0, dp_tiles) are processed whole, round-robin (full waves)
+  int units_per_cta;        // > 0: the other tiles are stream-K'd: contiguous (tile, k-block) units per CTA
+  float* sk_ws;             // stream-K partial tiles: [grid][2][BM x BN] fp32
+  unsigned int* sk_counters;  // stream-K arrivals per tile (zero between launches)
   int b_is_static;  // B was written before the previous kernel in the stream started (weights)
   int debug;        // tuning probe: 1 = no TMA traffic (MMA pacing only), 2 = no MMA (TMA pacing only)
 };
@@ -290,6 +295,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   uint64_t* tfull = bars + 2 * STAGES;   // [2]       MMA -> epilogue
   uint64_t* tempty = tfull + 2;          // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  int* sk_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
   // shfl-broadcast makes the warp index provably warp-uniform for the compiler: the role branches
   // below are then uniform, and the single-thread regions are entered through elect.sync, so the
@@ -325,42 +331,92 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   // prologue done (barriers, TMEM, descriptor prefetch): let the next kernel start its own
   ptx::pdl_trigger();
 
+  // Work decomposition.  A "segment" is a run of k-blocks [kb0, kb1) of one output tile, accumulated
+  // into one TMEM stage.
+  //   phase A (data-parallel): tiles [0, dp_tiles) round-robin over the CTAs, whole tiles (cut into
+  //     chunk_kb pieces in the fp32-parity mode).  All CTAs walk K in lockstep, so the CTAs that share
+  //     an A or B panel hit it in L2 at the same time.
+  //   phase B (stream-K tail): the (tile, k-block) space of the remaining tiles — the ragged last wave,
+  //     or everything when there are fewer tiles than SMs — is cut into equal contiguous ranges, one per
+  //     CTA, so no SM idles.  A tile covered by several CTAs is finished by whichever of them arrives
+  //     last (partials + arrival counter in the L2 workspace).
+  struct Seg {
+    int tile, kb0, kb1;
+    bool sk;
+  };
+  struct SegIt { int cursor, sub, u, u1; };
+  auto seg_begin = [&](SegIt& it) {
+    it.cursor = blockIdx.x; it.sub = 0;
+    it.u = blockIdx.x * p.units_per_cta;
+    it.u1 = p.units_per_cta > 0 ? min(it.u + p.units_per_cta, (total_tiles - p.dp_tiles) * num_kb) : 0;
+  };
+  auto seg_next = [&](SegIt& it, Seg& sg) -> bool {
+    if (it.cursor < p.dp_tiles && it.cursor < total_tiles) {
+      sg.tile = it.cursor;
+      sg.kb0 = it.sub;
+      sg.kb1 = min(num_kb, it.sub + p.chunk_kb);
+      sg.sk = false;
+      it.sub = sg.kb1;
+      if (it.sub >= num_kb) { it.sub = 0; it.cursor += gridDim.x; }
+      return true;
+    }
+    if (p.units_per_cta > 0 && it.u < it.u1) {
+      const int t = it.u / num_kb;
+      sg.tile = p.dp_tiles + t;
+      sg.kb0 = it.u - t * num_kb;
+      sg.kb1 = min(num_kb, sg.kb0 + (it.u1 - it.u));
+      sg.sk = true;
+      it.u += sg.kb1 - sg.kb0;
+      return true;
+    }
+    return false;
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    SegIt it;
+    Seg sg;
+    seg_begin(it);
     // The B operand is a weight matrix: it does not depend on the kernel running before this one,
     // so the first ring-full of weight tiles is requested BEFORE griddepcontrol.wait and streams
     // in from HBM while the upstream kernel drains.  Only the A tiles (activations) wait.
-    const int pre = p.b_is_static ? min(num_kb, STAGES) : 0;
-    if (pre > 0) {
-      const int g = blockIdx.x / tiles_per_group;
-      const int tn = (blockIdx.x - g * tiles_per_group) / p.tiles_m;
-      if (ptx::elect_one()) {
-        for (int kb = 0; kb < pre; ++kb) {
-          ptx::mbar_expect_tx(&full[kb], C::STAGE_BYTES);
-          if (BMN) {
+    int pre = 0;
+    {
+      SegIt it2 = it;
+      Seg first_seg;
+      if (p.b_is_static && seg_next(it2, first_seg)) {
+        pre = min(first_seg.kb1 - first_seg.kb0, STAGES);
+        const int g = first_seg.tile / tiles_per_group;
+        const int tn = (first_seg.tile - g * tiles_per_group) / p.tiles_m;
+        if (ptx::elect_one()) {
+          for (int i = 0; i < pre; ++i) {
+            const int kb = first_seg.kb0 + i;
+            ptx::mbar_expect_tx(&full[i], C::STAGE_BYTES);
+            if (BMN) {
 #pragma unroll
-            for (int a = 0; a < BN / 64; ++a)
-              ptx::tma_load_2d(smem_b + kb * C::B_BYTES + a * (BK * 128), &p.tma_b[g], &full[kb], tn * BN + a * 64, kb * BK);
-          } else {
+              for (int a = 0; a < BN / 64; ++a)
+                ptx::tma_load_2d(smem_b + i * C::B_BYTES + a * (BK * 128), &p.tma_b[g], &full[i], tn * BN + a * 64, kb * BK);
+            } else {
 #pragma unroll
-            for (int a = 0; a < C::KATOMS; ++a)
-              ptx::tma_load_2d(smem_b + kb * C::B_BYTES + a * (BN * 128), &p.tma_b[g], &full[kb], kb * BK + a * KA, tn * BN);
+              for (int a = 0; a < C::KATOMS; ++a)
+                ptx::tma_load_2d(smem_b + i * C::B_BYTES + a * (BN * 128), &p.tma_b[g], &full[i], kb * BK + a * KA, tn * BN);
+            }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
     ptx::pdl_wait();
-    bool first = true;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int g = tile / tiles_per_group;
-      const int r = tile - g * tiles_per_group;
+    int issued = 0;  // k-blocks issued by this CTA so far (the first `pre` already have their B tile)
+    while (seg_next(it, sg)) {
+      const int g = sg.tile / tiles_per_group;
+      const int r = sg.tile - g * tiles_per_group;
       const int tm = r % p.tiles_m;
       const int tn = r / p.tiles_m;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const bool prefetched = first && kb < pre;
+      for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++issued) {
+        const bool prefetched = issued < pre;
         if (!prefetched) ptx::mbar_wait(&empty[stage], phase ^ 1);
         if (ptx::elect_one()) {
           auto load_a = [&]() {
@@ -398,7 +454,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      first = false;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
@@ -407,56 +462,63 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
-        const int kb1 = min(num_kb, kb0 + p.chunk_kb);
-        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+    SegIt it;
+    Seg sg;
+    seg_begin(it);
+    while (seg_next(it, sg)) {
+      const int kb0 = sg.kb0, kb1 = sg.kb1;
+      ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&full[stage], phase);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint32_t a_base = ptx::smem_u32(smem_a + stage * A_BYTES);
-            const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::B_BYTES);
+        if (ptx::elect_one()) {
+          const uint32_t a_base = ptx::smem_u32(smem_a + stage * A_BYTES);
+          const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::B_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t adesc = AMN ? ptx::umma_smem_desc(a_base + k * 2048, BK * 128, 1024)
-                                        : ptx::umma_smem_desc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32, 16, 1024);
-              const uint64_t bdesc = BMN ? ptx::umma_smem_desc(b_base + k * 2048, BK * 128, 1024)
-                                        : ptx::umma_smem_desc(b_base + (k >> 2) * (BN * 128) + (k & 3) * 32, 16, 1024);
-              if (p.debug != 2) ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
-            }
-            ptx::umma_commit(&empty[stage]);
-            if (kb == kb1 - 1) ptx::umma_commit(&tfull[acc]);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = AMN ? ptx::umma_smem_desc(a_base + k * 2048, BK * 128, 1024)
+                                      : ptx::umma_smem_desc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32, 16, 1024);
+            const uint64_t bdesc = BMN ? ptx::umma_smem_desc(b_base + k * 2048, BK * 128, 1024)
+                                      : ptx::umma_smem_desc(b_base + (k >> 2) * (BN * 128) + (k & 3) * 32, 16, 1024);
+            if (p.debug != 2) ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          ptx::umma_commit(&empty[stage]);
+          if (kb == kb1 - 1) ptx::umma_commit(&tfull[acc]);
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // --------------------------------------------------------------- epilogue
     ptx::pdl_wait();               // residual / gelu_grad_of / out_f32 (chunked) come from upstream kernels
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
     const int half = (warp - 2) >> 2;  // two warps share a lane quarter and split the column chunks
+    const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int g = tile / tiles_per_group;
-      const int r = tile - g * tiles_per_group;
+    SegIt it;
+    Seg sg;
+    seg_begin(it);
+    int nseg = 0;   // stream-K segments seen so far
+    while (seg_next(it, sg)) {
+      const int g = sg.tile / tiles_per_group;
+      const int r = sg.tile - g * tiles_per_group;
       const int tm = r % p.tiles_m;
       const int tn = r / p.tiles_m;
       const DevEpilogue& e = p.epi[g];
-      const int m = tm * BM + quarter * 32 + lane;
-      for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
-        const bool first = kb0 == 0, last = kb0 + p.chunk_kb >= num_kb;
-        ptx::mbar_wait(&tfull[acc], acc_phase);
-        ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(acc * BN);
+      const int m = tm * BM + row;
+      const bool first = sg.kb0 == 0, last = sg.kb1 >= num_kb;
+      const bool partial = sg.sk && !(first && last);
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(acc * BN);
+      if (!partial) {
 #pragma unroll 1
         for (int c = half; c < BN / 32; c += 2) {
           uint32_t regs[32];
@@ -467,9 +529,63 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+      } else {
+        // stream-K: this CTA holds only part of the tile's K range.  Park the fp32 partial in the
+        // workspace (slot 0 = the CTA's first segment, slot 1 = any later one), then count arrivals.
+        float* slot = p.sk_ws + (static_cast<size_t>(blockIdx.x) * 2 + (nseg == 0 ? 0 : 1)) * (BM * BN);
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          uint32_t regs[32];
+          ptx::tmem_ld_32x32(t_row + c * 32, regs);
+          ptx::tmem_ld_wait();
+          // slot layout [chunk][j][row] in float4 units: lanes write consecutive 16-byte words (coalesced);
+          // the reducer below uses the same (row, chunk, j) -> address map, nobody else reads a slot
+          float4* dst = reinterpret_cast<float4*>(slot) + static_cast<size_t>(c) * 8 * BM + row;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j * BM] = make_float4(__uint_as_float(regs[4 * j]), __uint_as_float(regs[4 * j + 1]),
+                                      __uint_as_float(regs[4 * j + 2]), __uint_as_float(regs[4 * j + 3]));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int tl = sg.tile - p.dp_tiles;   // tile index inside the stream-K region
+        const int c_first = (tl * num_kb) / p.units_per_cta;
+        const int c_last = ((tl + 1) * num_kb - 1) / p.units_per_cta;
+        if (threadIdx.x == 64) *sk_flag = static_cast<int>(atomicAdd(p.sk_counters + sg.tile, 1u));
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (*sk_flag == c_last - c_first) {   // last contributor: sum the partials in CTA order, finish the tile
+          __threadfence();
+#pragma unroll 1
+          for (int c = half; c < BN / 32; c += 2) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int cc = c_first; cc <= c_last; ++cc) {
+              // contributor cc parked this tile in slot 0 iff the tile is where its range starts
+              const int which = ((cc * p.units_per_cta) / num_kb == tl) ? 0 : 1;
+              const float4* src = reinterpret_cast<const float4*>(p.sk_ws + (static_cast<size_t>(cc) * 2 + which) * (BM * BN)) +
+                                  static_cast<size_t>(c) * 8 * BM + row;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = __ldcg(src + j * BM);
+                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              }
+            }
+            uint32_t regs[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) regs[j] = __float_as_uint(v[j]);
+            epilogue_chunk(e, regs, m, tn * BN + c * 32, p.M, p.N, true, true);
+          }
+          if (threadIdx.x == 64) p.sk_counters[sg.tile] = 0u;   // self-cleaning for the next launch
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // sk_flag is reused by the next partial segment
       }
+      if (sg.sk) ++nseg;
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   }
 
@@ -483,9 +599,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
 
 int g_force_bn = 0;
 int g_debug = 0;
+int g_stream_k = 1;   // 0 = never, 1 = when the cost model says so, 2 = whenever legal (tests)
+constexpr int kSkMaxTiles = 16384;                      // arrival counters (64 KB)
+thread_local unsigned int* g_sk_counters = nullptr;     // caller-owned stream-K workspace (this thread)
+thread_local float* g_sk_ws = nullptr;
+thread_local size_t g_sk_ws_bytes = 0;
 
 template <int BN, bool AMN, bool BMN>
-int launch(const GemmParams& p, int total_tiles, cudaStream_t stream) {
+int launch(const GemmParams& p, int total_tiles, int num_kb, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_set[16] = {};
   int dev = 0;
@@ -496,7 +617,9 @@ int launch(const GemmParams& p, int total_tiles, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set[dev] = true;
   }
-  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  if (p.units_per_cta > 0) grid = p.sk_grid;
+  (void)num_kb;
   SEA_LAUNCH((gemm_bf16_tn_kernel<BN, AMN, BMN>), grid, kThreads, C::SMEM_BYTES, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
@@ -521,6 +644,19 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
 }  // namespace sea
 
 extern "C" void sea_gemm_force_tile_n(int bn) { sea::g_force_bn = bn; }
+extern "C" void sea_gemm_stream_k(int mode) { sea::g_stream_k = mode; }
+extern "C" int sea_gemm_set_workspace(void* ws, size_t bytes) {
+  using namespace sea;
+  if (ws == nullptr || bytes <= 65536 + 2 * BM * 64 * sizeof(float)) {
+    g_sk_counters = nullptr; g_sk_ws = nullptr; g_sk_ws_bytes = 0;
+    return ws == nullptr ? SEA_OK : SEA_ERR_WORKSPACE;
+  }
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return SEA_ERR_INVALID;
+  g_sk_counters = static_cast<unsigned int*>(ws);
+  g_sk_ws = reinterpret_cast<float*>(static_cast<char*>(ws) + 65536);
+  g_sk_ws_bytes = bytes - 65536;
+  return SEA_OK;
+}
 extern "C" void sea_gemm_debug_probe(int mode) { sea::g_debug = mode; }
 
 
@@ -546,22 +682,62 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   int rc = ensure_init();
   if (rc != SEA_OK) return rc;
 
+  // Tile width and decomposition.  Cost per candidate width, in units of one 64-wide k-block of an
+  // N = 1 column: tile width / mainloop efficiency of that width (measured, scripts/shape_bench.py: the
+  // issuing thread's fixed per-stage cost is amortised over N x BK, so narrow tiles stay below the MMA
+  // rate: 0.6 / 0.8 / 0.87 / 0.9 of it at N = 64 / 128 / 192 / 256) times the k-blocks on the critical
+  // CTA, plus an epilogue/latency term per tile pass.
+  //   data-parallel: ceil(tiles / SMs) whole tiles on the critical CTA              (wave quantisation)
+  //   hybrid       : floor(tiles / SMs) whole tiles + an equal share of the ragged remainder's k-blocks
+  //                  (stream-K tail, a tile split at most 8 ways) + the partial-tile fix-up
+  const int sms = num_sms();
+  const bool sk_possible = g_sk_ws != nullptr && g_stream_k != 0 && !(k_chunk > 0 && k_chunk < K);
   int bn = g_force_bn;
-  if (bn == 0) {
-    // Cost model: waves x tile width / mainloop efficiency of that width, plus a per-wave
-    // epilogue/latency term.  Efficiencies are measured (scripts/shape_bench.py gemm): the issuing
-    // thread's fixed per-stage cost is amortised over N x BK, so narrow tiles stay below the MMA rate
-    // (0.6 / 0.8 / 0.87 / 0.9 of it at N = 64 / 128 / 192 / 256).
+  int units_per_cta = 0, dp_tiles = -1, sk_grid = 0;
+  {
     const long long tm = (M + BM - 1) / BM;
     const int cand[4] = {64, 128, 192, 256};
     const double eff[4] = {0.6, 0.8, 0.87, 0.9};
     double best = 1e30;
     for (int i = 0; i < 4; ++i) {
+      if (g_force_bn != 0 && cand[i] != g_force_bn) continue;
       const long long tiles = tm * ((N + cand[i] - 1) / cand[i]) * num_problems;
-      const long long waves = (tiles + num_sms() - 1) / num_sms();
-      const double kb = (K + KA - 1) / KA;
-      const double cost = waves * (cand[i] / eff[i] * kb + 6.0 * cand[i] + 400.0);
-      if (cost < best) { best = cost; bn = cand[i]; }
+      const long long waves = (tiles + sms - 1) / sms;
+      const double kb64 = (K + KA - 1) / KA;
+      const double epi = 6.0 * cand[i] + 400.0;
+      const double tile_cost = cand[i] / eff[i] * kb64 + epi;
+      const double cost_dp = waves * tile_cost;
+      if (cost_dp < best || (g_force_bn != 0 && dp_tiles < 0)) {
+        best = cost_dp; bn = cand[i]; units_per_cta = 0; dp_tiles = static_cast<int>(tiles); sk_grid = 0;
+      }
+      const int bkc = cand[i] <= 128 ? 128 : 64;
+      const long long nkb = (K + bkc - 1) / bkc;
+      const long long full = tiles / sms, rem = tiles - full * sms;
+      if (sk_possible && rem > 0 && nkb >= 8 && rem <= kSkMaxTiles) {
+        const long long units = rem * nkb;
+        long long min_upc = (nkb + 7) / 8;           // a tile is split at most ~8 ways
+        if (min_upc < 4) min_upc = 4;
+        long long grid_sk = full > 0 ? sms : (units / min_upc < sms ? units / min_upc : sms);
+        if (grid_sk < 1) grid_sk = 1;
+        long long upc = (units + grid_sk - 1) / grid_sk;
+        if (upc < min_upc) upc = min_upc;
+        if (full == 0) grid_sk = (units + upc - 1) / upc;
+        const size_t need = static_cast<size_t>(grid_sk) * 2 * BM * cand[i] * sizeof(float);
+        const double cost_sk = full * tile_cost + cand[i] / eff[i] * (upc * (bkc / 64.0)) + 3.0 * epi;
+        // CTAs of a stream-K range sit at different K offsets, so panels shared between tiles are no
+        // longer fetched in lockstep: without full waves in front, the operands must fit L2 comfortably
+        // (measured: 796x2048x16384 drops from 1060 to 780 TFLOP/s otherwise).
+        const double operand_mb = 2.0 * num_problems * (static_cast<double>(M) + N) * K / 1e6;
+        // With full waves in front only the widest tile is worth it (fewest panel re-reads; narrower
+        // tiles measured slower than the model predicts).
+        const bool l2_ok = full > 0 ? cand[i] == 256 : operand_mb <= 48.0;
+        const double margin = full > 0 ? 1.1 : 1.2;
+        if (need <= g_sk_ws_bytes && upc < nkb && (g_stream_k == 2 || (l2_ok && cost_sk * margin < best))) {
+          best = g_stream_k == 2 ? -1.0 : cost_sk;   // mode 2 (tests): first legal stream-K candidate wins
+          bn = cand[i]; units_per_cta = static_cast<int>(upc);
+          dp_tiles = static_cast<int>(full * sms); sk_grid = static_cast<int>(grid_sk);
+        }
+      }
     }
   }
   if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return SEA_ERR_INVALID;
@@ -575,6 +751,11 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   p.chunk_kb = (k_chunk > 0 && k_chunk < K) ? k_chunk / bk : (K + bk - 1) / bk;
   const bool chunked = p.chunk_kb < (K + bk - 1) / bk;
   p.debug = g_debug;
+  p.units_per_cta = units_per_cta;
+  p.dp_tiles = units_per_cta > 0 ? dp_tiles : 0x7fffffff;
+  p.sk_grid = sk_grid;
+  p.sk_ws = g_sk_ws;
+  p.sk_counters = g_sk_counters;
   p.b_is_static = 1;
   for (int g = 0; g < num_problems; ++g) p.b_is_static &= probs[g].b_is_static != 0;
   for (int g = 0; g < num_problems; ++g) {
@@ -639,13 +820,14 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
              al32(e.out_pre_bf16, e.ld_out_pre_bf16, 2) && al32(e.out_bf16, e.ld_out_bf16, 2);
   }
   const int total = p.tiles_m * p.tiles_n * p.groups;
+  const int nkb = (K + bk - 1) / bk;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 #define SEA_GEMM_DISPATCH(AMN_, BMN_)                                   \
   do {                                                                  \
-    if (bn == 256) return launch<256, AMN_, BMN_>(p, total, s);         \
-    if (bn == 192) return launch<192, AMN_, BMN_>(p, total, s);         \
-    if (bn == 128) return launch<128, AMN_, BMN_>(p, total, s);         \
-    return launch<64, AMN_, BMN_>(p, total, s);                         \
+    if (bn == 256) return launch<256, AMN_, BMN_>(p, total, nkb, s);    \
+    if (bn == 192) return launch<192, AMN_, BMN_>(p, total, nkb, s);    \
+    if (bn == 128) return launch<128, AMN_, BMN_>(p, total, nkb, s);    \
+    return launch<64, AMN_, BMN_>(p, total, nkb, s);                    \
   } while (0)
   if (amn && bmn) SEA_GEMM_DISPATCH(true, true);
   if (bmn) SEA_GEMM_DISPATCH(false, true);

@@ -92,6 +92,9 @@ void layout_cache(const sea_temporal_desc* d, bool training, Arena& ar, CacheLay
   }
   for (int i = 0; i < V; ++i)
     if (ada) c.c2_final[i] = take_linear(ar, 2 * E, 2 * E, kf, training);
+  // stream-K workspace of the GEMM launches (arrival counters + parked partial tiles), see sea_gemm_set_workspace
+  c.splitk_bytes = kSplitKBytes;
+  c.splitk = ar.take(c.splitk_bytes);
 }
 
 static int pack_weight(const float* src, int N, int K, const PackedLinear& dst, int row_off,
@@ -216,6 +219,7 @@ extern "C" int sea_temporal_refresh_ex(const sea_temporal_desc* d, void* cache, 
   layout_cache(d, training != 0, ar, c);
   const bool fp32 = d->precision == SEA_PREC_FP32;
   const int E = d->embed_dim, Dd = d->down_dim, V = d->num_streams;
+  SEA_CUDA_OK(cudaMemsetAsync(c.splitk, 0, 65536, s));   // stream-K arrival counters start at zero
   SEA_TRY(for_each_weight(d, c, [&](const float* src, int N, int K, const PackedLinear& dst, int row_off, int n_total) {
     return pack_weight(src, N, K, dst, row_off, n_total, fp32, what, s);
   }));
@@ -598,6 +602,7 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
   Arena war{static_cast<char*>(workspace)};
   Tape tape;
   layout_tape(d, B, T, training != 0, war, tape);
+  SEA_TRY(sea_gemm_set_workspace(cl.splitk, cl.splitk_bytes));
 
   Ctx c{};
   c.d = d; c.cache = &cl; c.tape = &tape;

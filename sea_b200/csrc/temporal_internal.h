@@ -37,9 +37,12 @@ struct StreamCache {
   PackedLinear c2_ln0, c2_ln2, c2_lnc;
 };
 struct BlockCache { StreamCache s[SEA_MAX_STREAMS]; };
+constexpr size_t kSplitKBytes = 65536 + 148ull * 2 * 128 * 256 * 4;  // counters + two 128x256 fp32 slots per SM
 struct CacheLayout {
   std::vector<BlockCache> blocks;
   PackedLinear c2_final[SEA_MAX_STREAMS];
+  void* splitk;         // stream-K workspace (sea_gemm_set_workspace)
+  size_t splitk_bytes;
 };
 
 // "act" buffers are bf16 in SEA_PREC_BF16 and fp32 in SEA_PREC_FP32.

@@ -1,4 +1,6 @@
 """K1 parity: tcgen05 GEMM + fused epilogues vs torch (fp32 math on bf16-rounded operands)."""
+import ctypes
+
 import pytest
 import torch
 
@@ -154,3 +156,47 @@ def test_gemm_b_mn_major(cuda, M, N, K):
     print(f"\n[gemm B MN-major] M={M} N={N} K={K}: rel err {err:.2e} (K-major path {err2:.2e})")
     assert err < max(2e-6, 1.5 * err2), (err, err2)
     assert torch.equal(out, out2)   # same MMA sequence along K -> bit-identical
+
+
+@pytest.mark.parametrize("M,N,K,groups", [(32, 1024, 8192, 2), (160, 1024, 8192, 2), (800, 1024, 8192, 2),
+                                          (3200, 1024, 8192, 2), (796, 2048, 16384, 1), (100, 512, 1024, 1),
+                                          (3200, 8192, 1024, 2), (2000, 520, 2048, 1)])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
+def test_gemm_stream_k(cuda, M, N, K, groups, bn):
+    """Stream-K (contiguous (tile, k-block) ranges per CTA, last arriver reduces the partials in CTA
+    order) against the data-parallel schedule of the same kernel: fused epilogue (bias + residual +
+    GELU) included; deterministic across repeats; counters left clean."""
+    from sea_b200 import lib, ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    ws = torch.zeros(65536 + 148 * 2 * 128 * 256 * 4, dtype=torch.uint8, device=cuda)
+    outs = {}
+    a = [torch.randn(M, K, device=cuda, generator=g).bfloat16() for _ in range(groups)]
+    b = [(torch.randn(N, K, device=cuda, generator=g) * 0.02).bfloat16() for _ in range(groups)]
+    bias = torch.randn(N, device=cuda, generator=g)
+    res = torch.randn(M, N, device=cuda, generator=g)
+    for mode in (0, 2, 2):
+        of = [torch.empty(M, N, device=cuda) for _ in range(groups)]
+        ob = [torch.empty(M, N, device=cuda, dtype=torch.bfloat16) for _ in range(groups)]
+        lib.sea_gemm_stream_k(mode)
+        lib.sea_gemm_force_tile_n(bn)
+        assert lib.sea_gemm_set_workspace(ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel())) == 0
+        try:
+            ops.gemm_bf16_tn([ops.gemm_problem(a[i], b[i], bias=bias, residual=res, out_f32=of[i], out_bf16=ob[i],
+                                               act=ops.ACT_GELU) for i in range(groups)], M, N, K)
+        finally:
+            lib.sea_gemm_stream_k(1)
+            lib.sea_gemm_force_tile_n(0)
+            lib.sea_gemm_set_workspace(None, ctypes.c_size_t(0))
+        torch.cuda.synchronize()
+        outs.setdefault(mode, []).append((of, ob))
+    assert int(ws[:65536].view(torch.int32).abs().sum()) == 0          # arrival counters self-cleaned
+    (dp,), (sk1, sk2) = outs[0], outs[2]
+    ref = a[0].double() @ b[0].double().t() + bias.double() + res.double()
+    err = ((sk1[0][0].double() - ref).norm() / ref.norm()).item()
+    assert err < 3e-5, err
+    for i in range(groups):
+        assert torch.equal(sk1[0][i], sk2[0][i]) and torch.equal(sk1[1][i], sk2[1][i])     # deterministic
+        # shorter accumulation chains summed in fp32 RN vs one long chain in the (non-RN) tensor-core
+        # accumulator: the two schedules differ at the level of that accumulator's drift (DESIGN.md §3)
+        d = ((sk1[0][i].double() - dp[0][i].double()).norm() / dp[0][i].double().norm()).item()
+        assert d < 3e-5, d
