@@ -227,6 +227,9 @@ int sea_pack_operand(const sea_pack_args* args, sea_stream_t stream);
 /* out[n] += sum_m src[m,n]  (bias gradients). */
 int sea_colsum_accumulate(const float* src_f32, const void* src_bf16, int64_t ld, int M, int N,
                           float* out, sea_stream_t stream);
+/* n (<= SEA_MAX_STREAMS) column sums of equal shape in one launch; out[i] == NULL skips item i. */
+int sea_colsum_accumulate_group(int n, const float* const* src_f32, const void* const* src_bf16, int64_t ld,
+                                int M, int N, float* const* out, sea_stream_t stream);
 
 /* ------------------------------------------------------------------ backward of K4/K5/K6 ----
  * The reference differentiates these with autograd; here they are explicit kernels.  Parameter
@@ -254,6 +257,7 @@ typedef struct sea_norm_bwd_args {
   int32_t dcond_accumulate; /* 1: += into dcond (module applied twice in the exchange) */
 } sea_norm_bwd_args;
 int sea_norm_bwd(const sea_norm_bwd_args* args, sea_stream_t stream);
+int sea_norm_bwd_group(int n, const sea_norm_bwd_args* host_args, sea_stream_t stream);  /* equal (M, d, kind) */
 
 typedef struct sea_ln_gelu_bwd_args {
   const void* dg;   /* bf16 [M,H] gradient wrt GELU output */
@@ -270,6 +274,7 @@ typedef struct sea_ln_gelu_bwd_args {
   float* dbias;     /* [H] += */
 } sea_ln_gelu_bwd_args;
 int sea_ln_gelu_bwd(const sea_ln_gelu_bwd_args* args, sea_stream_t stream);
+int sea_ln_gelu_bwd_group(int n, const sea_ln_gelu_bwd_args* host_args, sea_stream_t stream); /* equal shapes */
 
 /* Backward of sea_adaln_hidden: dh [M,n] -> dw1 [n, ib_num] +=, db1 [n] +=  (ib_num <= 4). */
 int sea_adaln_hidden_bwd(const float* dh, int64_t lddh, const float* ib, int M, int ib_num,

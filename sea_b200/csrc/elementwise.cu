@@ -586,10 +586,14 @@ __global__ void __launch_bounds__(256) pack_kernel(const TIn* __restrict__ src, 
 }
 
 // out[n] = sum_m src[m, n] (bias gradients).  One warp per 32 columns x row-slab, atomics into out.
-__global__ void colsum_kernel(const float* __restrict__ src_f32, const __nv_bfloat16* __restrict__ src_bf16,
-                              long long ld, int M, int N, float* __restrict__ out) {
+struct ColsumGroup { const float* f32[SEA_MAX_STREAMS]; const __nv_bfloat16* b16[SEA_MAX_STREAMS]; float* out[SEA_MAX_STREAMS]; };
+__global__ void colsum_kernel(const ColsumGroup grp, long long ld, int M, int N) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
+  const float* __restrict__ src_f32 = grp.f32[blockIdx.z];
+  const __nv_bfloat16* __restrict__ src_bf16 = grp.b16[blockIdx.z];
+  float* __restrict__ out = grp.out[blockIdx.z];
+  if (out == nullptr) return;
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int r_begin = blockIdx.y * rows_per;
@@ -808,13 +812,29 @@ extern "C" int sea_pack_operand(const sea_pack_args* a, sea_stream_t stream) {
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int sea_colsum_accumulate(const float* src_f32, const void* src_bf16, int64_t ld, int M,
-                                     int N, float* out, sea_stream_t stream) {
-  if ((!src_f32 && !src_bf16) || !out || M <= 0 || N <= 0) return SEA_ERR_INVALID;
+extern "C" int sea_colsum_accumulate_group(int n, const float* const* src_f32, const void* const* src_bf16,
+                                           int64_t ld, int M, int N, float* const* out, sea_stream_t stream) {
+  if (n < 1 || n > SEA_MAX_STREAMS || !out || M <= 0 || N <= 0) return SEA_ERR_INVALID;
+  ColsumGroup g;
+  bool any = false;
+  for (int i = 0; i < n; ++i) {
+    g.f32[i] = src_f32 ? src_f32[i] : nullptr;
+    g.b16[i] = src_bf16 ? static_cast<const __nv_bfloat16*>(src_bf16[i]) : nullptr;
+    g.out[i] = out[i];
+    if (out[i] && !g.f32[i] && !g.b16[i]) return SEA_ERR_INVALID;
+    any = any || out[i] != nullptr;
+  }
+  if (!any) return SEA_OK;
   int slabs = M / 64;
   if (slabs < 1) slabs = 1;
   if (slabs > 64) slabs = 64;
-  dim3 grid((N + 31) / 32, slabs);
-  SEA_LAUNCH(colsum_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), src_f32, static_cast<const __nv_bfloat16*>(src_bf16), ld, M, N, out);
+  dim3 grid((N + 31) / 32, slabs, n);
+  SEA_LAUNCH(colsum_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), g, static_cast<long long>(ld), M, N);
   return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_colsum_accumulate(const float* src_f32, const void* src_bf16, int64_t ld, int M,
+                                     int N, float* out, sea_stream_t stream) {
+  if (!out) return SEA_ERR_INVALID;
+  return sea_colsum_accumulate_group(1, src_f32 ? &src_f32 : nullptr, src_bf16 ? &src_bf16 : nullptr, ld, M, N, &out, stream);
 }

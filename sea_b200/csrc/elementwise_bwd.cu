@@ -35,10 +35,13 @@ struct NormBwdDev {
 
 constexpr int kNormMaxChunks = 16;
 
+struct NormBwdGroup { NormBwdDev it[SEA_MAX_STREAMS]; };  // the V field streams share a launch (blockIdx.y)
+
 template <int CH>
-__global__ void __launch_bounds__(256) norm_bwd_kernel(const NormBwdDev a) {
+__global__ void __launch_bounds__(256) norm_bwd_kernel(const __grid_constant__ NormBwdGroup grp) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
+  const NormBwdDev& a = grp.it[blockIdx.y];
   extern __shared__ float red[];  // [8 warps][d] x2 (dweight, dbias partials; each lane owns its columns)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* rw = red;
@@ -143,17 +146,26 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const NormBwdDev a) {
 
 // ------------------------------------------------------------- LayerNorm(H)+GELU backward (K6)
 // dh = LN'(GELU'(u) * dg);  dweight/dbias of the inner nn.LayerNorm accumulate in shared memory.
+struct LnGeluBwdItem {
+  const __nv_bfloat16 *dg, *h; const float *stats, *weight, *bias; __nv_bfloat16* dh; float *dweight, *dbias;
+};
+struct LnGeluBwdGroup { LnGeluBwdItem it[SEA_MAX_STREAMS]; };
+
 template <int kDummy>
-__global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, long long lddg,
-                                                          const __nv_bfloat16* __restrict__ h, long long ldh,
-                                                          const float* __restrict__ stats,
-                                                          const float* __restrict__ weight,
-                                                          const float* __restrict__ bias,
-                                                          __nv_bfloat16* __restrict__ dh, long long lddh,
-                                                          float* __restrict__ dweight, float* __restrict__ dbias,
-                                                          int M, int H, int rows_per_cta) {
+__global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const __grid_constant__ LnGeluBwdGroup grp, long long lddg,
+                                                          long long ldh, long long lddh, int M, int H,
+                                                          int rows_per_cta) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
+  const LnGeluBwdItem& item = grp.it[blockIdx.y];
+  const __nv_bfloat16* __restrict__ dg = item.dg;
+  const __nv_bfloat16* __restrict__ h = item.h;
+  const float* __restrict__ stats = item.stats;
+  const float* __restrict__ weight = item.weight;
+  const float* __restrict__ bias = item.bias;
+  __nv_bfloat16* __restrict__ dh = item.dh;
+  float* __restrict__ dweight = item.dweight;
+  float* __restrict__ dbias = item.dbias;
   constexpr int kMaxChunks = 8;
   extern __shared__ float acc[];  // [2][H]
   __shared__ float red[2][8];
@@ -365,14 +377,13 @@ static int rows_per_cta_for(int M, int granule) {
   return r < granule ? granule : r;
 }
 
-extern "C" int sea_norm_bwd(const sea_norm_bwd_args* a, sea_stream_t stream) {
-  if (!a || !a->dy || !a->x || !a->stats || !a->weight || a->M <= 0 || a->d <= 0) return SEA_ERR_INVALID;
+static int fill_norm_bwd(const sea_norm_bwd_args* a, NormBwdDev& d) {
+  if (!a->dy || !a->x || !a->stats || !a->weight || a->M <= 0 || a->d <= 0) return SEA_ERR_INVALID;
   if ((a->d % 4) || a->d > kNormMaxChunks * 128) return SEA_ERR_UNSUPPORTED;
   if (a->kind == SEA_NORM_ADALN && !a->cond) return SEA_ERR_INVALID;
   if (!a->dx && !a->dx_bf16) return SEA_ERR_INVALID;
   if ((a->lddy % 4) || (a->ldx % 4) || (a->dx && (a->lddx % 4)) || (a->dres && (a->lddres % 4)))
     return SEA_ERR_INVALID;
-  NormBwdDev d;
   d.dy = a->dy; d.lddy = a->lddy; d.x = a->x; d.ldx = a->ldx; d.stats = a->stats;
   d.weight = a->weight; d.cond = a->cond; d.ldc = a->ldc;
   d.dres = a->dres; d.lddres = a->lddres;
@@ -382,7 +393,19 @@ extern "C" int sea_norm_bwd(const sea_norm_bwd_args* a, sea_stream_t stream) {
   d.dcond = a->dcond; d.lddc = a->lddcond; d.dcond_accumulate = a->dcond_accumulate;
   d.M = a->M; d.d = a->d; d.kind = a->kind;
   d.rows_per_cta = rows_per_cta_for(a->M, 8);
-  const int grid = (a->M + d.rows_per_cta - 1) / d.rows_per_cta;
+  return SEA_OK;
+}
+
+extern "C" int sea_norm_bwd_group(int n, const sea_norm_bwd_args* a, sea_stream_t stream) {
+  if (!a || n < 1 || n > SEA_MAX_STREAMS) return SEA_ERR_INVALID;
+  NormBwdGroup g;
+  for (int i = 0; i < n; ++i) {
+    int rc = fill_norm_bwd(&a[i], g.it[i]);
+    if (rc) return rc;
+    if (a[i].M != a->M || a[i].d != a->d || a[i].kind != a->kind) return SEA_ERR_INVALID;
+  }
+  const NormBwdDev& d = g.it[0];
+  const dim3 grid((a->M + d.rows_per_cta - 1) / d.rows_per_cta, n);
   const size_t smem = sizeof(float) * 16 * a->d;
   static bool attr_set[16] = {};
   int dev = 0;
@@ -394,19 +417,31 @@ extern "C" int sea_norm_bwd(const sea_norm_bwd_args* a, sea_stream_t stream) {
     attr_set[dev] = true;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a->d <= 512) SEA_LAUNCH((norm_bwd_kernel<4>), grid, 256, smem, s, d);
-  else if (a->d <= 1024) SEA_LAUNCH((norm_bwd_kernel<8>), grid, 256, smem, s, d);
-  else SEA_LAUNCH((norm_bwd_kernel<16>), grid, 256, smem, s, d);
+  if (a->d <= 512) SEA_LAUNCH((norm_bwd_kernel<4>), grid, 256, smem, s, g);
+  else if (a->d <= 1024) SEA_LAUNCH((norm_bwd_kernel<8>), grid, 256, smem, s, g);
+  else SEA_LAUNCH((norm_bwd_kernel<16>), grid, 256, smem, s, g);
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int sea_ln_gelu_bwd(const sea_ln_gelu_bwd_args* a, sea_stream_t stream) {
-  if (!a || !a->dg || !a->h || !a->stats || !a->weight || !a->bias || !a->dh || !a->dweight || !a->dbias)
-    return SEA_ERR_INVALID;
-  if (a->M <= 0 || a->H <= 0 || (a->H % 8) || a->H > 16384) return SEA_ERR_UNSUPPORTED;
-  if ((a->lddg % 8) || (a->ldh % 8) || (a->lddh % 8)) return SEA_ERR_INVALID;
-  const int rows = rows_per_cta_for(a->M, 1);
-  const int grid = (a->M + rows - 1) / rows;
+extern "C" int sea_norm_bwd(const sea_norm_bwd_args* a, sea_stream_t stream) {
+  return sea_norm_bwd_group(1, a, stream);
+}
+
+extern "C" int sea_ln_gelu_bwd_group(int n, const sea_ln_gelu_bwd_args* a, sea_stream_t stream) {
+  if (!a || n < 1 || n > SEA_MAX_STREAMS) return SEA_ERR_INVALID;
+  LnGeluBwdGroup g;
+  for (int i = 0; i < n; ++i) {
+    const sea_ln_gelu_bwd_args* x = &a[i];
+    if (!x->dg || !x->h || !x->stats || !x->weight || !x->bias || !x->dh || !x->dweight || !x->dbias)
+      return SEA_ERR_INVALID;
+    if (x->M <= 0 || x->H <= 0 || (x->H % 8) || x->H > 16384) return SEA_ERR_UNSUPPORTED;
+    if ((x->lddg % 8) || (x->ldh % 8) || (x->lddh % 8)) return SEA_ERR_INVALID;
+    if (x->M != a->M || x->H != a->H || x->lddg != a->lddg || x->ldh != a->ldh || x->lddh != a->lddh) return SEA_ERR_INVALID;
+    g.it[i] = LnGeluBwdItem{static_cast<const __nv_bfloat16*>(x->dg), static_cast<const __nv_bfloat16*>(x->h), x->stats,
+                            x->weight, x->bias, static_cast<__nv_bfloat16*>(x->dh), x->dweight, x->dbias};
+  }
+  const int rows = rows_per_cta_for(a->M * n, 1);
+  const dim3 grid((a->M + rows - 1) / rows, n);
   const size_t smem = sizeof(float) * 2 * a->H;
   static bool attr_set[16] = {};
   int dev = 0;
@@ -415,8 +450,13 @@ extern "C" int sea_ln_gelu_bwd(const sea_ln_gelu_bwd_args* a, sea_stream_t strea
     SEA_CUDA_OK(cudaFuncSetAttribute(ln_gelu_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
     attr_set[dev] = true;
   }
-  SEA_LAUNCH((ln_gelu_bwd_kernel<0>), grid, 256, smem, reinterpret_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a->dg), a->lddg, static_cast<const __nv_bfloat16*>(a->h), a->ldh, a->stats, a->weight, a->bias, static_cast<__nv_bfloat16*>(a->dh), a->lddh, a->dweight, a->dbias, a->M, a->H, rows);
+  SEA_LAUNCH((ln_gelu_bwd_kernel<0>), grid, 256, smem, reinterpret_cast<cudaStream_t>(stream), g, a->lddg, a->ldh,
+             a->lddh, a->M, a->H, rows);
   return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_ln_gelu_bwd(const sea_ln_gelu_bwd_args* a, sea_stream_t stream) {
+  return sea_ln_gelu_bwd_group(1, a, stream);
 }
 
 extern "C" int sea_adaln_hidden_bwd(const float* dh, int64_t lddh, const float* ib, int M, int ib_num,

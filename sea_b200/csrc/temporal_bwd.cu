@@ -43,11 +43,17 @@ int cast_f32(BCtx& b, const float* src, long long ld, int R, int Ccols, bf16* ds
   return sea_pack_operand(&a, b.st());
 }
 
-int colsum(BCtx& b, const float* f32, const bf16* b16, long long ld, int M, int N, float* out) {
-  if (!out) return SEA_OK;
+// bias gradients of the n grouped Linears in one launch (NULL destinations are skipped)
+int colsum_group(BCtx& b, int n, const float* const* f32, const bf16* const* b16, long long ld, int M, int N,
+                 float* const* out) {
+  bool any = false;
+  for (int g = 0; g < n; ++g) any = any || out[g] != nullptr;
+  if (!any) return SEA_OK;
+  const void* bp[SEA_MAX_STREAMS];
+  for (int g = 0; g < n; ++g) bp[g] = b16 ? b16[g] : nullptr;
   ++g_launches;
-  ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, (f32 ? 4.0 : 2.0) * M * N);
-  return sea_colsum_accumulate(f32, b16, ld, M, N, out, b.st());
+  ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, (f32 ? 4.0 : 2.0) * M * N * n);
+  return sea_colsum_accumulate_group(n, f32, b16 ? bp : nullptr, ld, M, N, out, b.st());
 }
 
 int gemm(BCtx& b, int n, sea_gemm_problem* probs, int M, int N, int K) {
@@ -95,10 +101,12 @@ int linear_bwd(BCtx& b, int n, LinB* L) {
         p.epi.residual = dW; p.epi.ld_residual = K;
       }
       SEA_TRY(gemm(b, n, probs, Np, K, M));
+      const bf16* src[SEA_MAX_STREAMS]; float* dbs[SEA_MAX_STREAMS];
       for (int g = 0; g < n; ++g) {
-        float* db = parts > 1 ? L[g].db_split[part] : L[g].db;
-        SEA_TRY(colsum(b, nullptr, L[g].dy + part * Np, L[g].lddy, M, Np, db));
+        src[g] = L[g].dy + part * Np;
+        dbs[g] = parts > 1 ? L[g].db_split[part] : L[g].db;
       }
+      SEA_TRY(colsum_group(b, n, nullptr, src, L[0].lddy, M, Np, dbs));
     }
   }
   // ---- dgrad
@@ -118,6 +126,28 @@ int linear_bwd(BCtx& b, int n, LinB* L) {
     SEA_TRY(gemm(b, n, probs, M, K, N));
   }
   return SEA_OK;
+}
+
+sea_norm_bwd_args norm_bwd_args(BCtx& b, int kind, const sea_norm_params& np, const float* cond, const float* dy,
+                                long long lddy, const float* x, long long ldx, const float* stats, int dim,
+                                const float* dres, long long lddres, float* dx, long long lddx, bf16* dxb,
+                                float* dcond, int dcond_acc) {
+  sea_norm_bwd_args a{};
+  a.dy = dy; a.lddy = lddy; a.x = x; a.ldx = ldx; a.stats = stats;
+  a.M = b.c.M; a.d = dim; a.kind = kind;
+  a.weight = np.weight.p; a.cond = cond; a.ldc = 2LL * dim;
+  a.dres = dres; a.lddres = lddres;
+  a.dx = dx; a.lddx = lddx; a.dx_bf16 = dxb; a.lddx_bf16 = dim;
+  a.dweight = np.weight.g;
+  a.dbias = kind == SEA_NORM_ADALN ? np.bias.g : nullptr;
+  a.dcond = kind == SEA_NORM_ADALN ? dcond : nullptr; a.lddcond = 2LL * dim; a.dcond_accumulate = dcond_acc;
+  return a;
+}
+
+int norm_bwd_group(BCtx& b, int n, const sea_norm_bwd_args* a) {
+  ++g_launches;
+  ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, 16.0 * b.c.M * a[0].d * n);
+  return sea_norm_bwd_group(n, a, b.st());
 }
 
 int norm_bwd(BCtx& b, int kind, const sea_norm_params& np, const float* cond, const float* dy,
@@ -155,8 +185,12 @@ int cond_bwd(BCtx& b, int n, const sea_norm_params* const* np, void* const* hid,
     l.da_f32 = b.bt->dhid[g]; l.ld_da = d2;
   }
   SEA_TRY(linear_bwd(b, n, L));
+  {
+    const float* src[SEA_MAX_STREAMS]; float* dbs[SEA_MAX_STREAMS];
+    for (int g = 0; g < n; ++g) { src[g] = dcond[g]; dbs[g] = np[g]->c2_b.g; }
+    SEA_TRY(colsum_group(b, n, src, nullptr, d2, M, d2, dbs));
+  }
   for (int g = 0; g < n; ++g) {
-    SEA_TRY(colsum(b, dcond[g], nullptr, d2, M, d2, np[g]->c2_b.g));
     if (np[g]->c0_w.g && np[g]->c0_b.g) {
       ++g_launches;
       SEA_TRY(sea_adaln_hidden_bwd(b.bt->dhid[g], d2, b.ib, M, b.c.d->ib_num, np[g]->c0_w.p, np[g]->c0_b.p,
@@ -256,10 +290,12 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
   // ---- final norm --------------------------------------------------------------------------
   {
     const LayerTape& last = tape.L[d->num_layers - 1];
+    sea_norm_bwd_args na[SEA_MAX_STREAMS];
     for (int i = 0; i < V; ++i)
-      SEA_TRY(norm_bwd(b, kind, d->final_ln[i], tape.condF[i], dy + static_cast<long long>(i) * E, ldY,
-                       last.s[i].xout, E, tape.stF[i], E, nullptr, 0, bt.s[i].dxout, E, bt.s[i].dxoutb,
-                       bt.s[i].dcondF, 0));
+      na[i] = norm_bwd_args(b, kind, d->final_ln[i], tape.condF[i], dy + static_cast<long long>(i) * E, ldY,
+                            last.s[i].xout, E, tape.stF[i], E, nullptr, 0, bt.s[i].dxout, E, bt.s[i].dxoutb,
+                            bt.s[i].dcondF, 0);
+    SEA_TRY(norm_bwd_group(b, V, na));
     if (ada) {
       const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
       float* dc[SEA_MAX_STREAMS]; const PackedLinear* W[SEA_MAX_STREAMS];
@@ -293,14 +329,18 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       q.dgrad = true; q.da_b16 = bt.s[i].dg; q.ld_dab = H;
     }
     SEA_TRY(linear_bwd(b, V, L));
-    for (int i = 0; i < V; ++i) {
-      sea_ln_gelu_bwd_args a{};
-      a.dg = bt.s[i].dg; a.lddg = H; a.h = lt.s[i].h; a.ldh = H; a.stats = lt.s[i].stH;
-      a.M = M; a.H = H; a.weight = bp.s[i].mlp_ln_w.p; a.bias = bp.s[i].mlp_ln_b.p;
-      a.dh = bt.s[i].dh; a.lddh = H; a.dweight = bp.s[i].mlp_ln_w.g; a.dbias = bp.s[i].mlp_ln_b.g;
+    {
+      sea_ln_gelu_bwd_args la[SEA_MAX_STREAMS];
+      for (int i = 0; i < V; ++i) {
+        sea_ln_gelu_bwd_args& a = la[i];
+        a = sea_ln_gelu_bwd_args{};
+        a.dg = bt.s[i].dg; a.lddg = H; a.h = lt.s[i].h; a.ldh = H; a.stats = lt.s[i].stH;
+        a.M = M; a.H = H; a.weight = bp.s[i].mlp_ln_w.p; a.bias = bp.s[i].mlp_ln_b.p;
+        a.dh = bt.s[i].dh; a.lddh = H; a.dweight = bp.s[i].mlp_ln_w.g; a.dbias = bp.s[i].mlp_ln_b.g;
+      }
       ++g_launches;
-      ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, 6.0 * M * static_cast<double>(H));
-      SEA_TRY(sea_ln_gelu_bwd(&a, b.st()));
+      ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, 6.0 * M * static_cast<double>(H) * V);
+      SEA_TRY(sea_ln_gelu_bwd_group(V, la, b.st()));
     }
     for (int i = 0; i < V; ++i) {
       LinB& q = L[i]; q = LinB{};
@@ -310,9 +350,13 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
     }
     SEA_TRY(linear_bwd(b, V, L));
     // Norm_{i,2} (+ skip) -> gradient at x2 = x_post + TIPI
-    for (int i = 0; i < V; ++i)
-      SEA_TRY(norm_bwd(b, kind, bp.s[i].ln2, lt.s[i].cond2, bt.s[i].dn2, E, lt.s[i].x2, E, lt.s[i].st2, E,
-                       bt.s[i].dx3, E, bt.s[i].dx2, E, bt.s[i].dx2b, bt.s[i].dcond2, 0));
+    {
+      sea_norm_bwd_args na[SEA_MAX_STREAMS];
+      for (int i = 0; i < V; ++i)
+        na[i] = norm_bwd_args(b, kind, bp.s[i].ln2, lt.s[i].cond2, bt.s[i].dn2, E, lt.s[i].x2, E, lt.s[i].st2, E,
+                              bt.s[i].dx3, E, bt.s[i].dx2, E, bt.s[i].dx2b, bt.s[i].dcond2, 0);
+      SEA_TRY(norm_bwd_group(b, V, na));
+    }
     if (ada) {
       const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
       float* dc[SEA_MAX_STREAMS]; const PackedLinear* W[SEA_MAX_STREAMS];
@@ -395,23 +439,30 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
           written = true; }
       }
     }
-    // pre-exchange branch of every stream: ln_cross + cross_down on x1
-    for (int i = 0; i < V; ++i) {
-      StreamTape& s = lt.s[i];
-      BwdStream& g = bt.s[i];
-      if (!pre_written[i]) {  // V == 1: the exchange is the identity
-        SEA_CUDA_OK(cudaMemcpyAsync(g.dx1, dxp[i], sizeof(float) * M * E, cudaMemcpyDeviceToDevice, b.c.s));
-        SEA_CUDA_OK(cudaMemcpyAsync(g.dx1b, dxpb[i], sizeof(bf16) * M * E, cudaMemcpyDeviceToDevice, b.c.s));
-        continue;
+    // pre-exchange branch of every stream: ln_cross + cross_down on x1 (grouped over the streams)
+    if (V == 1) {  // the exchange is the identity
+      BwdStream& g = bt.s[0];
+      SEA_CUDA_OK(cudaMemcpyAsync(g.dx1, dxp[0], sizeof(float) * M * E, cudaMemcpyDeviceToDevice, b.c.s));
+      SEA_CUDA_OK(cudaMemcpyAsync(g.dx1b, dxpb[0], sizeof(bf16) * M * E, cudaMemcpyDeviceToDevice, b.c.s));
+    } else {
+      sea_norm_bwd_args na[SEA_MAX_STREAMS];
+      for (int i = 0; i < V; ++i) {
+        StreamTape& s = lt.s[i];
+        BwdStream& g = bt.s[i];
+        na[i] = norm_bwd_args(b, kind, bp.s[i].ln_cross, s.condc, g.dnpre, Dd, s.dpre, Dd, s.stc_pre, Dd, nullptr, 0,
+                              g.ddn, Dd, g.ddnb, g.dcondc, (i < V - 1 && post_written[i]) ? 1 : 0);
       }
-      SEA_TRY(norm_bwd(b, kind, bp.s[i].ln_cross, s.condc, g.dnpre, Dd, s.dpre, Dd, s.stc_pre, Dd, nullptr, 0,
-                       g.ddn, Dd, g.ddnb, g.dcondc, (i < V - 1 && post_written[i]) ? 1 : 0));
-      LinB& q = L[0]; q = LinB{};
-      q.dy = g.ddnb; q.lddy = Dd; q.a = s.x1b; q.lda = E;
-      q.W = &bc.s[i].down; q.dW = bp.s[i].down_w.g; q.db = bp.s[i].down_b.g;
-      q.dgrad = true; q.da_f32 = g.dx1; q.ld_da = E; q.da_res = dxp[i]; q.ld_res = E;
-      q.da_b16 = g.dx1b; q.ld_dab = E;
-      SEA_TRY(linear_bwd(b, 1, L));
+      SEA_TRY(norm_bwd_group(b, V, na));
+      for (int i = 0; i < V; ++i) {
+        StreamTape& s = lt.s[i];
+        BwdStream& g = bt.s[i];
+        LinB& q = L[i]; q = LinB{};
+        q.dy = g.ddnb; q.lddy = Dd; q.a = s.x1b; q.lda = E;
+        q.W = &bc.s[i].down; q.dW = bp.s[i].down_w.g; q.db = bp.s[i].down_b.g;
+        q.dgrad = true; q.da_f32 = g.dx1; q.ld_da = E; q.da_res = dxp[i]; q.ld_res = E;
+        q.da_b16 = g.dx1b; q.ld_dab = E;
+      }
+      SEA_TRY(linear_bwd(b, V, L));
     }
     if (ada && V > 1) {
       const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
@@ -445,13 +496,17 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
     }
     SEA_TRY(linear_bwd(b, V, L));
     // Norm_{i,0} (+ skip) -> gradient at the layer input
-    for (int i = 0; i < V; ++i) {
-      float* dst = nullptr; long long ldd = E; bf16* dstb = nullptr;
-      if (l > 0) { dst = bt.s[i].dxout; dstb = bt.s[i].dxoutb; }
-      else if (dx) { dst = dx + static_cast<long long>(i) * E; ldd = ldY; }
-      else { dst = bt.s[i].dxout; }  // not requested: still needed for the parameter gradients
-      SEA_TRY(norm_bwd(b, kind, bp.s[i].ln0, lt.s[i].cond0, bt.s[i].dn0, E, xin[i], ldxin, lt.s[i].st0, E,
-                       bt.s[i].dx1, E, dst, ldd, dstb, bt.s[i].dcond0, 0));
+    {
+      sea_norm_bwd_args na[SEA_MAX_STREAMS];
+      for (int i = 0; i < V; ++i) {
+        float* dst = nullptr; long long ldd = E; bf16* dstb = nullptr;
+        if (l > 0) { dst = bt.s[i].dxout; dstb = bt.s[i].dxoutb; }
+        else if (dx) { dst = dx + static_cast<long long>(i) * E; ldd = ldY; }
+        else { dst = bt.s[i].dxout; }  // not requested: still needed for the parameter gradients
+        na[i] = norm_bwd_args(b, kind, bp.s[i].ln0, lt.s[i].cond0, bt.s[i].dn0, E, xin[i], ldxin, lt.s[i].st0, E,
+                              bt.s[i].dx1, E, dst, ldd, dstb, bt.s[i].dcond0, 0);
+      }
+      SEA_TRY(norm_bwd_group(b, V, na));
     }
     if (ada) {
       const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
