@@ -452,6 +452,13 @@ typedef struct sea_temporal_desc {
   sea_norm_params final_ln[SEA_MAX_STREAMS]; /* ln.{i} */
   const float* rope_self;  /* device, pair-major [(E/n_heads)/2, max_len, 2] (cos, sin) */
   const float* rope_cross; /* device, pair-major [(down_dim/n_heads)/2, max_len, 2] */
+  int32_t grads_fresh;     /* sea_temporal_backward only.  1 = the caller asserts that the gradient buffers of
+                              the nn.Linear WEIGHT matrices (everything the weight-gradient GEMMs write) hold no
+                              value worth keeping (optimizer.zero_grad()): their first contribution overwrites
+                              instead of accumulating, which saves zero-filling and re-reading 4 B/parameter.
+                              Every other gradient (biases, norm / TIPI / cond_mlp.0 parameters) still
+                              accumulates and must have been zeroed by the caller.  0 = accumulate everywhere. */
+  int32_t reserved1;
 } sea_temporal_desc;
 
 /* Packed low-precision copies of the weights (bf16, fused QKV / KV, optional transposes for the

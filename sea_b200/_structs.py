@@ -43,7 +43,8 @@ class TemporalDesc(C.Structure):
                 ("cond_cache", C.c_void_p), ("cond_cache_bytes", C.c_size_t),
                 ("blocks", C.POINTER(BlockParams)),
                 ("final_ln", NormParams * MAX_STREAMS),
-                ("rope_self", C.c_void_p), ("rope_cross", C.c_void_p)]
+                ("rope_self", C.c_void_p), ("rope_cross", C.c_void_p),
+                ("grads_fresh", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class NormArgs(C.Structure):

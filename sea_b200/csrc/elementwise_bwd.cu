@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const __grid_constant_
             const int k = 2 * q + e;
             const float xhat = (hv2[e] - mean) * rstd;
             const float u = xhat * ww[k] + bb[k];
-            const float dgu = gv2[e] * ptx::gelu_erf_grad(u);
+            const float dgu = gv2[e] * ptx::gelu_erf_grad_fast(u);
             aw[col + k] += dgu * xhat;   // this thread is the only writer of these columns
             ab[col + k] += dgu;
             const float dxh = dgu * ww[k];
@@ -244,9 +244,17 @@ __global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const __grid_constant_
     }
     __syncthreads();
   }
-  for (int i = tid; i < H; i += 256) {
-    atomicAdd(dweight + i, aw[i]);
-    atomicAdd(dbias + i, ab[i]);
+  __syncthreads();
+  if (((reinterpret_cast<uintptr_t>(dweight) | reinterpret_cast<uintptr_t>(dbias)) & 15) == 0) {
+    for (int i = tid * 4; i < H; i += 1024) {   // H % 8 == 0
+      ptx::red_add_v4(dweight + i, aw[i], aw[i + 1], aw[i + 2], aw[i + 3]);
+      ptx::red_add_v4(dbias + i, ab[i], ab[i + 1], ab[i + 2], ab[i + 3]);
+    }
+  } else {
+    for (int i = tid; i < H; i += 256) {
+      atomicAdd(dweight + i, aw[i]);
+      atomicAdd(dbias + i, ab[i]);
+    }
   }
 }
 
@@ -440,7 +448,9 @@ extern "C" int sea_ln_gelu_bwd_group(int n, const sea_ln_gelu_bwd_args* a, sea_s
     g.it[i] = LnGeluBwdItem{static_cast<const __nv_bfloat16*>(x->dg), static_cast<const __nv_bfloat16*>(x->h), x->stats,
                             x->weight, x->bias, static_cast<__nv_bfloat16*>(x->dh), x->dweight, x->dbias};
   }
-  const int rows = rows_per_cta_for(a->M * n, 1);
+  // one wave of CTAs (each keeps [2][H] partial sums in shared memory and ends with 2H global reductions)
+  int rows = (a->M * n + 147) / 148;
+  if (rows < 1) rows = 1;
   const dim3 grid((a->M + rows - 1) / rows, n);
   const size_t smem = sizeof(float) * 2 * a->H;
   static bool attr_set[16] = {};

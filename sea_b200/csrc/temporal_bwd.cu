@@ -31,6 +31,8 @@ struct BCtx {
   Ctx c;
   const float* ib;
   BwdTape* bt;
+  bool fresh = false;                 // desc->grads_fresh: first wgrad contribution overwrites
+  std::vector<const float*> touched;  // weight gradients already written by this call
   sea_stream_t st() const { return reinterpret_cast<sea_stream_t>(c.s); }
 };
 
@@ -98,7 +100,11 @@ int linear_bwd(BCtx& b, int n, LinB* L) {
         p.mn_major = SEA_GEMM_A_MN | SEA_GEMM_B_MN;
         float* dW = parts > 1 ? L[g].dW_split[part] : L[g].dW;
         p.epi.out_f32 = dW; p.epi.ld_out_f32 = K;
-        p.epi.residual = dW; p.epi.ld_residual = K;
+        // fresh gradients: the first contribution to a weight overwrites (no zero-fill, no read-back)
+        bool first_touch = b.fresh;
+        for (const float* t : b.touched) first_touch = first_touch && t != dW;
+        if (first_touch) { b.touched.push_back(dW); }
+        else { p.epi.residual = dW; p.epi.ld_residual = K; }
       }
       SEA_TRY(gemm(b, n, probs, Np, K, M));
       const bf16* src[SEA_MAX_STREAMS]; float* dbs[SEA_MAX_STREAMS];
@@ -280,6 +286,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
   b.c.fp32 = false; b.c.B = B; b.c.T = T; b.c.M = B * T;
   b.c.Mc = b.c.M; b.c.ld_ib = d->ib_num; b.c.cond_div = 1;
   b.ib = ib; b.bt = &bt;
+  b.fresh = d->grads_fresh != 0;
   const int M = b.c.M, V = d->num_streams, E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
   const int hd = E / d->n_heads, hdc = Dd / d->n_heads;
   const int kind = d->norm_kind;

@@ -243,17 +243,29 @@ class TemporalEngine:
         return out
 
     # ---- flat gradient buffer: param.grad are views into it (also the DP all-reduce bucket) ----
+    @staticmethod
+    def _is_gemm_weight(name: str, p: torch.Tensor) -> bool:
+        """Parameters whose gradient is produced by a weight-gradient GEMM (every nn.Linear weight on the
+        path except the tiny TIPI / cond_mlp.0 layers, whose gradients come from atomics)."""
+        return p.dim() == 2 and "ib.layers" not in name and "cond_mlp.0." not in name
+
     def _ensure_flat_grads(self):
         live = [(n, p) for n, p in self._live_params() if p.requires_grad]
+        # small / atomically accumulated gradients first, GEMM weight gradients last: after zero_grad only
+        # the first region has to be zero-filled (the weight-gradient GEMMs overwrite, desc.grads_fresh)
+        live.sort(key=lambda np_: self._is_gemm_weight(*np_))
         total = sum((p.numel() + 63) // 64 * 64 for _, p in live)
         dev = live[0][1].device
         if getattr(self, "_flat_grad", None) is None or self._flat_grad.numel() != total or self._flat_grad.device != dev:
             self._flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
             self._grad_views = {}
             off = 0
+            self._small_elems = 0
             for n, p in live:
                 self._grad_views[n] = self._flat_grad[off:off + p.numel()].view_as(p)
                 off += (p.numel() + 63) // 64 * 64
+                if not self._is_gemm_weight(n, p):
+                    self._small_elems = off
             self._desc = None  # pointers changed
         return live
 
@@ -271,8 +283,12 @@ class TemporalEngine:
         """torch semantics: grad None -> zeros; else keep accumulating.  All-None (the state after
         optimizer.zero_grad()) costs a single memset."""
         live = self._ensure_flat_grads()
+        self._grads_fresh = False
         if all(p.grad is None for _, p in live):
-            self._flat_grad.zero_()
+            # zero_grad(set_to_none=True): only the atomically accumulated gradients need zeros; the
+            # weight-gradient GEMMs overwrite their destinations on first touch (desc.grads_fresh)
+            self._flat_grad[: self._small_elems].zero_()
+            self._grads_fresh = True
             for n, p in live:
                 p.grad = self._grad_views[n]
             return
@@ -434,6 +450,8 @@ class TemporalEngine:
         ib = ib.contiguous().float()
         dy = dy.contiguous().float()
         dx = torch.empty_like(x) if need_dx else None
+        self._desc.grads_fresh = int(getattr(self, "_grads_fresh", False))
+        self._grads_fresh = False
         with torch.cuda.device(x.device):
             check(lib.sea_temporal_backward(C.byref(self._desc), C.c_void_p(self._cache.data_ptr()),
                                             C.c_void_p(x.data_ptr()), C.c_void_p(ib.data_ptr()),

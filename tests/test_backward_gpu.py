@@ -225,3 +225,31 @@ def test_training_loss_curve_100_steps(cuda, tag, ln):
           f"{losses[0]:.4f} -> {losses[-1]:.4f} (cuda); max per-step rel diff {rel.max():.3e}")
     assert ref_losses[-1] < 0.9 * ref_losses[0]          # it actually trains
     assert rel.max() < 2e-2
+
+
+def test_gradient_accumulation_and_fresh_overwrite(cuda):
+    """zero_grad(set_to_none) -> backward takes the 'fresh' path (weight-gradient GEMMs overwrite, only
+    the small-gradient region is zero-filled); a second backward without zero_grad must accumulate
+    (2x); a later fresh backward must not see stale values."""
+    g, sd, cfg, m, x, ib, tgt = _mirror("small_adaln", "adaln", cuda)
+    xg, ibg, tg = x.to(cuda), ib.to(cuda), tgt.to(cuda)
+
+    def run():
+        F.mse_loss(m(xg, ibg), tg).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+
+    m.engine().flat_grad().fill_(123.0)          # poison: the fresh path must not read it
+    for p in m.parameters():
+        p.grad = None
+    g1 = run()
+    g2 = run()                                    # accumulates on top of g1
+    for p in m.parameters():
+        p.grad = None
+    g3 = run()
+    assert len(g1) > 50
+    for n in g1:
+        assert torch.isfinite(g1[n]).all(), n
+        scale = g1[n].abs().max().item() + 1e-12
+        assert (g2[n] - 2 * g1[n]).abs().max().item() <= 2e-3 * scale + 1e-7, n      # atomics reorder sums
+        assert (g3[n] - g1[n]).abs().max().item() <= 2e-3 * scale + 1e-7, n
