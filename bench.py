@@ -67,7 +67,7 @@ def peaks():
 
 def gemm_traffic():
     """DRAM bytes per GEMM launch from the committed `ncu --set full` capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r1c_gemm_traffic.json")
     try:
         with open(path) as f:
             return float(json.load(f)["dram_bytes_per_launch"])
@@ -357,7 +357,7 @@ def main():
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["sustained"],
                      "unit": "TFLOP/s", "frac": gemm_tflops / pk["sustained"], "traffic": gemm_traffic(),
                      "traffic_note": "DRAM bytes per GEMM launch of the T=100 forward, ncu --set full "
-                                     "(profiles/r1b_summary.md section 2); not measured in this run",
+                                     "(profiles/r1c_summary.md section 2); not measured in this run",
                      "kernel": "gemm_bf16_tn_kernel (tcgen05)", "peak_source": pk["src"] + ", sustained",
                      "gemm_share_of_kernel_time": ps["gemm"]["ms"] / total_kernel_ms if total_kernel_ms else None,
                      "attention_tflops": attn_tflops, "attention_frac": attn_tflops / pk["sustained"],
