@@ -173,3 +173,45 @@ def test_kv_cached_rollout_matches_prefix_loop(cuda, tag, ln, prec, varying_ib):
     print(f"\n[kv-cached rollout] {tag} {prec} varying_ib={varying_ib}: cached {e_kv:.3e} prefix {e_pref:.3e} "
           f"(vs oracle); cached vs prefix {d:.3e}")
     assert e_kv < TOL[prec] and d < (1e-5 if prec == "fp32" else 1e-2)
+
+
+@pytest.mark.parametrize("cfg_name,E,ln", [("cylinder_flow", 1024, "adaln"), ("multiphase_flow", 2048, "ln")])
+def test_full_size_properties(cuda, cfg_name, E, ln):
+    """Size-independent properties at the bench's full width and batch (B=32, T=100), where the CPU
+    oracle would take minutes: (1) causality — the outputs of a prefix do not depend on later inputs;
+    (2) trajectories are independent — permuting the batch permutes the outputs; (3) the graphed,
+    eager and KV-cached rollouts agree."""
+    from sea_b200.rollout import rollout
+    from sea_b200.temporal import TemporalModel
+    torch.manual_seed(42)
+    m = TemporalModel(1, E, 8, 2024, 8, 0, 2, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln).to(cuda).eval()
+    B, T = 32, 100
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, T, 2, E, device=cuda, generator=g)
+    ib = torch.rand(B, T, 1, device=cuda, generator=g)
+    with torch.no_grad():
+        y = m(x, ib)
+        assert torch.isfinite(y).all()
+        # (1) causality: same arithmetic per row whatever T (tile schedules differ, sums along K do not
+        # except under stream-K) -> tight tolerance, not bit-exactness
+        for t in (1, 37, 64):
+            yt = m(x[:, :t].contiguous(), ib[:, :t].contiguous())
+            assert rel_l2(yt, y[:, :t]) < 2e-3, t
+        x2 = x.clone()
+        x2[:, 60:] = torch.randn(B, T - 60, 2, E, device=cuda, generator=g)
+        assert rel_l2(m(x2, ib)[:, :60], y[:, :60]) < 2e-3
+        # (2) batch equivariance (a row's k-block partial sums are associated by tile position under
+        # stream-K, so permuted rows agree to rounding, not bit for bit)
+        perm = torch.randperm(B, device=cuda, generator=g)
+        d_perm = rel_l2(m(x[perm].contiguous(), ib[perm].contiguous()), y[perm])
+        assert d_perm < 2e-3, d_perm
+        # (3) three engines, 24-step rollout, time-invariant ib
+        ibc = ib[:, :1].expand(B, 24, 1).contiguous()
+        x0 = x[:, :1].contiguous()
+        r_graph = rollout(m, x0, ibc, 24)
+        r_eager = rollout(m, x0, ibc, 24, graphs=False)
+        r_kv = rollout(m, x0, ibc, 24, cached=True)
+        assert torch.equal(r_graph, r_eager)
+        d = rel_l2(r_kv, r_graph)
+        print(f"\n[full-size properties] {cfg_name}: KV-cached vs prefix loop after 24 steps: {d:.3e}")
+        assert d < 2e-2
