@@ -162,10 +162,22 @@ typedef struct sea_norm_args {
   void* y_bf16;
   int64_t ldy_bf16;
   float* stats;
+  int32_t cond_folded;       /* AdaLN: the cond rows already hold the effective gamma | beta
+                                (sea_adaln_fold); weight / bias are then not read */
+  int32_t x_rows_per_batch;  /* > 0: x is a [B, *, ...] buffer with more rows per trajectory than this call
+                                covers: row m lives at x + (m / x_rows_per_batch) * x_batch_stride +
+                                (m % x_rows_per_batch) * ldx (a prefix of a longer sequence buffer) */
+  int64_t x_batch_stride;
 } sea_norm_args;
 int sea_norm_fwd(const sea_norm_args* args, sea_stream_t stream);
 /* `n` (1..SEA_MAX_STREAMS) norms of equal (M, d, kind) in ONE launch (the V field streams). */
 int sea_norm_fwd_group(int n, const sea_norm_args* host_args, sea_stream_t stream);
+
+/* In place: cond[r, :d] = weight + cond[r, :d] + 1, cond[r, d:] = bias + cond[r, d:] for R condition rows:
+ * AdaLN's effective gamma | beta (models/base_blocks.py:345-350), folded once per trajectory when the
+ * condition is time-invariant; consumed with sea_norm_args.cond_folded = 1. */
+int sea_adaln_fold(float* cond, int64_t ldc, int R, int d, const float* weight, const float* bias,
+                   sea_stream_t stream);
 
 /* AdaLN cond_mlp[0] + SiLU on the scalar condition: h[m,j] = SiLU(w1[j,:]·ib[m,:] + b1[j]), j < n
  * (models/base_blocks.py:337-339, 344).  Either output may be NULL. */

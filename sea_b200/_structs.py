@@ -56,7 +56,8 @@ class NormArgs(C.Structure):
                 ("tipi_hid", C.c_int32), ("tipi_w", C.c_void_p), ("tipi_b", C.c_void_p),
                 ("x_out", C.c_void_p), ("ldxo", C.c_int64), ("y_f32", C.c_void_p),
                 ("ldy_f32", C.c_int64), ("y_bf16", C.c_void_p), ("ldy_bf16", C.c_int64),
-                ("stats", C.c_void_p)]
+                ("stats", C.c_void_p), ("cond_folded", C.c_int32), ("x_rows_per_batch", C.c_int32),
+                ("x_batch_stride", C.c_int64)]
 
 
 class LnGeluArgs(C.Structure):

@@ -99,6 +99,8 @@ struct NormDev {
   float* y_f32; long long ldy_f32;
   __nv_bfloat16* y_bf16; long long ldy_bf16;
   float* stats;
+  int cond_folded;                 // cond rows already hold gamma | beta (sea_adaln_fold)
+  int x_rows; long long x_bs;      // x_rows > 0: row m of x lives at x + (m / x_rows) * x_bs + (m % x_rows) * ldx
 };
 
 constexpr int kNormMaxChunks = 16;  // 16 chunks x 32 lanes x 4 floats = 2048
@@ -114,7 +116,8 @@ __global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * (blockDim.x >> 5) + warp;
   if (m >= a.M) return;
-  const float* xr = a.x + static_cast<long long>(m) * a.ldx;
+  const float* xr = a.x_rows > 0 ? a.x + static_cast<long long>(m / a.x_rows) * a.x_bs + static_cast<long long>(m % a.x_rows) * a.ldx
+                                 : a.x + static_cast<long long>(m) * a.ldx;
   const float* cr = ADALN ? a.cond + static_cast<long long>(m / a.cond_div) * a.ldc : nullptr;
   const float* ar = a.add_rows ? a.add_rows + static_cast<long long>(m / a.add_div) * a.ld_add : nullptr;
   // Occupancy over prefetch: the grid of these small kernels should be resident in ONE wave
@@ -211,6 +214,100 @@ __global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const 
       }
     }
   }
+}
+
+// Inference variant for the two cases where the affine vectors are just two rows (plain LayerNorm:
+// weight only; AdaLN with the per-trajectory gamma | beta already folded by adaln_fold_kernel):
+// every global load of the row — x, the TIPI row, gamma, beta — is issued up front, so the warp pays
+// ONE memory round trip instead of two (the generic kernel loads the affine vectors after the
+// statistics to stay within 64 registers).  96-128 registers, 16 warps / SM, 3x the bytes in flight.
+template <int CH, bool FOLDED>
+__global__ void __launch_bounds__(256, (CH <= 8) ? 2 : 1) norm_fwd_prefetch_kernel(const __grid_constant__ NormGroup grp) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const NormDev& a = grp.it[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (m >= a.M) return;
+  const float* xr = a.x_rows > 0 ? a.x + static_cast<long long>(m / a.x_rows) * a.x_bs + static_cast<long long>(m % a.x_rows) * a.ldx
+                                 : a.x + static_cast<long long>(m) * a.ldx;
+  const float* gr = FOLDED ? a.cond + static_cast<long long>(m / a.cond_div) * a.ldc : a.weight;
+  const float* br = FOLDED ? gr + a.d : nullptr;
+  const float* ar = a.add_rows ? a.add_rows + static_cast<long long>(m / a.add_div) * a.ld_add : nullptr;
+  float4 v[CH], gm[CH], bt[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = c * 128 + lane * 4;
+    if (col < a.d) {
+      v[c] = *reinterpret_cast<const float4*>(xr + col);
+      gm[c] = __ldg(reinterpret_cast<const float4*>(gr + col));
+      if (FOLDED) bt[c] = __ldg(reinterpret_cast<const float4*>(br + col));
+    }
+  }
+  if (ar != nullptr) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = c * 128 + lane * 4;
+      if (col < a.d) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(ar + col));
+        v[c].x += t.x; v[c].y += t.y; v[c].z += t.z; v[c].w += t.w;
+        *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(m) * a.ldxo + col) = v[c];
+      }
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    if (c * 128 + lane * 4 < a.d) sum += v[c].x + v[c].y + v[c].z + v[c].w;
+  const float mean = warp_sum(sum) / a.d;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if (c * 128 + lane * 4 < a.d) {
+      const float dx = v[c].x - mean, dy = v[c].y - mean, dz = v[c].z - mean, dw = v[c].w - mean;
+      sq += dx * dx + dy * dy + dz * dz + dw * dw;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / a.d + 1e-5f);
+  if (a.stats && lane == 0) {
+    a.stats[2 * m] = mean;
+    a.stats[2 * m + 1] = rstd;
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = c * 128 + lane * 4;
+    if (col < a.d) {
+      const float4 w = gm[c];
+      const float4 b = FOLDED ? bt[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 y;
+      y.x = (v[c].x - mean) * rstd * w.x + b.x;
+      y.y = (v[c].y - mean) * rstd * w.y + b.y;
+      y.z = (v[c].z - mean) * rstd * w.z + b.z;
+      y.w = (v[c].w - mean) * rstd * w.w + b.w;
+      if (a.y_f32) *reinterpret_cast<float4*>(a.y_f32 + static_cast<long long>(m) * a.ldy_f32 + col) = y;
+      if (a.y_bf16) {
+        uint2 o;
+        o.x = ptx::pack_bf16(y.x, y.y);
+        o.y = ptx::pack_bf16(y.z, y.w);
+        *reinterpret_cast<uint2*>(a.y_bf16 + static_cast<long long>(m) * a.ldy_bf16 + col) = o;
+      }
+    }
+  }
+}
+
+// cond[r, :d] = weight + cond[r, :d] + 1 ;  cond[r, d:] = bias + cond[r, d:]   (in place, once per trajectory):
+// AdaLN's effective gamma | beta (models/base_blocks.py:345-350) for the rows of a condition cache.
+__global__ void __launch_bounds__(256) adaln_fold_kernel(float* __restrict__ cond, long long ldc, int R, int d,
+                                                         const float* __restrict__ weight,
+                                                         const float* __restrict__ bias) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (i >= d || r >= R) return;
+  float* row = cond + static_cast<long long>(r) * ldc;
+  row[i] = weight[i] + row[i] + 1.f;
+  row[d + i] = bias[i] + row[d + i];
 }
 
 // rows[r, n] = W3[n, :] . g[r, :] + b3[n]   — the TIPI term for `R` distinct conditions
@@ -714,6 +811,18 @@ static int launch_norm(const NormGroup& g, int n, cudaStream_t s) {
   const NormDev& d = g.it[0];
   const int rows_per_cta = 8;
   const dim3 grid((d.M + rows_per_cta - 1) / rows_per_cta, n);
+  bool prefetch = d.tipi_g == nullptr;   // the general (per-token) TIPI path stays in the generic kernel
+  for (int i = 0; i < n; ++i)
+    prefetch = prefetch && g.it[i].tipi_g == nullptr && g.it[i].cond_folded == d.cond_folded &&
+               (d.kind != SEA_NORM_ADALN || g.it[i].cond_folded);
+  if (prefetch && d.kind == SEA_NORM_ADALN) {
+    SEA_LAUNCH((norm_fwd_prefetch_kernel<CH, true>), grid, rows_per_cta * 32, 0, s, g);
+    return static_cast<int>(cudaGetLastError());
+  }
+  if (prefetch && d.kind == SEA_NORM_LN) {
+    SEA_LAUNCH((norm_fwd_prefetch_kernel<CH, false>), grid, rows_per_cta * 32, 0, s, g);
+    return static_cast<int>(cudaGetLastError());
+  }
   if (d.kind == SEA_NORM_ADALN) SEA_LAUNCH((norm_fwd_kernel<CH, true>), grid, rows_per_cta * 32, 0, s, g);
   else SEA_LAUNCH((norm_fwd_kernel<CH, false>), grid, rows_per_cta * 32, 0, s, g);
   return static_cast<int>(cudaGetLastError());
@@ -739,7 +848,19 @@ static int fill_norm(const sea_norm_args* a, NormDev& d) {
   d.y_f32 = a->y_f32; d.ldy_f32 = a->ldy_f32;
   d.y_bf16 = static_cast<__nv_bfloat16*>(a->y_bf16); d.ldy_bf16 = a->ldy_bf16;
   d.stats = a->stats;
+  d.cond_folded = a->cond_folded;
+  d.x_rows = a->x_rows_per_batch; d.x_bs = a->x_batch_stride;
+  if (a->cond_folded && a->kind != SEA_NORM_ADALN) return SEA_ERR_INVALID;
+  if (a->x_rows_per_batch < 0 || (a->x_rows_per_batch > 0 && (a->x_batch_stride % 4))) return SEA_ERR_INVALID;
   return SEA_OK;
+}
+
+extern "C" int sea_adaln_fold(float* cond, int64_t ldc, int R, int d, const float* weight, const float* bias,
+                              sea_stream_t stream) {
+  if (!cond || !weight || !bias || R <= 0 || d <= 0 || ldc < 2LL * d) return SEA_ERR_INVALID;
+  dim3 grid((d + 255) / 256, R);
+  SEA_LAUNCH(adaln_fold_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), cond, static_cast<long long>(ldc), R, d, weight, bias);
+  return static_cast<int>(cudaGetLastError());
 }
 
 extern "C" int sea_norm_fwd_group(int n, const sea_norm_args* a, sea_stream_t stream) {

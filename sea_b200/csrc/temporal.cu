@@ -408,6 +408,7 @@ NormCall norm_call(Ctx& c, int kind, const sea_norm_params& np, const float* con
   a.weight = np.weight.p;
   a.bias = kind == SEA_NORM_ADALN ? np.bias.p : nullptr;
   a.cond = cond; a.ldc = 2LL * dim; a.cond_div = c.cond_div;
+  a.cond_folded = (kind == SEA_NORM_ADALN && c.inv) ? 1 : 0;   // per-trajectory rows hold gamma | beta already
   if (tipi && c.inv) {
     a.add_rows = tipi_g; a.ld_add = dim; a.add_div = c.cond_div;  // tipi_g = per-trajectory TIPI rows
     a.x_out = x_out; a.ldxo = dim;
@@ -678,6 +679,23 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
         np[i] = &d->final_ln[i]; hid[i] = tape.hidF[i]; W[i] = &cl.c2_final[i]; cond[i] = tape.condF[i];
       }
       SEA_TRY(adaln_cond(c, V, np, hid, W, cond, 2 * E, ib));
+    }
+    if (ada && inv) {
+      // one condition row per trajectory: fold AdaLN's own weight / bias into it once, so the norm
+      // kernels read two vectors per row instead of four (models/base_blocks.py:345-350)
+      for (int l = 0; l < d->num_layers; ++l)
+        for (int i = 0; i < V; ++i) {
+          const sea_stream_params& sp = d->blocks[l].s[i];
+          StreamTape& stp = tape.L[l].s[i];
+          SEA_TRY(sea_adaln_fold(stp.cond0, 2LL * E, B, E, sp.ln0.weight.p, sp.ln0.bias.p, st));
+          SEA_TRY(sea_adaln_fold(stp.cond2, 2LL * E, B, E, sp.ln2.weight.p, sp.ln2.bias.p, st));
+          SEA_TRY(sea_adaln_fold(stp.condc, 2LL * Dd, B, Dd, sp.ln_cross.weight.p, sp.ln_cross.bias.p, st));
+          g_launches += 3;
+        }
+      for (int i = 0; i < V; ++i) {
+        SEA_TRY(sea_adaln_fold(tape.condF[i], 2LL * E, B, E, d->final_ln[i].weight.p, d->final_ln[i].bias.p, st));
+        ++g_launches;
+      }
     }
   }
 
