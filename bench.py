@@ -349,8 +349,8 @@ def main():
                    "l2": "no flush: per-step working set (174 MB bf16 weights + activations up to "
                          ">1 GB) exceeds the 126 MB L2",
                    "bench_step": f"one {R}-step rollout of {B} trajectories per GPU",
-                   "execution": "sea_b200.rollout.RolloutPlan: one CUDA graph per prefix length (gather prefix, "
-                                "full forward over the prefix, append last step); the roofline leg replays the "
+                   "execution": "sea_b200.rollout.RolloutPlan: one CUDA graph per prefix length (full forward "
+                                "over the prefix read in place from the sequence buffer, append last step); the roofline leg replays the "
                                 "same kernels eagerly with per-launch CUDA events",
                    "algorithmic_tflop_per_step_per_gpu": flops / 1e12,
                    "model_tflops_per_gpu": flops / (ms_step * 1e-3) / 1e12},

@@ -88,7 +88,10 @@ typedef struct sea_gemm_epilogue {
   int64_t ld_out_bf16;
   int32_t rope_pos0;        /* position of row m is rope_pos0 + (m % seq_len): the incremental (KV-cached)
                                step rotates its single new token by its absolute position */
-  int32_t reserved0;
+  int32_t res_rows_per_batch; /* > 0: the residual is a [B, *, ...] buffer with more rows per trajectory than this
+                                 call covers: row m lives at residual + (m / res_rows_per_batch) * res_batch_stride
+                                 + (m % res_rows_per_batch) * ld_residual */
+  int64_t res_batch_stride;
 } sea_gemm_epilogue;
 
 typedef struct sea_gemm_problem {
@@ -508,6 +511,12 @@ int sea_temporal_step(const sea_temporal_desc* d, const void* cache, void* kv_ca
                       int max_len, const float* x_t, int64_t x_batch_stride, const float* ib_t,
                       int64_t ib_batch_stride, float* y_t, int64_t y_batch_stride, int B, int pos,
                       void* workspace, size_t workspace_bytes, sea_stream_t stream);
+/* sea_temporal_forward on a prefix of a longer sequence buffer: x is [B, >= T, V, E] with
+ * `x_batch_stride` elements between trajectories (the rollout loop keeps ONE [B, steps+1, V, E] buffer and
+ * runs the model on x[:, :T] without gathering the prefix first).  Inference only. */
+int sea_temporal_forward_strided(const sea_temporal_desc* d, const void* cache, const float* x,
+                                 int64_t x_batch_stride, const float* ib, float* y, int B, int T,
+                                 void* workspace, size_t workspace_bytes, sea_stream_t stream);
 /* Backward of the last sea_temporal_forward(..., training=1) that used this `workspace`
  * (autograd in the reference, train/train_temporal.py:257).  dy [B,T,V,E] fp32 contiguous.
  * Parameter gradients ACCUMULATE (+=) into the `g` pointers of the descriptor (NULL = frozen);

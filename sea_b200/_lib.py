@@ -37,7 +37,8 @@ class GemmEpilogue(C.Structure):
         ("out_bf16", C.c_void_p),
         ("ld_out_bf16", C.c_int64),
         ("rope_pos0", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("res_rows_per_batch", C.c_int32),
+        ("res_batch_stride", C.c_int64),
     ]
 
 

@@ -42,6 +42,7 @@ struct DevEpilogue {
   __nv_bfloat16* out_bf16;
   long long ld_residual, ld_gelu, ld_out_f32, ld_out_pre_bf16, ld_out_bf16;
   int act, rope_cols, head_dim, seq_len, rope_ld, rope_pos0;
+  int res_rows; long long res_bs;  // res_rows > 0: residual row m at (m / res_rows) * res_bs + (m % res_rows) * ld_residual
   float rope_sign;
   int vec8;  // every row base / pitch is 32-byte aligned: use 256-bit global accesses
 };
@@ -110,7 +111,8 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
         }
       }
       if (e.residual != nullptr) {
-        const float* rp = e.residual + static_cast<long long>(m) * e.ld_residual + n0;
+        const float* rp = e.residual + (e.res_rows > 0 ? static_cast<long long>(m / e.res_rows) * e.res_bs + static_cast<long long>(m % e.res_rows) * e.ld_residual
+                                                       : static_cast<long long>(m) * e.ld_residual) + n0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           if (j < nvalid) {
@@ -138,7 +140,8 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
     }
   }
   if (first && e.residual != nullptr) {
-    const float* rp = e.residual + static_cast<long long>(m) * e.ld_residual + n0;
+    const float* rp = e.residual + (e.res_rows > 0 ? static_cast<long long>(m / e.res_rows) * e.res_bs + static_cast<long long>(m % e.res_rows) * e.ld_residual
+                                                   : static_cast<long long>(m) * e.ld_residual) + n0;
     if (e.vec8) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
@@ -812,11 +815,13 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
     d.seq_len = e.seq_len;
     d.rope_ld = e.rope_ld;
     d.rope_pos0 = e.rope_pos0;
+    d.res_rows = e.res_rows_per_batch; d.res_bs = e.res_batch_stride;
     d.rope_sign = (e.rope_sign == 0.0f) ? 1.0f : e.rope_sign;
     auto al32 = [](const void* ptr, long long ld_elems, int esz) {
       return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr) & 31) == 0) && ((ld_elems * esz) % 32 == 0));
     };
-    d.vec8 = (N % 16 == 0) && al32(e.residual, e.ld_residual, 4) && al32(e.out_f32, e.ld_out_f32, 4) &&
+    if (e.res_rows_per_batch < 0 || (e.res_rows_per_batch > 0 && (e.res_batch_stride % 4))) return SEA_ERR_INVALID;
+    d.vec8 = (N % 16 == 0) && al32(e.residual, e.ld_residual, 4) && (e.res_rows_per_batch == 0 || (e.res_batch_stride * 4) % 32 == 0) && al32(e.out_f32, e.ld_out_f32, 4) &&
              al32(e.out_pre_bf16, e.ld_out_pre_bf16, 2) && al32(e.out_bf16, e.ld_out_bf16, 2);
   }
   const int total = p.tiles_m * p.tiles_n * p.groups;

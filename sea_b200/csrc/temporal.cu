@@ -366,6 +366,7 @@ int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, c
     sea_gemm_epilogue& e = p.epi;
     e.bias = o.bias;
     e.residual = o.residual; e.ld_residual = o.ld_res;
+    e.res_rows_per_batch = o.res_rows; e.res_batch_stride = o.res_bs;
     e.act = o.act;
     if (o.rope_cols > 0) {
       e.rope_cols = o.rope_cols; e.head_dim = o.head_dim; e.seq_len = c.T;
@@ -560,7 +561,7 @@ extern "C" size_t sea_temporal_kv_cache_bytes(const sea_temporal_desc* d, int B,
 
 static int forward_impl(const sea_temporal_desc* d, const void* cache, const float* x, const float* ib, float* y,
                         int B, int T, void* workspace, size_t workspace_bytes, int training,
-                        const StepCtx* step, sea_stream_t stream);
+                        const StepCtx* step, sea_stream_t stream, long long x_seq_bs = 0);
 
 extern "C" int sea_temporal_forward(const sea_temporal_desc* d, const void* cache, const float* x,
                                     const float* ib, float* y, int B, int T, void* workspace,
@@ -586,9 +587,17 @@ extern "C" int sea_temporal_step(const sea_temporal_desc* d, const void* cache, 
   return forward_impl(d, cache, x_t, ib_t, y_t, B, 1, workspace, workspace_bytes, 0, &sc, stream);
 }
 
+extern "C" int sea_temporal_forward_strided(const sea_temporal_desc* d, const void* cache, const float* x,
+                                            int64_t x_batch_stride, const float* ib, float* y, int B, int T,
+                                            void* workspace, size_t workspace_bytes, sea_stream_t stream) {
+  if (!d || x_batch_stride < static_cast<int64_t>(T) * d->num_streams * d->embed_dim || (x_batch_stride % 8))
+    return SEA_ERR_INVALID;
+  return forward_impl(d, cache, x, ib, y, B, T, workspace, workspace_bytes, 0, nullptr, stream, x_batch_stride);
+}
+
 static int forward_impl(const sea_temporal_desc* d, const void* cache, const float* x, const float* ib, float* y,
                         int B, int T, void* workspace, size_t workspace_bytes, int training,
-                        const StepCtx* step, sea_stream_t stream) {
+                        const StepCtx* step, sea_stream_t stream, long long x_seq_bs) {
   SEA_TRY(validate_desc(d));
   if (!cache || !x || !ib || !y || !workspace || B <= 0 || T <= 0) return SEA_ERR_INVALID;
   if (T > d->max_len) return SEA_ERR_UNSUPPORTED;
@@ -715,9 +724,13 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
     // (1) x_i += SelfAttn_i(Norm_{i,0}(x_i))          models/temporal.py:135-136
     NormCall ncall[SEA_MAX_STREAMS];
     sea_attn_args acall[SEA_MAX_STREAMS];
-    for (int i = 0; i < V; ++i)
+    // layer 0 may read a prefix of a longer [B, steps+1, V, E] sequence buffer in place
+    const bool xs = (l == 0 && x_seq_bs > 0);
+    for (int i = 0; i < V; ++i) {
       ncall[i] = norm_call(c, kind, bp.s[i].ln0, lt.s[i].cond0, xin[i], ldxin, E, lt.s[i].n0, nullptr, 0,
                            lt.s[i].st0, nullptr, nullptr, nullptr);
+      if (xs) { ncall[i].a.x_rows_per_batch = T; ncall[i].a.x_batch_stride = x_seq_bs; }
+    }
     SEA_TRY(norm_group(c, V, ncall));
     for (int i = 0; i < V; ++i) {
       in[i] = LinIn{lt.s[i].n0, E, 0};
@@ -754,6 +767,7 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
       W[i] = &bc.s[i].sproj;
       out[i] = LinOut{};
       out[i].residual = xin[i]; out[i].ld_res = ldxin;
+      if (xs) { out[i].res_rows = T; out[i].res_bs = x_seq_bs; }
       out[i].f32 = lt.s[i].x1; out[i].ld_f32 = E;
       out[i].pre = lt.s[i].x1b; out[i].ld_pre = E;
     }

@@ -123,6 +123,7 @@ struct LinIn {
 struct LinOut {
   const float* bias;
   const float* residual; long long ld_res;
+  int res_rows; long long res_bs;   // residual is a prefix of a longer per-trajectory buffer (see sea_gemm_epilogue)
   float* f32; long long ld_f32;   // fp32 copy of v
   void* pre; long long ld_pre;    // act-dtype copy of v
   void* post; long long ld_post;  // act-dtype copy of act(v)

@@ -38,7 +38,7 @@ def gemm_problem(a, b, *, bias=None, residual=None, gelu_grad_of=None, act=ACT_N
         _ptr(bias), _ptr(residual), _ld(residual), _ptr(gelu_grad_of), _ld(gelu_grad_of), act,
         rope_cols, head_dim, seq_len, float(rope_sign), rope_ld, _ptr(rope_table),
         _ptr(out_f32), _ld(out_f32), _ptr(out_pre_bf16), _ld(out_pre_bf16),
-        _ptr(out_bf16), _ld(out_bf16), int(rope_pos0), 0)
+        _ptr(out_bf16), _ld(out_bf16), int(rope_pos0), 0, 0)
     return GemmProblem(_ptr(a), a.stride(0), _ptr(b), b.stride(0), e, int(b_is_static), int(mn_major))
 
 

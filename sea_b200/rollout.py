@@ -27,9 +27,9 @@ class RolloutPlan:
     """The same loop with every step pre-recorded as a CUDA graph.
 
     Step t (prefix length t) of the reference loop is: forward over the whole prefix, append the
-    last output.  Both are recorded once per (B, steps): graph t = [gather prefix seq[:, :t] into
-    the contiguous forward input] -> [the ~30 kernels of sea_temporal_forward at T = t] ->
-    [scatter y[:, -1] into seq[:, t]].  Replaying costs one cudaGraphLaunch per step instead of
+    last output.  Both are recorded once per (B, steps): graph t = [the 22 kernels of
+    sea_temporal_forward at T = t, reading the prefix seq[:, :t] in place from the plan's
+    [B, steps+1, V, E] sequence buffer] -> [append y[:, -1] to seq[:, t]].  Replaying costs one cudaGraphLaunch per step instead of
     ~30 kernel launches + tensor-map encodes + torch.cat on the host, which is what bounds the short
     prefixes.  Arithmetic, kernels and per-step work are exactly those of the eager loop (the full
     prefix is still recomputed every step); requires a time-invariant ib (checked by the caller)."""
@@ -45,7 +45,6 @@ class RolloutPlan:
         self.V, self.E = V, E
         f32 = dict(dtype=torch.float32, device=device)
         self.seq = torch.zeros(B, steps + 1, V, E, **f32)
-        self.xin = torch.empty(B * steps * V * E, **f32)
         self.y = torch.empty(B * steps * V * E, **f32)
         self.ib1 = torch.zeros(B, 1, nib, **f32)      # step 1 reads ib as [B,1,nib]
         self.ib2 = torch.zeros(B, 2, nib, **f32)      # step 2 (first time-invariant call) as [B,2,nib]
@@ -59,11 +58,11 @@ class RolloutPlan:
 
     def _step(self, t: int) -> int:
         B, V, E = self.B, self.V, self.E
-        x = self.xin[: B * t * V * E].view(B, t, V, E)
         y = self.y[: B * t * V * E].view(B, t, V, E)
-        x.copy_(self.seq[:, :t])
         ib = self.ib1 if t == 1 else self.ib2   # only read while the condition cache is not valid (t <= 2)
-        n = self.eng.forward_into(x, ib, y, self.ws, time_invariant=True, cond_buf=self.cond, cond_valid=t > 2)
+        # the model reads the prefix in place from the sequence buffer (batch-strided view, no gather)
+        n = self.eng.forward_into(self.seq[:, :t], ib, y, self.ws, time_invariant=True, cond_buf=self.cond,
+                                  cond_valid=t > 2)
         self.seq[:, t].copy_(y[:, t - 1])
         return n
 
@@ -81,7 +80,7 @@ class RolloutPlan:
                 n = self._step(t)
             pool = g.pool()
             self.graphs.append(g)
-            self.launches.append(n + 2)
+            self.launches.append(n + 1)
         torch.cuda.current_stream().wait_stream(side)
 
     def valid_for(self, eng) -> bool:

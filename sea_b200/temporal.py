@@ -509,10 +509,14 @@ class TemporalEngine:
     def forward_into(self, x: torch.Tensor, ib: torch.Tensor, y: torch.Tensor, ws: torch.Tensor, *,
                      time_invariant: bool, cond_buf: Optional[torch.Tensor] = None,
                      cond_valid: bool = False) -> int:
-        """Allocation-free inference forward (CUDA-graph capturable): contiguous fp32 x [B,T,V,E],
+        """Allocation-free inference forward (CUDA-graph capturable): fp32 x [B,T,V,E] — contiguous, or
+        a prefix view ``seq[:, :T]`` of a longer [B,S,V,E] buffer (only the batch stride may differ) —
         ib [B,T,ib_num] -> y, activations in the caller's workspace ``ws``; the caller has already
         run ``_ensure(False)``.  Returns the number of kernels enqueued."""
         B, T, V, E = x.shape
+        if x.dtype != torch.float32 or x.stride(3) != 1 or x.stride(2) != E or x.stride(1) != V * E:
+            raise RuntimeError("sea_b200 forward_into: x must be fp32 [B,T,V,E] with contiguous trajectories")
+        strided = x.stride(0) != T * V * E
         d = self._desc
         d.ib_time_invariant = int(time_invariant)
         if cond_buf is not None and time_invariant and T > 1:
@@ -520,12 +524,20 @@ class TemporalEngine:
         else:
             d.cond_cache, d.cond_cache_bytes, d.cond_cache_valid = None, 0, 0
         with torch.cuda.device(x.device):
-            check(lib.sea_temporal_forward(C.byref(d), C.c_void_p(self._cache.data_ptr()),
-                                           C.c_void_p(x.data_ptr()), C.c_void_p(ib.data_ptr()),
-                                           C.c_void_p(y.data_ptr()), B, T, C.c_void_p(ws.data_ptr()),
-                                           C.c_size_t(ws.numel()), 0,
-                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)),
-                  "temporal_forward")
+            if strided:
+                check(lib.sea_temporal_forward_strided(C.byref(d), C.c_void_p(self._cache.data_ptr()),
+                                                       C.c_void_p(x.data_ptr()), C.c_int64(x.stride(0)),
+                                                       C.c_void_p(ib.data_ptr()), C.c_void_p(y.data_ptr()), B, T,
+                                                       C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()),
+                                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                      "temporal_forward_strided")
+            else:
+                check(lib.sea_temporal_forward(C.byref(d), C.c_void_p(self._cache.data_ptr()),
+                                               C.c_void_p(x.data_ptr()), C.c_void_p(ib.data_ptr()),
+                                               C.c_void_p(y.data_ptr()), B, T, C.c_void_p(ws.data_ptr()),
+                                               C.c_size_t(ws.numel()), 0,
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                      "temporal_forward")
         return int(lib.sea_last_launch_count())
 
     @torch.no_grad()
