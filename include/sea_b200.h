@@ -576,6 +576,28 @@ int sea_spatial_encode(const sea_spatial_desc* d, float* x, float* z, int B, int
 int sea_spatial_decode(const sea_spatial_desc* d, const float* z, float* out, int B, int latent_layout,
                        sea_stream_t stream);
 
+/* ------------------------------------------------------------------ mesh patchify / unpatch ----
+ * DataPartitioner2D of the reference (utils/data_processors.py:9-111; called from patchify_and_scale
+ * :484-542 and inverse_scale_and_unpatch :553-573) on the device.  All index work is exact:
+ *   sea_patch_bucketize   patch_id[c] = (ix-1)*(n-1) + (iy-1) with ix = clamp(bucketize(x[c], x_boundary,
+ *                         right=True), 1, m-1) (:34-38), and the cell count of every patch (counts is
+ *                         zeroed by the call; max(counts) is the padded patch length `capacity`);
+ *   sea_patch_index_map   index_map[p, :] = ascending cell indices of patch p (mask.nonzero(), :43-45),
+ *                         padded to `capacity` with pad_id (< 0) (:61-88);
+ *   sea_patch_gather      out[s, p, c, f] = fields[f][s, index_map[p, c]], pad -> pad_value  (layout_pfc = 0:
+ *                         the reference's stacked [S, P, C, F], :529; layout_pfc = 1: [S, P, F, C], the
+ *                         SpatialModel input); fields[f] is [S, n_cells] with row pitch ld_field; F <= 8;
+ *   sea_patch_scatter     inverse_partition (:90-111): out[s, index_map[p, c], f] = part[s, p, c, f]. */
+int sea_patch_bucketize(const float* x, const float* y, int n_cells, const float* x_boundary, int m,
+                        const float* y_boundary, int n, int32_t* patch_id, int32_t* counts, sea_stream_t stream);
+int sea_patch_index_map(const int32_t* patch_id, int n_cells, int n_patches, int capacity, int64_t pad_id,
+                        int64_t* index_map, sea_stream_t stream);
+int sea_patch_gather(const float* const* host_field_ptrs, int n_fields, int64_t ld_field, const int64_t* index_map,
+                     int n_snapshots, int n_patches, int capacity, float pad_value, int layout_pfc, float* out,
+                     sea_stream_t stream);
+int sea_patch_scatter(const float* part, const int64_t* index_map, int n_snapshots, int n_patches, int capacity,
+                      int n_fields, int n_cells, int layout_pfc, float* out, sea_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -326,6 +326,29 @@ def run_sk():
     lib.sea_gemm_set_workspace(None, C.c_size_t(0))
 
 
+def run_patchify():
+    """Mesh patchify / unpatch throughput (HBM-bound gather / scatter), 60k-cell mesh, 3 fields."""
+    from sea_b200.patchify import DataPartitioner2D
+    g = torch.Generator(device="cuda").manual_seed(1)
+    N, F = 60_000, 3
+    x = torch.rand(N, device=dev, generator=g) * 2.2
+    y = torch.rand(N, device=dev, generator=g) * 0.41
+    for S in (256, 2048):
+        vars_ = [torch.randn(S, N, device=dev, generator=g) for _ in range(F)]
+        part = DataPartitioner2D(x, y, device=dev)
+        t_idx = timeit(lambda: part._build_index(), reps=5, warm=1)
+        stacked = torch.stack(vars_, 0)
+        fields = part.gather(vars_)
+        us_g = timeit(lambda: part.gather(vars_), reps=10, warm=2) - timeit(lambda: torch.stack(vars_, 0), reps=10, warm=2)
+        us_gp = timeit(lambda: part.gather(vars_, layout_pfc=True), reps=10, warm=2)
+        us_s = timeit(lambda: part.scatter(fields), reps=10, warm=2)
+        P, Cc = part.index_map_tensor.shape
+        by_g = 4.0 * S * N * F + 4.0 * S * P * Cc * F
+        print(f"patchify S={S} N={N} F={F} P={P} C={Cc}: index {t_idx:.0f} us | gather {us_g:.0f} us "
+              f"({by_g/us_g/1e3:.0f} GB/s) | gather+stack [S,P,F,C] {us_gp:.0f} us | scatter {us_s:.0f} us ({by_g/us_s/1e3:.0f} GB/s)", flush=True)
+        del vars_, fields, stacked
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gemm"
-    {"gemm": run_gemm, "attn": run_attn, "train": run_train, "rollout": run_rollout, "floor": run_floor, "kblock": run_kblock, "sk": run_sk}[what]()
+    {"gemm": run_gemm, "attn": run_attn, "train": run_train, "rollout": run_rollout, "floor": run_floor, "kblock": run_kblock, "sk": run_sk, "patchify": run_patchify}[what]()
