@@ -92,6 +92,11 @@ typedef struct sea_gemm_epilogue {
                                  call covers: row m lives at residual + (m / res_rows_per_batch) * res_batch_stride
                                  + (m % res_rows_per_batch) * ld_residual */
   int64_t res_batch_stride;
+  float dropout_p;          /* > 0: nn.Dropout on (acc + bias) BEFORE the residual is added
+                               (MLP.forward, models/base_blocks.py:44-47 followed by the skip, temporal.py:145);
+                               element (m, n) uses mask index m * N + n of `dropout_site` (sea_dropout_mask) */
+  uint32_t dropout_site;
+  uint64_t dropout_seed;
 } sea_gemm_epilogue;
 
 typedef struct sea_gemm_problem {
@@ -171,6 +176,10 @@ typedef struct sea_norm_args {
                                 covers: row m lives at x + (m / x_rows_per_batch) * x_batch_stride +
                                 (m % x_rows_per_batch) * ldx (a prefix of a longer sequence buffer) */
   int64_t x_batch_stride;
+  float tipi_dropout_p;      /* > 0: nn.Dropout on the TIPI term (W3 g + b3) before it is added to x
+                                (the `ib` MLP's own dropout, models/base_blocks.py:47); mask index m * d + col */
+  uint32_t tipi_dropout_site;
+  uint64_t tipi_dropout_seed;
 } sea_norm_args;
 int sea_norm_fwd(const sea_norm_args* args, sea_stream_t stream);
 /* `n` (1..SEA_MAX_STREAMS) norms of equal (M, d, kind) in ONE launch (the V field streams). */
@@ -203,6 +212,16 @@ int sea_tipi_rows(const float* g, int64_t ldg, int R, int E, int hid, const floa
 int sea_tipi_hidden(const float* ib, int64_t ld_ib, int M, int ib_num, const float* w0, const float* b0,
                     const float* ln_w, const float* ln_b, int hid, float* g_out, float* pre_out,
                     float* stats_out, sea_stream_t stream);
+
+/* Dropout helpers.  sea_dropout_mask writes the keep decisions (1 / 0) of elements [0, n) of `site` —
+ * what the fused kernels apply on the fly — so a test can feed the identical masks to a reference
+ * implementation.  sea_dropout_apply: dst[m, n] = src[m, n] * mask(m * N + n) / (1 - p) for an [M, N] fp32
+ * matrix (row pitch ld_src), fp32 and / or bf16 destination (used by the backward pass for the gradients that
+ * enter a dropped branch).  Site ids of the temporal executor: ((layer * 4 + kind) * 4 + i) * 4 + j with
+ * kind 0 = self-attention of stream i, 1 = exchange attention (i, j), 2 = stream-MLP output, 3 = TIPI output. */
+int sea_dropout_mask(uint64_t seed, uint32_t site, int64_t n, float p, uint8_t* out, sea_stream_t stream);
+int sea_dropout_apply(const float* src, int64_t ld_src, int M, int N, uint64_t seed, uint32_t site, float p,
+                      float* dst_f32, int64_t ld_f32, void* dst_bf16, int64_t ld_bf16, sea_stream_t stream);
 
 /* ------------------------------------------------------------------ K6: LayerNorm(H) + GELU --
  * The MLP's inner nn.LayerNorm(H) (affine, eps 1e-5) followed by exact-erf GELU
@@ -332,6 +351,11 @@ typedef struct sea_attn_args {
   int32_t src_len;
   float scale;
   int32_t prec; /* SEA_PREC_BF16: bf16 in/out; SEA_PREC_FP32: fp32 in/out */
+  float dropout_p;        /* > 0 (bf16 tensor-core path only): nn.Dropout on the attention probabilities after
+                             the softmax (models/base_blocks.py:194, 286); element (b, h, q, k) uses mask index
+                             ((b * n_heads + h) * T + q) * T2 + k, T2 = T rounded up to even */
+  uint32_t dropout_site;
+  uint64_t dropout_seed;
 } sea_attn_args;
 int sea_attention_fwd(const sea_attn_args* args, sea_stream_t stream);
 /* `n` (1..SEA_MAX_STREAMS) problems of identical shape (B, T, n_heads, head_dim, src_len, scale,
@@ -376,6 +400,9 @@ typedef struct sea_attn_bwd_args {
   int32_t prec;
   const float* rope_table; /* pair-major [head_dim/2, rope_ld, 2] or NULL */
   int32_t rope_ld;
+  float dropout_p;         /* must repeat the forward's dropout_p / site / seed (the mask is regenerated) */
+  uint32_t dropout_site;
+  uint64_t dropout_seed;
 } sea_attn_bwd_args;
 int sea_attention_bwd(const sea_attn_bwd_args* args, sea_stream_t stream);
 /* Test hook: 1 forces the CUDA-core kernel even where the tcgen05 kernel applies. */
@@ -467,6 +494,12 @@ typedef struct sea_temporal_desc {
   sea_norm_params final_ln[SEA_MAX_STREAMS]; /* ln.{i} */
   const float* rope_self;  /* device, pair-major [(E/n_heads)/2, max_len, 2] (cos, sin) */
   const float* rope_cross; /* device, pair-major [(down_dim/n_heads)/2, max_len, 2] */
+  float dropout_p;         /* train mode (training = 1 forward and its backward): dropout probability of every
+                              nn.Dropout on the path (attention probabilities, stream-MLP output, TIPI MLP output,
+                              models/base_blocks.py:47, 194, 286); 0 in eval mode.  Masks are counter-based
+                              functions of (dropout_seed, site, element), regenerated by the backward */
+  uint32_t reserved2;
+  uint64_t dropout_seed;   /* drawn by the caller once per forward; the backward must see the same value */
   int32_t grads_fresh;     /* sea_temporal_backward only.  1 = the caller asserts that the gradient buffers of
                               the nn.Linear WEIGHT matrices (everything the weight-gradient GEMMs write) hold no
                               value worth keeping (optimizer.zero_grad()): their first contribution overwrites

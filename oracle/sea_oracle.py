@@ -115,25 +115,37 @@ def masked_attention(x_q, x_kv, sd: State, name: str, n_heads: int, src_len: int
     return F.linear(out, sd[name + ".projection.weight"])
 
 
-def mlp(x, sd: State, name: str):
-    """MLP.forward with num_layers None/1: Linear → nn.LayerNorm → GELU → Linear,
-    models/base_blocks.py:22-26, 44-47 (dropout = identity in eval / p=0)."""
+def mlp(x, sd: State, name: str, drop_mult: Optional[torch.Tensor] = None):
+    """MLP.forward with num_layers None/1: Linear → nn.LayerNorm → GELU → Linear → Dropout,
+    models/base_blocks.py:22-26, 44-47.  `drop_mult` = the train-mode dropout as an explicit multiplier
+    tensor (mask / (1 - p)); None = eval mode / p = 0."""
     h = linear(x, sd, name + ".layers.0")
     h = layer_norm(h, sd[name + ".layers.1.weight"], sd[name + ".layers.1.bias"])
-    return linear(gelu(h), sd, name + ".layers.3")
+    out = linear(gelu(h), sd, name + ".layers.3")
+    return out if drop_mult is None else out * drop_mult
 
 
 # ----------------------------------------------------------------------------- temporal model
 def temporal_block(xs: List[torch.Tensor], ib, sd: State, prefix: str, *, n_heads: int,
-                   ln_type: str, src_len: int = 0, taps: Optional[dict] = None):
+                   ln_type: str, src_len: int = 0, taps: Optional[dict] = None,
+                   drop: Optional[dict] = None, layer: int = 0):
     """BaseBlockTemporal.forward + SEABlockTemporal exchange with add_info_after_cross=True,
     ib_scale_mode='mlp', ib_addition_mode='add' (the only mode either config selects)."""
     V = len(xs)
     xs = list(xs)
+    # train-mode dropout as explicit multipliers (mask / (1-p)) per site: ("self", l, i), ("cross", l, i, j)
+    # on the attention probabilities [B,nh,T,T]; ("mlp", l, i), ("tipi", l, i) on [B,T,E]
+    dm = (lambda *k: drop.get(k)) if drop is not None else (lambda *k: None)
+
+    def attn(xq, xkv, name, mult):
+        if mult is None:
+            return masked_attention(xq, xkv, sd, name, n_heads, src_len)
+        return masked_attention(xq, xkv, sd, name, n_heads, src_len, attn_dropout_mask=mult, dropout_p=0.0)
+
     # per-field causal self-attention, models/temporal.py:135-136
     for i in range(V):
         n = norm(xs[i], ib, sd, f"{prefix}.ln.exp.{i}.0", ln_type)
-        xs[i] = xs[i] + masked_attention(n, n, sd, f"{prefix}.attn.self.{i}", n_heads, src_len)
+        xs[i] = xs[i] + attn(n, n, f"{prefix}.attn.self.{i}", dm("self", layer, i))
         if taps is not None:
             taps[f"self.{i}"] = xs[i]
     # State-Exchange Attention, sequential over i (Gauss–Seidel), models/temporal.py:176-192
@@ -146,19 +158,18 @@ def temporal_block(xs: List[torch.Tensor], ib, sd: State, prefix: str, *, n_head
             dj = linear(xs[j], sd, f"{prefix}.cross_down.{j}")
             ni = norm(di, ib, sd, f"{prefix}.ln_cross.{i}", ln_type)
             nj = norm(dj, ib, sd, f"{prefix}.ln_cross.{j}", ln_type)
-            a = masked_attention(ni, nj, sd, f"{prefix}.cross_attn.{i}.{j}", n_heads, src_len)
+            a = attn(ni, nj, f"{prefix}.cross_attn.{i}.{j}", dm("cross", layer, i, j))
             acc = acc + linear(gelu(a), sd, f"{prefix}.cross_up.{i}")
         xs[i] = xs[i] + acc
         if taps is not None:
             taps[f"exchange.{i}"] = xs[i]
     # TIPI after the exchange, one shared MLP(ib_num → scale·ib_num → E), models/temporal.py:140-142
-    tipi = mlp(ib, sd, f"{prefix}.ib")
-    for i in range(V):
-        xs[i] = xs[i] + tipi
+    for i in range(V):   # the shared ib-MLP is CALLED once per stream: its dropout draws a mask per call
+        xs[i] = xs[i] + mlp(ib, sd, f"{prefix}.ib", dm("tipi", layer, i))
     # stream MLP + proj (proj REPLACES the stream), models/temporal.py:144-146
     for i in range(V):
         n = norm(xs[i], ib, sd, f"{prefix}.ln.exp.{i}.2", ln_type)
-        xs[i] = xs[i] + mlp(n, sd, f"{prefix}.mlp.{i}")
+        xs[i] = xs[i] + mlp(n, sd, f"{prefix}.mlp.{i}", dm("mlp", layer, i))
         xs[i] = linear(xs[i], sd, f"{prefix}.proj.{i}")
         if taps is not None:
             taps[f"block_out.{i}"] = xs[i]
@@ -166,13 +177,13 @@ def temporal_block(xs: List[torch.Tensor], ib, sd: State, prefix: str, *, n_head
 
 
 def temporal_forward(x, ib, sd: State, *, num_layers: int, n_heads: int, ln_type: str,
-                     src_len: int = 0, taps: Optional[dict] = None):
+                     src_len: int = 0, taps: Optional[dict] = None, drop: Optional[dict] = None):
     """TemporalModel.forward, models/temporal.py:405-416.  x [B,T,V,E], ib [B,T,ib_num]."""
     V = x.shape[2]
     xs = [x[:, :, i, :] for i in range(V)]
     for layer in range(num_layers):
         xs = temporal_block(xs, ib, sd, f"blocks.{layer}", n_heads=n_heads, ln_type=ln_type,
-                            src_len=src_len, taps=taps)
+                            src_len=src_len, taps=taps, drop=drop, layer=layer)
     xs = [norm(xs[i], ib, sd, f"ln.{i}", ln_type) for i in range(V)]
     return torch.stack(xs, dim=2)
 

@@ -39,6 +39,9 @@ class GemmEpilogue(C.Structure):
         ("rope_pos0", C.c_int32),
         ("res_rows_per_batch", C.c_int32),
         ("res_batch_stride", C.c_int64),
+        ("dropout_p", C.c_float),
+        ("dropout_site", C.c_uint32),
+        ("dropout_seed", C.c_uint64),
     ]
 
 

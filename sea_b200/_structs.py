@@ -44,6 +44,7 @@ class TemporalDesc(C.Structure):
                 ("blocks", C.POINTER(BlockParams)),
                 ("final_ln", NormParams * MAX_STREAMS),
                 ("rope_self", C.c_void_p), ("rope_cross", C.c_void_p),
+                ("dropout_p", C.c_float), ("reserved2", C.c_uint32), ("dropout_seed", C.c_uint64),
                 ("grads_fresh", C.c_int32), ("reserved1", C.c_int32)]
 
 
@@ -57,7 +58,8 @@ class NormArgs(C.Structure):
                 ("x_out", C.c_void_p), ("ldxo", C.c_int64), ("y_f32", C.c_void_p),
                 ("ldy_f32", C.c_int64), ("y_bf16", C.c_void_p), ("ldy_bf16", C.c_int64),
                 ("stats", C.c_void_p), ("cond_folded", C.c_int32), ("x_rows_per_batch", C.c_int32),
-                ("x_batch_stride", C.c_int64)]
+                ("x_batch_stride", C.c_int64), ("tipi_dropout_p", C.c_float), ("tipi_dropout_site", C.c_uint32),
+                ("tipi_dropout_seed", C.c_uint64)]
 
 
 class LnGeluArgs(C.Structure):
@@ -79,7 +81,8 @@ class AttnArgs(C.Structure):
                 ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64),
                 ("o", C.c_void_p), ("ldo", C.c_int64), ("lse", C.c_void_p),
                 ("B", C.c_int32), ("T", C.c_int32), ("n_heads", C.c_int32), ("head_dim", C.c_int32),
-                ("src_len", C.c_int32), ("scale", C.c_float), ("prec", C.c_int32)]
+                ("src_len", C.c_int32), ("scale", C.c_float), ("prec", C.c_int32),
+                ("dropout_p", C.c_float), ("dropout_site", C.c_uint32), ("dropout_seed", C.c_uint64)]
 
 
 class NormBwdArgs(C.Structure):
@@ -106,7 +109,8 @@ class AttnBwdArgs(C.Structure):
                 ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddq", C.c_int64),
                 ("lddk", C.c_int64), ("lddv", C.c_int64), ("B", C.c_int32), ("T", C.c_int32),
                 ("n_heads", C.c_int32), ("head_dim", C.c_int32), ("src_len", C.c_int32),
-                ("scale", C.c_float), ("prec", C.c_int32), ("rope_table", C.c_void_p), ("rope_ld", C.c_int32)]
+                ("scale", C.c_float), ("prec", C.c_int32), ("rope_table", C.c_void_p), ("rope_ld", C.c_int32),
+                ("dropout_p", C.c_float), ("dropout_site", C.c_uint32), ("dropout_seed", C.c_uint64)]
 
 
 class TipiBwdArgs(C.Structure):

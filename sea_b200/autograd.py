@@ -22,6 +22,7 @@ class _TemporalFn(torch.autograd.Function):
         ws = engine.acquire_training_workspace(B, T)
         y = engine.forward_nograd(x, ib, training=True, ws=ws)
         ctx.engine, ctx.ws, ctx.shape = engine, ws, (B, T)
+        ctx.dropout = (engine.last_dropout_seed, float(engine.dropout))   # the backward regenerates the masks
         ctx.save_for_backward(x, ib)
         ctx.need_dx = x.requires_grad
         return y
@@ -30,7 +31,7 @@ class _TemporalFn(torch.autograd.Function):
     def backward(ctx, dy):
         eng = ctx.engine
         x, ib = ctx.saved_tensors
-        dx = eng.backward(x, ib, dy, ctx.ws, ctx.need_dx)
+        dx = eng.backward(x, ib, dy, ctx.ws, ctx.need_dx, dropout_seed=ctx.dropout[0], dropout_p=ctx.dropout[1])
         eng.release_training_workspace(ctx.shape, ctx.ws)
         return dx, None, None, None
 

@@ -34,12 +34,15 @@ extern "C" int sea_attention_fwd_group(int n, const sea_attn_args* a, sea_stream
     int rc = validate(&a[i]);
     if (rc) return rc;
     if (a[i].B != a[0].B || a[i].T != a[0].T || a[i].n_heads != a[0].n_heads || a[i].head_dim != a[0].head_dim ||
-        a[i].src_len != a[0].src_len || a[i].scale != a[0].scale || a[i].prec != a[0].prec || a[i].ldo != a[0].ldo)
+        a[i].src_len != a[0].src_len || a[i].scale != a[0].scale || a[i].prec != a[0].prec || a[i].ldo != a[0].ldo ||
+        a[i].dropout_p != a[0].dropout_p || a[i].dropout_seed != a[0].dropout_seed)
       return SEA_ERR_INVALID;
     tc = tc && attention_tc_supported(&a[i]);
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a[0].dropout_p < 0.f || a[0].dropout_p >= 1.f) return SEA_ERR_INVALID;
   if (tc) return attention_fwd_tc(n, a, s);
+  if (a[0].dropout_p > 0.f) return SEA_ERR_UNSUPPORTED;   // probability dropout lives in the tensor-core kernels only
   for (int i = 0; i < n; ++i) {
     int rc = attention_fwd_simt(&a[i], s);
     if (rc) return rc;

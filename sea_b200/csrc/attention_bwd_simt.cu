@@ -334,6 +334,7 @@ extern "C" int sea_attention_bwd(const sea_attn_bwd_args* a, sea_stream_t stream
   d.scale = a->scale; d.rope = a->rope_table; d.rope_ld = a->rope_ld;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (!g_force_simt && attention_bwd_tc_supported(a)) return attention_bwd_tc(a, s);
+  if (a->dropout_p != 0.f) return SEA_ERR_UNSUPPORTED;   // probability dropout lives in the tensor-core kernels only
   if (a->prec == SEA_PREC_FP32) return launch_bwd<float>(d, s);
   if (a->prec == SEA_PREC_BF16) return launch_bwd<__nv_bfloat16>(d, s);
   return SEA_ERR_INVALID;

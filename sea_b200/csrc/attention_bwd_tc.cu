@@ -41,6 +41,9 @@ struct alignas(64) AttnBwdTcParams {
   const float *lse, *delta, *rope;
   int B, T, n_heads, src_len, rope_ld;
   float scale, scale_log2;
+  unsigned long long drop_seed;   // probability dropout of the forward, regenerated here (DROP kernels)
+  uint32_t drop_thresh, drop_site;
+  float drop_scale;
 };
 
 template <int HD, int BS, int MODE>
@@ -54,7 +57,7 @@ struct BCfg {
   static constexpr int SMEM = 2 * STAT_BYTES + STAGES * 2 * STR_BYTES + 1024 + 256 + 4 * BS * 4;
 };
 
-template <int HD, int BS, int MODE>
+template <int HD, int BS, int MODE, bool DROP>
 __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdTcParams p) {
   using C = BCfg<HD, BS, MODE>;
   constexpr int STAGES = C::STAGES;
@@ -255,8 +258,22 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
               const int kk = MODE == 0 ? cpos : rpos;
               if (kk > qq + p.src_len || kk >= p.T || qq >= p.T) pe = 0.f;
             }
-            pv[u] = pe;
-            dv[u] = pe * (__uint_as_float(rd[e + u]) - dl) * p.scale;
+            float dpv = __uint_as_float(rd[e + u]);
+            if (DROP) {
+              // O = (mask/(1-p) o P) V: dV uses the dropped P, dP picks up the same factor; delta = rowsum(dO o O)
+              // already equals sum_k P_k dP_k, so dS = P o (dP - delta) keeps the UNdropped P in front
+              const int qq = MODE == 0 ? rpos : cpos;
+              const int kk = MODE == 0 ? cpos : rpos;
+              const float mult = ptx::drop_mult(p.drop_seed, p.drop_site,
+                                                ((static_cast<unsigned long long>(b) * p.n_heads + h) * p.T + qq) *
+                                                        static_cast<unsigned long long>((p.T + 1) & ~1) + kk,
+                                                p.drop_thresh, p.drop_scale);
+              dpv *= mult;
+              pv[u] = pe * mult;
+            } else {
+              pv[u] = pe;
+            }
+            dv[u] = pe * (dpv - dl) * p.scale;
           }
           rs[e >> 1] = ptx::pack_bf16(pv[0], pv[1]);
           rd[e >> 1] = ptx::pack_bf16(dv[0], dv[1]);
@@ -349,14 +366,14 @@ __global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const __nv_bfloat16
   }
 }
 
-template <int HD, int BS, int MODE>
+template <int HD, int BS, int MODE, bool DROP>
 int launch_mode(const sea_attn_bwd_args* a, cudaStream_t s) {
   using C = BCfg<HD, BS, MODE>;
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    SEA_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, BS, MODE>,
+    SEA_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, BS, MODE, DROP>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set[dev] = true;
   }
@@ -385,17 +402,25 @@ int launch_mode(const sea_attn_bwd_args* a, cudaStream_t s) {
   p.lse = a->lse; p.delta = a->delta; p.rope = a->rope_table; p.rope_ld = a->rope_ld;
   p.B = a->B; p.T = a->T; p.n_heads = a->n_heads; p.src_len = a->src_len;
   p.scale = a->scale; p.scale_log2 = a->scale * kLog2e;
+  p.drop_seed = a->dropout_seed; p.drop_site = a->dropout_site;
+  p.drop_thresh = a->dropout_p > 0.f ? static_cast<uint32_t>(static_cast<double>(a->dropout_p) * 4294967296.0) : 0u;
+  p.drop_scale = 1.0f / (1.0f - a->dropout_p);
   const int tiles = (a->T + BR - 1) / BR;
   dim3 grid(tiles * (MODE == 1 ? C::HALVES : 1), a->n_heads, a->B);
-  SEA_LAUNCH((attn_bwd_tc_kernel<HD, BS, MODE>), grid, kThreads, C::SMEM, s, p);
+  SEA_LAUNCH((attn_bwd_tc_kernel<HD, BS, MODE, DROP>), grid, kThreads, C::SMEM, s, p);
   return static_cast<int>(cudaGetLastError());
 }
 
 template <int HD, int BS>
 int launch_both(const sea_attn_bwd_args* a, cudaStream_t s) {
-  int rc = launch_mode<HD, BS, 0>(a, s);
+  if (a->dropout_p > 0.f) {
+    int rc = launch_mode<HD, BS, 0, true>(a, s);
+    if (rc) return rc;
+    return launch_mode<HD, BS, 1, true>(a, s);
+  }
+  int rc = launch_mode<HD, BS, 0, false>(a, s);
   if (rc) return rc;
-  return launch_mode<HD, BS, 1>(a, s);
+  return launch_mode<HD, BS, 1, false>(a, s);
 }
 
 }  // namespace
@@ -413,6 +438,7 @@ bool attention_bwd_tc_supported(const sea_attn_bwd_args* a) {
   if (all & 15) return false;
   if (reinterpret_cast<uintptr_t>(a->o) & 3) return false;
   if (a->rope_table != nullptr && a->rope_ld < a->T) return false;
+  if (a->dropout_p < 0.f || a->dropout_p >= 1.f) return false;
   return true;
 }
 

@@ -38,12 +38,16 @@ struct AttnTcItem {
   CUtensorMap tq, tk, tv;
   __nv_bfloat16* o;
   float* lse;
+  uint32_t drop_site;
 };
 struct alignas(64) AttnTcParams {
   AttnTcItem it[SEA_MAX_STREAMS];
   long long ldo;
   int B, T, n_heads, src_len;
   float scale_log2;  // scale * log2(e)
+  unsigned long long drop_seed;   // dropout on the probabilities (DROP kernels only)
+  uint32_t drop_thresh;
+  float drop_scale;
 };
 
 template <int HD, int BKV, int STAGES_>
@@ -58,7 +62,7 @@ struct ACfg {
   static constexpr int MIN_CTAS = (SMEM <= 110 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
 };
 
-template <int HD, int BKV, int STAGES_>
+template <int HD, int BKV, int STAGES_, bool DROP>
 __global__ void __launch_bounds__(kThreads, (ACfg<HD, BKV, STAGES_>::MIN_CTAS))
 attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
   using C = ACfg<HD, BKV, STAGES_>;
@@ -226,11 +230,20 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
       // p = 2^(s * scale_log2 - m): one FFMA + one MUFU per score; packed bf16 pairs overwrite S
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       float l0 = 0.f, l1 = 0.f;
+      // dropout acts on the NORMALISED probabilities (base_blocks.py:193-194): the row sum stays undropped,
+      // only the P that feeds P.V is masked and rescaled
+      const unsigned long long drop_row = DROP ? ((static_cast<unsigned long long>(b) * pp.n_heads + h) * pp.T + q) *
+                                                     static_cast<unsigned long long>((pp.T + 1) & ~1) + kv0 : 0ull;
 #pragma unroll
       for (int e = 0; e < BKV; e += 2) {
-        const float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), pp.scale_log2, neg_m));
-        const float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), pp.scale_log2, neg_m));
+        float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), pp.scale_log2, neg_m));
+        float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), pp.scale_log2, neg_m));
         l0 += p0; l1 += p1;
+        if (DROP) {
+          const uint2 hsh = ptx::drop_hash(pp.drop_seed, p.drop_site, (drop_row + e) >> 1);
+          p0 = hsh.x >= pp.drop_thresh ? p0 * pp.drop_scale : 0.f;
+          p1 = hsh.y >= pp.drop_thresh ? p1 * pp.drop_scale : 0.f;
+        }
         r[e >> 1] = ptx::pack_bf16(p0, p1);
       }
       l_sum += l0 + l1;
@@ -296,7 +309,7 @@ struct ACfg2 {
   static constexpr int SMEM = Q_BYTES + 2 * 2 * KV_BYTES + 1024 + 128;
 };
 
-template <int HD>
+template <int HD, bool DROP>
 __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid_constant__ AttnTcParams pp) {
   using C = ACfg2<HD>;
   constexpr int BKV = C::BKV;
@@ -481,11 +494,20 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
       // p = 2^(s * scale_log2 - m): one FFMA + one MUFU per score; packed bf16 pairs overwrite S
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       float l0 = 0.f, l1 = 0.f;
+      // dropout acts on the NORMALISED probabilities (base_blocks.py:193-194): the row sum stays undropped,
+      // only the P that feeds P.V is masked and rescaled
+      const unsigned long long drop_row = DROP ? ((static_cast<unsigned long long>(b) * pp.n_heads + h) * pp.T + q) *
+                                                     static_cast<unsigned long long>((pp.T + 1) & ~1) + kv0 : 0ull;
 #pragma unroll
       for (int e = 0; e < BKV; e += 2) {
-        const float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), pp.scale_log2, neg_m));
-        const float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), pp.scale_log2, neg_m));
+        float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), pp.scale_log2, neg_m));
+        float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), pp.scale_log2, neg_m));
         l0 += p0; l1 += p1;
+        if (DROP) {
+          const uint2 hsh = ptx::drop_hash(pp.drop_seed, p.drop_site, (drop_row + e) >> 1);
+          p0 = hsh.x >= pp.drop_thresh ? p0 * pp.drop_scale : 0.f;
+          p1 = hsh.y >= pp.drop_thresh ? p1 * pp.drop_scale : 0.f;
+        }
         r[e >> 1] = ptx::pack_bf16(p0, p1);
       }
       l_sum += l0 + l1;
@@ -531,14 +553,14 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
   }
 }
 
-template <int HD>
+template <int HD, bool DROP>
 int launch_tc2(int n, const sea_attn_args* a, cudaStream_t s) {
   using C = ACfg2<HD>;
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    SEA_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    SEA_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<HD, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set[dev] = true;
   }
   AttnTcParams p;
@@ -553,23 +575,27 @@ int launch_tc2(int n, const sea_attn_args* a, cudaStream_t s) {
     if (rc) return rc;
     p.it[i].o = static_cast<__nv_bfloat16*>(x.o);
     p.it[i].lse = x.lse;
+    p.it[i].drop_site = x.dropout_site;
   }
+  p.drop_seed = a->dropout_seed;
+  p.drop_thresh = a->dropout_p > 0.f ? static_cast<uint32_t>(static_cast<double>(a->dropout_p) * 4294967296.0) : 0u;
+  p.drop_scale = 1.0f / (1.0f - a->dropout_p);
   p.ldo = a->ldo;
   p.B = a->B; p.T = a->T; p.n_heads = a->n_heads; p.src_len = a->src_len;
   p.scale_log2 = a->scale * 1.44269504088896340736f;
   dim3 grid((a->T + 2 * BQ - 1) / (2 * BQ), a->n_heads, a->B * n);
-  SEA_LAUNCH((attn_fwd_tc2_kernel<HD>), grid, kThreads2, C::SMEM, s, p);
+  SEA_LAUNCH((attn_fwd_tc2_kernel<HD, DROP>), grid, kThreads2, C::SMEM, s, p);
   return static_cast<int>(cudaGetLastError());
 }
 
-template <int HD, int BKV, int STAGES_>
+template <int HD, int BKV, int STAGES_, bool DROP>
 int launch_tc(int n, const sea_attn_args* a, cudaStream_t s) {
   using C = ACfg<HD, BKV, STAGES_>;
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    SEA_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, BKV, STAGES_>,
+    SEA_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, BKV, STAGES_, DROP>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set[dev] = true;
   }
@@ -585,12 +611,16 @@ int launch_tc(int n, const sea_attn_args* a, cudaStream_t s) {
     if (rc) return rc;
     p.it[i].o = static_cast<__nv_bfloat16*>(x.o);
     p.it[i].lse = x.lse;
+    p.it[i].drop_site = x.dropout_site;
   }
+  p.drop_seed = a->dropout_seed;
+  p.drop_thresh = a->dropout_p > 0.f ? static_cast<uint32_t>(static_cast<double>(a->dropout_p) * 4294967296.0) : 0u;
+  p.drop_scale = 1.0f / (1.0f - a->dropout_p);
   p.ldo = a->ldo;
   p.B = a->B; p.T = a->T; p.n_heads = a->n_heads; p.src_len = a->src_len;
   p.scale_log2 = a->scale * 1.44269504088896340736f;
   dim3 grid((a->T + BQ - 1) / BQ, a->n_heads, a->B * n);
-  SEA_LAUNCH((attn_fwd_tc_kernel<HD, BKV, STAGES_>), grid, kThreads, C::SMEM, s, p);
+  SEA_LAUNCH((attn_fwd_tc_kernel<HD, BKV, STAGES_, DROP>), grid, kThreads, C::SMEM, s, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -615,14 +645,23 @@ int attention_fwd_tc(int n, const sea_attn_args* a, cudaStream_t s) {
   int rc = ensure_init();
   if (rc) return rc;
   const int k_last = (a->T - 1 + a->src_len < a->T - 1) ? a->T - 1 + a->src_len : a->T - 1;
+  const bool drop = a->dropout_p > 0.f;
+#define SEA_ATTN_FWD(HD_, BKV_)                                                                     \
+  do {                                                                                              \
+    if (k_last < BKV_)                                                                              \
+      return drop ? launch_tc<HD_, BKV_, 1, true>(n, a, s) : launch_tc<HD_, BKV_, 1, false>(n, a, s); \
+    if (HD_ <= 128 && g_attn_two_tiles)                                                             \
+      return drop ? launch_tc2<(HD_ <= 128 ? HD_ : 128), true>(n, a, s)                             \
+                  : launch_tc2<(HD_ <= 128 ? HD_ : 128), false>(n, a, s);                           \
+    return drop ? launch_tc<HD_, BKV_, 2, true>(n, a, s) : launch_tc<HD_, BKV_, 2, false>(n, a, s); \
+  } while (0)
   switch (a->head_dim) {
-    case 64: return k_last < 128 ? launch_tc<64, 128, 1>(n, a, s)
-                                 : (g_attn_two_tiles ? launch_tc2<64>(n, a, s) : launch_tc<64, 128, 2>(n, a, s));
-    case 128: return k_last < 128 ? launch_tc<128, 128, 1>(n, a, s)
-                                  : (g_attn_two_tiles ? launch_tc2<128>(n, a, s) : launch_tc<128, 128, 2>(n, a, s));
-    case 256: return k_last < 64 ? launch_tc<256, 64, 1>(n, a, s) : launch_tc<256, 64, 2>(n, a, s);
+    case 64: SEA_ATTN_FWD(64, 128);
+    case 128: SEA_ATTN_FWD(128, 128);
+    case 256: SEA_ATTN_FWD(256, 64);
     default: return SEA_ERR_UNSUPPORTED;
   }
+#undef SEA_ATTN_FWD
 }
 
 }  // namespace sea

@@ -100,6 +100,7 @@ struct NormDev {
   __nv_bfloat16* y_bf16; long long ldy_bf16;
   float* stats;
   int cond_folded;                 // cond rows already hold gamma | beta (sea_adaln_fold)
+  unsigned long long drop_seed; uint32_t drop_thresh, drop_site; float drop_scale;   // TIPI-term dropout (0 = off)
   int x_rows; long long x_bs;      // x_rows > 0: row m of x lives at x + (m / x_rows) * x_bs + (m % x_rows) * ldx
 };
 
@@ -161,6 +162,9 @@ __global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const 
               s = fmaf(a.tipi_w[(col + e) * a.tipi_hid + k],
                        a.tipi_g[static_cast<long long>(m) * a.tipi_hid + k], s);
           }
+          if (a.drop_thresh != 0u)   // the ib-MLP's own nn.Dropout (models/base_blocks.py:47)
+            s *= ptx::drop_mult(a.drop_seed, a.drop_site, static_cast<unsigned long long>(m) * a.d + col + e,
+                                a.drop_thresh, a.drop_scale);
           add[e] = s;
         }
         v[c].x += add[0]; v[c].y += add[1]; v[c].z += add[2]; v[c].w += add[3];
@@ -713,6 +717,32 @@ __global__ void colsum_kernel(const ColsumGroup grp, long long ld, int M, int N)
 }
 
 
+// keep decisions of elements [0, n) of one dropout site (test / oracle helper)
+__global__ void __launch_bounds__(256) dropout_mask_kernel(unsigned long long seed, uint32_t site, long long n,
+                                                           uint32_t thresh, unsigned char* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ptx::drop_mult(seed, site, static_cast<unsigned long long>(i), thresh, 1.0f) != 0.f ? 1 : 0;
+}
+
+// dst[m, n] = src[m, n] * mask(m * N + n) / (1 - p): the gradient that enters a dropped branch
+__global__ void __launch_bounds__(256) dropout_apply_kernel(const float* __restrict__ src, long long ld_src, int M, int N,
+                                                            unsigned long long seed, uint32_t site, uint32_t thresh,
+                                                            float scale, float* __restrict__ dst_f32, long long ld_f32,
+                                                            __nv_bfloat16* __restrict__ dst_b16, long long ld_b16) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const long long pairs_per_row = N >> 1;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= pairs_per_row * M) return;
+  const int m = static_cast<int>(t / pairs_per_row);
+  const int n = static_cast<int>(t - static_cast<long long>(m) * pairs_per_row) * 2;
+  const float2 v = *reinterpret_cast<const float2*>(src + static_cast<long long>(m) * ld_src + n);
+  const uint2 h = ptx::drop_hash(seed, site, (static_cast<unsigned long long>(m) * N + n) >> 1);
+  const float a = h.x >= thresh ? v.x * scale : 0.f, b = h.y >= thresh ? v.y * scale : 0.f;
+  if (dst_f32) *reinterpret_cast<float2*>(dst_f32 + static_cast<long long>(m) * ld_f32 + n) = make_float2(a, b);
+  if (dst_b16) *reinterpret_cast<uint32_t*>(dst_b16 + static_cast<long long>(m) * ld_b16 + n) = ptx::pack_bf16(a, b);
+}
+
 // Vectorised variant (N % 8 == 0, 16-byte aligned rows): a thread owns 8 consecutive columns (one
 // 16-byte load per bf16 row), a warp 256, the 8 warps of a CTA stride over the rows of a slab with four
 // rows in flight each; partials meet in shared memory, one atomicAdd per column and CTA.
@@ -849,6 +879,11 @@ static int fill_norm(const sea_norm_args* a, NormDev& d) {
   d.y_bf16 = static_cast<__nv_bfloat16*>(a->y_bf16); d.ldy_bf16 = a->ldy_bf16;
   d.stats = a->stats;
   d.cond_folded = a->cond_folded;
+  if (a->tipi_dropout_p < 0.f || a->tipi_dropout_p >= 1.f) return SEA_ERR_INVALID;
+  if (a->tipi_dropout_p > 0.f && !a->tipi_g) return SEA_ERR_UNSUPPORTED;   // only the per-token TIPI path drops
+  d.drop_seed = a->tipi_dropout_seed; d.drop_site = a->tipi_dropout_site;
+  d.drop_thresh = a->tipi_dropout_p > 0.f ? static_cast<uint32_t>(static_cast<double>(a->tipi_dropout_p) * 4294967296.0) : 0u;
+  d.drop_scale = 1.0f / (1.0f - a->tipi_dropout_p);
   d.x_rows = a->x_rows_per_batch; d.x_bs = a->x_batch_stride;
   if (a->cond_folded && a->kind != SEA_NORM_ADALN) return SEA_ERR_INVALID;
   if (a->x_rows_per_batch < 0 || (a->x_rows_per_batch > 0 && (a->x_batch_stride % 4))) return SEA_ERR_INVALID;
@@ -977,6 +1012,27 @@ extern "C" int sea_pack_operand(const sea_pack_args* a, sea_stream_t stream) {
     SEA_LAUNCH((pack_kernel<float>), grid, 256, 0, s, a->src_f32, a->ld, a->R, a->C, a->transpose, a->split, a->act, a->split_inner, static_cast<__nv_bfloat16*>(a->dst), a->ld_dst);
   else
     SEA_LAUNCH((pack_kernel<__nv_bfloat16>), grid, 256, 0, s, static_cast<const __nv_bfloat16*>(a->src_bf16), a->ld, a->R, a->C, a->transpose, a->split, a->act, a->split_inner, static_cast<__nv_bfloat16*>(a->dst), a->ld_dst);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_dropout_mask(uint64_t seed, uint32_t site, int64_t n, float p, uint8_t* out, sea_stream_t stream) {
+  if (!out || n <= 0 || p < 0.f || p >= 1.f) return SEA_ERR_INVALID;
+  const uint32_t thresh = static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
+  SEA_LAUNCH(dropout_mask_kernel, static_cast<unsigned>((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream),
+             static_cast<unsigned long long>(seed), site, static_cast<long long>(n), thresh, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_dropout_apply(const float* src, int64_t ld_src, int M, int N, uint64_t seed, uint32_t site, float p,
+                                 float* dst_f32, int64_t ld_f32, void* dst_bf16, int64_t ld_bf16, sea_stream_t stream) {
+  if (!src || (!dst_f32 && !dst_bf16) || M <= 0 || N <= 0 || p < 0.f || p >= 1.f) return SEA_ERR_INVALID;
+  if ((N % 2) || (ld_src % 2) || (dst_f32 && (ld_f32 % 2)) || (dst_bf16 && (ld_bf16 % 2))) return SEA_ERR_UNSUPPORTED;
+  const uint32_t thresh = static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
+  const long long work = static_cast<long long>(M) * (N / 2);
+  SEA_LAUNCH(dropout_apply_kernel, static_cast<unsigned>((work + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream),
+             src, static_cast<long long>(ld_src), M, N, static_cast<unsigned long long>(seed), site, thresh,
+             1.0f / (1.0f - p), dst_f32, static_cast<long long>(ld_f32), static_cast<__nv_bfloat16*>(dst_bf16),
+             static_cast<long long>(ld_bf16));
   return static_cast<int>(cudaGetLastError());
 }
 

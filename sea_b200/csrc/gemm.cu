@@ -42,6 +42,7 @@ struct DevEpilogue {
   __nv_bfloat16* out_bf16;
   long long ld_residual, ld_gelu, ld_out_f32, ld_out_pre_bf16, ld_out_bf16;
   int act, rope_cols, head_dim, seq_len, rope_ld, rope_pos0;
+  unsigned long long drop_seed; uint32_t drop_thresh, drop_site; float drop_scale;  // drop_thresh 0 = no dropout
   int res_rows; long long res_bs;  // res_rows > 0: residual row m at (m / res_rows) * res_bs + (m % res_rows) * ld_residual
   float rope_sign;
   int vec8;  // every row base / pitch is 32-byte aligned: use 256-bit global accesses
@@ -137,6 +138,16 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
         const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
+    }
+  }
+  if (e.drop_thresh != 0u) {
+    // nn.Dropout on the Linear's output, before the skip connection is added (base_blocks.py:47)
+    const unsigned long long idx0 = static_cast<unsigned long long>(m) * N + n0;   // even: N % 8 == 0, n0 % 32 == 0
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const uint2 h = ptx::drop_hash(e.drop_seed, e.drop_site, (idx0 + j) >> 1);
+      v[j] = h.x >= e.drop_thresh ? v[j] * e.drop_scale : 0.f;
+      v[j + 1] = h.y >= e.drop_thresh ? v[j + 1] * e.drop_scale : 0.f;
     }
   }
   if (first && e.residual != nullptr) {
@@ -816,6 +827,10 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
     d.rope_ld = e.rope_ld;
     d.rope_pos0 = e.rope_pos0;
     d.res_rows = e.res_rows_per_batch; d.res_bs = e.res_batch_stride;
+    if (e.dropout_p < 0.f || e.dropout_p >= 1.f || (e.dropout_p > 0.f && chunked)) return SEA_ERR_INVALID;
+    d.drop_seed = e.dropout_seed; d.drop_site = e.dropout_site;
+    d.drop_thresh = e.dropout_p > 0.f ? static_cast<uint32_t>(static_cast<double>(e.dropout_p) * 4294967296.0) : 0u;
+    d.drop_scale = 1.0f / (1.0f - e.dropout_p);
     d.rope_sign = (e.rope_sign == 0.0f) ? 1.0f : e.rope_sign;
     auto al32 = [](const void* ptr, long long ld_elems, int esz) {
       return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr) & 31) == 0) && ((ld_elems * esz) % 32 == 0));

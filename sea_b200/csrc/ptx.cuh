@@ -312,6 +312,24 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// ------------------------------------------------------------------- dropout
+// Counter-based Bernoulli masks (train-mode nn.Dropout, models/base_blocks.py:42-47, 114, 194, 286): the
+// decision for element `idx` of site `site` is a pure function of (seed, site, idx), so the backward pass
+// regenerates the forward's mask instead of storing it.  One splitmix64 round yields the decisions of the
+// two elements 2k, 2k+1.  keep iff r >= thresh, thresh = p * 2^32; kept values are scaled by 1/(1-p).
+__device__ __forceinline__ uint2 drop_hash(unsigned long long seed, uint32_t site, unsigned long long pair_idx) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (pair_idx + 1ull) + 0xD1B54A32D192ED03ull * (site + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return make_uint2(static_cast<uint32_t>(z), static_cast<uint32_t>(z >> 32));
+}
+__device__ __forceinline__ float drop_mult(unsigned long long seed, uint32_t site, unsigned long long idx,
+                                           uint32_t thresh, float scale) {
+  const uint2 h = drop_hash(seed, site, idx >> 1);
+  return ((idx & 1ull) ? h.y : h.x) >= thresh ? scale : 0.f;
+}
+
 // d/dx gelu_erf(x) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7); the Gaussian
 // exp(-x^2/2) is shared between the erf tail and the density term: 1 rcp + 1 ex2 + ~10 FMA.
 __device__ __forceinline__ float gelu_erf_grad_fast(float x) {

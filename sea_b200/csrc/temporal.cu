@@ -367,6 +367,7 @@ int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, c
     e.bias = o.bias;
     e.residual = o.residual; e.ld_residual = o.ld_res;
     e.res_rows_per_batch = o.res_rows; e.res_batch_stride = o.res_bs;
+    e.dropout_p = o.drop_p; e.dropout_site = o.drop_site; e.dropout_seed = c.d->dropout_seed;
     e.act = o.act;
     if (o.rope_cols > 0) {
       e.rope_cols = o.rope_cols; e.head_dim = o.head_dim; e.seq_len = c.T;
@@ -439,8 +440,9 @@ int norm_group(Ctx& c, int n, const NormCall* calls) {
 }
 
 sea_attn_args attn_call(Ctx& c, const void* q, long long ldq, const void* k, const void* v, long long ldkv,
-                        void* o, long long ldo, float* lse, int head_dim) {
+                        void* o, long long ldo, float* lse, int head_dim, unsigned site = 0) {
   sea_attn_args a{};
+  a.dropout_p = c.drop_p; a.dropout_site = site; a.dropout_seed = c.d->dropout_seed;
   a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldkv; a.ldv = ldkv;
   a.o = o; a.ldo = ldo; a.lse = lse;
   a.B = c.B; a.T = c.T; a.n_heads = c.d->n_heads; a.head_dim = head_dim;
@@ -620,6 +622,9 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
   c.fp32 = d->precision == SEA_PREC_FP32;
   c.B = B; c.T = T; c.M = B * T;
   c.pos0 = step ? step->pos : 0;
+  c.drop_p = (training != 0 && d->dropout_p > 0.f) ? d->dropout_p : 0.f;
+  if (d->dropout_p < 0.f || d->dropout_p >= 1.f) return SEA_ERR_INVALID;
+  if (c.drop_p > 0.f && c.fp32) return SEA_ERR_UNSUPPORTED;   // training runs in bf16 mode
   // time-invariant condition (inference): one cond / TIPI row per trajectory instead of per token
   const bool inv = d->ib_time_invariant != 0 && training == 0 && (T > 1 || step != nullptr);
   c.inv = inv;
@@ -758,7 +763,7 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
       for (int i = 0; i < V; ++i) {
         char* base = static_cast<char*>(lt.s[i].qkv);
         acall[i] = attn_call(c, base, 3 * E, base + esz * E, base + esz * 2 * E, 3 * E, lt.s[i].ao, E,
-                             lt.s[i].lse, hd);
+                             lt.s[i].lse, hd, drop_site(l, SEA_SITE_SELF, i, 0));
       }
       SEA_TRY(attention_group(c, V, acall));
     }
@@ -859,7 +864,8 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
           SEA_TRY(decode_group(c, 1, &dc));
         } else {
           char* kvb = static_cast<char*>(s.kv[j]);
-          acall[0] = attn_call(c, s.q[j], Dd, kvb, kvb + esz * Dd, 2 * Dd, s.a[j], Dd, s.lse_c[j], hdc);
+          acall[0] = attn_call(c, s.q[j], Dd, kvb, kvb + esz * Dd, 2 * Dd, s.a[j], Dd, s.lse_c[j], hdc,
+                               drop_site(l, SEA_SITE_CROSS, i, j));
           SEA_TRY(attention_group(c, 1, acall));
         }
         // cross_up(GELU(projection(attn)))             models/base_blocks.py:293, temporal.py:185
@@ -896,9 +902,14 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
     }
 
     // (3) x_i += TIPI(ib) fused with Norm_{i,2}; (4) MLP; (5) proj    models/temporal.py:140-146
-    for (int i = 0; i < V; ++i)
+    for (int i = 0; i < V; ++i) {
       ncall[i] = norm_call(c, kind, bp.s[i].ln2, lt.s[i].cond2, lt.s[i].xp, E, E, lt.s[i].n2, nullptr, 0,
                            lt.s[i].st2, &bp, inv ? lt.tipi_rows : lt.tipi_g, lt.s[i].x2);
+      if (c.drop_p > 0.f) {   // the ib-MLP is called once per stream: independent masks (temporal.py:140-142)
+        ncall[i].a.tipi_dropout_p = c.drop_p; ncall[i].a.tipi_dropout_site = drop_site(l, SEA_SITE_TIPI, i, 0);
+        ncall[i].a.tipi_dropout_seed = d->dropout_seed;
+      }
+    }
     SEA_TRY(norm_group(c, V, ncall));
     for (int i = 0; i < V; ++i) {
       in[i] = LinIn{lt.s[i].n2, E, 0};
@@ -929,6 +940,7 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
       out[i].bias = bp.s[i].mlp3_b.p;
       out[i].residual = lt.s[i].x2; out[i].ld_res = E;
       out[i].post = lt.s[i].x3; out[i].ld_post = E;
+      out[i].drop_p = c.drop_p; out[i].drop_site = drop_site(l, SEA_SITE_MLP, i, 0);
     }
     SEA_TRY(linear_group(c, V, in, W, out, M));
     for (int i = 0; i < V; ++i) {

@@ -208,8 +208,9 @@ int cond_bwd(BCtx& b, int n, const sea_norm_params* const* np, void* const* hid,
 
 int attention_bwd(BCtx& b, const bf16* q, long long ldq, const bf16* k, const bf16* v, long long ldkv,
                   const bf16* o, const bf16* d_o, long long ldo, const float* lse, bf16* dq, long long lddq,
-                  bf16* dk, bf16* dv, long long lddkv, int hd, const float* rope) {
+                  bf16* dk, bf16* dv, long long lddkv, int hd, const float* rope, unsigned site) {
   sea_attn_bwd_args a{};
+  a.dropout_p = b.c.drop_p; a.dropout_site = site; a.dropout_seed = b.c.d->dropout_seed;
   a.q = q; a.k = k; a.v = v; a.o = o; a.d_o = d_o;
   a.ldq = ldq; a.ldk = ldkv; a.ldv = ldkv; a.ldo = ldo; a.lddo = ldo;
   a.lse = lse; a.delta = b.bt->delta;
@@ -287,6 +288,8 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
   b.c.Mc = b.c.M; b.c.ld_ib = d->ib_num; b.c.cond_div = 1;
   b.ib = ib; b.bt = &bt;
   b.fresh = d->grads_fresh != 0;
+  if (d->dropout_p < 0.f || d->dropout_p >= 1.f) return SEA_ERR_INVALID;
+  b.c.drop_p = d->dropout_p;
   const int M = b.c.M, V = d->num_streams, E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
   const int hd = E / d->n_heads, hdc = Dd / d->n_heads;
   const int kind = d->norm_kind;
@@ -328,6 +331,15 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       q.dgrad = true; q.da_f32 = bt.s[i].dx3; q.ld_da = E; q.da_b16 = bt.s[i].dx3b; q.ld_dab = E;
     }
     SEA_TRY(linear_bwd(b, V, L));
+    if (b.c.drop_p > 0.f) {
+      // x3 = x2 + Drop(mlp(n2)): the gradient entering the MLP branch carries the forward's mask; the
+      // skip path keeps dx3 as it is (fp32), so only the bf16 operand of the mlp3 backward is rewritten
+      for (int i = 0; i < V; ++i) {
+        ++g_launches;
+        SEA_TRY(sea_dropout_apply(bt.s[i].dx3, E, M, E, d->dropout_seed, drop_site(l, SEA_SITE_MLP, i, 0), b.c.drop_p,
+                                  nullptr, 0, bt.s[i].dx3b, E, b.st()));
+      }
+    }
     // (4) MLP: Linear2, LN+GELU, Linear1
     for (int i = 0; i < V; ++i) {
       LinB& q = L[i]; q = LinB{};
@@ -374,6 +386,15 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
     if (bp.ib3_w.g) {
       sea_tipi_bwd_args a{};
       for (int i = 0; i < V; ++i) a.dx[i] = bt.s[i].dx2;
+      if (b.c.drop_p > 0.f) {
+        // x2 = x_post + Drop_i(TIPI): each stream's branch gradient carries its own mask (dn2 is free here)
+        for (int i = 0; i < V; ++i) {
+          ++g_launches;
+          SEA_TRY(sea_dropout_apply(bt.s[i].dx2, E, M, E, d->dropout_seed, drop_site(l, SEA_SITE_TIPI, i, 0), b.c.drop_p,
+                                    bt.s[i].dn2, E, nullptr, 0, b.st()));
+          a.dx[i] = bt.s[i].dn2;
+        }
+      }
       a.lddx = E; a.n_streams = V; a.M = M; a.E = E; a.hid = d->ib_hidden; a.ib_num = d->ib_num;
       a.g = lt.tipi_g; a.u = lt.tipi_pre; a.stats = lt.tipi_st; a.ib = ib;
       a.w3 = bp.ib3_w.p; a.ln_w = bp.ib_ln_w.p; a.ln_b = bp.ib_ln_b.p;
@@ -420,7 +441,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
         const bf16* kv = static_cast<const bf16*>(s.kv[j]);
         SEA_TRY(attention_bwd(b, static_cast<const bf16*>(s.q[j]), Dd, kv, kv + Dd, 2 * Dd,
                               static_cast<const bf16*>(s.a[j]), g.da, Dd, s.lse_c[j], g.dq, Dd, g.dkv,
-                              g.dkv + Dd, 2 * Dd, hdc, d->rope_cross));
+                              g.dkv + Dd, 2 * Dd, hdc, d->rope_cross, drop_site(l, SEA_SITE_CROSS, i, j)));
         // q projection (input: ln_cross_i(down_i(x1_i)))
         { LinB& q = L[0]; q = LinB{};
           q.dy = g.dq; q.lddy = Dd; q.a = static_cast<const bf16*>(s.npre); q.lda = Dd;
@@ -491,7 +512,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       bf16* dqkv = bt.s[i].dqkv;
       SEA_TRY(attention_bwd(b, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, static_cast<const bf16*>(lt.s[i].ao),
                             bt.s[i].dao, E, lt.s[i].lse, dqkv, 3 * E, dqkv + E, dqkv + 2 * E, 3 * E, hd,
-                            d->rope_self));
+                            d->rope_self, drop_site(l, SEA_SITE_SELF, i, 0)));
     }
     for (int i = 0; i < V; ++i) {
       LinB& q = L[i]; q = LinB{};

@@ -112,6 +112,7 @@ struct Ctx {
   long long ld_ib;   // row pitch of ib for the condition path
   int cond_div;      // token row m uses condition row m / cond_div
   bool inv;          // condition path evaluated once per trajectory (time-invariant ib)
+  float drop_p;      // train-mode dropout probability of this call (0 in eval / inference)
   int pos0;          // absolute position of row 0 of every trajectory (KV-cached step: the new token's)
 };
 
@@ -129,6 +130,7 @@ struct LinOut {
   void* post; long long ld_post;  // act-dtype copy of act(v)
   int act;
   int rope_cols, head_dim; const float* rope_table;
+  float drop_p; unsigned drop_site;   // nn.Dropout on (acc + bias) before the residual (train mode)
 };
 
 void layout_cache(const sea_temporal_desc* d, bool training, Arena& ar, CacheLayout& c);
@@ -137,6 +139,10 @@ void layout_cond_cache(const sea_temporal_desc* d, int B, Arena& ar, Tape& t);
 int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, const LinOut* out, int Mrows);
 
 extern thread_local int g_launches;
+
+// dropout site ids of the temporal executor (see sea_dropout_mask)
+inline unsigned drop_site(int layer, int kind, int i, int j) { return static_cast<unsigned>(((layer * 4 + kind) * 4 + i) * 4 + j); }
+enum { SEA_SITE_SELF = 0, SEA_SITE_CROSS = 1, SEA_SITE_MLP = 2, SEA_SITE_TIPI = 3 };
 
 // RAII CUDA-event pair around one launch when profiling is on (no-op otherwise).
 // `work` is the launch's algorithmic work: FLOPs for GEMM / attention, bytes for HBM-bound kernels.

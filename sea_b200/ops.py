@@ -29,7 +29,7 @@ def _ld(t: Optional[torch.Tensor]) -> int:
 def gemm_problem(a, b, *, bias=None, residual=None, gelu_grad_of=None, act=ACT_NONE,
                  rope_table=None, rope_cols=0, head_dim=0, seq_len=0, rope_sign=1.0,
                  out_f32=None, out_pre_bf16=None, out_bf16=None, b_is_static=False, mn_major=0,
-                 rope_pos0=0) -> GemmProblem:
+                 rope_pos0=0, dropout_p=0.0, dropout_site=0, dropout_seed=0) -> GemmProblem:
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.stride(1) == 1 and b.stride(1) == 1
     # rope_table: pair-major [head_dim/2, rope_ld, 2]
@@ -38,7 +38,7 @@ def gemm_problem(a, b, *, bias=None, residual=None, gelu_grad_of=None, act=ACT_N
         _ptr(bias), _ptr(residual), _ld(residual), _ptr(gelu_grad_of), _ld(gelu_grad_of), act,
         rope_cols, head_dim, seq_len, float(rope_sign), rope_ld, _ptr(rope_table),
         _ptr(out_f32), _ld(out_f32), _ptr(out_pre_bf16), _ld(out_pre_bf16),
-        _ptr(out_bf16), _ld(out_bf16), int(rope_pos0), 0, 0)
+        _ptr(out_bf16), _ld(out_bf16), int(rope_pos0), 0, 0, float(dropout_p), int(dropout_site), int(dropout_seed))
     return GemmProblem(_ptr(a), a.stride(0), _ptr(b), b.stride(0), e, int(b_is_static), int(mn_major))
 
 

@@ -10,6 +10,7 @@ module tree below only HOLDS parameters; all arithmetic happens in the CUDA libr
 Supported configuration = what both reference configs select (configs/cylinder_flow.py:112-128):
 exchange_mode='sea', ib_scale_mode='mlp', ib_addition_mode='add', add_info_after_cross=True,
 LN_type in {'adaln','ln'}.  Anything else raises NotImplementedError — there is no fallback path.
+Train-mode dropout (cylinder_flow: 0.1) is applied inside the kernels (counter-based masks).
 """
 from __future__ import annotations
 
@@ -160,7 +161,9 @@ class TemporalModel(nn.Module):
     def forward(self, x, x_additional_info):
         assert x.shape[2] == self.num_variables, \
             f"Expected {self.num_variables} variables, but got {x.shape[2]}"
-        return self.engine()(x, x_additional_info)
+        eng = self.engine()
+        eng.dropout = self.dropout_p if self.training else 0.0    # nn.Dropout is the identity in eval mode
+        return eng(x, x_additional_info)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -440,7 +443,7 @@ class TemporalEngine:
             pool.append(ws)
 
     @torch.no_grad()
-    def backward(self, x, ib, dy, ws, need_dx: bool):
+    def backward(self, x, ib, dy, ws, need_dx: bool, dropout_seed: int = 0, dropout_p: float = 0.0):
         if self.precision != "bf16":
             raise NotImplementedError("sea_b200 backward runs in bf16 mode (fp32 split mode is forward-only)")
         self._ensure(True)
@@ -451,6 +454,7 @@ class TemporalEngine:
         dy = dy.contiguous().float()
         dx = torch.empty_like(x) if need_dx else None
         self._desc.grads_fresh = int(getattr(self, "_grads_fresh", False))
+        self._desc.dropout_p, self._desc.dropout_seed = float(dropout_p), int(dropout_seed)
         self._grads_fresh = False
         with torch.cuda.device(x.device):
             check(lib.sea_temporal_backward(C.byref(self._desc), C.c_void_p(self._cache.data_ptr()),
@@ -469,9 +473,8 @@ class TemporalEngine:
                        ws: Optional[torch.Tensor] = None) -> torch.Tensor:
         if x.device.type != "cuda":
             raise RuntimeError("sea_b200 has no CPU path: inputs must be CUDA tensors")
-        if training and self.dropout > 0.0:
-            raise NotImplementedError("train-mode dropout > 0 is not implemented in sea_b200; "
-                                      "set config['dropout'] = 0.0 (multiphase_flow already does)")
+        if training and self.dropout > 0.0 and self.precision != "bf16":
+            raise NotImplementedError("sea_b200: train-mode dropout runs in bf16 mode only")
         self._ensure(training)
         B, T, V, E = x.shape
         x = x.contiguous().float()
@@ -481,6 +484,15 @@ class TemporalEngine:
             ws = self.workspace(B, T, training)
         inv = bool(self.ib_time_invariant) and not training
         self._desc.ib_time_invariant = int(inv)
+        # train-mode nn.Dropout (attention probabilities, MLP and TIPI outputs): counter-based masks keyed by
+        # a seed drawn from torch's CPU generator (torch.manual_seed makes runs repeatable); the backward of
+        # this forward must see the same seed (autograd.py keeps it)
+        self._desc.dropout_p = float(self.dropout) if training else 0.0
+        if training and self.dropout > 0.0:
+            self.last_dropout_seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        else:
+            self.last_dropout_seed = 0
+        self._desc.dropout_seed = self.last_dropout_seed
         self._desc.cond_cache, self._desc.cond_cache_bytes, self._desc.cond_cache_valid = None, 0, 0
         use_cc = inv and self.cond_reuse and T > 1
         if use_cc:
