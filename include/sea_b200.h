@@ -134,6 +134,9 @@ int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem* host_prob
  * whose last wave is ragged split the flattened (tile, k-block) space evenly over the SMs; the CTA that
  * arrives last at a shared tile sums the partials in CTA order (deterministic) and runs the epilogue. */
 int sea_gemm_set_workspace(void* workspace, size_t bytes);
+/* Tuning hook: 1 = launch 256-wide-tile GEMMs as two-CTA clusters over vertically adjacent tiles, each CTA
+ * fetching half of the shared B tile and TMA-multicasting it to both (halves B's L2 traffic); default 0. */
+void sea_gemm_cluster(int on);
 /* Tuning hook: 0 = never stream-K, 1 = when the cost model prefers it (default), 2 = whenever legal. */
 void sea_gemm_stream_k(int mode);
 /* Test / tuning hook: force the N-tile (64, 128, 256) of the next launches; 0 = heuristic. */

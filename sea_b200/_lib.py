@@ -79,6 +79,10 @@ class _Lazy:
                     getattr(dll, fn).restype = C.c_size_t
             if os.environ.get("SEA_B200_PDL", "1") == "0":   # A/B switch for programmatic dependent launch
                 dll.sea_set_pdl(0)
+            if os.environ.get("SEA_B200_CLUSTER", "0") == "1":   # opt-in: two-CTA multicast GEMM variant
+                dll.sea_gemm_cluster(1)
+            if os.environ.get("SEA_B200_STREAMK", "1") == "0":   # A/B switch: stream-K tails
+                dll.sea_gemm_stream_k(0)
             self._dll = dll
         return self._dll
 

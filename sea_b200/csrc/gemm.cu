@@ -55,6 +55,7 @@ struct alignas(64) GemmParams {
   int M, N, K;
   int groups, tiles_m, tiles_n;
   int chunk_kb;  // k-blocks per accumulation chunk (== num_kb when not chunked)
+  int cluster;              // 2: two-CTA clusters with multicast B halves (N-tile 256, data-parallel only)
   int sk_grid;              // CTAs of a launch with a stream-K tail
   int dp_tiles;             // tiles [0, dp_tiles) are processed whole, round-robin (full waves)
   int units_per_cta;        // > 0: the other tiles are stream-K'd: contiguous (tile, k-block) units per CTA
@@ -291,7 +292,12 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
 //     wgrad     dW = dy^T x       A = dy [M,N] = [Kc, M'] B = x  [M,K] = [Kc, N'] (true,  true)
 //   Stage layout of an MN-major operand, per 64-wide M/N chunk: [BK k-rows][128 B]; descriptors step
 //   16 k-rows (2048 B) per MMA, LBO = chunk stride, SBO = 1024 B (8 k-rows).
-template <int BN, bool AMN, bool BMN>
+// CL = 2: thread-block cluster of two CTAs that work on vertically adjacent tiles (same N-tile, M-tiles
+// 2k and 2k+1).  They need the same B tile, so each CTA requests only HALF of it and TMA multicasts that
+// half into both CTAs' shared memory: B's L2 -> SM traffic halves (the 128x256 tiles are L2-bandwidth
+// bound at full grid: 48 KB per 4.2 MFLOP).  A ring stage is refilled only when both CTAs have consumed
+// it (the MMA warps' commits arrive on both CTAs' `empty` barriers).
+template <int BN, bool AMN, bool BMN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
@@ -319,7 +325,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
-  const int tiles_per_group = p.tiles_m * p.tiles_n;
+  const int crank = CL > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int vcta = blockIdx.x / CL, vgrid = gridDim.x / CL;      // tiles are dealt to clusters
+  const int tiles_m_v = (p.tiles_m + CL - 1) / CL;                // M-tile pairs
+  const int tiles_per_group = tiles_m_v * p.tiles_n;
   const int total_tiles = tiles_per_group * p.groups;
 
   if (threadIdx.x == 0) {
@@ -329,7 +338,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&empty[s], CL);   // one commit per CTA of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
@@ -339,11 +348,43 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();   // the peer's barriers must exist before anything lands on them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // prologue done (barriers, TMEM, descriptor prefetch): let the next kernel start its own
   ptx::pdl_trigger();
+
+  // B tile of one stage.  CL = 1: the whole tile.  CL = 2: this CTA's half (K-major: rows [crank*BN/2, +BN/2)
+  // through a half-height box; MN-major: its half of the 64-column chunks), multicast to both CTAs.
+  auto load_b_tile = [&](int stg, int g, int tn, int kb) {
+    uint8_t* dst = smem_b + stg * C::B_BYTES;
+    if (CL == 1) {
+      if (BMN) {
+#pragma unroll
+        for (int a = 0; a < BN / 64; ++a)
+          ptx::tma_load_2d(dst + a * (BK * 128), &p.tma_b[g], &full[stg], tn * BN + a * 64, kb * BK);
+      } else {
+#pragma unroll
+        for (int a = 0; a < C::KATOMS; ++a)
+          ptx::tma_load_2d(dst + a * (BN * 128), &p.tma_b[g], &full[stg], kb * BK + a * KA, tn * BN);
+      }
+    } else {
+      constexpr uint16_t kMask = (1u << CL) - 1u;
+      if (BMN) {
+#pragma unroll
+        for (int a0 = 0; a0 < BN / 64 / CL; ++a0) {
+          const int a = crank * (BN / 64 / CL) + a0;
+          ptx::tma_load_2d_mc(dst + a * (BK * 128), &p.tma_b[g], &full[stg], tn * BN + a * 64, kb * BK, kMask);
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < C::KATOMS; ++a)
+          ptx::tma_load_2d_mc(dst + a * (BN * 128) + crank * (BN / CL) * 128, &p.tma_b[g], &full[stg],
+                              kb * BK + a * KA, tn * BN + crank * (BN / CL), kMask);
+      }
+    }
+  };
 
   // Work decomposition.  A "segment" is a run of k-blocks [kb0, kb1) of one output tile, accumulated
   // into one TMEM stage.
@@ -360,8 +401,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   };
   struct SegIt { int cursor, sub, u, u1; };
   auto seg_begin = [&](SegIt& it) {
-    it.cursor = blockIdx.x; it.sub = 0;
-    it.u = blockIdx.x * p.units_per_cta;
+    it.cursor = vcta; it.sub = 0;
+    it.u = vcta * p.units_per_cta;
     it.u1 = p.units_per_cta > 0 ? min(it.u + p.units_per_cta, (total_tiles - p.dp_tiles) * num_kb) : 0;
   };
   auto seg_next = [&](SegIt& it, Seg& sg) -> bool {
@@ -371,7 +412,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       sg.kb1 = min(num_kb, it.sub + p.chunk_kb);
       sg.sk = false;
       it.sub = sg.kb1;
-      if (it.sub >= num_kb) { it.sub = 0; it.cursor += gridDim.x; }
+      if (it.sub >= num_kb) { it.sub = 0; it.cursor += vgrid; }
       return true;
     }
     if (p.units_per_cta > 0 && it.u < it.u1) {
@@ -403,20 +444,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       if (p.b_is_static && seg_next(it2, first_seg)) {
         pre = min(first_seg.kb1 - first_seg.kb0, STAGES);
         const int g = first_seg.tile / tiles_per_group;
-        const int tn = (first_seg.tile - g * tiles_per_group) / p.tiles_m;
+        const int tn = (first_seg.tile - g * tiles_per_group) / tiles_m_v;
         if (ptx::elect_one()) {
           for (int i = 0; i < pre; ++i) {
             const int kb = first_seg.kb0 + i;
             ptx::mbar_expect_tx(&full[i], C::STAGE_BYTES);
-            if (BMN) {
-#pragma unroll
-              for (int a = 0; a < BN / 64; ++a)
-                ptx::tma_load_2d(smem_b + i * C::B_BYTES + a * (BK * 128), &p.tma_b[g], &full[i], tn * BN + a * 64, kb * BK);
-            } else {
-#pragma unroll
-              for (int a = 0; a < C::KATOMS; ++a)
-                ptx::tma_load_2d(smem_b + i * C::B_BYTES + a * (BN * 128), &p.tma_b[g], &full[i], kb * BK + a * KA, tn * BN);
-            }
+            load_b_tile(i, g, tn, kb);
           }
         }
         __syncwarp();
@@ -427,8 +460,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
     while (seg_next(it, sg)) {
       const int g = sg.tile / tiles_per_group;
       const int r = sg.tile - g * tiles_per_group;
-      const int tm = r % p.tiles_m;
-      const int tn = r / p.tiles_m;
+      const int tm = (r % tiles_m_v) * CL + crank;
+      const int tn = r / tiles_m_v;
       for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++issued) {
         const bool prefetched = issued < pre;
         if (!prefetched) ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -444,17 +477,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
                 ptx::tma_load_2d(smem_a + stage * A_BYTES + a * (BM * 128), &p.tma_a[g], &full[stage], kb * BK + a * KA, tm * BM);
             }
           };
-          auto load_b = [&]() {
-            if (BMN) {
-#pragma unroll
-              for (int a = 0; a < BN / 64; ++a)
-                ptx::tma_load_2d(smem_b + stage * C::B_BYTES + a * (BK * 128), &p.tma_b[g], &full[stage], tn * BN + a * 64, kb * BK);
-            } else {
-#pragma unroll
-              for (int a = 0; a < C::KATOMS; ++a)
-                ptx::tma_load_2d(smem_b + stage * C::B_BYTES + a * (BN * 128), &p.tma_b[g], &full[stage], kb * BK + a * KA, tn * BN);
-            }
-          };
+          auto load_b = [&]() { load_b_tile(stage, g, tn, kb); };
           if (prefetched) {
             load_a();
           } else if (p.debug == 1) {
@@ -498,7 +521,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
                                       : ptx::umma_smem_desc(b_base + (k >> 2) * (BN * 128) + (k & 3) * 32, 16, 1024);
             if (p.debug != 2) ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty[stage]);
+          if (CL > 1) ptx::umma_commit_mc(&empty[stage], static_cast<uint16_t>((1u << CL) - 1u));
+          else ptx::umma_commit(&empty[stage]);
           if (kb == kb1 - 1) ptx::umma_commit(&tfull[acc]);
         }
         __syncwarp();
@@ -522,8 +546,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
     while (seg_next(it, sg)) {
       const int g = sg.tile / tiles_per_group;
       const int r = sg.tile - g * tiles_per_group;
-      const int tm = r % p.tiles_m;
-      const int tn = r / p.tiles_m;
+      const int tm = (r % tiles_m_v) * CL + crank;
+      const int tn = r / tiles_m_v;
       const DevEpilogue& e = p.epi[g];
       const int m = tm * BM + row;
       const bool first = sg.kb0 == 0, last = sg.kb1 >= num_kb;
@@ -604,7 +628,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();   // no CTA leaves while the peer may still multicast into it
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -613,6 +638,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
 
 int g_force_bn = 0;
 int g_debug = 0;
+int g_cluster = 0;    // 1 = two-CTA multicast variant for 256-wide tiles.  Opt-in: measured +8 % on the multiphase
+                      // MLP up-projection (3184x16384x2048), neutral to -1.5 % on the cylinder shapes (the big GEMMs
+                      // already sit at the sustained cuBLAS rate, so halving B's L2 traffic buys little)
 int g_stream_k = 1;   // 0 = never, 1 = when the cost model says so, 2 = whenever legal (tests)
 constexpr int kSkMaxTiles = 16384;                      // arrival counters (64 KB)
 thread_local unsigned int* g_sk_counters = nullptr;     // caller-owned stream-K workspace (this thread)
@@ -626,15 +654,38 @@ int launch(const GemmParams& p, int total_tiles, int num_kb, cudaStream_t stream
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, AMN, BMN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, AMN, BMN, 1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
+    if (BN == 256) {
+      e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<256, AMN, BMN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Cfg<256>::SMEM_BYTES);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
     attr_set[dev] = true;
+  }
+  (void)num_kb;
+  if (BN == 256 && p.cluster == 2) {
+    // clusters of two CTAs over M-tile pairs, B halves multicast
+    const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n * p.groups;
+    int clusters = num_sms() / 2;
+    if (pairs < clusters) clusters = pairs;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<256>::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_enabled() && !pdl_take_fence()) ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<256, AMN, BMN, 2>, p);
+    return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   if (p.units_per_cta > 0) grid = p.sk_grid;
-  (void)num_kb;
-  SEA_LAUNCH((gemm_bf16_tn_kernel<BN, AMN, BMN>), grid, kThreads, C::SMEM_BYTES, stream, p);
+  SEA_LAUNCH((gemm_bf16_tn_kernel<BN, AMN, BMN, 1>), grid, kThreads, C::SMEM_BYTES, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -659,6 +710,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
 
 extern "C" void sea_gemm_force_tile_n(int bn) { sea::g_force_bn = bn; }
 extern "C" void sea_gemm_stream_k(int mode) { sea::g_stream_k = mode; }
+extern "C" void sea_gemm_cluster(int on) { sea::g_cluster = on; }
 extern "C" int sea_gemm_set_workspace(void* ws, size_t bytes) {
   using namespace sea;
   if (ws == nullptr || bytes <= 65536 + 2 * BM * 64 * sizeof(float)) {
@@ -768,6 +820,8 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   p.units_per_cta = units_per_cta;
   p.dp_tiles = units_per_cta > 0 ? dp_tiles : 0x7fffffff;
   p.sk_grid = sk_grid;
+  p.cluster = (bn == 256 && units_per_cta == 0 && g_cluster != 0 && !(k_chunk > 0 && k_chunk < K) &&
+               (M + BM - 1) / BM >= 2) ? 2 : 1;
   p.sk_ws = g_sk_ws;
   p.sk_counters = g_sk_counters;
   p.b_is_static = 1;
@@ -805,7 +859,7 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
              : make_tmap_bf16_2d(&p.tma_a[g], q.a, K, M, q.lda, KA, BM);
     if (rc != SEA_OK) return rc;
     rc = bmn ? make_tmap_bf16_2d(&p.tma_b[g], q.b, N, K, q.ldb, 64, bk)
-             : make_tmap_bf16_2d(&p.tma_b[g], q.b, K, N, q.ldb, KA, bn);
+             : make_tmap_bf16_2d(&p.tma_b[g], q.b, K, N, q.ldb, KA, p.cluster == 2 ? bn / 2 : bn);
     if (rc != SEA_OK) return rc;
     DevEpilogue& d = p.epi[g];
     d.bias = e.bias;

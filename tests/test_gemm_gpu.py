@@ -200,3 +200,35 @@ def test_gemm_stream_k(cuda, M, N, K, groups, bn):
         # accumulator: the two schedules differ at the level of that accumulator's drift
         d = ((sk1[0][i].double() - dp[0][i].double()).norm() / dp[0][i].double().norm()).item()
         assert d < 3e-5, d
+
+
+@pytest.mark.parametrize("M,N,K,groups,mn", [(3200, 8192, 1024, 2, 0), (796, 2048, 2048, 1, 0), (1000, 1024, 512, 2, 2),
+                                             (384, 512, 4096, 1, 0), (1024, 768, 520, 1, 3)])
+def test_gemm_cluster_multicast_variant(cuda, M, N, K, groups, mn):
+    """Two-CTA clusters with TMA-multicast B halves (opt-in) against the single-CTA schedule of the same
+    tile width: bit-identical (same MMA sequence per output element), odd M-tile counts included."""
+    from sea_b200 import lib, ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a_shape, b_shape = ((K, M) if mn & 1 else (M, K)), ((K, N) if mn & 2 else (N, K))
+    a = [torch.randn(*a_shape, device=cuda, generator=g).bfloat16() for _ in range(groups)]
+    b = [(torch.randn(*b_shape, device=cuda, generator=g) * 0.05).bfloat16() for _ in range(groups)]
+    bias = torch.randn(N, device=cuda, generator=g)
+    outs = []
+    for cl in (0, 1):
+        of = [torch.empty(M, N, device=cuda) for _ in range(groups)]
+        lib.sea_gemm_force_tile_n(256)
+        lib.sea_gemm_cluster(cl)
+        try:
+            ops.gemm_bf16_tn([ops.gemm_problem(a[i], b[i], bias=bias, out_f32=of[i], mn_major=mn, b_is_static=True)
+                              for i in range(groups)], M, N, K)
+        finally:
+            lib.sea_gemm_force_tile_n(0)
+            lib.sea_gemm_cluster(0)
+        torch.cuda.synchronize()
+        outs.append(of)
+    for i in range(groups):
+        assert torch.equal(outs[0][i], outs[1][i])
+    A = a[0].double().t() if mn & 1 else a[0].double()
+    Bm = b[0].double() if mn & 2 else b[0].double().t()
+    ref = A @ Bm + bias.double()
+    assert ((outs[1][0].double() - ref).norm() / ref.norm()).item() < 1e-5
