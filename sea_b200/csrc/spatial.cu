@@ -154,14 +154,15 @@ __device__ __forceinline__ long long latent_index(int b, int p, int g, int d, in
 // ------------------------------------------------------------------------------------ encoder
 __global__ void __launch_bounds__(kThreads) spatial_encode_kernel(const SpatialDev a, float* __restrict__ x,
                                                                   float* __restrict__ z, int layout,
-                                                                  float pad_idx, int fix_pad) {
+                                                                  float pad_idx, int fix_pad, int staged) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int FC = a.n_fields * a.C, Es = a.n_groups * a.D;
   const int big_w = max(4 * Es, kChunk);
+  // staged == 0 (snapshot too wide for shared memory): the patch MLP reads the snapshot in place
   float* Xin = sm;                  // [64][FC]      (only until the patch MLPs are done)
-  float* Z = Xin + P * FC;          // [64][Es]      residual state
+  float* Z = Xin + (staged ? P * FC : 0);   // [64][Es]  residual state
   float* Nn = Z + P * Es;           // [64][Es]      normed input / attention output
   float* BIG = Nn + P * Es;         // [64][big_w]   q|k|v, MLP hidden, patch-MLP hidden chunk
   const int b = blockIdx.x;
@@ -177,9 +178,10 @@ __global__ void __launch_bounds__(kThreads) spatial_encode_kernel(const SpatialD
         *reinterpret_cast<float4*>(xb + i) = v;
       }
     }
-    *reinterpret_cast<float4*>(Xin + i) = v;
+    if (staged) *reinterpret_cast<float4*>(Xin + i) = v;
   }
   __syncthreads();
+  if (!staged) Xin = xb;
   // (2) per-group patch MLP: Linear(C*g, Hs, no bias) -> GELU -> Linear(Hs, D) + b   (:108-111)
   for (int g = 0; g < a.n_groups; ++g) {
     const int Kin = a.g_count[g] * a.C;
@@ -229,15 +231,16 @@ __global__ void __launch_bounds__(kThreads) spatial_encode_kernel(const SpatialD
 
 // ------------------------------------------------------------------------------------ decoder
 __global__ void __launch_bounds__(kThreads) spatial_decode_kernel(const SpatialDev a, const float* __restrict__ z,
-                                                                  float* __restrict__ out, int layout) {
+                                                                  float* __restrict__ out, int layout, int staged) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int FC = a.n_fields * a.C, Es = a.n_groups * a.D;
+  const int b = blockIdx.x;
+  float* ob = out + static_cast<long long>(b) * P * FC;
   float* Zin = sm;                 // [64][Es]
   float* BIG = Zin + P * Es;       // [64][kChunk]
-  float* Out = BIG + P * kChunk;   // [64][FC]
-  const int b = blockIdx.x;
+  float* Out = staged ? BIG + P * kChunk : ob;   // [64][FC]; accumulated in place when too wide for smem
   for (int i = threadIdx.x; i < P * Es; i += kThreads) {
     const int p = i / Es, c = i - p * Es, g = c / a.D, d = c - g * a.D;
     Zin[i] = z[latent_index(b, p, g, d, a.n_groups, a.D, layout)];
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(kThreads) spatial_decode_kernel(const SpatialD
       __syncthreads();
     }
   }
-  float* ob = out + static_cast<long long>(b) * P * FC;
+  if (!staged) return;
   for (int i = threadIdx.x * 4; i < P * FC; i += kThreads * 4)
     *reinterpret_cast<float4*>(ob + i) = *reinterpret_cast<const float4*>(Out + i);
 }
@@ -302,10 +305,12 @@ extern "C" int sea_spatial_encode(const sea_spatial_desc* d, float* x, float* z,
   if (!a.ln_w || !a.ln_b || !a.pe || (a.num_layers > 0 && !d->layers)) return SEA_ERR_INVALID;
   const int FC = a.n_fields * a.C, Es = a.n_groups * a.D;
   const int big_w = 4 * Es > kChunk ? 4 * Es : kChunk;
-  const size_t smem = sizeof(float) * (static_cast<size_t>(P) * FC + 2 * P * Es + static_cast<size_t>(P) * big_w);
+  size_t smem = sizeof(float) * (static_cast<size_t>(P) * FC + 2 * P * Es + static_cast<size_t>(P) * big_w);
+  const int staged = smem <= 220 * 1024;
+  if (!staged) smem -= sizeof(float) * static_cast<size_t>(P) * FC;
   if (smem > 220 * 1024) return SEA_ERR_UNSUPPORTED;
   SEA_CUDA_OK(cudaFuncSetAttribute(spatial_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  SEA_LAUNCH(spatial_encode_kernel, B, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), a, x, z, latent_layout, pad_idx, fix_pad);
+  SEA_LAUNCH(spatial_encode_kernel, B, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), a, x, z, latent_layout, pad_idx, fix_pad, staged);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -318,9 +323,11 @@ extern "C" int sea_spatial_decode(const sea_spatial_desc* d, const float* z, flo
   for (int g = 0; g < a.n_groups; ++g)
     if (!a.dec_w1[g] || !a.dec_w2[g] || !a.dec_b2[g]) return SEA_ERR_INVALID;
   const int FC = a.n_fields * a.C, Es = a.n_groups * a.D;
-  const size_t smem = sizeof(float) * (static_cast<size_t>(P) * Es + static_cast<size_t>(P) * kChunk + static_cast<size_t>(P) * FC);
+  size_t smem = sizeof(float) * (static_cast<size_t>(P) * Es + static_cast<size_t>(P) * kChunk + static_cast<size_t>(P) * FC);
+  const int staged = smem <= 220 * 1024;
+  if (!staged) smem -= sizeof(float) * static_cast<size_t>(P) * FC;
   if (smem > 220 * 1024) return SEA_ERR_UNSUPPORTED;
   SEA_CUDA_OK(cudaFuncSetAttribute(spatial_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  SEA_LAUNCH(spatial_decode_kernel, B, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), a, z, out, latent_layout);
+  SEA_LAUNCH(spatial_decode_kernel, B, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), a, z, out, latent_layout, staged);
   return static_cast<int>(cudaGetLastError());
 }

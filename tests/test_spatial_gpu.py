@@ -64,6 +64,34 @@ def test_spatial_ragged_batch_and_oracle(cuda):
     assert rel_l2(z.cpu(), ref_z) < 1e-4 and rel_l2(y.cpu(), ref_y) < 1e-4
 
 
+@pytest.mark.parametrize("C", [256, 320])
+def test_spatial_wide_snapshot_unstaged(cuda, C):
+    """Snapshots too wide for the CTA's shared memory (BASELINE configs[4] sweeps C up to 256):
+    the patch MLPs read / accumulate the snapshot in place in global memory; results must match
+    the oracle exactly like the staged path, including the in-place -9999 rewrite."""
+    from oracle import golden_recipe as gr
+    from sea_b200.spatial import SpatialModel
+    fg = [[0, 1], [2]]
+    shapes = [(k, tuple(v.shape)) for k, v in so.init_spatial_state(
+        field_groups=fg, n_inp=C, mlp_hidden=480, num_layers=2, embed_dim=16).items()]
+    sd = gr.fill_state(shapes, 11)
+    m = SpatialModel(fg, C, 480, 2, 16, 8, 2024, 0, 0.0, False)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(cuda).eval()
+    xb = torch.randn(9, 64, 3, C, generator=torch.Generator().manual_seed(6))
+    xb[0, 0, 0, -4:] = -9999.0
+    xin = xb.clone().to(cuda)
+    xz = xb.clone()
+    xz[xz == -9999.0] = 0
+    with torch.no_grad():
+        ref_z = so.spatial_encode(xz, sd, field_groups=fg, num_layers=2, n_heads=8)
+        ref_y = so.spatial_decode(ref_z, sd, field_groups=fg)
+        y = m(xin)
+        z = m.encode(xin)
+    assert rel_l2(z.cpu(), ref_z) < 1e-4 and rel_l2(y.cpu(), ref_y) < 1e-4
+    assert torch.equal(xin.cpu(), xz)
+
+
 def test_spatial_throughput_report(cuda):
     from oracle import golden_recipe as gr
     g, sd, cfg, m, x = build("cylinder_flow", cuda)
