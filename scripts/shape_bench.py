@@ -89,6 +89,31 @@ def run_attn():
               f"bwd {us_b:8.1f} us {2.5*fl/us_b/1e6:7.1f} TF/s", flush=True)
 
 
+def run_attn_trace():
+    """clock64 probes of CTA (0,0,0) of the two-tile forward kernel (the heaviest query block)."""
+    import ctypes as C
+    from sea_b200._lib import lib
+    B, T, nh, hd = 4, 2024, 8, 128
+    qkv = torch.randn(B * T, 3 * nh * hd, device=dev).bfloat16()
+    q, k, v = qkv[:, : nh * hd], qkv[:, nh * hd: 2 * nh * hd], qkv[:, 2 * nh * hd:]
+    buf = torch.zeros(3 * 64 * 8, dtype=torch.int64, device=dev)
+    for _ in range(3):
+        ops.attention_fwd(q, k, v, nh, B=B)
+    lib.sea_attention_debug_trace(C.c_void_p(buf.data_ptr()))
+    ops.attention_fwd(q, k, v, nh, B=B)
+    torch.cuda.synchronize()
+    lib.sea_attention_debug_trace(C.c_void_p(0))
+    t = buf.cpu().view(3, 64, 8)
+    t0 = int(t[t > 0].min())
+    n = (T + 127) // 128
+    print("softmax group g, tile j: [s_full seen, ld done, max/rescale done, exp done, P stored+arrive] (cycles from first probe)")
+    for j in range(n):
+        for g in range(2):
+            r = [int(v) - t0 if int(v) else -1 for v in t[g, j, :5]]
+            m = [int(v) - t0 if int(v) else -1 for v in t[2, j, g * 3: g * 3 + 3]]
+            print(f"j={j:2d} g={g}: sm {r}   mma [p_full seen, kv seen, issued] {m}")
+
+
 def run_train():
     from sea_b200.rollout import profile
     from sea_b200.temporal import TemporalModel
@@ -351,4 +376,7 @@ def run_patchify():
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+    if what == "attn_trace":
+        run_attn_trace()
+        sys.exit(0)
     {"gemm": run_gemm, "attn": run_attn, "train": run_train, "rollout": run_rollout, "floor": run_floor, "kblock": run_kblock, "sk": run_sk, "patchify": run_patchify}[what]()

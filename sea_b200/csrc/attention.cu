@@ -18,7 +18,8 @@ static int validate(const sea_attn_args* a) {
 }
 }  // namespace sea
 
-namespace sea { extern int g_attn_two_tiles; }
+namespace sea { extern int g_attn_two_tiles; void attention_set_trace(void*); }
+extern "C" void sea_attention_debug_trace(void* dev_buf) { sea::attention_set_trace(dev_buf); }
 extern "C" void sea_attention_force_simt(int on) { sea::g_force_simt = on; }
 extern "C" void sea_attention_two_tiles(int on) { sea::g_attn_two_tiles = on; }
 

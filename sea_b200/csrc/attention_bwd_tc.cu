@@ -81,13 +81,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
 
   // warp-uniform role index + elect.sync regions (see gemm.cu): no waterfall loops around UTMALDG / UTCHMMA
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-  const int h = blockIdx.y, b = blockIdx.z;
+  // blockIdx.x = (batch, head), blockIdx.z = tile: the heaviest tiles of ALL (batch, head) pairs launch first
+  const int h = blockIdx.x % p.n_heads, b = blockIdx.x / p.n_heads;
   int tile, half = 0;
   if (MODE == 0) {
-    tile = gridDim.x - 1 - blockIdx.x;  // late query tiles see the most keys: schedule them first
+    tile = gridDim.z - 1 - blockIdx.z;  // late query tiles see the most keys: schedule them first
   } else {
-    tile = blockIdx.x / C::HALVES;      // early key tiles are seen by the most queries
-    half = blockIdx.x % C::HALVES;
+    tile = blockIdx.z / C::HALVES;      // early key tiles are seen by the most queries
+    half = blockIdx.z % C::HALVES;
   }
   const int r0 = tile * BR;
   // streamed tile range [it0, it0 + n_it)
@@ -406,7 +407,7 @@ int launch_mode(const sea_attn_bwd_args* a, cudaStream_t s) {
   p.drop_thresh = a->dropout_p > 0.f ? static_cast<uint32_t>(static_cast<double>(a->dropout_p) * 4294967296.0) : 0u;
   p.drop_scale = 1.0f / (1.0f - a->dropout_p);
   const int tiles = (a->T + BR - 1) / BR;
-  dim3 grid(tiles * (MODE == 1 ? C::HALVES : 1), a->n_heads, a->B);
+  dim3 grid(a->n_heads * a->B, 1, tiles * (MODE == 1 ? C::HALVES : 1));
   SEA_LAUNCH((attn_bwd_tc_kernel<HD, BS, MODE, DROP>), grid, kThreads, C::SMEM, s, p);
   return static_cast<int>(cudaGetLastError());
 }

@@ -17,7 +17,7 @@
 // (256 columns allocated) or, for HD = 256, O [256,512) (512 allocated).
 // STAGES = 1 (the whole key range fits one tile: short prefixes of a rollout) halves the shared
 // memory, so two CTAs share an SM and B x heads = 256 CTAs run as a single wave.
-// Up to SEA_MAX_STREAMS same-shape problems (the V field streams) share one launch (blockIdx.z).
+// Up to SEA_MAX_STREAMS same-shape problems (the V field streams) share one launch (blockIdx.x).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -48,6 +48,7 @@ struct alignas(64) AttnTcParams {
   unsigned long long drop_seed;   // dropout on the probabilities (DROP kernels only)
   uint32_t drop_thresh;
   float drop_scale;
+  long long* trace;               // clock64 probe buffer (TRACE kernels only; sea_attention_debug_trace)
 };
 
 template <int HD, int BKV, int STAGES_>
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(kThreads, (ACfg<HD, BKV, STAGES_>::MIN_CTAS))
 attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
   using C = ACfg<HD, BKV, STAGES_>;
   constexpr uint32_t kColO = C::COL_O;
-  const AttnTcItem& p = pp.it[blockIdx.z / pp.B];
+  const int bz = blockIdx.x / pp.n_heads;   // (problem, batch); blockIdx.z = query tile: heaviest tiles launch first
+  const AttnTcItem& p = pp.it[bz / pp.B];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -86,8 +88,8 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
   // warp-uniform role index + elect.sync regions: see the note in gemm.cu (no waterfall loops
   // around UTMALDG / UTCHMMA)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;  // heavy (late) query tiles first
-  const int h = blockIdx.y, b = blockIdx.z % pp.B;
+  const int qt = gridDim.z - 1 - blockIdx.z;  // heavy (late) query tiles first, across ALL (batch, head) pairs
+  const int h = blockIdx.x % pp.n_heads, b = bz % pp.B;
   const int q0 = qt * BQ;
   const int q_hi = min(pp.T - 1, q0 + BQ - 1);
   const int k_last = min(pp.T - 1, q_hi + pp.src_len);
@@ -309,11 +311,18 @@ struct ACfg2 {
   static constexpr int SMEM = Q_BYTES + 2 * 2 * KV_BYTES + 1024 + 128;
 };
 
-template <int HD, bool DROP>
+// TRACE: CTA (0,0,0) records clock64 at the hand-off points: trace[(role * 64 + j) * 8 + k], role 0/1 = softmax
+// group, 2 = MMA warp (tuning aid behind sea_attention_debug_trace; never on the product path).
+template <int HD, bool DROP, bool TRACE = false>
 __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid_constant__ AttnTcParams pp) {
   using C = ACfg2<HD>;
+  const bool tr_on = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0;
+  auto probe = [&](int role, int j, int k) {
+    if (TRACE && tr_on && j < 64) pp.trace[(role * 64 + j) * 8 + k] = clock64();
+  };
   constexpr int BKV = C::BKV;
-  const AttnTcItem& p = pp.it[blockIdx.z / pp.B];
+  const int bz = blockIdx.x / pp.n_heads;   // (problem, batch); blockIdx.z = query tile: heaviest tiles launch first
+  const AttnTcItem& p = pp.it[bz / pp.B];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -330,8 +339,8 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-  const int qb = gridDim.x - 1 - blockIdx.x;  // heavy (late) query blocks first
-  const int h = blockIdx.y, b = blockIdx.z % pp.B;
+  const int qb = gridDim.z - 1 - blockIdx.z;  // heavy (late) query blocks first, across ALL (batch, head) pairs
+  const int h = blockIdx.x % pp.n_heads, b = bz % pp.B;
   const int q0 = qb * 2 * BQ;
   int n_kv[2];
 #pragma unroll
@@ -425,7 +434,9 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
       for (int g = 0; g < 2; ++g) {
         if (j < n_kv[g]) {
           ptx::mbar_wait(&p_full[g], j & 1);
+          probe(2, j, g * 3);
           if (j + 1 < n_kv[g]) ptx::mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
+          probe(2, j, g * 3 + 1);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             issue_pv(g, s, j);
@@ -433,6 +444,7 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
             else ptx::umma_commit(&o_done[g]);
           }
           __syncwarp();
+          probe(2, j, g * 3 + 2);
         }
       }
       (void)more;
@@ -454,12 +466,14 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
       const int kv0 = j * BKV;
       ptx::mbar_wait(&s_full[g], j & 1);
       ptx::tc_fence_after();
+      if (quarter == 2) probe(g, j, 0);
       const bool need_mask = (kv0 + BKV - 1 > qg0 + pp.src_len) || (kv0 + BKV > pp.T);
       // the whole score row of this tile in registers: ONE TMEM round trip (four loads in flight)
       uint32_t r[BKV];
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld_32x32p(tmem + lane_base + colS + c * 32, r + c * 32);
       ptx::tmem_ld_wait();
+      if (quarter == 2) probe(g, j, 1);
       float mx = -INFINITY;   // max of the RAW scores (scale > 0 commutes with max)
       if (need_mask) {
 #pragma unroll
@@ -494,6 +508,7 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
       // p = 2^(s * scale_log2 - m): one FFMA + one MUFU per score; packed bf16 pairs overwrite S
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       float l0 = 0.f, l1 = 0.f;
+      if (quarter == 2) probe(g, j, 2);
       // dropout acts on the NORMALISED probabilities (base_blocks.py:193-194): the row sum stays undropped,
       // only the P that feeds P.V is masked and rescaled
       const unsigned long long drop_row = DROP ? ((static_cast<unsigned long long>(b) * pp.n_heads + h) * pp.T + q) *
@@ -511,11 +526,13 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
         r[e >> 1] = ptx::pack_bf16(p0, p1);
       }
       l_sum += l0 + l1;
+      if (quarter == 2) probe(g, j, 3);
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) ptx::tmem_st_32x16p(tmem + lane_base + colS + c * 16, r + c * 16);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&p_full[g]);
+      if (quarter == 2) probe(g, j, 4);
     }
     if (n_mine > 0) {
       ptx::mbar_wait(&o_done[g], 0);
@@ -553,6 +570,8 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
   }
 }
 
+long long* g_attn_trace = nullptr;
+
 template <int HD, bool DROP>
 int launch_tc2(int n, const sea_attn_args* a, cudaStream_t s) {
   using C = ACfg2<HD>;
@@ -583,7 +602,15 @@ int launch_tc2(int n, const sea_attn_args* a, cudaStream_t s) {
   p.ldo = a->ldo;
   p.B = a->B; p.T = a->T; p.n_heads = a->n_heads; p.src_len = a->src_len;
   p.scale_log2 = a->scale * 1.44269504088896340736f;
-  dim3 grid((a->T + 2 * BQ - 1) / (2 * BQ), a->n_heads, a->B * n);
+  dim3 grid(a->n_heads * a->B * n, 1, (a->T + 2 * BQ - 1) / (2 * BQ));
+  p.trace = g_attn_trace;
+  if constexpr (HD == 128 && !DROP) {
+    if (g_attn_trace != nullptr) {
+      SEA_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<HD, DROP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      SEA_LAUNCH((attn_fwd_tc2_kernel<HD, DROP, true>), grid, kThreads2, C::SMEM, s, p);
+      return static_cast<int>(cudaGetLastError());
+    }
+  }
   SEA_LAUNCH((attn_fwd_tc2_kernel<HD, DROP>), grid, kThreads2, C::SMEM, s, p);
   return static_cast<int>(cudaGetLastError());
 }
@@ -619,7 +646,7 @@ int launch_tc(int n, const sea_attn_args* a, cudaStream_t s) {
   p.ldo = a->ldo;
   p.B = a->B; p.T = a->T; p.n_heads = a->n_heads; p.src_len = a->src_len;
   p.scale_log2 = a->scale * 1.44269504088896340736f;
-  dim3 grid((a->T + BQ - 1) / BQ, a->n_heads, a->B * n);
+  dim3 grid(a->n_heads * a->B * n, 1, (a->T + BQ - 1) / BQ);
   SEA_LAUNCH((attn_fwd_tc_kernel<HD, BKV, STAGES_, DROP>), grid, kThreads, C::SMEM, s, p);
   return static_cast<int>(cudaGetLastError());
 }
@@ -637,6 +664,8 @@ bool attention_tc_supported(const sea_attn_args* a) {
     return false;
   return true;
 }
+
+void attention_set_trace(void* dev_buf) { g_attn_trace = static_cast<long long*>(dev_buf); }
 
 int g_attn_two_tiles = 1;  // tuning hook: 0 = one query tile per CTA also for long sequences
 
