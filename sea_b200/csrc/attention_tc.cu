@@ -292,23 +292,29 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
 
 // ---------------------------------------------------------------------------------------------
 // Two query tiles per CTA (T > 128, HD <= 128): the tensor pipe and the softmax warps overlap.
-//   warp 0      TMA (Q for 256 query rows once, K_j / V_j ring of 2 stages)
-//   warp 1      tcgen05.mma issue, interleaved so each softmax group always has its next S ready:
-//                 S0_0, S1_0, then per key tile j:  [P0_j ready] PV0_j, S0_{j+1}   [P1_j ready] PV1_j, S1_{j+1}
+//   warp 0      TMA (Q for 256 query rows once; K_j and V_j rings of 2 stages each, released separately:
+//               K_j is free as soon as S(j) is issued, V_j after P.V(j), so both loads run a tile ahead)
+//   warp 1      tcgen05.mma issue, interleaved so each softmax group always has its next S in flight:
+//                 S0_0, S1_0, then per key tile j:  PV0_j (two halves), S0_{j+1},  PV1_j (two halves), S1_{j+1}
 //   warps 2..5  softmax group 0 (query rows q0 .. q0+127),  warps 6..9  group 1 (q0+128 .. q0+255)
-// While group 0 exponentiates tile j the pipe computes S1_j / PV1_{j-1}, and vice versa.  Because the
-// MMAs execute in issue order, "S_g(j) complete" implies "PV_g(j-1) complete": a group may rescale its
-// O accumulator as soon as it sees its next S, no extra barrier.
+// While group 0 exponentiates tile j the pipe computes PV1_{j-1} / S1_j, and vice versa.  A group hands
+// its P over in two halves of 64 keys: the pipe starts P.V on the first half while the second half is
+// still being exponentiated.  Because the MMAs execute in issue order, "S_g(j) complete" implies
+// "PV_g(j-1) complete": a group may rescale its O accumulator as soon as it sees its next S.
 // TMEM columns: S0|P0 [0,128)  S1|P1 [128,256)  O0 [256,256+HD)  O1 [384,384+HD).
+// The exponentials stay on the SFU: scripts/micro/sfu_probe.cu (profiles/r1d_attention.md) measured 8 cycles
+// per score and sub-partition for FFMA + MUFU.EX2 + FADD + pack with four warps (14 with one), and a
+// polynomial 2^x on the FMA pipe ADDS to that instead of overlapping (10 cycles with 3 of 8 scores moved).
 constexpr int kThreads2 = 320;
 
 template <int HD>
 struct ACfg2 {
   static constexpr int BKV = 128;
+  static constexpr int HB = 64;     // keys per P hand-off
   static constexpr int ATOMS = HD / 64;
   static constexpr int Q_BYTES = 2 * BQ * HD * 2;
   static constexpr int KV_BYTES = BKV * HD * 2;
-  static constexpr int SMEM = Q_BYTES + 2 * 2 * KV_BYTES + 1024 + 128;
+  static constexpr int SMEM = Q_BYTES + 2 * 2 * KV_BYTES + 1024 + 256;
 };
 
 // TRACE: CTA (0,0,0) records clock64 at the hand-off points: trace[(role * 64 + j) * 8 + k], role 0/1 = softmax
@@ -316,11 +322,11 @@ struct ACfg2 {
 template <int HD, bool DROP, bool TRACE = false>
 __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid_constant__ AttnTcParams pp) {
   using C = ACfg2<HD>;
+  constexpr int BKV = C::BKV, HB = C::HB;
   const bool tr_on = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0;
   auto probe = [&](int role, int j, int k) {
     if (TRACE && tr_on && j < 64) pp.trace[(role * 64 + j) * 8 + k] = clock64();
   };
-  constexpr int BKV = C::BKV;
   const int bz = blockIdx.x / pp.n_heads;   // (problem, batch); blockIdx.z = query tile: heaviest tiles launch first
   const AttnTcItem& p = pp.it[bz / pp.B];
   extern __shared__ uint8_t smem_raw[];
@@ -331,12 +337,14 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
   uint8_t* sV = sK + 2 * C::KV_BYTES;                   // [2][KV_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * C::KV_BYTES);
   uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;      // [2] per group: MMA -> softmax
-  uint64_t* p_full = bars + 7;      // [2] per group: softmax (128 arrivals) -> MMA
-  uint64_t* o_done = bars + 9;      // [2] per group: MMA -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* k_full = bars + 1;      // [2]
+  uint64_t* v_full = bars + 3;      // [2]
+  uint64_t* k_empty = bars + 5;     // [2]
+  uint64_t* v_empty = bars + 7;     // [2]
+  uint64_t* s_full = bars + 9;      // [group]: MMA -> softmax
+  uint64_t* p_full = bars + 11;     // [group][half]: softmax (128 arrivals) -> MMA
+  uint64_t* o_done = bars + 15;     // [group]: MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int qb = gridDim.z - 1 - blockIdx.z;  // heavy (late) query blocks first, across ALL (batch, head) pairs
@@ -356,12 +364,14 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
     ptx::prefetch_tmap(&p.tv);
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&kv_full[s], 1);
-      ptx::mbar_init(&kv_empty[s], 1);
+      ptx::mbar_init(&k_full[s], 1);
+      ptx::mbar_init(&v_full[s], 1);
+      ptx::mbar_init(&k_empty[s], 1);
+      ptx::mbar_init(&v_empty[s], 1);
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&p_full[s], 128);
       ptx::mbar_init(&o_done[s], 1);
     }
+    for (int s = 0; s < 4; ++s) ptx::mbar_init(&p_full[s], 128);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -385,14 +395,20 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
     __syncwarp();
     for (int j = 0; j < n_tot; ++j) {
       const int s = j & 1;
-      ptx::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+      ptx::mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
       if (ptx::elect_one()) {
-        ptx::mbar_expect_tx(&kv_full[s], 2 * C::KV_BYTES);
+        ptx::mbar_expect_tx(&k_full[s], C::KV_BYTES);
 #pragma unroll
-        for (int a = 0; a < C::ATOMS; ++a) {
-          ptx::tma_load_3d(sK + s * C::KV_BYTES + a * (BKV * 128), &p.tk, &kv_full[s], h * HD + a * 64, j * BKV, b);
-          ptx::tma_load_3d(sV + s * C::KV_BYTES + a * (BKV * 128), &p.tv, &kv_full[s], h * HD + a * 64, j * BKV, b);
-        }
+        for (int a = 0; a < C::ATOMS; ++a)
+          ptx::tma_load_3d(sK + s * C::KV_BYTES + a * (BKV * 128), &p.tk, &k_full[s], h * HD + a * 64, j * BKV, b);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(&v_full[s], C::KV_BYTES);
+#pragma unroll
+        for (int a = 0; a < C::ATOMS; ++a)
+          ptx::tma_load_3d(sV + s * C::KV_BYTES + a * (BKV * 128), &p.tv, &v_full[s], h * HD + a * 64, j * BKV, b);
       }
       __syncwarp();
     }
@@ -412,43 +428,51 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
       }
       ptx::umma_commit(&s_full[g]);
     };
-    auto issue_pv = [&](int g, int s, int j) {   // O_g (+)= P_g V
+    auto issue_pv = [&](int g, int s, int j, int half) {   // O_g (+)= P_g[:, half] V[half, :]
       const uint32_t vb = ptx::smem_u32(sV + s * C::KV_BYTES);
 #pragma unroll
-      for (int k = 0; k < BKV / 16; ++k)
+      for (int k = half * (HB / 16); k < (half + 1) * (HB / 16); ++k)
         ptx::umma_f16_ts(tmem + 256 + g * 128, tmem + g * 128 + k * 8,
                          ptx::umma_smem_desc(vb + k * 2048, BKV * 128, 1024), idesc_o, (j | k) != 0 ? 1u : 0u);
     };
     ptx::mbar_wait(q_full, 0);
-    ptx::mbar_wait(&kv_full[0], 0);
+    ptx::mbar_wait(&k_full[0], 0);
     ptx::tc_fence_after();
     if (ptx::elect_one()) {
       if (n_kv[0] > 0) issue_s(0, 0);
       if (n_kv[1] > 0) issue_s(1, 0);
+      ptx::umma_commit(&k_empty[0]);
     }
     __syncwarp();
     for (int j = 0; j < n_tot; ++j) {
       const int s = j & 1, sn = (j + 1) & 1;
-      const bool more = j + 1 < n_tot;
+      ptx::mbar_wait(&v_full[s], (j >> 1) & 1);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         if (j < n_kv[g]) {
-          ptx::mbar_wait(&p_full[g], j & 1);
-          probe(2, j, g * 3);
-          if (j + 1 < n_kv[g]) ptx::mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
-          probe(2, j, g * 3 + 1);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            issue_pv(g, s, j);
-            if (j + 1 < n_kv[g]) issue_s(g, sn);
-            else ptx::umma_commit(&o_done[g]);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            ptx::mbar_wait(&p_full[g * 2 + half], j & 1);
+            probe(2, j, g * 3 + half);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) issue_pv(g, s, j, half);
+            __syncwarp();
+          }
+          if (j + 1 < n_kv[g]) {
+            ptx::mbar_wait(&k_full[sn], ((j + 1) >> 1) & 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) issue_s(g, sn);
+          } else if (ptx::elect_one()) {
+            ptx::umma_commit(&o_done[g]);
           }
           __syncwarp();
           probe(2, j, g * 3 + 2);
         }
       }
-      (void)more;
-      if (ptx::elect_one()) ptx::umma_commit(&kv_empty[s]);
+      if (ptx::elect_one()) {
+        ptx::umma_commit(&v_empty[s]);
+        if (j + 1 < n_tot) ptx::umma_commit(&k_empty[sn]);
+      }
       __syncwarp();
     }
   } else {
@@ -462,6 +486,7 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
     const uint32_t colS = g * 128, colO = 256 + g * 128;
     const int n_mine = n_kv[g];
     float m_ref = -INFINITY, l_sum = 0.f;
+    const uint32_t never = static_cast<uint32_t>(pp.src_len >> 31);   // 0 at run time (src_len >= 0), opaque to ptxas
     for (int j = 0; j < n_mine; ++j) {
       const int kv0 = j * BKV;
       ptx::mbar_wait(&s_full[g], j & 1);
@@ -474,18 +499,22 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
       for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld_32x32p(tmem + lane_base + colS + c * 32, r + c * 32);
       ptx::tmem_ld_wait();
       if (quarter == 2) probe(g, j, 1);
-      float mx = -INFINITY;   // max of the RAW scores (scale > 0 commutes with max)
       if (need_mask) {
 #pragma unroll
         for (int e = 0; e < BKV; ++e) {
           const int kk = kv0 + e;
           if (kk > q + pp.src_len || kk >= pp.T) r[e] = 0xff800000u;  // -inf
-          mx = fmaxf(mx, __uint_as_float(r[e]));
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < BKV; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
       }
+      // max of the RAW scores (scale > 0 commutes with max): four independent chains
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int e = 0; e < BKV; e += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(r[e + 2 * u]), __uint_as_float(r[e + 2 * u + 1])));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_cand = fmaxf(m_ref, mx * pp.scale_log2);
       const bool grow = (m_cand > m_ref + 8.0f) || (m_ref == -INFINITY && m_cand != -INFINITY);
       if (__any_sync(0xffffffffu, grow)) {
@@ -494,14 +523,15 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
         l_sum *= alpha;
         m_ref = m_cand;
         if (j > 0) {
-#pragma unroll
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld_32x32(tmem + lane_base + colO + c * 32, o);
+          // rare path: 16 columns at a time so that it does not push the score row out of the registers
+#pragma unroll 1
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            ptx::tmem_ld_32x16p(tmem + lane_base + colO + c * 16, o);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-            ptx::tmem_st_32x32(tmem + lane_base + colO + c * 32, o);
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            ptx::tmem_st_32x16p(tmem + lane_base + colO + c * 16, o);
           }
         }
       }
@@ -514,25 +544,52 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
       const unsigned long long drop_row = DROP ? ((static_cast<unsigned long long>(b) * pp.n_heads + h) * pp.T + q) *
                                                      static_cast<unsigned long long>((pp.T + 1) & ~1) + kv0 : 0ull;
 #pragma unroll
-      for (int e = 0; e < BKV; e += 2) {
-        float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), pp.scale_log2, neg_m));
-        float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), pp.scale_log2, neg_m));
-        l0 += p0; l1 += p1;
-        if (DROP) {
-          const uint2 hsh = ptx::drop_hash(pp.drop_seed, p.drop_site, (drop_row + e) >> 1);
-          p0 = hsh.x >= pp.drop_thresh ? p0 * pp.drop_scale : 0.f;
-          p1 = hsh.y >= pp.drop_thresh ? p1 * pp.drop_scale : 0.f;
+      float nm = neg_m;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        // (nm carries a data dependence on the first half's arrival: ptxas would otherwise hoist all 128
+        //  exponentials above the first hand-off)
+        if (half == 1) {
+          // registers: the CTA's 10 warps are allocated as 12, which caps a thread at 168 registers; the second
+          // half of the score row is dropped after the max and re-read here (one more ~60-cycle TMEM load)
+#pragma unroll
+          for (int c = HB / 32; c < BKV / 32; ++c) ptx::tmem_ld_32x32p(tmem + lane_base + colS + c * 32, r + c * 32);
+          ptx::tmem_ld_wait();
+          if (need_mask) {
+#pragma unroll
+            for (int e = HB; e < BKV; ++e) {
+              const int kk = kv0 + e;
+              if (kk > q + pp.src_len || kk >= pp.T) r[e] = 0xff800000u;
+            }
+          }
         }
-        r[e >> 1] = ptx::pack_bf16(p0, p1);
+#pragma unroll
+        for (int e = half * HB; e < (half + 1) * HB; e += 2) {
+          float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), pp.scale_log2, nm));
+          float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), pp.scale_log2, nm));
+          l0 += p0; l1 += p1;
+          if (DROP) {
+            const uint2 hsh = ptx::drop_hash(pp.drop_seed, p.drop_site, (drop_row + e) >> 1);
+            p0 = hsh.x >= pp.drop_thresh ? p0 * pp.drop_scale : 0.f;
+            p1 = hsh.y >= pp.drop_thresh ? p1 * pp.drop_scale : 0.f;
+          }
+          r[e >> 1] = ptx::pack_bf16(p0, p1);
+        }
+        // hand this half of P to the pipe: P.V on it overlaps the exponentials of the other half
+#pragma unroll
+        for (int c = 0; c < HB / 32; ++c)
+          ptx::tmem_st_32x16p(tmem + lane_base + colS + half * (HB / 2) + c * 16, r + half * (HB / 2) + c * 16);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        if (half == 0) {
+          const uint32_t tok = ptx::mbar_arrive_token(&p_full[g * 2]);
+          nm = __uint_as_float(__float_as_uint(nm) ^ (tok & never));
+        } else {
+          ptx::mbar_arrive(&p_full[g * 2 + 1]);
+        }
+        if (quarter == 2) probe(g, j, 3 + half);
       }
       l_sum += l0 + l1;
-      if (quarter == 2) probe(g, j, 3);
-#pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_st_32x16p(tmem + lane_base + colS + c * 16, r + c * 16);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&p_full[g]);
-      if (quarter == 2) probe(g, j, 4);
     }
     if (n_mine > 0) {
       ptx::mbar_wait(&o_done[g], 0);
