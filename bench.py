@@ -187,6 +187,30 @@ def train_step_aux(dev, timed):
     return out
 
 
+def attention_kernel_aux(dev, timed, pk):
+    """BASELINE metric, second half ("attention TFLOP/s vs peak"): the fused causal attention kernels
+    alone at the configs' max_len (T = 2024), cylinder_flow head geometry (8 heads x 128), bf16,
+    causal-useful FLOPs 2*B*nh*T^2*hd forward (c = 1/2), 2.5x that backward."""
+    from sea_b200 import ops
+    B, T, nh, hd = 4, 2024, 8, 128
+    g = torch.Generator(device=dev).manual_seed(9)
+    qkv = torch.randn(B * T, 3 * nh * hd, device=dev, generator=g).bfloat16()
+    q, k, v = qkv[:, : nh * hd], qkv[:, nh * hd: 2 * nh * hd], qkv[:, 2 * nh * hd:]
+    o, lse = ops.attention_fwd(q, k, v, nh, B=B, want_lse=True)
+    do = torch.randn(B * T, nh * hd, device=dev, generator=g).bfloat16()
+    for _ in range(3):
+        ops.attention_fwd(q, k, v, nh, B=B, want_lse=True)
+        ops.attention_bwd(q, k, v, o, do, lse, nh, B=B)
+    ms_f = timed(lambda: ops.attention_fwd(q, k, v, nh, B=B, want_lse=True), 20)
+    ms_b = timed(lambda: ops.attention_bwd(q, k, v, o, do, lse, nh, B=B), 10)
+    fl = 2.0 * B * nh * T * T * hd
+    tf_f, tf_b = fl / (ms_f * 1e-3) / 1e12, 2.5 * fl / (ms_b * 1e-3) / 1e12
+    return {"workload": f"causal self-attention B={B} T={T} heads={nh} head_dim={hd}, bf16 (tcgen05 kernels alone)",
+            "fwd_ms": ms_f, "fwd_tflops": tf_f, "fwd_frac_of_sustained_peak": tf_f / pk["sustained"],
+            "bwd_ms": ms_b, "bwd_tflops": tf_b, "bwd_frac_of_sustained_peak": tf_b / pk["sustained"],
+            "flops": "causal-useful (half of the dense count)"}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path.  /root/reference is Python
     and does not travel to the GPU box, so this times oracle/sea_oracle.py (the restatement pinned
@@ -317,6 +341,7 @@ def main():
 
     # ---- roofline leg: one more rollout with per-launch CUDA events on the launch stream ----
     pk = peaks()
+    attn_aux = attention_kernel_aux(dev, timed, pk)
     with profile() as prof:
         rollout(model, x0, ib, R)
         torch.cuda.synchronize()
@@ -368,6 +393,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "train_step": train_aux,
+        "attention_kernel": attn_aux,
         "cached_rollout": {"value": world * B * R / (ms_cached / 1e3), "unit": UNIT, "ms_per_step": ms_cached,
                            "rel_l2_vs_prefix_loop": cached_rel, "rel_l2_vs_prefix_loop_first_10_steps": cached_rel10,
                            "note": "opt-in KV-cached engine (sea_temporal_step): O(1) work per step instead of "

@@ -566,6 +566,17 @@ int sea_temporal_backward(const sea_temporal_desc* d, const void* cache, const f
                           void* workspace, size_t workspace_bytes, sea_stream_t stream);
 /* Number of kernels the last forward / backward call on this thread launched. */
 int sea_last_launch_count(void);
+/* Data-parallel overlap hook (the gradient all-reduce overlaps the tail of the backward).  The NEXT
+ * sea_temporal_backward of this process records `cuda_event` (a cudaEvent_t) on its stream right after the
+ * last stream-MLP weight gradient (mlp.{i}.layers.{0,3}.weight of every layer: 2/3 of the gradient bytes of
+ * multiphase_flow) is final, then forgets it.  `_pending` = 1 while an armed event has not been consumed. */
+void sea_temporal_backward_milestone(void* cuda_event);
+int sea_temporal_backward_milestone_pending(void);
+/* cudaEvent_t plumbing for hosts without a runtime binding: create (timing disabled) / destroy / make `stream`
+ * wait for the event.  Return 0 or a cudaError_t. */
+int sea_event_create(void** out_event);
+int sea_event_destroy(void* cuda_event);
+int sea_stream_wait_event(sea_stream_t stream, void* cuda_event);
 
 /* Optional per-launch timing (CUDA events on the launching stream) for roofline accounting.
  * Between begin and end every executor launch is bracketed by an event pair; end synchronises on

@@ -25,6 +25,7 @@ torch.cuda.set_device(dev)
 E, nh, scale, V, T, steps = 128, 2, 2, 2, 12, 30
 Bg = 2 * world                                            # global batch, 2 trajectories per rank
 ln = os.environ.get("SEA_LN", "adaln")
+OVERLAP = os.environ.get("SEA_DP_OVERLAP", "1") == "1"   # force the overlapped exchange (auto would skip it at this size)
 sd = gr.fill_state(gr.temporal_shapes(embed_dim=E, n_heads=nh, scale_ratio=scale, num_variables=V, ln_type=ln), 11)
 x, ib, tgt = gr.temporal_inputs(Bg, T, V, E, 11)
 m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln)
@@ -34,7 +35,7 @@ opt = torch.optim.AdamW(m.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, w
 xs, ibs, ts = (parallel.shard_trajectories(t, rank, world).to(dev) for t in (x, ib, tgt))
 losses = []
 for _ in range(steps):
-    loss = parallel.train_step(m, opt, F.mse_loss, xs, ts, ibs)
+    loss = parallel.train_step(m, opt, F.mse_loss, xs, ts, ibs, overlap=OVERLAP)
     lt = loss.detach().clone()
     if world > 1:
         dist.all_reduce(lt)

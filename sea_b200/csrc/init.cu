@@ -74,6 +74,23 @@ extern "C" int sea_version(void) { return 100; }
 extern "C" void sea_set_pdl(int on) { sea::g_pdl = on != 0; }
 extern "C" int sea_num_sms(void) { return sea::g_sms; }
 
+// Event plumbing for callers without a CUDA runtime binding (the Python host side): lets the data-parallel
+// gradient exchange on a second stream wait for a point INSIDE sea_temporal_backward.
+extern "C" int sea_event_create(void** out) {
+  if (!out) return SEA_ERR_INVALID;
+  cudaEvent_t ev = nullptr;
+  const cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  *out = ev;
+  return static_cast<int>(e);
+}
+extern "C" int sea_event_destroy(void* ev) {
+  return ev ? static_cast<int>(cudaEventDestroy(static_cast<cudaEvent_t>(ev))) : SEA_OK;
+}
+extern "C" int sea_stream_wait_event(sea_stream_t stream, void* ev) {
+  if (!ev) return SEA_ERR_INVALID;
+  return static_cast<int>(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(ev), 0));
+}
+
 extern "C" const char* sea_strerror(int code) {
   switch (code) {
     case SEA_OK: return "ok";

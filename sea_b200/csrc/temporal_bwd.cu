@@ -12,6 +12,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <vector>
 
 #include "../../include/sea_b200.h"
@@ -260,6 +262,11 @@ void layout_bwd_tape(const sea_temporal_desc* d, int B, int T, Arena& ar, BwdTap
 
 using namespace sea;
 
+// process-wide, not thread-local: autograd runs the backward on its own device thread
+namespace sea { std::atomic<void*> g_bwd_milestone{nullptr}; }
+extern "C" void sea_temporal_backward_milestone(void* ev) { sea::g_bwd_milestone.store(ev); }
+extern "C" int sea_temporal_backward_milestone_pending(void) { return sea::g_bwd_milestone.load() != nullptr; }
+
 extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cache, const float* x,
                                      const float* ib, const float* dy, float* dx, int B, int T,
                                      void* workspace, size_t workspace_bytes, sea_stream_t stream) {
@@ -368,6 +375,11 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       q.dgrad = true; q.da_f32 = bt.s[i].dn2; q.ld_da = E;
     }
     SEA_TRY(linear_bwd(b, V, L));
+    if (l == 0) {
+      // every layer's stream-MLP weight gradient (the bulk of the gradient bytes) is final from here on:
+      // the data-parallel exchange of that bucket may start while the rest of the backward runs
+      if (void* ev = g_bwd_milestone.exchange(nullptr)) SEA_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev), b.c.s));
+    }
     // Norm_{i,2} (+ skip) -> gradient at x2 = x_post + TIPI
     {
       sea_norm_bwd_args na[SEA_MAX_STREAMS];

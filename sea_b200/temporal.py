@@ -230,6 +230,21 @@ class TemporalEngine:
                     kind=kind, src_len=int(getattr(b0, "src_len", 0)), max_len=int(att.max_len))
 
     def _live_params(self):
+        """(name, parameter) pairs on the path.  The walk over named_parameters() costs ~0.3 ms of pure Python
+        for the configs' models and ran several times per train step, so the list is cached: Parameter OBJECTS
+        are stable across .to() / load_state_dict() / optimizer steps (their storage and version are re-read
+        on every call); call refresh_parameter_list() after replacing a Parameter object on the module."""
+        cached = getattr(self, "_live_cache", None)
+        if cached is not None:
+            return cached
+        self._live_cache = self._walk_live_params()
+        return self._live_cache
+
+    def refresh_parameter_list(self) -> None:
+        self._live_cache = None
+        self._desc = None
+
+    def _walk_live_params(self):
         dead = ("ln.cross.", ".residual_projection.")
         out = []
         for name, p in self.module.named_parameters():
@@ -256,7 +271,9 @@ class TemporalEngine:
         live = [(n, p) for n, p in self._live_params() if p.requires_grad]
         # small / atomically accumulated gradients first, GEMM weight gradients last: after zero_grad only
         # the first region has to be zero-filled (the weight-gradient GEMMs overwrite, desc.grads_fresh)
-        live.sort(key=lambda np_: self._is_gemm_weight(*np_))
+        # ... and among those the stream-MLP weights at the very end: their gradients are final first in the
+        # backward (sea_temporal_backward_milestone), so the DP exchange of that tail bucket overlaps the rest
+        live.sort(key=lambda np_: (self._is_gemm_weight(*np_), self._is_mlp_weight(np_[0])))
         total = sum((p.numel() + 63) // 64 * 64 for _, p in live)
         dev = live[0][1].device
         if getattr(self, "_flat_grad", None) is None or self._flat_grad.numel() != total or self._flat_grad.device != dev:
@@ -264,7 +281,10 @@ class TemporalEngine:
             self._grad_views = {}
             off = 0
             self._small_elems = 0
+            self._mlp_start = total
             for n, p in live:
+                if self._is_mlp_weight(n):
+                    self._mlp_start = min(self._mlp_start, off)
                 self._grad_views[n] = self._flat_grad[off:off + p.numel()].view_as(p)
                 off += (p.numel() + 63) // 64 * 64
                 if not self._is_gemm_weight(n, p):
@@ -272,9 +292,19 @@ class TemporalEngine:
             self._desc = None  # pointers changed
         return live
 
+    @staticmethod
+    def _is_mlp_weight(name: str) -> bool:
+        """blocks.{l}.mlp.{i}.layers.{0,3}.weight (models/temporal.py:80, base_blocks.py:22-26)."""
+        return ".mlp." in name and name.endswith(("layers.0.weight", "layers.3.weight"))
+
     def flat_grad(self) -> torch.Tensor:
         self._ensure_flat_grads()
         return self._flat_grad
+
+    def mlp_grad_offset(self) -> int:
+        """First element of the stream-MLP weight-gradient bucket at the tail of flat_grad()."""
+        self._ensure_flat_grads()
+        return self._mlp_start
 
     def anchor_param(self):
         for _, p in self._live_params():
