@@ -47,6 +47,7 @@ class AdamW(torch.optim.Optimizer):
         self.engine = engine
         self.grad_scale = float(grad_scale)
         self._tables = {}
+        self._steps = {}     # group index -> [ids of its stepped params, host step count, shared step tensor]
 
     def _table(self, gi, plist):
         """Device chunk table of one param group, rebuilt only when a pointer changes."""
@@ -81,6 +82,11 @@ class AdamW(torch.optim.Optimizer):
         self._tables[gi] = (key, ckey, tab, fused_copies)
         return tab, fused_copies
 
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._steps = {}
+        self._tables = {}
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -102,10 +108,22 @@ class AdamW(torch.optim.Optimizer):
                     st["step"] = torch.tensor(0.0, dtype=torch.float32)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            steps = {float(self.state[p]["step"]) for p in plist}
-            if len(steps) != 1:
-                raise RuntimeError("sea_b200.optim.AdamW: parameters of one group must share the step count")
-            t = steps.pop() + 1.0
+            # one step count per group: every parameter's `step` entry (torch's state layout) is the SAME
+            # tensor object, so a step costs one tiny update instead of one per parameter
+            key = tuple(id(p) for p in plist)
+            track = self._steps.get(gi)
+            if track is None or track[0] != key or any(self.state[p]["step"] is not track[2] for p in plist[:1]):
+                steps = {float(self.state[p]["step"]) for p in plist}
+                if len(steps) != 1:
+                    raise RuntimeError("sea_b200.optim.AdamW: parameters of one group must share the step count")
+                shared = torch.tensor(steps.pop(), dtype=torch.float32)
+                for p in plist:
+                    self.state[p]["step"] = shared
+                track = [key, float(shared), shared]
+                self._steps[gi] = track
+            track[1] += 1.0
+            track[2] += 1.0
+            t = track[1]
             b1, b2 = group["betas"]
             hp = AdamWHyper(group["lr"], b1, b2, group["eps"], group["weight_decay"],
                             1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t), self.grad_scale, 1.0 - b1, 1.0 - b2)
@@ -114,8 +132,6 @@ class AdamW(torch.optim.Optimizer):
                 check(lib.sea_adamw_step(C.c_void_p(tab.data_ptr()), tab.numel() // _CHUNK_DT.itemsize,
                                          C.byref(hp), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                       "adamw_step")
-            for p in plist:
-                self.state[p]["step"] += 1.0
             wrote_copies |= fused
         if self.engine is not None:
             self.engine.after_optimizer_step(straight_copies_fresh=wrote_copies)
