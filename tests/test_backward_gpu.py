@@ -253,3 +253,43 @@ def test_gradient_accumulation_and_fresh_overwrite(cuda):
         scale = g1[n].abs().max().item() + 1e-12
         assert (g2[n] - 2 * g1[n]).abs().max().item() <= 2e-3 * scale + 1e-7, n      # atomics reorder sums
         assert (g3[n] - g1[n]).abs().max().item() <= 2e-3 * scale + 1e-7, n
+
+
+@pytest.mark.parametrize("V,L,ln", [(4, 2, "adaln"), (3, 2, "ln")])
+def test_more_streams_and_layers_match_oracle(cuda, V, L, ln):
+    """BASELINE configs[4] sweeps the stream count (V = 2, 3, 4); the reference also allows several blocks.
+    Forward, loss and every live parameter gradient of a V-stream, L-layer model against the fp32 oracle on
+    fresh seeded inputs (tensor-core path: head dim 64, cross head dim 32 falls to the CUDA-core attention)."""
+    from sea_b200.temporal import TemporalModel
+    E, nh, scale, B, T = 128, 2, 2, 2, 21
+    shapes = gr.temporal_shapes(embed_dim=E, n_heads=nh, scale_ratio=scale, num_variables=V, num_layers=L, ln_type=ln)
+    sd = gr.fill_state(shapes, 23)
+    for v in sd.values():
+        v.requires_grad_(True)
+    x, ib, tgt = gr.temporal_inputs(B, T, V, E, 23)
+    m = TemporalModel(L, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln)
+    missing = m.load_state_dict({k: v.detach() for k, v in sd.items()}, strict=False)
+    assert not missing.unexpected_keys
+    m = m.to(cuda).train()
+    xr = x.clone().requires_grad_(True)
+    loss_ref = F.mse_loss(so.temporal_forward(xr, ib, sd, num_layers=L, n_heads=nh, ln_type=ln), tgt)
+    loss_ref.backward()
+    xg = x.to(cuda).requires_grad_(True)
+    y = m(xg, ib.to(cuda))
+    loss = F.mse_loss(y, tgt.to(cuda))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    params = dict(m.named_parameters())
+    checked = 0
+    for name, ref_p in sd.items():
+        ref = ref_p.grad
+        if ref is None or ref.double().norm().item() < 2e-5:
+            continue
+        got = params[name].grad
+        assert got is not None, name
+        cos = F.cosine_similarity(got.cpu().flatten().double(), ref.flatten().double(), dim=0).item()
+        assert cos > 0.99 and _rel(got.cpu(), ref) < 0.12, (name, _rel(got.cpu(), ref), cos)
+        checked += 1
+    assert checked > 40 * L
+    assert _rel(xg.grad.cpu(), xr.grad) < 6e-2
