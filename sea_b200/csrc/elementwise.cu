@@ -17,7 +17,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }   // MUFU.RCP + FMUL (2 ulp); IEEE "/" is ~10 instructions + a guarded slow path
 
 // ------------------------------------------------------------------ AdaLN cond hidden layer
 // h[m, j] = SiLU(sum_c w1[j, c] * ib[m, c] + b1[j])     models/base_blocks.py:337-339, 344

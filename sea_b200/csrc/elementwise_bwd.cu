@@ -151,10 +151,17 @@ struct LnGeluBwdItem {
 };
 struct LnGeluBwdGroup { LnGeluBwdItem it[SEA_MAX_STREAMS]; };
 
+// 512 threads per CTA, one row at a time, thread t owns columns (c*512 + t)*8 .. +8 of every row (c < 4: H <= 16384).
+// The next row's h / dg are already in flight (registers) while the current row is being processed, x-hat is
+// recomputed from the raw bf16 h in the second pass instead of being kept, and the per-CTA dweight / dbias
+// partial sums live in shared memory (each thread is the only writer of its columns).
+constexpr int kLgbThreads = 512;
+constexpr int kLgbChunks = 4;
+
 template <int kDummy>
-__global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const __grid_constant__ LnGeluBwdGroup grp, long long lddg,
-                                                          long long ldh, long long lddh, int M, int H,
-                                                          int rows_per_cta) {
+__global__ void __launch_bounds__(kLgbThreads, 1) ln_gelu_bwd_kernel(const __grid_constant__ LnGeluBwdGroup grp, long long lddg,
+                                                                      long long ldh, long long lddh, int M, int H,
+                                                                      int rows_per_cta) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
   const LnGeluBwdItem& item = grp.it[blockIdx.y];
@@ -166,36 +173,53 @@ __global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const __grid_constant_
   __nv_bfloat16* __restrict__ dh = item.dh;
   float* __restrict__ dweight = item.dweight;
   float* __restrict__ dbias = item.dbias;
-  constexpr int kMaxChunks = 8;
   extern __shared__ float acc[];  // [2][H]
-  __shared__ float red[2][8];
+  __shared__ float red[2][kLgbThreads / 32];
   __shared__ float bc[2];
   const int tid = threadIdx.x;
   float* aw = acc;
   float* ab = acc + H;
-  for (int i = tid; i < 2 * H; i += 256) acc[i] = 0.f;
+  for (int i = tid; i < 2 * H; i += kLgbThreads) acc[i] = 0.f;
   __syncthreads();
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(M, row_begin + rows_per_cta);
   const float inv_h = 1.0f / H;
-  for (int m = row_begin; m < row_end; ++m) {
-    const float mean = stats[2 * m], rstd = stats[2 * m + 1];
-    float hh[kMaxChunks][8], dhh[kMaxChunks][8];
-    float s1 = 0.f, s2 = 0.f;
+  uint4 nh[kLgbChunks], ng[kLgbChunks];   // next row, in flight
+  float2 nst = make_float2(0.f, 1.f);
+  auto fetch = [&](int m) {
+    nst = *reinterpret_cast<const float2*>(stats + 2 * m);
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      const int col = (c * 256 + tid) * 8;
+    for (int c = 0; c < kLgbChunks; ++c) {
+      const int col = (c * kLgbThreads + tid) * 8;
       if (col < H) {
-        const uint4 hr = *reinterpret_cast<const uint4*>(h + static_cast<long long>(m) * ldh + col);
-        const uint4 gr = *reinterpret_cast<const uint4*>(dg + static_cast<long long>(m) * lddg + col);
-        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&hr);
-        const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&gr);
+        nh[c] = *reinterpret_cast<const uint4*>(h + static_cast<long long>(m) * ldh + col);
+        ng[c] = *reinterpret_cast<const uint4*>(dg + static_cast<long long>(m) * lddg + col);
+      }
+    }
+  };
+  if (row_begin < row_end) fetch(row_begin);
+  for (int m = row_begin; m < row_end; ++m) {
+    const float mean = nst.x, rstd = nst.y;
+    uint4 ch[kLgbChunks];
+    float dhh[kLgbChunks][8];
+    float s1 = 0.f, s2 = 0.f;
+    uint4 cg[kLgbChunks];
+#pragma unroll
+    for (int c = 0; c < kLgbChunks; ++c) { ch[c] = nh[c]; cg[c] = ng[c]; }
+    if (m + 1 < row_end) fetch(m + 1);
+#pragma unroll
+    for (int c = 0; c < kLgbChunks; ++c) {
+      const int col = (c * kLgbThreads + tid) * 8;
+      if (col < H) {
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&ch[c]);
+        const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&cg[c]);
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
         const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col + 4));
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
         const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float daw[8], dab[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 hv = __bfloat1622float2(hp[q]);
@@ -207,14 +231,26 @@ __global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const __grid_constant_
             const float xhat = (hv2[e] - mean) * rstd;
             const float u = xhat * ww[k] + bb[k];
             const float dgu = gv2[e] * ptx::gelu_erf_grad_fast(u);
-            aw[col + k] += dgu * xhat;   // this thread is the only writer of these columns
-            ab[col + k] += dgu;
+            daw[k] = dgu * xhat;
+            dab[k] = dgu;
             const float dxh = dgu * ww[k];
-            hh[c][k] = xhat;
             dhh[c][k] = dxh;
             s1 += dxh;
             s2 += dxh * xhat;
           }
+        }
+        // partial sums: this thread is the only writer of its 8 columns.  Layout [plane][c*512 + tid] of float4
+        // (plane = low / high four columns): consecutive threads touch consecutive 16-byte words, so the
+        // read-modify-write is conflict-free (column-major [H] floats were an 8-way bank conflict and the
+        // whole kernel's bottleneck)
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          float4* pw = reinterpret_cast<float4*>(aw) + pl * (H / 8) + c * kLgbThreads + tid;
+          float4* pb = reinterpret_cast<float4*>(ab) + pl * (H / 8) + c * kLgbThreads + tid;
+          float4 vw = *pw, vb = *pb;
+          vw.x += daw[4 * pl]; vw.y += daw[4 * pl + 1]; vw.z += daw[4 * pl + 2]; vw.w += daw[4 * pl + 3];
+          vb.x += dab[4 * pl]; vb.y += dab[4 * pl + 1]; vb.z += dab[4 * pl + 2]; vb.w += dab[4 * pl + 3];
+          *pw = vw; *pb = vb;
         }
       }
     }
@@ -223,37 +259,56 @@ __global__ void __launch_bounds__(256) ln_gelu_bwd_kernel(const __grid_constant_
     if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = s2; }
     __syncthreads();
     if (tid < 32) {
-      float t1 = tid < 8 ? red[0][tid] : 0.f, t2 = tid < 8 ? red[1][tid] : 0.f;
+      float t1 = tid < kLgbThreads / 32 ? red[0][tid] : 0.f, t2 = tid < kLgbThreads / 32 ? red[1][tid] : 0.f;
       t1 = warp_sum(t1); t2 = warp_sum(t2);
       if (tid == 0) { bc[0] = t1 * inv_h; bc[1] = t2 * inv_h; }
     }
     __syncthreads();
     const float c1 = bc[0], c2 = bc[1];
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      const int col = (c * 256 + tid) * 8;
+    for (int c = 0; c < kLgbChunks; ++c) {
+      const int col = (c * kLgbThreads + tid) * 8;
       if (col < H) {
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&ch[c]);
         float o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = rstd * (dhh[c][k] - c1 - hh[c][k] * c2);
+        for (int q = 0; q < 4; ++q) {
+          const float2 hv = __bfloat1622float2(hp[q]);
+          o[2 * q] = rstd * (dhh[c][2 * q] - c1 - (hv.x - mean) * rstd * c2);
+          o[2 * q + 1] = rstd * (dhh[c][2 * q + 1] - c1 - (hv.y - mean) * rstd * c2);
+        }
         uint4 pk;
         pk.x = ptx::pack_bf16(o[0], o[1]); pk.y = ptx::pack_bf16(o[2], o[3]);
         pk.z = ptx::pack_bf16(o[4], o[5]); pk.w = ptx::pack_bf16(o[6], o[7]);
         *reinterpret_cast<uint4*>(dh + static_cast<long long>(m) * lddh + col) = pk;
       }
     }
+    // red[] / bc[] are rewritten only after the next row's first barrier has been passed by every thread
+    // that read them here; one barrier closes the hazard on bc[] (written by thread 0 after barrier 1)
     __syncthreads();
   }
-  __syncthreads();
-  if (((reinterpret_cast<uintptr_t>(dweight) | reinterpret_cast<uintptr_t>(dbias)) & 15) == 0) {
-    for (int i = tid * 4; i < H; i += 1024) {   // H % 8 == 0
-      ptx::red_add_v4(dweight + i, aw[i], aw[i + 1], aw[i + 2], aw[i + 3]);
-      ptx::red_add_v4(dbias + i, ab[i], ab[i + 1], ab[i + 2], ab[i + 3]);
-    }
-  } else {
-    for (int i = tid; i < H; i += 256) {
-      atomicAdd(dweight + i, aw[i]);
-      atomicAdd(dbias + i, ab[i]);
+  // every thread flushes the words it accumulated itself (no barrier needed): word (plane, c, tid) holds
+  // columns (c*512 + tid)*8 + plane*4 .. +4
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(dweight) | reinterpret_cast<uintptr_t>(dbias)) & 15) == 0;
+#pragma unroll
+  for (int c = 0; c < kLgbChunks; ++c) {
+    const int col = (c * kLgbThreads + tid) * 8;
+    if (col < H) {
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const float4 vw = reinterpret_cast<const float4*>(aw)[pl * (H / 8) + c * kLgbThreads + tid];
+        const float4 vb = reinterpret_cast<const float4*>(ab)[pl * (H / 8) + c * kLgbThreads + tid];
+        const int i = col + 4 * pl;
+        if (vec_ok) {
+          ptx::red_add_v4(dweight + i, vw.x, vw.y, vw.z, vw.w);
+          ptx::red_add_v4(dbias + i, vb.x, vb.y, vb.z, vb.w);
+        } else {
+          atomicAdd(dweight + i, vw.x); atomicAdd(dweight + i + 1, vw.y);
+          atomicAdd(dweight + i + 2, vw.z); atomicAdd(dweight + i + 3, vw.w);
+          atomicAdd(dbias + i, vb.x); atomicAdd(dbias + i + 1, vb.y);
+          atomicAdd(dbias + i + 2, vb.z); atomicAdd(dbias + i + 3, vb.w);
+        }
+      }
     }
   }
 }
@@ -277,7 +332,7 @@ __global__ void __launch_bounds__(256) adaln_hidden_bwd_kernel(const float* __re
   for (int m = r0; m < r1; ++m) {
     float pre = bj;
     for (int c = 0; c < ib_num && c < 4; ++c) pre = fmaf(wj[c], ib[static_cast<long long>(m) * ib_num + c], pre);
-    const float sig = 1.0f / (1.0f + __expf(-pre));
+    const float sig = __fdividef(1.0f, 1.0f + __expf(-pre));
     const float dsilu = sig * (1.0f + pre * (1.0f - sig));
     const float dp = dh[static_cast<long long>(m) * lddh + j] * dsilu;
     ab += dp;
@@ -460,7 +515,7 @@ extern "C" int sea_ln_gelu_bwd_group(int n, const sea_ln_gelu_bwd_args* a, sea_s
     SEA_CUDA_OK(cudaFuncSetAttribute(ln_gelu_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
     attr_set[dev] = true;
   }
-  SEA_LAUNCH((ln_gelu_bwd_kernel<0>), grid, 256, smem, reinterpret_cast<cudaStream_t>(stream), g, a->lddg, a->ldh,
+  SEA_LAUNCH((ln_gelu_bwd_kernel<0>), grid, kLgbThreads, smem, reinterpret_cast<cudaStream_t>(stream), g, a->lddg, a->ldh,
              a->lddh, a->M, a->H, rows);
   return static_cast<int>(cudaGetLastError());
 }

@@ -382,7 +382,8 @@ __device__ __forceinline__ float drop_mult(unsigned long long seed, uint32_t sit
 // exp(-x^2/2) is shared between the erf tail and the density term: 1 rcp + 1 ex2 + ~10 FMA.
 __device__ __forceinline__ float gelu_erf_grad_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;   // MUFU.RCP (1 ulp): the IEEE reciprocal costs a guarded slow-path call per element
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
