@@ -102,6 +102,8 @@ struct NormDev {
   int cond_folded;                 // cond rows already hold gamma | beta (sea_adaln_fold)
   unsigned long long drop_seed; uint32_t drop_thresh, drop_site; float drop_scale;   // TIPI-term dropout (0 = off)
   int x_rows; long long x_bs;      // x_rows > 0: row m of x lives at x + (m / x_rows) * x_bs + (m % x_rows) * ldx
+  int rows_per_cta;                // generic kernel: rows per CTA (multiple of 8; 8 rows in flight, one per warp)
+  int tipi_stage;                  // generic kernel: W3^T | b3 of the TIPI layer staged in shared memory
 };
 
 constexpr int kNormMaxChunks = 16;  // 16 chunks x 32 lanes x 4 floats = 2048
@@ -110,13 +112,23 @@ constexpr int kNormMaxChunks = 16;  // 16 chunks x 32 lanes x 4 floats = 2048
 struct NormGroup { NormDev it[SEA_MAX_STREAMS]; };
 
 template <int CH, bool ADALN>
-__global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const __grid_constant__ NormGroup grp) {
+__global__ void __launch_bounds__(256, (CH <= 8) ? 3 : 2) norm_fwd_kernel(const __grid_constant__ NormGroup grp) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
   const NormDev& a = grp.it[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (m >= a.M) return;
+  // Per-token TIPI term (training / eager forward): out[col] = b3[col] + sum_k W3[col][k] g[m][k].  W3 is [E][8]
+  // row-major, so reading it per column is a 32-sector access per load; the CTA stages W3^T (row pitch d + 4:
+  // conflict-free transposing stores, 16-byte aligned rows) and b3 once and serves its rows from shared memory.
+  extern __shared__ __align__(16) float tsm[];
+  const int ldt = a.d + 4;
+  if (a.tipi_stage) {
+    for (int i = threadIdx.x; i < a.d * 8; i += 256) tsm[(i & 7) * ldt + (i >> 3)] = __ldg(a.tipi_w + i);
+    for (int i = threadIdx.x; i < a.d; i += 256) tsm[8 * ldt + i] = __ldg(a.tipi_b + i);
+    __syncthreads();
+  }
+  const int row_end = min(a.M, (static_cast<int>(blockIdx.x) + 1) * a.rows_per_cta);
+  for (int m = blockIdx.x * a.rows_per_cta + warp; m < row_end; m += 8) {
   const float* xr = a.x_rows > 0 ? a.x + static_cast<long long>(m / a.x_rows) * a.x_bs + static_cast<long long>(m % a.x_rows) * a.ldx
                                  : a.x + static_cast<long long>(m) * a.ldx;
   const float* cr = ADALN ? a.cond + static_cast<long long>(m / a.cond_div) * a.ldc : nullptr;
@@ -149,23 +161,32 @@ __global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const 
       const int col = c * 128 + lane * 4;
       if (col < a.d) {
         float add[4];
+        if (a.tipi_stage) {
+          // same operation order as tipi_rows_kernel (bias first, one fma per hidden unit): the per-token and the
+          // per-trajectory TIPI paths give bit-identical rows
+          float4 acc4 = *reinterpret_cast<const float4*>(tsm + 8 * ldt + col);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float s = a.tipi_b[col + e];
-          if (a.tipi_hid == 8) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.tipi_w + (col + e) * 8));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.tipi_w + (col + e) * 8 + 4));
-            s += w0.x * gk[0] + w0.y * gk[1] + w0.z * gk[2] + w0.w * gk[3] + w1.x * gk[4] +
-                 w1.y * gk[5] + w1.z * gk[6] + w1.w * gk[7];
-          } else {
+          for (int k = 0; k < 8; ++k) {
+            const float4 w = *reinterpret_cast<const float4*>(tsm + k * ldt + col);
+            acc4.x = fmaf(w.x, gk[k], acc4.x); acc4.y = fmaf(w.y, gk[k], acc4.y);
+            acc4.z = fmaf(w.z, gk[k], acc4.z); acc4.w = fmaf(w.w, gk[k], acc4.w);
+          }
+          add[0] = acc4.x; add[1] = acc4.y; add[2] = acc4.z; add[3] = acc4.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float s = a.tipi_b[col + e];
             for (int k = 0; k < a.tipi_hid; ++k)
               s = fmaf(a.tipi_w[(col + e) * a.tipi_hid + k],
                        a.tipi_g[static_cast<long long>(m) * a.tipi_hid + k], s);
+            add[e] = s;
           }
-          if (a.drop_thresh != 0u)   // the ib-MLP's own nn.Dropout (models/base_blocks.py:47)
-            s *= ptx::drop_mult(a.drop_seed, a.drop_site, static_cast<unsigned long long>(m) * a.d + col + e,
-                                a.drop_thresh, a.drop_scale);
-          add[e] = s;
+        }
+        if (a.drop_thresh != 0u) {   // the ib-MLP's own nn.Dropout (models/base_blocks.py:47)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            add[e] *= ptx::drop_mult(a.drop_seed, a.drop_site, static_cast<unsigned long long>(m) * a.d + col + e,
+                                     a.drop_thresh, a.drop_scale);
         }
         v[c].x += add[0]; v[c].y += add[1]; v[c].z += add[2]; v[c].w += add[3];
         *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(m) * a.ldxo + col) = v[c];
@@ -217,6 +238,7 @@ __global__ void __launch_bounds__(256, (CH <= 8) ? 4 : 2) norm_fwd_kernel(const 
         *reinterpret_cast<uint2*>(a.y_bf16 + static_cast<long long>(m) * a.ldy_bf16 + col) = o;
       }
     }
+  }
   }
 }
 
@@ -853,8 +875,26 @@ static int launch_norm(const NormGroup& g, int n, cudaStream_t s) {
     SEA_LAUNCH((norm_fwd_prefetch_kernel<CH, false>), grid, rows_per_cta * 32, 0, s, g);
     return static_cast<int>(cudaGetLastError());
   }
-  if (d.kind == SEA_NORM_ADALN) SEA_LAUNCH((norm_fwd_kernel<CH, true>), grid, rows_per_cta * 32, 0, s, g);
-  else SEA_LAUNCH((norm_fwd_kernel<CH, false>), grid, rows_per_cta * 32, 0, s, g);
+  // generic kernel; with the per-token TIPI term the CTA stages W3^T | b3 (9 x (d + 4) floats) and, once there
+  // is more than a wave of 8-row CTAs, takes more rows so that the staging is amortised
+  NormGroup gg = g;
+  bool stage = true;
+  for (int i = 0; i < n; ++i) stage = stage && g.it[i].tipi_g != nullptr && g.it[i].tipi_hid == 8;
+  int rpc = rows_per_cta;
+  if (stage && d.M > 8 * 2 * 148) rpc = ((d.M + 2 * 148 - 1) / (2 * 148) + 7) / 8 * 8;
+  for (int i = 0; i < n; ++i) { gg.it[i].rows_per_cta = rpc; gg.it[i].tipi_stage = stage ? 1 : 0; }
+  const size_t smem = stage ? sizeof(float) * 9 * (d.d + 4) : 0;
+  const dim3 ggrid((d.M + rpc - 1) / rpc, n);
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    SEA_CUDA_OK(cudaFuncSetAttribute(norm_fwd_kernel<CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * (CH * 128 + 4) * 4));
+    SEA_CUDA_OK(cudaFuncSetAttribute(norm_fwd_kernel<CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * (CH * 128 + 4) * 4));
+    attr_set[dev] = true;
+  }
+  if (d.kind == SEA_NORM_ADALN) SEA_LAUNCH((norm_fwd_kernel<CH, true>), ggrid, 256, smem, s, gg);
+  else SEA_LAUNCH((norm_fwd_kernel<CH, false>), ggrid, 256, smem, s, gg);
   return static_cast<int>(cudaGetLastError());
 }
 

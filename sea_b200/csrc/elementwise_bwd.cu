@@ -37,24 +37,32 @@ constexpr int kNormMaxChunks = 16;
 
 struct NormBwdGroup { NormBwdDev it[SEA_MAX_STREAMS]; };  // the V field streams share a launch (blockIdx.y)
 
-template <int CH>
-__global__ void __launch_bounds__(256) norm_bwd_kernel(const __grid_constant__ NormBwdGroup grp) {
+// WPR warps share a row (each owns CH chunks of 128 columns): wide rows (d = 2048) would otherwise need 128
+// registers of row state per thread and 128 KB of per-warp partial sums, i.e. 8 warps per SM; with WPR = 2 the
+// kernel fits twice per SM.  The row sums of the WPR warps meet in shared memory behind a 64-thread named barrier.
+template <int CH, int WPR>
+__global__ void __launch_bounds__(256, WPR) norm_bwd_kernel(const __grid_constant__ NormBwdGroup grp) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
   const NormBwdDev& a = grp.it[blockIdx.y];
-  extern __shared__ float red[];  // [8 warps][d] x2 (dweight, dbias partials; each lane owns its columns)
+  constexpr int SLOTS = 8 / WPR;  // rows in flight per CTA
+  extern __shared__ float red[];  // [SLOTS][d] x2 (dweight, dbias partials; each lane owns its columns)
+  __shared__ float xs[2][SLOTS][WPR][2];   // row-sum exchange, double-buffered by row parity
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = warp / WPR, part = warp % WPR;
+  const int col0 = part * CH * 128;
   float* rw = red;
-  float* rb = red + 8 * a.d;
+  float* rb = red + SLOTS * a.d;
   const bool want_param = (a.dweight != nullptr) || (a.dbias != nullptr);
   if (want_param) {
-    for (int i = threadIdx.x; i < 16 * a.d; i += 256) red[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * SLOTS * a.d; i += 256) red[i] = 0.f;
     __syncthreads();
   }
   const int row_begin = blockIdx.x * a.rows_per_cta;
   const int row_end = min(a.M, row_begin + a.rows_per_cta);
   const float inv_d = 1.0f / a.d;
-  for (int m = row_begin + warp; m < row_end; m += 8) {
+  int it = 0;
+  for (int m = row_begin + slot; m < row_end; m += SLOTS, ++it) {
     const float mean = a.stats[2 * m], rstd = a.stats[2 * m + 1];
     const float* xr = a.x + static_cast<long long>(m) * a.ldx;
     const float* dyr = a.dy + static_cast<long long>(m) * a.lddy;
@@ -62,7 +70,7 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const __grid_constant__ N
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      const int col = c * 128 + lane * 4;
+      const int col = col0 + c * 128 + lane * 4;
       if (col < a.d) {
         const float4 xv = *reinterpret_cast<const float4*>(xr + col);
         const float4 dv = *reinterpret_cast<const float4*>(dyr + col);
@@ -82,8 +90,8 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const __grid_constant__ N
         // d gamma_eff = dy * xhat, d beta_eff = dy
         const float4 dgam = make_float4(dv.x * h.x, dv.y * h.y, dv.z * h.z, dv.w * h.w);
         if (want_param) {
-          float4* pw = reinterpret_cast<float4*>(rw + warp * a.d + col);
-          float4* pb = reinterpret_cast<float4*>(rb + warp * a.d + col);
+          float4* pw = reinterpret_cast<float4*>(rw + slot * a.d + col);
+          float4* pb = reinterpret_cast<float4*>(rb + slot * a.d + col);
           float4 t = *pw;
           t.x += dgam.x; t.y += dgam.y; t.z += dgam.z; t.w += dgam.w;
           *pw = t;
@@ -105,10 +113,19 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const __grid_constant__ N
         }
       }
     }
-    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (WPR > 1) {
+      if (lane == 0) { xs[it & 1][slot][part][0] = s1; xs[it & 1][slot][part][1] = s2; }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(32 * WPR) : "memory");
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPR; ++w) { s1 += xs[it & 1][slot][w][0]; s2 += xs[it & 1][slot][w][1]; }
+    }
+    const float c1 = s1 * inv_d, c2 = s2 * inv_d;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      const int col = c * 128 + lane * 4;
+      const int col = col0 + c * 128 + lane * 4;
       if (col < a.d) {
         float4 o;
         o.x = rstd * (g[c].x - c1 - xh[c].x * c2);
@@ -135,7 +152,7 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const __grid_constant__ N
   for (int col = threadIdx.x; col < a.d; col += blockDim.x) {
     float sw = 0.f, sb = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < SLOTS; ++w) {
       sw += rw[w * a.d + col];
       sb += rb[w * a.d + col];
     }
@@ -388,11 +405,23 @@ __global__ void __launch_bounds__(256) tipi_bwd_g_kernel(const TipiBwdDev a) {
     float dg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int s = 0; s < a.n_streams; ++s) {
       const float* dxr = a.dx[s] + static_cast<long long>(m) * a.lddx;
-      for (int n = lane; n < a.E; n += 32) {
-        const float v = dxr[n];
+      if (a.hid == 8) {
+        // W3 row n = 8 consecutive floats: two 16-byte loads instead of eight 4-byte loads with a 32-byte lane stride
+#pragma unroll 4
+        for (int n = lane; n < a.E; n += 32) {
+          const float v = dxr[n];
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w3 + n * 8));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w3 + n * 8 + 4));
+          dg[0] = fmaf(v, w0.x, dg[0]); dg[1] = fmaf(v, w0.y, dg[1]); dg[2] = fmaf(v, w0.z, dg[2]); dg[3] = fmaf(v, w0.w, dg[3]);
+          dg[4] = fmaf(v, w1.x, dg[4]); dg[5] = fmaf(v, w1.y, dg[5]); dg[6] = fmaf(v, w1.z, dg[6]); dg[7] = fmaf(v, w1.w, dg[7]);
+        }
+      } else {
+        for (int n = lane; n < a.E; n += 32) {
+          const float v = dxr[n];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k < a.hid) dg[k] = fmaf(v, __ldg(a.w3 + n * a.hid + k), dg[k]);
+          for (int k = 0; k < 8; ++k)
+            if (k < a.hid) dg[k] = fmaf(v, __ldg(a.w3 + n * a.hid + k), dg[k]);
+        }
       }
     }
 #pragma unroll
@@ -469,20 +498,21 @@ extern "C" int sea_norm_bwd_group(int n, const sea_norm_bwd_args* a, sea_stream_
   }
   const NormBwdDev& d = g.it[0];
   const dim3 grid((a->M + d.rows_per_cta - 1) / d.rows_per_cta, n);
-  const size_t smem = sizeof(float) * 16 * a->d;
+  const bool wide = a->d > 1024;
+  const size_t smem = sizeof(float) * (wide ? 8 : 16) * a->d;
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    SEA_CUDA_OK(cudaFuncSetAttribute(norm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4));
-    SEA_CUDA_OK(cudaFuncSetAttribute(norm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4));
-    SEA_CUDA_OK(cudaFuncSetAttribute(norm_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4));
+    SEA_CUDA_OK(cudaFuncSetAttribute((norm_bwd_kernel<4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4));
+    SEA_CUDA_OK(cudaFuncSetAttribute((norm_bwd_kernel<8, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4));
+    SEA_CUDA_OK(cudaFuncSetAttribute((norm_bwd_kernel<8, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4));
     attr_set[dev] = true;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a->d <= 512) SEA_LAUNCH((norm_bwd_kernel<4>), grid, 256, smem, s, g);
-  else if (a->d <= 1024) SEA_LAUNCH((norm_bwd_kernel<8>), grid, 256, smem, s, g);
-  else SEA_LAUNCH((norm_bwd_kernel<16>), grid, 256, smem, s, g);
+  if (a->d <= 512) SEA_LAUNCH((norm_bwd_kernel<4, 1>), grid, 256, smem, s, g);
+  else if (a->d <= 1024) SEA_LAUNCH((norm_bwd_kernel<8, 1>), grid, 256, smem, s, g);
+  else SEA_LAUNCH((norm_bwd_kernel<8, 2>), grid, 256, smem, s, g);
   return static_cast<int>(cudaGetLastError());
 }
 
