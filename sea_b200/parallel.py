@@ -55,9 +55,10 @@ def allreduce_mean_(flat: torch.Tensor, world: int | None = None) -> torch.Tenso
     return flat
 
 
-# Overlap pays once the overlapped bucket is large: on 2 B200s (scripts/dp_train_bench.py, profiles/r1d_dp.md) the
-# multiphase_flow step (512 MiB bucket) gains, the launch-bound cylinder_flow step (128 MiB bucket) does not.
-OVERLAP_MIN_BYTES = 256 << 20
+# Overlap pays once the overlapped bucket is worth a second collective launch: on 2 B200s (scripts/dp_train_bench.py,
+# profiles/r1d_dp.md) both configs gain (cylinder_flow: 128 MiB bucket, 2.61 -> 2.45 ms; multiphase_flow: 512 MiB,
+# 4.31 -> 3.69 ms); toy models keep the single collective.
+OVERLAP_MIN_BYTES = 64 << 20
 
 _overlap_state = {}
 
