@@ -292,6 +292,10 @@ typedef struct sea_norm_bwd_args {
   float* dcond;         /* AdaLN: [M,2d] gradient wrt cond (scale | shift) */
   int64_t lddcond;
   int32_t dcond_accumulate; /* 1: += into dcond (module applied twice in the exchange) */
+  void* dcond_bf16;     /* AdaLN, optional: [M,2d] bf16 copy of the cond gradient (row pitch 2d), the operand of the
+                           cond_mlp[2] backward GEMMs; with it `dcond` may be NULL.  Not with dcond_accumulate. */
+  float* dweight2;      /* optional second destinations of the column sums (+=): for AdaLN, sum_m dcond[m, :] equals */
+  float* dbias2;        /* (dweight | dbias), so cond_mlp[2].bias.grad = (dweight2 | dbias2) needs no extra pass */
 } sea_norm_bwd_args;
 int sea_norm_bwd(const sea_norm_bwd_args* args, sea_stream_t stream);
 int sea_norm_bwd_group(int n, const sea_norm_bwd_args* host_args, sea_stream_t stream);  /* equal (M, d, kind) */

@@ -92,7 +92,8 @@ class NormBwdArgs(C.Structure):
                 ("dres", C.c_void_p), ("lddres", C.c_int64), ("dx", C.c_void_p), ("lddx", C.c_int64),
                 ("dx_bf16", C.c_void_p), ("lddx_bf16", C.c_int64), ("dweight", C.c_void_p),
                 ("dbias", C.c_void_p), ("dcond", C.c_void_p), ("lddcond", C.c_int64),
-                ("dcond_accumulate", C.c_int32)]
+                ("dcond_accumulate", C.c_int32), ("dcond_bf16", C.c_void_p), ("dweight2", C.c_void_p),
+                ("dbias2", C.c_void_p)]
 
 
 class LnGeluBwdArgs(C.Structure):

@@ -30,6 +30,8 @@ struct NormBwdDev {
   __nv_bfloat16* dx_bf16; long long lddxb;
   float* dweight; float* dbias;
   float* dcond; long long lddc; int dcond_accumulate;
+  __nv_bfloat16* dcond_b16;   // optional bf16 copy of dcond (row pitch 2d)
+  float* dweight2; float* dbias2;
   int M, d, kind, rows_per_cta;
 };
 
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256, WPR) norm_bwd_kernel(const __grid_constan
   const int col0 = part * CH * 128;
   float* rw = red;
   float* rb = red + SLOTS * a.d;
-  const bool want_param = (a.dweight != nullptr) || (a.dbias != nullptr);
+  const bool want_param = (a.dweight != nullptr) || (a.dbias != nullptr) || (a.dweight2 != nullptr) || (a.dbias2 != nullptr);
   if (want_param) {
     for (int i = threadIdx.x; i < 2 * SLOTS * a.d; i += 256) red[i] = 0.f;
     __syncthreads();
@@ -111,6 +113,14 @@ __global__ void __launch_bounds__(256, WPR) norm_bwd_kernel(const __grid_constan
           *reinterpret_cast<float4*>(dc + col) = o1;
           *reinterpret_cast<float4*>(dc + a.d + col) = o2;
         }
+        if (a.dcond_b16) {   // (scale | shift) gradient as the bf16 operand of the cond_mlp[2] backward GEMMs
+          __nv_bfloat16* dcb = a.dcond_b16 + static_cast<long long>(m) * (2LL * a.d);
+          uint2 q1, q2;
+          q1.x = ptx::pack_bf16(dgam.x, dgam.y); q1.y = ptx::pack_bf16(dgam.z, dgam.w);
+          q2.x = ptx::pack_bf16(dv.x, dv.y); q2.y = ptx::pack_bf16(dv.z, dv.w);
+          *reinterpret_cast<uint2*>(dcb + col) = q1;
+          *reinterpret_cast<uint2*>(dcb + a.d + col) = q2;
+        }
       }
     }
     s1 = warp_sum(s1);
@@ -158,6 +168,8 @@ __global__ void __launch_bounds__(256, WPR) norm_bwd_kernel(const __grid_constan
     }
     if (a.dweight) atomicAdd(a.dweight + col, sw);
     if (a.dbias) atomicAdd(a.dbias + col, sb);
+    if (a.dweight2) atomicAdd(a.dweight2 + col, sw);
+    if (a.dbias2) atomicAdd(a.dbias2 + col, sb);
   }
 }
 
@@ -483,6 +495,9 @@ static int fill_norm_bwd(const sea_norm_bwd_args* a, NormBwdDev& d) {
   d.dx_bf16 = static_cast<__nv_bfloat16*>(a->dx_bf16); d.lddxb = a->lddx_bf16;
   d.dweight = a->dweight; d.dbias = a->dbias;
   d.dcond = a->dcond; d.lddc = a->lddcond; d.dcond_accumulate = a->dcond_accumulate;
+  d.dcond_b16 = a->kind == SEA_NORM_ADALN ? static_cast<__nv_bfloat16*>(a->dcond_bf16) : nullptr;
+  if (d.dcond_b16 && a->dcond_accumulate) return SEA_ERR_INVALID;
+  d.dweight2 = a->dweight2; d.dbias2 = a->dbias2;
   d.M = a->M; d.d = a->d; d.kind = a->kind;
   d.rows_per_cta = rows_per_cta_for(a->M, 8);
   return SEA_OK;

@@ -152,6 +152,16 @@ sea_norm_bwd_args norm_bwd_args(BCtx& b, int kind, const sea_norm_params& np, co
   return a;
 }
 
+// E-wide AdaLN norms (ln0, ln2, final): the cond gradient goes straight to the bf16 operand buffer of the
+// cond_mlp[2] backward GEMMs, and cond_mlp[2].bias.grad (= the column sums of dcond = this norm's d(weight) | d(bias))
+// comes out of the norm kernel's own column reduction: no fp32 dcond, no cast pass, no column-sum pass.
+void dcond_direct(BCtx& b, sea_norm_bwd_args& a, const sea_norm_params& np, int g) {
+  if (a.kind != SEA_NORM_ADALN) return;
+  a.dcond = nullptr;
+  a.dcond_bf16 = b.bt->dcb[g];
+  if (np.c2_b.g) { a.dweight2 = np.c2_b.g; a.dbias2 = np.c2_b.g + a.d; }
+}
+
 int norm_bwd_group(BCtx& b, int n, const sea_norm_bwd_args* a) {
   ++g_launches;
   ProfScope prof(b.c.s, SEA_PROF_ELEMWISE, 16.0 * b.c.M * a[0].d * n);
@@ -178,11 +188,11 @@ int norm_bwd(BCtx& b, int kind, const sea_norm_params& np, const float* cond, co
 
 // AdaLN cond_mlp backward for n modules of width d2 = 2*dim (grouped across streams).
 int cond_bwd(BCtx& b, int n, const sea_norm_params* const* np, void* const* hid, float* const* dcond,
-             const PackedLinear* const* W, int d2) {
+             const PackedLinear* const* W, int d2, bool direct = false) {
   const int M = b.c.M;
   LinB L[SEA_MAX_STREAMS];
   for (int g = 0; g < n; ++g) {
-    SEA_TRY(cast_f32(b, dcond[g], d2, M, d2, b.bt->dcb[g], d2, 0));
+    if (!direct) SEA_TRY(cast_f32(b, dcond[g], d2, M, d2, b.bt->dcb[g], d2, 0));
     LinB& l = L[g];
     l = LinB{};
     l.dy = b.bt->dcb[g]; l.lddy = d2;
@@ -193,7 +203,7 @@ int cond_bwd(BCtx& b, int n, const sea_norm_params* const* np, void* const* hid,
     l.da_f32 = b.bt->dhid[g]; l.ld_da = d2;
   }
   SEA_TRY(linear_bwd(b, n, L));
-  {
+  if (!direct) {
     const float* src[SEA_MAX_STREAMS]; float* dbs[SEA_MAX_STREAMS];
     for (int g = 0; g < n; ++g) { src[g] = dcond[g]; dbs[g] = np[g]->c2_b.g; }
     SEA_TRY(colsum_group(b, n, src, nullptr, d2, M, d2, dbs));
@@ -312,12 +322,13 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       na[i] = norm_bwd_args(b, kind, d->final_ln[i], tape.condF[i], dy + static_cast<long long>(i) * E, ldY,
                             last.s[i].xout, E, tape.stF[i], E, nullptr, 0, bt.s[i].dxout, E, bt.s[i].dxoutb,
                             bt.s[i].dcondF, 0);
+    for (int i = 0; i < V; ++i) dcond_direct(b, na[i], d->final_ln[i], i);
     SEA_TRY(norm_bwd_group(b, V, na));
     if (ada) {
       const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
       float* dc[SEA_MAX_STREAMS]; const PackedLinear* W[SEA_MAX_STREAMS];
       for (int i = 0; i < V; ++i) { np[i] = &d->final_ln[i]; hid[i] = tape.hidF[i]; dc[i] = bt.s[i].dcondF; W[i] = &cl.c2_final[i]; }
-      SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E));
+      SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E, true));
     }
   }
 
@@ -386,13 +397,14 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       for (int i = 0; i < V; ++i)
         na[i] = norm_bwd_args(b, kind, bp.s[i].ln2, lt.s[i].cond2, bt.s[i].dn2, E, lt.s[i].x2, E, lt.s[i].st2, E,
                               bt.s[i].dx3, E, bt.s[i].dx2, E, bt.s[i].dx2b, bt.s[i].dcond2, 0);
+      for (int i = 0; i < V; ++i) dcond_direct(b, na[i], bp.s[i].ln2, i);
       SEA_TRY(norm_bwd_group(b, V, na));
     }
     if (ada) {
       const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
       float* dc[SEA_MAX_STREAMS]; const PackedLinear* W[SEA_MAX_STREAMS];
       for (int i = 0; i < V; ++i) { np[i] = &bp.s[i].ln2; hid[i] = lt.s[i].hid2; dc[i] = bt.s[i].dcond2; W[i] = &bc.s[i].c2_ln2; }
-      SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E));
+      SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E, true));
     }
     // (3) TIPI (shared module: gradients of all streams add up)
     if (bp.ib3_w.g) {
@@ -545,6 +557,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
         else { dst = bt.s[i].dxout; }  // not requested: still needed for the parameter gradients
         na[i] = norm_bwd_args(b, kind, bp.s[i].ln0, lt.s[i].cond0, bt.s[i].dn0, E, xin[i], ldxin, lt.s[i].st0, E,
                               bt.s[i].dx1, E, dst, ldd, dstb, bt.s[i].dcond0, 0);
+        dcond_direct(b, na[i], bp.s[i].ln0, i);
       }
       SEA_TRY(norm_bwd_group(b, V, na));
     }
@@ -552,7 +565,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       const sea_norm_params* np[SEA_MAX_STREAMS]; void* hid[SEA_MAX_STREAMS];
       float* dc[SEA_MAX_STREAMS]; const PackedLinear* W[SEA_MAX_STREAMS];
       for (int i = 0; i < V; ++i) { np[i] = &bp.s[i].ln0; hid[i] = lt.s[i].hid0; dc[i] = bt.s[i].dcond0; W[i] = &bc.s[i].c2_ln0; }
-      SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E));
+      SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E, true));
     }
   }
   return SEA_OK;
