@@ -215,3 +215,28 @@ def test_full_size_properties(cuda, cfg_name, E, ln):
         d = rel_l2(r_kv, r_graph)
         print(f"\n[full-size properties] {cfg_name}: KV-cached vs prefix loop after 24 steps: {d:.3e}")
         assert d < 2e-2
+
+
+@pytest.mark.parametrize("B,T", [(1, 2024), (3, 1), (1, 129), (2, 257)])
+@pytest.mark.parametrize("ln", ["adaln", "ln"])
+def test_sequence_length_edges_match_oracle(cuda, B, T, ln):
+    """Edges of the token axis: the configs' max_len (T = 2024: 8 two-tile query blocks per head in the tcgen05
+    attention), a single token, and lengths one past a 128 / 256 tile boundary; head dim 128 (self) and 64 (cross),
+    both on the tensor-core kernels.  Forward against the fp32 oracle on fresh seeded inputs."""
+    from sea_b200.temporal import TemporalModel
+    from oracle import golden_recipe as gr
+    E, nh, scale = 256, 2, 2
+    sd = gr.fill_state(gr.temporal_shapes(embed_dim=E, n_heads=nh, scale_ratio=scale, num_variables=2, ln_type=ln), 31)
+    x, ib, _ = gr.temporal_inputs(B, T, 2, E, 31)
+    with torch.no_grad():
+        ref = so.temporal_forward(x, ib, sd, num_layers=1, n_heads=nh, ln_type=ln)
+    for precision in ("fp32", "bf16"):
+        m = TemporalModel(1, E, nh, 2024, scale, 0, 2, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln,
+                          precision=precision)
+        m.load_state_dict(sd, strict=False)
+        m = m.to(cuda).eval()
+        with torch.no_grad():
+            y = m(x.to(cuda), ib.to(cuda))
+        assert y.shape == ref.shape
+        assert rel_l2(y.cpu(), ref) < TOL[precision], (precision, rel_l2(y.cpu(), ref))
+        del m
