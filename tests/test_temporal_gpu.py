@@ -240,3 +240,30 @@ def test_sequence_length_edges_match_oracle(cuda, B, T, ln):
         assert y.shape == ref.shape
         assert rel_l2(y.cpu(), ref) < TOL[precision], (precision, rel_l2(y.cpu(), ref))
         del m
+
+
+@pytest.mark.parametrize("ln", ["adaln", "ln"])
+def test_long_kv_cached_rollout_crosses_tile_boundaries(cuda, ln):
+    """A 270-step rollout (the reference evaluates 399-step trajectories, utils/train_utils.py:170-175): the prefix
+    loop switches attention kernels at 128 keys (single tile -> two-tile pipeline) and the KV cache grows past
+    256 entries; in fp32 mode the cached engine, the graphed prefix loop and the oracle must still agree."""
+    from sea_b200.rollout import rollout
+    from sea_b200.temporal import TemporalModel
+    from oracle import golden_recipe as gr
+    E, nh, scale, B, steps = 256, 2, 2, 2, 270
+    sd = gr.fill_state(gr.temporal_shapes(embed_dim=E, n_heads=nh, scale_ratio=scale, num_variables=2, ln_type=ln), 37)
+    x, ib, _ = gr.temporal_inputs(B, 2, 2, E, 37)
+    m = TemporalModel(1, E, nh, 512, scale, 0, 2, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln,
+                      precision="fp32")
+    m.load_state_dict(sd, strict=False)
+    m = m.to(cuda).eval()
+    x0 = x[:, :1].contiguous().to(cuda)
+    ibs = ib[:, :1].expand(B, steps, 1).contiguous().to(cuda)
+    r_pref = rollout(m, x0, ibs, steps)
+    r_kv = rollout(m, x0, ibs, steps, cached=True)
+    with torch.no_grad():
+        ref = so.rollout(x0.cpu(), ibs.cpu(), steps, sd, num_layers=1, n_heads=nh, ln_type=ln)
+    assert r_pref.shape == (B, steps, 2, E)
+    e_pref, e_kv = rel_l2(r_pref.cpu(), ref), rel_l2(r_kv.cpu(), ref)
+    print(f"\n[long rollout] {ln}: prefix loop {e_pref:.3e}, cached {e_kv:.3e} vs oracle over {steps} steps")
+    assert e_pref < 1e-4 and e_kv < 1e-4
