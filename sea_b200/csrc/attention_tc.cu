@@ -189,23 +189,36 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
       ptx::mbar_wait(s_full, j & 1);
       ptx::tc_fence_after();
       const bool need_mask = (kv0 + BKV - 1 > q0 + pp.src_len) || (kv0 + BKV > pp.T);
-      // the whole score row of this tile in registers: ONE TMEM round trip (all loads in flight)
-      uint32_t r[BKV];
+      // Two sweeps over the score row in 64-column chunks (max, then exponentials): a thread never holds more
+      // than 64 scores, so the kernel stays under 128 registers — the per-sub-partition register file
+      // (16 K registers, 4 of a CTA pair's 12 warps) is what decides whether two CTAs really share an SM —
+      // at the price of one extra ~60-cycle TMEM read per chunk.
+      constexpr int CHK = BKV < 64 ? BKV : 64;
+      uint32_t r[CHK];
+      auto load_chunk = [&](int c) {
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld_32x32p(tmem + lane_base + kColS + c * 32, r + c * 32);
-      ptx::tmem_ld_wait();
-      float mx = -INFINITY;   // max of the RAW scores (scale > 0 commutes with max)
-      if (need_mask) {
+        for (int i = 0; i < CHK / 32; ++i) ptx::tmem_ld_32x32p(tmem + lane_base + kColS + c * CHK + i * 32, r + i * 32);
+        ptx::tmem_ld_wait();
+        if (need_mask) {
 #pragma unroll
-        for (int e = 0; e < BKV; ++e) {
-          const int kk = kv0 + e;
-          if (kk > q + pp.src_len || kk >= pp.T) r[e] = 0xff800000u;  // -inf
-          mx = fmaxf(mx, __uint_as_float(r[e]));
+          for (int e = 0; e < CHK; ++e) {
+            const int kk = kv0 + c * CHK + e;
+            if (kk > q + pp.src_len || kk >= pp.T) r[e] = 0xff800000u;  // -inf
+          }
         }
-      } else {
+      };
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // max of the RAW scores (scale > 0 commutes with max)
 #pragma unroll
-        for (int e = 0; e < BKV; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+      for (int c = 0; c < BKV / CHK; ++c) {
+        load_chunk(c);
+#pragma unroll
+        for (int e = 0; e < CHK; e += 8) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(r[e + 2 * u]), __uint_as_float(r[e + 2 * u + 1])));
+        }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_cand = fmaxf(m_ref, mx * pp.scale_log2);
       const bool grow = (m_cand > m_ref + 8.0f) || (m_ref == -INFINITY && m_cand != -INFINITY);
       const bool any_grow = __any_sync(0xffffffffu, grow);
@@ -218,14 +231,14 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
         l_sum *= alpha;
         m_ref = m_cand;
         if (j > 0) {
-#pragma unroll
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld_32x32(tmem + lane_base + kColO + c * 32, o);
+#pragma unroll 1
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            ptx::tmem_ld_32x16p(tmem + lane_base + kColO + c * 16, o);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-            ptx::tmem_st_32x32(tmem + lane_base + kColO + c * 32, o);
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            ptx::tmem_st_32x16p(tmem + lane_base + kColO + c * 16, o);
           }
         }
       }
@@ -237,21 +250,29 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
       const unsigned long long drop_row = DROP ? ((static_cast<unsigned long long>(b) * pp.n_heads + h) * pp.T + q) *
                                                      static_cast<unsigned long long>((pp.T + 1) & ~1) + kv0 : 0ull;
 #pragma unroll
-      for (int e = 0; e < BKV; e += 2) {
-        float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), pp.scale_log2, neg_m));
-        float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), pp.scale_log2, neg_m));
-        l0 += p0; l1 += p1;
-        if (DROP) {
-          const uint2 hsh = ptx::drop_hash(pp.drop_seed, p.drop_site, (drop_row + e) >> 1);
-          p0 = hsh.x >= pp.drop_thresh ? p0 * pp.drop_scale : 0.f;
-          p1 = hsh.y >= pp.drop_thresh ? p1 * pp.drop_scale : 0.f;
+      for (int c = 0; c < BKV / CHK; ++c) {
+        // chunk c of S is still intact: the packed P of chunks < c occupies columns [0, c * CHK / 2)
+        load_chunk(c);
+#pragma unroll
+        for (int e = 0; e < CHK; e += 2) {
+          float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), pp.scale_log2, neg_m));
+          float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), pp.scale_log2, neg_m));
+          l0 += p0; l1 += p1;
+          if (DROP) {
+            const uint2 hsh = ptx::drop_hash(pp.drop_seed, p.drop_site, (drop_row + c * CHK + e) >> 1);
+            p0 = hsh.x >= pp.drop_thresh ? p0 * pp.drop_scale : 0.f;
+            p1 = hsh.y >= pp.drop_thresh ? p1 * pp.drop_scale : 0.f;
+          }
+          r[e >> 1] = ptx::pack_bf16(p0, p1);
         }
-        r[e >> 1] = ptx::pack_bf16(p0, p1);
+#pragma unroll
+        for (int i = 0; i < CHK / 32; ++i)
+          ptx::tmem_st_32x16p(tmem + lane_base + kColP + c * (CHK / 2) + i * 16, r + i * 16);
+        // the next chunk's load must not overtake these stores in the TMEM pipe (P of chunk c lands in columns
+        // below chunk c+1, but the load of chunk c+1 reuses the registers the store is still reading)
+        ptx::tmem_st_wait();
       }
       l_sum += l0 + l1;
-#pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_st_32x16p(tmem + lane_base + kColP + c * 16, r + c * 16);
-      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
     }
