@@ -9,9 +9,12 @@ recomputed every step, no KV cache).  Trajectories are sharded across GPUs (weak
 GPU fixed), no data-path collective.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
-  python bench.py --impl reference [...]                         # CPU arm: oracle port, host cores
+  python bench.py --impl reference [...]                         # CPU arm: the UNMODIFIED reference (oracle/_ref)
 
-One JSON line on stdout (rank 0).
+One JSON line on stdout (rank 0).  Auxiliary objects on the same line (none of them is the headline):
+``train_dp`` (BASELINE configs[1],[2]: the data-parallel train step WITH its gradient all-reduce, at this N),
+``rollout_multiphase`` (configs[3] per-GPU shard), ``rollout_fp32``, ``dropin_loop`` (the unchanged eager loop through
+the rebound forward), ``drift`` (bf16 vs fp32-mode, full width, 100 steps), ``cached_rollout``, ``attention_kernel``.
 """
 from __future__ import annotations
 
@@ -29,14 +32,24 @@ import torch  # noqa: E402
 
 CFG = dict(name="cylinder_flow", num_layers=1, embed_dim=1024, n_heads=8, max_len=2024, scale_ratio=8,
            src_len=0, num_variables=2, down_proj=2, ln_type="adaln")
+CFG_MP = dict(name="multiphase_flow", num_layers=1, embed_dim=2048, n_heads=8, max_len=2024, scale_ratio=8,
+              src_len=0, num_variables=2, down_proj=2, ln_type="ln")
 B_PER_GPU = 32          # trajectories per GPU
 ROLLOUT_STEPS = 100     # autoregressive steps per trajectory
-CPU_SAMPLE = dict(B=8, R=40)   # bounded sample of the same workload for the CPU arm
-WORKLOAD = (f"cylinder_flow temporal model (configs/cylinder_flow.py: E=1024, 8 heads, H=8192, Dd=512, "
-            f"V=2, adaln), {ROLLOUT_STEPS}-step autoregressive rollout with full-prefix recompute, "
-            f"{B_PER_GPU} trajectories per GPU")
+CPU_B = 8               # the CPU arm runs CPU_B of the B_PER_GPU trajectories, ALL ROLLOUT_STEPS steps of each
 METRIC = "rollout_trajectory_steps_per_sec"
 UNIT = "trajectory-steps/s"
+
+
+def workload_config(B, R):
+    """The workload both arms are quoted on (identical dict on the `ours` and the `reference` line)."""
+    w = (f"cylinder_flow temporal model (configs/cylinder_flow.py: E=1024, 8 heads, H=8192, Dd=512, "
+         f"V=2, adaln), {R}-step autoregressive rollout with full-prefix recompute, "
+         f"{B} trajectories per GPU")
+    return {"workload": w,
+            "bench_step": f"one {R}-step rollout of {B} trajectories per GPU",
+            "l2": "no flush: per-step working set (174 MB bf16 weights + activations up to "
+                  ">1 GB) exceeds the 126 MB L2"}
 
 
 def fwd_flops(B, T, E=1024, H=8192, Dd=512, V=2, L=1, adaln=True, c=0.5):
@@ -66,12 +79,13 @@ def peaks():
 
 
 def gemm_traffic():
-    """DRAM bytes per GEMM launch from the committed `ncu --set full` capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r1c_gemm_traffic.json")
+    """DRAM bytes / algorithmic bytes per GEMM launch over ONE WHOLE rollout of the current kernels, from this round's
+    committed ncu pass (profiles/r2_gemm_traffic.json, written by scripts/ncu_traffic.py), or None."""
+    path = os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")
     try:
         with open(path) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
-    except (OSError, KeyError, ValueError):
+            return json.load(f)
+    except (OSError, ValueError):
         return None
 
 
@@ -82,12 +96,12 @@ def make_inputs(B, R, E, V, seed):
     return x0, ib
 
 
-def build_model(precision="bf16"):
+def build_model(precision="bf16", cfg=CFG, dropout=0.0):
     from sea_b200.temporal import TemporalModel
     torch.manual_seed(42)
-    c = CFG
+    c = cfg
     return TemporalModel(c["num_layers"], c["embed_dim"], c["n_heads"], c["max_len"], c["scale_ratio"],
-                         c["src_len"], c["num_variables"], c["down_proj"], 0.0, "sea", "learnable", "mlp",
+                         c["src_len"], c["num_variables"], c["down_proj"], dropout, "sea", "learnable", "mlp",
                          "add", 1, 1, True, c["ln_type"], precision=precision)
 
 
@@ -138,112 +152,164 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_rollout_rate(sd, B, R, reps, warm):
-    """Oracle port of the reference path on the host cores: trajectory-steps/s."""
-    from oracle import sea_oracle as so
-    torch.set_num_threads(os.cpu_count() or 1)
-    x0, ib = make_inputs(B, R, CFG["embed_dim"], CFG["num_variables"], 1234)
-    kw = dict(num_layers=1, n_heads=CFG["n_heads"], ln_type=CFG["ln_type"])
-    times = []
-    with torch.no_grad():
-        for i in range(warm + reps):
-            t0 = time.perf_counter()
-            so.rollout(x0, ib, R, sd, **kw)
-            if i >= warm:
-                times.append(time.perf_counter() - t0)
-    times.sort()
-    med = times[len(times) // 2]
-    return B * R / med, med, torch.get_num_threads()
+# CPU arm: the reference's own implementation on the host cores
+# ---------------------------------------------------------------------------------------------
+class CpuArm:
+    """The reference's CPU implementation of the path on a bounded sample of the workload: CPU_B trajectories x
+    all R steps, the loop of utils/train_utils.py:202-209 (model.eval(), no_grad, prefix + torch.cat).
+    kind = "reference": the UNMODIFIED reference classes from oracle/_ref (staged by build()); "port": the oracle
+    restatement, only when the staged reference is missing."""
 
+    def __init__(self, sd, R):
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.R, self.cores = R, torch.get_num_threads()
+        self.x0, self.ib = make_inputs(CPU_B, R, CFG["embed_dim"], CFG["num_variables"], 1234)
+        self.kind = "port"
+        try:
+            from oracle import ref as oref
+            if oref.available():
+                ns = oref.load()
+                c = CFG
+                m = ns.temporal.TemporalModel(c["num_layers"], c["embed_dim"], c["n_heads"], c["max_len"],
+                                              c["scale_ratio"], c["src_len"], c["num_variables"], c["down_proj"], 0.0,
+                                              "sea", "learnable", "mlp", "add", 1, 1, True, c["ln_type"])
+                m.load_state_dict(sd, strict=False)
+                self.model, self.kind = m.eval(), "reference"
+        except Exception as e:  # noqa: BLE001  (a broken staging must not kill the GPU arm's line)
+            print(f"[bench] reference unavailable ({e!r}); CPU arm falls back to the oracle port", file=sys.stderr)
+        self.sd = sd
 
-def train_step_aux(dev, timed):
-    """multiphase_flow (E=2048, hd=256, H=16384, ln), B=4, T=199 (configs/multiphase_flow.py:140-141):
-    zero_grad + forward + MSE + backward + fused AdamW, device-resident synthetic batch."""
-    from sea_b200.optim import AdamW
-    from sea_b200.temporal import TemporalModel
-    torch.manual_seed(42)
-    m = TemporalModel(1, 2048, 8, 2024, 8, 0, 2, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, "ln").to(dev).train()
-    opt = AdamW(m.parameters(), lr=8e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, engine=m.engine())
-    B, T = 4, 199
-    g = torch.Generator(device=dev).manual_seed(7)
-    x = torch.randn(B, T, 2, 2048, device=dev, generator=g)
-    ib = torch.rand(B, 1, 1, device=dev, generator=g).expand(B, T, 1).contiguous()
-    tgt = torch.randn(B, T, 2, 2048, device=dev, generator=g)
+    def one(self):
+        R = self.R
+        with torch.no_grad():
+            if self.kind == "reference":
+                seq = self.x0
+                for i in range(R):     # utils/train_utils.py:203-207
+                    out = self.model(seq, self.ib[:, : i + 1])
+                    seq = torch.cat((seq, out[:, -1:]), dim=1)
+                return seq[:, 1:]
+            from oracle import sea_oracle as so
+            return so.rollout(self.x0, self.ib, R, self.sd, num_layers=1, n_heads=CFG["n_heads"], ln_type=CFG["ln_type"])
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        loss = torch.nn.functional.mse_loss(m(x, ib), tgt)
-        loss.backward()
-        opt.step()
-
-    for _ in range(3):
-        step()
-    ms = timed(step, 5)
-    flops = 3 * fwd_flops(B, T, E=2048, H=16384, Dd=1024, adaln=False)
-    out = {"workload": "multiphase_flow train step (B=4, T=199): zero_grad + fwd + MSE + bwd + fused AdamW, bf16",
-           "ms_per_step": ms, "samples_per_sec": B / (ms / 1e3), "model_tflops": flops / (ms * 1e-3) / 1e12}
-    del m, opt
-    torch.cuda.empty_cache()
-    return out
-
-
-def attention_kernel_aux(dev, timed, pk):
-    """BASELINE metric, second half ("attention TFLOP/s vs peak"): the fused causal attention kernels
-    alone at the configs' max_len (T = 2024), cylinder_flow head geometry (8 heads x 128), bf16,
-    causal-useful FLOPs 2*B*nh*T^2*hd forward (SURVEY.md 8d, c = 1/2), 2.5x that backward."""
-    from sea_b200 import ops
-    B, T, nh, hd = 4, 2024, 8, 128
-    g = torch.Generator(device=dev).manual_seed(9)
-    qkv = torch.randn(B * T, 3 * nh * hd, device=dev, generator=g).bfloat16()
-    q, k, v = qkv[:, : nh * hd], qkv[:, nh * hd: 2 * nh * hd], qkv[:, 2 * nh * hd:]
-    o, lse = ops.attention_fwd(q, k, v, nh, B=B, want_lse=True)
-    do = torch.randn(B * T, nh * hd, device=dev, generator=g).bfloat16()
-    for _ in range(3):
-        ops.attention_fwd(q, k, v, nh, B=B, want_lse=True)
-        ops.attention_bwd(q, k, v, o, do, lse, nh, B=B)
-    ms_f = timed(lambda: ops.attention_fwd(q, k, v, nh, B=B, want_lse=True), 20)
-    ms_b = timed(lambda: ops.attention_bwd(q, k, v, o, do, lse, nh, B=B), 10)
-    fl = 2.0 * B * nh * T * T * hd
-    tf_f, tf_b = fl / (ms_f * 1e-3) / 1e12, 2.5 * fl / (ms_b * 1e-3) / 1e12
-    return {"workload": f"causal self-attention B={B} T={T} heads={nh} head_dim={hd}, bf16 (tcgen05 kernels alone)",
-            "fwd_ms": ms_f, "fwd_tflops": tf_f, "fwd_frac_of_sustained_peak": tf_f / pk["sustained"],
-            "bwd_ms": ms_b, "bwd_tflops": tf_b, "bwd_frac_of_sustained_peak": tf_b / pk["sustained"],
-            "flops": "causal-useful (half of the dense count)"}
+    def sample(self):
+        what = ("UNMODIFIED reference (oracle/_ref: models/temporal.py TemporalModel, eval, no_grad)"
+                if self.kind == "reference" else "oracle port (oracle/sea_oracle.py)")
+        return (f"{what}, torch CPU fp32, {self.cores} threads: {CPU_B} of the {B_PER_GPU} trajectories x all {self.R} "
+                f"steps of the same rollout (prefix recompute, torch.cat) per bench step")
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path.  /root/reference is Python
-    and does not travel to the GPU box, so this times oracle/sea_oracle.py (the restatement pinned
-    against the reference's outputs) on all host cores, on a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation, all host threads, on the `ours` arm's config."""
     if rank != 0:
         return
-    torch.manual_seed(42)
     sd = {k: v for k, v in build_model().state_dict().items()}
-    B, R = CPU_SAMPLE["B"], CPU_SAMPLE["R"]
-    from oracle import sea_oracle as so
-    torch.set_num_threads(os.cpu_count() or 1)
-    x0, ib = make_inputs(B, R, CFG["embed_dim"], CFG["num_variables"], 1234)
-    kw = dict(num_layers=1, n_heads=CFG["n_heads"], ln_type=CFG["ln_type"])
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            so.rollout(x0, ib, R, sd, **kw)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            so.rollout(x0, ib, R, sd, **kw)
-        dt = time.perf_counter() - t0
+    arm = CpuArm(sd, args.rollout)
+    for _ in range(args.warmup):
+        arm.one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        arm.one()
+    dt = time.perf_counter() - t0
     ms = dt / args.steps * 1e3
-    val = B * R / (ms / 1e3)
-    sample = (f"{B} trajectories x {R} steps of the same rollout (prefix recompute) per bench step, fp32, "
-              f"torch CPU ({torch.get_num_threads()} threads)")
+    val = CPU_B * args.rollout / (ms / 1e3)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample},
+        "config": workload_config(args.batch, args.rollout),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ---------------------------------------------------------------------------------------------
+# auxiliaries
+# ---------------------------------------------------------------------------------------------
+def train_dp_aux(dev, rank, world, timed_fn):
+    """BASELINE configs[1] / configs[2]: the data-parallel train step WITH its collective at this world size.
+    Per rank: zero_grad + forward + MSE + backward + gradient all-reduce (NCCL, mean) + fused AdamW on its own
+    per-GPU batch (weak scaling), bf16 tensor-core path, device-resident synthetic batch."""
+    import torch.nn.functional as F
+
+    from sea_b200 import parallel
+    from sea_b200.optim import AdamW
+    out = []
+    cases = [("cylinder_flow", CFG, 2, 399, 1e-4, 0.1), ("cylinder_flow", CFG, 16, 399, 1e-4, 0.1),
+             ("multiphase_flow", CFG_MP, 4, 199, 8e-5, 0.0)]
+    for name, cfg, b, T, lr, drop in cases:
+        m = build_model("bf16", cfg, dropout=drop).to(dev).train()
+        eng = m.engine()
+        opt = AdamW(m.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, engine=eng)
+        E = cfg["embed_dim"]
+        g = torch.Generator(device=dev).manual_seed(77 + rank)
+        x = torch.randn(b, T, 2, E, device=dev, generator=g)
+        ib = torch.rand(b, 1, 1, device=dev, generator=g).expand(b, T, 1).contiguous()
+        tgt = torch.randn(b, T, 2, E, device=dev, generator=g)
+
+        def local_step():
+            opt.zero_grad(set_to_none=True)
+            F.mse_loss(m(x, ib), tgt).backward()
+            opt.step()
+
+        step = parallel.TrainStep(m, opt, F.mse_loss) if hasattr(parallel, "TrainStep") else None
+
+        def dp_step(overlap):
+            if step is not None:
+                return step(x, tgt, ib, overlap=overlap)
+            return parallel.train_step(m, opt, F.mse_loss, x, tgt, ib, overlap=overlap)
+
+        for _ in range(3):
+            local_step()
+        ms_local = timed_fn(local_step, 10)
+        for _ in range(3):
+            dp_step(False)
+        ms_serial = timed_fn(lambda: dp_step(False), 10)
+        for _ in range(3):
+            dp_step(None)
+        ms_step = timed_fn(lambda: dp_step(None), 10)
+        flops = 3 * fwd_flops(b, T, E=E, H=cfg["scale_ratio"] * E, Dd=E // 2, adaln=cfg["ln_type"] == "adaln")
+        exch_serial, exch_exposed = max(ms_serial - ms_local, 0.0), max(ms_step - ms_local, 0.0)
+        info = step.info() if step is not None else {"grad_dtype": "f32", "buckets": 2, "graphed": False,
+                                                     "nccl_bytes_per_step": eng.flat_grad().numel() * 4}
+        out.append({
+            "config": name, "per_gpu_batch": b, "T": T, "dropout": drop, "n_gpus": world,
+            "ms_per_step": ms_step, "samples_per_sec": world * b / (ms_step / 1e3),
+            "ms_step_no_exchange": ms_local, "ms_step_exchange_after_backward": ms_serial,
+            "exchange_ms_serial": exch_serial, "exchange_ms_exposed": exch_exposed,
+            "overlap_fraction": (1.0 - exch_exposed / exch_serial) if exch_serial > 1e-3 else None,
+            "model_tflops_per_gpu": flops / (ms_step * 1e-3) / 1e12, **info})
+        del m, opt, eng, step
+        torch.cuda.empty_cache()
+    return {"workload": "train step = zero_grad + fwd + MSE + bwd + NCCL all-reduce(mean) of gradients + fused AdamW, "
+                        "bf16 operands / fp32 accumulate; per-GPU batch fixed (weak scaling); CUDA events, max over ranks",
+            "cases": out}
+
+
+def attention_kernel_aux(dev, timed, pk):
+    """BASELINE metric, second half ("attention TFLOP/s vs peak"): the fused causal attention kernels
+    alone at the configs' max_len (T = 2024), the three head geometries of the two configs, bf16,
+    causal-useful FLOPs 2*B*nh*T^2*hd forward (SURVEY.md 8d, c = 1/2), 2.5x that backward."""
+    from sea_b200 import ops
+    res = {}
+    for hd in (128, 256, 64):
+        B, T, nh = 4, 2024, 8
+        g = torch.Generator(device=dev).manual_seed(9)
+        qkv = torch.randn(B * T, 3 * nh * hd, device=dev, generator=g).bfloat16()
+        q, k, v = qkv[:, : nh * hd], qkv[:, nh * hd: 2 * nh * hd], qkv[:, 2 * nh * hd:]
+        o, lse = ops.attention_fwd(q, k, v, nh, B=B, want_lse=True)
+        do = torch.randn(B * T, nh * hd, device=dev, generator=g).bfloat16()
+        for _ in range(3):
+            ops.attention_fwd(q, k, v, nh, B=B, want_lse=True)
+            ops.attention_bwd(q, k, v, o, do, lse, nh, B=B)
+        ms_f = timed(lambda: ops.attention_fwd(q, k, v, nh, B=B, want_lse=True), 20)
+        ms_b = timed(lambda: ops.attention_bwd(q, k, v, o, do, lse, nh, B=B), 10)
+        fl = 2.0 * B * nh * T * T * hd
+        tf_f, tf_b = fl / (ms_f * 1e-3) / 1e12, 2.5 * fl / (ms_b * 1e-3) / 1e12
+        res[f"hd{hd}"] = {"fwd_ms": ms_f, "fwd_tflops": tf_f, "fwd_frac_of_sustained_peak": tf_f / pk["sustained"],
+                          "bwd_ms": ms_b, "bwd_tflops": tf_b, "bwd_frac_of_sustained_peak": tf_b / pk["sustained"]}
+    res["workload"] = ("causal self-attention B=4 T=2024 heads=8, head_dim 128 (cylinder self / multiphase cross), 256 "
+                       "(multiphase self), 64 (cylinder cross); bf16 (tcgen05 kernels alone); causal-useful FLOPs")
+    return res
 
 
 def main():
@@ -256,6 +322,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--rollout", type=int, default=ROLLOUT_STEPS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="headline + roofline only (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -267,7 +334,6 @@ def main():
         return
 
     import torch.distributed as dist
-    from sea_b200 import lib
     from sea_b200.rollout import profile, rollout, rollout_from_host
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
@@ -326,22 +392,80 @@ def main():
     h2d = x0_h.numel() * 4 + ib_h.numel() * 4
     d2h = out_h.numel() * 4
 
-    # ---- KV-cached incremental engine (opt-in, NOT the headline): same trajectories ----
-    pred_prefix = rollout(model, x0, ib, R)
-    for _ in range(2):
-        pred_cached = rollout(model, x0, ib, R, cached=True)
-    cached_rel = ((pred_cached - pred_prefix).norm() / pred_prefix.norm()).item()
-    n10 = min(10, R)
-    cached_rel10 = ((pred_cached[:, :n10] - pred_prefix[:, :n10]).norm() / pred_prefix[:, :n10].norm()).item()
-    ms_cached = timed(lambda: rollout(model, x0, ib, R, cached=True, _view_ok=True), args.steps)
-    del pred_prefix, pred_cached
+    aux = {}
+    pk = peaks()
+    if not args.no_aux:
+        # ---- KV-cached incremental engine (opt-in, NOT the headline): same trajectories ----
+        pred_prefix = rollout(model, x0, ib, R)
+        for _ in range(2):
+            pred_cached = rollout(model, x0, ib, R, cached=True)
+        cached_rel = ((pred_cached - pred_prefix).norm() / pred_prefix.norm()).item()
+        ms_cached = timed(lambda: rollout(model, x0, ib, R, cached=True, _view_ok=True), args.steps)
+        aux["cached_rollout"] = {
+            "value": world * B * R / (ms_cached / 1e3), "unit": UNIT, "ms_per_step": ms_cached,
+            "us_per_model_step": ms_cached * 1e3 / R,
+            "rel_l2_vs_prefix_loop": cached_rel,
+            "note": "opt-in KV-cached engine (sea_temporal_step): O(1) work per step instead of the reference loop's "
+                    "prefix recompute; same function up to rounding; not the headline value"}
+        del pred_cached
 
-    # ---- auxiliary: BASELINE configs[1], multiphase_flow fwd+bwd(+AdamW) train step at the reference batch ----
-    train_aux = train_step_aux(dev, timed) if world == 1 else None   # single-GPU figure only
+        # ---- the UNCHANGED eager loop through the rebound forward (what full_autoregressive_evaluation runs) ----
+        def dropin_loop():
+            seq = x0
+            with torch.no_grad():
+                for i in range(R):      # utils/train_utils.py:203-207
+                    out = model(seq, ib[:, : i + 1])
+                    seq = torch.cat((seq, out[:, -1:]), dim=1)
+            return seq[:, 1:]
+        pred_loop = dropin_loop()
+        loop_rel = ((pred_loop - pred_prefix).norm() / pred_prefix.norm()).item()
+        ms_loop = timed(dropin_loop, 2)
+        aux["dropin_loop"] = {
+            "value": world * B * R / (ms_loop / 1e3), "unit": UNIT, "ms_per_step": ms_loop,
+            "rel_l2_vs_graphed_rollout": loop_rel,
+            "note": "the reference's rollout loop verbatim (model(seq, ib[:, :i+1]); torch.cat) on the drop-in forward: "
+                    "one FFI call per step, no CUDA graphs, ib not known to be time-invariant"}
+        del pred_loop
+
+        # ---- fp32-parity mode on the same trajectories: throughput + the bf16 engine's drift against it ----
+        if args.precision == "bf16":
+            m32 = build_model("fp32").to(dev).eval()
+            for _ in range(2):
+                pred32 = rollout(m32, x0, ib, R)
+            ms32 = timed(lambda: rollout(m32, x0, ib, R, _view_ok=True), 2)
+            per_step = ((pred_prefix - pred32).flatten(2).norm(dim=(0, 2)) / pred32.flatten(2).norm(dim=(0, 2)))
+            aux["rollout_fp32"] = {"value": world * B * R / (ms32 / 1e3), "unit": UNIT, "ms_per_step": ms32,
+                                   "note": "precision='fp32' (3xbf16-split tensor-core GEMMs, fp32 attention / norms): "
+                                           "the 1e-4 parity mode, same workload"}
+            aux["drift"] = {"rel_l2_bf16_vs_fp32_mode_step10": per_step[min(9, R - 1)].item(),
+                            "rel_l2_bf16_vs_fp32_mode_step50": per_step[min(49, R - 1)].item(),
+                            "rel_l2_bf16_vs_fp32_mode_step100": per_step[R - 1].item(),
+                            "note": "full-width cylinder_flow, B=32: per-step relative L2 of the bf16 engine's predicted "
+                                    "latents against the fp32-mode engine (itself 2e-6 from the reference); north_star "
+                                    "bar: 2e-2 at step 10"}
+            del m32, pred32
+            torch.cuda.empty_cache()
+        del pred_prefix
+
+        # ---- BASELINE configs[3]: multiphase_flow 100-step rollout ensemble, batch 256 over 8 GPUs = 32 per GPU ----
+        mmp = build_model("bf16", CFG_MP).to(dev).eval()
+        x0m, ibm = make_inputs(B, R, CFG_MP["embed_dim"], 2, 4321 + rank)
+        x0m, ibm = x0m.to(dev), ibm.to(dev)
+        for _ in range(2):
+            rollout(mmp, x0m, ibm, R)
+        ms_mp = timed(lambda: rollout(mmp, x0m, ibm, R, _view_ok=True), 3)
+        aux["rollout_multiphase"] = {
+            "value": world * B * R / (ms_mp / 1e3), "unit": UNIT, "ms_per_step": ms_mp, "global_batch": world * B,
+            "workload": f"multiphase_flow (E=2048, hd=256, H=16384, ln), {R}-step prefix-recompute rollout, {B} "
+                        f"trajectories per GPU (BASELINE configs[3]: batch 256 = 32 x 8 GPUs)"}
+        del mmp, x0m, ibm
+        torch.cuda.empty_cache()
+
+        # ---- BASELINE configs[1], [2]: data-parallel train step with its collective ----
+        aux["train_dp"] = train_dp_aux(dev, rank, world, timed)
+        aux["attention_kernel"] = attention_kernel_aux(dev, timed, pk)
 
     # ---- roofline leg: one more rollout with per-launch CUDA events on the launch stream ----
-    pk = peaks()
-    attn_aux = attention_kernel_aux(dev, timed, pk)
     with profile() as prof:
         rollout(model, x0, ib, R)
         torch.cuda.synchronize()
@@ -350,6 +474,7 @@ def main():
     attn_tflops = ps["attention"]["work"] / (ps["attention"]["ms"] * 1e-3) / 1e12 if ps["attention"]["ms"] > 0 else 0.0
     elem_gbs = ps["elementwise"]["work"] / (ps["elementwise"]["ms"] * 1e-3) / 1e9 if ps["elementwise"]["ms"] > 0 else 0.0
     total_kernel_ms = sum(v["ms"] for v in ps.values())
+    executed_flops = ps["gemm"]["work"] + ps["attention"]["work"]      # hoisted / deduplicated FLOPs are NOT in here
 
     if rank != 0:
         if world > 1:
@@ -358,31 +483,39 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, med, cores = cpu_rollout_rate(sd_cpu, CPU_SAMPLE["B"], CPU_SAMPLE["R"], reps=2, warm=1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": (f"oracle port (torch CPU fp32) of the same rollout on {CPU_SAMPLE['B']} trajectories x "
-                          f"{CPU_SAMPLE['R']} steps, median of 2 after 1 warm-up ({med:.2f} s each)")}
+        arm = CpuArm(sd_cpu, R)
+        arm.one()
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            arm.one()
+            ts.append(time.perf_counter() - t0)
+        med = sorted(ts)[0]
+        cpu = {"value": CPU_B * R / med, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+               "sample": arm.sample() + f"; best of 2 after 1 warm-up ({med:.2f} s each)"}
 
-    flops = rollout_flops(B, R)
+    tr = gemm_traffic()
+    cfg = workload_config(B, R)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD if (B, R) == (B_PER_GPU, ROLLOUT_STEPS) else
-                   WORKLOAD + f" [override: B={B}, R={R}]",
-                   "l2": "no flush: per-step working set (174 MB bf16 weights + activations up to "
-                         ">1 GB) exceeds the 126 MB L2",
-                   "bench_step": f"one {R}-step rollout of {B} trajectories per GPU",
-                   "execution": "sea_b200.rollout.RolloutPlan: one CUDA graph per prefix length (full forward "
-                                "over the prefix read in place from the sequence buffer, append last step); the roofline leg replays the "
-                                "same kernels eagerly with per-launch CUDA events",
-                   "algorithmic_tflop_per_step_per_gpu": flops / 1e12,
-                   "model_tflops_per_gpu": flops / (ms_step * 1e-3) / 1e12},
+        "config": cfg,
+        "execution": {"how": "sea_b200.rollout.RolloutPlan: one CUDA graph per prefix length (full forward over the "
+                             "prefix read in place from the sequence buffer, append last step); the roofline leg replays "
+                             "the same kernels eagerly with per-launch CUDA events",
+                      "reference_count_tflop_per_step_per_gpu": rollout_flops(B, R) / 1e12,
+                      "executed_tflop_per_step_per_gpu": executed_flops / 1e12,
+                      "executed_tflops_per_gpu": executed_flops / (ms_step * 1e-3) / 1e12,
+                      "note": "executed = GEMM + attention FLOPs actually launched (AdaLN-condition / TIPI work is hoisted "
+                              "to once per trajectory and cross_down/ln_cross deduplicated, so it is below the reference "
+                              "count of SURVEY 8d)"},
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["sustained"],
-                     "unit": "TFLOP/s", "frac": gemm_tflops / pk["sustained"], "traffic": gemm_traffic(),
-                     "traffic_note": "DRAM bytes per GEMM launch of the T=100 forward, ncu --set full "
-                                     "(profiles/r1c_summary.md section 2); not measured in this run",
+                     "unit": "TFLOP/s", "frac": gemm_tflops / pk["sustained"],
+                     "traffic": None if tr is None else tr.get("dram_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": None if tr is None else tr.get("algorithmic_bytes_per_launch"),
+                     "traffic_note": None if tr is None else tr.get("note"),
                      "kernel": "gemm_bf16_tn_kernel (tcgen05)", "peak_source": pk["src"] + ", sustained",
                      "gemm_share_of_kernel_time": ps["gemm"]["ms"] / total_kernel_ms if total_kernel_ms else None,
                      "attention_tflops": attn_tflops, "attention_frac": attn_tflops / pk["sustained"],
@@ -392,14 +525,7 @@ def main():
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "train_step": train_aux,
-        "attention_kernel": attn_aux,
-        "cached_rollout": {"value": world * B * R / (ms_cached / 1e3), "unit": UNIT, "ms_per_step": ms_cached,
-                           "rel_l2_vs_prefix_loop": cached_rel, "rel_l2_vs_prefix_loop_first_10_steps": cached_rel10,
-                           "note": "opt-in KV-cached engine (sea_temporal_step): O(1) work per step instead of "
-                                   "the reference loop's prefix recompute; same outputs up to rounding (bf16 rounding "
-                                   "differences grow along a 100-step autoregressive rollout; in fp32 mode the two "
-                                   "engines agree to 2e-7, tests/test_temporal_gpu.py); not the headline value"},
+        **aux,
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
     }

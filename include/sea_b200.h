@@ -143,6 +143,12 @@ void sea_gemm_stream_k(int mode);
 void sea_gemm_force_tile_n(int bn);
 /* Tuning probe (results are garbage): 1 = skip the TMA traffic, 2 = skip the MMAs; 0 = normal. */
 void sea_gemm_debug_probe(int mode);
+/* Tuning probe: non-NULL = CTA 0 of every later GEMM launch records %globaltimer (ns) at 8 hand-off points into
+ * dev_buf[0..7]: kernel entry, prologue done, griddepcontrol.wait passed (TMA warp), first stage landed (MMA warp),
+ * last MMA committed, accumulator seen by the epilogue, epilogue stores issued, kernel exit.  NULL = off. */
+void sea_gemm_debug_trace(void* dev_buf);
+/* Tuning probe: {tile width, grid, stream-K units per CTA (0 = data-parallel), tiles} of the last launch. */
+void sea_gemm_last_config(int* out4);
 
 /* ------------------------------------------------------------------ K4: row norms -----------
  * LayerNorm (custom, weight only: models/base_blocks.py:80-88) or AdaLN (:343-350) over the last

@@ -9,11 +9,13 @@ The package holds only what the State-Exchange-Attention hot path needs:
 * ``ops``      one thin Python wrapper per C entry point (used by the parity tests);
 * ``temporal`` / ``spatial``  host-side mirrors of the reference ``TemporalModel`` /
                ``SpatialModel`` interface (same names, arguments, state_dict);
-* ``accelerate`` rebinding of ``forward`` on unchanged reference module instances.
+* ``accelerate`` rebinding of ``forward`` on unchanged reference module instances;
+* ``install()`` the one-line hook that wraps the reference's ``get_model`` / ``initialize_spatial_model``.
 
 There is no CPU fallback: importing is cheap, but every op raises if the CUDA library is missing.
 """
 from ._lib import lib, LibraryMissing, check  # noqa: F401
+from .hooks import install, uninstall  # noqa: F401
 
-__all__ = ["lib", "LibraryMissing", "check"]
+__all__ = ["lib", "LibraryMissing", "check", "install", "uninstall"]
 __version__ = "0.1.0"

@@ -5,6 +5,11 @@ backward = one FFI call that reads it.  Parameter gradients are accumulated by t
 straight into ``param.grad`` (views of one flat fp32 buffer owned by the engine — the same buffer
 the data-parallel all-reduce runs on), with torch's own semantics: ``grad is None`` -> fresh zeros,
 otherwise ``+=``; the reference's dead parameters keep ``grad = None``.
+
+Consequences of writing ``param.grad`` from inside the node (documented limits): ``torch.autograd.grad`` w.r.t.
+parameters and parameter hooks do not see these gradients (use ``loss.backward()`` as the reference loop does,
+train/train_temporal.py:257); the tape is released by the first backward, so a second backward over the same
+graph raises instead of reading a recycled workspace.
 """
 from __future__ import annotations
 
@@ -30,9 +35,13 @@ class _TemporalFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         eng = ctx.engine
+        if ctx.ws is None:
+            raise RuntimeError("sea_b200: the activation tape of this forward was released by its first backward "
+                               "(retain_graph / double backward are not supported; run the forward again)")
         x, ib = ctx.saved_tensors
         dx = eng.backward(x, ib, dy, ctx.ws, ctx.need_dx, dropout_seed=ctx.dropout[0], dropout_p=ctx.dropout[1])
         eng.release_training_workspace(ctx.shape, ctx.ws)
+        ctx.ws = None
         return dx, None, None, None
 
 

@@ -63,7 +63,16 @@ struct alignas(64) GemmParams {
   unsigned int* sk_counters;  // stream-K arrivals per tile (zero between launches)
   int b_is_static;  // B was written before the previous kernel in the stream started (weights)
   int debug;        // tuning probe: 1 = no TMA traffic (MMA pacing only), 2 = no MMA (TMA pacing only)
+  unsigned long long* trace;  // tuning probe (sea_gemm_debug_trace): CTA 0 records %globaltimer at 8 hand-off points
 };
+
+__device__ __forceinline__ void trace_mark(const GemmParams& p, int slot) {
+  if (p.trace != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[slot] = t;
+  }
+}
 
 // BK = K extent of one pipeline stage.  The issuing thread pays a fixed ~390 cycles per stage
 // (mbarrier wait, fence, tcgen05.commit, loop), independent of the tile; a stage must therefore
@@ -324,6 +333,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   // costs ~130 cycles per tcgen05.mma and paces the whole mainloop.
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_mark(p, 0);
   const int num_kb = (p.K + BK - 1) / BK;
   const int crank = CL > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int vcta = blockIdx.x / CL, vgrid = gridDim.x / CL;      // tiles are dealt to clusters
@@ -352,6 +362,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_mark(p, 1);
   // prologue done (barriers, TMEM, descriptor prefetch): let the next kernel start its own
   ptx::pdl_trigger();
 
@@ -456,6 +467,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       }
     }
     ptx::pdl_wait();
+    if (lane == 0) trace_mark(p, 2);
     int issued = 0;  // k-blocks issued by this CTA so far (the first `pre` already have their B tile)
     while (seg_next(it, sg)) {
       const int g = sg.tile / tiles_per_group;
@@ -510,6 +522,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
+        if (kb == kb0 && lane == 0) trace_mark(p, 3);
         if (ptx::elect_one()) {
           const uint32_t a_base = ptx::smem_u32(smem_a + stage * A_BYTES);
           const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::B_BYTES);
@@ -526,6 +539,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
           if (kb == kb1 - 1) ptx::umma_commit(&tfull[acc]);
         }
         __syncwarp();
+        if (kb == kb1 - 1 && lane == 0) trace_mark(p, 4);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       acc ^= 1;
@@ -554,6 +568,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       const bool partial = sg.sk && !(first && last);
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
+      if (threadIdx.x == 64) trace_mark(p, 5);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
       if (!partial) {
@@ -624,6 +639,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       if (sg.sk) ++nseg;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if (threadIdx.x == 64) trace_mark(p, 6);
     }
   }
 
@@ -634,8 +650,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+  if (threadIdx.x == 0) trace_mark(p, 7);
 }
 
+unsigned long long* g_trace = nullptr;
+int g_last_cfg[4] = {0, 0, 0, 0};   // tile width, grid, stream-K units per CTA, data-parallel tiles of the last launch
 int g_force_bn = 0;
 int g_debug = 0;
 int g_cluster = 0;    // 1 = two-CTA multicast variant for 256-wide tiles.  Opt-in: measured +8 % on the multiphase
@@ -724,6 +743,10 @@ extern "C" int sea_gemm_set_workspace(void* ws, size_t bytes) {
   return SEA_OK;
 }
 extern "C" void sea_gemm_debug_probe(int mode) { sea::g_debug = mode; }
+extern "C" void sea_gemm_debug_trace(void* dev_buf) { sea::g_trace = static_cast<unsigned long long*>(dev_buf); }
+extern "C" void sea_gemm_last_config(int* out) {
+  out[0] = sea::g_last_cfg[0]; out[1] = sea::g_last_cfg[1]; out[2] = sea::g_last_cfg[2]; out[3] = sea::g_last_cfg[3];
+}
 
 
 
@@ -817,6 +840,7 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   p.chunk_kb = (k_chunk > 0 && k_chunk < K) ? k_chunk / bk : (K + bk - 1) / bk;
   const bool chunked = p.chunk_kb < (K + bk - 1) / bk;
   p.debug = g_debug;
+  p.trace = g_trace;
   p.units_per_cta = units_per_cta;
   p.dp_tiles = units_per_cta > 0 ? dp_tiles : 0x7fffffff;
   p.sk_grid = sk_grid;
@@ -895,6 +919,8 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   }
   const int total = p.tiles_m * p.tiles_n * p.groups;
   const int nkb = (K + bk - 1) / bk;
+  g_last_cfg[0] = bn; g_last_cfg[1] = units_per_cta > 0 ? sk_grid : (total < sms ? total : sms);
+  g_last_cfg[2] = units_per_cta; g_last_cfg[3] = units_per_cta > 0 ? dp_tiles : total;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 #define SEA_GEMM_DISPATCH(AMN_, BMN_)                                   \
   do {                                                                  \

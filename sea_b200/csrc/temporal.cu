@@ -577,6 +577,9 @@ extern "C" int sea_temporal_step(const sea_temporal_desc* d, const void* cache, 
                                  int B, int pos, void* workspace, size_t workspace_bytes, sea_stream_t stream) {
   if (!d || !kv_cache || max_len <= 0 || pos < 0 || pos >= max_len) return SEA_ERR_INVALID;
   if (max_len > d->max_len) return SEA_ERR_UNSUPPORTED;
+  // tril(diagonal = src_len > 0) lets a query see src_len FUTURE keys (models/base_blocks.py:173,192): the prefix
+  // loop's outputs at earlier positions then change as the sequence grows, and no key/value cache reproduces it
+  if (d->src_len != 0) return SEA_ERR_UNSUPPORTED;
   if (kv_cache_bytes < sea_temporal_kv_cache_bytes(d, B, max_len)) return SEA_ERR_WORKSPACE;
   const int V = d->num_streams;
   if (x_batch_stride < static_cast<int64_t>(V) * d->embed_dim || (x_batch_stride % 4) ||

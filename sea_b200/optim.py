@@ -37,7 +37,8 @@ class AdamWHyper(C.Structure):
 class AdamW(torch.optim.Optimizer):
     """``AdamW(params, lr, betas, eps, weight_decay)`` — torch.optim.AdamW semantics (no amsgrad,
     no maximize).  ``engine`` (optional, a ``TemporalEngine``): lets ``step`` write the bf16 weight
-    copies in the same pass; ``grad_scale`` folds e.g. the data-parallel 1/world into the step."""
+    copies in the same pass (an engine that is NOT passed here still notices the update through the
+    parameters' version counters and re-packs its copies on its next call); ``grad_scale`` folds e.g. the data-parallel 1/world into the step."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, *,
                  engine=None, grad_scale: float = 1.0):
@@ -133,6 +134,9 @@ class AdamW(torch.optim.Optimizer):
                                          C.byref(hp), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                       "adamw_step")
             wrote_copies |= fused
+            # the kernel wrote the masters through raw pointers: tell autograd / every version-keyed cache (any
+            # TemporalEngine on these parameters, not only `self.engine`) that they changed
+            torch._C._increment_version(plist)
         if self.engine is not None:
             self.engine.after_optimizer_step(straight_copies_fresh=wrote_copies)
         return loss

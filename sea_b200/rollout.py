@@ -23,6 +23,15 @@ def _engine_of(model):
     return eng
 
 
+def _plan_key(eng):
+    """Everything a recorded graph reads through a baked-in pointer: the packed-weight cache, the live
+    parameters (``_cache_key[1]``: their data_ptrs — the train/eval flag in ``_cache_key[0]`` is NOT part of
+    the key: a plan is always recorded and replayed in inference mode) and the RoPE tables."""
+    rope = getattr(eng, "_rope", None)
+    return (eng._cache.data_ptr(), eng._cache_key[1],
+            None if rope is None else (rope[0].data_ptr(), rope[1].data_ptr()))
+
+
 class RolloutPlan:
     """The same loop with every step pre-recorded as a CUDA graph.
 
@@ -53,7 +62,9 @@ class RolloutPlan:
         ncc = lib.sea_temporal_cond_cache_bytes(C.byref(eng._desc), B)
         self.cond = torch.empty(ncc, dtype=torch.uint8, device=device)
         self.graphs, self.launches = [], []
-        self.key = (eng._cache.data_ptr(), eng._cache_key[:2])
+        # the graphs bake in device pointers: packed-weight cache, parameters (biases, norm weights), RoPE tables
+        self.key = _plan_key(eng)
+        self._rope = eng._rope          # keeps the captured tables alive for the lifetime of the graphs
         self._record()
 
     def _step(self, t: int) -> int:
@@ -84,7 +95,7 @@ class RolloutPlan:
         torch.cuda.current_stream().wait_stream(side)
 
     def valid_for(self, eng) -> bool:
-        return eng._cache is not None and self.key == (eng._cache.data_ptr(), eng._cache_key[:2])
+        return eng._cache is not None and self.key == _plan_key(eng)
 
     @torch.no_grad()
     def run(self, x0: torch.Tensor, ib: torch.Tensor) -> torch.Tensor:
@@ -118,6 +129,9 @@ class CachedRolloutPlan:
         self.eng, self.B, self.steps, self.inv = eng, B, steps, bool(time_invariant)
         eng._ensure(False)
         h = eng._h
+        if h["src_len"] != 0:
+            raise NotImplementedError("cached rollout needs src_len == 0: with tril(diagonal=src_len>0) a query "
+                                      "sees future keys and the prefix loop is not reproducible from a KV cache")
         V, E, nib = h["V"], h["E"], h["ib_num"]
         f32 = dict(dtype=torch.float32, device=device)
         self.seq = torch.zeros(B, steps + 1, V, E, **f32)
@@ -127,7 +141,9 @@ class CachedRolloutPlan:
         self.ws = torch.empty(lib.sea_temporal_workspace_bytes(d, B, 1, 0), dtype=torch.uint8, device=device)
         self.cond = torch.empty(lib.sea_temporal_cond_cache_bytes(d, B), dtype=torch.uint8, device=device)
         self.graphs, self.launches = [], []
-        self.key = (eng._cache.data_ptr(), eng._cache_key[:2])
+        # the graphs bake in device pointers: packed-weight cache, parameters (biases, norm weights), RoPE tables
+        self.key = _plan_key(eng)
+        self._rope = eng._rope          # keeps the captured tables alive for the lifetime of the graphs
         self._record()
 
     def _step(self, t: int) -> int:
@@ -151,7 +167,7 @@ class CachedRolloutPlan:
         torch.cuda.current_stream().wait_stream(side)
 
     def valid_for(self, eng) -> bool:
-        return eng._cache is not None and self.key == (eng._cache.data_ptr(), eng._cache_key[:2])
+        return eng._cache is not None and self.key == _plan_key(eng)
 
     @torch.no_grad()
     def run(self, x0: torch.Tensor, ib: torch.Tensor) -> torch.Tensor:

@@ -269,6 +269,12 @@ class TemporalEngine:
 
     def _ensure_flat_grads(self):
         live = [(n, p) for n, p in self._live_params() if p.requires_grad]
+        if not live:   # all parameters frozen (dx-only backward): nothing to bind
+            if getattr(self, "_flat_grad", None) is None or self._flat_grad.numel() != 0:
+                self._flat_grad = torch.zeros(0, dtype=torch.float32, device=next(self.module.parameters()).device)
+                self._grad_views, self._small_elems, self._mlp_start = {}, 0, 0
+                self._desc = None
+            return live
         # small / atomically accumulated gradients first, GEMM weight gradients last: after zero_grad only
         # the first region has to be zero-filled (the weight-gradient GEMMs overwrite, desc.grads_fresh)
         # ... and among those the stream-MLP weights at the very end: their gradients are final first in the
@@ -310,7 +316,7 @@ class TemporalEngine:
         for _, p in self._live_params():
             if p.requires_grad:
                 return p
-        raise RuntimeError("no trainable parameter")
+        return None   # every parameter frozen: the backward only produces dL/dx
 
     def _bind_grads(self):
         """torch semantics: grad None -> zeros; else keep accumulating.  All-None (the state after
@@ -390,11 +396,7 @@ class TemporalEngine:
             bp.ib_ln_w, bp.ib_ln_b = _P(il[1].weight), _P(il[1].bias)
             bp.ib3_w, bp.ib3_b = _P(il[3].weight), _P(il[3].bias)
 
-        b0 = m.blocks[0]
-        j0 = 1 if V > 1 else 0
-        # pair-major [hd/2, max_len, 2]: consecutive positions are contiguous (coalesced epilogue reads)
-        rope_self = torch.view_as_real(b0.attn["self"][0].freqs_cis).float().transpose(0, 1).contiguous()
-        rope_cross = torch.view_as_real(b0.cross_attn[0][j0].freqs_cis).float().transpose(0, 1).contiguous()
+        rope_self, rope_cross = self._rope_tables()
         d = S.TemporalDesc()
         d.num_layers, d.num_streams = L, V
         d.embed_dim, d.n_heads, d.hidden_dim, d.down_dim = h["E"], h["nh"], h["H"], h["Dd"]
@@ -408,6 +410,22 @@ class TemporalEngine:
         d.rope_self, d.rope_cross = rope_self.data_ptr(), rope_cross.data_ptr()
         self._desc, self._keep, self._h = d, (blocks, rope_self, rope_cross), h
         self._dev = dev
+
+    def _rope_tables(self):
+        """RoPE tables in the kernels' layout, built ONCE per (engine, source buffers): CUDA graphs recorded by
+        RolloutPlan / CachedRolloutPlan / the graphed train step hold their device pointers, so they must
+        outlive every _build (train <-> eval switches rebuild the descriptor, not these tensors)."""
+        b0 = self.module.blocks[0]
+        j0 = 1 if len(b0.proj) > 1 else 0
+        fs, fc = b0.attn["self"][0].freqs_cis, b0.cross_attn[0][j0].freqs_cis
+        key = (fs.data_ptr(), fc.data_ptr(), fs._version, fc._version, str(fs.device))
+        if getattr(self, "_rope_key", None) != key:
+            # pair-major [hd/2, max_len, 2]: consecutive positions are contiguous (coalesced epilogue reads)
+            self._rope = (torch.view_as_real(fs).float().transpose(0, 1).contiguous(),
+                          torch.view_as_real(fc).float().transpose(0, 1).contiguous())
+            self._rope_key = key
+            self.build_generation = getattr(self, "build_generation", 0) + 1
+        return self._rope
 
     def _key(self, training):
         live = self._live_params()
@@ -616,7 +634,9 @@ class TemporalEngine:
         if needs_grad:
             from .autograd import temporal_apply
             return temporal_apply(self, x, ib)
-        return self.forward_nograd(x, ib, training=False)
+        # nn.Dropout follows module.training, not the grad mode (models/base_blocks.py:47,194): a train-mode
+        # module under torch.no_grad() still drops
+        return self.forward_nograd(x, ib, training=bool(self.module.training) and self.dropout > 0.0)
 
 
 def accelerate(model: nn.Module, precision: str = "bf16") -> nn.Module:

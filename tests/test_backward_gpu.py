@@ -181,6 +181,49 @@ def test_model_gradients_match_reference(cuda, tag, ln):
     print(f"\n[temporal bwd] {tag}: loss {loss.item():.6f} vs {loss_ref.item():.6f}; worst param-grad rel err {worst:.3e}")
 
 
+@pytest.mark.parametrize("tag,ln", [("cylinder_flow", "adaln"), ("multiphase_flow", "ln")])
+def test_full_width_gradients_match_reference_golden(cuda, tag, ln):
+    """The two real configs at full width (E = 1024 / 2048: tcgen05 attention backward at head dim 128 / 256 self and
+    64 / 128 cross, K = 8192 / 16384 weight-gradient GEMMs) against the gradient goldens the UNMODIFIED reference
+    produced (oracle/make_golden.py): loss, the norm of every live parameter gradient, its projection on a seeded
+    random probe vector (error of the projection ~ ||g - g_ref||), and every small gradient element-wise."""
+    from sea_b200.temporal import TemporalModel
+    from tests.helpers import load_golden
+    g = load_golden("temporal_" + tag)
+    E, nh, scale, V, B, T, _ = [int(v) for v in g["meta"]]
+    shapes = gr.temporal_shapes(embed_dim=E, n_heads=nh, scale_ratio=scale, num_variables=V, ln_type=ln)
+    sd = gr.fill_state(shapes, SEED)
+    x, ib, tgt = gr.temporal_inputs(B, T, V, E, SEED)
+    m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(cuda).train()
+    loss = F.mse_loss(m(x.to(cuda), ib.to(cuda)), tgt.to(cuda))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(g["loss"])) < 2e-3 * float(g["loss"])
+    params = dict(m.named_parameters())
+    worst_norm = worst_probe = worst_small = 0.0
+    for name, ref_norm, ref_probe in zip(g["grad_names"], g["grad_norms"], g["grad_probes"]):
+        name = str(name)
+        got = params[name].grad
+        assert got is not None, name
+        if ref_norm < 1e-7:
+            continue
+        e_norm = abs(got.double().norm().item() - ref_norm) / ref_norm
+        pv = gr.probe_vector(name, got.shape, SEED).to(cuda).double()
+        e_probe = abs((got.double() * pv).sum().item() - ref_probe) / ref_norm
+        worst_norm, worst_probe = max(worst_norm, e_norm), max(worst_probe, e_probe)
+        assert e_norm < 3e-2 and e_probe < 8e-2, (name, e_norm, e_probe)
+        if "grad:" + name in g.files:
+            e = _rel(got.cpu(), torch.from_numpy(g["grad:" + name]))
+            worst_small = max(worst_small, e)
+            assert e < 5e-2, (name, e)
+    for name in [str(n) for n in g["dead_params"]]:
+        assert params[name].grad is None, name
+    print(f"\n[full-width bwd golden] {tag}: loss {loss.item():.6f} vs {float(g['loss']):.6f}; worst |norm| err "
+          f"{worst_norm:.2e}, worst probe err {worst_probe:.2e}, worst small-gradient rel err {worst_small:.2e}")
+
+
 def test_gradient_accumulation_semantics(cuda):
     g, sd, cfg, m, x, ib, tgt = _mirror("small_ln", "ln", cuda)
     xc, ic, tc = x.detach().to(cuda), ib.to(cuda), tgt.to(cuda)
