@@ -123,7 +123,7 @@ int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* host_problems, in
                      sea_stream_t stream);
 /* Same, but the K loop is cut into chunks of `k_chunk` elements (multiple of 64; 0 = one chunk):
  * every chunk gets a fresh TMEM accumulator and the chunk sums are added in fp32 round-to-nearest
- * by the epilogue through out_f32 (required, must not alias residual).  Used by the fp32-parity
+ * by the epilogue through out_f32 (required; it may alias residual for an in-place += ).  Used by the fp32-parity
  * mode: the tensor core's own accumulator does not round to nearest, so long K chains drift. */
 int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem* host_problems, int M, int N,
                              int K, int k_chunk, sea_stream_t stream);
@@ -145,7 +145,8 @@ void sea_gemm_force_tile_n(int bn);
 void sea_gemm_debug_probe(int mode);
 /* Tuning probe: non-NULL = CTA 0 of every later GEMM launch records %globaltimer (ns) at 8 hand-off points into
  * dev_buf[0..7]: kernel entry, prologue done, griddepcontrol.wait passed (TMA warp), first stage landed (MMA warp),
- * last MMA committed, accumulator seen by the epilogue, epilogue stores issued, kernel exit.  NULL = off. */
+ * last MMA committed, accumulator seen by the epilogue, epilogue stores issued, kernel exit.  NULL = off.  The probe
+ * points are compiled in only when gemm.cu is built with -DSEA_GEMM_TRACE (they cost ~6 % otherwise). */
 void sea_gemm_debug_trace(void* dev_buf);
 /* Tuning probe: {tile width, grid, stream-K units per CTA (0 = data-parallel), tiles} of the last launch. */
 void sea_gemm_last_config(int* out4);
@@ -319,9 +320,15 @@ typedef struct sea_ln_gelu_bwd_args {
   int64_t lddh;
   float* dweight;   /* [H] += */
   float* dbias;     /* [H] += */
+  int32_t prec;     /* SEA_PREC_BF16 (0, default): dg / h / dh are bf16.  SEA_PREC_FP32: all three are fp32 and the
+                       kernel uses erff / expf (the reference trains in fp32, train/train_temporal.py:252-258) */
 } sea_ln_gelu_bwd_args;
 int sea_ln_gelu_bwd(const sea_ln_gelu_bwd_args* args, sea_stream_t stream);
 int sea_ln_gelu_bwd_group(int n, const sea_ln_gelu_bwd_args* host_args, sea_stream_t stream); /* equal shapes */
+
+/* fp32-parity mode: d[m,n] *= gelu'(pre[m,n]) (exact erf form) — the GELU between the exchange attention's output
+ * projection and cross_up (models/temporal.py:185); the bf16 path fuses this into the dgrad GEMM epilogue. */
+int sea_gelu_grad_mul_f32(float* d, int64_t ldd, const float* pre, int64_t ldp, int M, int N, sea_stream_t stream);
 
 /* Backward of sea_adaln_hidden: dh [M,n] -> dw1 [n, ib_num] +=, db1 [n] +=  (ib_num <= 4). */
 int sea_adaln_hidden_bwd(const float* dh, int64_t lddh, const float* ib, int M, int ib_num,

@@ -9,6 +9,11 @@ For every Linear shape of the cylinder_flow forward at M = 32 / 320 / 960 rows:
   * the tile / grid / stream-K decision of the launch.
 
     python scripts/gemm_latency.py > gpurun_out/gemm_latency.txt
+
+The trace columns need a library built with the probe points compiled in (they are off in the product build because a
+`lane == 0` test inside the MMA warp's loop costs the uniform-datapath issue):
+    touch sea_b200/csrc/gemm.cu && NVCC_APPEND_FLAGS=-DSEA_GEMM_TRACE python -c "import __graft_entry__ as g; g.build()"
+Result of this round: profiles/r2_gemm_latency.md.
 """
 import ctypes as C
 import os

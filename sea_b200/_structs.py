@@ -100,7 +100,7 @@ class LnGeluBwdArgs(C.Structure):
     _fields_ = [("dg", C.c_void_p), ("lddg", C.c_int64), ("h", C.c_void_p), ("ldh", C.c_int64),
                 ("stats", C.c_void_p), ("M", C.c_int32), ("H", C.c_int32), ("weight", C.c_void_p),
                 ("bias", C.c_void_p), ("dh", C.c_void_p), ("lddh", C.c_int64),
-                ("dweight", C.c_void_p), ("dbias", C.c_void_p)]
+                ("dweight", C.c_void_p), ("dbias", C.c_void_p), ("prec", C.c_int32)]
 
 
 class AttnBwdArgs(C.Structure):

@@ -470,6 +470,74 @@ __global__ void __launch_bounds__(256) tipi_bwd_g_kernel(const TipiBwdDev a) {
   }
 }
 
+// ---------------------------------------------------------- fp32-parity mode (precision="fp32")
+// The reference trains in fp32 (train/train_temporal.py:252-258, no AMP).  These are the accurate, plain
+// counterparts of the bf16 kernels above: fp32 I/O, erff / expf (no MUFU approximations); speed is secondary.
+__global__ void __launch_bounds__(256) ln_gelu_bwd_f32_kernel(const float* __restrict__ dg, long long lddg,
+                                                              const float* __restrict__ h, long long ldh,
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ weight,
+                                                              const float* __restrict__ bias, float* __restrict__ dh,
+                                                              long long lddh, float* __restrict__ dweight,
+                                                              float* __restrict__ dbias, int M, int H, int rows_per_cta) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  extern __shared__ float acc32[];   // [2][H]; column c is only ever touched by thread c % 256
+  __shared__ float red[2][8];
+  __shared__ float bc[2];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * H; i += 256) acc32[i] = 0.f;
+  const int row_begin = blockIdx.x * rows_per_cta, row_end = min(M, row_begin + rows_per_cta);
+  const float inv_h = 1.0f / H;
+  for (int m = row_begin; m < row_end; ++m) {
+    const float mean = stats[2 * m], rstd = stats[2 * m + 1];
+    const float* hr = h + static_cast<long long>(m) * ldh;
+    const float* gr = dg + static_cast<long long>(m) * lddg;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = tid; c < H; c += 256) {
+      const float xhat = (hr[c] - mean) * rstd;
+      const float dgu = gr[c] * ptx::gelu_erf_grad(xhat * weight[c] + bias[c]);
+      acc32[c] += dgu * xhat;
+      acc32[H + c] += dgu;
+      const float dxh = dgu * weight[c];
+      s1 += dxh;
+      s2 += dxh * xhat;
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = s2; }
+    __syncthreads();
+    if (tid < 32) {
+      float t1 = tid < 8 ? red[0][tid] : 0.f, t2 = tid < 8 ? red[1][tid] : 0.f;
+      t1 = warp_sum(t1); t2 = warp_sum(t2);
+      if (tid == 0) { bc[0] = t1 * inv_h; bc[1] = t2 * inv_h; }
+    }
+    __syncthreads();
+    const float c1 = bc[0], c2 = bc[1];
+    float* dr = dh + static_cast<long long>(m) * lddh;
+    for (int c = tid; c < H; c += 256) {
+      const float xhat = (hr[c] - mean) * rstd;
+      const float dxh = gr[c] * ptx::gelu_erf_grad(xhat * weight[c] + bias[c]) * weight[c];
+      dr[c] = rstd * (dxh - c1 - xhat * c2);
+    }
+    __syncthreads();
+  }
+  for (int c = tid; c < H; c += 256) {
+    atomicAdd(dweight + c, acc32[c]);
+    atomicAdd(dbias + c, acc32[H + c]);
+  }
+}
+
+// d[m, n] *= gelu'(pre[m, n])   (the exchange branch: cross_up(GELU(projection(.))), models/temporal.py:185)
+__global__ void __launch_bounds__(256) gelu_grad_mul_f32_kernel(float* __restrict__ d, long long ldd,
+                                                                const float* __restrict__ pre, long long ldp, int M, int N) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= static_cast<long long>(M) * N) return;
+  const int m = static_cast<int>(i / N), n = static_cast<int>(i - static_cast<long long>(m) * N);
+  d[m * ldd + n] *= ptx::gelu_erf_grad(pre[m * ldp + n]);
+}
+
 }  // namespace
 }  // namespace sea
 
@@ -537,6 +605,28 @@ extern "C" int sea_norm_bwd(const sea_norm_bwd_args* a, sea_stream_t stream) {
 
 extern "C" int sea_ln_gelu_bwd_group(int n, const sea_ln_gelu_bwd_args* a, sea_stream_t stream) {
   if (!a || n < 1 || n > SEA_MAX_STREAMS) return SEA_ERR_INVALID;
+  if (a->prec == SEA_PREC_FP32) {   // parity mode: fp32 dg / h / dh, one plain launch per item
+    for (int i = 0; i < n; ++i) {
+      const sea_ln_gelu_bwd_args* x = &a[i];
+      if (!x->dg || !x->h || !x->stats || !x->weight || !x->bias || !x->dh || !x->dweight || !x->dbias || x->prec != SEA_PREC_FP32)
+        return SEA_ERR_INVALID;
+      if (x->M <= 0 || x->H <= 0 || x->H > 24576) return SEA_ERR_UNSUPPORTED;
+      int rows = (x->M + 147) / 148;
+      const size_t smem = sizeof(float) * 2 * x->H;
+      static bool attr32[16] = {};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev < 16 && !attr32[dev]) {
+        SEA_CUDA_OK(cudaFuncSetAttribute(ln_gelu_bwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 24576 * 4));
+        attr32[dev] = true;
+      }
+      SEA_LAUNCH(ln_gelu_bwd_f32_kernel, (x->M + rows - 1) / rows, 256, smem, reinterpret_cast<cudaStream_t>(stream),
+                 static_cast<const float*>(x->dg), static_cast<long long>(x->lddg), static_cast<const float*>(x->h),
+                 static_cast<long long>(x->ldh), x->stats, x->weight, x->bias, static_cast<float*>(x->dh),
+                 static_cast<long long>(x->lddh), x->dweight, x->dbias, x->M, x->H, rows);
+    }
+    return static_cast<int>(cudaGetLastError());
+  }
   LnGeluBwdGroup g;
   for (int i = 0; i < n; ++i) {
     const sea_ln_gelu_bwd_args* x = &a[i];
@@ -562,6 +652,14 @@ extern "C" int sea_ln_gelu_bwd_group(int n, const sea_ln_gelu_bwd_args* a, sea_s
   }
   SEA_LAUNCH((ln_gelu_bwd_kernel<0>), grid, kLgbThreads, smem, reinterpret_cast<cudaStream_t>(stream), g, a->lddg, a->ldh,
              a->lddh, a->M, a->H, rows);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_gelu_grad_mul_f32(float* d, int64_t ldd, const float* pre, int64_t ldp, int M, int N, sea_stream_t stream) {
+  if (!d || !pre || M <= 0 || N <= 0) return SEA_ERR_INVALID;
+  const long long work = static_cast<long long>(M) * N;
+  SEA_LAUNCH(gelu_grad_mul_f32_kernel, static_cast<unsigned>((work + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream),
+             d, static_cast<long long>(ldd), pre, static_cast<long long>(ldp), M, N);
   return static_cast<int>(cudaGetLastError());
 }
 

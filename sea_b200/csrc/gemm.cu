@@ -66,12 +66,18 @@ struct alignas(64) GemmParams {
   unsigned long long* trace;  // tuning probe (sea_gemm_debug_trace): CTA 0 records %globaltimer at 8 hand-off points
 };
 
+// Compiled in only with -DSEA_GEMM_TRACE (scripts/gemm_latency.py documents the build): a `lane == 0` test inside the
+// TMA / MMA warps' loops costs the uniform-datapath issue of UTMALDG / UTCHMMA (measured: +6 % on the whole rollout).
 __device__ __forceinline__ void trace_mark(const GemmParams& p, int slot) {
+#ifdef SEA_GEMM_TRACE
   if (p.trace != nullptr && blockIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.trace[slot] = t;
   }
+#else
+  (void)p; (void)slot;
+#endif
 }
 
 // BK = K extent of one pipeline stage.  The issuing thread pays a fixed ~390 cycles per stage
@@ -860,7 +866,9 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
       return SEA_ERR_INVALID;
     if (e.out_f32 == nullptr && e.out_bf16 == nullptr && e.out_pre_bf16 == nullptr)
       return SEA_ERR_INVALID;
-    if (chunked && (e.out_f32 == nullptr || e.out_f32 == e.residual)) return SEA_ERR_INVALID;
+    // chunked: out_f32 holds the running sum.  residual == out_f32 (in-place accumulate, e.g. dW += ...) is fine: the
+    // thread that owns an element reads the residual in the first chunk's epilogue and is the only one to write it
+    if (chunked && e.out_f32 == nullptr) return SEA_ERR_INVALID;
     if (e.out_f32 && ((e.ld_out_f32 % 4) || (reinterpret_cast<uintptr_t>(e.out_f32) & 15)))
       return SEA_ERR_INVALID;
     if (e.out_bf16 && ((e.ld_out_bf16 % 8) || (reinterpret_cast<uintptr_t>(e.out_bf16) & 15)))

@@ -78,18 +78,20 @@ struct Tape {
 };
 
 // Gradient buffers of the backward pass (one set, reused across layers; bf16 mode only).
+// "b" twins are the bf16 tensor-core operands (NULL in SEA_PREC_FP32, where the fp32 buffer is the operand);
+// void* buffers exist in one copy, in the mode's activation dtype (bf16 / fp32).
 struct BwdStream {
   float* dxout; bf16* dxoutb;   // gradient at the block output / previous layer's input
   float* dx3; bf16* dx3b;       // at x3 = x2 + MLP
-  bf16* dg; bf16* dh;           // at GELU output / at the MLP hidden pre-LN   [M,H]
+  void* dg; void* dh;           // at GELU output / at the MLP hidden pre-LN   [M,H]
   float* dn2;                   // at Norm_{i,2} output
   float* dx2; bf16* dx2b;       // at x2 = x_post + TIPI
   float* dxp; bf16* dxpb;       // at x_post when the exchanged stream feeds later streams
-  bf16 *dp, *da, *dq, *dkv;     // exchange branch: pre-GELU, attention out, q, k|v
+  void *dp, *da, *dq, *dkv;     // exchange branch: pre-GELU, attention out, q, k|v
   float *dnpre, *dnpost;        // at ln_cross outputs (accumulated over consumers)
   float* ddn; bf16* ddnb;       // at cross_down outputs
   float* dx1; bf16* dx1b;       // at x1 (after self-attention)
-  bf16* dao; bf16* dqkv;        // self-attention: at attention output, at q|k|v (RoPE undone)
+  void* dao; void* dqkv;        // self-attention: at attention output, at q|k|v (RoPE undone)
   float* dn0;                   // at Norm_{i,0} output
   float *dcond0, *dcond2, *dcondc, *dcondF;  // AdaLN: at the cond_mlp outputs
 };
@@ -98,6 +100,7 @@ struct BwdTape {
   bf16* dcb[SEA_MAX_STREAMS];    // bf16 copy of dcond
   float* dhid[SEA_MAX_STREAMS];  // gradient at SiLU output
   float* delta;                  // attention backward scratch
+  bf16 *pack1, *pack2;           // SEA_PREC_FP32: split-operand scratch of the 3x-bf16 backward GEMMs
 };
 void layout_bwd_tape(const sea_temporal_desc* d, int B, int T, Arena& ar, BwdTape& t);
 

@@ -181,6 +181,8 @@ def ln_gelu_bwd(dg, h, stats, weight, bias):
     a.dg, a.lddg, a.h, a.ldh, a.stats = dg.data_ptr(), dg.stride(0), h.data_ptr(), h.stride(0), stats.data_ptr()
     a.M, a.H, a.weight, a.bias = M, H, weight.data_ptr(), bias.data_ptr()
     a.dh, a.lddh, a.dweight, a.dbias = dh.data_ptr(), H, dw.data_ptr(), db.data_ptr()
+    a.prec = 1 if h.dtype == torch.float32 else 0      # fp32-parity variant: dg / h / dh all fp32
+    assert dg.dtype == h.dtype
     check(lib.sea_ln_gelu_bwd(C.byref(a), _stream()), "ln_gelu_bwd")
     return dh, dw, db
 
@@ -190,7 +192,10 @@ def ln_gelu_fwd_with_stats(h, weight, bias):
     g = torch.empty_like(h)
     st = torch.empty(M, 2, device=h.device)
     a = S.LnGeluArgs()
-    a.h_bf16, a.g_bf16 = h.data_ptr(), g.data_ptr()
+    if h.dtype == torch.float32:
+        a.h_f32, a.g_f32 = h.data_ptr(), g.data_ptr()
+    else:
+        a.h_bf16, a.g_bf16 = h.data_ptr(), g.data_ptr()
     a.ldh, a.ldg, a.M, a.H = h.stride(0), g.stride(0), M, H
     a.weight, a.bias, a.stats = weight.data_ptr(), bias.data_ptr(), st.data_ptr()
     check(lib.sea_ln_gelu_fwd(C.byref(a), _stream()), "ln_gelu_fwd")

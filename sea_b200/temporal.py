@@ -268,13 +268,9 @@ class TemporalEngine:
         return p.dim() == 2 and "ib.layers" not in name and "cond_mlp.0." not in name
 
     def _ensure_flat_grads(self):
-        live = [(n, p) for n, p in self._live_params() if p.requires_grad]
-        if not live:   # all parameters frozen (dx-only backward): nothing to bind
-            if getattr(self, "_flat_grad", None) is None or self._flat_grad.numel() != 0:
-                self._flat_grad = torch.zeros(0, dtype=torch.float32, device=next(self.module.parameters()).device)
-                self._grad_views, self._small_elems, self._mlp_start = {}, 0, 0
-                self._desc = None
-            return live
+        # every live parameter gets a slot, frozen or not: the backward kernels always have a destination (a frozen
+        # parameter's slot is scratch that is never bound to .grad), so partially / fully frozen models just work
+        live = list(self._live_params())
         # small / atomically accumulated gradients first, GEMM weight gradients last: after zero_grad only
         # the first region has to be zero-filled (the weight-gradient GEMMs overwrite, desc.grads_fresh)
         # ... and among those the stream-MLP weights at the very end: their gradients are final first in the
@@ -321,7 +317,7 @@ class TemporalEngine:
     def _bind_grads(self):
         """torch semantics: grad None -> zeros; else keep accumulating.  All-None (the state after
         optimizer.zero_grad()) costs a single memset."""
-        live = self._ensure_flat_grads()
+        live = [(n, p) for n, p in self._ensure_flat_grads() if p.requires_grad]
         self._grads_fresh = False
         if all(p.grad is None for _, p in live):
             # zero_grad(set_to_none=True): only the atomically accumulated gradients need zeros; the
@@ -492,8 +488,8 @@ class TemporalEngine:
 
     @torch.no_grad()
     def backward(self, x, ib, dy, ws, need_dx: bool, dropout_seed: int = 0, dropout_p: float = 0.0):
-        if self.precision != "bf16":
-            raise NotImplementedError("sea_b200 backward runs in bf16 mode (fp32 split mode is forward-only)")
+        if self.precision != "bf16" and dropout_p > 0.0:
+            raise NotImplementedError("sea_b200: train-mode dropout runs in bf16 mode only")
         self._ensure(True)
         self._bind_grads()
         B, T, V, E = x.shape

@@ -63,6 +63,25 @@ def test_ln_gelu_bwd(cuda, H):
     assert _rel(dw, w.grad) < 1e-3 and _rel(db, b.grad) < 1e-3
 
 
+@pytest.mark.parametrize("H", [256, 8192, 16384])
+def test_ln_gelu_bwd_fp32(cuda, H):
+    """fp32-parity variant (fp32 dg / h / dh, erff / expf) against autograd in float64."""
+    from sea_b200 import ops
+    M = 77
+    g = torch.Generator(device="cuda").manual_seed(H + 1)
+    h = torch.randn(M, H, device=cuda, generator=g) * 1.5
+    w = (1 + 0.1 * torch.randn(H, device=cuda, generator=g))
+    b = (0.1 * torch.randn(H, device=cuda, generator=g))
+    dg = torch.randn(M, H, device=cuda, generator=g)
+    hd_, wd, bd = (t.double().requires_grad_(True) for t in (h, w, b))
+    (F.gelu(F.layer_norm(hd_, (H,), wd, bd, 1e-5)) * dg.double()).sum().backward()
+    _, st = ops.ln_gelu_fwd_with_stats(h, w, b)
+    dh, dw, db = ops.ln_gelu_bwd(dg, h, st, w, b)
+    assert dh.dtype == torch.float32
+    assert _rel(dh, hd_.grad) < 2e-5
+    assert _rel(dw, wd.grad) < 2e-5 and _rel(db, bd.grad) < 2e-5
+
+
 @pytest.mark.parametrize("hd", [32, 64, 128, 256])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,T,src_len", [(2, 77, 0), (1, 200, 0), (2, 33, 2)])

@@ -232,3 +232,48 @@ def test_gemm_cluster_multicast_variant(cuda, M, N, K, groups, mn):
     Bm = b[0].double() if mn & 2 else b[0].double().t()
     ref = A @ Bm + bias.double()
     assert ((outs[1][0].double() - ref).norm() / ref.norm()).item() < 1e-5
+
+
+def test_gemm_chunked_inplace_accumulate(cuda):
+    """fp32-mode weight gradients: out_f32 aliases residual (dW += ...) with the K loop cut into 512-column chunks."""
+    from sea_b200 import ops
+    M, N, K = 300, 264, 2000
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    b = (torch.randn(N, K, device=cuda, generator=g) * 0.05).bfloat16()
+    acc = torch.randn(M, N, device=cuda, generator=g)
+    want = acc.double() + a.double() @ b.double().t()
+    ops.gemm_bf16_tn([ops.gemm_problem(a, b, residual=acc, out_f32=acc)], M, N, K, k_chunk=512)
+    torch.cuda.synchronize()
+    assert (acc.double() - want).abs().max().item() < 2e-4 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(798, 1024, 512), (199, 3072, 1024)])
+def test_split_wgrad_is_fp32_accurate(cuda, M, N, K):
+    """dW = dy^T a through the 3x-bf16 split (transposed split packs, contraction over the padded row count, fresh
+    accumulator every 512 columns): fp32-accurate against a float64 product (the recipe of linear_bwd_fp32)."""
+    import ctypes as C
+    from sea_b200 import _structs as S, check, lib, ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    dy = torch.randn(M, N, device=cuda, generator=g)
+    a = torch.randn(M, K, device=cuda, generator=g)
+    Mp = (M + 7) // 8 * 8
+    P1 = torch.zeros(N, 6 * Mp, device=cuda, dtype=torch.bfloat16)
+    P2 = torch.zeros(K, 6 * Mp, device=cuda, dtype=torch.bfloat16)
+
+    def pack(src, dst, split):
+        pa = S.PackArgs()
+        pa.src_f32, pa.ld, pa.R, pa.C = src.data_ptr(), src.stride(0), src.shape[0], src.shape[1]
+        pa.transpose, pa.split, pa.act, pa.split_inner = 1, split, 0, Mp
+        pa.dst, pa.ld_dst = dst.data_ptr(), dst.stride(0)
+        check(lib.sea_pack_operand(C.byref(pa), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pack")
+
+    pack(dy, P1, 1)
+    pack(a, P2, 2)
+    dW = torch.empty(N, K, device=cuda)
+    ops.gemm_bf16_tn([ops.gemm_problem(P1, P2, out_f32=dW)], N, K, 6 * Mp, k_chunk=512)
+    torch.cuda.synchronize()
+    want = dy.double().t() @ a.double()
+    rel = ((dW.double() - want).norm() / want.norm()).item()
+    print(f"\n[split wgrad] M={M} N={N} K={K}: rel {rel:.2e}")
+    assert rel < 5e-6
