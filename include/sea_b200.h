@@ -449,7 +449,7 @@ typedef struct sea_adamw_chunk {
   float* v;
   void* p_bf16;
   int32_t n;
-  int32_t reserved;
+  int32_t g_is_bf16; /* 1: `g` points at bf16 values (an averaged bf16 gradient bucket); 0: fp32 */
 } sea_adamw_chunk;
 typedef struct sea_adamw_hyper {
   float lr, beta1, beta2, eps, weight_decay;
@@ -461,6 +461,15 @@ typedef struct sea_adamw_hyper {
 } sea_adamw_hyper;
 int sea_adamw_step(const sea_adamw_chunk* chunks_dev, int num_chunks, const sea_adamw_hyper* hp,
                    sea_stream_t stream);
+/* Same update with the step count in DEVICE memory (CUDA-graph capturable: nothing step-dependent is baked into the
+ * launch): *step_dev (fp32, as torch keeps it) is incremented first, then bias_corr1 = 1 - beta1^t and
+ * bias_corr2_sqrt = sqrt(1 - beta2^t) are evaluated on the device; hp->bias_corr* are ignored. */
+int sea_adamw_step_dev(const sea_adamw_chunk* chunks_dev, int num_chunks, const sea_adamw_hyper* hp, float* step_dev,
+                       sea_stream_t stream);
+/* dst[i] = bf16(src[i]) / dst[i] = fp32(src[i]) over n contiguous elements (gradient-bucket compression of the
+ * small, reduction-produced gradients; decompression of an averaged bf16 bucket back into param.grad). */
+int sea_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, sea_stream_t stream);
+int sea_cast_bf16_f32(const void* src_bf16, float* dst, int64_t n, sea_stream_t stream);
 
 /* ------------------------------------------------------------------ temporal model -----------
  * Whole-model executor for TemporalModel with exchange_mode='sea', ib_scale_mode='mlp',
@@ -471,6 +480,7 @@ int sea_adamw_step(const sea_adamw_chunk* chunks_dev, int num_chunks, const sea_
  * The descriptor mirrors the reference module tree: every field is the fp32 master parameter
  * (`p`, the nn.Parameter's storage) and, for training, where its gradient goes (`g`, may be NULL).
  * Dead parameters of the reference do not appear. */
+#define SEA_BWD_GROUPS 5
 typedef struct sea_param {
   const float* p;
   float* g;
@@ -530,6 +540,19 @@ typedef struct sea_temporal_desc {
                               Every other gradient (biases, norm / TIPI / cond_mlp.0 parameters) still
                               accumulates and must have been zeroed by the caller.  0 = accumulate everywhere. */
   int32_t reserved1;
+  /* ---- data-parallel training (sea_temporal_backward only; all optional, zero = off) ----
+   * Every `g` of this descriptor points into ONE flat fp32 buffer starting at grad_f32_base (the all-reduce
+   * bucket).  With grad_bf16 set, each weight-gradient GEMM also stores the bf16 rounding of the value it leaves
+   * in its fp32 destination at the same element offset of grad_bf16 (no extra pass: second store of the epilogue),
+   * so the gradient exchange can move half the bytes; gradients produced by reductions (biases, norm / TIPI /
+   * cond_mlp.0 parameters) are NOT mirrored — the caller casts that (small) region itself (sea_cast_f32_bf16).
+   * bwd_events[k] (cudaEvent_t or NULL) is recorded on the stream once the parameter gradients of group k are
+   * final, so the exchange of that bucket can start while the rest of the backward runs:
+   *   0 final norms ln.{i} | 1 stream MLP + proj | 2 ln.exp.{i}.2 + TIPI | 3 exchange (cross_*, ln_cross) |
+   *   4 self-attention + ln.exp.{i}.0 (= end of the backward).  Groups 1-4 are recorded in the LAST processed layer. */
+  const float* grad_f32_base;
+  void* grad_bf16;
+  void* bwd_events[SEA_BWD_GROUPS];
 } sea_temporal_desc;
 
 /* Packed low-precision copies of the weights (bf16, fused QKV / KV, optional transposes for the
@@ -583,12 +606,6 @@ int sea_temporal_backward(const sea_temporal_desc* d, const void* cache, const f
                           void* workspace, size_t workspace_bytes, sea_stream_t stream);
 /* Number of kernels the last forward / backward call on this thread launched. */
 int sea_last_launch_count(void);
-/* Data-parallel overlap hook (the gradient all-reduce overlaps the tail of the backward).  The NEXT
- * sea_temporal_backward of this process records `cuda_event` (a cudaEvent_t) on its stream right after the
- * last stream-MLP weight gradient (mlp.{i}.layers.{0,3}.weight of every layer: 2/3 of the gradient bytes of
- * multiphase_flow) is final, then forgets it.  `_pending` = 1 while an armed event has not been consumed. */
-void sea_temporal_backward_milestone(void* cuda_event);
-int sea_temporal_backward_milestone_pending(void);
 /* cudaEvent_t plumbing for hosts without a runtime binding: create (timing disabled) / destroy / make `stream`
  * wait for the event.  Return 0 or a cudaError_t. */
 int sea_event_create(void** out_event);

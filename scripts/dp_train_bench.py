@@ -73,7 +73,7 @@ eng = m.engine()
 flat = eng.flat_grad()
 if rank == 0:
     print(json.dumps({"config": args.config, "n_gpus": world, "per_gpu_batch": b, "T": T,
-                      "grad_bytes": flat.numel() * 4, "overlapped_bucket_bytes": (flat.numel() - eng.mlp_grad_offset()) * 4,
+                      "grad_bytes": flat.numel() * 4, **parallel.TrainStep(m, opt, F.mse_loss).info(),
                       "ms_step_no_exchange": ms_local, "ms_step_exchange_after_backward": ms_seq,
                       "ms_step_exchange_overlapped": ms_ovl,
                       "samples_per_sec_overlapped": world * b / (ms_ovl / 1e3)}))

@@ -23,6 +23,11 @@ rank, world, local = parallel.init_from_env()
 dev = torch.device("cuda", local)
 torch.cuda.set_device(dev)
 E, nh, scale, V, T, steps = 128, 2, 2, 2, 12, 30
+LR = 1e-3
+if os.environ.get("SEA_DP_WIDTH", "small") == "full":    # cylinder_flow / multiphase_flow widths (short T: the oracle runs on CPU)
+    LR = 1e-4 if os.environ.get("SEA_LN", "adaln") == "adaln" else 8e-5        # configs/*.py:147
+    E, nh, scale, T, steps = (1024 if os.environ.get("SEA_LN", "adaln") == "adaln" else 2048), 8, 8, 16, 12
+FUSED = os.environ.get("SEA_DP_OPT", "torch") == "fused"   # fused AdamW stepping from the averaged bf16 bucket
 Bg = 2 * world                                            # global batch, 2 trajectories per rank
 ln = os.environ.get("SEA_LN", "adaln")
 OVERLAP = os.environ.get("SEA_DP_OVERLAP", "1") == "1"   # force the overlapped exchange (auto would skip it at this size)
@@ -31,7 +36,11 @@ x, ib, tgt = gr.temporal_inputs(Bg, T, V, E, 11)
 m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln)
 m.load_state_dict(sd, strict=False)
 m = m.to(dev).train()
-opt = torch.optim.AdamW(m.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+if FUSED:
+    from sea_b200.optim import AdamW
+    opt = AdamW(m.parameters(), lr=LR, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, engine=m.engine())
+else:
+    opt = torch.optim.AdamW(m.parameters(), lr=LR, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
 xs, ibs, ts = (parallel.shard_trajectories(t, rank, world).to(dev) for t in (x, ib, tgt))
 losses = []
 for _ in range(steps):
@@ -50,7 +59,7 @@ drift = (w - ref).abs().max().item()
 ok = True
 if rank == 0:
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    o = torch.optim.AdamW(list(leaves.values()), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    o = torch.optim.AdamW(list(leaves.values()), lr=LR, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
     ref_losses = []
     for _ in range(steps):
         o.zero_grad()

@@ -34,6 +34,9 @@ class BlockParams(C.Structure):
                 ("ib3_w", Param), ("ib3_b", Param)]
 
 
+BWD_GROUPS = 5
+
+
 class TemporalDesc(C.Structure):
     _fields_ = [("num_layers", C.c_int32), ("num_streams", C.c_int32),
                 ("embed_dim", C.c_int32), ("n_heads", C.c_int32), ("hidden_dim", C.c_int32),
@@ -45,7 +48,8 @@ class TemporalDesc(C.Structure):
                 ("final_ln", NormParams * MAX_STREAMS),
                 ("rope_self", C.c_void_p), ("rope_cross", C.c_void_p),
                 ("dropout_p", C.c_float), ("reserved2", C.c_uint32), ("dropout_seed", C.c_uint64),
-                ("grads_fresh", C.c_int32), ("reserved1", C.c_int32)]
+                ("grads_fresh", C.c_int32), ("reserved1", C.c_int32),
+                ("grad_f32_base", C.c_void_p), ("grad_bf16", C.c_void_p), ("bwd_events", C.c_void_p * BWD_GROUPS)]
 
 
 class NormArgs(C.Structure):

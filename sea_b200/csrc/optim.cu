@@ -1,7 +1,7 @@
 // Fused multi-tensor AdamW.  Replaces torch.optim.AdamW.step as configured by
 // utils/train_utils.py:33-39 (betas (0.9, 0.999), eps 1e-8, decoupled weight decay) for the temporal
 // model's parameters: ONE launch walks a device-resident chunk table, reads p, g, m, v once, writes
-// p, m, v once (28 B / parameter = the HBM floor) and, where the parameter is a tensor-core operand,
+// p, m, v once (28 B / parameter = the HBM floor; 26 B when g is an averaged bf16 gradient bucket) and, where the parameter is a tensor-core operand,
 // drops the refreshed bf16 copy straight into the engine's packed-weight cache (+2 B) so that no
 // separate repack pass has to re-read the fp32 masters.
 #include <cuda_bf16.h>
@@ -25,20 +25,40 @@ __device__ __forceinline__ void adamw1(float& p, float g, float& m, float& v, co
   p -= (h.lr / h.bias_corr1) * (m / denom);
 }
 
-__global__ void __launch_bounds__(kThreads) adamw_kernel(const sea_adamw_chunk* __restrict__ chunks,
-                                                         const sea_adamw_hyper h) {
+__global__ void adamw_tick_kernel(float* step) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
+  *step += 1.0f;
+}
+
+__global__ void __launch_bounds__(kThreads) adamw_kernel(const sea_adamw_chunk* __restrict__ chunks,
+                                                         sea_adamw_hyper h, const float* __restrict__ step_dev) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  if (step_dev != nullptr) {   // graph-capturable variant: the step count lives on the device
+    const float t = *step_dev;
+    h.bias_corr1 = 1.0f - powf(h.beta1, t);
+    h.bias_corr2_sqrt = sqrtf(1.0f - powf(h.beta2, t));
+  }
   const sea_adamw_chunk c = chunks[blockIdx.x];
   const int n4 = c.n >> 2;
   float4* p4 = reinterpret_cast<float4*>(c.p);
   const float4* g4 = reinterpret_cast<const float4*>(c.g);
+  const uint2* gh4 = reinterpret_cast<const uint2*>(c.g);
   float4* m4 = reinterpret_cast<float4*>(c.m);
   float4* v4 = reinterpret_cast<float4*>(c.v);
   uint2* b4 = reinterpret_cast<uint2*>(c.p_bf16);
   for (int i = threadIdx.x; i < n4; i += kThreads) {
     float4 p = p4[i], m = m4[i], v = v4[i];
-    const float4 g = __ldcs(g4 + i);
+    float4 g;
+    if (c.g_is_bf16) {
+      const uint2 r = __ldcs(gh4 + i);
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+      g = make_float4(lo.x, lo.y, hi.x, hi.y);
+    } else {
+      g = __ldcs(g4 + i);
+    }
     adamw1(p.x, g.x, m.x, v.x, h);
     adamw1(p.y, g.y, m.y, v.y, h);
     adamw1(p.z, g.z, m.z, v.z, h);
@@ -48,14 +68,72 @@ __global__ void __launch_bounds__(kThreads) adamw_kernel(const sea_adamw_chunk* 
   }
   for (int i = (n4 << 2) + threadIdx.x; i < c.n; i += kThreads) {
     float p = c.p[i], m = c.m[i], v = c.v[i];
-    adamw1(p, c.g[i], m, v, h);
+    const float g = c.g_is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(c.g)[i]) : c.g[i];
+    adamw1(p, g, m, v, h);
     c.p[i] = p; c.m[i] = m; c.v[i] = v;
     if (c.p_bf16 != nullptr) static_cast<__nv_bfloat16*>(c.p_bf16)[i] = __float2bfloat16_rn(p);
   }
 }
 
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                           long long n) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const long long i4 = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i4);
+    *reinterpret_cast<uint2*>(dst + i4) = make_uint2(ptx::pack_bf16(v.x, v.y), ptx::pack_bf16(v.z, v.w));
+  } else {
+    for (long long i = i4; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+                                                           long long n) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const long long i4 = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const uint2 r = *reinterpret_cast<const uint2*>(src + i4);
+    const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+    const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+    *reinterpret_cast<float4*>(dst + i4) = make_float4(lo.x, lo.y, hi.x, hi.y);
+  } else {
+    for (long long i = i4; i < n; ++i) dst[i] = __bfloat162float(src[i]);
+  }
+}
+
 }  // namespace
 }  // namespace sea
+
+extern "C" int sea_cast_f32_bf16(const float* src, void* dst, int64_t n, sea_stream_t stream) {
+  using namespace sea;
+  if (!src || !dst || n < 0 || ((reinterpret_cast<uintptr_t>(src) & 15) != 0) || ((reinterpret_cast<uintptr_t>(dst) & 7) != 0))
+    return SEA_ERR_INVALID;
+  if (n == 0) return SEA_OK;
+  SEA_LAUNCH(cast_f32_bf16_kernel, static_cast<unsigned>((n + 1023) / 1024), 256, 0, reinterpret_cast<cudaStream_t>(stream),
+             src, static_cast<__nv_bfloat16*>(dst), static_cast<long long>(n));
+  return static_cast<int>(cudaGetLastError());
+}
+extern "C" int sea_cast_bf16_f32(const void* src, float* dst, int64_t n, sea_stream_t stream) {
+  using namespace sea;
+  if (!src || !dst || n < 0 || ((reinterpret_cast<uintptr_t>(dst) & 15) != 0) || ((reinterpret_cast<uintptr_t>(src) & 7) != 0))
+    return SEA_ERR_INVALID;
+  if (n == 0) return SEA_OK;
+  SEA_LAUNCH(cast_bf16_f32_kernel, static_cast<unsigned>((n + 1023) / 1024), 256, 0, reinterpret_cast<cudaStream_t>(stream),
+             static_cast<const __nv_bfloat16*>(src), dst, static_cast<long long>(n));
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_adamw_step_dev(const sea_adamw_chunk* chunks_dev, int num_chunks, const sea_adamw_hyper* hp,
+                                  float* step_dev, sea_stream_t stream) {
+  using namespace sea;
+  if (chunks_dev == nullptr || hp == nullptr || step_dev == nullptr || num_chunks < 0) return SEA_ERR_INVALID;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  SEA_LAUNCH(adamw_tick_kernel, 1, 1, 0, s, step_dev);
+  if (num_chunks == 0) return static_cast<int>(cudaGetLastError());
+  SEA_LAUNCH(adamw_kernel, num_chunks, kThreads, 0, s, chunks_dev, *hp, static_cast<const float*>(step_dev));
+  return static_cast<int>(cudaGetLastError());
+}
 
 extern "C" int sea_adamw_step(const sea_adamw_chunk* chunks_dev, int num_chunks, const sea_adamw_hyper* hp,
                               sea_stream_t stream) {
@@ -64,6 +142,6 @@ extern "C" int sea_adamw_step(const sea_adamw_chunk* chunks_dev, int num_chunks,
   if (num_chunks == 0) return SEA_OK;
   if (!(hp->bias_corr1 > 0.f) || !(hp->bias_corr2_sqrt > 0.f)) return SEA_ERR_INVALID;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  SEA_LAUNCH(adamw_kernel, num_chunks, kThreads, 0, s, chunks_dev, *hp);
+  SEA_LAUNCH(adamw_kernel, num_chunks, kThreads, 0, s, chunks_dev, *hp, static_cast<const float*>(nullptr));
   return static_cast<int>(cudaGetLastError());
 }

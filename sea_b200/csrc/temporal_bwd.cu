@@ -42,6 +42,16 @@ struct BCtx {
   bool fp32 = false;                  // SEA_PREC_FP32: fp32 operands / gradients, split GEMMs
   // the GEMM operand copy of a gradient / activation: its bf16 twin, or (fp32 mode) the fp32 buffer itself
   const void* op(const float* f, const bf16* h) const { return fp32 ? static_cast<const void*>(f) : static_cast<const void*>(h); }
+  bf16* gb16 = nullptr;               // desc->grad_bf16: bf16 twin of the flat gradient buffer (data-parallel buckets)
+  const float* gf32 = nullptr;
+  bf16* twin_of(const float* g) const {   // where the bf16 copy of gradient element g lives (NULL: not mirrored)
+    return (gb16 != nullptr && g != nullptr && g >= gf32) ? gb16 + (g - gf32) : nullptr;
+  }
+  cudaError_t mark(int group) const { // "parameter gradients of `group` are final" (desc->bwd_events)
+    void* ev = c.d->bwd_events[group];
+    if (ev == nullptr) return cudaSuccess;
+    return cudaEventRecord(static_cast<cudaEvent_t>(ev), c.s);
+  }
   bool fresh = false;                 // desc->grads_fresh: first wgrad contribution overwrites
   std::vector<const float*> touched;  // weight gradients already written by this call
   sea_stream_t st() const { return reinterpret_cast<sea_stream_t>(c.s); }
@@ -201,6 +211,9 @@ int linear_bwd(BCtx& b, int n, LinB* L) {
         for (const float* t : b.touched) first_touch = first_touch && t != dW;
         if (first_touch) { b.touched.push_back(dW); }
         else { p.epi.residual = dW; p.epi.ld_residual = K; }
+        // data-parallel bf16 bucket: the value this launch leaves in dW, rounded, at the same offset of the twin
+        // (the last contribution to a weight writes its final value)
+        if (bf16* tw = b.twin_of(dW)) { p.epi.out_pre_bf16 = tw; p.epi.ld_out_pre_bf16 = K; }
       }
       SEA_TRY(gemm(b, n, probs, Np, K, M));
       const void* src[SEA_MAX_STREAMS]; float* dbs[SEA_MAX_STREAMS];
@@ -385,11 +398,6 @@ void layout_bwd_tape(const sea_temporal_desc* d, int B, int T, Arena& ar, BwdTap
 
 using namespace sea;
 
-// process-wide, not thread-local: autograd runs the backward on its own device thread
-namespace sea { std::atomic<void*> g_bwd_milestone{nullptr}; }
-extern "C" void sea_temporal_backward_milestone(void* ev) { sea::g_bwd_milestone.store(ev); }
-extern "C" int sea_temporal_backward_milestone_pending(void) { return sea::g_bwd_milestone.load() != nullptr; }
-
 extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cache, const float* x,
                                      const float* ib, const float* dy, float* dx, int B, int T,
                                      void* workspace, size_t workspace_bytes, sea_stream_t stream) {
@@ -419,6 +427,8 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
   b.c.Mc = b.c.M; b.c.ld_ib = d->ib_num; b.c.cond_div = 1;
   b.ib = ib; b.bt = &bt;
   b.fresh = d->grads_fresh != 0;
+  if (d->grad_bf16 != nullptr && !fp32) { b.gb16 = static_cast<bf16*>(d->grad_bf16); b.gf32 = d->grad_f32_base; }
+  if (d->grad_bf16 != nullptr && d->grad_f32_base == nullptr) return SEA_ERR_INVALID;
   if (d->dropout_p < 0.f || d->dropout_p >= 1.f) return SEA_ERR_INVALID;
   b.c.drop_p = d->dropout_p;
   const int M = b.c.M, V = d->num_streams, E = d->embed_dim, Dd = d->down_dim, H = d->hidden_dim;
@@ -444,6 +454,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       for (int i = 0; i < V; ++i) { np[i] = &d->final_ln[i]; hid[i] = tape.hidF[i]; dc[i] = bt.s[i].dcondF; W[i] = &cl.c2_final[i]; }
       SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E, true));
     }
+    SEA_CUDA_OK(b.mark(0));
   }
 
   for (int l = d->num_layers - 1; l >= 0; --l) {
@@ -504,7 +515,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
     if (l == 0) {
       // every layer's stream-MLP weight gradient (the bulk of the gradient bytes) is final from here on:
       // the data-parallel exchange of that bucket may start while the rest of the backward runs
-      if (void* ev = g_bwd_milestone.exchange(nullptr)) SEA_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev), b.c.s));
+      SEA_CUDA_OK(b.mark(1));
     }
     // Norm_{i,2} (+ skip) -> gradient at x2 = x_post + TIPI
     {
@@ -542,6 +553,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       g_launches += V + 1;
       SEA_TRY(sea_tipi_bwd(&a, b.st()));
     }
+    if (l == 0) SEA_CUDA_OK(b.mark(2));
 
     // (2) state exchange, reverse order
     bool pre_written[SEA_MAX_STREAMS] = {}, post_written[SEA_MAX_STREAMS] = {};
@@ -641,6 +653,8 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * Dd));
     }
 
+    if (l == 0) SEA_CUDA_OK(b.mark(3));
+
     // (1) self-attention
     for (int i = 0; i < V; ++i) {
       LinB& q = L[i]; q = LinB{};
@@ -688,5 +702,6 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
       SEA_TRY(cond_bwd(b, V, np, hid, dc, W, 2 * E, true));
     }
   }
+  SEA_CUDA_OK(b.mark(4));
   return SEA_OK;
 }

@@ -50,10 +50,15 @@ class AdamW(torch.optim.Optimizer):
         self._tables = {}
         self._steps = {}     # group index -> [ids of its stepped params, host step count, shared step tensor]
 
-    def _table(self, gi, plist):
-        """Device chunk table of one param group, rebuilt only when a pointer changes."""
+    def _table(self, gi, plist, twin=False):
+        """Device chunk table of one param group, rebuilt only when a pointer changes.  twin: weight gradients are read
+        from the engine's averaged bf16 bucket (data-parallel exchange, sea_b200.parallel) instead of param.grad."""
         eng = self.engine
+        gi = (gi, bool(twin))
         key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr()) for p in plist)
+        if twin:
+            flat, tw, n_w = eng.flat_grad(), eng.flat_grad_bf16(), eng.grad_buckets()[-1][0]
+            key = key + (flat.data_ptr(), tw.data_ptr())
         ckey = None if eng is None else ((eng._cache.data_ptr() if eng._cache is not None else 0),
                                          eng._cache_key[0] if eng._cache_key else None)
         hit = self._tables.get(gi)
@@ -72,11 +77,16 @@ class AdamW(torch.optim.Optimizer):
                 slot = out.value or 0
                 fused_copies |= slot != 0
             n = p.numel()
+            g_ptr, g_sz, g_b16 = p.grad.data_ptr(), 4, 0
+            if twin:
+                e0 = (g_ptr - flat.data_ptr()) // 4
+                if 0 <= e0 < n_w:                     # a weight-gradient slot of the flat buffer: its bf16 twin
+                    g_ptr, g_sz, g_b16 = tw.data_ptr() + 2 * e0, 2, 1
             for off in range(0, n, CHUNK):
                 c = min(CHUNK, n - off)
-                rows.append((p.data_ptr() + 4 * off, p.grad.data_ptr() + 4 * off,
+                rows.append((p.data_ptr() + 4 * off, g_ptr + g_sz * off,
                              st["exp_avg"].data_ptr() + 4 * off, st["exp_avg_sq"].data_ptr() + 4 * off,
-                             (slot + 2 * off) if slot else 0, c, 0))
+                             (slot + 2 * off) if slot else 0, c, g_b16))
         arr = np.array(rows, dtype=_CHUNK_DT)
         dev = plist[0].device
         tab = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
@@ -88,8 +98,15 @@ class AdamW(torch.optim.Optimizer):
         self._steps = {}
         self._tables = {}
 
+    def step_from_bf16_twin(self):
+        """step() with the weight gradients taken from the engine's averaged bf16 bucket (what
+        sea_b200.parallel.exchange_gradients(..., grad_dtype="bf16") leaves behind): 26 B / parameter instead of 28."""
+        if self.engine is None:
+            raise RuntimeError("step_from_bf16_twin needs the engine that owns the gradient buckets")
+        return self.step(_twin=True)
+
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, _twin=False):
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -128,7 +145,7 @@ class AdamW(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             hp = AdamWHyper(group["lr"], b1, b2, group["eps"], group["weight_decay"],
                             1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t), self.grad_scale, 1.0 - b1, 1.0 - b2)
-            tab, fused = self._table(gi, plist)
+            tab, fused = self._table(gi, plist, _twin)
             with torch.cuda.device(plist[0].device):
                 check(lib.sea_adamw_step(C.c_void_p(tab.data_ptr()), tab.numel() // _CHUNK_DT.itemsize,
                                          C.byref(hp), C.c_void_p(torch.cuda.current_stream().cuda_stream)),

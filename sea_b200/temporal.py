@@ -271,28 +271,75 @@ class TemporalEngine:
         # every live parameter gets a slot, frozen or not: the backward kernels always have a destination (a frozen
         # parameter's slot is scratch that is never bound to .grad), so partially / fully frozen models just work
         live = list(self._live_params())
-        # small / atomically accumulated gradients first, GEMM weight gradients last: after zero_grad only
-        # the first region has to be zero-filled (the weight-gradient GEMMs overwrite, desc.grads_fresh)
-        # ... and among those the stream-MLP weights at the very end: their gradients are final first in the
-        # backward (sea_temporal_backward_milestone), so the DP exchange of that tail bucket overlaps the rest
-        live.sort(key=lambda np_: (self._is_gemm_weight(*np_), self._is_mlp_weight(np_[0])))
+        # GEMM weight gradients first, in the order in which the backward FINISHES them (desc.bwd_events groups 0..4), so
+        # the data-parallel exchange of each bucket can start while the rest of the backward still runs; the small /
+        # atomically accumulated gradients (biases, norm, TIPI, cond_mlp.0) last: final only when the backward ends, and
+        # after zero_grad only that tail has to be zero-filled (the weight-gradient GEMMs overwrite, desc.grads_fresh)
+        live.sort(key=lambda np_: (not self._is_gemm_weight(*np_), self._bwd_group(np_[0])))
         total = sum((p.numel() + 63) // 64 * 64 for _, p in live)
         dev = live[0][1].device
         if getattr(self, "_flat_grad", None) is None or self._flat_grad.numel() != total or self._flat_grad.device != dev:
             self._flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+            self._flat_grad_bf16 = None
             self._grad_views = {}
             off = 0
-            self._small_elems = 0
-            self._mlp_start = total
+            self._small_start = total
+            self._group_start = [total] * (S.BWD_GROUPS + 1)     # first element of every weight group, + their end
             for n, p in live:
-                if self._is_mlp_weight(n):
-                    self._mlp_start = min(self._mlp_start, off)
+                if self._is_gemm_weight(n, p):
+                    g = self._bwd_group(n)
+                    self._group_start[g] = min(self._group_start[g], off)
+                else:
+                    self._small_start = min(self._small_start, off)
                 self._grad_views[n] = self._flat_grad[off:off + p.numel()].view_as(p)
                 off += (p.numel() + 63) // 64 * 64
-                if not self._is_gemm_weight(n, p):
-                    self._small_elems = off
+            self._group_start[S.BWD_GROUPS] = self._small_start
+            for g in range(S.BWD_GROUPS - 1, -1, -1):             # empty groups collapse onto their successor
+                self._group_start[g] = min(self._group_start[g], self._group_start[g + 1])
             self._desc = None  # pointers changed
         return live
+
+    @staticmethod
+    def _bwd_group(name: str) -> int:
+        """Which backward event (sea_temporal_desc.bwd_events) makes this parameter's gradient final."""
+        if name.startswith("ln."):
+            return 0                                   # final norms ln.{i}
+        parts = name.split(".")
+        if parts[0] == "blocks" and parts[1] != "0":
+            return 1                                   # upper layers are done before layer 0's first event
+        if ".mlp." in name or ".proj." in name:
+            return 1
+        if ".ln.exp." in name:
+            return 2 if parts[parts.index("exp") + 2] == "2" else 4
+        if ".ib." in name:
+            return 2
+        if "cross" in name:
+            return 3                                   # cross_down / cross_up / cross_attn / ln_cross
+        return 4                                       # attn.self
+
+    def grad_buckets(self):
+        """[(begin, end)] element ranges of the flat gradient buffer in exchange order: the weight groups 0..4 as the
+        backward finishes them, then the small (reduction-produced) gradients, which are final only at the end."""
+        self._ensure_flat_grads()
+        gs = self._group_start
+        return [(gs[g], gs[g + 1]) for g in range(S.BWD_GROUPS)] + [(self._small_start, self._flat_grad.numel())]
+
+    def flat_grad_bf16(self) -> torch.Tensor:
+        """bf16 twin of flat_grad() (allocated on first use): the weight-gradient GEMMs mirror their results into it
+        (desc.grad_bf16) — the data-parallel exchange then moves half the bytes."""
+        self._ensure_flat_grads()
+        if self._flat_grad_bf16 is None:
+            self._flat_grad_bf16 = torch.zeros(self._flat_grad.numel(), dtype=torch.bfloat16, device=self._flat_grad.device)
+        return self._flat_grad_bf16
+
+    def twin_to_flat_grad(self) -> None:
+        """param.grad (fp32 views of flat_grad()) <- the averaged bf16 weight-gradient bucket: what an optimizer other than
+        the fused AdamW needs after a bf16 gradient exchange."""
+        n_w = self.grad_buckets()[-1][0]
+        if n_w:
+            with torch.cuda.device(self._flat_grad.device):
+                check(lib.sea_cast_bf16_f32(C.c_void_p(self.flat_grad_bf16().data_ptr()), C.c_void_p(self._flat_grad.data_ptr()),
+                                            C.c_int64(n_w), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "cast_bf16_f32")
 
     @staticmethod
     def _is_mlp_weight(name: str) -> bool:
@@ -303,10 +350,9 @@ class TemporalEngine:
         self._ensure_flat_grads()
         return self._flat_grad
 
-    def mlp_grad_offset(self) -> int:
-        """First element of the stream-MLP weight-gradient bucket at the tail of flat_grad()."""
-        self._ensure_flat_grads()
-        return self._mlp_start
+    # data-parallel hooks, set by sea_b200.parallel.TrainStep around loss.backward()
+    bwd_events = None          # list of BWD_GROUPS cudaEvent_t handles (or None)
+    mirror_bf16 = False        # weight-gradient GEMMs also write the bf16 twin
 
     def anchor_param(self):
         for _, p in self._live_params():
@@ -322,7 +368,7 @@ class TemporalEngine:
         if all(p.grad is None for _, p in live):
             # zero_grad(set_to_none=True): only the atomically accumulated gradients need zeros; the
             # weight-gradient GEMMs overwrite their destinations on first touch (desc.grads_fresh)
-            self._flat_grad[: self._small_elems].zero_()
+            self._flat_grad[self._small_start:].zero_()
             self._grads_fresh = True
             for n, p in live:
                 p.grad = self._grad_views[n]
@@ -499,6 +545,11 @@ class TemporalEngine:
         dx = torch.empty_like(x) if need_dx else None
         self._desc.grads_fresh = int(getattr(self, "_grads_fresh", False))
         self._desc.dropout_p, self._desc.dropout_seed = float(dropout_p), int(dropout_seed)
+        self._desc.grad_f32_base = self._flat_grad.data_ptr()
+        self._desc.grad_bf16 = self.flat_grad_bf16().data_ptr() if self.mirror_bf16 and self.precision == "bf16" else None
+        for k in range(S.BWD_GROUPS):
+            ev = None if self.bwd_events is None else self.bwd_events[k]
+            self._desc.bwd_events[k] = ev.value if hasattr(ev, "value") else ev
         self._grads_fresh = False
         with torch.cuda.device(x.device):
             check(lib.sea_temporal_backward(C.byref(self._desc), C.c_void_p(self._cache.data_ptr()),

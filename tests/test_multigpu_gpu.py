@@ -17,11 +17,12 @@ def _torchrun(n, script_args, port):
     return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
 
 
+@pytest.mark.parametrize("width,opt", [("small", "torch"), ("small", "fused"), ("full", "fused")])
 @pytest.mark.parametrize("ln", ["adaln", "ln"])
-def test_dp_training_matches_oracle_global_batch(cuda, ln):
+def test_dp_training_matches_oracle_global_batch(cuda, ln, width, opt):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    env = dict(os.environ, SEA_LN=ln)
+    env = dict(os.environ, SEA_LN=ln, SEA_DP_WIDTH=width, SEA_DP_OPT=opt)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29517", "scripts/dp_train_check.py"]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)

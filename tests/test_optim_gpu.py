@@ -83,3 +83,72 @@ def test_training_with_fused_adamw_tracks_torch_adamw(cuda, ln):
         fresh = TemporalEngine(mb, precision="bf16")
         y_new = fresh.forward_nograd(x, ib, training=True, ws=fresh.acquire_training_workspace(B, T))
     assert torch.equal(y_inc, y_new)
+
+
+@pytest.mark.parametrize("ln", ["adaln", "ln"])
+def test_bf16_gradient_twin_and_fused_step_from_it(cuda, ln):
+    """Data-parallel plumbing on one GPU (sea_temporal_desc.grad_bf16 / bwd_events): with the mirror on, every weight-gradient
+    GEMM leaves bf16(final fp32 gradient) in the twin buffer (bit-exact), the per-group events are recorded, the fused
+    AdamW stepping from the twin tracks the fp32-gradient step to bf16 rounding, and twin_to_flat_grad() writes the
+    rounded values back into param.grad."""
+    import ctypes as C
+
+    from sea_b200 import _structs as S
+    from sea_b200._lib import check, lib
+    from sea_b200.optim import AdamW
+    from sea_b200.temporal import TemporalModel
+    E, nh, scale, V, B, T = 256, 2, 4, 2, 2, 24
+    shapes = gr.temporal_shapes(embed_dim=E, n_heads=nh, scale_ratio=scale, num_variables=V, ln_type=ln)
+    sd = gr.fill_state(shapes, 11)
+    x, ib, tgt = (t.to(cuda) for t in gr.temporal_inputs(B, T, V, E, 11))
+
+    def make():
+        m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln)
+        m.load_state_dict(sd, strict=False)
+        return m.to(cuda).train()
+
+    ma, mb = make(), make()
+    ea, eb = ma.engine(), mb.engine()
+    oa = AdamW(ma.parameters(), lr=1e-3, engine=ea)
+    ob = AdamW(mb.parameters(), lr=1e-3, engine=eb)
+    events = []
+    for _ in range(S.BWD_GROUPS):
+        ev = C.c_void_p()
+        check(lib.sea_event_create(C.byref(ev)), "event_create")
+        events.append(ev)
+    for step in range(3):
+        oa.zero_grad(set_to_none=True)
+        ob.zero_grad(set_to_none=True)
+        F.mse_loss(ma(x, ib), tgt).backward()
+        eb.bwd_events, eb.mirror_bf16 = events, True
+        F.mse_loss(mb(x, ib), tgt).backward()
+        eb.bwd_events, eb.mirror_bf16 = None, False
+        side = torch.cuda.Stream()
+        for ev in events:       # every group's event was recorded on the compute stream: a side stream can wait on it
+            check(lib.sea_stream_wait_event(C.c_void_p(side.cuda_stream), ev), "wait")
+        side.synchronize()
+        n_w = eb.grad_buckets()[-1][0]
+        flat, twin = eb.flat_grad(), eb.flat_grad_bf16()
+        assert n_w > 0.9 * flat.numel()
+        # padding between parameter slots is never written by either side: compare parameter by parameter
+        for n, v in eb._grad_views.items():
+            off = (v.data_ptr() - flat.data_ptr()) // 4
+            if off < n_w:
+                assert torch.equal(twin[off:off + v.numel()].view_as(v), v.to(torch.bfloat16)), n
+        if step == 0:
+            for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
+                if p.grad is not None:
+                    assert torch.equal(p.grad, q.grad), n
+        oa.step()
+        ob.step_from_bf16_twin()
+    for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
+        if p.grad is not None:
+            assert _rel(q.data, p.data) < 2e-3, n
+    g_before = {n: v.clone() for n, v in eb._grad_views.items()}
+    eb.twin_to_flat_grad()
+    for n, v in eb._grad_views.items():
+        off = (v.data_ptr() - flat.data_ptr()) // 4
+        want = g_before[n].to(torch.bfloat16).float() if off < n_w else g_before[n]
+        assert torch.equal(v, want), n
+    for ev in events:
+        lib.sea_event_destroy(ev)

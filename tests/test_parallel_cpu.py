@@ -59,18 +59,45 @@ def test_shard_range_partitions(n, world):
     assert max(sizes) - min(sizes) <= 1
 
 
-def test_flat_gradient_layout_puts_stream_mlp_bucket_last():
-    """The DP exchange overlaps the bucket whose gradients are final first in the backward (the stream-MLP
-    weights, sea_temporal_backward_milestone): it must be one contiguous tail of the flat buffer, behind the
-    atomically accumulated (zero-filled) head and the other GEMM weights."""
+def test_flat_gradient_layout_follows_backward_completion_order():
+    """The DP exchange sends each bucket as soon as the backward has finished it (sea_temporal_desc.bwd_events): the flat
+    buffer holds the GEMM weight gradients first, grouped in completion order, and the small reduction-produced
+    gradients (the only region zero-filled after zero_grad) as one contiguous tail."""
+    from sea_b200 import _structs as S
     from sea_b200.temporal import TemporalModel
     m = TemporalModel(1, 64, 2, 64, 2, 0, 2, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, "adaln")
     eng = m.engine()
-    flat, k = eng.flat_grad(), eng.mlp_grad_offset()
-    tail = sorted(n for n, v in eng._grad_views.items() if v.data_ptr() >= flat.data_ptr() + 4 * k)
-    assert tail == sorted(f"blocks.0.mlp.{i}.layers.{j}.weight" for i in range(2) for j in (0, 3))
-    assert eng._small_elems <= k < flat.numel()
-    assert (flat.numel() - k) == 4 * 64 * 128          # 2 streams x (E x H + H x E), E=64, H=2E
+    flat = eng.flat_grad()
+    buckets = eng.grad_buckets()
+    assert len(buckets) == S.BWD_GROUPS + 1
+    assert buckets[0][0] == 0 and buckets[-1][1] == flat.numel()
+    assert all(buckets[i][1] == buckets[i + 1][0] for i in range(len(buckets) - 1))
+
+    def names(k):
+        b, e = buckets[k]
+        lo, hi = flat.data_ptr() + 4 * b, flat.data_ptr() + 4 * e
+        return sorted(n for n, v in eng._grad_views.items() if lo <= v.data_ptr() < hi)
+
+    assert names(0) == sorted(f"ln.{i}.cond_mlp.2.weight" for i in range(2))
+    assert names(1) == sorted([f"blocks.0.mlp.{i}.layers.{j}.weight" for i in range(2) for j in (0, 3)]
+                              + [f"blocks.0.proj.{i}.weight" for i in range(2)])
+    assert names(2) == sorted(f"blocks.0.ln.exp.{i}.2.cond_mlp.2.weight" for i in range(2))
+    assert all("cross" in n for n in names(3)) and len(names(3)) > 0
+    assert all(".attn.self." in n or ".ln.exp." in n for n in names(4)) and len(names(4)) > 0
+    # the tail: everything that is not a weight-gradient GEMM output
+    assert all(v.dim() != 2 or "ib.layers" in n or "cond_mlp.0." in n
+               for n, v in eng._grad_views.items() if n in names(5))
+    assert sum(len(names(k)) for k in range(6)) == len(eng._grad_views)
+
+
+def test_plan_buckets_merges_small_groups():
+    from sea_b200.parallel import plan_buckets
+    groups = [(0, 10), (10, 110), (110, 120), (120, 125), (125, 225)]
+    assert plan_buckets(groups, 2, min_bytes=100) == [(0, 110, 1), (110, 225, 4)]
+    assert plan_buckets(groups, 2, min_bytes=1) == [(b, e, k) for k, (b, e) in enumerate(groups)]
+    assert plan_buckets(groups, 2, min_bytes=10 ** 9) == [(0, 225, 4)]
+    assert plan_buckets([(0, 100), (100, 100), (100, 105)], 4, min_bytes=100) == [(0, 105, 2)]
+    assert plan_buckets([(0, 0)], 4) == []
 
 
 def _exchange_worker(rank, world, port, q):
@@ -86,11 +113,8 @@ def _exchange_worker(rank, world, port, q):
         def flat_grad(self):
             return self.flat
 
-        def mlp_grad_offset(self):
-            return 8
-
     e = Eng()
-    parallel.exchange_gradients(e, armed_event=None)
+    parallel.exchange_gradients(e, events=None)
     if rank == 0:
         q.put(e.flat.tolist())
     dist.barrier()
