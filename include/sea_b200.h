@@ -681,6 +681,24 @@ int sea_patch_gather(const float* const* host_field_ptrs, int n_fields, int64_t 
                      sea_stream_t stream);
 int sea_patch_scatter(const float* part, const int64_t* index_map, int n_snapshots, int n_patches, int capacity,
                       int n_fields, int n_cells, int layout_pfc, float* out, sea_stream_t stream);
+/* The same two passes fused with the per-field-group MinMaxScaler of MeshProcessor (utils/data_processors.py:225-272,
+ * _scale_fields :544-551, inverse_scale_and_unpatch :553-573) and reading / writing the reference's own interleaved
+ * field tensor [S, n_cells, F] (no per-field copies): the resident fields -> latents -> fields pipeline.
+ *   gather_scaled   out[s,p,..] = ((x - min) / (max - min)) * range + lo     (transform, :245-252; pad -> pad_value)
+ *   scatter_scaled  out[s,idx,f] = ((v - lo) / range) * (max - min) + min     (inverse_transform, :258-272)
+ * evaluated as the same sequence of IEEE fp32 operations torch performs (bit-identical).  enabled = 0: identity. */
+typedef struct sea_field_scaler {
+  float min_val, max_val; /* fitted on the training data (MinMaxScaler.fit) */
+  float lo, range;        /* feature_range[0], feature_range[1] - feature_range[0] */
+  int32_t enabled;
+  int32_t reserved;
+} sea_field_scaler;
+int sea_patch_gather_scaled(const float* fields, int n_cells, int n_fields, const sea_field_scaler* host_scalers,
+                            const int64_t* index_map, int n_snapshots, int n_patches, int capacity, float pad_value,
+                            int layout_pfc, float* out, sea_stream_t stream);
+int sea_patch_scatter_scaled(const float* part, const int64_t* index_map, int n_snapshots, int n_patches, int capacity,
+                             int n_fields, int n_cells, int layout_pfc, const sea_field_scaler* host_scalers,
+                             float* out, sea_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -122,6 +122,60 @@ __global__ void __launch_bounds__(256) patch_scatter_kernel(const float* __restr
   out[(static_cast<long long>(s) * n_cells + idx) * F + f] = part[(static_cast<long long>(s) * P + p) * capacity * F + e];
 }
 
+
+// MinMaxScaler.transform / inverse_transform (utils/data_processors.py:245-252, :258-272) in the reference's own
+// operation order, one IEEE fp32 operation per torch op (no contraction into FMAs): bit-identical to the eager result.
+struct FieldScalers { sea_field_scaler f[8]; };
+__device__ __forceinline__ float scale_fwd(float v, const sea_field_scaler& sc) {
+  if (!sc.enabled) return v;
+  const float std_ = __fdiv_rn(__fsub_rn(v, sc.min_val), __fsub_rn(sc.max_val, sc.min_val));
+  return __fadd_rn(__fmul_rn(std_, sc.range), sc.lo);
+}
+__device__ __forceinline__ float scale_inv(float v, const sea_field_scaler& sc) {
+  if (!sc.enabled) return v;
+  const float std_ = __fdiv_rn(__fsub_rn(v, sc.lo), sc.range);
+  return __fadd_rn(__fmul_rn(std_, __fsub_rn(sc.max_val, sc.min_val)), sc.min_val);
+}
+
+// fields [S, n_cells, F] (interleaved, as the reference holds them) -> scaled, padded patches [S, P, F, C] / [S, P, C, F]
+__global__ void __launch_bounds__(256) patch_gather_scaled_kernel(const float* __restrict__ fields, int n_cells,
+                                                                  const FieldScalers sc,
+                                                                  const long long* __restrict__ index_map, int P,
+                                                                  int capacity, int F, float pad_value, int layout_pfc,
+                                                                  float* __restrict__ out) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= capacity * F) return;
+  const int p = blockIdx.y, s = blockIdx.z;
+  int c, f;
+  if (layout_pfc) { f = e / capacity; c = e - f * capacity; }
+  else { c = e / F; f = e - c * F; }
+  const long long idx = index_map[static_cast<long long>(p) * capacity + c];
+  float v = pad_value;
+  if (idx >= 0) v = scale_fwd(fields[(static_cast<long long>(s) * n_cells + idx) * F + f], sc.f[f]);
+  out[(static_cast<long long>(s) * P + p) * capacity * F + e] = v;
+}
+
+// padded patches -> unscaled fields [S, n_cells, F]
+__global__ void __launch_bounds__(256) patch_scatter_scaled_kernel(const float* __restrict__ part,
+                                                                   const long long* __restrict__ index_map, int P,
+                                                                   int capacity, int F, int n_cells, int layout_pfc,
+                                                                   const FieldScalers sc, float* __restrict__ out) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= capacity * F) return;
+  const int p = blockIdx.y, s = blockIdx.z;
+  int c, f;
+  if (layout_pfc) { f = e / capacity; c = e - f * capacity; }
+  else { c = e / F; f = e - c * F; }
+  const long long idx = index_map[static_cast<long long>(p) * capacity + c];
+  if (idx < 0) return;
+  out[(static_cast<long long>(s) * n_cells + idx) * F + f] =
+      scale_inv(part[(static_cast<long long>(s) * P + p) * capacity * F + e], sc.f[f]);
+}
+
 }  // namespace
 }  // namespace sea
 
@@ -173,5 +227,35 @@ extern "C" int sea_patch_scatter(const float* part, const int64_t* index_map, in
   dim3 grid((capacity * n_fields + 255) / 256, n_patches, n_snapshots);
   SEA_LAUNCH(patch_scatter_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), part,
              reinterpret_cast<const long long*>(index_map), n_patches, capacity, n_fields, n_cells, layout_pfc, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_patch_gather_scaled(const float* fields, int n_cells, int n_fields, const sea_field_scaler* scalers,
+                                       const int64_t* index_map, int n_snapshots, int n_patches, int capacity,
+                                       float pad_value, int layout_pfc, float* out, sea_stream_t stream) {
+  using namespace sea;
+  if (!fields || !index_map || !out || n_fields < 1 || n_fields > 8 || n_cells <= 0) return SEA_ERR_INVALID;
+  if (n_snapshots <= 0 || n_patches <= 0 || capacity <= 0 || n_snapshots > 65535 || n_patches > 65535) return SEA_ERR_INVALID;
+  FieldScalers sc{};
+  for (int i = 0; i < n_fields; ++i)
+    if (scalers) sc.f[i] = scalers[i];
+  dim3 grid((capacity * n_fields + 255) / 256, n_patches, n_snapshots);
+  SEA_LAUNCH(patch_gather_scaled_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), fields, n_cells, sc,
+             reinterpret_cast<const long long*>(index_map), n_patches, capacity, n_fields, pad_value, layout_pfc, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_patch_scatter_scaled(const float* part, const int64_t* index_map, int n_snapshots, int n_patches,
+                                        int capacity, int n_fields, int n_cells, int layout_pfc,
+                                        const sea_field_scaler* scalers, float* out, sea_stream_t stream) {
+  using namespace sea;
+  if (!part || !index_map || !out || n_fields < 1 || n_fields > 8 || n_cells <= 0) return SEA_ERR_INVALID;
+  if (n_snapshots <= 0 || n_patches <= 0 || capacity <= 0 || n_snapshots > 65535 || n_patches > 65535) return SEA_ERR_INVALID;
+  FieldScalers sc{};
+  for (int i = 0; i < n_fields; ++i)
+    if (scalers) sc.f[i] = scalers[i];
+  dim3 grid((capacity * n_fields + 255) / 256, n_patches, n_snapshots);
+  SEA_LAUNCH(patch_scatter_scaled_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), part,
+             reinterpret_cast<const long long*>(index_map), n_patches, capacity, n_fields, n_cells, layout_pfc, sc, out);
   return static_cast<int>(cudaGetLastError());
 }

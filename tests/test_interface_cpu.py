@@ -92,7 +92,8 @@ def test_ctypes_struct_sizes_match_header():
              "sea_norm_bwd_args": S.NormBwdArgs, "sea_ln_gelu_bwd_args": S.LnGeluBwdArgs,
              "sea_attn_bwd_args": S.AttnBwdArgs, "sea_tipi_bwd_args": S.TipiBwdArgs,
              "sea_spatial_layer": S.SpatialLayer, "sea_spatial_desc": S.SpatialDesc,
-             "sea_adamw_hyper": __import__("sea_b200.optim", fromlist=["AdamWHyper"]).AdamWHyper}
+             "sea_adamw_hyper": __import__("sea_b200.optim", fromlist=["AdamWHyper"]).AdamWHyper,
+             "sea_field_scaler": __import__("sea_b200.pipeline", fromlist=["FieldScaler"]).FieldScaler}
     src = '#include <stdio.h>\n#include "sea_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:
