@@ -69,13 +69,14 @@ def local_step():
 ms_local = timed(local_step, args.steps)
 ms_seq = timed(lambda: parallel.train_step(m, opt, F.mse_loss, x, tgt, ib, overlap=False), args.steps)
 ms_ovl = timed(lambda: parallel.train_step(m, opt, F.mse_loss, x, tgt, ib, overlap=True), args.steps)
+ms_ovl_f32 = timed(lambda: parallel.train_step(m, opt, F.mse_loss, x, tgt, ib, overlap=True, grad_dtype="f32"), args.steps)
 eng = m.engine()
 flat = eng.flat_grad()
 if rank == 0:
     print(json.dumps({"config": args.config, "n_gpus": world, "per_gpu_batch": b, "T": T,
                       "grad_bytes": flat.numel() * 4, **parallel.TrainStep(m, opt, F.mse_loss).info(),
                       "ms_step_no_exchange": ms_local, "ms_step_exchange_after_backward": ms_seq,
-                      "ms_step_exchange_overlapped": ms_ovl,
+                      "ms_step_exchange_overlapped": ms_ovl, "ms_step_exchange_overlapped_f32_buckets": ms_ovl_f32,
                       "samples_per_sec_overlapped": world * b / (ms_ovl / 1e3)}))
 if world > 1:
     dist.destroy_process_group()

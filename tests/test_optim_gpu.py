@@ -137,8 +137,8 @@ def test_bf16_gradient_twin_and_fused_step_from_it(cuda, ln):
                 assert torch.equal(twin[off:off + v.numel()].view_as(v), v.to(torch.bfloat16)), n
         if step == 0:
             for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
-                if p.grad is not None:
-                    assert torch.equal(p.grad, q.grad), n
+                if p.grad is not None:      # atomically accumulated gradients (TIPI, cond_mlp.0, biases) are not bit-stable
+                    assert _rel(q.grad, p.grad) < 1e-4, n
         oa.step()
         ob.step_from_bf16_twin()
     for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
