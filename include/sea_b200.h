@@ -659,6 +659,18 @@ int sea_spatial_encode(const sea_spatial_desc* d, float* x, float* z, int B, int
                        float pad_idx, int fix_pad, sea_stream_t stream);
 int sea_spatial_decode(const sea_spatial_desc* d, const float* z, float* out, int B, int latent_layout,
                        sea_stream_t stream);
+/* The same two passes with every contraction (patch MLPs, q|k|v / projection / MLP of the encoder blocks, QK^T and P.V
+ * of the 8-head attention) on the tensor cores: warp-level bf16 mma.sync.m16n8k16, fp32 accumulation; residual state,
+ * LayerNorm statistics, softmax and GELU in fp32 (the bf16 parity mode: 2e-2 bar; the fp32 kernels above keep the 1e-4
+ * bar).  Weights are rounded to bf16 once into a caller-owned cache (256-byte aligned, sea_spatial_cache_bytes):
+ * sea_spatial_pack must run after every parameter update.  Needs embed_dim, mlp_hidden, n_inp*|group| multiples of 16
+ * and n_inp a multiple of 8; SEA_ERR_UNSUPPORTED when a snapshot's working set exceeds the 227 KB of shared memory. */
+size_t sea_spatial_cache_bytes(const sea_spatial_desc* d);
+int sea_spatial_pack(const sea_spatial_desc* d, void* cache, size_t cache_bytes, sea_stream_t stream);
+int sea_spatial_encode_tc(const sea_spatial_desc* d, const void* cache, float* x, float* z, int B, int latent_layout,
+                          float pad_idx, int fix_pad, sea_stream_t stream);
+int sea_spatial_decode_tc(const sea_spatial_desc* d, const void* cache, const float* z, float* out, int B,
+                          int latent_layout, sea_stream_t stream);
 
 /* ------------------------------------------------------------------ mesh patchify / unpatch ----
  * DataPartitioner2D of the reference (utils/data_processors.py:9-111; called from patchify_and_scale

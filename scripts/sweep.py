@@ -62,15 +62,20 @@ def temporal():
             torch.cuda.empty_cache()
 
 
-def spatial():
+def spatial(precision="fp32", cs=(32, 64, 128, 256), batches=(128, 1000, 8000)):
+    """HBM roofline of the codec: bytes_spatial(min) = 4*P*F*C in + 4*P*G*D latent out per snapshot."""
     from sea_b200.spatial import SpatialModel
-    print("\n| config | snapshots | cells/patch C | encode ms | encode snapshots/s | decode ms | decode snapshots/s |")
-    print("|---|---:|---:|---:|---:|---:|---:|")
+    print(f"\ncodec precision = {precision}")
+    print("| config | snapshots | cells/patch C | encode ms | encode snapshots/s | encode GB/s (algorithmic) | encode TFLOP/s | decode ms | decode snapshots/s |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|---:|")
     for cfg, D, Hs in (("cylinder_flow", 16, 480), ("multiphase_flow", 32, 624)):
-        for C in (32, 64, 128, 256):
+        for C in cs:
             torch.manual_seed(42)
-            m = SpatialModel([[0, 1], [2]], C, Hs, 12, D, 8, 2024, 0, 0.0, False).to(dev).eval()
-            for Bs in (128, 1000, 8000):
+            m = SpatialModel([[0, 1], [2]], C, Hs, 12, D, 8, 2024, 0, 0.0, False, precision=precision).to(dev).eval()
+            Es = 2 * D
+            enc_flops = 2 * 64 * (3 * C) * Hs + 2 * 64 * Hs * D * 2 + 12 * (24 * 64 * Es * Es + 4 * 64 * 64 * Es)
+            enc_bytes = 4 * 64 * 3 * C + 4 * 64 * Es
+            for Bs in batches:
                 x = torch.randn(Bs, 64, 3, C, device=dev)
                 try:
                     with torch.no_grad():
@@ -80,7 +85,8 @@ def spatial():
                 except RuntimeError as e:
                     print(f"| {cfg} | {Bs} | {C} | unsupported: {e} | | | |", flush=True)
                     continue
-                print(f"| {cfg} | {Bs} | {C} | {ms_e:.3f} | {Bs/ms_e*1e3:.0f} | {ms_d:.3f} | {Bs/ms_d*1e3:.0f} |", flush=True)
+                print(f"| {cfg} | {Bs} | {C} | {ms_e:.3f} | {Bs/ms_e*1e3:.0f} | {Bs*enc_bytes/ms_e/1e6:.1f} | "
+                      f"{Bs*enc_flops/ms_e/1e9:.2f} | {ms_d:.3f} | {Bs/ms_d*1e3:.0f} |", flush=True)
                 del x, z
             del m
 
@@ -90,4 +96,8 @@ if __name__ == "__main__":
     if what in ("temporal", "all"):
         temporal()
     if what in ("spatial", "all"):
-        spatial()
+        spatial("fp32")
+        spatial("bf16")
+    if what == "spatial_tc":
+        spatial("fp32", cs=(64,), batches=(1000, 8000))
+        spatial("bf16", cs=(32, 64, 128, 256), batches=(1000, 8000, 32000))

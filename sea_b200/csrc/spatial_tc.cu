@@ -1,0 +1,549 @@
+// K7' / K8' — the ViT-mesh patch encoder / decoder (models/encoder_decoder.py:75-146) on the tensor cores.
+//
+// Same decomposition as spatial.cu (one CTA per snapshot, the 64 x Es latent state resident in shared memory from the
+// patch gather to the final LayerNorm, weights streamed from L2), but every contraction — the per-group patch MLPs
+// (C*g -> Hs -> D and back), q|k|v / projection / MLP of the 12 encoder blocks, and the 8-head attention itself
+// (QK^T with the head dim zero-padded to k = 16, P.V with P taken straight from the score accumulators) — is a warp-level
+// bf16 mma.sync.m16n8k16 with fp32 accumulation.  At these widths (Es = 32 / 64, head dim 4 / 8, 64 tokens) a
+// 128-row tcgen05 tile would be three quarters padding; the warp-level shape fits the problem exactly.
+//
+// Operand layout trick: the contraction index may be permuted freely as long as A and B use the same permutation, so
+// thread t of a quad owns the 8 CONSECUTIVE k elements [32*i + 8t, 32*i + 8t + 8) of two k-steps at once: one 16-byte
+// load per operand row feeds two MMAs (no ldmatrix, no transposed copies; B = the nn.Linear weight [N, K] as it lies).
+// Activations are bf16 in shared memory with a row pitch == 32 (mod 64) elements, which makes the quad-wise 16-byte
+// loads bank-conflict free; the residual stream, LayerNorm statistics, softmax and GELU stay fp32.
+//
+// Weights are pre-rounded to bf16 once (sea_spatial_pack: q|k|v fused along N) into a caller-owned cache.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/sea_b200.h"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace sea {
+namespace {
+
+using bf16 = __nv_bfloat16;
+constexpr int P = 64;
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+
+struct LayerTC {
+  const bf16 *qkv_w, *proj_w, *mlp0_w, *mlp3_w;
+  const float *qkv_b, *ln1_w, *ln2_w, *mlp0_b, *mlp_ln_w, *mlp_ln_b, *mlp3_b;
+};
+struct SpatialTC {
+  int n_groups, n_fields, C, Hs, D, n_heads, num_layers;
+  int g_first[4], g_count[4];
+  const bf16 *enc_w1[4], *enc_w2[4], *dec_w1[4], *dec_w2[4];
+  const float *enc_b2[4], *dec_b2[4];
+  const float *ln_w, *ln_b, *pe;
+  LayerTC layers[16];
+};
+
+__host__ __device__ inline int pitch_of(int K) {   // smallest pitch >= K with pitch % 64 == 32 (bf16 elements)
+  int p = (K / 64) * 64 + 32;
+  return p >= K ? p : p + 64;
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Y[64, N] = X[64, K] . W[N, K]^T, X bf16 in shared memory (pitch ldx), W bf16 in global memory (row pitch ldw).
+// 16 warps = 4 row tiles x 4 column groups; a warp walks its n-tiles (8 columns each) NT at a time.
+// epi(row, col, v0, v1) receives the two adjacent columns (col even) of one row.  K % 16 == 0, N % 8 == 0.
+template <int NT, class Epi>
+__device__ __forceinline__ void gemm64(const bf16* __restrict__ X, int ldx, int K, const bf16* __restrict__ W,
+                                       long long ldw, int N, Epi&& epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, r = lane >> 2;
+  const int rt = warp & 3, cg = warp >> 2;
+  const int ntiles = N >> 3;
+  const bf16* xa = X + (rt * 16 + r) * ldx;
+  const bf16* xb = xa + 8 * ldx;
+  for (int j0 = cg; j0 < ntiles; j0 += 4 * NT) {
+    float acc[NT][4];
+    const bf16* wp[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      const int j = min(j0 + 4 * i, ntiles - 1);
+      wp[i] = W + static_cast<long long>(j * 8 + r) * ldw;
+    }
+    int k0 = 0;
+#pragma unroll 2
+    for (; k0 + 32 <= K; k0 += 32) {
+      const uint4 alo = *reinterpret_cast<const uint4*>(xa + k0 + t * 8);
+      const uint4 ahi = *reinterpret_cast<const uint4*>(xb + k0 + t * 8);
+      uint4 b[NT];
+#pragma unroll
+      for (int i = 0; i < NT; ++i) b[i] = __ldg(reinterpret_cast<const uint4*>(wp[i] + k0 + t * 8));
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        mma16816(acc[i], alo.x, ahi.x, alo.y, ahi.y, b[i].x, b[i].y);
+        mma16816(acc[i], alo.z, ahi.z, alo.w, ahi.w, b[i].z, b[i].w);
+      }
+    }
+    if (k0 < K) {   // 16-wide tail: thread t owns k0 + 4t .. 4t + 3
+      const uint2 alo = *reinterpret_cast<const uint2*>(xa + k0 + t * 4);
+      const uint2 ahi = *reinterpret_cast<const uint2*>(xb + k0 + t * 4);
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(wp[i] + k0 + t * 4));
+        mma16816(acc[i], alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int j = j0 + 4 * i;
+      if (j < ntiles) {
+        epi(rt * 16 + r, j * 8 + 2 * t, acc[i][0], acc[i][1]);
+        epi(rt * 16 + r + 8, j * 8 + 2 * t, acc[i][2], acc[i][3]);
+      }
+    }
+  }
+}
+
+template <class Epi>
+__device__ __forceinline__ void gemm64_any(const bf16* X, int ldx, int K, const bf16* W, long long ldw, int N, Epi&& epi) {
+  if (N >= 128) gemm64<4>(X, ldx, K, W, ldw, N, epi);
+  else gemm64<1>(X, ldx, K, W, ldw, N, epi);
+}
+
+// Row LayerNorm of the fp32 state (warp per row): Y (bf16, pitch ldy) = (x - mean) * rstd * w (+ b), optional GELU.
+__device__ __forceinline__ void layernorm_rows(const float* __restrict__ X, int ldx, int d, const float* __restrict__ w,
+                                               const float* __restrict__ b, bf16* __restrict__ Y, int ldy, bool gelu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = warp; row < P; row += kWarps) {
+    const float* xr = X + row * ldx;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+    for (int c = lane; c < d; c += 32) { const float e = xr[c] - mean; q = fmaf(e, e, q); }
+    const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+    for (int c = lane; c < d; c += 32) {
+      float y = (xr[c] - mean) * rstd * __ldg(w + c);
+      if (b) y += __ldg(b + c);
+      Y[row * ldy + c] = __float2bfloat16_rn(gelu ? ptx::gelu_fast(y) : y);
+    }
+  }
+}
+
+// Non-causal attention over the 64 patches for all heads (models/base_blocks.py:105-121) on the tensor cores.
+// Q, K: bf16 [64][ld] (column h*HD + d); Vt: bf16 [Es (+8)][ldv], row h*HD + d, column = key; O: bf16 [64][ld].
+// One (head, 16-query tile) per warp pass: S = Q K^T (head dim zero-padded to k = 16), softmax in registers
+// (a query row lives in one quad), P re-used as the A operand of P.V from the accumulator registers.
+template <int HD>
+__device__ __forceinline__ void attention_tc(const bf16* __restrict__ Q, const bf16* __restrict__ Kk, int ld,
+                                             const bf16* __restrict__ Vt, int ldv, int n_heads, bf16* __restrict__ O) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3, r = lane >> 2;
+  const float sl2 = rsqrtf(static_cast<float>(HD)) * 1.4426950408889634f;
+  constexpr int NTV = HD > 8 ? HD / 8 : 1;
+  for (int item = warp; item < n_heads * 4; item += kWarps) {
+    const int h = item >> 2, rt = item & 3;
+    const bf16* q0 = Q + (rt * 16 + r) * ld + h * HD;
+    const bool lo_ok = 2 * t < HD, hi_ok = 2 * t + 8 < HD;
+    const uint32_t a0 = lo_ok ? *reinterpret_cast<const uint32_t*>(q0 + 2 * t) : 0u;
+    const uint32_t a1 = lo_ok ? *reinterpret_cast<const uint32_t*>(q0 + 8 * ld + 2 * t) : 0u;
+    const uint32_t a2 = hi_ok ? *reinterpret_cast<const uint32_t*>(q0 + 2 * t + 8) : 0u;
+    const uint32_t a3 = hi_ok ? *reinterpret_cast<const uint32_t*>(q0 + 8 * ld + 2 * t + 8) : 0u;
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bf16* kr = Kk + (j * 8 + r) * ld + h * HD;
+      const uint32_t b0 = lo_ok ? *reinterpret_cast<const uint32_t*>(kr + 2 * t) : 0u;
+      const uint32_t b1 = hi_ok ? *reinterpret_cast<const uint32_t*>(kr + 2 * t + 8) : 0u;
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      mma16816(s[j], a0, a1, a2, a3, b0, b1);
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      m0 = fmaxf(m0, fmaxf(s[j][0], s[j][1]));
+      m1 = fmaxf(m1, fmaxf(s[j][2], s[j][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f((s[j][0] - m0) * sl2); s[j][1] = exp2f((s[j][1] - m0) * sl2);
+      s[j][2] = exp2f((s[j][2] - m1) * sl2); s[j][3] = exp2f((s[j][3] - m1) * sl2);
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[NTV][4];
+#pragma unroll
+    for (int nt = 0; nt < NTV; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t p0 = ptx::pack_bf16(s[2 * ks][0], s[2 * ks][1]);
+      const uint32_t p1 = ptx::pack_bf16(s[2 * ks][2], s[2 * ks][3]);
+      const uint32_t p2 = ptx::pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+      const uint32_t p3 = ptx::pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+      for (int nt = 0; nt < NTV; ++nt) {
+        const bf16* vr = Vt + (h * HD + nt * 8 + r) * ldv + ks * 16 + 2 * t;   // rows past the head: discarded columns
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + 8);
+        mma16816(o[nt], p0, p1, p2, p3, b0, b1);
+      }
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+    for (int nt = 0; nt < NTV; ++nt) {
+      const int d = nt * 8 + 2 * t;
+      if (d < HD) {
+        bf16* orow = O + (rt * 16 + r) * ld + h * HD + d;
+        *reinterpret_cast<uint32_t*>(orow) = ptx::pack_bf16(o[nt][0] * i0, o[nt][1] * i0);
+        *reinterpret_cast<uint32_t*>(orow + 8 * ld) = ptx::pack_bf16(o[nt][2] * i1, o[nt][3] * i1);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void attention_dispatch_tc(int hd, const bf16* Q, const bf16* Kk, int ld, const bf16* Vt, int ldv,
+                                                      int n_heads, bf16* O) {
+  switch (hd) {
+    case 2: attention_tc<2>(Q, Kk, ld, Vt, ldv, n_heads, O); break;
+    case 4: attention_tc<4>(Q, Kk, ld, Vt, ldv, n_heads, O); break;
+    case 8: attention_tc<8>(Q, Kk, ld, Vt, ldv, n_heads, O); break;
+    default: attention_tc<16>(Q, Kk, ld, Vt, ldv, n_heads, O); break;
+  }
+}
+
+__device__ __forceinline__ long long latent_index(int b, int p, int g, int d, int G, int D, int layout) {
+  return layout == 0 ? ((static_cast<long long>(b) * P + p) * G + g) * D + d
+                     : ((static_cast<long long>(b) * G + g) * P + p) * D + d;
+}
+
+// Shared-memory plan of the encoder (bytes, 16-byte aligned regions).  Region A is used twice: first by the patch MLPs
+// (snapshot in bf16 + the GELU'd hidden layer), then by the encoder blocks' MLP (fp32 pre-LN hidden + its bf16 GELU).
+struct EncPlan { int ld_in, ld_hid, ld_e, ld_v, ld_h4; size_t off_z, off_n, off_q, off_k, off_v, off_a, a_hid, a_hh, a_hb, total; };
+__host__ __device__ inline EncPlan enc_plan(int FC, int Hs, int Es) {
+  EncPlan p{};
+  p.ld_in = pitch_of(FC); p.ld_hid = pitch_of(Hs); p.ld_e = pitch_of(Es); p.ld_v = pitch_of(P); p.ld_h4 = pitch_of(4 * Es);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t a = o; o += (bytes + 15) & ~static_cast<size_t>(15); return a; };
+  p.off_z = take(sizeof(float) * P * Es);
+  p.off_n = take(sizeof(bf16) * P * p.ld_e);
+  p.off_q = take(sizeof(bf16) * P * p.ld_e);
+  p.off_k = take(sizeof(bf16) * P * p.ld_e);
+  p.off_v = take(sizeof(bf16) * (Es + 8) * p.ld_v);
+  p.off_a = o;
+  const size_t in_bytes = (sizeof(bf16) * P * p.ld_in + 15) & ~static_cast<size_t>(15);
+  const size_t hh_bytes = (sizeof(float) * P * 4 * Es + 15) & ~static_cast<size_t>(15);
+  p.a_hid = p.off_a + in_bytes;
+  p.a_hh = p.off_a;
+  p.a_hb = p.off_a + hh_bytes;
+  const size_t use1 = in_bytes + sizeof(bf16) * P * p.ld_hid, use2 = hh_bytes + sizeof(bf16) * P * p.ld_h4;
+  p.total = p.off_a + (use1 > use2 ? use1 : use2);
+  return p;
+}
+
+// ------------------------------------------------------------------------------------ encoder
+__global__ void __launch_bounds__(kThreads, 1) spatial_encode_tc_kernel(const SpatialTC a, float* __restrict__ x,
+                                                                        float* __restrict__ z, int layout, float pad_idx,
+                                                                        int fix_pad) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int FC = a.n_fields * a.C, Es = a.n_groups * a.D, hd = Es / a.n_heads;
+  const EncPlan pl = enc_plan(FC, a.Hs, Es);
+  float* Z = reinterpret_cast<float*>(smraw + pl.off_z);     // [64][Es] fp32 residual state
+  bf16* Nn = reinterpret_cast<bf16*>(smraw + pl.off_n);      // [64][ld_e] normed input / attention output
+  bf16* Qs = reinterpret_cast<bf16*>(smraw + pl.off_q);
+  bf16* Ks = reinterpret_cast<bf16*>(smraw + pl.off_k);
+  bf16* Vt = reinterpret_cast<bf16*>(smraw + pl.off_v);      // [Es + 8][ld_v] values, transposed
+  bf16* Xin = reinterpret_cast<bf16*>(smraw + pl.off_a);     // [64][ld_in]
+  bf16* Hid = reinterpret_cast<bf16*>(smraw + pl.a_hid);     // [64][ld_hid]
+  float* Hh = reinterpret_cast<float*>(smraw + pl.a_hh);     // [64][4 Es] fp32 (pre-LN MLP hidden)
+  bf16* Hb = reinterpret_cast<bf16*>(smraw + pl.a_hb);       // [64][ld_h4]
+  const int b = blockIdx.x;
+  float* xb = x + static_cast<long long>(b) * P * FC;
+  // (1) snapshot -> bf16; generate_padding_mask (models/encoder_decoder.py:173-176) in place
+  for (int i = threadIdx.x * 4; i < P * FC; i += kThreads * 4) {
+    float4 v = *reinterpret_cast<const float4*>(xb + i);
+    if (fix_pad) {
+      const bool hit = v.x == pad_idx || v.y == pad_idx || v.z == pad_idx || v.w == pad_idx;
+      if (hit) {
+        v.x = v.x == pad_idx ? 0.f : v.x; v.y = v.y == pad_idx ? 0.f : v.y;
+        v.z = v.z == pad_idx ? 0.f : v.z; v.w = v.w == pad_idx ? 0.f : v.w;
+        *reinterpret_cast<float4*>(xb + i) = v;
+      }
+    }
+    const int p = i / FC, c = i - p * FC;   // FC % 4 == 0: the four elements share a row
+    *reinterpret_cast<uint2*>(Xin + p * pl.ld_in + c) = make_uint2(ptx::pack_bf16(v.x, v.y), ptx::pack_bf16(v.z, v.w));
+  }
+  for (int i = threadIdx.x; i < 8 * pl.ld_v; i += kThreads) Vt[Es * pl.ld_v + i] = __float2bfloat16_rn(0.f);
+  __syncthreads();
+  // (2) per-group patch MLP: Linear(C*g, Hs, no bias) -> GELU -> Linear(Hs, D) + b, + positional encoding (:108-114)
+  for (int g = 0; g < a.n_groups; ++g) {
+    const int Kin = a.g_count[g] * a.C;
+    gemm64_any(Xin + a.g_first[g] * a.C, pl.ld_in, Kin, a.enc_w1[g], Kin, a.Hs,
+               [&](int row, int col, float v0, float v1) {
+                 *reinterpret_cast<uint32_t*>(Hid + row * pl.ld_hid + col) = ptx::pack_bf16(ptx::gelu_fast(v0), ptx::gelu_fast(v1));
+               });
+    __syncthreads();
+    const float* b2 = a.enc_b2[g];
+    gemm64_any(Hid, pl.ld_hid, a.Hs, a.enc_w2[g], a.Hs, a.D, [&](int row, int col, float v0, float v1) {
+      const int c = g * a.D + col;
+      const float2 pe = __ldg(reinterpret_cast<const float2*>(a.pe + row * Es + c));
+      *reinterpret_cast<float2*>(Z + row * Es + c) = make_float2(v0 + __ldg(b2 + col) + pe.x, v1 + __ldg(b2 + col + 1) + pe.y);
+    });
+    __syncthreads();
+  }
+  // (3) encoder blocks (base_blocks.py:123-138)
+  for (int l = 0; l < a.num_layers; ++l) {
+    const LayerTC& L = a.layers[l];
+    layernorm_rows(Z, Es, Es, L.ln1_w, nullptr, Nn, pl.ld_e, false);
+    __syncthreads();
+    gemm64_any(Nn, pl.ld_e, Es, L.qkv_w, Es, 3 * Es, [&](int row, int col, float v0, float v1) {
+      v0 += __ldg(L.qkv_b + col); v1 += __ldg(L.qkv_b + col + 1);
+      if (col < Es) *reinterpret_cast<uint32_t*>(Qs + row * pl.ld_e + col) = ptx::pack_bf16(v0, v1);
+      else if (col < 2 * Es) *reinterpret_cast<uint32_t*>(Ks + row * pl.ld_e + col - Es) = ptx::pack_bf16(v0, v1);
+      else {
+        Vt[(col - 2 * Es) * pl.ld_v + row] = __float2bfloat16_rn(v0);
+        Vt[(col - 2 * Es + 1) * pl.ld_v + row] = __float2bfloat16_rn(v1);
+      }
+    });
+    __syncthreads();
+    attention_dispatch_tc(hd, Qs, Ks, pl.ld_e, Vt, pl.ld_v, a.n_heads, Nn);
+    __syncthreads();
+    gemm64_any(Nn, pl.ld_e, Es, L.proj_w, Es, Es, [&](int row, int col, float v0, float v1) {
+      float2* zp = reinterpret_cast<float2*>(Z + row * Es + col);
+      const float2 zv = *zp;
+      *zp = make_float2(zv.x + v0, zv.y + v1);
+    });
+    __syncthreads();
+    layernorm_rows(Z, Es, Es, L.ln2_w, nullptr, Nn, pl.ld_e, false);
+    __syncthreads();
+    gemm64_any(Nn, pl.ld_e, Es, L.mlp0_w, Es, 4 * Es, [&](int row, int col, float v0, float v1) {
+      *reinterpret_cast<float2*>(Hh + row * 4 * Es + col) = make_float2(v0 + __ldg(L.mlp0_b + col), v1 + __ldg(L.mlp0_b + col + 1));
+    });
+    __syncthreads();
+    layernorm_rows(Hh, 4 * Es, 4 * Es, L.mlp_ln_w, L.mlp_ln_b, Hb, pl.ld_h4, true);
+    __syncthreads();
+    gemm64_any(Hb, pl.ld_h4, 4 * Es, L.mlp3_w, 4 * Es, Es, [&](int row, int col, float v0, float v1) {
+      float2* zp = reinterpret_cast<float2*>(Z + row * Es + col);
+      const float2 zv = *zp;
+      *zp = make_float2(zv.x + v0 + __ldg(L.mlp3_b + col), zv.y + v1 + __ldg(L.mlp3_b + col + 1));
+    });
+    __syncthreads();
+  }
+  // (4) final nn.LayerNorm(Es) (fp32) and the latent store (optionally already in the temporal layout)
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = warp; row < P; row += kWarps) {
+      const float* xr = Z + row * Es;
+      float s = 0.f;
+      for (int c = lane; c < Es; c += 32) s += xr[c];
+      const float mean = warp_sum(s) / Es;
+      float q = 0.f;
+      for (int c = lane; c < Es; c += 32) { const float e = xr[c] - mean; q = fmaf(e, e, q); }
+      const float rstd = rsqrtf(warp_sum(q) / Es + 1e-5f);
+      for (int c = lane; c < Es; c += 32) {
+        const int g = c / a.D, d = c - g * a.D;
+        z[latent_index(b, row, g, d, a.n_groups, a.D, layout)] = (xr[c] - mean) * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ decoder
+__global__ void __launch_bounds__(kThreads, 1) spatial_decode_tc_kernel(const SpatialTC a, const float* __restrict__ z,
+                                                                        float* __restrict__ out, int layout) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int FC = a.n_fields * a.C, Es = a.n_groups * a.D;
+  const int ld_e = pitch_of(Es), ld_hid = pitch_of(a.Hs);
+  bf16* Zb = reinterpret_cast<bf16*>(smraw);                                  // [64][ld_e]
+  bf16* Hid = Zb + ((P * ld_e + 7) & ~7);                                     // [64][ld_hid]
+  const int b = blockIdx.x;
+  float* ob = out + static_cast<long long>(b) * P * FC;
+  for (int i = threadIdx.x; i < P * Es; i += kThreads) {
+    const int p = i / Es, c = i - p * Es, g = c / a.D, d = c - g * a.D;
+    Zb[p * ld_e + c] = __float2bfloat16_rn(z[latent_index(b, p, g, d, a.n_groups, a.D, layout)]);
+  }
+  __syncthreads();
+  // per group: Linear(D, Hs, no bias) -> GELU -> Linear(Hs, C*g) + b   (encoder_decoder.py:140-143)
+  for (int g = 0; g < a.n_groups; ++g) {
+    const int Nout = a.g_count[g] * a.C;
+    gemm64_any(Zb + g * a.D, ld_e, a.D, a.dec_w1[g], a.D, a.Hs, [&](int row, int col, float v0, float v1) {
+      *reinterpret_cast<uint32_t*>(Hid + row * ld_hid + col) = ptx::pack_bf16(ptx::gelu_fast(v0), ptx::gelu_fast(v1));
+    });
+    __syncthreads();
+    const float* b2 = a.dec_b2[g];
+    float* og = ob + a.g_first[g] * a.C;
+    gemm64_any(Hid, ld_hid, a.Hs, a.dec_w2[g], a.Hs, Nout, [&](int row, int col, float v0, float v1) {
+      *reinterpret_cast<float2*>(og + row * FC + col) = make_float2(v0 + __ldg(b2 + col), v1 + __ldg(b2 + col + 1));
+    });
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+struct CacheMap {
+  size_t enc_w1[4], enc_w2[4], dec_w1[4], dec_w2[4];
+  size_t qkv_w[16], proj_w[16], mlp0_w[16], mlp3_w[16], qkv_b[16];
+  size_t total;
+};
+
+int check_desc(const sea_spatial_desc* d) {
+  if (!d || d->n_groups < 1 || d->n_groups > 4 || d->num_layers < 0 || d->num_layers > 16) return SEA_ERR_UNSUPPORTED;
+  if (d->n_patches != P || d->n_heads < 1) return SEA_ERR_UNSUPPORTED;
+  const int Es = d->n_groups * d->embed_dim;
+  if (Es % d->n_heads) return SEA_ERR_UNSUPPORTED;
+  const int hd = Es / d->n_heads;
+  if (hd != 2 && hd != 4 && hd != 8 && hd != 16) return SEA_ERR_UNSUPPORTED;
+  // contraction widths must be multiples of 16 (one k-step), output widths multiples of 8 (one n-tile)
+  if ((d->embed_dim % 16) || (d->mlp_hidden % 16) || (Es % 16) || (d->n_inp % 8)) return SEA_ERR_UNSUPPORTED;
+  for (int g = 0; g < d->n_groups; ++g) {
+    const int cnt = d->group_num_fields[g], first = d->group_first_field[g];
+    if (cnt < 1 || first < 0 || first + cnt > d->n_fields) return SEA_ERR_INVALID;
+    if ((cnt * d->n_inp) % 16) return SEA_ERR_UNSUPPORTED;
+  }
+  return SEA_OK;
+}
+
+void map_cache(const sea_spatial_desc* d, CacheMap& m) {
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t a = o; o += (bytes + 255) & ~static_cast<size_t>(255); return a; };
+  const size_t Hs = d->mlp_hidden, D = d->embed_dim, Es = static_cast<size_t>(d->n_groups) * D;
+  for (int g = 0; g < d->n_groups; ++g) {
+    const size_t Kg = static_cast<size_t>(d->group_num_fields[g]) * d->n_inp;
+    m.enc_w1[g] = take(2 * Hs * Kg); m.enc_w2[g] = take(2 * D * Hs);
+    m.dec_w1[g] = take(2 * Hs * D); m.dec_w2[g] = take(2 * Kg * Hs);
+  }
+  for (int l = 0; l < d->num_layers; ++l) {
+    m.qkv_w[l] = take(2 * 3 * Es * Es); m.proj_w[l] = take(2 * Es * Es);
+    m.mlp0_w[l] = take(2 * 4 * Es * Es); m.mlp3_w[l] = take(2 * 4 * Es * Es);
+    m.qkv_b[l] = take(4 * 3 * Es);
+  }
+  m.total = o + 256;
+}
+
+int fill_tc(const sea_spatial_desc* d, const void* cache, SpatialTC& a) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!cache || (reinterpret_cast<uintptr_t>(cache) & 255)) return SEA_ERR_INVALID;
+  CacheMap m;
+  map_cache(d, m);
+  const char* base = static_cast<const char*>(cache);
+  a.n_groups = d->n_groups; a.n_fields = d->n_fields; a.C = d->n_inp; a.Hs = d->mlp_hidden;
+  a.D = d->embed_dim; a.n_heads = d->n_heads; a.num_layers = d->num_layers;
+  for (int g = 0; g < d->n_groups; ++g) {
+    a.g_first[g] = d->group_first_field[g]; a.g_count[g] = d->group_num_fields[g];
+    a.enc_w1[g] = reinterpret_cast<const bf16*>(base + m.enc_w1[g]); a.enc_w2[g] = reinterpret_cast<const bf16*>(base + m.enc_w2[g]);
+    a.dec_w1[g] = reinterpret_cast<const bf16*>(base + m.dec_w1[g]); a.dec_w2[g] = reinterpret_cast<const bf16*>(base + m.dec_w2[g]);
+    a.enc_b2[g] = d->enc_b2[g]; a.dec_b2[g] = d->dec_b2[g];
+  }
+  a.ln_w = d->ln_w; a.ln_b = d->ln_b; a.pe = d->pe;
+  for (int l = 0; l < d->num_layers; ++l) {
+    const sea_spatial_layer& s = d->layers[l];
+    a.layers[l] = LayerTC{reinterpret_cast<const bf16*>(base + m.qkv_w[l]), reinterpret_cast<const bf16*>(base + m.proj_w[l]),
+                          reinterpret_cast<const bf16*>(base + m.mlp0_w[l]), reinterpret_cast<const bf16*>(base + m.mlp3_w[l]),
+                          reinterpret_cast<const float*>(base + m.qkv_b[l]), s.ln1_w, s.ln2_w, s.mlp0_b, s.mlp_ln_w,
+                          s.mlp_ln_b, s.mlp3_b};
+  }
+  return SEA_OK;
+}
+
+}  // namespace
+}  // namespace sea
+
+using namespace sea;
+
+extern "C" size_t sea_spatial_cache_bytes(const sea_spatial_desc* d) {
+  if (check_desc(d) != SEA_OK) return 0;
+  CacheMap m;
+  map_cache(d, m);
+  return m.total;
+}
+
+extern "C" int sea_spatial_pack(const sea_spatial_desc* d, void* cache, size_t cache_bytes, sea_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!cache || (reinterpret_cast<uintptr_t>(cache) & 255)) return SEA_ERR_INVALID;
+  CacheMap m;
+  map_cache(d, m);
+  if (cache_bytes < m.total) return SEA_ERR_WORKSPACE;
+  char* base = static_cast<char*>(cache);
+  const int64_t Hs = d->mlp_hidden, D = d->embed_dim, Es = static_cast<int64_t>(d->n_groups) * D;
+  auto cast = [&](const float* src, size_t off, int64_t n) -> int {
+    if (!src) return SEA_ERR_INVALID;
+    return sea_cast_f32_bf16(src, base + off, n, stream);
+  };
+#define SEA_TRY_(e) do { int _rc = (e); if (_rc != SEA_OK) return _rc; } while (0)
+  for (int g = 0; g < d->n_groups; ++g) {
+    const int64_t Kg = static_cast<int64_t>(d->group_num_fields[g]) * d->n_inp;
+    if (d->enc_w1[g]) { SEA_TRY_(cast(d->enc_w1[g], m.enc_w1[g], Hs * Kg)); SEA_TRY_(cast(d->enc_w2[g], m.enc_w2[g], D * Hs)); }
+    if (d->dec_w1[g]) { SEA_TRY_(cast(d->dec_w1[g], m.dec_w1[g], Hs * D)); SEA_TRY_(cast(d->dec_w2[g], m.dec_w2[g], Kg * Hs)); }
+  }
+  if (d->num_layers > 0 && !d->layers) return SEA_ERR_INVALID;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  for (int l = 0; l < d->num_layers; ++l) {
+    const sea_spatial_layer& L = d->layers[l];
+    SEA_TRY_(cast(L.q_w, m.qkv_w[l], Es * Es));
+    SEA_TRY_(cast(L.k_w, m.qkv_w[l] + 2 * Es * Es, Es * Es));
+    SEA_TRY_(cast(L.v_w, m.qkv_w[l] + 4 * Es * Es, Es * Es));
+    SEA_TRY_(cast(L.proj_w, m.proj_w[l], Es * Es));
+    SEA_TRY_(cast(L.mlp0_w, m.mlp0_w[l], 4 * Es * Es));
+    SEA_TRY_(cast(L.mlp3_w, m.mlp3_w[l], 4 * Es * Es));
+    if (!L.q_b || !L.k_b || !L.v_b) return SEA_ERR_INVALID;
+    SEA_CUDA_OK(cudaMemcpyAsync(base + m.qkv_b[l], L.q_b, 4 * Es, cudaMemcpyDeviceToDevice, s));
+    SEA_CUDA_OK(cudaMemcpyAsync(base + m.qkv_b[l] + 4 * Es, L.k_b, 4 * Es, cudaMemcpyDeviceToDevice, s));
+    SEA_CUDA_OK(cudaMemcpyAsync(base + m.qkv_b[l] + 8 * Es, L.v_b, 4 * Es, cudaMemcpyDeviceToDevice, s));
+  }
+#undef SEA_TRY_
+  return SEA_OK;
+}
+
+extern "C" int sea_spatial_encode_tc(const sea_spatial_desc* d, const void* cache, float* x, float* z, int B,
+                                     int latent_layout, float pad_idx, int fix_pad, sea_stream_t stream) {
+  if (!x || !z || B <= 0) return SEA_ERR_INVALID;
+  SpatialTC a{};
+  int rc = fill_tc(d, cache, a);
+  if (rc) return rc;
+  for (int g = 0; g < a.n_groups; ++g)
+    if (!d->enc_w1[g] || !d->enc_w2[g] || !a.enc_b2[g]) return SEA_ERR_INVALID;
+  if (!a.ln_w || !a.ln_b || !a.pe) return SEA_ERR_INVALID;
+  const EncPlan pl = enc_plan(a.n_fields * a.C, a.Hs, a.n_groups * a.D);
+  if (pl.total > 227 * 1024) return SEA_ERR_UNSUPPORTED;
+  SEA_CUDA_OK(cudaFuncSetAttribute(spatial_encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.total)));
+  SEA_LAUNCH(spatial_encode_tc_kernel, B, kThreads, pl.total, reinterpret_cast<cudaStream_t>(stream), a, x, z, latent_layout,
+             pad_idx, fix_pad);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_spatial_decode_tc(const sea_spatial_desc* d, const void* cache, const float* z, float* out, int B,
+                                     int latent_layout, sea_stream_t stream) {
+  if (!z || !out || B <= 0) return SEA_ERR_INVALID;
+  SpatialTC a{};
+  int rc = fill_tc(d, cache, a);
+  if (rc) return rc;
+  for (int g = 0; g < a.n_groups; ++g)
+    if (!d->dec_w1[g] || !d->dec_w2[g] || !a.dec_b2[g]) return SEA_ERR_INVALID;
+  const int Es = a.n_groups * a.D;
+  const size_t smem = sizeof(bf16) * (((P * pitch_of(Es) + 7) & ~7) + static_cast<size_t>(P) * pitch_of(a.Hs)) + 16;
+  if (smem > 227 * 1024) return SEA_ERR_UNSUPPORTED;
+  SEA_CUDA_OK(cudaFuncSetAttribute(spatial_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  SEA_LAUNCH(spatial_decode_tc_kernel, B, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), a, z, out, latent_layout);
+  return static_cast<int>(cudaGetLastError());
+}

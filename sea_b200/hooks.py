@@ -27,7 +27,8 @@ def _is_cuda(device) -> bool:
     return torch.device(device).type == "cuda"
 
 
-def install(precision: str = "bf16", fused_optimizer: bool = False, spatial: bool = True) -> None:
+def install(precision: str = "bf16", fused_optimizer: bool = False, spatial: bool = True,
+            spatial_precision: str = "fp32") -> None:
     """Wrap the reference factories (idempotent).  ``fused_optimizer=True`` additionally replaces the
     ``torch.optim.AdamW`` the reference builds (utils/train_utils.py:33-39) by ``sea_b200.optim.AdamW`` with the
     same hyper-parameters (same arithmetic, one launch per step)."""
@@ -54,6 +55,7 @@ def install(precision: str = "bf16", fused_optimizer: bool = False, spatial: boo
         get_model.__wrapped__ = ref_get_model
         tt.get_model = get_model
     _saved["precision"], _saved["fused_optimizer"] = precision, bool(fused_optimizer)
+    _saved["spatial_precision"] = spatial_precision
 
     if spatial and "init_spatial" not in _saved:
         dp = importlib.import_module("utils.data_processors")
@@ -63,7 +65,7 @@ def install(precision: str = "bf16", fused_optimizer: bool = False, spatial: boo
         def initialize_spatial_model(self):
             model = ref_init(self)
             if _is_cuda(self.device) and not getattr(model, "variational", False):
-                accelerate_spatial(model)
+                accelerate_spatial(model, precision=_saved.get("spatial_precision", "fp32"))
             return model
 
         initialize_spatial_model.__wrapped__ = ref_init
@@ -79,3 +81,4 @@ def uninstall() -> None:
         cls.initialize_spatial_model = fn
     _saved.pop("precision", None)
     _saved.pop("fused_optimizer", None)
+    _saved.pop("spatial_precision", None)

@@ -111,11 +111,16 @@ def _init_block_weights(m):
 class SpatialCodec:
     """Builds the C descriptor from any module tree with the reference's naming and runs the kernels."""
 
-    def __init__(self, module):
+    def __init__(self, module, precision: str = "fp32"):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' (CUDA-core fp32 kernels, 1e-4 parity) or 'bf16' (tensor cores, 2e-2)")
         self.module = module
+        self.precision = precision
         self._desc = None
         self._keep = None
         self._key = None
+        self._wcache = None       # bf16 weight copies of the tensor-core kernels (sea_spatial_pack)
+        self._wkey = None
 
     def _build(self):
         m = self.module
@@ -165,6 +170,21 @@ class SpatialCodec:
         if self._desc is None or key != self._key:
             self._build()
             self._key = key
+            self._wkey = None
+        if self.precision == "bf16":
+            wkey = sum(p._version for p in self.module.parameters())
+            if self._wkey != wkey:      # (re)round the weights to bf16 after any parameter update
+                dev = self.module.encode.ln.weight.device
+                n = lib.sea_spatial_cache_bytes(C.byref(self._desc))
+                if n == 0:
+                    raise NotImplementedError("tensor-core codec needs embed_dim, mlp_hidden and n_inp*|group| to be multiples "
+                                              "of 16 (use precision='fp32' for other shapes)")
+                if self._wcache is None or self._wcache.numel() < n or self._wcache.device != dev:
+                    self._wcache = torch.empty(n, dtype=torch.uint8, device=dev)
+                with torch.cuda.device(dev):
+                    check(lib.sea_spatial_pack(C.byref(self._desc), C.c_void_p(self._wcache.data_ptr()), C.c_size_t(n),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), "spatial_pack")
+                self._wkey = wkey
 
     @torch.no_grad()
     def encode(self, x, fix_pad=False, latent_layout=0, pad_idx=-9999.0):
@@ -179,9 +199,14 @@ class SpatialCodec:
         shape = (B, 64, dm["G"], dm["D"]) if latent_layout == 0 else (B, dm["G"], 64 * dm["D"])
         z = torch.empty(shape, device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
-            check(lib.sea_spatial_encode(C.byref(self._desc), C.c_void_p(x.data_ptr()), C.c_void_p(z.data_ptr()),
-                                         B, latent_layout, C.c_float(pad_idx), int(fix_pad),
-                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "spatial_encode")
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if self.precision == "bf16":
+                check(lib.sea_spatial_encode_tc(C.byref(self._desc), C.c_void_p(self._wcache.data_ptr()),
+                                                C.c_void_p(x.data_ptr()), C.c_void_p(z.data_ptr()), B, latent_layout,
+                                                C.c_float(pad_idx), int(fix_pad), st), "spatial_encode_tc")
+            else:
+                check(lib.sea_spatial_encode(C.byref(self._desc), C.c_void_p(x.data_ptr()), C.c_void_p(z.data_ptr()),
+                                             B, latent_layout, C.c_float(pad_idx), int(fix_pad), st), "spatial_encode")
         return z
 
     @torch.no_grad()
@@ -194,9 +219,14 @@ class SpatialCodec:
         z = z.contiguous().float()
         out = torch.empty(B, 64, dm["F"], dm["C"], device=z.device, dtype=torch.float32)
         with torch.cuda.device(z.device):
-            check(lib.sea_spatial_decode(C.byref(self._desc), C.c_void_p(z.data_ptr()), C.c_void_p(out.data_ptr()),
-                                         B, latent_layout, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
-                  "spatial_decode")
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if self.precision == "bf16":
+                check(lib.sea_spatial_decode_tc(C.byref(self._desc), C.c_void_p(self._wcache.data_ptr()),
+                                                C.c_void_p(z.data_ptr()), C.c_void_p(out.data_ptr()), B, latent_layout, st),
+                      "spatial_decode_tc")
+            else:
+                check(lib.sea_spatial_decode(C.byref(self._desc), C.c_void_p(z.data_ptr()), C.c_void_p(out.data_ptr()),
+                                             B, latent_layout, st), "spatial_decode")
         return out
 
 
@@ -204,8 +234,9 @@ class SpatialModel(nn.Module):
     """Drop-in for models/encoder_decoder.py:SpatialModel (variational=False)."""
 
     def __init__(self, field_groups, n_inp, MLP_hidden, num_layers, embed_dim, n_heads, max_len, src_len,
-                 dropout=0.1, variational=False):
+                 dropout=0.1, variational=False, precision="fp32"):
         super().__init__()
+        self.precision = precision
         if variational:
             raise NotImplementedError("sea_b200 implements the PointwiseEncode path (variational=False) only")
         self.variational = False
@@ -215,7 +246,7 @@ class SpatialModel(nn.Module):
 
     def _codec(self) -> SpatialCodec:
         if self._codec_obj is None:
-            object.__setattr__(self, "_codec_obj", SpatialCodec(self))
+            object.__setattr__(self, "_codec_obj", SpatialCodec(self, self.precision))
         return self._codec_obj
 
     def generate_padding_mask(self, x, pad_idx=-9999):
@@ -229,11 +260,12 @@ class SpatialModel(nn.Module):
         return self._codec().decode(z)
 
 
-def accelerate_spatial(model: nn.Module) -> nn.Module:
-    """Rebind encode / decode / forward of an UNCHANGED reference SpatialModel instance."""
+def accelerate_spatial(model: nn.Module, precision: str = "fp32") -> nn.Module:
+    """Rebind encode / decode / forward of an UNCHANGED reference SpatialModel instance.  precision: "fp32" (CUDA-core
+    kernels, 1e-4 of the eager module) or "bf16" (tensor-core kernels: bf16 operands, fp32 accumulation, 2e-2)."""
     if getattr(model, "variational", False):
         raise NotImplementedError("variational encoder is out of scope")
-    codec = SpatialCodec(model)
+    codec = SpatialCodec(model, precision)
     enc_mod, dec_mod = model.encode, model.decode
     enc_mod.forward = types.MethodType(lambda self, x: codec.encode(x, fix_pad=False), enc_mod)
     dec_mod.forward = types.MethodType(lambda self, z: codec.decode(z), dec_mod)

@@ -112,3 +112,54 @@ def test_spatial_throughput_report(cuda):
     print(f"\n[spatial perf] cylinder B={B}: encode {te:.2f} ms ({B/te*1e3:.0f} snapshots/s, "
           f"{flops_enc*B/te/1e9:.1f} TFLOP/s fp32, {B*(49152+8192)/te/1e6:.1f} GB/s algorithmic), "
           f"decode {td:.2f} ms ({B/td*1e3:.0f} snapshots/s)")
+
+
+@pytest.mark.parametrize("tag", ["cylinder_flow", "multiphase_flow"])
+def test_tensor_core_codec_matches_reference_golden(cuda, tag):
+    """precision='bf16': every contraction of the codec on mma.sync bf16 tensor-core tiles (sea_spatial_encode_tc /
+    _decode_tc).  Bar: north_star's bf16 tolerance (2e-2 relative) against the unmodified reference's fp32 goldens;
+    measured values are printed.  Same in-place pad rewrite, same latent layouts."""
+    from sea_b200.spatial import SpatialModel
+    g, sd, cfg, x = spatial_case(tag)
+    n_inp, hidden, layers, D, nh, B = [int(v) for v in g["meta"]]
+    m = SpatialModel(cfg["field_groups"], n_inp, hidden, layers, D, nh, 2024, 0, 0.0, False, precision="bf16")
+    m.load_state_dict(sd, strict=False)
+    m = m.to(cuda).eval()
+    xin = x.clone().to(cuda)
+    with torch.no_grad():
+        y = m(xin)
+        z = m.encode(xin)
+        y2 = m.decode(torch.as_tensor(g["z"]).to(cuda))     # decoder alone, from the reference's latents
+    torch.cuda.synchronize()
+    ez, ey, ey2 = rel_l2(z.cpu(), g["z"]), rel_l2(y.cpu(), g["y"]), rel_l2(y2.cpu(), g["y"])
+    print(f"\n[spatial tc] {tag}: latent rel {ez:.2e}, reconstruction rel {ey:.2e}, decoder alone {ey2:.2e}")
+    assert ez < 2e-2 and ey < 2e-2 and ey2 < 2e-2
+    assert np.array_equal(xin.cpu().numpy()[0, 0, 0, -4:], g["x_after"])
+    codec = m._codec()
+    lat = codec.encode(xin, latent_layout=1)
+    assert torch.equal(lat.view(B, 2, 64, D).permute(0, 2, 1, 3), z)        # layout 1 is a pure permutation of layout 0
+    assert torch.equal(codec.decode(lat, latent_layout=1), m.decode(z))
+    # weights re-packed after a parameter update
+    with torch.no_grad():
+        m.encode.ln.bias.add_(0.5)
+        m.encode.encoders[0].layer2.weight.mul_(1.5)
+        z2 = m.encode(xin)
+        ref2 = so.spatial_encode(xin.cpu(), {k: v.detach().cpu() for k, v in m.state_dict().items()}, **cfg)
+    assert rel_l2(z2.cpu(), ref2) < 2e-2 and rel_l2(z2.cpu(), g["z"]) > 0.05
+
+
+def test_tensor_core_codec_ragged_batches_vs_fp32_kernels(cuda):
+    """Batch sizes 1 / 37 / 300 and a different n_inp (C = 32, 128): the tensor-core kernels against the fp32 CUDA-core
+    kernels of the same library on the same weights."""
+    from sea_b200.spatial import SpatialModel
+    for C_, B in ((32, 1), (64, 37), (128, 300)):
+        torch.manual_seed(C_)
+        a = SpatialModel([[0, 1], [2]], C_, 480, 12, 16, 8, 2024, 0, 0.0, False, precision="fp32").to(cuda).eval()
+        b = SpatialModel([[0, 1], [2]], C_, 480, 12, 16, 8, 2024, 0, 0.0, False, precision="bf16").to(cuda).eval()
+        b.load_state_dict(a.state_dict())
+        x = torch.randn(B, 64, 3, C_, device=cuda)
+        x[:, :, :, C_ - 5:] = 0.0
+        with torch.no_grad():
+            za, zb = a.encode(x), b.encode(x)
+            ya, yb = a.decode(za), b.decode(za)
+        assert rel_l2(zb.cpu(), za.cpu()) < 2e-2 and rel_l2(yb.cpu(), ya.cpu()) < 2e-2, (C_, B)
