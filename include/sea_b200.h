@@ -634,7 +634,7 @@ int sea_profile_end(sea_profile_summary* out);
  * x / out: [B, 64, n_fields, n_inp] fp32; z: [B, 64, G, D] (latent_layout 0) or the temporal
  * model's [B, G, 64*D] (latent_layout 1 = transform_processed_data, utils/train_utils.py:315-337,
  * fused into the store / load).  All parameters fp32, reference layouts.  n_patches must be 64,
- * n_inp / embed_dim / mlp_hidden multiples of 4, head_dim = G*D/n_heads in {2,4,8,16}, <= 16 layers. */
+ * embed_dim / mlp_hidden multiples of 4 (n_inp arbitrary; multiples of 4 take the vector path), head_dim = G*D/n_heads in {2,4,8,16}, <= 16 layers. */
 typedef struct sea_spatial_layer {
   const float *ln1_w, *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *proj_w, *ln2_w;
   const float *mlp0_w, *mlp0_b, *mlp_ln_w, *mlp_ln_b, *mlp3_w, *mlp3_b;
@@ -663,8 +663,8 @@ int sea_spatial_decode(const sea_spatial_desc* d, const float* z, float* out, in
  * of the 8-head attention) on the tensor cores: warp-level bf16 mma.sync.m16n8k16, fp32 accumulation; residual state,
  * LayerNorm statistics, softmax and GELU in fp32 (the bf16 parity mode: 2e-2 bar; the fp32 kernels above keep the 1e-4
  * bar).  Weights are rounded to bf16 once into a caller-owned cache (256-byte aligned, sea_spatial_cache_bytes):
- * sea_spatial_pack must run after every parameter update.  Needs embed_dim, mlp_hidden, n_inp*|group| multiples of 16
- * and n_inp a multiple of 8; SEA_ERR_UNSUPPORTED when a snapshot's working set exceeds the 227 KB of shared memory. */
+ * sea_spatial_pack must run after every parameter update.  Needs embed_dim and mlp_hidden multiples of 16 (n_inp is
+ * arbitrary: its axis is zero-padded to a multiple of 16 at pack time); SEA_ERR_UNSUPPORTED when a snapshot's working set exceeds the 227 KB of shared memory. */
 size_t sea_spatial_cache_bytes(const sea_spatial_desc* d);
 int sea_spatial_pack(const sea_spatial_desc* d, void* cache, size_t cache_bytes, sea_stream_t stream);
 int sea_spatial_encode_tc(const sea_spatial_desc* d, const void* cache, float* x, float* z, int B, int latent_layout,

@@ -73,6 +73,27 @@ __device__ __forceinline__ void linear64(const float* __restrict__ X, int ldx, i
   }
 }
 
+// Same contraction with scalar loads: rows of X / W that are not 16-byte aligned (n_inp not a multiple of 4 — the
+// reference sets n_inp to the cell count of the fullest patch, utils/data_processors.py:61-88, an arbitrary integer).
+__device__ __forceinline__ void linear64_scalar(const float* __restrict__ X, int ldx, int K, const float* __restrict__ W,
+                                                int ldw, int N, float* __restrict__ Y, int ldy, bool gelu) {
+  for (int item = threadIdx.x; item < N * 8; item += kThreads) {
+    const int rg = item / N, n = item - rg * N;
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    const float* wrow = W + static_cast<long long>(n) * ldw;
+    const float* xrow = X + rg * 8 * ldx;
+    for (int k = 0; k < K; ++k) {
+      const float w = __ldg(wrow + k);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = fmaf(xrow[r * ldx + k], w, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) Y[(rg * 8 + r) * ldy + n] = gelu ? ptx::gelu_erf(acc[r]) : acc[r];
+  }
+}
+
 // Row LayerNorm over d columns for the 64 rows (warp per row): Y = (X-mean)*rstd*w (+b), opt. GELU.
 __device__ __forceinline__ void layernorm64(const float* __restrict__ X, int ldx, int d,
                                             const float* __restrict__ w, const float* __restrict__ b,
@@ -188,7 +209,8 @@ __global__ void __launch_bounds__(kThreads) spatial_encode_kernel(const SpatialD
     const float* xin = Xin + a.g_first[g] * a.C;
     for (int c0 = 0; c0 < a.Hs; c0 += kChunk) {
       const int ch = min(kChunk, a.Hs - c0);
-      linear64<false>(xin, FC, Kin, a.enc_w1[g] + static_cast<long long>(c0) * Kin, Kin, nullptr, ch, BIG, big_w, true);
+      if ((a.C & 3) == 0) linear64<false>(xin, FC, Kin, a.enc_w1[g] + static_cast<long long>(c0) * Kin, Kin, nullptr, ch, BIG, big_w, true);
+      else linear64_scalar(xin, FC, Kin, a.enc_w1[g] + static_cast<long long>(c0) * Kin, Kin, ch, BIG, big_w, true);
       __syncthreads();
       if (c0 == 0) linear64<false>(BIG, big_w, ch, a.enc_w2[g] + c0, a.Hs, a.enc_b2[g], a.D, Z + g * a.D, Es, false);
       else linear64<true>(BIG, big_w, ch, a.enc_w2[g] + c0, a.Hs, nullptr, a.D, Z + g * a.D, Es, false);
@@ -267,7 +289,7 @@ __global__ void __launch_bounds__(kThreads) spatial_decode_kernel(const SpatialD
 int fill_dev(const sea_spatial_desc* d, SpatialDev& a) {
   if (!d || d->n_groups < 1 || d->n_groups > 4 || d->num_layers < 0 || d->num_layers > 16) return SEA_ERR_UNSUPPORTED;
   if (d->n_patches != P) return SEA_ERR_UNSUPPORTED;
-  if ((d->n_inp % 4) || (d->embed_dim % 4) || (d->mlp_hidden % 4) || d->n_heads < 1) return SEA_ERR_UNSUPPORTED;
+  if (d->n_inp < 1 || (d->embed_dim % 4) || (d->mlp_hidden % 4) || d->n_heads < 1) return SEA_ERR_UNSUPPORTED;
   const int Es = d->n_groups * d->embed_dim;
   if (Es % d->n_heads) return SEA_ERR_UNSUPPORTED;
   const int hd = Es / d->n_heads;

@@ -13,7 +13,10 @@
 // Activations are bf16 in shared memory with a row pitch == 32 (mod 64) elements, which makes the quad-wise 16-byte
 // loads bank-conflict free; the residual stream, LayerNorm statistics, softmax and GELU stay fp32.
 //
-// Weights are pre-rounded to bf16 once (sea_spatial_pack: q|k|v fused along N) into a caller-owned cache.
+// Weights are pre-rounded to bf16 once (sea_spatial_pack: q|k|v fused along N) into a caller-owned cache.  n_inp (cells of
+// the fullest patch: data dependent, utils/data_processors.py:61-88, train/train_temporal.py:147) is arbitrary: the
+// pack step pads every field's cell axis of the patch-MLP weights to a multiple of 16 with zeros, the kernels pad the
+// snapshot the same way in shared memory and mask the decoder's stores.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -35,7 +38,7 @@ struct LayerTC {
   const float *qkv_b, *ln1_w, *ln2_w, *mlp0_b, *mlp_ln_w, *mlp_ln_b, *mlp3_b;
 };
 struct SpatialTC {
-  int n_groups, n_fields, C, Hs, D, n_heads, num_layers;
+  int n_groups, n_fields, C, Cp, Hs, D, n_heads, num_layers;   // Cp: cells per patch padded to a multiple of 16
   int g_first[4], g_count[4];
   const bf16 *enc_w1[4], *enc_w2[4], *dec_w1[4], *dec_w2[4];
   const float *enc_b2[4], *dec_b2[4];
@@ -263,8 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_encode_tc_kernel(const Sp
   ptx::pdl_trigger();
   ptx::pdl_wait();
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int FC = a.n_fields * a.C, Es = a.n_groups * a.D, hd = Es / a.n_heads;
-  const EncPlan pl = enc_plan(FC, a.Hs, Es);
+  const int FC = a.n_fields * a.C, FCp = a.n_fields * a.Cp, Es = a.n_groups * a.D, hd = Es / a.n_heads;
+  const EncPlan pl = enc_plan(FCp, a.Hs, Es);
   float* Z = reinterpret_cast<float*>(smraw + pl.off_z);     // [64][Es] fp32 residual state
   bf16* Nn = reinterpret_cast<bf16*>(smraw + pl.off_n);      // [64][ld_e] normed input / attention output
   bf16* Qs = reinterpret_cast<bf16*>(smraw + pl.off_q);
@@ -277,25 +280,44 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_encode_tc_kernel(const Sp
   const int b = blockIdx.x;
   float* xb = x + static_cast<long long>(b) * P * FC;
   // (1) snapshot -> bf16; generate_padding_mask (models/encoder_decoder.py:173-176) in place
-  for (int i = threadIdx.x * 4; i < P * FC; i += kThreads * 4) {
-    float4 v = *reinterpret_cast<const float4*>(xb + i);
-    if (fix_pad) {
-      const bool hit = v.x == pad_idx || v.y == pad_idx || v.z == pad_idx || v.w == pad_idx;
-      if (hit) {
-        v.x = v.x == pad_idx ? 0.f : v.x; v.y = v.y == pad_idx ? 0.f : v.y;
-        v.z = v.z == pad_idx ? 0.f : v.z; v.w = v.w == pad_idx ? 0.f : v.w;
-        *reinterpret_cast<float4*>(xb + i) = v;
+  if ((a.C & 3) == 0) {
+    for (int i = threadIdx.x * 4; i < P * FC; i += kThreads * 4) {
+      float4 v = *reinterpret_cast<const float4*>(xb + i);
+      if (fix_pad) {
+        const bool hit = v.x == pad_idx || v.y == pad_idx || v.z == pad_idx || v.w == pad_idx;
+        if (hit) {
+          v.x = v.x == pad_idx ? 0.f : v.x; v.y = v.y == pad_idx ? 0.f : v.y;
+          v.z = v.z == pad_idx ? 0.f : v.z; v.w = v.w == pad_idx ? 0.f : v.w;
+          *reinterpret_cast<float4*>(xb + i) = v;
+        }
       }
+      const int pf = i / a.C, c = i - pf * a.C;   // C % 4 == 0: the four elements share a (patch, field) row
+      const int p = pf / a.n_fields, f = pf - p * a.n_fields;
+      *reinterpret_cast<uint2*>(Xin + p * pl.ld_in + f * a.Cp + c) = make_uint2(ptx::pack_bf16(v.x, v.y), ptx::pack_bf16(v.z, v.w));
     }
-    const int p = i / FC, c = i - p * FC;   // FC % 4 == 0: the four elements share a row
-    *reinterpret_cast<uint2*>(Xin + p * pl.ld_in + c) = make_uint2(ptx::pack_bf16(v.x, v.y), ptx::pack_bf16(v.z, v.w));
+  } else {
+    for (int i = threadIdx.x; i < P * FC; i += kThreads) {
+      float v = xb[i];
+      if (fix_pad && v == pad_idx) { v = 0.f; xb[i] = 0.f; }
+      const int pf = i / a.C, c = i - pf * a.C;
+      const int p = pf / a.n_fields, f = pf - p * a.n_fields;
+      Xin[p * pl.ld_in + f * a.Cp + c] = __float2bfloat16_rn(v);
+    }
+  }
+  if (a.Cp != a.C) {   // zero the padded cells (their weight columns are zero too, but smem garbage may be NaN)
+    const int padw = a.Cp - a.C;
+    for (int i = threadIdx.x; i < P * a.n_fields * padw; i += kThreads) {
+      const int pf = i / padw, c = a.C + i - pf * padw;
+      const int p = pf / a.n_fields, f = pf - p * a.n_fields;
+      Xin[p * pl.ld_in + f * a.Cp + c] = __float2bfloat16_rn(0.f);
+    }
   }
   for (int i = threadIdx.x; i < 8 * pl.ld_v; i += kThreads) Vt[Es * pl.ld_v + i] = __float2bfloat16_rn(0.f);
   __syncthreads();
   // (2) per-group patch MLP: Linear(C*g, Hs, no bias) -> GELU -> Linear(Hs, D) + b, + positional encoding (:108-114)
   for (int g = 0; g < a.n_groups; ++g) {
-    const int Kin = a.g_count[g] * a.C;
-    gemm64_any(Xin + a.g_first[g] * a.C, pl.ld_in, Kin, a.enc_w1[g], Kin, a.Hs,
+    const int Kin = a.g_count[g] * a.Cp;
+    gemm64_any(Xin + a.g_first[g] * a.Cp, pl.ld_in, Kin, a.enc_w1[g], Kin, a.Hs,
                [&](int row, int col, float v0, float v1) {
                  *reinterpret_cast<uint32_t*>(Hid + row * pl.ld_hid + col) = ptx::pack_bf16(ptx::gelu_fast(v0), ptx::gelu_fast(v1));
                });
@@ -384,17 +406,49 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_decode_tc_kernel(const Sp
   __syncthreads();
   // per group: Linear(D, Hs, no bias) -> GELU -> Linear(Hs, C*g) + b   (encoder_decoder.py:140-143)
   for (int g = 0; g < a.n_groups; ++g) {
-    const int Nout = a.g_count[g] * a.C;
+    const int Nout = a.g_count[g] * a.Cp;   // padded: columns with cell index >= C are masked below
     gemm64_any(Zb + g * a.D, ld_e, a.D, a.dec_w1[g], a.D, a.Hs, [&](int row, int col, float v0, float v1) {
       *reinterpret_cast<uint32_t*>(Hid + row * ld_hid + col) = ptx::pack_bf16(ptx::gelu_fast(v0), ptx::gelu_fast(v1));
     });
     __syncthreads();
     const float* b2 = a.dec_b2[g];
     float* og = ob + a.g_first[g] * a.C;
+    const bool pair_ok = (a.C & 1) == 0;
     gemm64_any(Hid, ld_hid, a.Hs, a.dec_w2[g], a.Hs, Nout, [&](int row, int col, float v0, float v1) {
-      *reinterpret_cast<float2*>(og + row * FC + col) = make_float2(v0 + __ldg(b2 + col), v1 + __ldg(b2 + col + 1));
+      const int fi = col / a.Cp, c = col - fi * a.Cp;   // Cp even: both columns belong to the same field
+      if (c >= a.C) return;
+      const int n = fi * a.C + c;
+      float* dst = og + row * FC + n;
+      if (pair_ok) {   // C even: c + 1 < C as well, and the address is 8-byte aligned
+        *reinterpret_cast<float2*>(dst) = make_float2(v0 + __ldg(b2 + n), v1 + __ldg(b2 + n + 1));
+      } else {
+        dst[0] = v0 + __ldg(b2 + n);
+        if (c + 1 < a.C) dst[1] = v1 + __ldg(b2 + n + 1);
+      }
     });
     __syncthreads();
+  }
+}
+
+// fp32 [R, G*C] -> bf16 [R, G*Cp] (pad_rows = 0: every field's C columns padded to Cp with zeros) or
+// fp32 [G*C, Kc] -> bf16 [G*Cp, Kc] (pad_rows = 1: every field's C rows padded to Cp zero rows).
+__global__ void __launch_bounds__(256) pad_cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int G,
+                                                       int C, int Cp, int Kc, int pad_rows) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const long long total = pad_rows ? static_cast<long long>(G) * Cp * Kc : static_cast<long long>(R) * G * Cp;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    float v = 0.f;
+    if (pad_rows) {
+      const long long rp = i / Kc; const int k = static_cast<int>(i - rp * Kc);
+      const int f = static_cast<int>(rp / Cp), c = static_cast<int>(rp - static_cast<long long>(f) * Cp);
+      if (c < C) v = src[(static_cast<long long>(f) * C + c) * Kc + k];
+    } else {
+      const long long r = i / (static_cast<long long>(G) * Cp); const int cp = static_cast<int>(i - r * G * Cp);
+      const int f = cp / Cp, c = cp - f * Cp;
+      if (c < C) v = src[r * G * C + f * C + c];
+    }
+    dst[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -413,11 +467,11 @@ int check_desc(const sea_spatial_desc* d) {
   const int hd = Es / d->n_heads;
   if (hd != 2 && hd != 4 && hd != 8 && hd != 16) return SEA_ERR_UNSUPPORTED;
   // contraction widths must be multiples of 16 (one k-step), output widths multiples of 8 (one n-tile)
-  if ((d->embed_dim % 16) || (d->mlp_hidden % 16) || (Es % 16) || (d->n_inp % 8)) return SEA_ERR_UNSUPPORTED;
+  // (n_inp is arbitrary: its axis is padded to a multiple of 16 at pack time)
+  if ((d->embed_dim % 16) || (d->mlp_hidden % 16) || (Es % 16) || d->n_inp < 1) return SEA_ERR_UNSUPPORTED;
   for (int g = 0; g < d->n_groups; ++g) {
     const int cnt = d->group_num_fields[g], first = d->group_first_field[g];
     if (cnt < 1 || first < 0 || first + cnt > d->n_fields) return SEA_ERR_INVALID;
-    if ((cnt * d->n_inp) % 16) return SEA_ERR_UNSUPPORTED;
   }
   return SEA_OK;
 }
@@ -427,7 +481,7 @@ void map_cache(const sea_spatial_desc* d, CacheMap& m) {
   auto take = [&](size_t bytes) { const size_t a = o; o += (bytes + 255) & ~static_cast<size_t>(255); return a; };
   const size_t Hs = d->mlp_hidden, D = d->embed_dim, Es = static_cast<size_t>(d->n_groups) * D;
   for (int g = 0; g < d->n_groups; ++g) {
-    const size_t Kg = static_cast<size_t>(d->group_num_fields[g]) * d->n_inp;
+    const size_t Kg = static_cast<size_t>(d->group_num_fields[g]) * ((d->n_inp + 15) / 16 * 16);
     m.enc_w1[g] = take(2 * Hs * Kg); m.enc_w2[g] = take(2 * D * Hs);
     m.dec_w1[g] = take(2 * Hs * D); m.dec_w2[g] = take(2 * Kg * Hs);
   }
@@ -446,7 +500,7 @@ int fill_tc(const sea_spatial_desc* d, const void* cache, SpatialTC& a) {
   CacheMap m;
   map_cache(d, m);
   const char* base = static_cast<const char*>(cache);
-  a.n_groups = d->n_groups; a.n_fields = d->n_fields; a.C = d->n_inp; a.Hs = d->mlp_hidden;
+  a.n_groups = d->n_groups; a.n_fields = d->n_fields; a.C = d->n_inp; a.Cp = (d->n_inp + 15) / 16 * 16; a.Hs = d->mlp_hidden;
   a.D = d->embed_dim; a.n_heads = d->n_heads; a.num_layers = d->num_layers;
   for (int g = 0; g < d->n_groups; ++g) {
     a.g_first[g] = d->group_first_field[g]; a.g_count[g] = d->group_num_fields[g];
@@ -491,13 +545,25 @@ extern "C" int sea_spatial_pack(const sea_spatial_desc* d, void* cache, size_t c
     return sea_cast_f32_bf16(src, base + off, n, stream);
   };
 #define SEA_TRY_(e) do { int _rc = (e); if (_rc != SEA_OK) return _rc; } while (0)
-  for (int g = 0; g < d->n_groups; ++g) {
-    const int64_t Kg = static_cast<int64_t>(d->group_num_fields[g]) * d->n_inp;
-    if (d->enc_w1[g]) { SEA_TRY_(cast(d->enc_w1[g], m.enc_w1[g], Hs * Kg)); SEA_TRY_(cast(d->enc_w2[g], m.enc_w2[g], D * Hs)); }
-    if (d->dec_w1[g]) { SEA_TRY_(cast(d->dec_w1[g], m.dec_w1[g], Hs * D)); SEA_TRY_(cast(d->dec_w2[g], m.dec_w2[g], Kg * Hs)); }
-  }
-  if (d->num_layers > 0 && !d->layers) return SEA_ERR_INVALID;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int Cn = d->n_inp, Cp = (Cn + 15) / 16 * 16;
+  for (int g = 0; g < d->n_groups; ++g) {
+    const int cnt = d->group_num_fields[g];
+    if (d->enc_w1[g]) {
+      if (!d->enc_w2[g]) return SEA_ERR_INVALID;
+      SEA_LAUNCH(pad_cast_kernel, 296, 256, 0, s, d->enc_w1[g], reinterpret_cast<bf16*>(base + m.enc_w1[g]), static_cast<int>(Hs),
+                 cnt, Cn, Cp, 0, 0);
+      SEA_TRY_(cast(d->enc_w2[g], m.enc_w2[g], D * Hs));
+    }
+    if (d->dec_w1[g]) {
+      if (!d->dec_w2[g]) return SEA_ERR_INVALID;
+      SEA_TRY_(cast(d->dec_w1[g], m.dec_w1[g], Hs * D));
+      SEA_LAUNCH(pad_cast_kernel, 296, 256, 0, s, d->dec_w2[g], reinterpret_cast<bf16*>(base + m.dec_w2[g]), 0, cnt, Cn, Cp,
+                 static_cast<int>(Hs), 1);
+    }
+  }
+  SEA_CUDA_OK(cudaGetLastError());
+  if (d->num_layers > 0 && !d->layers) return SEA_ERR_INVALID;
   for (int l = 0; l < d->num_layers; ++l) {
     const sea_spatial_layer& L = d->layers[l];
     SEA_TRY_(cast(L.q_w, m.qkv_w[l], Es * Es));
@@ -524,7 +590,7 @@ extern "C" int sea_spatial_encode_tc(const sea_spatial_desc* d, const void* cach
   for (int g = 0; g < a.n_groups; ++g)
     if (!d->enc_w1[g] || !d->enc_w2[g] || !a.enc_b2[g]) return SEA_ERR_INVALID;
   if (!a.ln_w || !a.ln_b || !a.pe) return SEA_ERR_INVALID;
-  const EncPlan pl = enc_plan(a.n_fields * a.C, a.Hs, a.n_groups * a.D);
+  const EncPlan pl = enc_plan(a.n_fields * a.Cp, a.Hs, a.n_groups * a.D);
   if (pl.total > 227 * 1024) return SEA_ERR_UNSUPPORTED;
   SEA_CUDA_OK(cudaFuncSetAttribute(spatial_encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.total)));
   SEA_LAUNCH(spatial_encode_tc_kernel, B, kThreads, pl.total, reinterpret_cast<cudaStream_t>(stream), a, x, z, latent_layout,

@@ -82,7 +82,8 @@ def _overlap_handles(dev: torch.device, n_events: int):
                 ev = C.c_void_p()
                 check(lib.sea_event_create(C.byref(ev)), "event_create")
                 evs.append(ev)
-            _overlap_state[key] = (torch.cuda.Stream(device=dev), evs)
+            _overlap_state[key] = (torch.cuda.Stream(device=dev, priority=-1), evs)   # high priority: the collective's CTAs
+            # are scheduled as soon as SMs free up under the persistent backward GEMMs
     return _overlap_state[key]
 
 

@@ -142,7 +142,8 @@ def test_bf16_gradient_twin_and_fused_step_from_it(cuda, ln):
         oa.step()
         ob.step_from_bf16_twin()
     for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
-        if p.grad is not None:
+        # (k.bias: its true gradient is zero — softmax is shift-invariant — so Adam normalises pure rounding noise)
+        if p.grad is not None and not n.endswith(".k.bias"):
             assert _rel(q.data, p.data) < 2e-3, n
     g_before = {n: v.clone() for n, v in eb._grad_views.items()}
     eb.twin_to_flat_grad()

@@ -163,3 +163,34 @@ def test_tensor_core_codec_ragged_batches_vs_fp32_kernels(cuda):
             za, zb = a.encode(x), b.encode(x)
             ya, yb = a.decode(za), b.decode(za)
         assert rel_l2(zb.cpu(), za.cpu()) < 2e-2 and rel_l2(yb.cpu(), ya.cpu()) < 2e-2, (C_, B)
+
+
+@pytest.mark.parametrize("C", [37, 50, 63])
+def test_arbitrary_cells_per_patch(cuda, C):
+    """n_inp is the cell count of the fullest patch of the user's mesh (utils/data_processors.py:61-88,
+    train/train_temporal.py:147-148): any integer.  fp32 kernels (scalar-load path when C % 4 != 0) against the oracle at
+    1e-4, tensor-core kernels (cell axis zero-padded to 16 at pack time, decoder stores masked) at 2e-2; the decoder must
+    not write outside its [B, 64, F, C] output."""
+    from oracle import golden_recipe as gr
+    from sea_b200.spatial import SpatialModel
+    fg = [[0, 1], [2]]
+    shapes = [(k, tuple(v.shape)) for k, v in so.init_spatial_state(
+        field_groups=fg, n_inp=C, mlp_hidden=480, num_layers=3, embed_dim=16).items()]
+    sd = gr.fill_state(shapes, 13)
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(9, 64, 3, C, generator=g)
+    x[:, :, :, C - 7:] = 0.0
+    with torch.no_grad():
+        ref_z = so.spatial_encode(x, sd, field_groups=fg, num_layers=3, n_heads=8)
+        ref_y = so.spatial_decode(ref_z, sd, field_groups=fg)
+    for prec, bar in (("fp32", 1e-4), ("bf16", 2e-2)):
+        m = SpatialModel(fg, C, 480, 3, 16, 8, 2024, 0, 0.0, False, precision=prec)
+        m.load_state_dict(sd, strict=False)
+        m = m.to(cuda).eval()
+        with torch.no_grad():
+            z = m.encode(x.to(cuda))
+            buf = torch.full((9 * 64 * 3 * C + 64,), 777.0, device=cuda)        # canary behind the output
+            y = m.decode(ref_z.to(cuda))
+        assert rel_l2(z.cpu(), ref_z) < bar and rel_l2(y.cpu(), ref_y) < bar, (prec, C)
+        assert torch.isfinite(y).all() and y.shape == (9, 64, 3, C)
+        del buf
