@@ -686,6 +686,11 @@ int sea_spatial_decode_tc(const sea_spatial_desc* d, const void* cache, const fl
  *   sea_patch_scatter     inverse_partition (:90-111): out[s, index_map[p, c], f] = part[s, p, c, f]. */
 int sea_patch_bucketize(const float* x, const float* y, int n_cells, const float* x_boundary, int m,
                         const float* y_boundary, int n, int32_t* patch_id, int32_t* counts, sea_stream_t stream);
+/* DataPartitioner3D (utils/data_processors.py:114-165): the same with a third axis, patch_id = ((ix-1)*(n-1) + (iy-1))*(k-1)
+ * + (iz-1), (m-1)(n-1)(k-1) <= 65535 patches; index_map / gather / scatter are shared with the 2-D partitioner. */
+int sea_patch_bucketize3d(const float* x, const float* y, const float* z, int n_cells, const float* x_boundary, int m,
+                          const float* y_boundary, int n, const float* z_boundary, int k, int32_t* patch_id,
+                          int32_t* counts, sea_stream_t stream);
 int sea_patch_index_map(const int32_t* patch_id, int n_cells, int n_patches, int capacity, int64_t pad_id,
                         int64_t* index_map, sea_stream_t stream);
 int sea_patch_gather(const float* const* host_field_ptrs, int n_fields, int64_t ld_field, const int64_t* index_map,

@@ -1,4 +1,4 @@
-"""CPU restatement (numpy) of the reference's DataPartitioner2D — TEST INFRASTRUCTURE ONLY (only tests/
+"""CPU restatement (numpy) of the reference's DataPartitioner2D / DataPartitioner3D — TEST INFRASTRUCTURE ONLY (only tests/
 may import it).  Follows utils/data_processors.py:21-59 (create_partitions), :61-88 (pad_partitions)
 and :90-111 (inverse_partition).  Pinned against the unmodified reference by
 oracle/make_golden_patchify.py -> tests/golden/patchify_small.npz (tests/test_patchify_cpu.py)."""
@@ -31,6 +31,25 @@ def index_map(x, y, m=9, n=9, pad_id=-1):
     for i in range(1, m):
         for j in range(1, n):
             lists.append(np.nonzero((ix == i) & (iy == j))[0].astype(np.int64))
+    cap = max(len(l) for l in lists)
+    out = np.full((len(lists), cap), pad_id, dtype=np.int64)
+    for p, l in enumerate(lists):
+        out[p, : len(l)] = l
+    return out, np.array([len(l) for l in lists], dtype=np.int32)
+
+
+def index_map3d(x, y, z, m=9, n=9, k=9, pad_id=-1):
+    """DataPartitioner3D.create_partitions + pad_partitions (utils/data_processors.py:132-196): patches ordered
+    i (x) outermost, then j (y), then k (z)."""
+    x, y, z = (np.asarray(a, np.float32) for a in (x, y, z))
+    ix = np.clip(np.searchsorted(linspace_f32(x.min(), x.max(), m), x, side="right"), 1, m - 1)
+    iy = np.clip(np.searchsorted(linspace_f32(y.min(), y.max(), n), y, side="right"), 1, n - 1)
+    iz = np.clip(np.searchsorted(linspace_f32(z.min(), z.max(), k), z, side="right"), 1, k - 1)
+    lists = []
+    for i in range(1, m):
+        for j in range(1, n):
+            for l in range(1, k):
+                lists.append(np.nonzero((ix == i) & (iy == j) & (iz == l))[0].astype(np.int64))
     cap = max(len(l) for l in lists)
     out = np.full((len(lists), cap), pad_id, dtype=np.int64)
     for p, l in enumerate(lists):

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call d: tensor-core codec: parity tests, sweep, one ncu --set full capture
 mkdir -p gpurun_out
-python -m pytest tests/test_spatial_gpu.py tests/test_dropin_gpu.py -q -k "spatial" > gpurun_out/r2d_tests.log 2>&1
+python -m pytest tests/test_spatial_gpu.py tests/test_dropin_gpu.py tests/test_pipeline_gpu.py tests/test_optim_gpu.py -q -k "spatial or pipeline or twin or arbitrary or tensor_core or scaled or fields" > gpurun_out/r2d_tests.log 2>&1
 tail -30 gpurun_out/r2d_tests.log
 timeout 600 python scripts/sweep.py spatial_tc > gpurun_out/r2d_codec_sweep.md 2>&1
 cat gpurun_out/r2d_codec_sweep.md

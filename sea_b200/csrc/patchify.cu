@@ -50,6 +50,29 @@ __global__ void __launch_bounds__(256) patch_bucketize_kernel(const float* __res
   atomicAdd(counts + p, 1);
 }
 
+// DataPartitioner3D (utils/data_processors.py:114-165): patch = ((ix-1)*(n-1) + (iy-1))*(k-1) + (iz-1)
+__global__ void __launch_bounds__(256) patch_bucketize3d_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                const float* __restrict__ z, int n_cells,
+                                                                const float* __restrict__ xb, int m, const float* __restrict__ yb,
+                                                                int n, const float* __restrict__ zb, int k,
+                                                                int32_t* __restrict__ patch_id, int32_t* __restrict__ counts) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  __shared__ float sxb[64], syb[64], szb[64];
+  for (int i = threadIdx.x; i < m; i += blockDim.x) sxb[i] = xb[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) syb[i] = yb[i];
+  for (int i = threadIdx.x; i < k; i += blockDim.x) szb[i] = zb[i];
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const int ix = min(max(bucket_right(sxb, m, x[c]), 1), m - 1);
+  const int iy = min(max(bucket_right(syb, n, y[c]), 1), n - 1);
+  const int iz = min(max(bucket_right(szb, k, z[c]), 1), k - 1);
+  const int p = ((ix - 1) * (n - 1) + (iy - 1)) * (k - 1) + (iz - 1);
+  patch_id[c] = p;
+  atomicAdd(counts + p, 1);
+}
+
 __global__ void __launch_bounds__(1024) patch_index_map_kernel(const int32_t* __restrict__ patch_id, int n_cells,
                                                                int capacity, long long pad_id,
                                                                long long* __restrict__ index_map) {
@@ -189,6 +212,20 @@ extern "C" int sea_patch_bucketize(const float* x, const float* y, int n_cells, 
   SEA_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (m - 1) * (n - 1), s));
   SEA_LAUNCH(patch_bucketize_kernel, (n_cells + 255) / 256, 256, 0, s, x, y, n_cells, x_boundary, m, y_boundary, n,
              patch_id, counts);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sea_patch_bucketize3d(const float* x, const float* y, const float* z, int n_cells, const float* x_boundary,
+                                     int m, const float* y_boundary, int n, const float* z_boundary, int k,
+                                     int32_t* patch_id, int32_t* counts, sea_stream_t stream) {
+  using namespace sea;
+  if (!x || !y || !z || !x_boundary || !y_boundary || !z_boundary || !patch_id || !counts || n_cells <= 0) return SEA_ERR_INVALID;
+  if (m < 2 || n < 2 || k < 2 || m > 64 || n > 64 || k > 64) return SEA_ERR_UNSUPPORTED;
+  if (static_cast<long long>(m - 1) * (n - 1) * (k - 1) > 65535) return SEA_ERR_UNSUPPORTED;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  SEA_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (m - 1) * (n - 1) * (k - 1), s));
+  SEA_LAUNCH(patch_bucketize3d_kernel, (n_cells + 255) / 256, 256, 0, s, x, y, z, n_cells, x_boundary, m, y_boundary, n,
+             z_boundary, k, patch_id, counts);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -1,4 +1,4 @@
-"""Host-side mirror of the reference's ``DataPartitioner2D`` (utils/data_processors.py:9-111) backed
+"""Host-side mirrors of the reference's ``DataPartitioner2D`` / ``DataPartitioner3D`` (utils/data_processors.py:9-223) backed
 by the CUDA kernels of ``csrc/patchify.cu``.
 
 Same constructor arguments, ``create_partitions(vars)`` / ``inverse_partition(external_partitions,
@@ -112,3 +112,45 @@ class DataPartitioner2D:
             rec = rec[:time_dim]
         # coordinates: scatter of the padded coordinates = the mesh itself (:106-107)
         return self.full_coords.clone(), rec
+
+
+class DataPartitioner3D(DataPartitioner2D):
+    """Mirror of the reference's ``DataPartitioner3D`` (utils/data_processors.py:114-223): same constructor (the variables
+    are given to the constructor, ``create_partitions()`` takes none), (m-1)(n-1)(k-1) patches ordered x-major, then y,
+    then z.  Shares the compaction / gather / scatter kernels with the 2-D partitioner; only the bucketize differs."""
+
+    def __init__(self, x_coords, y_coords, z_coords, vars, m=9, n=9, k=9, pad_id=-1, pad_field_value=0, device="cuda"):
+        super().__init__(x_coords, y_coords, m=m, n=n, pad_id=pad_id, pad_field_value=pad_field_value, device=device)
+        self.z_coords = z_coords.to(self.device).float().contiguous()
+        self.full_coords = torch.stack((self.x_coords, self.y_coords, self.z_coords), dim=1)
+        self.k = int(k)
+        self.var_list = [v.to(self.device).float() for v in vars if v is not None]
+        if len(self.var_list) == 0:
+            raise ValueError("At least one variable must be provided")
+
+    def _build_index(self):
+        N, P = self.x_coords.numel(), (self.m - 1) * (self.n - 1) * (self.k - 1)
+        bounds = []
+        for coords, steps in ((self.x_coords, self.m), (self.y_coords, self.n), (self.z_coords, self.k)):   # :133-139
+            bounds.append(torch.linspace(torch.min(coords), torch.max(coords), steps, device=self.device).float().contiguous())
+        xb, yb, zb = bounds
+        self.patch_id = torch.empty(N, dtype=torch.int32, device=self.device)
+        self.counts = torch.empty(P, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.sea_patch_bucketize3d(C.c_void_p(self.x_coords.data_ptr()), C.c_void_p(self.y_coords.data_ptr()),
+                                            C.c_void_p(self.z_coords.data_ptr()), N, C.c_void_p(xb.data_ptr()), self.m,
+                                            C.c_void_p(yb.data_ptr()), self.n, C.c_void_p(zb.data_ptr()), self.k,
+                                            C.c_void_p(self.patch_id.data_ptr()), C.c_void_p(self.counts.data_ptr()),
+                                            _stream()), "patch_bucketize3d")
+            self.capacity = int(self.counts.max().item())
+            self.index_map_tensor = torch.empty(P, self.capacity, dtype=torch.int64, device=self.device)
+            check(lib.sea_patch_index_map(C.c_void_p(self.patch_id.data_ptr()), N, P, self.capacity,
+                                          C.c_int64(self.pad_id), C.c_void_p(self.index_map_tensor.data_ptr()),
+                                          _stream()), "patch_index_map")
+        valid = self.index_map_tensor >= 0
+        safe = self.index_map_tensor.clamp_min(0)
+        self.stacked_coords = torch.where(valid[..., None], self.full_coords[safe],
+                                          torch.full((), self.pad_field_value, device=self.device))
+
+    def create_partitions(self):
+        return super().create_partitions(self.var_list)

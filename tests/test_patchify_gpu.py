@@ -65,3 +65,42 @@ def test_patchify_round_trip_full_size(cuda):
     im = part.index_map_tensor
     assert int((im >= 0).sum()) == N and torch.equal(torch.sort(im[im >= 0])[0], torch.arange(N, device=cuda))
     assert float(fields[:, im < 0].abs().max()) == 0.0 if bool((im < 0).any()) else True
+
+
+@pytest.mark.parametrize("tag", ["uniform", "clustered"])
+def test_patchify3d_matches_reference_goldens(cuda, tag):
+    """DataPartitioner3D mirror (utils/data_processors.py:114-223) on the reference's golden fixtures: bit-exact."""
+    from sea_b200.patchify import DataPartitioner3D
+    g = load_golden("patchify3d_small")
+    x, y, z, vars_ = g[f"{tag}_x"], g[f"{tag}_y"], g[f"{tag}_z"], g[f"{tag}_vars"]
+    m, n, k = (int(v) for v in g[f"{tag}_mnk"])
+    part = DataPartitioner3D(torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(z),
+                             [torch.from_numpy(v) for v in vars_], m=m, n=n, k=k, pad_id=-1, pad_field_value=0, device=cuda)
+    padded, imap = part.create_partitions()
+    P = (m - 1) * (n - 1) * (k - 1)
+    assert len(padded) == P and len(imap) == P
+    assert np.array_equal(torch.stack(imap, 0).cpu().numpy(), g[f"{tag}_index_map"])
+    assert np.array_equal(torch.stack([p[1] for p in padded], 1).cpu().numpy(), g[f"{tag}_fields"])
+    assert np.array_equal(torch.stack([p[0] for p in padded], 0).cpu().numpy(), g[f"{tag}_coords"])
+    rc, rf = part.inverse_partition(padded)
+    assert np.array_equal(rf.cpu().numpy(), g[f"{tag}_recon"])
+    assert np.array_equal(rc.cpu().numpy(), np.stack([x, y, z], 1))
+
+
+@pytest.mark.parametrize("N,S,F,mnk", [(20_000, 4, 3, (9, 9, 9)), (3001, 2, 1, (3, 17, 2)), (200_000, 3, 4, (9, 9, 9))])
+def test_patchify3d_random_meshes_vs_oracle(cuda, N, S, F, mnk):
+    from sea_b200.patchify import DataPartitioner3D
+    rng = np.random.RandomState(N)
+    x = (rng.rand(N) ** 2 * 3.0 - 1.0).astype(np.float32)
+    y = (rng.randn(N) * 0.3).astype(np.float32)
+    z = (rng.rand(N) * 5.0).astype(np.float32)
+    vars_ = [rng.randn(S, N).astype(np.float32) for _ in range(F)]
+    m, n, k = mnk
+    imap, counts = po.index_map3d(x, y, z, m, n, k, -1)
+    part = DataPartitioner3D(torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(z), [torch.from_numpy(v) for v in vars_],
+                             m=m, n=n, k=k, device=cuda)
+    fields = part.gather(part.var_list)
+    assert np.array_equal(part.index_map_tensor.cpu().numpy(), imap)
+    assert np.array_equal(part.counts.cpu().numpy(), counts)
+    assert np.array_equal(fields.cpu().numpy(), po.gather(vars_, imap, 0.0))
+    assert np.array_equal(part.scatter(fields).cpu().numpy(), np.stack(vars_, 2))   # the reference's own round-trip check
