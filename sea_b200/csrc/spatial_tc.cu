@@ -30,8 +30,9 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 constexpr int P = 64;
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
+constexpr int kThreads = 256;             // 8 warps = 4 row tiles x 2 column groups; two or more CTAs share an SM, so
+constexpr int kWarps = kThreads / 32;     // one snapshot's barrier / latency stalls are filled by another's work
+constexpr int kColGroups = kWarps / 4;
 
 struct LayerTC {
   const bf16 *qkv_w, *proj_w, *mlp0_w, *mlp3_w;
@@ -66,7 +67,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Y[64, N] = X[64, K] . W[N, K]^T, X bf16 in shared memory (pitch ldx), W bf16 in global memory (row pitch ldw).
-// 16 warps = 4 row tiles x 4 column groups; a warp walks its n-tiles (8 columns each) NT at a time.
+// kWarps = 4 row tiles x kColGroups column groups; a warp walks its n-tiles (8 columns each) NT at a time.
 // epi(row, col, v0, v1) receives the two adjacent columns (col even) of one row.  K % 16 == 0, N % 8 == 0.
 template <int NT, class Epi>
 __device__ __forceinline__ void gemm64(const bf16* __restrict__ X, int ldx, int K, const bf16* __restrict__ W,
@@ -76,13 +77,13 @@ __device__ __forceinline__ void gemm64(const bf16* __restrict__ X, int ldx, int 
   const int ntiles = N >> 3;
   const bf16* xa = X + (rt * 16 + r) * ldx;
   const bf16* xb = xa + 8 * ldx;
-  for (int j0 = cg; j0 < ntiles; j0 += 4 * NT) {
+  for (int j0 = cg; j0 < ntiles; j0 += kColGroups * NT) {
     float acc[NT][4];
     const bf16* wp[NT];
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
       acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-      const int j = min(j0 + 4 * i, ntiles - 1);
+      const int j = min(j0 + kColGroups * i, ntiles - 1);
       wp[i] = W + static_cast<long long>(j * 8 + r) * ldw;
     }
     int k0 = 0;
@@ -110,7 +111,7 @@ __device__ __forceinline__ void gemm64(const bf16* __restrict__ X, int ldx, int 
     }
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-      const int j = j0 + 4 * i;
+      const int j = j0 + kColGroups * i;
       if (j < ntiles) {
         epi(rt * 16 + r, j * 8 + 2 * t, acc[i][0], acc[i][1]);
         epi(rt * 16 + r + 8, j * 8 + 2 * t, acc[i][2], acc[i][3]);
@@ -125,22 +126,60 @@ __device__ __forceinline__ void gemm64_any(const bf16* X, int ldx, int K, const 
   else gemm64<1>(X, ldx, K, W, ldw, N, epi);
 }
 
-// Row LayerNorm of the fp32 state (warp per row): Y (bf16, pitch ldy) = (x - mean) * rstd * w (+ b), optional GELU.
-__device__ __forceinline__ void layernorm_rows(const float* __restrict__ X, int ldx, int d, const float* __restrict__ w,
-                                               const float* __restrict__ b, bf16* __restrict__ Y, int ldy, bool gelu) {
+// Row LayerNorm of the fp32 state (warp per row, the row in registers: NPL = d / 32 values per lane, two-pass
+// statistics): Y (bf16, pitch ldy) = (x - mean) * rstd * w (+ b), optional GELU (tanh-fitted form: the result is rounded to
+// bf16 next).  `Y` may alias `X` when the bf16 row fits in front of its own fp32 row (a warp reads its whole row first).
+template <int NPL>
+__device__ __forceinline__ void layernorm_rows_t(const float* X, int ldx, const float* __restrict__ w,
+                                                 const float* __restrict__ b, bf16* Y, int ldy, bool gelu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr float inv_d = 1.0f / (32 * NPL);
+  float wv[NPL], bv[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) { wv[i] = __ldg(w + lane + 32 * i); bv[i] = b ? __ldg(b + lane + 32 * i) : 0.f; }
+  for (int row = warp; row < P; row += kWarps) {
+    const float* xr = X + row * ldx;
+    float v[NPL], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) { v[i] = xr[lane + 32 * i]; s += v[i]; }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
+    const float rstd = rsqrtf(fmaf(warp_sum(q), inv_d, 1e-5f));
+    __syncwarp();   // in-place use: every lane has read its fp32 values before any bf16 value lands on them
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const float y = fmaf(v[i] * rstd, wv[i], bv[i]);
+      Y[row * ldy + lane + 32 * i] = __float2bfloat16_rn(gelu ? ptx::gelu_bf16(y) : y);
+    }
+  }
+}
+__device__ __forceinline__ void layernorm_rows(const float* X, int ldx, int d, const float* __restrict__ w,
+                                               const float* __restrict__ b, bf16* Y, int ldy, bool gelu) {
+  switch (d) {
+    case 32: layernorm_rows_t<1>(X, ldx, w, b, Y, ldy, gelu); return;
+    case 64: layernorm_rows_t<2>(X, ldx, w, b, Y, ldy, gelu); return;
+    case 96: layernorm_rows_t<3>(X, ldx, w, b, Y, ldy, gelu); return;
+    case 128: layernorm_rows_t<4>(X, ldx, w, b, Y, ldy, gelu); return;
+    case 192: layernorm_rows_t<6>(X, ldx, w, b, Y, ldy, gelu); return;
+    case 256: layernorm_rows_t<8>(X, ldx, w, b, Y, ldy, gelu); return;
+    default: break;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inv_d = 1.0f / d;
   for (int row = warp; row < P; row += kWarps) {
     const float* xr = X + row * ldx;
     float s = 0.f;
     for (int c = lane; c < d; c += 32) s += xr[c];
-    const float mean = warp_sum(s) / d;
+    const float mean = warp_sum(s) * inv_d;
     float q = 0.f;
     for (int c = lane; c < d; c += 32) { const float e = xr[c] - mean; q = fmaf(e, e, q); }
-    const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+    const float rstd = rsqrtf(fmaf(warp_sum(q), inv_d, 1e-5f));
     for (int c = lane; c < d; c += 32) {
       float y = (xr[c] - mean) * rstd * __ldg(w + c);
       if (b) y += __ldg(b + c);
-      Y[row * ldy + c] = __float2bfloat16_rn(gelu ? ptx::gelu_fast(y) : y);
+      Y[row * ldy + c] = __float2bfloat16_rn(gelu ? ptx::gelu_bf16(y) : y);
     }
   }
 }
@@ -183,8 +222,8 @@ __device__ __forceinline__ void attention_tc(const bf16* __restrict__ Q, const b
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s[j][0] = exp2f((s[j][0] - m0) * sl2); s[j][1] = exp2f((s[j][1] - m0) * sl2);
-      s[j][2] = exp2f((s[j][2] - m1) * sl2); s[j][3] = exp2f((s[j][3] - m1) * sl2);
+      s[j][0] = ptx::ex2((s[j][0] - m0) * sl2); s[j][1] = ptx::ex2((s[j][1] - m0) * sl2);
+      s[j][2] = ptx::ex2((s[j][2] - m1) * sl2); s[j][3] = ptx::ex2((s[j][3] - m1) * sl2);
       l0 += s[j][0] + s[j][1];
       l1 += s[j][2] + s[j][3];
     }
@@ -207,7 +246,9 @@ __device__ __forceinline__ void attention_tc(const bf16* __restrict__ Q, const b
         mma16816(o[nt], p0, p1, p2, p3, b0, b1);
       }
     }
-    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    float i0, i1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(l0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(l1));
 #pragma unroll
     for (int nt = 0; nt < NTV; ++nt) {
       const int d = nt * 8 + 2 * t;
@@ -237,10 +278,14 @@ __device__ __forceinline__ long long latent_index(int b, int p, int g, int d, in
 
 // Shared-memory plan of the encoder (bytes, 16-byte aligned regions).  Region A is used twice: first by the patch MLPs
 // (snapshot in bf16 + the GELU'd hidden layer), then by the encoder blocks' MLP (fp32 pre-LN hidden + its bf16 GELU).
-struct EncPlan { int ld_in, ld_hid, ld_e, ld_v, ld_h4; size_t off_z, off_n, off_q, off_k, off_v, off_a, a_hid, a_hh, a_hb, total; };
+// The patch-MLP hidden layer is processed in two column chunks (the second Linear accumulates over them) and the MLP's
+// bf16 GELU output overwrites the front of its own fp32 pre-LN row, which keeps a cylinder_flow snapshot under half an SM.
+struct EncPlan { int ld_in, ld_hid, ld_e, ld_v, ld_hh, hchunk; size_t off_z, off_n, off_q, off_k, off_v, off_a, a_hid, a_hh, total; };
 __host__ __device__ inline EncPlan enc_plan(int FC, int Hs, int Es) {
   EncPlan p{};
-  p.ld_in = pitch_of(FC); p.ld_hid = pitch_of(Hs); p.ld_e = pitch_of(Es); p.ld_v = pitch_of(P); p.ld_h4 = pitch_of(4 * Es);
+  p.hchunk = ((Hs + 1) / 2 + 15) / 16 * 16;
+  p.ld_in = pitch_of(FC); p.ld_hid = pitch_of(p.hchunk); p.ld_e = pitch_of(Es); p.ld_v = pitch_of(P);
+  p.ld_hh = 4 * Es + 16;   // fp32 pitch; read as bf16 the same rows have pitch 2 * ld_hh == 32 (mod 64)
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t a = o; o += (bytes + 15) & ~static_cast<size_t>(15); return a; };
   p.off_z = take(sizeof(float) * P * Es);
@@ -250,17 +295,15 @@ __host__ __device__ inline EncPlan enc_plan(int FC, int Hs, int Es) {
   p.off_v = take(sizeof(bf16) * (Es + 8) * p.ld_v);
   p.off_a = o;
   const size_t in_bytes = (sizeof(bf16) * P * p.ld_in + 15) & ~static_cast<size_t>(15);
-  const size_t hh_bytes = (sizeof(float) * P * 4 * Es + 15) & ~static_cast<size_t>(15);
   p.a_hid = p.off_a + in_bytes;
   p.a_hh = p.off_a;
-  p.a_hb = p.off_a + hh_bytes;
-  const size_t use1 = in_bytes + sizeof(bf16) * P * p.ld_hid, use2 = hh_bytes + sizeof(bf16) * P * p.ld_h4;
+  const size_t use1 = in_bytes + sizeof(bf16) * P * p.ld_hid, use2 = sizeof(float) * P * p.ld_hh;
   p.total = p.off_a + (use1 > use2 ? use1 : use2);
   return p;
 }
 
 // ------------------------------------------------------------------------------------ encoder
-__global__ void __launch_bounds__(kThreads, 1) spatial_encode_tc_kernel(const SpatialTC a, float* __restrict__ x,
+__global__ void __launch_bounds__(kThreads, 2) spatial_encode_tc_kernel(const SpatialTC a, float* __restrict__ x,
                                                                         float* __restrict__ z, int layout, float pad_idx,
                                                                         int fix_pad) {
   ptx::pdl_trigger();
@@ -275,8 +318,8 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_encode_tc_kernel(const Sp
   bf16* Vt = reinterpret_cast<bf16*>(smraw + pl.off_v);      // [Es + 8][ld_v] values, transposed
   bf16* Xin = reinterpret_cast<bf16*>(smraw + pl.off_a);     // [64][ld_in]
   bf16* Hid = reinterpret_cast<bf16*>(smraw + pl.a_hid);     // [64][ld_hid]
-  float* Hh = reinterpret_cast<float*>(smraw + pl.a_hh);     // [64][4 Es] fp32 (pre-LN MLP hidden)
-  bf16* Hb = reinterpret_cast<bf16*>(smraw + pl.a_hb);       // [64][ld_h4]
+  float* Hh = reinterpret_cast<float*>(smraw + pl.a_hh);     // [64][ld_hh] fp32 (pre-LN MLP hidden)
+  bf16* Hb = reinterpret_cast<bf16*>(Hh);                    // its GELU(LN(.)) in bf16, in place: pitch 2 * ld_hh
   const int b = blockIdx.x;
   float* xb = x + static_cast<long long>(b) * P * FC;
   // (1) snapshot -> bf16; generate_padding_mask (models/encoder_decoder.py:173-176) in place
@@ -317,18 +360,27 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_encode_tc_kernel(const Sp
   // (2) per-group patch MLP: Linear(C*g, Hs, no bias) -> GELU -> Linear(Hs, D) + b, + positional encoding (:108-114)
   for (int g = 0; g < a.n_groups; ++g) {
     const int Kin = a.g_count[g] * a.Cp;
-    gemm64_any(Xin + a.g_first[g] * a.Cp, pl.ld_in, Kin, a.enc_w1[g], Kin, a.Hs,
-               [&](int row, int col, float v0, float v1) {
-                 *reinterpret_cast<uint32_t*>(Hid + row * pl.ld_hid + col) = ptx::pack_bf16(ptx::gelu_fast(v0), ptx::gelu_fast(v1));
-               });
-    __syncthreads();
     const float* b2 = a.enc_b2[g];
-    gemm64_any(Hid, pl.ld_hid, a.Hs, a.enc_w2[g], a.Hs, a.D, [&](int row, int col, float v0, float v1) {
-      const int c = g * a.D + col;
-      const float2 pe = __ldg(reinterpret_cast<const float2*>(a.pe + row * Es + c));
-      *reinterpret_cast<float2*>(Z + row * Es + c) = make_float2(v0 + __ldg(b2 + col) + pe.x, v1 + __ldg(b2 + col + 1) + pe.y);
-    });
-    __syncthreads();
+    for (int c0 = 0; c0 < a.Hs; c0 += pl.hchunk) {
+      const int ch = min(pl.hchunk, a.Hs - c0);
+      gemm64_any(Xin + a.g_first[g] * a.Cp, pl.ld_in, Kin, a.enc_w1[g] + static_cast<long long>(c0) * Kin, Kin, ch,
+                 [&](int row, int col, float v0, float v1) {
+                   *reinterpret_cast<uint32_t*>(Hid + row * pl.ld_hid + col) = ptx::pack_bf16(ptx::gelu_bf16(v0), ptx::gelu_bf16(v1));
+                 });
+      __syncthreads();
+      gemm64_any(Hid, pl.ld_hid, ch, a.enc_w2[g] + c0, a.Hs, a.D, [&](int row, int col, float v0, float v1) {
+        const int c = g * a.D + col;
+        float2* zp = reinterpret_cast<float2*>(Z + row * Es + c);
+        if (c0 == 0) {
+          const float2 pe = __ldg(reinterpret_cast<const float2*>(a.pe + row * Es + c));
+          *zp = make_float2(v0 + __ldg(b2 + col) + pe.x, v1 + __ldg(b2 + col + 1) + pe.y);
+        } else {
+          const float2 zv = *zp;
+          *zp = make_float2(zv.x + v0, zv.y + v1);
+        }
+      });
+      __syncthreads();
+    }
   }
   // (3) encoder blocks (base_blocks.py:123-138)
   for (int l = 0; l < a.num_layers; ++l) {
@@ -356,12 +408,12 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_encode_tc_kernel(const Sp
     layernorm_rows(Z, Es, Es, L.ln2_w, nullptr, Nn, pl.ld_e, false);
     __syncthreads();
     gemm64_any(Nn, pl.ld_e, Es, L.mlp0_w, Es, 4 * Es, [&](int row, int col, float v0, float v1) {
-      *reinterpret_cast<float2*>(Hh + row * 4 * Es + col) = make_float2(v0 + __ldg(L.mlp0_b + col), v1 + __ldg(L.mlp0_b + col + 1));
+      *reinterpret_cast<float2*>(Hh + row * pl.ld_hh + col) = make_float2(v0 + __ldg(L.mlp0_b + col), v1 + __ldg(L.mlp0_b + col + 1));
     });
     __syncthreads();
-    layernorm_rows(Hh, 4 * Es, 4 * Es, L.mlp_ln_w, L.mlp_ln_b, Hb, pl.ld_h4, true);
+    layernorm_rows(Hh, pl.ld_hh, 4 * Es, L.mlp_ln_w, L.mlp_ln_b, Hb, 2 * pl.ld_hh, true);
     __syncthreads();
-    gemm64_any(Hb, pl.ld_h4, 4 * Es, L.mlp3_w, 4 * Es, Es, [&](int row, int col, float v0, float v1) {
+    gemm64_any(Hb, 2 * pl.ld_hh, 4 * Es, L.mlp3_w, 4 * Es, Es, [&](int row, int col, float v0, float v1) {
       float2* zp = reinterpret_cast<float2*>(Z + row * Es + col);
       const float2 zv = *zp;
       *zp = make_float2(zv.x + v0 + __ldg(L.mlp3_b + col), zv.y + v1 + __ldg(L.mlp3_b + col + 1));
@@ -388,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_encode_tc_kernel(const Sp
 }
 
 // ------------------------------------------------------------------------------------ decoder
-__global__ void __launch_bounds__(kThreads, 1) spatial_decode_tc_kernel(const SpatialTC a, const float* __restrict__ z,
+__global__ void __launch_bounds__(kThreads, 2) spatial_decode_tc_kernel(const SpatialTC a, const float* __restrict__ z,
                                                                         float* __restrict__ out, int layout) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
@@ -408,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_decode_tc_kernel(const Sp
   for (int g = 0; g < a.n_groups; ++g) {
     const int Nout = a.g_count[g] * a.Cp;   // padded: columns with cell index >= C are masked below
     gemm64_any(Zb + g * a.D, ld_e, a.D, a.dec_w1[g], a.D, a.Hs, [&](int row, int col, float v0, float v1) {
-      *reinterpret_cast<uint32_t*>(Hid + row * ld_hid + col) = ptx::pack_bf16(ptx::gelu_fast(v0), ptx::gelu_fast(v1));
+      *reinterpret_cast<uint32_t*>(Hid + row * ld_hid + col) = ptx::pack_bf16(ptx::gelu_bf16(v0), ptx::gelu_bf16(v1));
     });
     __syncthreads();
     const float* b2 = a.dec_b2[g];
@@ -468,7 +520,8 @@ int check_desc(const sea_spatial_desc* d) {
   if (hd != 2 && hd != 4 && hd != 8 && hd != 16) return SEA_ERR_UNSUPPORTED;
   // contraction widths must be multiples of 16 (one k-step), output widths multiples of 8 (one n-tile)
   // (n_inp is arbitrary: its axis is padded to a multiple of 16 at pack time)
-  if ((d->embed_dim % 16) || (d->mlp_hidden % 16) || (Es % 16) || d->n_inp < 1) return SEA_ERR_UNSUPPORTED;
+  // (the MLP's in-place LayerNorm needs its 4*Es-wide row in registers: Es in {16, 32, 48, 64})
+  if ((d->embed_dim % 16) || (d->mlp_hidden % 16) || (Es % 16) || Es > 64 || d->n_inp < 1) return SEA_ERR_UNSUPPORTED;
   for (int g = 0; g < d->n_groups; ++g) {
     const int cnt = d->group_num_fields[g], first = d->group_first_field[g];
     if (cnt < 1 || first < 0 || first + cnt > d->n_fields) return SEA_ERR_INVALID;
@@ -593,6 +646,7 @@ extern "C" int sea_spatial_encode_tc(const sea_spatial_desc* d, const void* cach
   const EncPlan pl = enc_plan(a.n_fields * a.Cp, a.Hs, a.n_groups * a.D);
   if (pl.total > 227 * 1024) return SEA_ERR_UNSUPPORTED;
   SEA_CUDA_OK(cudaFuncSetAttribute(spatial_encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.total)));
+  SEA_CUDA_OK(cudaFuncSetAttribute(spatial_encode_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   SEA_LAUNCH(spatial_encode_tc_kernel, B, kThreads, pl.total, reinterpret_cast<cudaStream_t>(stream), a, x, z, latent_layout,
              pad_idx, fix_pad);
   return static_cast<int>(cudaGetLastError());
@@ -610,6 +664,7 @@ extern "C" int sea_spatial_decode_tc(const sea_spatial_desc* d, const void* cach
   const size_t smem = sizeof(bf16) * (((P * pitch_of(Es) + 7) & ~7) + static_cast<size_t>(P) * pitch_of(a.Hs)) + 16;
   if (smem > 227 * 1024) return SEA_ERR_UNSUPPORTED;
   SEA_CUDA_OK(cudaFuncSetAttribute(spatial_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  SEA_CUDA_OK(cudaFuncSetAttribute(spatial_decode_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   SEA_LAUNCH(spatial_decode_tc_kernel, B, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), a, z, out, latent_layout);
   return static_cast<int>(cudaGetLastError());
 }
