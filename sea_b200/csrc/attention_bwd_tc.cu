@@ -11,12 +11,16 @@
 //                   (K_j, V_j) stay, (Q_i, dO_i) stream.  Everything is transposed so keys sit on
 //                   the TMEM lanes:  S^T = K_j Q_i^T, dP^T = V_j dO_i^T,
 //                     dV_j += P^T dO_i ,  dK_j += dS^T Q_i   (TS MMAs, operands MN-major)
-// Roles inside a CTA (192 threads): warp 0 TMA, warp 1 tcgen05.mma issue + TMEM, warps 2..5 one
-// TMEM lane (= one query / key row) per thread.  P / dS overwrite the S / dP columns in place
-// (tcgen05.mma executes in issue order, so the next tile's S cannot overtake their consumer).
+// Roles inside a CTA (320 threads): warp 0 TMA, warp 1 tcgen05.mma issue + TMEM, warps 2..9 = two compute
+// warpgroups; a thread owns one TMEM lane (= one query / key row) and HALF of the streamed columns of a tile.
+// Streamed tiles are 64 wide and S|dP are DOUBLE-BUFFERED in TMEM: the S / dP MMAs of tile it+1 are issued before
+// the accumulate MMAs of tile it, so the tensor pipe recomputes the next scores while the compute warps turn the
+// current ones into P / dS (exp2, mask, dropout, (dP - delta) * scale) — the pipe no longer idles during the
+// softmax-backward arithmetic, nor the compute warps during the MMAs.  P / dS overwrite the S / dP columns in
+// place (tcgen05.mma executes in issue order, so a later tile's S cannot overtake their consumer).
 // The RoPE of the forward (fused in the projection GEMM epilogue) is undone on dQ / dK in the
 // epilogue: rotating the gradient by -theta is the transpose of the forward rotation.
-// TMEM columns: S|P [0,128)  dP|dS [128,256)  acc0 [256,..)  acc1 [384,512).
+// TMEM columns: buffer b in {0,1}: S|P [128b, 128b+64)  dP|dS [128b+64, 128b+128);  acc0 [256,..)  acc1 [384,512).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -30,8 +34,9 @@ namespace sea {
 namespace {
 
 constexpr int BR = 128;  // stationary rows per CTA (TMEM lanes)
-constexpr int kThreads = 192;
-constexpr uint32_t kColS = 0, kColDP = 128, kColAcc0 = 256, kColAcc1 = 384;
+constexpr int kComputeWarps = 8;
+constexpr int kThreads = 64 + 32 * kComputeWarps;
+constexpr uint32_t kColBuf = 128, kColAcc0 = 256, kColAcc1 = 384;   // S at buffer + 0, dP at buffer + BS
 constexpr float kLog2e = 1.44269504088896340736f;
 
 struct alignas(64) AttnBwdTcParams {
@@ -53,8 +58,11 @@ struct BCfg {
   static constexpr int HALVES = HD / DH;
   static constexpr int STAT_BYTES = BR * HD * 2;
   static constexpr int STR_BYTES = BS * HD * 2;
-  static constexpr int STAGES = (2 * STAT_BYTES + 4 * STR_BYTES + 4096 <= 227 * 1024) ? 2 : 1;
-  static constexpr int SMEM = 2 * STAT_BYTES + STAGES * 2 * STR_BYTES + 1024 + 256 + 4 * BS * 4;
+  static constexpr int FIT = (227 * 1024 - 4096 - 2 * STAT_BYTES) / (2 * STR_BYTES);
+  static constexpr int STAGES = FIT >= 4 ? 4 : (FIT >= 3 ? 3 : (FIT >= 2 ? 2 : 1));
+  static constexpr bool PIPE = STAGES >= 2;   // S/dP of tile it+1 ahead of the accumulate MMAs of tile it
+  static constexpr int SMEM = 2 * STAT_BYTES + STAGES * 2 * STR_BYTES + 1024 + 512 + 4 * BS * 4;
+  static_assert(BS == 64, "TMEM plan: two S|dP buffers of 2 x 64 columns");
 };
 
 template <int HD, int BS, int MODE, bool DROP>
@@ -70,13 +78,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
   uint8_t* sB2 = sB1 + STAGES * C::STR_BYTES;          // [STAGES][STR_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + STAGES * C::STR_BYTES);
   uint64_t* a_full = bars;         // 1
-  uint64_t* b_full = bars + 1;     // [2]
-  uint64_t* b_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;     // MMA -> compute
-  uint64_t* p_full = bars + 6;     // compute (128 arrivals) -> MMA
-  uint64_t* acc_done = bars + 7;   // MMA -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* lse_s = reinterpret_cast<float*>(bars + 32);  // [2][BS]  (MODE 1: per-column lse*log2e)
+  uint64_t* b_full = bars + 1;     // [4]
+  uint64_t* b_empty = bars + 5;    // [4]
+  uint64_t* s_full = bars + 9;     // [2] MMA -> compute, one per TMEM buffer
+  uint64_t* p_full = bars + 11;    // [2] compute (256 arrivals) -> MMA
+  uint64_t* acc_done = bars + 13;  // MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* lse_s = reinterpret_cast<float*>(bars + 64);  // [2][BS]  (MODE 1: per-column lse*log2e)
   float* dl_s = lse_s + 2 * BS;                        // [2][BS]  (MODE 1: per-column delta)
 
   // warp-uniform role index + elect.sync regions (see gemm.cu): no waterfall loops around UTMALDG / UTCHMMA
@@ -110,12 +118,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     ptx::prefetch_tmap(&p.tb1);
     ptx::prefetch_tmap(&p.tb2);
     ptx::mbar_init(a_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&b_full[s], 1);
       ptx::mbar_init(&b_empty[s], 1);
     }
-    ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(p_full, 128);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&p_full[s], 32 * kComputeWarps);
+    }
     ptx::mbar_init(acc_done, 1);
     ptx::fence_barrier_init();
   }
@@ -158,31 +168,39 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BR, BS, 0, 0);
     constexpr uint32_t idesc_acc = ptx::umma_idesc_bf16(BR, C::DH, 0, 1);  // B operand MN-major
     ptx::mbar_wait(a_full, 0);
-    for (int it = 0; it < n_it; ++it) {
+    const uint32_t a1 = ptx::smem_u32(sA1), a2 = ptx::smem_u32(sA2);
+    // S = A1 . B1^T and dP = A2 . B2^T of streamed tile `it` into TMEM buffer it & 1
+    auto issue_scores = [&](int it) {
       const int s = it % STAGES;
       ptx::mbar_wait(&b_full[s], (it / STAGES) & 1);
       ptx::tc_fence_after();
-      const uint32_t a1 = ptx::smem_u32(sA1), a2 = ptx::smem_u32(sA2);
       const uint32_t b1 = ptx::smem_u32(sB1 + s * C::STR_BYTES), b2 = ptx::smem_u32(sB2 + s * C::STR_BYTES);
+      const uint32_t buf = tmem + (it & 1) * kColBuf;
       if (ptx::elect_one()) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           const uint32_t aoff = (k >> 2) * (BR * 128) + (k & 3) * 32;
           const uint32_t boff = (k >> 2) * (BS * 128) + (k & 3) * 32;
-          ptx::umma_f16_ss(tmem + kColS, ptx::umma_smem_desc(a1 + aoff, 16, 1024),
+          ptx::umma_f16_ss(buf, ptx::umma_smem_desc(a1 + aoff, 16, 1024),
                            ptx::umma_smem_desc(b1 + boff, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           const uint32_t aoff = (k >> 2) * (BR * 128) + (k & 3) * 32;
           const uint32_t boff = (k >> 2) * (BS * 128) + (k & 3) * 32;
-          ptx::umma_f16_ss(tmem + kColDP, ptx::umma_smem_desc(a2 + aoff, 16, 1024),
+          ptx::umma_f16_ss(buf + BS, ptx::umma_smem_desc(a2 + aoff, 16, 1024),
                            ptx::umma_smem_desc(b2 + boff, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         }
-        ptx::umma_commit(s_full);
+        ptx::umma_commit(&s_full[it & 1]);
       }
       __syncwarp();
-      ptx::mbar_wait(p_full, it & 1);
+    };
+    // dQ += dS K   /   dV += P^T dO, dK += dS^T Q   from the P | dS the compute warps left in buffer it & 1
+    auto issue_accumulate = [&](int it) {
+      const int s = it % STAGES;
+      const uint32_t b1 = ptx::smem_u32(sB1 + s * C::STR_BYTES), b2 = ptx::smem_u32(sB2 + s * C::STR_BYTES);
+      const uint32_t buf = tmem + (it & 1) * kColBuf;
+      ptx::mbar_wait(&p_full[it & 1], (it >> 1) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t hoff = half * (C::DH / 64) * (BS * 128);
@@ -190,13 +208,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
         for (int k = 0; k < BS / 16; ++k) {
           // 16 streamed rows per step = two 8-row groups (SBO 1024 B); 64-wide chunks LBO apart
           const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+          const uint32_t pk = (k >> 1) * 32 + (k & 1) * 8;   // 16 streamed columns = 8 packed TMEM columns, per 32-column half
           if (MODE == 0) {
-            ptx::umma_f16_ts(tmem + kColAcc0, tmem + kColDP + k * 8,
+            ptx::umma_f16_ts(tmem + kColAcc0, buf + BS + pk,
                              ptx::umma_smem_desc(b1 + k * 2048, BS * 128, 1024), idesc_acc, acc);
           } else {
-            ptx::umma_f16_ts(tmem + kColAcc0, tmem + kColS + k * 8,
+            ptx::umma_f16_ts(tmem + kColAcc0, buf + pk,
                              ptx::umma_smem_desc(b2 + hoff + k * 2048, BS * 128, 1024), idesc_acc, acc);
-            ptx::umma_f16_ts(tmem + kColAcc1, tmem + kColDP + k * 8,
+            ptx::umma_f16_ts(tmem + kColAcc1, buf + BS + pk,
                              ptx::umma_smem_desc(b1 + hoff + k * 2048, BS * 128, 1024), idesc_acc, acc);
           }
         }
@@ -204,12 +223,25 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
         if (it == n_it - 1) ptx::umma_commit(acc_done);
       }
       __syncwarp();
+    };
+    if (C::PIPE) {
+      issue_scores(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_scores(it + 1);
+        issue_accumulate(it);
+      }
+    } else {
+      for (int it = 0; it < n_it; ++it) {
+        issue_scores(it);
+        issue_accumulate(it);
+      }
     }
   } else {
     // ---------------------------------------------------------------- compute warps
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int tid = threadIdx.x - 64;  // 0..127
+    const int chalf = (warp - 2) >> 2;   // which 32 of a tile's 64 streamed columns this thread handles
+    const int tid = threadIdx.x - 64;    // 0..255
     const int rpos = r0 + row;         // query (MODE 0) or key (MODE 1) position of this thread
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const long long stat_base = (static_cast<long long>(b) * p.n_heads + h) * p.T;
@@ -226,33 +258,32 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
           lse_s[(it & 1) * BS + tid] = q < p.T ? p.lse[stat_base + q] * kLog2e : 0.f;
           dl_s[(it & 1) * BS + tid] = q < p.T ? p.delta[stat_base + q] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       bool need_mask;
       if (MODE == 0) need_mask = (c0 + BS - 1 > r0 + p.src_len) || (c0 + BS > p.T) || (r0 + BR > p.T);
       else need_mask = (r0 + BR - 1 > c0 + p.src_len) || (c0 + BS > p.T) || (r0 + BR > p.T);
       const float* lrow = lse_s + (it & 1) * BS;
       const float* drow = dl_s + (it & 1) * BS;
-      ptx::mbar_wait(s_full, it & 1);
+      ptx::mbar_wait(&s_full[it & 1], (it >> 1) & 1);
       ptx::tc_fence_after();
-      // 64 columns of S and dP per TMEM round trip (four loads in flight), results written back in place
-#pragma unroll
-      for (int c2 = 0; c2 < BS / 64; ++c2) {
-        uint32_t rs[64], rd[64];
-        ptx::tmem_ld_32x32p(tmem + lane_base + kColS + c2 * 64, rs);
-        ptx::tmem_ld_32x32p(tmem + lane_base + kColS + c2 * 64 + 32, rs + 32);
-        ptx::tmem_ld_32x32p(tmem + lane_base + kColDP + c2 * 64, rd);
-        ptx::tmem_ld_32x32p(tmem + lane_base + kColDP + c2 * 64 + 32, rd + 32);
+      // this thread's 32 columns of S and dP in one TMEM round trip, results written back in place
+      {
+        const uint32_t buf = tmem + lane_base + (it & 1) * kColBuf;
+        const int cb = chalf * 32;
+        uint32_t rs[32], rd[32];
+        ptx::tmem_ld_32x32p(buf + cb, rs);
+        ptx::tmem_ld_32x32p(buf + BS + cb, rd);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 64; e += 2) {
+        for (int e = 0; e < 32; e += 2) {
           float pv[2], dv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int cpos = c0 + c2 * 64 + e + u;
+            const int cpos = c0 + cb + e + u;
             float l2, dl;
             if (MODE == 0) { l2 = my_lse2; dl = my_dl; }
-            else { l2 = lrow[c2 * 64 + e + u]; dl = drow[c2 * 64 + e + u]; }
+            else { l2 = lrow[cb + e + u]; dl = drow[cb + e + u]; }
             float pe = ptx::ex2(fmaf(__uint_as_float(rs[e + u]), p.scale_log2, -l2));
             if (need_mask) {
               const int qq = MODE == 0 ? rpos : cpos;
@@ -279,16 +310,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
           rs[e >> 1] = ptx::pack_bf16(pv[0], pv[1]);
           rd[e >> 1] = ptx::pack_bf16(dv[0], dv[1]);
         }
-        if (MODE == 1) {
-          ptx::tmem_st_32x16p(tmem + lane_base + kColS + c2 * 32, rs);
-          ptx::tmem_st_32x16p(tmem + lane_base + kColS + c2 * 32 + 16, rs + 16);
-        }
-        ptx::tmem_st_32x16p(tmem + lane_base + kColDP + c2 * 32, rd);
-        ptx::tmem_st_32x16p(tmem + lane_base + kColDP + c2 * 32 + 16, rd + 16);
+        // packed bf16 results go to the front of the columns THIS thread has just read (the other warpgroup may
+        // still be loading its half): P at S + 32 * chalf, dS at dP + 32 * chalf, 16 columns each
+        if (MODE == 1) ptx::tmem_st_32x16p(buf + cb, rs);
+        ptx::tmem_st_32x16p(buf + BS + cb, rd);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(p_full);
+      ptx::mbar_arrive(&p_full[it & 1]);
     }
     // epilogue: accumulators -> (un-RoPE) -> bf16 rows
     ptx::mbar_wait(acc_done, 0);
@@ -301,7 +330,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       __nv_bfloat16* out = (which == 0 ? p.out0 : p.out1) + orow * (which == 0 ? p.ld0 : p.ld1) + h * HD + half * C::DH;
       const uint32_t col = which == 0 ? kColAcc0 : kColAcc1;
 #pragma unroll
-      for (int c = 0; c < C::DH / 32; ++c) {
+      for (int cc = 0; cc < C::DH / 64; ++cc) {
+        const int c = cc * 2 + chalf;     // the two compute warpgroups take alternate 32-column slabs
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem + lane_base + col + c * 32, r);
         ptx::tmem_ld_wait();
@@ -451,8 +481,8 @@ int attention_bwd_tc(const sea_attn_bwd_args* a, cudaStream_t s) {
              static_cast<const __nv_bfloat16*>(a->o), a->ldo, static_cast<const __nv_bfloat16*>(a->d_o), a->lddo,
              a->delta, a->B, a->T, a->n_heads, a->head_dim);
   switch (a->head_dim) {
-    case 64: return launch_both<64, 128>(a, s);
-    case 128: return launch_both<128, 128>(a, s);
+    case 64: return launch_both<64, 64>(a, s);
+    case 128: return launch_both<128, 64>(a, s);
     case 256: return launch_both<256, 64>(a, s);
     default: return SEA_ERR_UNSUPPORTED;
   }

@@ -276,15 +276,17 @@ __device__ __forceinline__ long long latent_index(int b, int p, int g, int d, in
                      : ((static_cast<long long>(b) * G + g) * P + p) * D + d;
 }
 
-// Shared-memory plan of the encoder (bytes, 16-byte aligned regions).  Region A is used twice: first by the patch MLPs
-// (snapshot in bf16 + the GELU'd hidden layer), then by the encoder blocks' MLP (fp32 pre-LN hidden + its bf16 GELU).
-// The patch-MLP hidden layer is processed in two column chunks (the second Linear accumulates over them) and the MLP's
-// bf16 GELU output overwrites the front of its own fp32 pre-LN row, which keeps a cylinder_flow snapshot under half an SM.
+// Shared-memory plan of the encoder (bytes, 16-byte aligned regions).  The snapshot is staged one field GROUP at a
+// time (bf16), the patch-MLP hidden layer is processed in three column chunks (the second Linear accumulates over
+// them), the MLP's fp32 pre-LN hidden reuses the q | k | v^T area plus the patch-MLP area (both dead by then) and its
+// bf16 GELU output overwrites the front of its own fp32 row: a cylinder_flow snapshot needs 67 KB (three CTAs per SM),
+// a multiphase_flow one 112 KB (two).
 struct EncPlan { int ld_in, ld_hid, ld_e, ld_v, ld_hh, hchunk; size_t off_z, off_n, off_q, off_k, off_v, off_a, a_hid, a_hh, total; };
-__host__ __device__ inline EncPlan enc_plan(int FC, int Hs, int Es) {
+__host__ __device__ inline EncPlan enc_plan(int group_width, int Hs, int Es) {
   EncPlan p{};
-  p.hchunk = ((Hs + 1) / 2 + 15) / 16 * 16;
-  p.ld_in = pitch_of(FC); p.ld_hid = pitch_of(p.hchunk); p.ld_e = pitch_of(Es); p.ld_v = pitch_of(P);
+  p.hchunk = ((Hs + 2) / 3 + 15) / 16 * 16;
+  p.ld_in = pitch_of(group_width); p.ld_hid = pitch_of(p.hchunk); p.ld_e = pitch_of(Es);
+  p.ld_v = P + 8;          // 36 words: the 8 value rows of a B fragment fall on distinct banks
   p.ld_hh = 4 * Es + 16;   // fp32 pitch; read as bf16 the same rows have pitch 2 * ld_hh == 32 (mod 64)
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t a = o; o += (bytes + 15) & ~static_cast<size_t>(15); return a; };
@@ -293,77 +295,80 @@ __host__ __device__ inline EncPlan enc_plan(int FC, int Hs, int Es) {
   p.off_q = take(sizeof(bf16) * P * p.ld_e);
   p.off_k = take(sizeof(bf16) * P * p.ld_e);
   p.off_v = take(sizeof(bf16) * (Es + 8) * p.ld_v);
-  p.off_a = o;
-  const size_t in_bytes = (sizeof(bf16) * P * p.ld_in + 15) & ~static_cast<size_t>(15);
-  p.a_hid = p.off_a + in_bytes;
-  p.a_hh = p.off_a;
-  const size_t use1 = in_bytes + sizeof(bf16) * P * p.ld_hid, use2 = sizeof(float) * P * p.ld_hh;
-  p.total = p.off_a + (use1 > use2 ? use1 : use2);
+  p.off_a = take(sizeof(bf16) * P * p.ld_in);
+  p.a_hid = take(sizeof(bf16) * P * p.ld_hid);
+  p.a_hh = p.off_q;
+  const size_t end_hh = p.a_hh + sizeof(float) * P * p.ld_hh;
+  p.total = o > end_hh ? o : end_hh;
   return p;
 }
 
 // ------------------------------------------------------------------------------------ encoder
-__global__ void __launch_bounds__(kThreads, 2) spatial_encode_tc_kernel(const SpatialTC a, float* __restrict__ x,
+__global__ void __launch_bounds__(kThreads, 3) spatial_encode_tc_kernel(const SpatialTC a, float* __restrict__ x,
                                                                         float* __restrict__ z, int layout, float pad_idx,
                                                                         int fix_pad) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int FC = a.n_fields * a.C, FCp = a.n_fields * a.Cp, Es = a.n_groups * a.D, hd = Es / a.n_heads;
-  const EncPlan pl = enc_plan(FCp, a.Hs, Es);
+  const int FC = a.n_fields * a.C, Es = a.n_groups * a.D, hd = Es / a.n_heads;
+  int gmax = 0;
+  for (int g = 0; g < a.n_groups; ++g) gmax = max(gmax, a.g_count[g]);
+  const EncPlan pl = enc_plan(gmax * a.Cp, a.Hs, Es);
   float* Z = reinterpret_cast<float*>(smraw + pl.off_z);     // [64][Es] fp32 residual state
   bf16* Nn = reinterpret_cast<bf16*>(smraw + pl.off_n);      // [64][ld_e] normed input / attention output
   bf16* Qs = reinterpret_cast<bf16*>(smraw + pl.off_q);
   bf16* Ks = reinterpret_cast<bf16*>(smraw + pl.off_k);
   bf16* Vt = reinterpret_cast<bf16*>(smraw + pl.off_v);      // [Es + 8][ld_v] values, transposed
-  bf16* Xin = reinterpret_cast<bf16*>(smraw + pl.off_a);     // [64][ld_in]
+  bf16* Xin = reinterpret_cast<bf16*>(smraw + pl.off_a);     // [64][ld_in] one field group of the snapshot
   bf16* Hid = reinterpret_cast<bf16*>(smraw + pl.a_hid);     // [64][ld_hid]
-  float* Hh = reinterpret_cast<float*>(smraw + pl.a_hh);     // [64][ld_hh] fp32 (pre-LN MLP hidden)
+  float* Hh = reinterpret_cast<float*>(smraw + pl.a_hh);     // [64][ld_hh] fp32 (pre-LN MLP hidden), over q | k | v^T | Xin..
   bf16* Hb = reinterpret_cast<bf16*>(Hh);                    // its GELU(LN(.)) in bf16, in place: pitch 2 * ld_hh
   const int b = blockIdx.x;
   float* xb = x + static_cast<long long>(b) * P * FC;
-  // (1) snapshot -> bf16; generate_padding_mask (models/encoder_decoder.py:173-176) in place
-  if ((a.C & 3) == 0) {
-    for (int i = threadIdx.x * 4; i < P * FC; i += kThreads * 4) {
+  // (1) generate_padding_mask (models/encoder_decoder.py:173-176): x[x == pad_idx] = 0, in place, whole snapshot
+  if (fix_pad) {
+    for (int i = threadIdx.x * 4; i < P * FC; i += kThreads * 4) {   // P * FC is a multiple of 64: aligned float4
       float4 v = *reinterpret_cast<const float4*>(xb + i);
-      if (fix_pad) {
-        const bool hit = v.x == pad_idx || v.y == pad_idx || v.z == pad_idx || v.w == pad_idx;
-        if (hit) {
-          v.x = v.x == pad_idx ? 0.f : v.x; v.y = v.y == pad_idx ? 0.f : v.y;
-          v.z = v.z == pad_idx ? 0.f : v.z; v.w = v.w == pad_idx ? 0.f : v.w;
-          *reinterpret_cast<float4*>(xb + i) = v;
-        }
+      if (v.x == pad_idx || v.y == pad_idx || v.z == pad_idx || v.w == pad_idx) {
+        v.x = v.x == pad_idx ? 0.f : v.x; v.y = v.y == pad_idx ? 0.f : v.y;
+        v.z = v.z == pad_idx ? 0.f : v.z; v.w = v.w == pad_idx ? 0.f : v.w;
+        *reinterpret_cast<float4*>(xb + i) = v;
       }
-      const int pf = i / a.C, c = i - pf * a.C;   // C % 4 == 0: the four elements share a (patch, field) row
-      const int p = pf / a.n_fields, f = pf - p * a.n_fields;
-      *reinterpret_cast<uint2*>(Xin + p * pl.ld_in + f * a.Cp + c) = make_uint2(ptx::pack_bf16(v.x, v.y), ptx::pack_bf16(v.z, v.w));
     }
-  } else {
-    for (int i = threadIdx.x; i < P * FC; i += kThreads) {
-      float v = xb[i];
-      if (fix_pad && v == pad_idx) { v = 0.f; xb[i] = 0.f; }
-      const int pf = i / a.C, c = i - pf * a.C;
-      const int p = pf / a.n_fields, f = pf - p * a.n_fields;
-      Xin[p * pl.ld_in + f * a.Cp + c] = __float2bfloat16_rn(v);
-    }
+    __syncthreads();
   }
-  if (a.Cp != a.C) {   // zero the padded cells (their weight columns are zero too, but smem garbage may be NaN)
-    const int padw = a.Cp - a.C;
-    for (int i = threadIdx.x; i < P * a.n_fields * padw; i += kThreads) {
-      const int pf = i / padw, c = a.C + i - pf * padw;
-      const int p = pf / a.n_fields, f = pf - p * a.n_fields;
-      Xin[p * pl.ld_in + f * a.Cp + c] = __float2bfloat16_rn(0.f);
-    }
-  }
-  for (int i = threadIdx.x; i < 8 * pl.ld_v; i += kThreads) Vt[Es * pl.ld_v + i] = __float2bfloat16_rn(0.f);
-  __syncthreads();
   // (2) per-group patch MLP: Linear(C*g, Hs, no bias) -> GELU -> Linear(Hs, D) + b, + positional encoding (:108-114)
   for (int g = 0; g < a.n_groups; ++g) {
-    const int Kin = a.g_count[g] * a.Cp;
+    const int cnt = a.g_count[g], Kin = cnt * a.Cp, gw = cnt * a.C;
+    const float* xg = xb + a.g_first[g] * a.C;        // row p of the group: xg + p * FC, gw contiguous floats
+    if ((a.C & 3) == 0) {
+      const int q4 = gw >> 2;
+      for (int i = threadIdx.x; i < P * q4; i += kThreads) {
+        const int p = i / q4, c4 = (i - p * q4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(xg + p * FC + c4);
+        const int f = c4 / a.C, c = c4 - f * a.C;      // C % 4 == 0: the four cells share a field
+        *reinterpret_cast<uint2*>(Xin + p * pl.ld_in + f * a.Cp + c) = make_uint2(ptx::pack_bf16(v.x, v.y), ptx::pack_bf16(v.z, v.w));
+      }
+    } else {
+      for (int i = threadIdx.x; i < P * gw; i += kThreads) {
+        const int p = i / gw, cc = i - p * gw;
+        const int f = cc / a.C, c = cc - f * a.C;
+        Xin[p * pl.ld_in + f * a.Cp + c] = __float2bfloat16_rn(xg[p * FC + cc]);
+      }
+    }
+    if (a.Cp != a.C) {   // zero the padded cells (their weight columns are zero too, but smem garbage may be NaN)
+      const int padw = a.Cp - a.C;
+      for (int i = threadIdx.x; i < P * cnt * padw; i += kThreads) {
+        const int pf = i / padw, c = a.C + i - pf * padw;
+        const int p = pf / cnt, f = pf - p * cnt;
+        Xin[p * pl.ld_in + f * a.Cp + c] = __float2bfloat16_rn(0.f);
+      }
+    }
+    __syncthreads();
     const float* b2 = a.enc_b2[g];
     for (int c0 = 0; c0 < a.Hs; c0 += pl.hchunk) {
       const int ch = min(pl.hchunk, a.Hs - c0);
-      gemm64_any(Xin + a.g_first[g] * a.Cp, pl.ld_in, Kin, a.enc_w1[g] + static_cast<long long>(c0) * Kin, Kin, ch,
+      gemm64_any(Xin, pl.ld_in, Kin, a.enc_w1[g] + static_cast<long long>(c0) * Kin, Kin, ch,
                  [&](int row, int col, float v0, float v1) {
                    *reinterpret_cast<uint32_t*>(Hid + row * pl.ld_hid + col) = ptx::pack_bf16(ptx::gelu_bf16(v0), ptx::gelu_bf16(v1));
                  });
@@ -386,6 +391,9 @@ __global__ void __launch_bounds__(kThreads, 2) spatial_encode_tc_kernel(const Sp
   for (int l = 0; l < a.num_layers; ++l) {
     const LayerTC& L = a.layers[l];
     layernorm_rows(Z, Es, Es, L.ln1_w, nullptr, Nn, pl.ld_e, false);
+    // rows past the last head of v^T feed discarded accumulator columns only, but must not hold NaN bit patterns
+    // (the area is shared with the previous layer's fp32 MLP hidden)
+    for (int i = threadIdx.x; i < 8 * pl.ld_v; i += kThreads) Vt[Es * pl.ld_v + i] = __float2bfloat16_rn(0.f);
     __syncthreads();
     gemm64_any(Nn, pl.ld_e, Es, L.qkv_w, Es, 3 * Es, [&](int row, int col, float v0, float v1) {
       v0 += __ldg(L.qkv_b + col); v1 += __ldg(L.qkv_b + col + 1);
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 2) spatial_encode_tc_kernel(const Sp
 }
 
 // ------------------------------------------------------------------------------------ decoder
-__global__ void __launch_bounds__(kThreads, 2) spatial_decode_tc_kernel(const SpatialTC a, const float* __restrict__ z,
+__global__ void __launch_bounds__(kThreads, 3) spatial_decode_tc_kernel(const SpatialTC a, const float* __restrict__ z,
                                                                         float* __restrict__ out, int layout) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
@@ -643,7 +651,9 @@ extern "C" int sea_spatial_encode_tc(const sea_spatial_desc* d, const void* cach
   for (int g = 0; g < a.n_groups; ++g)
     if (!d->enc_w1[g] || !d->enc_w2[g] || !a.enc_b2[g]) return SEA_ERR_INVALID;
   if (!a.ln_w || !a.ln_b || !a.pe) return SEA_ERR_INVALID;
-  const EncPlan pl = enc_plan(a.n_fields * a.Cp, a.Hs, a.n_groups * a.D);
+  int gmax = 0;
+  for (int g = 0; g < a.n_groups; ++g) gmax = a.g_count[g] > gmax ? a.g_count[g] : gmax;
+  const EncPlan pl = enc_plan(gmax * a.Cp, a.Hs, a.n_groups * a.D);
   if (pl.total > 227 * 1024) return SEA_ERR_UNSUPPORTED;
   SEA_CUDA_OK(cudaFuncSetAttribute(spatial_encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.total)));
   SEA_CUDA_OK(cudaFuncSetAttribute(spatial_encode_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
