@@ -61,6 +61,10 @@ struct ACfg {
   static constexpr uint32_t COL_O = HD <= 128 ? 128 : 256;
   static constexpr uint32_t TMEM_COLS = HD <= 128 ? 256 : 512;
   static constexpr int MIN_CTAS = (SMEM <= 110 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
+  // HD = 256 (one query tile per CTA: two would not fit TMEM): two S|P buffers of BKV = 64 columns in front of O, so
+  // the pipe computes S(j+1) while the softmax warps work on S(j) — the overlap the two-tile kernel gets from its
+  // second tile.  Issue order: S0, S1, then per key tile j: PV(j), S(j+2).
+  static constexpr bool PING = (HD == 256 && STAGES_ == 2 && 2 * BKV <= static_cast<int>(COL_O));
 };
 
 template <int HD, int BKV, int STAGES_, bool DROP>
@@ -80,10 +84,11 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
   uint64_t* q_full = bars;          // 1
   uint64_t* kv_full = bars + 1;     // [2]
   uint64_t* kv_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;      // 1   MMA -> softmax
-  uint64_t* p_full = bars + 6;      // 1   softmax (128 arrivals) -> MMA
-  uint64_t* o_done = bars + 7;      // 1   MMA -> softmax
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_full = bars + 5;      // [2] MMA -> softmax (one per S buffer)
+  uint64_t* p_full = bars + 7;      // [2] softmax (128 arrivals) -> MMA
+  uint64_t* o_done = bars + 9;      // 1   MMA -> softmax
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  constexpr bool PING = C::PING;
 
   // warp-uniform role index + elect.sync regions: see the note in gemm.cu (no waterfall loops
   // around UTMALDG / UTCHMMA)
@@ -104,8 +109,10 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
       ptx::mbar_init(&kv_full[s], 1);
       ptx::mbar_init(&kv_empty[s], 1);
     }
-    ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(p_full, 128);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&p_full[s], 128);
+    }
     ptx::mbar_init(o_done, 1);
     ptx::fence_barrier_init();
   }
@@ -145,8 +152,9 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
     constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
     constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
     ptx::mbar_wait(q_full, 0);
-    for (int j = 0; j < n_kv; ++j) {
+    auto issue_s = [&](int j) {
       const int s = j % C::STAGES;
+      const int sb = PING ? (j & 1) : 0;
       ptx::mbar_wait(&kv_full[s], (j / C::STAGES) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
@@ -156,13 +164,17 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
         for (int k = 0; k < HD / 16; ++k) {
           const uint32_t off = (k >> 2) * (BQ * 128) + (k & 3) * 32;
           const uint32_t koff = (k >> 2) * (BKV * 128) + (k & 3) * 32;
-          ptx::umma_f16_ss(tmem + kColS, ptx::umma_smem_desc(qb + off, 16, 1024),
+          ptx::umma_f16_ss(tmem + kColS + sb * BKV, ptx::umma_smem_desc(qb + off, 16, 1024),
                            ptx::umma_smem_desc(kb + koff, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         }
-        ptx::umma_commit(s_full);
+        ptx::umma_commit(&s_full[sb]);
       }
       __syncwarp();
-      ptx::mbar_wait(p_full, j & 1);
+    };
+    auto issue_pv = [&](int j) {
+      const int s = j % C::STAGES;
+      const int sb = PING ? (j & 1) : 0;
+      ptx::mbar_wait(&p_full[sb], PING ? ((j >> 1) & 1) : (j & 1));
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t vb = ptx::smem_u32(sV + s * C::KV_BYTES);
@@ -170,12 +182,24 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
         for (int k = 0; k < BKV / 16; ++k) {
           // 16 keys per step = two 8-row groups (SBO 1024 B); 64-wide head-dim chunks LBO apart
           const uint64_t vdesc = ptx::umma_smem_desc(vb + k * 2048, BKV * 128, 1024);
-          ptx::umma_f16_ts(tmem + kColO, tmem + kColP + k * 8, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+          ptx::umma_f16_ts(tmem + kColO, tmem + kColP + sb * BKV + k * 8, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
         }
         ptx::umma_commit(&kv_empty[s]);
         ptx::umma_commit(o_done);
       }
       __syncwarp();
+    };
+    if (PING) {
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_s(j + 1);
+        issue_pv(j);
+      }
+    } else {
+      for (int j = 0; j < n_kv; ++j) {
+        issue_s(j);
+        issue_pv(j);
+      }
     }
   } else {
     // ---------------------------------------------------------------- softmax warps
@@ -186,7 +210,9 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
     float m_ref = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int kv0 = j * BKV;
-      ptx::mbar_wait(s_full, j & 1);
+      const int sb = PING ? (j & 1) : 0;
+      const uint32_t colS = kColS + sb * BKV;     // this tile's S buffer; its packed P overwrites it in place
+      ptx::mbar_wait(&s_full[sb], PING ? ((j >> 1) & 1) : (j & 1));
       ptx::tc_fence_after();
       const bool need_mask = (kv0 + BKV - 1 > q0 + pp.src_len) || (kv0 + BKV > pp.T);
       // Two sweeps over the score row in 64-column chunks (max, then exponentials): a thread never holds more
@@ -197,7 +223,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
       uint32_t r[CHK];
       auto load_chunk = [&](int c) {
 #pragma unroll
-        for (int i = 0; i < CHK / 32; ++i) ptx::tmem_ld_32x32p(tmem + lane_base + kColS + c * CHK + i * 32, r + i * 32);
+        for (int i = 0; i < CHK / 32; ++i) ptx::tmem_ld_32x32p(tmem + lane_base + colS + c * CHK + i * 32, r + i * 32);
         ptx::tmem_ld_wait();
         if (need_mask) {
 #pragma unroll
@@ -222,7 +248,9 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
       const float m_cand = fmaxf(m_ref, mx * pp.scale_log2);
       const bool grow = (m_cand > m_ref + 8.0f) || (m_ref == -INFINITY && m_cand != -INFINITY);
       const bool any_grow = __any_sync(0xffffffffu, grow);
-      if (j > 0) {  // O is owned by the previous P·V until it retires
+      // O is owned by the previous P.V until it retires.  With one S buffer so is P's destination; with two, only a
+      // rescale of O has to wait (S(j) complete implies P.V(j-2) complete, so the parity wait cannot lag a phase)
+      if (j > 0 && (!PING || any_grow)) {
         ptx::mbar_wait(o_done, (j - 1) & 1);
         ptx::tc_fence_after();
       }
@@ -267,14 +295,14 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams pp) {
         }
 #pragma unroll
         for (int i = 0; i < CHK / 32; ++i)
-          ptx::tmem_st_32x16p(tmem + lane_base + kColP + c * (CHK / 2) + i * 16, r + i * 16);
+          ptx::tmem_st_32x16p(tmem + lane_base + colS + c * (CHK / 2) + i * 16, r + i * 16);
         // the next chunk's load must not overtake these stores in the TMEM pipe (P of chunk c lands in columns
         // below chunk c+1, but the load of chunk c+1 reuses the registers the store is still reading)
         ptx::tmem_st_wait();
       }
       l_sum += l0 + l1;
       ptx::tc_fence_before();
-      ptx::mbar_arrive(p_full);
+      ptx::mbar_arrive(&p_full[sb]);
     }
     // epilogue: O / l  -> bf16, log-sum-exp
     ptx::mbar_wait(o_done, (n_kv - 1) & 1);
