@@ -429,6 +429,9 @@ int sea_attention_bwd(const sea_attn_bwd_args* args, sea_stream_t stream);
 void sea_attention_force_simt(int on);
 /* Tuning hook: 0 = one 128-query tile per CTA for every T (default 1: two tiles per CTA, overlapped, when T > 128). */
 void sea_attention_two_tiles(int on);
+/* tuning probe for the tensor-core backward (results are WRONG when non-zero): 1 = the compute warps only hand the
+ * barriers over, 2 = they move S | dP through TMEM but skip the arithmetic; 0 = normal. */
+void sea_attention_bwd_probe(int mode);
 /* Tuning hook: non-NULL = the two-tile forward kernel (head_dim 128, no dropout) records clock64 probes of CTA (0,0,0)
  * into dev_buf (3 x 64 x 8 int64: softmax group 0 / 1 and the MMA warp, per key tile); NULL switches it off. */
 void sea_attention_debug_trace(void* dev_buf);

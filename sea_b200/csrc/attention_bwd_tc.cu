@@ -31,6 +31,7 @@
 #include "ptx.cuh"
 
 namespace sea {
+int g_attn_bwd_probe = 0;
 namespace {
 
 constexpr int BR = 128;  // stationary rows per CTA (TMEM lanes)
@@ -49,6 +50,7 @@ struct alignas(64) AttnBwdTcParams {
   unsigned long long drop_seed;   // probability dropout of the forward, regenerated here (DROP kernels)
   uint32_t drop_thresh, drop_site;
   float drop_scale;
+  int probe;   // tuning probe (sea_attention_bwd_probe): 1 = compute warps skip TMEM traffic and arithmetic, 2 = skip arithmetic only
 };
 
 template <int HD, int BS, int MODE>
@@ -268,13 +270,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       ptx::mbar_wait(&s_full[it & 1], (it >> 1) & 1);
       ptx::tc_fence_after();
       // this thread's 32 columns of S and dP in one TMEM round trip, results written back in place
-      {
+      if (p.probe != 1) {
         const uint32_t buf = tmem + lane_base + (it & 1) * kColBuf;
         const int cb = chalf * 32;
         uint32_t rs[32], rd[32];
         ptx::tmem_ld_32x32p(buf + cb, rs);
         ptx::tmem_ld_32x32p(buf + BS + cb, rd);
         ptx::tmem_ld_wait();
+        if (p.probe != 2)
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           float pv[2], dv[2];
@@ -436,6 +439,7 @@ int launch_mode(const sea_attn_bwd_args* a, cudaStream_t s) {
   p.drop_seed = a->dropout_seed; p.drop_site = a->dropout_site;
   p.drop_thresh = a->dropout_p > 0.f ? static_cast<uint32_t>(static_cast<double>(a->dropout_p) * 4294967296.0) : 0u;
   p.drop_scale = 1.0f / (1.0f - a->dropout_p);
+  p.probe = g_attn_bwd_probe;
   const int tiles = (a->T + BR - 1) / BR;
   dim3 grid(a->n_heads * a->B, 1, tiles * (MODE == 1 ? C::HALVES : 1));
   SEA_LAUNCH((attn_bwd_tc_kernel<HD, BS, MODE, DROP>), grid, kThreads, C::SMEM, s, p);

@@ -64,7 +64,14 @@ struct ACfg {
   // HD = 256 (one query tile per CTA: two would not fit TMEM): two S|P buffers of BKV = 64 columns in front of O, so
   // the pipe computes S(j+1) while the softmax warps work on S(j) — the overlap the two-tile kernel gets from its
   // second tile.  Issue order: S0, S1, then per key tile j: PV(j), S(j+2).
+  // Measured on B200 (B=4, T=2024): 116.7 us with the two buffers vs 105.5 us with one — the softmax warps, not the
+  // pipe, bound this kernel (64 scores per thread against 1024 cycles of MMA per key tile), and issuing S(j+1) first
+  // only delays P.V(j) behind it.  Kept as a compile-time switch (SEA_ATTN_PING256), off by default.
+#ifdef SEA_ATTN_PING256
   static constexpr bool PING = (HD == 256 && STAGES_ == 2 && 2 * BKV <= static_cast<int>(COL_O));
+#else
+  static constexpr bool PING = false;
+#endif
 };
 
 template <int HD, int BKV, int STAGES_, bool DROP>
