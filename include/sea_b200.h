@@ -556,6 +556,16 @@ typedef struct sea_temporal_desc {
   const float* grad_f32_base;
   void* grad_bf16;
   void* bwd_events[SEA_BWD_GROUPS];
+  /* ---- two-stream inference schedule (sea_temporal_forward / _strided / _step, bf16 mode; optional, NULL = off) ----
+   * The exchange is sequential over the streams (Gauss-Seidel, models/temporal.py:187-192) and its steps are small,
+   * latency-bound launches.  Once stream i has been exchanged, its TIPI / MLP / proj tail (models/temporal.py:140-146)
+   * does not depend on the later streams: the executor enqueues it on aux_stream (a cudaStream_t), released by
+   * fork_events[i] (cudaEvent_t, recorded on the caller's stream), and the caller's stream waits for join_event
+   * (recorded on aux_stream) at the end of the block.  Capturable: the auxiliary stream joins a stream capture
+   * through the events.  Same kernels, same arithmetic, same results. */
+  void* aux_stream;
+  void* fork_events[SEA_MAX_STREAMS];
+  void* join_event;
 } sea_temporal_desc;
 
 /* Packed low-precision copies of the weights (bf16, fused QKV / KV, optional transposes for the

@@ -95,6 +95,7 @@ void layout_cache(const sea_temporal_desc* d, bool training, Arena& ar, CacheLay
   // stream-K workspace of the GEMM launches (arrival counters + parked partial tiles), see sea_gemm_set_workspace
   c.splitk_bytes = kSplitKBytes;
   c.splitk = ar.take(c.splitk_bytes);
+  c.splitk_aux = ar.take(c.splitk_bytes);
 }
 
 static int pack_weight(const float* src, int N, int K, const PackedLinear& dst, int row_off,
@@ -220,6 +221,7 @@ extern "C" int sea_temporal_refresh_ex(const sea_temporal_desc* d, void* cache, 
   const bool fp32 = d->precision == SEA_PREC_FP32;
   const int E = d->embed_dim, Dd = d->down_dim, V = d->num_streams;
   SEA_CUDA_OK(cudaMemsetAsync(c.splitk, 0, 65536, s));   // stream-K arrival counters start at zero
+  SEA_CUDA_OK(cudaMemsetAsync(c.splitk_aux, 0, 65536, s));
   SEA_TRY(for_each_weight(d, c, [&](const float* src, int N, int K, const PackedLinear& dst, int row_off, int n_total) {
     return pack_weight(src, N, K, dst, row_off, n_total, fp32, what, s);
   }));
@@ -386,6 +388,7 @@ int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, c
     }
   }
   ++g_launches;
+  if (c.splitk != nullptr) SEA_TRY(sea_gemm_set_workspace(c.splitk, kSplitKBytes));   // host-side selection, per launch
   ProfScope prof(c.s, SEA_PROF_GEMM, 2.0 * Mrows * static_cast<double>(N) * K * n);
   if (c.fp32) {
     // fresh accumulator every 512 columns of K' so the tensor core's non-RN accumulation cannot drift
@@ -640,6 +643,14 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
   const int kind = d->norm_kind;
   const size_t esz = c.fp32 ? 4 : 2;
   sea_stream_t st = stream;
+  // two-stream schedule (inference, bf16): see the fork inside the exchange loop.  Needs the caller's auxiliary stream and
+  // events (desc->aux_stream, fork_events, join_event); the auxiliary GEMMs get their own stream-K workspace.
+  bool fork = d->aux_stream != nullptr && d->join_event != nullptr && training == 0 && !c.fp32 && V >= 2 && !g_prof_on;
+  for (int i = 0; fork && i < V - 1; ++i) fork = d->fork_events[i] != nullptr;
+  c.splitk = cl.splitk;
+  Ctx caux = c;
+  caux.s = reinterpret_cast<cudaStream_t>(d->aux_stream);
+  caux.splitk = cl.splitk_aux;
 
   // ---- everything that depends on ib only: TIPI hidden + all AdaLN conditions (hoisted) ----
   // With a time-invariant condition the results live in the caller's persistent cond cache and
@@ -781,6 +792,65 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
     }
     SEA_TRY(linear_group(c, V, in, W, out, M));
 
+    // (3) x_i += TIPI(ib) fused with Norm_{i,2}; (4) MLP; (5) proj    models/temporal.py:140-146
+    // for the streams [i0, i1), enqueued through `cx` (the caller's stream, or the auxiliary one: see the fork below)
+    auto block_tail = [&](Ctx& cx, int i0, int i1) -> int {
+      const int nn = i1 - i0;
+      NormCall nc2[SEA_MAX_STREAMS];
+      LinIn tin[SEA_MAX_STREAMS];
+      LinOut tout[SEA_MAX_STREAMS];
+      const PackedLinear* tW[SEA_MAX_STREAMS];
+      for (int i = i0; i < i1; ++i) {
+        nc2[i - i0] = norm_call(cx, kind, bp.s[i].ln2, lt.s[i].cond2, lt.s[i].xp, E, E, lt.s[i].n2, nullptr, 0,
+                             lt.s[i].st2, &bp, inv ? lt.tipi_rows : lt.tipi_g, lt.s[i].x2);
+        if (cx.drop_p > 0.f) {   // the ib-MLP is called once per stream: independent masks (temporal.py:140-142)
+          nc2[i - i0].a.tipi_dropout_p = cx.drop_p; nc2[i - i0].a.tipi_dropout_site = drop_site(l, SEA_SITE_TIPI, i, 0);
+          nc2[i - i0].a.tipi_dropout_seed = d->dropout_seed;
+        }
+      }
+      SEA_TRY(norm_group(cx, nn, nc2));
+      for (int i = i0; i < i1; ++i) {
+        tin[i - i0] = LinIn{lt.s[i].n2, E, 0};
+        tW[i - i0] = &bc.s[i].mlp0;
+        tout[i - i0] = LinOut{};
+        tout[i - i0].bias = bp.s[i].mlp0_b.p;
+        tout[i - i0].post = lt.s[i].h; tout[i - i0].ld_post = H;
+      }
+      SEA_TRY(linear_group(cx, nn, tin, tW, tout, M));
+      {
+        sea_ln_gelu_args la[SEA_MAX_STREAMS];
+        for (int i = i0; i < i1; ++i) {
+          sea_ln_gelu_args& a = la[i - i0];
+          a = sea_ln_gelu_args{};
+          if (cx.fp32) { a.h_f32 = static_cast<const float*>(lt.s[i].h); a.g_f32 = static_cast<float*>(lt.s[i].gh); }
+          else { a.h_bf16 = lt.s[i].h; a.g_bf16 = lt.s[i].gh; }
+          a.ldh = H; a.ldg = H; a.M = M; a.H = H;
+          a.weight = bp.s[i].mlp_ln_w.p; a.bias = bp.s[i].mlp_ln_b.p; a.stats = lt.s[i].stH;
+        }
+        ProfScope prof(cx.s, SEA_PROF_ELEMWISE, 2.0 * esz * M * static_cast<double>(H) * nn);
+        SEA_TRY(sea_ln_gelu_fwd_group(nn, la, reinterpret_cast<sea_stream_t>(cx.s)));
+        ++g_launches;
+      }
+      for (int i = i0; i < i1; ++i) {
+        tin[i - i0] = LinIn{lt.s[i].gh, H, 0};
+        tW[i - i0] = &bc.s[i].mlp3;
+        tout[i - i0] = LinOut{};
+        tout[i - i0].bias = bp.s[i].mlp3_b.p;
+        tout[i - i0].residual = lt.s[i].x2; tout[i - i0].ld_res = E;
+        tout[i - i0].post = lt.s[i].x3; tout[i - i0].ld_post = E;
+        tout[i - i0].drop_p = cx.drop_p; tout[i - i0].drop_site = drop_site(l, SEA_SITE_MLP, i, 0);
+      }
+      SEA_TRY(linear_group(cx, nn, tin, tW, tout, M));
+      for (int i = i0; i < i1; ++i) {
+        tin[i - i0] = LinIn{lt.s[i].x3, E, 0};
+        tW[i - i0] = &bc.s[i].proj;
+        tout[i - i0] = LinOut{};
+        tout[i - i0].bias = bp.s[i].proj_b.p;
+        tout[i - i0].f32 = lt.s[i].xout; tout[i - i0].ld_f32 = E;
+      }
+      SEA_TRY(linear_group(cx, nn, tin, tW, tout, M));
+      return SEA_OK;
+    };
     // (2) State-Exchange Attention, sequential over i   models/temporal.py:176-192
     for (int i = 0; i < V; ++i) {
       in[i] = LinIn{c.fp32 ? static_cast<const void*>(lt.s[i].x1) : lt.s[i].x1b, E, 0};
@@ -891,6 +961,13 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
       if (V == 1) {  // no partner stream: exchange is the identity
         SEA_CUDA_OK(cudaMemcpyAsync(s.xp, s.x1, sizeof(float) * M * E, cudaMemcpyDeviceToDevice, c.s));
       }
+      if (fork && i < V - 1) {
+        // stream i is final for this block: its TIPI / MLP / proj tail (half of the block's FLOPs at V = 2) goes to the
+        // auxiliary stream and fills the SMs the remaining, latency-bound exchange steps of the later streams leave idle
+        SEA_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(d->fork_events[i]), c.s));
+        SEA_CUDA_OK(cudaStreamWaitEvent(caux.s, static_cast<cudaEvent_t>(d->fork_events[i]), 0));
+        SEA_TRY(block_tail(caux, i, i + 1));
+      }
       if (i < V - 1) {  // later streams see the UPDATED stream i (Gauss–Seidel)
         in[0] = LinIn{c.fp32 ? static_cast<const void*>(s.xp) : s.xpb, E, 0};
         W[0] = &bc.s[i].down;
@@ -904,56 +981,13 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
       }
     }
 
-    // (3) x_i += TIPI(ib) fused with Norm_{i,2}; (4) MLP; (5) proj    models/temporal.py:140-146
-    for (int i = 0; i < V; ++i) {
-      ncall[i] = norm_call(c, kind, bp.s[i].ln2, lt.s[i].cond2, lt.s[i].xp, E, E, lt.s[i].n2, nullptr, 0,
-                           lt.s[i].st2, &bp, inv ? lt.tipi_rows : lt.tipi_g, lt.s[i].x2);
-      if (c.drop_p > 0.f) {   // the ib-MLP is called once per stream: independent masks (temporal.py:140-142)
-        ncall[i].a.tipi_dropout_p = c.drop_p; ncall[i].a.tipi_dropout_site = drop_site(l, SEA_SITE_TIPI, i, 0);
-        ncall[i].a.tipi_dropout_seed = d->dropout_seed;
-      }
+    if (fork) {   // the last stream's tail on the caller's stream; the others are already running on the auxiliary one
+      SEA_TRY(block_tail(c, V - 1, V));
+      SEA_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(d->join_event), caux.s));
+      SEA_CUDA_OK(cudaStreamWaitEvent(c.s, static_cast<cudaEvent_t>(d->join_event), 0));
+    } else {
+      SEA_TRY(block_tail(c, 0, V));
     }
-    SEA_TRY(norm_group(c, V, ncall));
-    for (int i = 0; i < V; ++i) {
-      in[i] = LinIn{lt.s[i].n2, E, 0};
-      W[i] = &bc.s[i].mlp0;
-      out[i] = LinOut{};
-      out[i].bias = bp.s[i].mlp0_b.p;
-      out[i].post = lt.s[i].h; out[i].ld_post = H;
-    }
-    SEA_TRY(linear_group(c, V, in, W, out, M));
-    {
-      sea_ln_gelu_args la[SEA_MAX_STREAMS];
-      for (int i = 0; i < V; ++i) {
-        sea_ln_gelu_args& a = la[i];
-        a = sea_ln_gelu_args{};
-        if (c.fp32) { a.h_f32 = static_cast<const float*>(lt.s[i].h); a.g_f32 = static_cast<float*>(lt.s[i].gh); }
-        else { a.h_bf16 = lt.s[i].h; a.g_bf16 = lt.s[i].gh; }
-        a.ldh = H; a.ldg = H; a.M = M; a.H = H;
-        a.weight = bp.s[i].mlp_ln_w.p; a.bias = bp.s[i].mlp_ln_b.p; a.stats = lt.s[i].stH;
-      }
-      ProfScope prof(c.s, SEA_PROF_ELEMWISE, 2.0 * esz * M * static_cast<double>(H) * V);
-      SEA_TRY(sea_ln_gelu_fwd_group(V, la, st));
-      ++g_launches;
-    }
-    for (int i = 0; i < V; ++i) {
-      in[i] = LinIn{lt.s[i].gh, H, 0};
-      W[i] = &bc.s[i].mlp3;
-      out[i] = LinOut{};
-      out[i].bias = bp.s[i].mlp3_b.p;
-      out[i].residual = lt.s[i].x2; out[i].ld_res = E;
-      out[i].post = lt.s[i].x3; out[i].ld_post = E;
-      out[i].drop_p = c.drop_p; out[i].drop_site = drop_site(l, SEA_SITE_MLP, i, 0);
-    }
-    SEA_TRY(linear_group(c, V, in, W, out, M));
-    for (int i = 0; i < V; ++i) {
-      in[i] = LinIn{lt.s[i].x3, E, 0};
-      W[i] = &bc.s[i].proj;
-      out[i] = LinOut{};
-      out[i].bias = bp.s[i].proj_b.p;
-      out[i].f32 = lt.s[i].xout; out[i].ld_f32 = E;
-    }
-    SEA_TRY(linear_group(c, V, in, W, out, M));
     for (int i = 0; i < V; ++i) xin[i] = lt.s[i].xout;
     ldxin = E;
   }

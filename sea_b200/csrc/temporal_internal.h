@@ -42,6 +42,7 @@ struct CacheLayout {
   std::vector<BlockCache> blocks;
   PackedLinear c2_final[SEA_MAX_STREAMS];
   void* splitk;         // stream-K workspace (sea_gemm_set_workspace)
+  void* splitk_aux;     // a second one for GEMMs enqueued on the auxiliary stream (desc->aux_stream)
   size_t splitk_bytes;
 };
 
@@ -117,6 +118,7 @@ struct Ctx {
   bool inv;          // condition path evaluated once per trajectory (time-invariant ib)
   float drop_p;      // train-mode dropout probability of this call (0 in eval / inference)
   int pos0;          // absolute position of row 0 of every trajectory (KV-cached step: the new token's)
+  void* splitk;      // stream-K workspace of the GEMMs this context launches (NULL: leave the current one)
 };
 
 struct LinIn {

@@ -15,6 +15,7 @@ Train-mode dropout (cylinder_flow: 0.1) is applied inside the kernels (counter-b
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 import types
 from typing import Dict, Optional
@@ -450,7 +451,28 @@ class TemporalEngine:
         for i in range(V):
             d.final_ln[i] = norm(m.ln[i])
         d.rope_self, d.rope_cross = rope_self.data_ptr(), rope_cross.data_ptr()
+        # two-stream inference schedule (sea_temporal_desc.aux_stream): one auxiliary stream + events per engine
+        if self.two_streams and self.precision == "bf16" and V >= 2:
+            aux = self._aux_handles(dev, V)
+            d.aux_stream = aux[0].cuda_stream
+            for i in range(V - 1):
+                d.fork_events[i] = aux[1][i]
+            d.join_event = aux[1][V - 1]
         self._desc, self._keep, self._h = d, (blocks, rope_self, rope_cross), h
+
+    two_streams = os.environ.get("SEA_TWO_STREAMS", "1") != "0"
+
+    def _aux_handles(self, dev, V):
+        key = (dev.index, V)
+        if getattr(self, "_aux", None) is None or self._aux[2] != key:
+            evs = []
+            with torch.cuda.device(dev):
+                for _ in range(V):
+                    ev = C.c_void_p()
+                    check(lib.sea_event_create(C.byref(ev)), "event_create")
+                    evs.append(ev)
+                self._aux = (torch.cuda.Stream(device=dev), evs, key)
+        return self._aux
         self._dev = dev
 
     def _rope_tables(self):
