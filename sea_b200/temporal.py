@@ -459,6 +459,7 @@ class TemporalEngine:
                 d.fork_events[i] = aux[1][i]
             d.join_event = aux[1][V - 1]
         self._desc, self._keep, self._h = d, (blocks, rope_self, rope_cross), h
+        self._dev = dev
 
     two_streams = os.environ.get("SEA_TWO_STREAMS", "1") != "0"
 
@@ -473,7 +474,6 @@ class TemporalEngine:
                     evs.append(ev)
                 self._aux = (torch.cuda.Stream(device=dev), evs, key)
         return self._aux
-        self._dev = dev
 
     def _rope_tables(self):
         """RoPE tables in the kernels' layout, built ONCE per (engine, source buffers): CUDA graphs recorded by
