@@ -1,0 +1,372 @@
+"""Module-level CUDA path for the reference's NON-DEFAULT block variants.
+
+The fused whole-model executor (``sea_temporal_forward`` / ``_backward``) implements the configuration both reference
+configs select (``exchange_mode='sea'``, ``ib_scale_mode='mlp'``, ``ib_addition_mode='add'``).  The reference also ships
+``SEAPoolBlockTemporal`` / ``AddBlockTemporal`` / ``SimpleBlockTemporal`` (models/temporal.py:197-312) and the
+``fourier`` / ``linear`` ib layers with the ``concat`` / ``attention`` / ``none`` addition modes (:103-120).  For those,
+``accelerate_modules(model)`` keeps the reference's own Python orchestration of a block (its ``forward`` and
+``_apply_exchange`` run unchanged) and rebinds ``forward`` on the leaf modules that carry the FLOPs —
+
+* ``nn.Linear``                              one tcgen05 GEMM (bias in the epilogue); backward = dgrad + wgrad GEMMs reading
+                                             the operands as they lie (MN-major descriptors) + a column-sum kernel,
+* ``MaskedMultiHeadAttention`` / ``MaskedMultiHeadCrossAttention`` / ``MultiHeadCrossAttention``
+                                             q | k | v projections (RoPE in the GEMM epilogue) -> fused flash attention
+                                             (tcgen05 forward, recompute backward with the un-rotation in its epilogue)
+                                             -> output projection,
+* ``AdaLN`` / ``LayerNorm`` (weight only)    the row-norm kernels (forward + backward incl. the condition gradient),
+* ``MLP``                                    Linear -> [nn.LayerNorm + GELU fused kernel] -> Linear (single-hidden-layer form),
+
+each as a ``torch.autograd.Function`` over the C ABI, so ``.grad`` lands on the same ``nn.Parameter`` objects.  bf16
+tensor-core operands, fp32 accumulation / residuals (the library's bf16 mode).  Leaf modules whose shapes the kernels do
+not cover (head dims outside {32k}, widths not multiples of 8, train-mode attention dropout) are LEFT UNTOUCHED and keep
+running the reference's own eager code — that is not a fallback shipped by this package.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import types
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import check, lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _to_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Contiguous 2-D fp32 -> bf16 through the library's cast kernel (bf16 inputs pass through)."""
+    if x.dtype == torch.bfloat16:
+        return x if x.is_contiguous() else x.contiguous()
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if x.numel():
+        check(lib.sea_cast_f32_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), C.c_int64(x.numel()), _stream()),
+              "cast_f32_bf16")
+    return out
+
+
+class _WeightCache:
+    """bf16 tensor-core copies of fp32 parameters, refreshed when the parameter's version / storage changes."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, p: torch.Tensor) -> torch.Tensor:
+        key = id(p)
+        hit = self._d.get(key)
+        if hit is None or hit[0] != p._version or hit[1] != p.data_ptr():
+            hit = (p._version, p.data_ptr(), _to_bf16(p.detach()))
+            self._d[key] = hit
+        return hit[2]
+
+
+_weights = _WeightCache()
+
+
+def _colsum(dy: torch.Tensor) -> torch.Tensor:
+    out = torch.zeros(dy.shape[1], device=dy.device, dtype=torch.float32)
+    f32 = dy.dtype == torch.float32
+    check(lib.sea_colsum_accumulate(C.c_void_p(dy.data_ptr()) if f32 else None, None if f32 else C.c_void_p(dy.data_ptr()),
+                                    C.c_int64(dy.stride(0)), dy.shape[0], dy.shape[1], C.c_void_p(out.data_ptr()), _stream()),
+          "colsum")
+    return out
+
+
+def _gemm_nt(a_b16, w_b16, bias=None, *, rope=None, head_dim=0, seq_len=0, out_dtype=torch.float32, static=True):
+    """[M,K] x [N,K]^T (+bias, optional RoPE on all N columns) -> [M,N]."""
+    M, K = a_b16.shape
+    N = w_b16.shape[0]
+    out = torch.empty(M, N, device=a_b16.device, dtype=out_dtype)
+    kw = dict(bias=bias, b_is_static=static)
+    if rope is not None:
+        kw.update(rope_table=rope, rope_cols=N, head_dim=head_dim, seq_len=seq_len)
+    if out_dtype == torch.float32:
+        kw["out_f32"] = out
+    else:
+        kw["out_pre_bf16"] = out
+    ops.gemm_bf16_tn([ops.gemm_problem(a_b16, w_b16, **kw)], M, N, K)
+    return out
+
+
+def _gemm_dgrad(dy_b16, w_b16, out_dtype=torch.float32):
+    """dx[M,K] = dy[M,N] W[N,K]: W read as an MN-major B operand."""
+    M, N = dy_b16.shape
+    K = w_b16.shape[1]
+    out = torch.empty(M, K, device=dy_b16.device, dtype=out_dtype)
+    kw = {"out_f32": out} if out_dtype == torch.float32 else {"out_pre_bf16": out}
+    ops.gemm_bf16_tn([ops.gemm_problem(dy_b16, w_b16, mn_major=2, b_is_static=True, **kw)], M, K, N)
+    return out
+
+
+def _gemm_wgrad(dy_b16, x_b16):
+    """dW[N,K] = dy[M,N]^T x[M,K]: both operands MN-major, no transposes."""
+    M, N = dy_b16.shape
+    K = x_b16.shape[1]
+    out = torch.empty(N, K, device=dy_b16.device, dtype=torch.float32)
+    ops.gemm_bf16_tn([ops.gemm_problem(dy_b16, x_b16, mn_major=3, out_f32=out)], N, K, M)
+    return out
+
+
+def _linear_ok(lin: nn.Linear) -> bool:
+    N, K = lin.weight.shape
+    return (lin.weight.is_cuda and lin.weight.dtype == torch.float32 and K % 8 == 0 and N % 8 == 0 and K >= 16 and N >= 16)
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, weight, bias):
+        xb = _to_bf16(x2)
+        wb = _weights.get(weight)
+        y = _gemm_nt(xb, wb, None if bias is None else bias.detach())
+        ctx.save_for_backward(xb, wb)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb = ctx.saved_tensors
+        dyb = _to_bf16(dy)
+        dx = _gemm_dgrad(dyb, wb) if ctx.needs_input_grad[0] else None
+        dw = _gemm_wgrad(dyb, xb) if ctx.needs_input_grad[1] else None
+        db = _colsum(dy.contiguous()) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def _linear_forward(self, x):
+    if not x.is_cuda:
+        raise RuntimeError("sea_b200 has no CPU path: inputs must be CUDA tensors")
+    shp = x.shape
+    y = _LinearFn.apply(x.reshape(-1, shp[-1]), self.weight, self.bias)
+    return y.view(*shp[:-1], y.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _rope_table(mod) -> Optional[torch.Tensor]:
+    """freqs_cis [max_len, hd/2] complex -> the kernels' pair-major [hd/2, max_len, 2] fp32 table (cached on the module)."""
+    fc = getattr(mod, "freqs_cis", None)
+    if fc is None:
+        return None
+    key = (fc.data_ptr(), fc._version)
+    hit = getattr(mod, "_sea_rope", None)
+    if hit is None or hit[0] != key:
+        hit = (key, torch.view_as_real(fc).float().transpose(0, 1).contiguous())
+        mod._sea_rope = hit
+    return hit[1]
+
+
+class _AttnFn(torch.autograd.Function):
+    """projection(softmax(mask(rope(q(x1)) rope(k(x2))^T * hd^-1/2)) v(x2)) — models/base_blocks.py:175-203, 215-242,
+    267-295.  causal: tril(diagonal=src_len); rope: llama-style interleaved pairs on q and k."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, qw, qb, kw, kb, vw, vb, pw, n_heads, src_len, rope, B):
+        M, Cq = x1.shape
+        T = M // B
+        hd = qw.shape[0] // n_heads
+        x1b = _to_bf16(x1)
+        x2b = x1b if x2 is x1 else _to_bf16(x2)
+        kwargs = dict(rope=rope, head_dim=hd, seq_len=T, out_dtype=torch.bfloat16) if rope is not None else dict(out_dtype=torch.bfloat16)
+        q = _gemm_nt(x1b, _weights.get(qw), qb.detach(), **kwargs)
+        k = _gemm_nt(x2b, _weights.get(kw), kb.detach(), **kwargs)
+        v = _gemm_nt(x2b, _weights.get(vw), vb.detach(), out_dtype=torch.bfloat16)
+        o, lse = ops.attention_fwd(q, k, v, n_heads, src_len=src_len, B=B, want_lse=True)
+        y = _gemm_nt(o, _weights.get(pw), None)
+        ctx.save_for_backward(x1b, x2b, q, k, v, o, lse, _weights.get(qw), _weights.get(kw), _weights.get(vw), _weights.get(pw))
+        ctx.meta = (n_heads, src_len, rope, B, x2 is x1)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x1b, x2b, q, k, v, o, lse, qwb, kwb, vwb, pwb = ctx.saved_tensors
+        n_heads, src_len, rope, B, same = ctx.meta
+        dyb = _to_bf16(dy)
+        d_o = _gemm_dgrad(dyb, pwb, out_dtype=torch.bfloat16)
+        dpw = _gemm_wgrad(dyb, o)
+        dq, dk, dv = ops.attention_bwd(q, k, v, o, d_o, lse, n_heads, B=B, src_len=src_len, rope_table=rope)
+        dx1 = _gemm_dgrad(dq, qwb)
+        dx2 = _gemm_dgrad(dk, kwb)
+        dx2v = _gemm_dgrad(dv, vwb)
+        dx2 = dx2.add_(dx2v)
+        if same:
+            dx1 = dx1.add_(dx2)
+            dx2 = None
+        return (dx1, dx2, _gemm_wgrad(dq, x1b), _colsum(dq), _gemm_wgrad(dk, x2b), _colsum(dk), _gemm_wgrad(dv, x2b), _colsum(dv),
+                dpw, None, None, None, None)
+
+
+def _attn_ok(mod) -> bool:
+    hd = mod.head_dim
+    lin_ok = all(_linear_ok(l) for l in (mod.q, mod.k, mod.v, mod.projection))
+    return lin_ok and hd % 32 == 0 and hd <= 256 and mod.projection.bias is None
+
+
+def _attn_call(mod, x1, x2, causal: bool):
+    p_drop = float(mod.dropout.p) if isinstance(mod.dropout, nn.Dropout) else 0.0
+    if mod.training and p_drop > 0.0:
+        return None          # probability dropout: the caller keeps the reference's eager forward for this call
+    B, T, Cq = x1.shape
+    if x2.shape[1] != T:
+        return None
+    if causal:
+        src_len = int(mod.tril[0, 0, 0].sum().item()) - 1 if not hasattr(mod, "_sea_src_len") else mod._sea_src_len
+        mod._sea_src_len = src_len
+    else:
+        src_len = T          # every key visible
+    rope = _rope_table(mod) if causal else None
+    y = _AttnFn.apply(x1.reshape(B * T, Cq), x1.reshape(B * T, Cq) if x2 is x1 else x2.reshape(B * T, x2.shape[-1]),
+                      mod.q.weight, mod.q.bias, mod.k.weight, mod.k.bias, mod.v.weight, mod.v.bias, mod.projection.weight,
+                      mod.n_heads, src_len, rope, B)
+    return y.view(B, T, -1)
+
+
+def _self_attn_forward(self, x):
+    xr = x.reshape(x.shape[0] * x.shape[1], x.shape[2])
+    p_drop = float(self.dropout.p)
+    if self.training and p_drop > 0.0:
+        return self._sea_eager_forward(x)
+    B, T, Cq = x.shape
+    if not hasattr(self, "_sea_src_len"):
+        self._sea_src_len = int(self.tril[0, 0, 0].sum().item()) - 1
+    y = _AttnFn.apply(xr, xr, self.q.weight, self.q.bias, self.k.weight, self.k.bias, self.v.weight, self.v.bias,
+                      self.projection.weight, self.n_heads, self._sea_src_len, _rope_table(self), B)
+    return y.view(B, T, -1)
+
+
+def _masked_cross_forward(self, x_1, x_2):
+    y = _attn_call(self, x_1, x_2, causal=True)
+    return self._sea_eager_forward(x_1, x_2) if y is None else y
+
+
+def _plain_cross_forward(self, x_1, x_2):
+    y = _attn_call(self, x_1, x_2, causal=False)
+    return self._sea_eager_forward(x_1, x_2) if y is None else y
+
+
+# ------------------------------------------------------------------------------------------ norms
+class _NormFn(torch.autograd.Function):
+    """kind 0: F.layer_norm(x, weight) (base_blocks.py:80-88);  kind 1: AdaLN modulate (:345-350) with cond = [w | b]."""
+
+    @staticmethod
+    def forward(ctx, x2, weight, bias, cond, kind):
+        x2 = x2.contiguous()
+        c2 = None if cond is None else cond.contiguous()
+        y, _, st = ops.norm_fwd(x2, weight.detach(), bias=None if bias is None else bias.detach(), cond=c2, kind=kind,
+                                out_dtype=torch.float32, stats=True)
+        ctx.save_for_backward(x2, st, weight, c2 if c2 is not None else x2.new_empty(0))
+        ctx.kind = kind
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, st, weight, c2 = ctx.saved_tensors
+        kind = ctx.kind
+        dx, _, dw, db, dc = ops.norm_bwd(dy.contiguous(), x2, st, weight.detach(), cond=c2 if kind == 1 else None, kind=kind)
+        return dx, dw, db, dc, None
+
+
+def _layernorm_forward(self, x, cond=None):
+    shp = x.shape
+    y = _NormFn.apply(x.reshape(-1, shp[-1]), self.weight, None, None, 0)
+    return y.view(shp)
+
+
+def _adaln_forward(self, x, condition):
+    # cond_mlp = Linear(ib_num, 2d) -> SiLU -> Linear(2d, 2d) (:337-341): the first layer is K = ib_num (a scalar
+    # condition) and stays on torch; the 2d x 2d layer is a rebound nn.Linear (one GEMM)
+    cond = self.cond_mlp(condition)
+    d = x.shape[-1]
+    lead = torch.broadcast_shapes(x.shape[:-1], cond.shape[:-1])      # e.g. the pool token [B,1,d] against ib [B,T,1]
+    x = x.expand(*lead, d)
+    cond = cond.expand(*lead, 2 * d)
+    y = _NormFn.apply(x.reshape(-1, d), self.weight, self.bias, cond.reshape(-1, 2 * d), 1)
+    return y.view(*lead, d)
+
+
+# ------------------------------------------------------------------------------------------ MLP
+class _LnGeluFn(torch.autograd.Function):
+    """GELU_erf(nn.LayerNorm(H)(h)) — models/base_blocks.py:23-26 — one fused row kernel each way."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias):
+        hb = _to_bf16(h)
+        g, st = ops.ln_gelu_fwd_with_stats(hb, weight.detach(), bias.detach())
+        ctx.save_for_backward(hb, st, weight, bias)
+        return g
+
+    @staticmethod
+    def backward(ctx, dg):
+        hb, st, weight, bias = ctx.saved_tensors
+        dh, dw, db = ops.ln_gelu_bwd(_to_bf16(dg), hb, st, weight.detach(), bias.detach())
+        return dh.float(), dw, db
+
+
+def _mlp_ok(mod) -> bool:
+    ls = mod.layers
+    return (len(ls) == 4 and isinstance(ls[0], nn.Linear) and isinstance(ls[1], nn.LayerNorm) and isinstance(ls[2], nn.GELU)
+            and isinstance(ls[3], nn.Linear) and _linear_ok(ls[0]) and _linear_ok(ls[3]) and ls[1].weight.numel() % 8 == 0
+            and ls[1].weight.numel() <= 16384)
+
+
+def _mlp_forward(self, x):
+    shp = x.shape
+    ls = self.layers
+    h = _LinearFn.apply(x.reshape(-1, shp[-1]), ls[0].weight, ls[0].bias)
+    g = _LnGeluFn.apply(h, ls[1].weight, ls[1].bias)
+    y = _LinearFn.apply(g, ls[3].weight, ls[3].bias)
+    return self.dropout(y.view(*shp[:-1], y.shape[-1]))
+
+
+# ------------------------------------------------------------------------------------------ the walk
+def accelerate_modules(model: nn.Module) -> dict:
+    """Rebind ``forward`` on every supported leaf module of `model` (an UNCHANGED reference ``TemporalModel`` of any
+    exchange / ib mode, already on a CUDA device).  Returns {kind: count} of what was switched; modules not listed keep
+    the reference's eager code.  Idempotent."""
+    dev = next(model.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("sea_b200 has no CPU path: move the model to a CUDA device")
+    counts = {"linear": 0, "self_attention": 0, "masked_cross_attention": 0, "cross_attention": 0, "norm": 0, "adaln": 0,
+              "mlp": 0, "left_eager": 0}
+
+    def bind(mod, fn, kind):
+        if getattr(mod, "_sea_bound", False):
+            return
+        mod._sea_eager_forward = mod.forward
+        mod.forward = types.MethodType(fn, mod)
+        mod._sea_bound = True
+        counts[kind] += 1
+
+    for mod in model.modules():
+        name = type(mod).__name__
+        if name == "MaskedMultiHeadAttention":
+            bind(mod, _self_attn_forward, "self_attention") if _attn_ok(mod) else counts.__setitem__("left_eager", counts["left_eager"] + 1)
+        elif name == "MaskedMultiHeadCrossAttention":
+            bind(mod, _masked_cross_forward, "masked_cross_attention") if _attn_ok(mod) else counts.__setitem__("left_eager", counts["left_eager"] + 1)
+        elif name == "MultiHeadCrossAttention":
+            bind(mod, _plain_cross_forward, "cross_attention") if _attn_ok(mod) else counts.__setitem__("left_eager", counts["left_eager"] + 1)
+        elif name == "MLP":
+            bind(mod, _mlp_forward, "mlp") if _mlp_ok(mod) else counts.__setitem__("left_eager", counts["left_eager"] + 1)
+        elif name == "AdaLN" and mod.weight.numel() % 8 == 0 and mod.weight.numel() <= 2048:
+            bind(mod, _adaln_forward, "adaln")
+        elif name == "LayerNorm" and type(mod) is not nn.LayerNorm and getattr(mod, "bias", None) is None \
+                and mod.weight.numel() % 8 == 0 and mod.weight.numel() <= 2048:
+            bind(mod, _layernorm_forward, "norm")
+    # nn.Linear last: the q/k/v/projection of rebound attention modules and the layers of rebound MLPs are consumed by
+    # their owners' fused functions; every other Linear (cross_down / cross_up / proj / pool_update / cond_mlp[2] ...)
+    owned = set()
+    for mod in model.modules():
+        if getattr(mod, "_sea_bound", False):
+            tname = type(mod).__name__
+            if "Attention" in tname:
+                owned.update(id(l) for l in (mod.q, mod.k, mod.v, mod.projection))
+            elif tname == "MLP":
+                owned.update(id(l) for l in mod.layers if isinstance(l, nn.Linear))
+    for mod in model.modules():
+        if isinstance(mod, nn.Linear) and id(mod) not in owned and _linear_ok(mod):
+            bind(mod, _linear_forward, "linear")
+    model._sea_modules = counts
+    return counts

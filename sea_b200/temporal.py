@@ -710,10 +710,25 @@ class TemporalEngine:
 
 def accelerate(model: nn.Module, precision: str = "bf16") -> nn.Module:
     """Rebind ``forward`` of an UNCHANGED reference ``TemporalModel`` instance (or the mirror) to
-    the CUDA path.  Parameters are read in place; state_dict / optimizer objects keep working."""
-    _check_modes(getattr(model, "exchange_mode", "sea"), getattr(model, "ib_scale_mode", "mlp"),
-                 getattr(model, "ib_addition_mode", "add"),
-                 getattr(model.blocks[0], "add_info_after_cross", True), getattr(model, "LN_type", "ln"))
+    the CUDA path.  Parameters are read in place; state_dict / optimizer objects keep working.
+
+    The configuration both reference configs select (exchange_mode='sea', ib 'mlp' + 'add', add_info_after_cross) runs
+    through the fused whole-model executor.  Every other block / ib variant the reference ships (pool / addition / simple
+    exchange, fourier / linear ib layers, concat / attention / none addition: models/temporal.py:103-120, 197-312) keeps
+    the reference's own block orchestration and gets the module-level CUDA path (sea_b200.modules: GEMMs, fused
+    attention, norms and the MLP core as autograd Functions over the same kernels, bf16 mode)."""
+    try:
+        _check_modes(getattr(model, "exchange_mode", "sea"), getattr(model, "ib_scale_mode", "mlp"),
+                     getattr(model, "ib_addition_mode", "add"),
+                     getattr(model.blocks[0], "add_info_after_cross", True), getattr(model, "LN_type", "ln"))
+        if getattr(model.blocks[0], "ib_mlp_layers", 1) not in (None, 1):
+            raise NotImplementedError("ib_mlp_layers")
+    except NotImplementedError:
+        if precision != "bf16":
+            raise NotImplementedError("non-default exchange / ib modes are accelerated module by module in bf16 mode only")
+        from .modules import accelerate_modules
+        accelerate_modules(model)
+        return model
     drop = getattr(model.blocks[0], "dropout", 0.0)
     drop = float(getattr(drop, "p", drop))
     eng = TemporalEngine(model, precision=precision, dropout=drop)

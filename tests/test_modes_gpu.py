@@ -1,0 +1,83 @@
+"""Non-default block / ib variants of the reference (models/temporal.py:103-120, 197-312) through the module-level CUDA
+path (sea_b200.modules): the reference's own TemporalModel is built for every exchange_mode / ib mode, deep-copied, one
+copy accelerate()d, and forward, loss and every parameter gradient are compared with the eager fp32 copy on the same GPU."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref as oref
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not oref.available(), reason="reference not staged (oracle/_ref)")]
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ns():
+    return oref.load()
+
+
+CASES = [
+    # exchange, ib_scale, ib_add, after_cross, LN
+    ("addition", "mlp", "add", True, "adaln"),
+    ("addition", "mlp", "add", True, "ln"),
+    ("simple", "mlp", "add", True, "adaln"),
+    ("pool", "mlp", "add", True, "adaln"),
+    ("pool", "mlp", "add", True, "ln"),
+    ("sea", "fourier", "add", True, "adaln"),
+    ("sea", "linear", "add", True, "ln"),
+    ("sea", "mlp", "none", True, "adaln"),
+    ("sea", "mlp", "attention", True, "ln"),
+    ("sea", "mlp", "add", False, "adaln"),
+    ("sea", "mlp", "concat", False, "ln"),       # internal width E + 64: head dim not a multiple of 32 -> attention stays eager
+]
+
+
+@pytest.mark.parametrize("exchange,ib_scale,ib_add,after,ln", CASES)
+def test_non_default_modes_forward_and_gradients(cuda, ns, exchange, ib_scale, ib_add, after, ln):
+    from sea_b200.temporal import accelerate
+    torch.manual_seed(3)
+    E, nh, V, B, T = 512, 4, 2, 3, 40
+    kw = dict(num_layers=1, embed_dim=E, n_heads=nh, max_len=128, scale_ratio=4, src_len=0, num_variables=V, down_proj=2,
+              dropout=0.0, exchange_mode=exchange, pos_encoding_mode="learnable", ib_scale_mode=ib_scale,
+              ib_addition_mode=ib_add, ib_mlp_layers=1, ib_num=1, add_info_after_cross=after, LN_type=ln)
+    ref = ns.temporal.TemporalModel(**kw).to(cuda).train()
+    fast = copy.deepcopy(ref)
+    accelerate(fast, precision="bf16")
+    assert type(fast) is ns.temporal.TemporalModel
+    counts = getattr(fast, "_sea_modules", None)
+    assert counts is not None and counts["linear"] > 0 and counts["mlp"] == V, counts
+    if ib_add != "concat":
+        assert counts["self_attention"] == V
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(B, T, V, E, generator=g).to(cuda)
+    ib = torch.rand(B, 1, 1, generator=g).expand(B, T, 1).contiguous().to(cuda)
+    tgt = torch.randn(B, T, V, E, generator=g).to(cuda)
+    ya, yb = ref(x, ib), fast(x, ib)
+    la, lb = F.mse_loss(ya, tgt), F.mse_loss(yb, tgt)
+    la.backward()
+    lb.backward()
+    e_fwd = _rel(yb, ya)
+    worst, n = 0.0, 0
+    for (name, p), (_, q) in zip(ref.named_parameters(), fast.named_parameters()):
+        assert (p.grad is None) == (q.grad is None), name
+        if p.grad is None or p.grad.norm() < 1e-7 * max(1.0, p.numel() ** 0.5) or name.endswith(".k.bias"):
+            continue
+        cos = F.cosine_similarity(p.grad.flatten().double(), q.grad.flatten().double(), dim=0).item()
+        worst = max(worst, 1.0 - cos)
+        n += 1
+        assert cos > 0.99 and _rel(q.grad, p.grad) < 0.12, (name, cos, _rel(q.grad, p.grad))
+    print(f"\\n[modes] {exchange}/{ib_scale}/{ib_add}/after={after}/{ln}: forward rel {e_fwd:.2e}, loss {la.item():.5f} vs "
+          f"{lb.item():.5f}, worst 1-cos over {n} gradients {worst:.1e}; switched {counts}")
+    assert e_fwd < 2e-2 and abs(la.item() - lb.item()) / la.item() < 1e-2
+
+
+def test_default_mode_still_uses_the_fused_executor(cuda, ns):
+    from sea_b200.temporal import accelerate
+    m = ns.temporal.TemporalModel(1, 256, 2, 64, 4, 0, 2, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, "adaln").to(cuda)
+    accelerate(m)
+    assert hasattr(m, "_sea_engine") and not hasattr(m, "_sea_modules")

@@ -94,7 +94,10 @@ def test_accelerate_on_reference_instance_builds_descriptor_and_refuses_cpu(ns):
     with pytest.raises(RuntimeError, match="no CPU path"):
         with torch.no_grad():
             m(torch.zeros(1, 4, 2, 128), torch.zeros(1, 4, 1))
-    for bad in ("pool", "addition"):
-        mb = ns.temporal.TemporalModel(1, 128, 2, 64, 2, 0, 2, 2, 0.0, bad, "learnable", "mlp", "add", 1, 1, True, "ln")
+    # non-default exchange modes go to the module-level path (sea_b200.modules): bf16 only, and CUDA only
+    for other in ("pool", "addition"):
+        mb = ns.temporal.TemporalModel(1, 128, 2, 64, 2, 0, 2, 2, 0.0, other, "learnable", "mlp", "add", 1, 1, True, "ln")
         with pytest.raises(NotImplementedError):
+            accelerate(mb, precision="fp32")
+        with pytest.raises(RuntimeError, match="no CPU path"):
             accelerate(mb)
