@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import golden_recipe as gr
 from oracle import sea_oracle as so
 from tests.helpers import TEMPORAL_CASES, rel_l2, temporal_case
 
@@ -267,3 +268,32 @@ def test_long_kv_cached_rollout_crosses_tile_boundaries(cuda, ln):
     e_pref, e_kv = rel_l2(r_pref.cpu(), ref), rel_l2(r_kv.cpu(), ref)
     print(f"\n[long rollout] {ln}: prefix loop {e_pref:.3e}, cached {e_kv:.3e} vs oracle over {steps} steps")
     assert e_pref < 1e-4 and e_kv < 1e-4
+
+
+@pytest.mark.parametrize("ln", ["adaln", "ln"])
+def test_two_stream_schedule_is_bit_identical(cuda, ln):
+    """sea_temporal_desc.aux_stream: an exchanged stream's TIPI / MLP / proj tail on an auxiliary stream (fork / join events)
+    launches the same kernels on the same data — outputs must be bit-identical to the single-stream schedule, for the
+    forward, the graphed rollout and the KV-cached rollout."""
+    from sea_b200.rollout import rollout
+    from sea_b200.temporal import TemporalModel
+    E, nh, scale, V, B, T = 256, 2, 4, 2, 3, 37
+    shapes = gr.temporal_shapes(embed_dim=E, n_heads=nh, scale_ratio=scale, num_variables=V, ln_type=ln)
+    sd = gr.fill_state(shapes, 5)
+    x, ib, _ = gr.temporal_inputs(B, T, V, E, 5)
+    x, ib = x.to(cuda), ib.to(cuda)
+    outs = []
+    for two in (False, True):
+        m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln)
+        m.load_state_dict(sd, strict=False)
+        m = m.to(cuda).eval()
+        m.engine().two_streams = two
+        with torch.no_grad():
+            y = m(x, ib)
+            r = rollout(m, x[:, :1], ib, 12).clone()
+            rc = rollout(m, x[:, :1], ib, 12, cached=True).clone()
+        torch.cuda.synchronize()
+        assert (m.engine()._desc.aux_stream is not None) == two
+        outs.append((y, r, rc))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
