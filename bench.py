@@ -285,6 +285,52 @@ def train_dp_aux(dev, rank, world, timed_fn):
             "cases": out}
 
 
+def codec_aux(dev, pk):
+    """ViT-mesh patch encoder / decoder (models/encoder_decoder.py), north_star component: snapshots/s of the fp32
+    CUDA-core kernels (1e-4 parity mode) and of the tensor-core kernels (bf16 mma.sync, 2e-2 mode) at C = 64 cells per
+    patch, 8000 snapshots, both configs' codec sizes; algorithmic HBM bytes (4*P*F*C in + 4*P*G*D out) against
+    the measured HBM peak."""
+    from sea_b200.spatial import SpatialModel
+
+    def timed(fn, steps):      # rank-local (no collective: only rank 0 runs this auxiliary)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    out = {}
+    S_, C_ = 8000, 64
+    for cfg, D, Hs in (("cylinder_flow", 16, 480), ("multiphase_flow", 32, 624)):
+        row = {}
+        Es = 2 * D
+        enc_bytes = 4 * 64 * 3 * C_ + 4 * 64 * Es
+        enc_flops = 2 * 64 * (3 * C_) * Hs + 2 * 64 * Hs * D * 2 + 12 * (24 * 64 * Es * Es + 4 * 64 * 64 * Es)
+        for prec in ("fp32", "bf16"):
+            torch.manual_seed(42)
+            m = SpatialModel([[0, 1], [2]], C_, Hs, 12, D, 8, 2024, 0, 0.0, False, precision=prec).to(dev).eval()
+            x = torch.randn(S_, 64, 3, C_, device=dev)
+            with torch.no_grad():
+                z = m.encode(x)
+                m.decode(z)
+                ms_e = timed(lambda: m.encode(x), 5)
+                ms_d = timed(lambda: m.decode(z), 5)
+            row[prec] = {"encode_snapshots_per_s": S_ / (ms_e * 1e-3), "decode_snapshots_per_s": S_ / (ms_d * 1e-3),
+                         "encode_tflops": S_ * enc_flops / (ms_e * 1e-3) / 1e12,
+                         "encode_hbm_gbs_algorithmic": S_ * enc_bytes / (ms_e * 1e-3) / 1e9,
+                         "encode_frac_of_hbm_peak": S_ * enc_bytes / (ms_e * 1e-3) / 1e9 / pk["hbm"]}
+            del m, x, z
+        row["encode_speedup_tensor_core"] = row["bf16"]["encode_snapshots_per_s"] / row["fp32"]["encode_snapshots_per_s"]
+        row["decode_speedup_tensor_core"] = row["bf16"]["decode_snapshots_per_s"] / row["fp32"]["decode_snapshots_per_s"]
+        out[cfg] = row
+    out["workload"] = f"{S_} snapshots x 64 patches x 3 fields x {C_} cells, 12 encoder layers; compute-bound (the whole per-snapshot state stays in shared memory: DRAM traffic = the algorithmic bytes)"
+    torch.cuda.empty_cache()
+    return out
+
+
 def attention_kernel_aux(dev, timed, pk):
     """BASELINE metric, second half ("attention TFLOP/s vs peak"): the fused causal attention kernels
     alone at the configs' max_len (T = 2024), the three head geometries of the two configs, bf16,
@@ -464,6 +510,8 @@ def main():
         # ---- BASELINE configs[1], [2]: data-parallel train step with its collective ----
         aux["train_dp"] = train_dp_aux(dev, rank, world, timed)
         aux["attention_kernel"] = attention_kernel_aux(dev, timed, pk)
+        if rank == 0:
+            aux["codec"] = codec_aux(dev, pk)
 
     # ---- roofline leg: one more rollout with per-launch CUDA events on the launch stream ----
     with profile() as prof:
