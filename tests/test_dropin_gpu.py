@@ -95,6 +95,30 @@ def test_accelerated_reference_forward_and_rollout(cuda, ns, name, precision, ba
     assert e_fwd < bar and e_roll < bar
 
 
+@pytest.mark.parametrize("name", list(CASES))
+def test_bench_size_forward_against_the_reference_itself(cuda, ns, name):
+    """BASELINE's full size (32 trajectories, prefix length 100 = the last and heaviest step of the benchmark's rollout),
+    both configs at full width: the accelerated copy against the UNMODIFIED reference's eager fp32 forward on the same GPU —
+    fp32 mode within 1e-4, bf16 mode within 2e-2, and the two modes of the library within 2e-2 of each other."""
+    outs = {}
+    g = torch.Generator(device="cpu").manual_seed(21)
+    E = 1024 if name == "cylinder_flow" else 2048
+    x = torch.randn(32, 100, 2, E, generator=g).to(cuda)
+    ib = torch.rand(32, 1, 1, generator=g).expand(32, 100, 1).contiguous().to(cuda)
+    for precision in ("fp32", "bf16"):
+        _, (ref_m, _, _), (fast_m, _, _) = _pair(ns, name, cuda, precision)
+        ref_m.eval(), fast_m.eval()
+        with torch.no_grad():
+            if "ref" not in outs:
+                outs["ref"] = ref_m(x, ib)
+            outs[precision] = fast_m(x, ib)
+        del ref_m, fast_m
+        torch.cuda.empty_cache()
+    e32, e16 = _rel(outs["fp32"], outs["ref"]), _rel(outs["bf16"], outs["ref"])
+    print(f"\n[drop-in full size] {name} [32,100,2,{E}]: fp32 mode rel {e32:.2e}, bf16 mode rel {e16:.2e}")
+    assert e32 < 1e-4 and e16 < 2e-2 and _rel(outs["bf16"], outs["fp32"]) < 2e-2
+
+
 GRAD_BARS = {"bf16": dict(loss=2e-3, dx=2e-2, grad=4e-2, cos=0.999), "fp32": dict(loss=1e-5, dx=1e-4, grad=2e-4, cos=0.999999)}
 
 
