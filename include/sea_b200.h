@@ -432,6 +432,9 @@ void sea_attention_two_tiles(int on);
 /* tuning probe for the tensor-core backward (results are WRONG when non-zero): 1 = the compute warps only hand the
  * barriers over, 2 = they move S | dP through TMEM but skip the arithmetic; 0 = normal. */
 void sea_attention_bwd_probe(int mode);
+/* tuning hook: 1 (default) = 128-wide streamed tiles with a two-half hand-over of P | dS (head dims 64 / 128), 0 = the
+ * 64-wide double-buffered plan of the same kernel family; results are identical up to summation order. */
+void sea_attention_bwd_wide(int on);
 /* Tuning hook: non-NULL = the two-tile forward kernel (head_dim 128, no dropout) records clock64 probes of CTA (0,0,0)
  * into dev_buf (3 x 64 x 8 int64: softmax group 0 / 1 and the MMA warp, per key tile); NULL switches it off. */
 void sea_attention_debug_trace(void* dev_buf);

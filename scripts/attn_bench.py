@@ -11,6 +11,10 @@ import torch  # noqa: E402
 from sea_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda", 0)
+if os.environ.get("SEA_BWD_WIDE") is not None:      # A/B of the two backward plans
+    from sea_b200._lib import lib
+    lib.sea_attention_bwd_wide(int(os.environ["SEA_BWD_WIDE"]))
+    print(f"backward plan: {'128-wide, two-half hand-over' if int(os.environ['SEA_BWD_WIDE']) else '64-wide, double-buffered'}")
 pk = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
 sustained = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1396.0)))
 nh = 8

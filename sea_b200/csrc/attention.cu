@@ -22,8 +22,9 @@ namespace sea { extern int g_attn_two_tiles; void attention_set_trace(void*); }
 extern "C" void sea_attention_debug_trace(void* dev_buf) { sea::attention_set_trace(dev_buf); }
 extern "C" void sea_attention_force_simt(int on) { sea::g_force_simt = on; }
 extern "C" void sea_attention_two_tiles(int on) { sea::g_attn_two_tiles = on; }
-namespace sea { extern int g_attn_bwd_probe; }
+namespace sea { extern int g_attn_bwd_probe; extern int g_attn_bwd_wide; }
 extern "C" void sea_attention_bwd_probe(int mode) { sea::g_attn_bwd_probe = mode; }
+extern "C" void sea_attention_bwd_wide(int on) { sea::g_attn_bwd_wide = on; }
 
 extern "C" int sea_attention_fwd(const sea_attn_args* a, sea_stream_t stream) {
   return sea_attention_fwd_group(1, a, stream);
