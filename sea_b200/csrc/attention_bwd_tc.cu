@@ -389,6 +389,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
 template <int HD, int MODE>
 struct B2Cfg {
   static constexpr int BS = 128;
+  static constexpr int COMPUTE_WARPS = 16;            // four per TMEM lane quarter: a thread owns one row and 16 of a half's 64 columns
+  static constexpr int THREADS = 64 + 32 * COMPUTE_WARPS;
   static constexpr int ATOMS = HD / 64;
   static constexpr int STAT_BYTES = BR * HD * 2;
   static constexpr int STR_BYTES = BS * HD * 2;
@@ -399,7 +401,7 @@ struct B2Cfg {
 };
 
 template <int HD, int MODE, bool DROP>
-__global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc2_kernel(const __grid_constant__ AttnBwdTcParams p) {
+__global__ void __launch_bounds__((B2Cfg<HD, MODE>::THREADS), 1) attn_bwd_tc2_kernel(const __grid_constant__ AttnBwdTcParams p) {
   using C = B2Cfg<HD, MODE>;
   constexpr int BS = C::BS, STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc2_kernel(const __grid_
       ptx::mbar_init(&b_full[s], 1);
       ptx::mbar_init(&b_empty[s], 1);
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&p_half[s], 32 * kComputeWarps);
+      ptx::mbar_init(&p_half[s], 32 * C::COMPUTE_WARPS);
     }
     ptx::mbar_init(dp_full, 1);
     ptx::mbar_init(acc_done, 1);
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc2_kernel(const __grid_
         for (int kk = 0; kk < 4; ++kk) {
           const int k = hf * 4 + kk;
           const uint32_t acc = (it | k) != 0 ? 1u : 0u;
-          const uint32_t pk = (k >> 1) * 32 + (k & 1) * 8;   // 16 streamed columns = 8 packed TMEM columns per 32-column group
+          const uint32_t pk = k * 16;   // the 16 streamed columns of k-step k: 8 packed TMEM columns at the front of their own range
           if (MODE == 0) {
             ptx::umma_f16_ts(tmem + C::COL_ACC0, tmem + C::COL_DP + pk, ptx::umma_smem_desc(b1 + k * 2048, BS * 128, 1024),
                              idesc_acc, acc);
@@ -597,8 +599,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc2_kernel(const __grid_
     // ---------------------------------------------------------------- compute warps
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int chalf = (warp - 2) >> 2;   // which 32 of a half's 64 streamed columns this thread handles
-    const int tid = threadIdx.x - 64;    // 0..255
+    const int cq = (warp - 2) >> 2;      // which 16 of a half's 64 streamed columns this thread handles
+    const int tid = threadIdx.x - 64;    // 0..511
     const int rpos = r0 + row;           // query (MODE 0) or key (MODE 1) position of this thread
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const long long stat_base = (static_cast<long long>(b) * p.n_heads + h) * p.T;
@@ -615,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc2_kernel(const __grid_
         lse_s[tid] = q < p.T ? p.lse[stat_base + q] * kLog2e : 0.f;
         dl_s[tid] = q < p.T ? p.delta[stat_base + q] : 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
     }
     for (int it = 0; it < n_it; ++it) {
       const int c0 = (it0 + it) * BS;  // first streamed position (keys in MODE 0, queries in MODE 1)
@@ -640,13 +642,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc2_kernel(const __grid_
       ptx::tc_fence_after();
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const int cb = hf * 64 + chalf * 32;
-        uint32_t rs[32], rd[32];
-        ptx::tmem_ld_32x32p(sbuf + cb, rs);
-        ptx::tmem_ld_32x32p(dbuf + cb, rd);
+        const int cb = hf * 64 + cq * 16;
+        uint32_t rs[16], rd[16];
+        ptx::tmem_ld_32x16p(sbuf + cb, rs);
+        ptx::tmem_ld_32x16p(dbuf + cb, rd);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
+        for (int e = 0; e < 16; e += 2) {
           float pv[2], dv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -679,8 +681,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc2_kernel(const __grid_
           rd[e >> 1] = ptx::pack_bf16(dv[0], dv[1]);
         }
         // packed results over the front of the columns this thread has just read
-        if (MODE == 1) ptx::tmem_st_32x16p(sbuf + cb, rs);
-        ptx::tmem_st_32x16p(dbuf + cb, rd);
+        if (MODE == 1) ptx::tmem_st_32x8p(sbuf + cb, rs);
+        ptx::tmem_st_32x8p(dbuf + cb, rd);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&p_half[hf]);
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc2_kernel(const __grid_
           lse_s[((it + 1) & 1) * BS + tid] = nx_l;
           dl_s[((it + 1) & 1) * BS + tid] = nx_d;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
       }
     }
     // epilogue: accumulators -> (un-RoPE) -> bf16 rows
@@ -703,9 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc2_kernel(const __grid_
       const bool rot = p.rope != nullptr && (MODE == 0 || which == 1);
       __nv_bfloat16* out = (which == 0 ? p.out0 : p.out1) + orow * (which == 0 ? p.ld0 : p.ld1) + h * HD;
       const uint32_t col = which == 0 ? C::COL_ACC0 : C::COL_ACC1;
-#pragma unroll
-      for (int cc = 0; cc < HD / 64; ++cc) {
-        const int c = cc * 2 + chalf;     // the two compute warpgroups take alternate 32-column slabs
+      for (int c = cq; c < HD / 32; c += 4) {   // the four warps of a lane quarter take one 32-column slab each
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem + lane_base + col + c * 32, r);
         ptx::tmem_ld_wait();
@@ -857,7 +857,7 @@ int launch_mode2(const sea_attn_bwd_args* a, cudaStream_t s) {
   p.probe = g_attn_bwd_probe;
   const int tiles = (a->T + BR - 1) / BR;
   dim3 grid(a->n_heads * a->B, 1, tiles);
-  SEA_LAUNCH((attn_bwd_tc2_kernel<HD, MODE, DROP>), grid, kThreads, C::SMEM, s, p);
+  SEA_LAUNCH((attn_bwd_tc2_kernel<HD, MODE, DROP>), grid, C::THREADS, C::SMEM, s, p);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -230,6 +230,12 @@ __device__ __forceinline__ void tmem_st_32x16p(uint32_t taddr, const uint32_t* r
       "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x8p(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
 // 2^x on the SFU, flush-to-zero, no range fix-up (inputs here are <= 0 or -inf)
 __device__ __forceinline__ float ex2(float x) {
   float y;
