@@ -646,6 +646,16 @@ __global__ void __launch_bounds__((B2Cfg<HD, MODE>::THREADS), 1) attn_bwd_tc2_ke
         uint32_t rs[16], rd[16];
         ptx::tmem_ld_32x16p(sbuf + cb, rs);
         ptx::tmem_ld_32x16p(dbuf + cb, rd);
+        float l2v[16], dlv[16];
+        if (MODE == 1) {   // per-column statistics of the streamed queries: four 16-byte shared loads each
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(lrow + cb + e);
+            const float4 d4 = *reinterpret_cast<const float4*>(drow + cb + e);
+            l2v[e] = a4.x; l2v[e + 1] = a4.y; l2v[e + 2] = a4.z; l2v[e + 3] = a4.w;
+            dlv[e] = d4.x; dlv[e + 1] = d4.y; dlv[e + 2] = d4.z; dlv[e + 3] = d4.w;
+          }
+        }
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
@@ -655,7 +665,7 @@ __global__ void __launch_bounds__((B2Cfg<HD, MODE>::THREADS), 1) attn_bwd_tc2_ke
             const int cpos = c0 + cb + e + u;
             float l2, dl;
             if (MODE == 0) { l2 = my_lse2; dl = my_dl; }
-            else { l2 = lrow[cb + e + u]; dl = drow[cb + e + u]; }
+            else { l2 = l2v[e + u]; dl = dlv[e + u]; }
             float pe = ptx::ex2(fmaf(__uint_as_float(rs[e + u]), p.scale_log2, -l2));
             if (need_mask) {
               const int qq = MODE == 0 ? rpos : cpos;
@@ -675,7 +685,7 @@ __global__ void __launch_bounds__((B2Cfg<HD, MODE>::THREADS), 1) attn_bwd_tc2_ke
             } else {
               pv[u] = pe;
             }
-            dv[u] = pe * (dpv - dl) * p.scale;
+            dv[u] = pe * (dpv - dl);   // the softmax scale is applied once to dQ / dK in the epilogue
           }
           rs[e >> 1] = ptx::pack_bf16(pv[0], pv[1]);
           rd[e >> 1] = ptx::pack_bf16(dv[0], dv[1]);
@@ -710,8 +720,9 @@ __global__ void __launch_bounds__((B2Cfg<HD, MODE>::THREADS), 1) attn_bwd_tc2_ke
         ptx::tmem_ld_32x32(tmem + lane_base + col + c * 32, r);
         ptx::tmem_ld_wait();
         float v[32];
+        const float osc = (MODE == 0 || which == 1) ? p.scale : 1.0f;   // dS carried no scale: dQ, dK pick it up here
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) * osc;
         if (rot) {
           const float2* tab = reinterpret_cast<const float2*>(p.rope) + static_cast<long long>((c * 32) >> 1) * p.rope_ld + tpos;
 #pragma unroll
