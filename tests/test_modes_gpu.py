@@ -37,12 +37,19 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("exchange,ib_scale,ib_add,after,ln", CASES)
-def test_non_default_modes_forward_and_gradients(cuda, ns, exchange, ib_scale, ib_add, after, ln):
+WIDTHS = {"small": (512, 4, 4, 3, 40, 128), "cylinder_flow": (1024, 8, 8, 2, 399, 2024)}    # E, heads, scale_ratio, B, T, max_len
+
+
+@pytest.mark.parametrize("exchange,ib_scale,ib_add,after,ln,width",
+                         [c + ("small",) for c in CASES] + [("addition", "mlp", "add", True, "adaln", "cylinder_flow"),
+                                                            ("pool", "mlp", "add", True, "adaln", "cylinder_flow"),
+                                                            ("sea", "fourier", "add", True, "adaln", "cylinder_flow")])
+def test_non_default_modes_forward_and_gradients(cuda, ns, exchange, ib_scale, ib_add, after, ln, width):
     from sea_b200.temporal import accelerate
     torch.manual_seed(3)
-    E, nh, V, B, T = 512, 4, 2, 3, 40
-    kw = dict(num_layers=1, embed_dim=E, n_heads=nh, max_len=128, scale_ratio=4, src_len=0, num_variables=V, down_proj=2,
+    E, nh, sr, B, T, max_len = WIDTHS[width]
+    V = 2
+    kw = dict(num_layers=1, embed_dim=E, n_heads=nh, max_len=max_len, scale_ratio=sr, src_len=0, num_variables=V, down_proj=2,
               dropout=0.0, exchange_mode=exchange, pos_encoding_mode="learnable", ib_scale_mode=ib_scale,
               ib_addition_mode=ib_add, ib_mlp_layers=1, ib_num=1, add_info_after_cross=after, LN_type=ln)
     ref = ns.temporal.TemporalModel(**kw).to(cuda).train()
