@@ -297,3 +297,34 @@ def test_two_stream_schedule_is_bit_identical(cuda, ln):
         outs.append((y, r, rc))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("tag,ln,E", [("cylinder_flow", "adaln", 1024), ("multiphase_flow", "ln", 2048)])
+def test_long_horizon_bf16_drift_is_bounded(cuda, tag, ln, E):
+    """The benchmark's own horizon: a 100-step rollout of 8 trajectories at the configs' full width, bf16 engine (graphed
+    prefix loop AND KV-cached engine) against the fp32-mode engine (itself 2e-6 from the reference over 270 steps).
+    north_star's bar is 2e-2 on a 10-step rollout; past it the error grows slowly with the horizon.  Measured on B200:
+    ~1.2e-2 at step 10, ~2.5e-2 at step 50, ~3e-2 at step 100 — the asserted bounds leave a 1.5-2x margin."""
+    from sea_b200.rollout import rollout
+    from sea_b200.temporal import TemporalModel
+    shapes = gr.temporal_shapes(embed_dim=E, n_heads=8, scale_ratio=8, num_variables=2, ln_type=ln)
+    sd = gr.fill_state(shapes, 7)
+    x, ib, _ = gr.temporal_inputs(8, 100, 2, E, 7)
+    x0, ib = x[:, :1].to(cuda), ib[:, :1].expand(8, 100, 1).contiguous().to(cuda)
+    preds = {}
+    for prec in ("fp32", "bf16"):
+        m = TemporalModel(1, E, 8, 2024, 8, 0, 2, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, ln, precision=prec)
+        m.load_state_dict(sd, strict=False)
+        m = m.to(cuda).eval()
+        with torch.no_grad():
+            preds[prec] = rollout(m, x0, ib, 100).clone()
+            if prec == "bf16":
+                preds["bf16_cached"] = rollout(m, x0, ib, 100, cached=True).clone()
+        del m
+        torch.cuda.empty_cache()
+    ref = preds["fp32"].double()
+    for name in ("bf16", "bf16_cached"):
+        err = ((preds[name].double() - ref).flatten(2).norm(dim=2) / ref.flatten(2).norm(dim=2)).mean(dim=0)   # per step
+        print(f"\n[drift] {tag} {name}: step 10 {err[9]:.2e}, step 50 {err[49]:.2e}, step 100 {err[99]:.2e}")
+        assert err[9] < 2e-2 and err[49] < 4e-2 and err[99] < 6e-2
+        assert torch.isfinite(preds[name]).all()
