@@ -597,11 +597,14 @@ class TemporalEngine:
         self._ensure(training)
         B, T, V, E = x.shape
         x = x.contiguous().float()
+        auto_key = None
+        inv = bool(self.ib_time_invariant) and not training
+        if not inv and not training and self.auto_time_invariant and T > 1:
+            inv, auto_key = self._auto_invariant(ib, B)
         ib = ib.contiguous().float()
         y = torch.empty_like(x)
         if ws is None:
             ws = self.workspace(B, T, training)
-        inv = bool(self.ib_time_invariant) and not training
         self._desc.ib_time_invariant = int(inv)
         # train-mode nn.Dropout (attention probabilities, MLP and TIPI outputs): counter-based masks keyed by
         # a seed drawn from torch's CPU generator (torch.manual_seed makes runs repeatable); the backward of
@@ -613,9 +616,9 @@ class TemporalEngine:
             self.last_dropout_seed = 0
         self._desc.dropout_seed = self.last_dropout_seed
         self._desc.cond_cache, self._desc.cond_cache_bytes, self._desc.cond_cache_valid = None, 0, 0
-        use_cc = inv and self.cond_reuse and T > 1
+        use_cc = inv and (self.cond_reuse or auto_key is not None) and T > 1
         if use_cc:
-            key = (B, self._cache_key)
+            key = (B, self._cache_key, auto_key)
             if self._cond_key != key or self._cond_buf is None:
                 n = lib.sea_temporal_cond_cache_bytes(C.byref(self._desc), B)
                 self._cond_buf = torch.empty(n, dtype=torch.uint8, device=self._dev)
@@ -635,6 +638,25 @@ class TemporalEngine:
         self.last_launches = lib.sea_last_launch_count()
         self.total_launches += self.last_launches
         return y
+
+    # The reference's rollout loops (utils/train_utils.py:171-175, 203-207) call model(seq, ib[:, :i+1]) with growing views of
+    # ONE condition tensor.  The BASE tensor is tested once for time-invariance (one device sync per distinct tensor /
+    # version); every later call on a view of it then takes the per-trajectory condition path and reuses the cached AdaLN /
+    # TIPI condition rows, which depend on ib and the weights only — what rollout() is told explicitly.
+    auto_time_invariant = os.environ.get("SEA_AUTO_INVARIANT", "1") != "0"
+
+    def _auto_invariant(self, ib: torch.Tensor, B: int):
+        base = ib._base if ib._base is not None else ib
+        if base.dim() != 3 or not base.is_cuda or ib.dim() != 3:
+            return False, None
+        key = (base.data_ptr(), base._version, tuple(base.shape), tuple(base.stride()))
+        if getattr(self, "_ib_auto_key", None) != key:
+            self._ib_auto = bool((base == base[:, :1]).all().item())
+            self._ib_auto_key = key
+        if not self._ib_auto:
+            return False, None
+        # the cached condition rows belong to THESE trajectories: same view origin, same batch
+        return True, (key, ib.data_ptr(), B)
 
     @torch.no_grad()
     def forward_into(self, x: torch.Tensor, ib: torch.Tensor, y: torch.Tensor, ws: torch.Tensor, *,

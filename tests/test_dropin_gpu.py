@@ -365,3 +365,36 @@ def test_accelerated_reference_spatial_model(cuda, ns, name, precision, bar):
     print(f"\n[drop-in spatial] {name} {precision}: forward rel {_rel(yb, ya):.2e}, encode {_rel(zb, za):.2e}, "
           f"decode {_rel(db, da):.2e}")
     assert _rel(yb, ya) < bar and _rel(zb, za) < bar and _rel(db, da) < bar
+
+
+def test_eager_loop_condition_detection(cuda, ns):
+    """The unchanged loop model(seq, ib[:, :i+1]) through the drop-in forward: the engine tests the BASE condition tensor once
+    for time-invariance and then takes the per-trajectory condition path with cached condition rows.  It must (i) agree with
+    the eager reference for a time-invariant ib, (ii) NOT take that path for a time-varying ib, (iii) notice an in-place
+    update of ib (version counter) and a different batch slice of the same base tensor."""
+    _, (ref_m, _, _), (fast_m, _, _) = _pair(ns, "cylinder_flow", cuda, "fp32")
+    ref_m.eval(), fast_m.eval()
+    eng = fast_m._sea_engine
+    g = torch.Generator(device="cpu").manual_seed(17)
+    B, steps = 6, 7
+    x0 = torch.randn(B, 1, 2, 1024, generator=g).to(cuda)
+
+    def loop(m, x0_, ib_):
+        seq = x0_
+        with torch.no_grad():
+            for i in range(steps):     # utils/train_utils.py:203-207
+                out = m(seq, ib_[:, : i + 1])
+                seq = torch.cat((seq, out[:, -1:]), dim=1)
+        return seq[:, 1:]
+
+    ib_inv = torch.rand(B, 1, 1, generator=g).expand(B, steps, 1).contiguous().to(cuda)
+    assert _rel(loop(fast_m, x0, ib_inv), loop(ref_m, x0, ib_inv)) < 1e-4
+    assert eng._ib_auto is True
+    ib_inv.mul_(0.5)                                       # in place: same storage, new version
+    assert _rel(loop(fast_m, x0, ib_inv), loop(ref_m, x0, ib_inv)) < 1e-4
+    # a batch slice of the same base tensor: other trajectories, other condition rows
+    assert _rel(loop(fast_m, x0[2:5], ib_inv[2:5]), loop(ref_m, x0[2:5], ib_inv[2:5])) < 1e-4
+    assert _rel(loop(fast_m, x0[:3], ib_inv[:3]), loop(ref_m, x0[:3], ib_inv[:3])) < 1e-4
+    ib_var = torch.rand(B, steps, 1, generator=g).to(cuda)
+    assert _rel(loop(fast_m, x0, ib_var), loop(ref_m, x0, ib_var)) < 1e-4
+    assert eng._ib_auto is False
