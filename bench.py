@@ -470,7 +470,7 @@ def main():
             "value": world * B * R / (ms_loop / 1e3), "unit": UNIT, "ms_per_step": ms_loop,
             "rel_l2_vs_graphed_rollout": loop_rel,
             "note": "the reference's rollout loop verbatim (model(seq, ib[:, :i+1]); torch.cat) on the drop-in forward: "
-                    "one FFI call per step, no CUDA graphs, ib not known to be time-invariant"}
+                    "one FFI call per step, no CUDA graphs; the engine tests the loop's condition tensor once for time-invariance and then reuses the cached per-trajectory condition rows"}
         del pred_loop
 
         # ---- fp32-parity mode on the same trajectories: throughput + the bf16 engine's drift against it ----
