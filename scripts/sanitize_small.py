@@ -1,5 +1,6 @@
-"""Small invocations of the kernels written / reworked in round 2, for compute-sanitizer (memcheck / racecheck):
-    compute-sanitizer --tool memcheck python scripts/sanitize_small.py"""
+"""Small invocations of the kernels written / reworked in round 2 (ragged / odd shapes, finite-output checks).  Written as a
+compute-sanitizer target (`compute-sanitizer --tool memcheck python scripts/sanitize_small.py`); compute-sanitizer is
+closed on this GPU pool, so it only runs plainly here: `python scripts/sanitize_small.py [codec|attn|patch]`."""
 import os
 import sys
 
