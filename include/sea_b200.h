@@ -545,7 +545,9 @@ typedef struct sea_temporal_desc {
                               instead of accumulating, which saves zero-filling and re-reading 4 B/parameter.
                               Every other gradient (biases, norm / TIPI / cond_mlp.0 parameters) still
                               accumulates and must have been zeroed by the caller.  0 = accumulate everywhere. */
-  int32_t reserved1;
+  int32_t splitk_slot;     /* 0..3: which of the cache's four stream-K workspaces this call's GEMMs use.  Calls that may
+                              run concurrently on different streams (the micro-batches of a rollout plan) must use
+                              different slots; the two-stream schedule's auxiliary stream takes (slot + 2) % 4. */
   /* ---- data-parallel training (sea_temporal_backward only; all optional, zero = off) ----
    * Every `g` of this descriptor points into ONE flat fp32 buffer starting at grad_f32_base (the all-reduce
    * bucket).  With grad_bf16 set, each weight-gradient GEMM also stores the bf16 rounding of the value it leaves

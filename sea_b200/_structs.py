@@ -48,7 +48,7 @@ class TemporalDesc(C.Structure):
                 ("final_ln", NormParams * MAX_STREAMS),
                 ("rope_self", C.c_void_p), ("rope_cross", C.c_void_p),
                 ("dropout_p", C.c_float), ("reserved2", C.c_uint32), ("dropout_seed", C.c_uint64),
-                ("grads_fresh", C.c_int32), ("reserved1", C.c_int32),
+                ("grads_fresh", C.c_int32), ("splitk_slot", C.c_int32),
                 ("grad_f32_base", C.c_void_p), ("grad_bf16", C.c_void_p), ("bwd_events", C.c_void_p * BWD_GROUPS),
                 ("aux_stream", C.c_void_p), ("fork_events", C.c_void_p * MAX_STREAMS), ("join_event", C.c_void_p)]
 

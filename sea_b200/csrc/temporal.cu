@@ -94,8 +94,7 @@ void layout_cache(const sea_temporal_desc* d, bool training, Arena& ar, CacheLay
     if (ada) c.c2_final[i] = take_linear(ar, 2 * E, 2 * E, kf, training);
   // stream-K workspace of the GEMM launches (arrival counters + parked partial tiles), see sea_gemm_set_workspace
   c.splitk_bytes = kSplitKBytes;
-  c.splitk = ar.take(c.splitk_bytes);
-  c.splitk_aux = ar.take(c.splitk_bytes);
+  for (int k = 0; k < 4; ++k) c.splitk[k] = ar.take(c.splitk_bytes);
 }
 
 static int pack_weight(const float* src, int N, int K, const PackedLinear& dst, int row_off,
@@ -220,8 +219,7 @@ extern "C" int sea_temporal_refresh_ex(const sea_temporal_desc* d, void* cache, 
   layout_cache(d, training != 0, ar, c);
   const bool fp32 = d->precision == SEA_PREC_FP32;
   const int E = d->embed_dim, Dd = d->down_dim, V = d->num_streams;
-  SEA_CUDA_OK(cudaMemsetAsync(c.splitk, 0, 65536, s));   // stream-K arrival counters start at zero
-  SEA_CUDA_OK(cudaMemsetAsync(c.splitk_aux, 0, 65536, s));
+  for (int k = 0; k < 4; ++k) SEA_CUDA_OK(cudaMemsetAsync(c.splitk[k], 0, 65536, s));   // stream-K arrival counters start at zero
   SEA_TRY(for_each_weight(d, c, [&](const float* src, int N, int K, const PackedLinear& dst, int row_off, int n_total) {
     return pack_weight(src, N, K, dst, row_off, n_total, fp32, what, s);
   }));
@@ -620,7 +618,8 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
   Arena war{static_cast<char*>(workspace)};
   Tape tape;
   layout_tape(d, B, T, training != 0, war, tape);
-  SEA_TRY(sea_gemm_set_workspace(cl.splitk, cl.splitk_bytes));
+  if (d->splitk_slot < 0 || d->splitk_slot > 3) return SEA_ERR_INVALID;
+  SEA_TRY(sea_gemm_set_workspace(cl.splitk[d->splitk_slot], cl.splitk_bytes));
 
   Ctx c{};
   c.d = d; c.cache = &cl; c.tape = &tape;
@@ -647,10 +646,10 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
   // events (desc->aux_stream, fork_events, join_event); the auxiliary GEMMs get their own stream-K workspace.
   bool fork = d->aux_stream != nullptr && d->join_event != nullptr && training == 0 && !c.fp32 && V >= 2 && !g_prof_on;
   for (int i = 0; fork && i < V - 1; ++i) fork = d->fork_events[i] != nullptr;
-  c.splitk = cl.splitk;
+  c.splitk = cl.splitk[d->splitk_slot];
   Ctx caux = c;
   caux.s = reinterpret_cast<cudaStream_t>(d->aux_stream);
-  caux.splitk = cl.splitk_aux;
+  caux.splitk = cl.splitk[(d->splitk_slot + 2) & 3];
 
   // ---- everything that depends on ib only: TIPI hidden + all AdaLN conditions (hoisted) ----
   // With a time-invariant condition the results live in the caller's persistent cond cache and

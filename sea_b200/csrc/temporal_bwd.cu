@@ -413,7 +413,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
   Arena car{const_cast<char*>(static_cast<const char*>(cache))};
   CacheLayout cl;
   layout_cache(d, true, car, cl);
-  SEA_TRY(sea_gemm_set_workspace(cl.splitk, cl.splitk_bytes));
+  SEA_TRY(sea_gemm_set_workspace(cl.splitk[0], cl.splitk_bytes));
   Arena war{static_cast<char*>(workspace)};
   Tape tape;
   layout_tape(d, B, T, true, war, tape);

@@ -41,8 +41,9 @@ constexpr size_t kSplitKBytes = 65536 + 148ull * 2 * 128 * 256 * 4;  // counters
 struct CacheLayout {
   std::vector<BlockCache> blocks;
   PackedLinear c2_final[SEA_MAX_STREAMS];
-  void* splitk;         // stream-K workspace (sea_gemm_set_workspace)
-  void* splitk_aux;     // a second one for GEMMs enqueued on the auxiliary stream (desc->aux_stream)
+  // stream-K workspaces (sea_gemm_set_workspace): GEMMs that may run CONCURRENTLY — the micro-batches of a rollout
+  // plan on their own streams (desc->splitk_slot), the auxiliary stream of the two-stream schedule — need their own
+  void* splitk[4];
   size_t splitk_bytes;
 };
 

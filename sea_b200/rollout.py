@@ -32,6 +32,21 @@ def _plan_key(eng):
             None if rope is None else (rope[0].data_ptr(), rope[1].data_ptr()))
 
 
+def _split_ranges(B: int, splits: int):
+    """[(b0, b1)] of at most 4 (the cache holds four stream-K workspaces) near-equal groups of trajectories."""
+    splits = max(1, min(int(splits), 4, B))
+    base, rem = divmod(B, splits)
+    out, b0 = [], 0
+    for k in range(splits):
+        b1 = b0 + base + (1 if k < rem else 0)
+        out.append((b0, b1))
+        b0 = b1
+    return out
+
+
+DEFAULT_SPLITS = int(__import__("os").environ.get("SEA_ROLLOUT_SPLITS", "1"))
+
+
 class RolloutPlan:
     """The same loop with every step pre-recorded as a CUDA graph.
 
@@ -43,24 +58,32 @@ class RolloutPlan:
     prefixes.  Arithmetic, kernels and per-step work are exactly those of the eager loop (the full
     prefix is still recomputed every step); requires a time-invariant ib (checked by the caller)."""
 
-    def __init__(self, model, B: int, steps: int, device):
+    def __init__(self, model, B: int, steps: int, device, splits: int = 1):
         eng = _engine_of(model)
         if eng is None:
             raise RuntimeError("RolloutPlan needs a sea_b200 temporal engine (mirror model or accelerate())")
         self.eng, self.B, self.steps = eng, B, steps
+        # micro-batches: the B trajectories are independent, and at short prefixes a step is a chain of ~22 small,
+        # latency-bound launches that leaves most SMs idle.  `splits` groups of trajectories run the same chain on their
+        # own streams inside one graph, so one group's launch / drain latencies are filled with another group's work
+        # (same kernels per trajectory: results are bit-identical to the single-batch plan).
+        self.subs = _split_ranges(B, splits)
         eng._ensure(False)
         h = eng._h
         V, E, nib = h["V"], h["E"], h["ib_num"]
         self.V, self.E = V, E
         f32 = dict(dtype=torch.float32, device=device)
         self.seq = torch.zeros(B, steps + 1, V, E, **f32)
-        self.y = torch.empty(B * steps * V * E, **f32)
         self.ib1 = torch.zeros(B, 1, nib, **f32)      # step 1 reads ib as [B,1,nib]
         self.ib2 = torch.zeros(B, 2, nib, **f32)      # step 2 (first time-invariant call) as [B,2,nib]
-        nws = lib.sea_temporal_workspace_bytes(C.byref(eng._desc), B, steps, 0)
-        self.ws = torch.empty(nws, dtype=torch.uint8, device=device)
-        ncc = lib.sea_temporal_cond_cache_bytes(C.byref(eng._desc), B)
-        self.cond = torch.empty(ncc, dtype=torch.uint8, device=device)
+        self.ws, self.cond, self.ys = [], [], []
+        for b0, b1 in self.subs:
+            nws = lib.sea_temporal_workspace_bytes(C.byref(eng._desc), b1 - b0, steps, 0)
+            self.ws.append(torch.empty(nws, dtype=torch.uint8, device=device))
+            ncc = lib.sea_temporal_cond_cache_bytes(C.byref(eng._desc), b1 - b0)
+            self.cond.append(torch.empty(ncc, dtype=torch.uint8, device=device))
+            self.ys.append(torch.empty((b1 - b0) * steps * V * E, **f32))
+        self.streams = [torch.cuda.Stream(device=device) for _ in self.subs[1:]]
         self.graphs, self.launches = [], []
         # the graphs bake in device pointers: packed-weight cache, parameters (biases, norm weights), RoPE tables
         self.key = _plan_key(eng)
@@ -68,13 +91,23 @@ class RolloutPlan:
         self._record()
 
     def _step(self, t: int) -> int:
-        B, V, E = self.B, self.V, self.E
-        y = self.y[: B * t * V * E].view(B, t, V, E)
+        V, E = self.V, self.E
         ib = self.ib1 if t == 1 else self.ib2   # only read while the condition cache is not valid (t <= 2)
-        # the model reads the prefix in place from the sequence buffer (batch-strided view, no gather)
-        n = self.eng.forward_into(self.seq[:, :t], ib, y, self.ws, time_invariant=True, cond_buf=self.cond,
-                                  cond_valid=t > 2)
-        self.seq[:, t].copy_(y[:, t - 1])
+        cur = torch.cuda.current_stream()
+        for st in self.streams:                  # fork: the other micro-batches start where this step starts
+            st.wait_stream(cur)
+        n = 0
+        for k, (b0, b1) in enumerate(self.subs):
+            with torch.cuda.stream(cur if k == 0 else self.streams[k - 1]):
+                y = self.ys[k][: (b1 - b0) * t * V * E].view(b1 - b0, t, V, E)
+                self.eng._desc.splitk_slot = k
+                # the model reads the prefix in place from the sequence buffer (batch-strided view, no gather)
+                n += self.eng.forward_into(self.seq[b0:b1, :t], ib[b0:b1], y, self.ws[k], time_invariant=True,
+                                           cond_buf=self.cond[k], cond_valid=t > 2)
+                self.seq[b0:b1, t].copy_(y[:, t - 1])
+        self.eng._desc.splitk_slot = 0
+        for st in self.streams:                  # join
+            cur.wait_stream(st)
         return n
 
     def _record(self):
@@ -91,7 +124,7 @@ class RolloutPlan:
                 n = self._step(t)
             pool = g.pool()
             self.graphs.append(g)
-            self.launches.append(n + 1)
+            self.launches.append(n + len(self.subs))
         torch.cuda.current_stream().wait_stream(side)
 
     def valid_for(self, eng) -> bool:
@@ -122,11 +155,12 @@ class CachedRolloutPlan:
     x_t from and writes y_t into one [B, steps+1, V, E] sequence buffer, so a step has no copy kernels.
     Works for time-invariant and time-varying ib."""
 
-    def __init__(self, model, B: int, steps: int, device, time_invariant: bool):
+    def __init__(self, model, B: int, steps: int, device, time_invariant: bool, splits: int = 1):
         eng = _engine_of(model)
         if eng is None:
             raise RuntimeError("CachedRolloutPlan needs a sea_b200 temporal engine")
         self.eng, self.B, self.steps, self.inv = eng, B, steps, bool(time_invariant)
+        self.subs = _split_ranges(B, splits)     # micro-batches on their own streams (see RolloutPlan)
         eng._ensure(False)
         h = eng._h
         if h["src_len"] != 0:
@@ -137,9 +171,11 @@ class CachedRolloutPlan:
         self.seq = torch.zeros(B, steps + 1, V, E, **f32)
         self.ib = torch.zeros(B, steps, nib, **f32)
         d = C.byref(eng._desc)
-        self.kv = torch.empty(lib.sea_temporal_kv_cache_bytes(d, B, steps), dtype=torch.uint8, device=device)
-        self.ws = torch.empty(lib.sea_temporal_workspace_bytes(d, B, 1, 0), dtype=torch.uint8, device=device)
-        self.cond = torch.empty(lib.sea_temporal_cond_cache_bytes(d, B), dtype=torch.uint8, device=device)
+        u8 = dict(dtype=torch.uint8, device=device)
+        self.kv = [torch.empty(lib.sea_temporal_kv_cache_bytes(d, b1 - b0, steps), **u8) for b0, b1 in self.subs]
+        self.ws = [torch.empty(lib.sea_temporal_workspace_bytes(d, b1 - b0, 1, 0), **u8) for b0, b1 in self.subs]
+        self.cond = [torch.empty(lib.sea_temporal_cond_cache_bytes(d, b1 - b0), **u8) for b0, b1 in self.subs]
+        self.streams = [torch.cuda.Stream(device=device) for _ in self.subs[1:]]
         self.graphs, self.launches = [], []
         # the graphs bake in device pointers: packed-weight cache, parameters (biases, norm weights), RoPE tables
         self.key = _plan_key(eng)
@@ -147,8 +183,20 @@ class CachedRolloutPlan:
         self._record()
 
     def _step(self, t: int) -> int:
-        return self.eng.step_into(self.seq[:, t], self.ib[:, t], self.seq[:, t + 1], t, self.kv, self.steps,
-                                  self.ws, time_invariant=self.inv, cond_buf=self.cond, cond_valid=t > 0)
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            st.wait_stream(cur)
+        n = 0
+        for k, (b0, b1) in enumerate(self.subs):
+            with torch.cuda.stream(cur if k == 0 else self.streams[k - 1]):
+                self.eng._desc.splitk_slot = k
+                n += self.eng.step_into(self.seq[b0:b1, t], self.ib[b0:b1, t], self.seq[b0:b1, t + 1], t, self.kv[k],
+                                        self.steps, self.ws[k], time_invariant=self.inv, cond_buf=self.cond[k],
+                                        cond_valid=t > 0)
+        self.eng._desc.splitk_slot = 0
+        for st in self.streams:
+            cur.wait_stream(st)
+        return n
 
     def _record(self):
         for t in range(self.steps):      # eager pass: launch attributes are set outside any capture
@@ -188,7 +236,7 @@ def _profiling() -> bool:
 @torch.no_grad()
 def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
             ib_time_invariant: bool | None = None, graphs: bool = True, cached: bool = False,
-            _view_ok: bool = False) -> torch.Tensor:
+            _view_ok: bool = False, splits: int | None = None) -> torch.Tensor:
     """x0 [B,1,V,E], ib [B,>=steps,ib_num] -> predicted latents [B,steps,V,E].
 
     ``ib`` is the time-invariant physical parameter of a trajectory in the reference's data
@@ -207,23 +255,25 @@ def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
             raise RuntimeError("cached rollout needs a sea_b200 temporal engine on a CUDA device")
         eng._ensure(False)
         plans = eng.__dict__.setdefault("_cached_plans", {})
-        key = (x0.shape[0], steps, x0.device.index, bool(ib_time_invariant))
+        nsplit = DEFAULT_SPLITS if splits is None else int(splits)
+        key = (x0.shape[0], steps, x0.device.index, bool(ib_time_invariant), nsplit)
         plan = plans.get(key)
         if plan is None or not plan.valid_for(eng):
             if len(plans) >= 4:
                 plans.clear()
-            plan = plans[key] = CachedRolloutPlan(model, x0.shape[0], steps, x0.device, bool(ib_time_invariant))
+            plan = plans[key] = CachedRolloutPlan(model, x0.shape[0], steps, x0.device, bool(ib_time_invariant), nsplit)
         out = plan.run(x0, ib)
         return out if _view_ok else out.clone()
     if graphs and eng is not None and ib_time_invariant and x0.is_cuda and not _profiling():
         eng._ensure(False)
         plans = eng.__dict__.setdefault("_rollout_plans", {})
-        key = (x0.shape[0], steps, x0.device.index)
+        nsplit = DEFAULT_SPLITS if splits is None else int(splits)
+        key = (x0.shape[0], steps, x0.device.index, nsplit)
         plan = plans.get(key)
         if plan is None or not plan.valid_for(eng):
             if len(plans) >= 4:
                 plans.clear()
-            plan = plans[key] = RolloutPlan(model, x0.shape[0], steps, x0.device)
+            plan = plans[key] = RolloutPlan(model, x0.shape[0], steps, x0.device, nsplit)
         out = plan.run(x0, ib)
         return out if _view_ok else out.clone()   # the plan's buffer is overwritten by the next run
     prev = None
