@@ -328,3 +328,27 @@ def test_long_horizon_bf16_drift_is_bounded(cuda, tag, ln, E):
         print(f"\n[drift] {tag} {name}: step 10 {err[9]:.2e}, step 50 {err[49]:.2e}, step 100 {err[99]:.2e}")
         assert err[9] < 2e-2 and err[49] < 4e-2 and err[99] < 6e-2
         assert torch.isfinite(preds[name]).all()
+
+
+def test_micro_batched_rollout_plans_match_single_batch(cuda):
+    """rollout(..., splits=k): groups of trajectories on their own streams inside one graph per step (opt-in).  Every
+    trajectory goes through the same kernels; only the GEMM tiling (rows per launch) differs, so fp32 mode agrees to
+    rounding and the KV-cached engine (one row tile either way) bit for bit."""
+    from sea_b200.rollout import rollout
+    from sea_b200.temporal import TemporalModel
+    E, nh, scale, V, B = 256, 2, 4, 2, 7
+    shapes = gr.temporal_shapes(embed_dim=E, n_heads=nh, scale_ratio=scale, num_variables=V, ln_type="adaln")
+    sd = gr.fill_state(shapes, 9)
+    x, ib, _ = gr.temporal_inputs(B, 16, V, E, 9)
+    x0, ib = x[:, :1].to(cuda), ib[:, :1].expand(B, 16, 1).contiguous().to(cuda)
+    m = TemporalModel(1, E, nh, 64, scale, 0, V, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, "adaln", precision="fp32")
+    m.load_state_dict(sd, strict=False)
+    m = m.to(cuda).eval()
+    with torch.no_grad():
+        ref = rollout(m, x0, ib, 14).clone()
+        ref_c = rollout(m, x0, ib, 14, cached=True).clone()
+        for splits in (2, 3, 4):
+            out = rollout(m, x0, ib, 14, splits=splits).clone()
+            out_c = rollout(m, x0, ib, 14, cached=True, splits=splits).clone()
+            assert rel_l2(out.cpu(), ref.cpu()) < 1e-5, splits
+            assert rel_l2(out_c.cpu(), ref_c.cpu()) < 1e-5, splits
