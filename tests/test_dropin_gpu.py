@@ -105,17 +105,32 @@ def test_bench_size_forward_against_the_reference_itself(cuda, ns, name):
     E = 1024 if name == "cylinder_flow" else 2048
     x = torch.randn(32, 100, 2, E, generator=g).to(cuda)
     ib = torch.rand(32, 1, 1, generator=g).expand(32, 100, 1).contiguous().to(cuda)
+    def ms_of(fn):      # informational only (printed, never asserted): same GPU, same inputs, CUDA events
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 3
+
+    ms = {}
     for precision in ("fp32", "bf16"):
         _, (ref_m, _, _), (fast_m, _, _) = _pair(ns, name, cuda, precision)
         ref_m.eval(), fast_m.eval()
         with torch.no_grad():
             if "ref" not in outs:
                 outs["ref"] = ref_m(x, ib)
+                ms["ref"] = ms_of(lambda: ref_m(x, ib))
             outs[precision] = fast_m(x, ib)
+            ms[precision] = ms_of(lambda: fast_m(x, ib))
         del ref_m, fast_m
         torch.cuda.empty_cache()
     e32, e16 = _rel(outs["fp32"], outs["ref"]), _rel(outs["bf16"], outs["ref"])
-    print(f"\n[drop-in full size] {name} [32,100,2,{E}]: fp32 mode rel {e32:.2e}, bf16 mode rel {e16:.2e}")
+    print(f"\n[drop-in full size] {name} [32,100,2,{E}]: fp32 mode rel {e32:.2e}, bf16 mode rel {e16:.2e}; one forward: "
+          f"reference eager fp32 on this GPU {ms['ref']:.2f} ms, accelerated fp32 mode {ms['fp32']:.2f} ms, bf16 mode {ms['bf16']:.2f} ms")
     assert e32 < 1e-4 and e16 < 2e-2 and _rel(outs["bf16"], outs["fp32"]) < 2e-2
 
 
