@@ -127,34 +127,6 @@ int sea_gemm_bf16_tn(int num_problems, const sea_gemm_problem* host_problems, in
  * mode: the tensor core's own accumulator does not round to nearest, so long K chains drift. */
 int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem* host_problems, int M, int N,
                              int K, int k_chunk, sea_stream_t stream);
-/* Small-M variant (M <= 32 rows: the KV-cached rollout step, one new token per trajectory) with an optional fused row
- * norm in front: C = op(A) B^T with the same epilogue.  A is either bf16 rows (a_bf16) or fp32 rows x normalised on the
- * fly: SEA_NORM_LN = F.layer_norm(x, weight) (models/base_blocks.py:87-88), SEA_NORM_ADALN = (x - mean) * rstd * gamma_m +
- * beta_m with the FOLDED per-row gamma | beta of sea_adaln_fold (cond row m, [2K]); optional add_rows[m] is added to x
- * first and the sum written to x_out (the TIPI add of models/temporal.py:140-142).  Warp-level bf16 mma.sync, weights
- * streamed once from HBM by CTAs of 32 / 64 output columns.  K % 128 == 0, K <= 2048, N % 8 == 0; no dropout, no
- * gelu_grad_of (inference).  Up to 4 same-shape problems per launch. */
-typedef struct sea_gemm_smallm_problem {
-  const void* a_bf16;    /* bf16 [M, lda] or NULL */
-  int64_t lda;
-  const float* x;        /* fp32 [M, ldx] when a_bf16 == NULL */
-  int64_t ldx;
-  int32_t norm_kind;     /* SEA_NORM_LN / SEA_NORM_ADALN (x path only) */
-  int32_t reserved;
-  const float* weight;   /* LN weight [K] */
-  const float* cond;     /* AdaLN folded rows [M, ldc], ldc >= 2K */
-  int64_t ldc;
-  const float* add_rows; /* optional [M, ld_add] */
-  int64_t ld_add;
-  float* x_out;          /* optional [M, ldxo] = x + add_rows */
-  int64_t ldxo;
-  const void* b;         /* bf16 weight [N, ldb] */
-  int64_t ldb;
-  sea_gemm_epilogue epi;
-} sea_gemm_smallm_problem;
-int sea_gemm_smallm_supported(int M, int N, int K);
-int sea_gemm_smallm(int num_problems, const sea_gemm_smallm_problem* host_problems, int M, int N, int K,
-                    sea_stream_t stream);
 /* Stream-K workspace of the calling thread's later GEMM launches (caller-owned device memory, 256-byte
  * aligned; NULL = none).  The first 64 KB are per-tile arrival counters and MUST be zero when handed
  * over (the kernels leave them zero); the rest parks fp32 partial tiles: 2 x 128 x BN x 4 bytes per CTA,
@@ -652,9 +624,6 @@ int sea_temporal_backward(const sea_temporal_desc* d, const void* cache, const f
                           void* workspace, size_t workspace_bytes, sea_stream_t stream);
 /* Number of kernels the last forward / backward call on this thread launched. */
 int sea_last_launch_count(void);
-/* tuning hook: 0 = sea_temporal_step keeps the tcgen05 GEMMs and separate row norms; 1 (default) = steps of at most 32 new
- * tokens (bf16) use sea_gemm_smallm with the row norms fused into its operand staging. */
-void sea_temporal_small_m(int on);
 /* cudaEvent_t plumbing for hosts without a runtime binding: create (timing disabled) / destroy / make `stream`
  * wait for the event.  Return 0 or a cudaError_t. */
 int sea_event_create(void** out_event);

@@ -942,314 +942,3 @@ extern "C" int sea_gemm_bf16_tn_chunked(int num_problems, const sea_gemm_problem
   SEA_GEMM_DISPATCH(false, false);
 #undef SEA_GEMM_DISPATCH
 }
-
-
-// =============================================================================================
-// Small-M GEMM with an optional fused row-norm prologue (the KV-cached rollout step: M = one new token per
-// trajectory, M <= 32).  At this size a 128-row tcgen05 tile is three quarters padding, its mainloop is bound by the
-// ~64-75 cycles every tcgen05.mma costs whatever its N, and the row norm in front of it is a launch of its own.  Here:
-//   * one CTA = (problem, slab of 32 / 64 output columns), full K; the CTA's weight slab (<= 256 KB) is prefetched
-//     into L2 BEFORE griddepcontrol.wait (weights are static), so its HBM fetch overlaps the upstream kernel's tail;
-//   * the A operand (all M rows x K) is staged in shared memory as bf16 — either copied from a bf16 activation, or
-//     produced on the fly from fp32 rows by the fused LayerNorm / folded-AdaLN (+ TIPI row add) prologue, which
-//     removes the norm launch of models/temporal.py:135, 140-145, 177-180 from the step's dependency chain;
-//   * the 8 warps split K; each streams its weight fragments straight from global memory (16-byte loads, k-permuted
-//     operand layout as in spatial_tc.cu: one load feeds two mma.sync.m16n8k16) with all loads of a k-range in flight;
-//   * partial sums meet in shared memory; 32 / 64 threads then run the SAME epilogue as the tcgen05 kernel
-//     (bias, residual, RoPE at the step's position, GELU, fp32 / bf16 stores into strided KV-cache rows).
-namespace sea {
-namespace {
-
-constexpr int kSmThreads = 256;
-constexpr int kSmRows = 32;
-
-struct SmallA {
-  const __nv_bfloat16* a; long long lda;   // bf16 rows [M, K], or (a == nullptr):
-  const float* x; long long ldx;           // fp32 rows, normalised on the fly
-  int norm;                                // SEA_NORM_LN: weight[k];  SEA_NORM_ADALN: folded gamma | beta rows
-  const float* weight;
-  const float* cond; long long ldc;
-  const float* add; long long ld_add;      // x' = x + add[m]  (written to x_out by slab 0)
-  float* x_out; long long ldxo;
-};
-struct alignas(64) SmallParams {
-  SmallA a[kMaxGroups];
-  const __nv_bfloat16* b[kMaxGroups];
-  long long ldb[kMaxGroups];
-  DevEpilogue epi[kMaxGroups];
-  int M, N, K, slabs;
-};
-
-__host__ __device__ inline int small_pitch(int K) {   // bf16 elements, == 32 (mod 64): conflict-free quad-wise 16-byte loads
-  int p = (K / 64) * 64 + 32;
-  return p >= K ? p : p + 64;
-}
-
-__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                         uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-template <int BNS>
-__global__ void __launch_bounds__(kSmThreads, 1) gemm_smallm_kernel(const __grid_constant__ SmallParams p) {
-  extern __shared__ __align__(16) uint8_t smraw[];
-  const int g = blockIdx.x / p.slabs, slab = blockIdx.x - g * p.slabs, n0 = slab * BNS;
-  const SmallA& A = p.a[g];
-  const int K = p.K, M = p.M, ldA = small_pitch(K);
-  __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(smraw);
-  float* red = reinterpret_cast<float*>(smraw + ((static_cast<size_t>(kSmRows) * ldA * 2 + 127) & ~static_cast<size_t>(127)));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const __nv_bfloat16* W = p.b[g];
-  const long long ldb = p.ldb[g];
-  ptx::pdl_trigger();
-  {  // static weights: pull this CTA's slab towards L2 while the upstream kernel is still finishing
-    const int lines_per_row = (K * 2 + 127) / 128;
-    const int rows = min(BNS, p.N - n0);
-    for (int i = tid; i < rows * lines_per_row; i += kSmThreads) {
-      const int r = i / lines_per_row, l = i - r * lines_per_row;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(W + static_cast<long long>(n0 + r) * ldb + l * 64));
-    }
-  }
-  ptx::pdl_wait();
-  // ---- stage A (bf16 [32][ldA]; rows >= M are zero)
-  if (A.a != nullptr) {
-    const int vec = K >> 3;
-    for (int i = tid; i < kSmRows * vec; i += kSmThreads) {
-      const int m = i / vec, c = (i - m * vec) * 8;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (m < M) v = *reinterpret_cast<const uint4*>(A.a + static_cast<long long>(m) * A.lda + c);
-      *reinterpret_cast<uint4*>(As + m * ldA + c) = v;
-    }
-  } else {
-    const float inv_k = 1.0f / K;
-    for (int m = warp; m < kSmRows; m += kSmThreads / 32) {
-      if (m >= M) {
-        for (int c = lane * 8; c < K; c += 256) *reinterpret_cast<uint4*>(As + m * ldA + c) = make_uint4(0u, 0u, 0u, 0u);
-        continue;
-      }
-      const float* xr = A.x + static_cast<long long>(m) * A.ldx;
-      const float* ar = A.add ? A.add + static_cast<long long>(m) * A.ld_add : nullptr;
-      float4 v[16];   // K <= 2048: 16 x 128 columns
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int col = c * 128 + lane * 4;
-        if (col < K) {
-          v[c] = *reinterpret_cast<const float4*>(xr + col);
-          if (ar != nullptr) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(ar + col));
-            v[c].x += t.x; v[c].y += t.y; v[c].z += t.z; v[c].w += t.w;
-            if (slab == 0 && A.x_out != nullptr) *reinterpret_cast<float4*>(A.x_out + static_cast<long long>(m) * A.ldxo + col) = v[c];
-          }
-          sum += v[c].x + v[c].y + v[c].z + v[c].w;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float mean = sum * inv_k;
-      float sq = 0.f;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        if (c * 128 + lane * 4 < K) {
-          const float dx = v[c].x - mean, dy = v[c].y - mean, dz = v[c].z - mean, dw = v[c].w - mean;
-          sq += dx * dx + dy * dy + dz * dz + dw * dw;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      const float rstd = rsqrtf(sq * inv_k + 1e-5f);
-      const bool folded = A.norm == SEA_NORM_ADALN;
-      const float* gr = folded ? A.cond + static_cast<long long>(m) * A.ldc : A.weight;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int col = c * 128 + lane * 4;
-        if (col < K) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(gr + col));
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (folded) b = __ldg(reinterpret_cast<const float4*>(gr + K + col));
-          uint2 o;
-          o.x = ptx::pack_bf16((v[c].x - mean) * rstd * w.x + b.x, (v[c].y - mean) * rstd * w.y + b.y);
-          o.y = ptx::pack_bf16((v[c].z - mean) * rstd * w.z + b.z, (v[c].w - mean) * rstd * w.w + b.w);
-          *reinterpret_cast<uint2*>(As + m * ldA + col) = o;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // ---- main loop: warp w owns k in [w K/8, (w+1) K/8)
-  constexpr int NT = BNS / 8;
-  const int t = lane & 3, r = lane >> 2;
-  float acc[2][NT][4];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int j = 0; j < NT; ++j) acc[mt][j][0] = acc[mt][j][1] = acc[mt][j][2] = acc[mt][j][3] = 0.f;
-  const int kw = K >> 3, kbeg = warp * kw, kend = kbeg + kw;
-  const __nv_bfloat16* wrow[NT];
-  bool nvalid[NT];
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    nvalid[j] = n0 + j * 8 < p.N;      // N % 8 == 0: an n-tile is entirely inside or outside
-    wrow[j] = W + static_cast<long long>(nvalid[j] ? n0 + j * 8 + r : 0) * ldb;
-  }
-  int k0 = kbeg;
-#pragma unroll 2
-  for (; k0 + 32 <= kend; k0 += 32) {
-    uint4 b[NT];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) b[j] = __ldg(reinterpret_cast<const uint4*>(wrow[j] + k0 + t * 8));
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const uint4 alo = *reinterpret_cast<const uint4*>(As + (mt * 16 + r) * ldA + k0 + t * 8);
-      const uint4 ahi = *reinterpret_cast<const uint4*>(As + (mt * 16 + r + 8) * ldA + k0 + t * 8);
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        mma16816(acc[mt][j], alo.x, ahi.x, alo.y, ahi.y, b[j].x, b[j].y);
-        mma16816(acc[mt][j], alo.z, ahi.z, alo.w, ahi.w, b[j].z, b[j].w);
-      }
-    }
-  }
-  if (k0 < kend) {   // 16-wide tail (K / 8 == 16 mod 32)
-    uint2 b[NT];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) b[j] = __ldg(reinterpret_cast<const uint2*>(wrow[j] + k0 + t * 4));
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const uint2 alo = *reinterpret_cast<const uint2*>(As + (mt * 16 + r) * ldA + k0 + t * 4);
-      const uint2 ahi = *reinterpret_cast<const uint2*>(As + (mt * 16 + r + 8) * ldA + k0 + t * 4);
-#pragma unroll
-      for (int j = 0; j < NT; ++j) mma16816(acc[mt][j], alo.x, ahi.x, alo.y, ahi.y, b[j].x, b[j].y);
-    }
-  }
-  // ---- the 8 warps' partial sums meet in shared memory: red[w][32][BNS + 1... ] (row pitch BNS + 4 against conflicts)
-  constexpr int RP = BNS + 4;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      float* d0 = red + (static_cast<size_t>(warp) * kSmRows + mt * 16 + r) * RP + j * 8 + 2 * t;
-      *reinterpret_cast<float2*>(d0) = make_float2(acc[mt][j][0], acc[mt][j][1]);
-      *reinterpret_cast<float2*>(d0 + 8 * RP) = make_float2(acc[mt][j][2], acc[mt][j][3]);
-    }
-  __syncthreads();
-  for (int i = tid; i < kSmRows * BNS; i += kSmThreads) {
-    const int m = i / BNS, c = i - m * BNS;
-    float sacc = 0.f;
-#pragma unroll
-    for (int w = 0; w < kSmThreads / 32; ++w) sacc += red[(static_cast<size_t>(w) * kSmRows + m) * RP + c];
-    red[static_cast<size_t>(m) * RP + c] = sacc;   // warp 0's slot: element (m, c) is read and written by this thread only
-  }
-  __syncthreads();
-  // ---- epilogue: one thread per (row, 32 columns), the tcgen05 kernel's own epilogue code
-  constexpr int CH = BNS / 32;
-  if (tid < kSmRows * CH) {
-    const int m = tid / CH, ch = tid - m * CH;
-    uint32_t rr[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) rr[e] = __float_as_uint(red[static_cast<size_t>(m) * RP + ch * 32 + e]);
-    epilogue_chunk(p.epi[g], rr, m, n0 + ch * 32, M, p.N, true, true);
-  }
-}
-
-int fill_epilogue(const sea_gemm_epilogue& e, DevEpilogue& d, int N) {
-  d.bias = e.bias;
-  d.residual = e.residual;
-  d.gelu_grad_of = static_cast<const __nv_bfloat16*>(e.gelu_grad_of);
-  d.rope_table = (e.rope_cols > 0) ? e.rope_table : nullptr;
-  d.out_f32 = e.out_f32;
-  d.out_pre_bf16 = static_cast<__nv_bfloat16*>(e.out_pre_bf16);
-  d.out_bf16 = static_cast<__nv_bfloat16*>(e.out_bf16);
-  d.ld_residual = e.ld_residual; d.ld_gelu = e.ld_gelu; d.ld_out_f32 = e.ld_out_f32;
-  d.ld_out_pre_bf16 = e.ld_out_pre_bf16; d.ld_out_bf16 = e.ld_out_bf16;
-  d.act = e.act; d.rope_cols = e.rope_cols; d.head_dim = e.head_dim; d.seq_len = e.seq_len;
-  d.rope_ld = e.rope_ld; d.rope_pos0 = e.rope_pos0;
-  d.res_rows = e.res_rows_per_batch; d.res_bs = e.res_batch_stride;
-  if (e.dropout_p != 0.f) return SEA_ERR_UNSUPPORTED;   // inference path
-  d.drop_seed = 0; d.drop_site = 0; d.drop_thresh = 0u; d.drop_scale = 1.0f;
-  d.rope_sign = (e.rope_sign == 0.0f) ? 1.0f : e.rope_sign;
-  if (e.out_f32 == nullptr && e.out_bf16 == nullptr && e.out_pre_bf16 == nullptr) return SEA_ERR_INVALID;
-  if (e.out_f32 && ((e.ld_out_f32 % 4) || (reinterpret_cast<uintptr_t>(e.out_f32) & 15))) return SEA_ERR_INVALID;
-  if (e.out_bf16 && ((e.ld_out_bf16 % 8) || (reinterpret_cast<uintptr_t>(e.out_bf16) & 15))) return SEA_ERR_INVALID;
-  if (e.out_pre_bf16 && ((e.ld_out_pre_bf16 % 8) || (reinterpret_cast<uintptr_t>(e.out_pre_bf16) & 15))) return SEA_ERR_INVALID;
-  if (e.residual && ((e.ld_residual % 4) || (reinterpret_cast<uintptr_t>(e.residual) & 15))) return SEA_ERR_INVALID;
-  if (e.gelu_grad_of != nullptr) return SEA_ERR_UNSUPPORTED;
-  if (e.bias && (reinterpret_cast<uintptr_t>(e.bias) & 15)) return SEA_ERR_INVALID;
-  if (e.rope_table != nullptr && e.rope_cols > 0) {
-    if (e.head_dim <= 0 || (e.head_dim % 32) || (e.rope_cols % e.head_dim) || e.seq_len <= 0 || e.rope_pos0 < 0 ||
-        e.rope_ld < e.rope_pos0 + e.seq_len)
-      return SEA_ERR_UNSUPPORTED;
-  }
-  if (e.res_rows_per_batch < 0 || (e.res_rows_per_batch > 0 && (e.res_batch_stride % 4))) return SEA_ERR_INVALID;
-  auto al32 = [](const void* ptr, long long ld_elems, int esz) {
-    return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr) & 31) == 0) && ((ld_elems * esz) % 32 == 0));
-  };
-  d.vec8 = (N % 16 == 0) && al32(e.residual, e.ld_residual, 4) && (e.res_rows_per_batch == 0 || (e.res_batch_stride * 4) % 32 == 0) &&
-           al32(e.out_f32, e.ld_out_f32, 4) && al32(e.out_pre_bf16, e.ld_out_pre_bf16, 2) && al32(e.out_bf16, e.ld_out_bf16, 2);
-  return SEA_OK;
-}
-
-}  // namespace
-}  // namespace sea
-
-extern "C" int sea_gemm_smallm_supported(int M, int N, int K) {
-  return (M >= 1 && M <= sea::kSmRows && N >= 8 && (N % 8) == 0 && K >= 128 && (K % 128) == 0 && K <= 2048) ? 1 : 0;
-}
-
-extern "C" int sea_gemm_smallm(int num_problems, const sea_gemm_smallm_problem* probs, int M, int N, int K,
-                               sea_stream_t stream) {
-  using namespace sea;
-  if (probs == nullptr || num_problems < 1 || num_problems > kMaxGroups) return SEA_ERR_INVALID;
-  if (!sea_gemm_smallm_supported(M, N, K)) return SEA_ERR_UNSUPPORTED;
-  int rc = ensure_init();
-  if (rc != SEA_OK) return rc;
-  SmallParams p{};
-  p.M = M; p.N = N; p.K = K;
-  for (int g = 0; g < num_problems; ++g) {
-    const sea_gemm_smallm_problem& q = probs[g];
-    SmallA& a = p.a[g];
-    if (q.b == nullptr || (q.ldb % 8) || q.ldb < K || (reinterpret_cast<uintptr_t>(q.b) & 15)) return SEA_ERR_INVALID;
-    if (q.a_bf16 != nullptr) {
-      if ((q.lda % 8) || q.lda < K || (reinterpret_cast<uintptr_t>(q.a_bf16) & 15)) return SEA_ERR_INVALID;
-      a.a = static_cast<const __nv_bfloat16*>(q.a_bf16); a.lda = q.lda;
-    } else {
-      if (q.x == nullptr || (q.ldx % 4) || q.ldx < K || (reinterpret_cast<uintptr_t>(q.x) & 15)) return SEA_ERR_INVALID;
-      if (q.norm_kind != SEA_NORM_LN && q.norm_kind != SEA_NORM_ADALN) return SEA_ERR_INVALID;
-      if (q.norm_kind == SEA_NORM_LN && (q.weight == nullptr || (reinterpret_cast<uintptr_t>(q.weight) & 15))) return SEA_ERR_INVALID;
-      if (q.norm_kind == SEA_NORM_ADALN && (q.cond == nullptr || (q.ldc % 4) || q.ldc < 2LL * K || (reinterpret_cast<uintptr_t>(q.cond) & 15)))
-        return SEA_ERR_INVALID;
-      if (q.add_rows != nullptr && ((q.ld_add % 4) || (reinterpret_cast<uintptr_t>(q.add_rows) & 15))) return SEA_ERR_INVALID;
-      if (q.x_out != nullptr && ((q.ldxo % 4) || (reinterpret_cast<uintptr_t>(q.x_out) & 15))) return SEA_ERR_INVALID;
-      a.a = nullptr; a.x = q.x; a.ldx = q.ldx; a.norm = q.norm_kind; a.weight = q.weight; a.cond = q.cond; a.ldc = q.ldc;
-      a.add = q.add_rows; a.ld_add = q.ld_add; a.x_out = q.x_out; a.ldxo = q.ldxo;
-    }
-    p.b[g] = static_cast<const __nv_bfloat16*>(q.b); p.ldb[g] = q.ldb;
-    rc = fill_epilogue(q.epi, p.epi[g], N);
-    if (rc != SEA_OK) return rc;
-  }
-  // wide outputs take 64-column slabs (half as many CTAs re-stage A), narrow ones 32 (more CTAs stream the weights)
-  const int bns = (static_cast<long long>(N) * num_problems >= 148LL * 2 * 32) ? 64 : 32;
-  p.slabs = (N + bns - 1) / bns;
-  const size_t a_bytes = (static_cast<size_t>(kSmRows) * small_pitch(K) * 2 + 127) & ~static_cast<size_t>(127);
-  const size_t smem = a_bytes + static_cast<size_t>(kSmThreads / 32) * kSmRows * (bns + 4) * 4;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  static bool attr_set[2][16] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (bns == 64) {
-    if (dev < 16 && !attr_set[1][dev]) {
-      SEA_CUDA_OK(cudaFuncSetAttribute(gemm_smallm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_set[1][dev] = true;
-    }
-    SEA_LAUNCH(gemm_smallm_kernel<64>, p.slabs * num_problems, kSmThreads, smem, s, p);
-  } else {
-    if (dev < 16 && !attr_set[0][dev]) {
-      SEA_CUDA_OK(cudaFuncSetAttribute(gemm_smallm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_set[0][dev] = true;
-    }
-    SEA_LAUNCH(gemm_smallm_kernel<32>, p.slabs * num_problems, kSmThreads, smem, s, p);
-  }
-  return static_cast<int>(cudaGetLastError());
-}

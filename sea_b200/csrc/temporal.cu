@@ -25,7 +25,6 @@
 namespace sea {
 
 thread_local int g_launches = 0;
-int g_small_m = 1;   // tuning hook (sea_temporal_small_m): 0 = the KV-cached step keeps the tcgen05 GEMMs + separate norms
 
 // ---------------------------------------------------------------------------------- profiler
 // Optional per-launch CUDA-event timing on the launching stream (bench.py's roofline leg).
@@ -166,7 +165,6 @@ static int for_each_weight(const sea_temporal_desc* d, CacheLayout& c, F&& f) {
 using namespace sea;
 
 extern "C" int sea_last_launch_count(void) { return g_launches; }
-extern "C" void sea_temporal_small_m(int on) { sea::g_small_m = on; }
 
 extern "C" void sea_profile_begin(void) {
   for (auto& r : g_prof) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
@@ -341,48 +339,10 @@ void layout_cond_cache(const sea_temporal_desc* d, int B, Arena& ar, Tape& t) {
 }
 
 // ------------------------------------------------------------------------------ op helpers
-// The epilogue of one Linear as the GEMM kernels take it (bf16 mode).
-static void fill_epi(Ctx& c, const LinOut& o, sea_gemm_epilogue& e) {
-  e.bias = o.bias;
-  e.residual = o.residual; e.ld_residual = o.ld_res;
-  e.res_rows_per_batch = o.res_rows; e.res_batch_stride = o.res_bs;
-  e.dropout_p = o.drop_p; e.dropout_site = o.drop_site; e.dropout_seed = c.d->dropout_seed;
-  e.act = o.act;
-  if (o.rope_cols > 0) {
-    e.rope_cols = o.rope_cols; e.head_dim = o.head_dim; e.seq_len = c.T;
-    e.rope_table = o.rope_table; e.rope_sign = 1.f; e.rope_ld = c.d->max_len;
-    e.rope_pos0 = c.pos0;
-  }
-  e.out_f32 = o.f32; e.ld_out_f32 = o.ld_f32;
-  e.out_pre_bf16 = o.pre; e.ld_out_pre_bf16 = o.ld_pre;
-  e.out_bf16 = o.post; e.ld_out_bf16 = o.ld_post;
-}
-
 int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, const LinOut* out,
                  int Mrows) {
   sea_gemm_problem probs[SEA_MAX_STREAMS];
   const int N = W[0]->N, K = W[0]->K;
-  if (c.small && sea_gemm_smallm_supported(Mrows, N, K)) {
-    sea_gemm_smallm_problem sp[SEA_MAX_STREAMS];
-    for (int g = 0; g < n; ++g) {
-      sea_gemm_smallm_problem& q = sp[g];
-      q = sea_gemm_smallm_problem{};
-      if (in[g].nx != nullptr) {
-        q.x = in[g].nx; q.ldx = in[g].ldnx; q.norm_kind = in[g].nkind; q.weight = in[g].nweight;
-        q.cond = in[g].ncond; q.ldc = in[g].ldnc; q.add_rows = in[g].nadd; q.ld_add = in[g].ld_nadd;
-        q.x_out = in[g].nxout; q.ldxo = in[g].ld_nxout;
-      } else {
-        q.a_bf16 = in[g].a; q.lda = in[g].lda;
-      }
-      q.b = W[g]->w; q.ldb = W[g]->ldw;
-      fill_epi(c, out[g], q.epi);
-    }
-    ++g_launches;
-    ProfScope prof(c.s, SEA_PROF_GEMM, 2.0 * Mrows * static_cast<double>(N) * K * n);
-    return sea_gemm_smallm(n, sp, Mrows, N, K, reinterpret_cast<sea_stream_t>(c.s));
-  }
-  for (int g = 0; g < n; ++g)
-    if (in[g].nx != nullptr) return SEA_ERR_UNSUPPORTED;   // a fused norm needs the small-M kernel (the caller checks)
   for (int g = 0; g < n; ++g) {
     sea_gemm_problem& p = probs[g];
     p = sea_gemm_problem{};
@@ -687,12 +647,6 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
   bool fork = d->aux_stream != nullptr && d->join_event != nullptr && training == 0 && !c.fp32 && V >= 2 && !g_prof_on;
   for (int i = 0; fork && i < V - 1; ++i) fork = d->fork_events[i] != nullptr;
   c.splitk = cl.splitk[d->splitk_slot];
-  // KV-cached step, M <= 32 new tokens, bf16: every Linear with K <= 2048 goes through the small-M kernel, and the row
-  // norms in front of them (LayerNorm, or AdaLN with the folded per-trajectory rows) are fused into its operand staging
-  c.small = step != nullptr && !c.fp32 && c.M <= 32 && g_small_m != 0;
-  const bool fuse_norm = c.small && (d->norm_kind == SEA_NORM_LN || inv) && sea_gemm_smallm_supported(c.M, 8, d->embed_dim) &&
-                         sea_gemm_smallm_supported(c.M, 8, d->down_dim);
-  const bool fuse_tipi = fuse_norm && inv;     // the TIPI term exists as per-trajectory rows only then
   Ctx caux = c;
   caux.s = reinterpret_cast<cudaStream_t>(d->aux_stream);
   caux.splitk = cl.splitk[(d->splitk_slot + 2) & 3];
@@ -795,13 +749,9 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
                            lt.s[i].st0, nullptr, nullptr, nullptr);
       if (xs) { ncall[i].a.x_rows_per_batch = T; ncall[i].a.x_batch_stride = x_seq_bs; }
     }
-    if (!fuse_norm) SEA_TRY(norm_group(c, V, ncall));
+    SEA_TRY(norm_group(c, V, ncall));
     for (int i = 0; i < V; ++i) {
       in[i] = LinIn{lt.s[i].n0, E, 0};
-      if (fuse_norm) {
-        in[i].nx = xin[i]; in[i].ldnx = ldxin; in[i].nkind = kind;
-        in[i].nweight = bp.s[i].ln0.weight.p; in[i].ncond = lt.s[i].cond0; in[i].ldnc = 2LL * E;
-      }
       W[i] = &bc.s[i].qkv;
       out[i] = LinOut{};
       out[i].bias = bc.s[i].qkv_bias;
@@ -857,15 +807,9 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
           nc2[i - i0].a.tipi_dropout_seed = d->dropout_seed;
         }
       }
-      if (!fuse_tipi) SEA_TRY(norm_group(cx, nn, nc2));
+      SEA_TRY(norm_group(cx, nn, nc2));
       for (int i = i0; i < i1; ++i) {
         tin[i - i0] = LinIn{lt.s[i].n2, E, 0};
-        if (fuse_tipi) {   // x2 = x_post + TIPI row, Norm_{i,2}(x2) as the up-projection's operand; x2 is kept for the skip
-          LinIn& q = tin[i - i0];
-          q.nx = lt.s[i].xp; q.ldnx = E; q.nkind = kind; q.nweight = bp.s[i].ln2.weight.p;
-          q.ncond = lt.s[i].cond2; q.ldnc = 2LL * E;
-          q.nadd = lt.tipi_rows; q.ld_nadd = E; q.nxout = lt.s[i].x2; q.ld_nxout = E;
-        }
         tW[i - i0] = &bc.s[i].mlp0;
         tout[i - i0] = LinOut{};
         tout[i - i0].bias = bp.s[i].mlp0_b.p;
@@ -918,7 +862,7 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
     for (int i = 0; i < V; ++i)
       ncall[i] = norm_call(c, kind, bp.s[i].ln_cross, lt.s[i].condc, lt.s[i].dpre, Dd, Dd, lt.s[i].npre,
                            nullptr, 0, lt.s[i].stc_pre, nullptr, nullptr, nullptr);
-    if (!fuse_norm) SEA_TRY(norm_group(c, V, ncall));
+    SEA_TRY(norm_group(c, V, ncall));
     // Every q projection, and the k / v projections whose source stream has not been exchanged yet
     // (j > i), read only the pre-exchange ln_cross outputs: same shape [M, Dd] x [Dd, Dd], so they
     // go out together, up to four per launch (models/base_blocks.py:271-276).
@@ -933,13 +877,9 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
         ng = 0;
         return rc;
       };
-      auto push = [&](int src, const PackedLinear& w, int row_off, const float* bias, void* dst,
+      auto push = [&](const void* a_src, const PackedLinear& w, int row_off, const float* bias, void* dst,
                       long long ld_dst, bool rope) -> int {
-        gin[ng] = LinIn{lt.s[src].npre, Dd, 0};
-        if (fuse_norm) {   // ln_cross of the source stream, recomputed inside every consumer (M <= 32 rows)
-          gin[ng].nx = lt.s[src].dpre; gin[ng].ldnx = Dd; gin[ng].nkind = kind;
-          gin[ng].nweight = bp.s[src].ln_cross.weight.p; gin[ng].ncond = lt.s[src].condc; gin[ng].ldnc = 2LL * Dd;
-        }
+        gin[ng] = LinIn{a_src, Dd, 0};
         gw[ng] = w;
         gw[ng].N = Dd;
         gw[ng].w = w.w + static_cast<long long>(row_off) * w.ldw;
@@ -954,7 +894,7 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
         StreamTape& s = lt.s[i];
         for (int j = 0; j < V; ++j) {
           if (j == i) continue;
-          SEA_TRY(push(i, bc.s[i].cq[j], 0, bp.s[i].cross_attn[j].q_b.p, s.q[j], Dd, true));
+          SEA_TRY(push(s.npre, bc.s[i].cq[j], 0, bp.s[i].cross_attn[j].q_b.p, s.q[j], Dd, true));
           if (j > i) {
             char* kvb = static_cast<char*>(s.kv[j]);
             long long ldkv = 2 * Dd;
@@ -962,8 +902,8 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
               kvb = static_cast<char*>(step->kv->L[static_cast<size_t>(l) * V + i].kvc[j]) + esz * 2 * Dd * step->pos;
               ldkv = 2LL * Dd * step->max_len;
             }
-            SEA_TRY(push(j, bc.s[i].ckv[j], 0, bc.s[i].ckv_bias[j], kvb, ldkv, true));
-            SEA_TRY(push(j, bc.s[i].ckv[j], Dd, bc.s[i].ckv_bias[j] + Dd, kvb + esz * Dd, ldkv, false));
+            SEA_TRY(push(lt.s[j].npre, bc.s[i].ckv[j], 0, bc.s[i].ckv_bias[j], kvb, ldkv, true));
+            SEA_TRY(push(lt.s[j].npre, bc.s[i].ckv[j], Dd, bc.s[i].ckv_bias[j] + Dd, kvb + esz * Dd, ldkv, false));
           }
         }
       }
@@ -977,10 +917,6 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
         if (j < i) {
           // (k,v) from the already exchanged stream j     models/temporal.py:189-191
           in[0] = LinIn{lt.s[j].npost, Dd, 0};
-          if (fuse_norm) {
-            in[0].nx = lt.s[j].dpost; in[0].ldnx = Dd; in[0].nkind = kind;
-            in[0].nweight = bp.s[j].ln_cross.weight.p; in[0].ncond = lt.s[j].condc; in[0].ldnc = 2LL * Dd;
-          }
           W[0] = &bc.s[i].ckv[j];
           out[0] = LinOut{};
           out[0].bias = bc.s[i].ckv_bias[j];
@@ -1040,7 +976,7 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
         SEA_TRY(linear_group(c, 1, in, W, out, M));
         ncall[0] = norm_call(c, kind, bp.s[i].ln_cross, s.condc, s.dpost, Dd, Dd, s.npost, nullptr, 0,
                              s.stc_post, nullptr, nullptr, nullptr);
-        if (!fuse_norm) SEA_TRY(norm_group(c, 1, ncall));
+        SEA_TRY(norm_group(c, 1, ncall));
       }
     }
 

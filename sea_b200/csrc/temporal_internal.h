@@ -120,18 +120,12 @@ struct Ctx {
   float drop_p;      // train-mode dropout probability of this call (0 in eval / inference)
   int pos0;          // absolute position of row 0 of every trajectory (KV-cached step: the new token's)
   void* splitk;      // stream-K workspace of the GEMMs this context launches (NULL: leave the current one)
-  bool small;        // KV-cached step with M <= 32 rows in bf16 mode: Linears go through sea_gemm_smallm (fused row norms)
 };
 
 struct LinIn {
   const void* a;  // act dtype [M, K]
   long long lda;
   int act_on_load;  // fp32 mode only: GELU applied while packing
-  // small-M step path (Ctx::small): the row norm in front of this Linear is fused into the GEMM's A-operand staging
-  // (a is then ignored): rows nx [M, K] fp32, LN weight or folded AdaLN rows, optional TIPI row add (+ x_out)
-  const float* nx = nullptr; long long ldnx = 0;
-  int nkind = 0; const float* nweight = nullptr; const float* ncond = nullptr; long long ldnc = 0;
-  const float* nadd = nullptr; long long ld_nadd = 0; float* nxout = nullptr; long long ld_nxout = 0;
 };
 struct LinOut {
   const float* bias;
