@@ -68,6 +68,26 @@ def test_non_default_modes_forward_and_gradients(cuda, ns, exchange, ib_scale, i
     la, lb = F.mse_loss(ya, tgt), F.mse_loss(yb, tgt)
     la.backward()
     lb.backward()
+    ms = {}
+    if width != "small":      # informational (printed, never asserted): forward + backward on this GPU
+        for tag, mdl in (("eager", ref), ("modules", fast)):
+            def step():
+                mdl.zero_grad(set_to_none=True)
+                F.mse_loss(mdl(x, ib), tgt).backward()
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms[tag] = e0.elapsed_time(e1) / 3
+        la = F.mse_loss(ref(x, ib), tgt)
+        lb = F.mse_loss(fast(x, ib), tgt)
+        ref.zero_grad(set_to_none=True), fast.zero_grad(set_to_none=True)
+        la.backward()
+        lb.backward()
     e_fwd = _rel(yb, ya)
     worst, n = 0.0, 0
     for (name, p), (_, q) in zip(ref.named_parameters(), fast.named_parameters()):
@@ -79,7 +99,8 @@ def test_non_default_modes_forward_and_gradients(cuda, ns, exchange, ib_scale, i
         n += 1
         assert cos > 0.99 and _rel(q.grad, p.grad) < 0.12, (name, cos, _rel(q.grad, p.grad))
     print(f"\\n[modes] {exchange}/{ib_scale}/{ib_add}/after={after}/{ln}: forward rel {e_fwd:.2e}, loss {la.item():.5f} vs "
-          f"{lb.item():.5f}, worst 1-cos over {n} gradients {worst:.1e}; switched {counts}")
+          f"{lb.item():.5f}, worst 1-cos over {n} gradients {worst:.1e}; switched {counts}"
+          + (f"; fwd+bwd {ms['eager']:.2f} ms eager fp32 vs {ms['modules']:.2f} ms module path" if ms else ""))
     assert e_fwd < 2e-2 and abs(la.item() - lb.item()) / la.item() < 1e-2
 
 

@@ -133,3 +133,12 @@ def test_gloo_world2_exchange_gradients_mean():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert out == [1.5] * 12
+
+
+def test_rollout_micro_batch_ranges():
+    from sea_b200.rollout import _split_ranges
+    assert _split_ranges(32, 1) == [(0, 32)]
+    assert _split_ranges(32, 2) == [(0, 16), (16, 32)]
+    assert _split_ranges(7, 4) == [(0, 2), (2, 4), (4, 6), (6, 7)]
+    assert _split_ranges(3, 8) == [(0, 1), (1, 2), (2, 3)]          # at most B groups, at most 4 (stream-K workspaces)
+    assert _split_ranges(5, 0) == [(0, 5)]
