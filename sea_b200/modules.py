@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import ctypes as C
 import types
+import weakref
 from typing import Optional
 
 import torch
@@ -51,7 +52,8 @@ def _to_bf16(x: torch.Tensor) -> torch.Tensor:
 
 
 class _WeightCache:
-    """bf16 tensor-core copies of fp32 parameters, refreshed when the parameter's version / storage changes."""
+    """bf16 tensor-core copies of fp32 parameters, refreshed when the parameter's version / storage changes.  Entries are
+    tied to the parameter OBJECT through a weak reference (an id or an address alone may be recycled for another tensor)."""
 
     def __init__(self):
         self._d = {}
@@ -59,10 +61,10 @@ class _WeightCache:
     def get(self, p: torch.Tensor) -> torch.Tensor:
         key = id(p)
         hit = self._d.get(key)
-        if hit is None or hit[0] != p._version or hit[1] != p.data_ptr():
-            hit = (p._version, p.data_ptr(), _to_bf16(p.detach()))
+        if hit is None or hit[0]() is not p or hit[1] != p._version or hit[2] != p.data_ptr():
+            hit = (weakref.ref(p, lambda _r, k=key: self._d.pop(k, None)), p._version, p.data_ptr(), _to_bf16(p.detach()))
             self._d[key] = hit
-        return hit[2]
+        return hit[3]
 
 
 _weights = _WeightCache()

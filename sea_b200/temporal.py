@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 import math
 import types
 from typing import Dict, Optional
@@ -649,14 +650,17 @@ class TemporalEngine:
         base = ib._base if ib._base is not None else ib
         if base.dim() != 3 or not base.is_cuda or ib.dim() != 3:
             return False, None
-        key = (base.data_ptr(), base._version, tuple(base.shape), tuple(base.stride()))
-        if getattr(self, "_ib_auto_key", None) != key:
+        # identity of the base tensor OBJECT (weak reference) + its version counter — never its address: the caching
+        # allocator hands the next batch's condition tensor the same address, and that one holds other values
+        ref = getattr(self, "_ib_auto_ref", None)
+        if ref is None or ref() is not base or self._ib_auto_version != base._version:
             self._ib_auto = bool((base == base[:, :1]).all().item())
-            self._ib_auto_key = key
+            self._ib_auto_ref, self._ib_auto_version = weakref.ref(base), base._version
+            self._ib_auto_gen = getattr(self, "_ib_auto_gen", 0) + 1
         if not self._ib_auto:
             return False, None
-        # the cached condition rows belong to THESE trajectories: same view origin, same batch
-        return True, (key, ib.data_ptr(), B)
+        # the cached condition rows belong to THESE trajectories of THIS tensor: generation, view origin, batch
+        return True, (self._ib_auto_gen, ib.data_ptr() - base.data_ptr(), B)
 
     @torch.no_grad()
     def forward_into(self, x: torch.Tensor, ib: torch.Tensor, y: torch.Tensor, ws: torch.Tensor, *,

@@ -413,3 +413,15 @@ def test_eager_loop_condition_detection(cuda, ns):
     ib_var = torch.rand(B, steps, 1, generator=g).to(cuda)
     assert _rel(loop(fast_m, x0, ib_var), loop(ref_m, x0, ib_var)) < 1e-4
     assert eng._ib_auto is False
+    # a NEW tensor that the caching allocator places at the SAME address (next batch of a validation loop), other values:
+    # the cache is tied to the tensor object, never to its address
+    addr = None
+    for k in range(4):
+        vals = torch.rand(B, 1, 1, generator=g)
+        ib_new = (vals.expand(B, steps, 1) if k % 2 == 0 else torch.rand(B, steps, 1, generator=g)).contiguous().to(cuda)
+        if addr is not None:
+            assert ib_new.data_ptr() == addr            # same address as the tensor freed in the previous iteration
+        addr = ib_new.data_ptr()
+        assert _rel(loop(fast_m, x0, ib_new), loop(ref_m, x0, ib_new)) < 1e-4, k
+        assert eng._ib_auto is (k % 2 == 0)
+        del ib_new
