@@ -619,6 +619,7 @@ static int forward_impl(const sea_temporal_desc* d, const void* cache, const flo
   Tape tape;
   layout_tape(d, B, T, training != 0, war, tape);
   if (d->splitk_slot < 0 || d->splitk_slot > 3) return SEA_ERR_INVALID;
+  SplitKGuard splitk_guard;
   SEA_TRY(sea_gemm_set_workspace(cl.splitk[d->splitk_slot], cl.splitk_bytes));
 
   Ctx c{};

@@ -413,6 +413,7 @@ extern "C" int sea_temporal_backward(const sea_temporal_desc* d, const void* cac
   Arena car{const_cast<char*>(static_cast<const char*>(cache))};
   CacheLayout cl;
   layout_cache(d, true, car, cl);
+  SplitKGuard splitk_guard;
   SEA_TRY(sea_gemm_set_workspace(cl.splitk[0], cl.splitk_bytes));
   Arena war{static_cast<char*>(workspace)};
   Tape tape;

@@ -146,6 +146,13 @@ int linear_group(Ctx& c, int n, const LinIn* in, const PackedLinear* const* W, c
 
 extern thread_local int g_launches;
 
+// The stream-K workspace of the GEMM launches is thread-local state of the library (sea_gemm_set_workspace): an executor
+// call points it into the caller's weight cache and MUST take it back before returning — the cache may be freed right
+// after the call, and a later stand-alone sea_gemm_bf16_tn on this thread would park partial tiles in freed memory.
+struct SplitKGuard {
+  ~SplitKGuard() { sea_gemm_set_workspace(nullptr, 0); }
+};
+
 // dropout site ids of the temporal executor (see sea_dropout_mask)
 inline unsigned drop_site(int layer, int kind, int i, int j) { return static_cast<unsigned>(((layer * 4 + kind) * 4 + i) * 4 + j); }
 enum { SEA_SITE_SELF = 0, SEA_SITE_CROSS = 1, SEA_SITE_MLP = 2, SEA_SITE_TIPI = 3 };
