@@ -196,18 +196,22 @@ __device__ __forceinline__ void attention_tc(const bf16* __restrict__ Q, const b
   constexpr int NTV = HD > 8 ? HD / 8 : 1;
   for (int item = warp; item < n_heads * 4; item += kWarps) {
     const int h = item >> 2, rt = item & 3;
-    const bf16* q0 = Q + (rt * 16 + r) * ld + h * HD;
-    const bool lo_ok = 2 * t < HD, hi_ok = 2 * t + 8 < HD;
+    // the 16-dim group of the k = 16 MMA that contains this head's HD dims: Q and K fragments are loaded unconditionally
+    // from it, and the lanes of the A fragment that belong to other heads are zeroed (S = A_h . K_group^T is exact)
+    const int gbase = (h * HD) & ~15;
+    const bf16* q0 = Q + (rt * 16 + r) * ld + gbase;
+    const int dlo = gbase + 2 * t - h * HD, dhi = dlo + 8;
+    const bool lo_ok = dlo >= 0 && dlo < HD, hi_ok = dhi >= 0 && dhi < HD;
     const uint32_t a0 = lo_ok ? *reinterpret_cast<const uint32_t*>(q0 + 2 * t) : 0u;
     const uint32_t a1 = lo_ok ? *reinterpret_cast<const uint32_t*>(q0 + 8 * ld + 2 * t) : 0u;
     const uint32_t a2 = hi_ok ? *reinterpret_cast<const uint32_t*>(q0 + 2 * t + 8) : 0u;
     const uint32_t a3 = hi_ok ? *reinterpret_cast<const uint32_t*>(q0 + 8 * ld + 2 * t + 8) : 0u;
     float s[8][4];
+    const bf16* kr = Kk + r * ld + gbase + 2 * t;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const bf16* kr = Kk + (j * 8 + r) * ld + h * HD;
-      const uint32_t b0 = lo_ok ? *reinterpret_cast<const uint32_t*>(kr + 2 * t) : 0u;
-      const uint32_t b1 = hi_ok ? *reinterpret_cast<const uint32_t*>(kr + 2 * t + 8) : 0u;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + j * 8 * ld);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + j * 8 * ld + 8);
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
       mma16816(s[j], a0, a1, a2, a3, b0, b1);
     }
@@ -220,10 +224,11 @@ __device__ __forceinline__ void attention_tc(const bf16* __restrict__ Q, const b
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
     float l0 = 0.f, l1 = 0.f;
+    const float nm0 = -m0 * sl2, nm1 = -m1 * sl2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s[j][0] = ptx::ex2((s[j][0] - m0) * sl2); s[j][1] = ptx::ex2((s[j][1] - m0) * sl2);
-      s[j][2] = ptx::ex2((s[j][2] - m1) * sl2); s[j][3] = ptx::ex2((s[j][3] - m1) * sl2);
+      s[j][0] = ptx::ex2(fmaf(s[j][0], sl2, nm0)); s[j][1] = ptx::ex2(fmaf(s[j][1], sl2, nm0));
+      s[j][2] = ptx::ex2(fmaf(s[j][2], sl2, nm1)); s[j][3] = ptx::ex2(fmaf(s[j][3], sl2, nm1));
       l0 += s[j][0] + s[j][1];
       l1 += s[j][2] + s[j][3];
     }
