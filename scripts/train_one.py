@@ -1,4 +1,4 @@
-"""Two fwd+bwd+AdamW steps of one config (for ncu launch lists of the train step).
+"""Three fwd+bwd+AdamW steps (the last one is steady state: optimizer state exists) of one config (for ncu launch lists of the train step).
     python scripts/train_one.py [cylinder_flow|multiphase_flow] [B]"""
 import os
 import sys
@@ -21,7 +21,7 @@ opt = AdamW(m.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=
 x = torch.randn(b, T, 2, E, device=dev)
 ib = torch.rand(b, 1, 1, device=dev).expand(b, T, 1).contiguous()
 tgt = torch.randn(b, T, 2, E, device=dev)
-for _ in range(2):
+for _ in range(3):
     opt.zero_grad(set_to_none=True)
     F.mse_loss(m(x, ib), tgt).backward()
     opt.step()
