@@ -93,10 +93,44 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 3 : 4));
   static constexpr int TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // allocation must be a power of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    2 * BN * 4 /*bias slice of the tile in each accumulator stage*/;
 };
 
-__device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint32_t (&r)[32],
+// Residual values of one epilogue chunk (row m, columns [n0, n0 + 32)) into registers.  Issued ahead of the chunk's
+// accumulator (the residual does not depend on this launch's MMAs), so its L2 round trip overlaps the mainloop / the
+// previous chunk instead of sitting between tcgen05.ld and the stores.
+__device__ __forceinline__ void load_residual_chunk(const DevEpilogue& e, int m, int n0, int M, int N, uint32_t (&res)[32]) {
+  if (m >= M || n0 >= N) return;
+  const int nvalid = min(32, N - n0);
+  const float* rp = e.residual + (e.res_rows > 0 ? static_cast<long long>(m / e.res_rows) * e.res_bs + static_cast<long long>(m % e.res_rows) * e.ld_residual
+                                                 : static_cast<long long>(m) * e.ld_residual) + n0;
+  if (e.vec8) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < nvalid) {
+        uint32_t t[8];
+        ptx::ldg256(rp + j, t);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) res[j + q] = t[q];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < nvalid) {
+        const float4 b = *reinterpret_cast<const float4*>(rp + j);
+        res[j] = __float_as_uint(b.x); res[j + 1] = __float_as_uint(b.y);
+        res[j + 2] = __float_as_uint(b.z); res[j + 3] = __float_as_uint(b.w);
+      }
+    }
+  }
+}
+
+// bias_s: this chunk's 32 bias values in shared memory (staged per tile by the epilogue warps while the mainloop
+// runs; zero past N); res: load_residual_chunk's registers (read only when first && e.residual).
+__device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint32_t (&r)[32], const float* bias_s,
+                                               const uint32_t (&res)[32],
                                                int m, int n0, int M, int N, bool first, bool last) {
   // One thread = one output row m, 32 consecutive columns starting at n0.
   if (m >= M || n0 >= N) return;
@@ -122,21 +156,15 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           if (j < nvalid) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+            const float4 b = *reinterpret_cast<const float4*>(bias_s + j);
             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
         }
       }
       if (e.residual != nullptr) {
-        const float* rp = e.residual + (e.res_rows > 0 ? static_cast<long long>(m / e.res_rows) * e.res_bs + static_cast<long long>(m % e.res_rows) * e.ld_residual
-                                                       : static_cast<long long>(m) * e.ld_residual) + n0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (j < nvalid) {
-            const float4 b = *reinterpret_cast<const float4*>(rp + j);
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] += __uint_as_float(res[j]);
       }
     }
     float* op = e.out_f32 + static_cast<long long>(m) * e.ld_out_f32 + n0;
@@ -151,7 +179,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       if (j < nvalid) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + j);
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
     }
@@ -167,27 +195,9 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
     }
   }
   if (first && e.residual != nullptr) {
-    const float* rp = e.residual + (e.res_rows > 0 ? static_cast<long long>(m / e.res_rows) * e.res_bs + static_cast<long long>(m % e.res_rows) * e.ld_residual
-                                                   : static_cast<long long>(m) * e.ld_residual) + n0;
-    if (e.vec8) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        if (j < nvalid) {
-          uint32_t t[8];
-          ptx::ldg256(rp + j, t);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[j + q] += __uint_as_float(t[q]);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < nvalid) {
-          const float4 b = *reinterpret_cast<const float4*>(rp + j);
-          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-        }
-      }
-    }
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) v[j] += __uint_as_float(res[j]);
   }
   if (e.rope_table != nullptr && n0 < e.rope_cols) {
     // models/base_blocks.py:314-324 — interleaved pairs (x[2k], x[2k+1]) times (cos + i sin).
@@ -331,6 +341,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   uint64_t* tempty = tfull + 2;          // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   int* sk_flag = reinterpret_cast<int*>(tmem_slot + 1);
+  float* bias_stage = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256);   // [2][BN]
 
   // shfl-broadcast makes the warp index provably warp-uniform for the compiler: the role branches
   // below are then uniform, and the single-thread regions are entered through elect.sync, so the
@@ -572,6 +583,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       const int m = tm * BM + row;
       const bool first = sg.kb0 == 0, last = sg.kb1 >= num_kb;
       const bool partial = sg.sk && !(first && last);
+      // While the mainloop of this segment runs: bias slice of the tile -> shared memory, residual of the first chunk
+      // -> registers.  Neither depends on the accumulator; fetched after the tfull wait they put one L2 round trip per
+      // 32-column chunk on the launch's critical path (~0.4 us per chunk, 1-3 us of a single-wave GEMM).
+      constexpr int NCH = BN / 64;          // 32-column chunks per thread
+      float* bias_s = bias_stage + acc * BN;
+      const bool use_res = first && e.residual != nullptr;
+      uint32_t regs[32], resv[32], res_next[32];
+      if (e.bias != nullptr) {
+        const int te = static_cast<int>(threadIdx.x) - 64;
+        if (te < BN) {
+          const int col = tn * BN + te;
+          bias_s[te] = col < p.N ? __ldg(e.bias + col) : 0.f;
+        }
+      }
+      if (use_res && !partial) load_residual_chunk(e, m, tn * BN + half * 32, p.M, p.N, resv);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       if (threadIdx.x == 64) trace_mark(p, 5);
@@ -579,11 +606,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
                              static_cast<uint32_t>(acc * BN);
       if (!partial) {
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
-          uint32_t regs[32];
+        for (int i = 0; i < NCH; ++i) {
+          const int c = half + 2 * i;
           ptx::tmem_ld_32x32(t_row + c * 32, regs);
-          ptx::tmem_ld_wait();
-          epilogue_chunk(e, regs, m, tn * BN + c * 32, p.M, p.N, first, last);
+          // the next chunk's residual goes in flight before this chunk is processed (its L2 latency is ~10x TMEM's)
+          if (NCH > 1 && i + 1 < NCH && use_res) load_residual_chunk(e, m, tn * BN + (c + 2) * 32, p.M, p.N, res_next);
+          ptx::tmem_ld_wait_on(regs);
+          epilogue_chunk(e, regs, bias_s + c * 32, resv, m, tn * BN + c * 32, p.M, p.N, first, last);
+          if (NCH > 1 && use_res) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) resv[j] = res_next[j];
+          }
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -594,16 +627,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
         float* slot = p.sk_ws + (static_cast<size_t>(blockIdx.x) * 2 + (nseg == 0 ? 0 : 1)) * (BM * BN);
 #pragma unroll 1
         for (int c = half; c < BN / 32; c += 2) {
-          uint32_t regs[32];
-          ptx::tmem_ld_32x32(t_row + c * 32, regs);
+          uint32_t part[32];
+          ptx::tmem_ld_32x32(t_row + c * 32, part);
           ptx::tmem_ld_wait();
           // slot layout [chunk][j][row] in float4 units: lanes write consecutive 16-byte words (coalesced);
           // the reducer below uses the same (row, chunk, j) -> address map, nobody else reads a slot
           float4* dst = reinterpret_cast<float4*>(slot) + static_cast<size_t>(c) * 8 * BM + row;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            dst[j * BM] = make_float4(__uint_as_float(regs[4 * j]), __uint_as_float(regs[4 * j + 1]),
-                                      __uint_as_float(regs[4 * j + 2]), __uint_as_float(regs[4 * j + 3]));
+            dst[j * BM] = make_float4(__uint_as_float(part[4 * j]), __uint_as_float(part[4 * j + 1]),
+                                      __uint_as_float(part[4 * j + 2]), __uint_as_float(part[4 * j + 3]));
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -633,10 +666,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
                 v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
               }
             }
-            uint32_t regs[32];
+            uint32_t sum[32], rres[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) regs[j] = __float_as_uint(v[j]);
-            epilogue_chunk(e, regs, m, tn * BN + c * 32, p.M, p.N, true, true);
+            for (int j = 0; j < 32; ++j) sum[j] = __float_as_uint(v[j]);
+            if (e.residual != nullptr) load_residual_chunk(e, m, tn * BN + c * 32, p.M, p.N, rres);
+            epilogue_chunk(e, sum, bias_s + c * 32, rres, m, tn * BN + c * 32, p.M, p.N, true, true);
           }
           if (threadIdx.x == 64) p.sk_counters[sg.tile] = 0u;   // self-cleaning for the next launch
         }
