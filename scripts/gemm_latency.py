@@ -38,6 +38,7 @@ cfg = (C.c_int * 4)()
 
 print(f"{'shape':18s} {'M':>5s} {'N':>6s} {'K':>6s} g | bn grid upc tiles | chain us | trace ns: prolog pdlwait 1st-stage mainloop "
       f"acc-seen epilogue exit | total")
+lib.sea_gemm_debug_probe(int(os.environ.get('SEA_PROBE', '0')))
 for M in (32, 320, 960, 3200):
     for name, N, K, g in SHAPES:
         A = [torch.randn(M, K, device=dev).bfloat16() for _ in range(g)]
