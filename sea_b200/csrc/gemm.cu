@@ -601,7 +601,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
-      if (threadIdx.x == 64) trace_mark(p, 5);
+      if (threadIdx.x == 128) trace_mark(p, 5);   // warp 4: TMEM lanes 0-31 = rows that exist at any M
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
       if (!partial) {
@@ -679,7 +679,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       if (sg.sk) ++nseg;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-      if (threadIdx.x == 64) trace_mark(p, 6);
+      if (threadIdx.x == 128) trace_mark(p, 6);
     }
   }
 
