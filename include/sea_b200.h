@@ -378,6 +378,10 @@ typedef struct sea_attn_args {
   uint64_t dropout_seed;
 } sea_attn_args;
 int sea_attention_fwd(const sea_attn_args* args, sea_stream_t stream);
+/* Tuning switch: 1 (default) = bf16 problems with T <= 24 (head_dim 128) / 40 (head_dim 64) and no probability
+ * dropout run on the short-sequence kernel (one small CTA per (batch, head), warp-level mma.sync); 2 = every
+ * T <= 128 (tests); 0 = always the tcgen05 kernel. */
+void sea_attention_small(int on);
 /* `n` (1..SEA_MAX_STREAMS) problems of identical shape (B, T, n_heads, head_dim, src_len, scale,
  * prec, ldo) in ONE launch: the self-attention of the V independent field streams
  * (models/temporal.py:135-136 runs them one after the other). */

@@ -7,6 +7,8 @@
 namespace sea {
 int attention_fwd_simt(const sea_attn_args* a, cudaStream_t s);
 int attention_fwd_tc(int n, const sea_attn_args* a, cudaStream_t s);  // attention_tc.cu
+int attention_fwd_small(int n, const sea_attn_args* a, cudaStream_t s);  // attention_small.cu: T <= 128, mma.sync
+bool attention_small_supported(const sea_attn_args* a);
 bool attention_tc_supported(const sea_attn_args* a);
 int g_force_simt = 0;  // test hook: route bf16 attention (fwd and bwd) to the CUDA-core kernels
 
@@ -45,6 +47,7 @@ extern "C" int sea_attention_fwd_group(int n, const sea_attn_args* a, sea_stream
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a[0].dropout_p < 0.f || a[0].dropout_p >= 1.f) return SEA_ERR_INVALID;
+  if (tc && attention_small_supported(&a[0])) return attention_fwd_small(n, a, s);   // same shape for all n (checked above)
   if (tc) return attention_fwd_tc(n, a, s);
   if (a[0].dropout_p > 0.f) return SEA_ERR_UNSUPPORTED;   // probability dropout lives in the tensor-core kernels only
   for (int i = 0; i < n; ++i) {

@@ -143,12 +143,44 @@ def test_attention_tcgen05(cuda, hd, B, T, src_len):
     g = torch.Generator(device="cuda").manual_seed(hd + T)
     qkv = torch.randn(B * T, 3 * nh * hd, device=cuda, generator=g).bfloat16()
     q, k, v = qkv[:, :nh * hd], qkv[:, nh * hd:2 * nh * hd], qkv[:, 2 * nh * hd:]
-    o, lse = ops.attention_fwd(q, k, v, nh, src_len=src_len, B=B, want_lse=True)
+    from sea_b200._lib import lib
+    lib.sea_attention_small(0)          # T <= 128 would otherwise go to the short-sequence kernel
+    try:
+        o, lse = ops.attention_fwd(q, k, v, nh, src_len=src_len, B=B, want_lse=True)
+    finally:
+        lib.sea_attention_small(1)
     torch.cuda.synchronize()
     ref, ref_lse = _attn_ref(q, k, v, B, nh, src_len)
     assert torch.isfinite(o.float()).all()
     assert _rel(o.float(), ref) < 8e-3
     assert _rel(lse, ref_lse) < 1e-4
+
+
+@pytest.mark.parametrize("hd", [64, 128])
+@pytest.mark.parametrize("T", [1, 2, 5, 16, 17, 33, 64, 100, 127, 128])
+@pytest.mark.parametrize("src_len", [0, 2])
+def test_attention_short_sequences(cuda, hd, T, src_len):
+    """attention_small.cu (T <= 128: the rollout's prefixes) against the fp32 reference and the tcgen05 kernel."""
+    from sea_b200 import ops
+    from sea_b200._lib import lib
+    B, nh = 3, 4
+    g = torch.Generator(device="cuda").manual_seed(1000 * hd + 10 * T + src_len)
+    qkv = torch.randn(B * T, 3 * nh * hd + 8, device=cuda, generator=g).bfloat16()       # padded pitch
+    q, k, v = qkv[:, :nh * hd], qkv[:, nh * hd:2 * nh * hd], qkv[:, 2 * nh * hd:3 * nh * hd]
+    try:
+        lib.sea_attention_small(2)      # every T <= 128 (the default hands T > 24 / 40 to the tcgen05 kernel)
+        o, lse = ops.attention_fwd(q, k, v, nh, src_len=src_len, B=B, want_lse=True)
+        lib.sea_attention_small(0)
+        o_tc, lse_tc = ops.attention_fwd(q, k, v, nh, src_len=src_len, B=B, want_lse=True)
+    finally:
+        lib.sea_attention_small(1)
+    torch.cuda.synchronize()
+    ref, ref_lse = _attn_ref(q, k, v, B, nh, src_len)
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    assert _rel(o.float(), ref) < 8e-3
+    assert _rel(lse, ref_lse) < 1e-4
+    assert _rel(o.float(), o_tc.float()) < 8e-3
+    assert _rel(lse, lse_tc) < 1e-4
 
 
 def test_attention_tcgen05_peaked_scores(cuda):
