@@ -550,7 +550,7 @@ def main():
         "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32",
         "data": "synthetic",
         "config": cfg,
-        "execution": {"how": "sea_b200.rollout.RolloutPlan: one CUDA graph per prefix length (full forward over the "
+        "execution": {"how": "sea_b200.rollout.RolloutPlan: the kernels of every prefix length recorded in CUDA graphs, 10 steps per graph (full forward over the "
                              "prefix read in place from the sequence buffer, append last step); the roofline leg replays "
                              "the same kernels eagerly with per-launch CUDA events",
                       "reference_count_tflop_per_step_per_gpu": rollout_flops(B, R) / 1e12,
