@@ -129,8 +129,12 @@ __device__ __forceinline__ void load_residual_chunk(const DevEpilogue& e, int m,
 
 // bias_s: this chunk's 32 bias values in shared memory (staged per tile by the epilogue warps while the mainloop
 // runs; zero past N); res: load_residual_chunk's registers (read only when first && e.residual).
+// n0_next >= 0: as soon as this chunk's residual registers have been consumed they are refilled for the chunk at
+// n0_next, so that load is in flight under this chunk's stores and the next accumulator read (a second register
+// buffer would push the kernel from ~140 to 168 registers: measured, that leaves no room for an NCCL CTA beside a GEMM
+// CTA on the SM and the overlapped data-parallel step at per-GPU batch 2 went from 2.29 to 2.63 ms on 2 GPUs).
 __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint32_t (&r)[32], const float* bias_s,
-                                               const uint32_t (&res)[32],
+                                               uint32_t (&res)[32], int n0_next,
                                                int m, int n0, int M, int N, bool first, bool last) {
   // One thread = one output row m, 32 consecutive columns starting at n0.
   if (m >= M || n0 >= N) return;
@@ -165,6 +169,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (j < nvalid) v[j] += __uint_as_float(res[j]);
+        if (n0_next >= 0) load_residual_chunk(e, m, n0_next, M, N, res);
       }
     }
     float* op = e.out_f32 + static_cast<long long>(m) * e.ld_out_f32 + n0;
@@ -198,6 +203,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j < nvalid) v[j] += __uint_as_float(res[j]);
+    if (n0_next >= 0) load_residual_chunk(e, m, n0_next, M, N, res);
   }
   if (e.rope_table != nullptr && n0 < e.rope_cols) {
     // models/base_blocks.py:314-324 — interleaved pairs (x[2k], x[2k+1]) times (cos + i sin).
@@ -322,8 +328,12 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpilogue& e, const uint3
 // half into both CTAs' shared memory: B's L2 -> SM traffic halves (the 128x256 tiles are L2-bandwidth
 // bound at full grid: 48 KB per 4.2 MFLOP).  A ring stage is refilled only when both CTAs have consumed
 // it (the MMA warps' commits arrive on both CTAs' `empty` barriers).
+// 144 registers, not the 168 that 320 threads (allocated as 12 warps) would allow: the data-parallel train step overlaps
+// NCCL's all-reduce with the backward's GEMMs, and an NCCL CTA only finds room beside a GEMM CTA when the latter leaves
+// registers free — at 168 the overlapped step at per-GPU batch 2 went from 2.29 to 2.63 ms on 2 GPUs (3.41 against
+// 2.42 on 8); the rollout pays ~1 % for the cap.
 template <int BN, bool AMN, bool BMN, int CL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(144)
 gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
@@ -589,7 +599,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
       constexpr int NCH = BN / 64;          // 32-column chunks per thread
       float* bias_s = bias_stage + acc * BN;
       const bool use_res = first && e.residual != nullptr;
-      uint32_t regs[32], resv[32], res_next[32];
+      uint32_t regs[32], resv[32];
       if (e.bias != nullptr) {
         const int te = static_cast<int>(threadIdx.x) - 64;
         if (te < BN) {
@@ -609,14 +619,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
         for (int i = 0; i < NCH; ++i) {
           const int c = half + 2 * i;
           ptx::tmem_ld_32x32(t_row + c * 32, regs);
-          // the next chunk's residual goes in flight before this chunk is processed (its L2 latency is ~10x TMEM's)
-          if (NCH > 1 && i + 1 < NCH && use_res) load_residual_chunk(e, m, tn * BN + (c + 2) * 32, p.M, p.N, res_next);
           ptx::tmem_ld_wait_on(regs);
-          epilogue_chunk(e, regs, bias_s + c * 32, resv, m, tn * BN + c * 32, p.M, p.N, first, last);
-          if (NCH > 1 && use_res) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) resv[j] = res_next[j];
-          }
+          epilogue_chunk(e, regs, bias_s + c * 32, resv, (use_res && i + 1 < NCH) ? tn * BN + (c + 2) * 32 : -1,
+                         m, tn * BN + c * 32, p.M, p.N, first, last);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -670,7 +675,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum[j] = __float_as_uint(v[j]);
             if (e.residual != nullptr) load_residual_chunk(e, m, tn * BN + c * 32, p.M, p.N, rres);
-            epilogue_chunk(e, sum, bias_s + c * 32, rres, m, tn * BN + c * 32, p.M, p.N, true, true);
+            epilogue_chunk(e, sum, bias_s + c * 32, rres, -1, m, tn * BN + c * 32, p.M, p.N, true, true);
           }
           if (threadIdx.x == 64) p.sk_counters[sg.tile] = 0u;   // self-cleaning for the next launch
         }
