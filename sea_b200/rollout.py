@@ -51,6 +51,14 @@ DEFAULT_SPLITS = int(__import__("os").environ.get("SEA_ROLLOUT_SPLITS", "1"))
 STEPS_PER_GRAPH = int(__import__("os").environ.get("SEA_ROLLOUT_STEPS_PER_GRAPH", "10"))   # measured: 1 -> 5..20: -1 %
 
 
+def _graph_groups(first: int, last: int, per: int):
+    """[(t0, t1)] inclusive step ranges recorded into one CUDA graph each: `per` consecutive steps per graph
+    (per <= 0: everything in one graph)."""
+    n = last - first + 1
+    per = n if per <= 0 else per
+    return [(t0, min(last, t0 + per - 1)) for t0 in range(first, last + 1, per)]
+
+
 class RolloutPlan:
     """The same loop with every step pre-recorded as a CUDA graph.
 
@@ -125,12 +133,11 @@ class RolloutPlan:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         pool = None
-        per = STEPS_PER_GRAPH if STEPS_PER_GRAPH > 0 else self.steps
-        for t0 in range(1, self.steps + 1, per):
+        for t0, t1 in _graph_groups(1, self.steps, STEPS_PER_GRAPH):
             g = torch.cuda.CUDAGraph()
             n = 0
             with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode="relaxed"):
-                for t in range(t0, min(self.steps, t0 + per - 1) + 1):
+                for t in range(t0, t1 + 1):
                     n += self._step(t) + len(self.subs)
             pool = g.pool()
             self.graphs.append(g)
@@ -216,12 +223,11 @@ class CachedRolloutPlan:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         pool = None
-        per = STEPS_PER_GRAPH if STEPS_PER_GRAPH > 0 else self.steps
-        for t0 in range(0, self.steps, per):
+        for t0, t1 in _graph_groups(0, self.steps - 1, STEPS_PER_GRAPH):
             g = torch.cuda.CUDAGraph()
             n = 0
             with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode="relaxed"):
-                for t in range(t0, min(self.steps, t0 + per)):
+                for t in range(t0, t1 + 1):
                     self.last_step_launches = self._step(t)
                     n += self.last_step_launches
             pool = g.pool()

@@ -142,3 +142,15 @@ def test_rollout_micro_batch_ranges():
     assert _split_ranges(7, 4) == [(0, 2), (2, 4), (4, 6), (6, 7)]
     assert _split_ranges(3, 8) == [(0, 1), (1, 2), (2, 3)]          # at most B groups, at most 4 (stream-K workspaces)
     assert _split_ranges(5, 0) == [(0, 5)]
+
+
+def test_rollout_graph_groups():
+    """Steps per CUDA graph of the rollout plans (sea_b200/rollout.py): every step exactly once, in order."""
+    from sea_b200.rollout import _graph_groups
+    assert _graph_groups(1, 100, 10) == [(1 + 10 * i, 10 + 10 * i) for i in range(10)]
+    assert _graph_groups(1, 100, 1) == [(t, t) for t in range(1, 101)]
+    assert _graph_groups(1, 100, 0) == [(1, 100)]
+    assert _graph_groups(0, 6, 3) == [(0, 2), (3, 5), (6, 6)]
+    for first, last, per in [(1, 7, 10), (0, 0, 4), (1, 23, 8)]:
+        g = _graph_groups(first, last, per)
+        assert [t for a, b in g for t in range(a, b + 1)] == list(range(first, last + 1))
