@@ -272,3 +272,15 @@ def accelerate_spatial(model: nn.Module, precision: str = "fp32") -> nn.Module:
     model.forward = types.MethodType(lambda self, x: codec.decode(codec.encode(x, fix_pad=True)), model)
     model._sea_codec = codec
     return model
+
+
+def accelerate_spatial_training(model):
+    """Encoder / decoder TRAINING (train/train_encoder.py:205-214; optional in SURVEY §8a): rebinds the nn.Linear, MLP
+    and LayerNorm leaves of the reference's own ``SpatialModel`` to the tcgen05 GEMM / row-norm kernels with their
+    backward (``sea_b200.modules``); the attention core over the 64 patch tokens (head dim 8 / 16) keeps the
+    reference's eager code.  bf16 operands, fp32 accumulation and master weights; ``tests/test_modes_gpu.py::
+    test_encoder_decoder_training_through_the_module_path`` (loss 1e-5, gradients 7e-3, ten AdamW iterations against the
+    eager fp32 copy).  Returns the {kind: count} of rebound modules.  The frozen-codec inference path is
+    ``accelerate_spatial``."""
+    from .modules import accelerate_modules
+    return accelerate_modules(model)

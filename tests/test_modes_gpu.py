@@ -109,3 +109,60 @@ def test_default_mode_still_uses_the_fused_executor(cuda, ns):
     m = ns.temporal.TemporalModel(1, 256, 2, 64, 4, 0, 2, 2, 0.0, "sea", "learnable", "mlp", "add", 1, 1, True, "adaln").to(cuda)
     accelerate(m)
     assert hasattr(m, "_sea_engine") and not hasattr(m, "_sea_modules")
+
+
+@pytest.mark.parametrize("name", ["cylinder_flow", "multiphase_flow"])
+def test_encoder_decoder_training_through_the_module_path(cuda, ns, name):
+    """Encoder / decoder TRAINING (train/train_encoder.py:205-214, optional in SURVEY §8a): the reference's own
+    SpatialModel, built by ProcessData.initialize_spatial_model, with its nn.Linear / MLP / LayerNorm leaves rebound to
+    the tcgen05 GEMM and row-norm kernels (forward and backward); the 64-token attention core (head dim 8 / 16) stays
+    the reference's eager code.  Loss, every gradient and ten AdamW iterations against the eager fp32 copy."""
+    from sea_b200.modules import accelerate_modules
+    cfg = oref.temporal_config(name)
+    cfg["device"] = str(cuda)
+    cfg["dropout_spatial"] = 0.0
+    torch.manual_seed(3)
+    proc = ns.data_processors.ProcessData(64, cfg)
+    eager = proc.initialize_spatial_model().train()
+    fast = copy.deepcopy(eager)
+    counts = accelerate_modules(fast)
+    assert counts["linear"] > 0 and counts["mlp"] > 0, counts
+    n_fields = max(max(g) for g in cfg["field_groups"]) + 1
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(24, 64, n_fields, 64, generator=g).to(cuda)
+    opts = [torch.optim.AdamW(m.parameters(), lr=1e-4) for m in (eager, fast)]
+    curves = ([], [])
+    for it in range(10):
+        for k, (m, opt) in enumerate(zip((eager, fast), opts)):
+            opt.zero_grad()
+            loss = F.mse_loss(m(x.clone()), x)
+            loss.backward()
+            curves[k].append(loss.item())
+            if it == 0 and k == 1:
+                worst = 0.0
+                for (pn, pe), (_, pf) in zip(eager.named_parameters(), fast.named_parameters()):
+                    if pe.grad is None or pe.grad.norm() < 1e-10:
+                        continue
+                    assert pf.grad is not None, pn
+                    worst = max(worst, _rel(pf.grad, pe.grad))
+                print(f"\n[encoder training, module path] {name}: bound {counts}, loss rel {abs(curves[1][0] - curves[0][0]) / curves[0][0]:.2e}, "
+                      f"worst gradient rel {worst:.2e}")
+                assert worst < 8e-2
+        for opt in opts:
+            opt.step()
+    for a, b in zip(*curves):
+        assert abs(a - b) / a < 2e-2
+    # informational: one training iteration, eager fp32 vs module path, same GPU
+    times = []
+    for m, opt in zip((eager, fast), opts):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            opt.zero_grad()
+            F.mse_loss(m(x.clone()), x).backward()
+            opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) / 10)
+    print(f"[encoder training, module path] {name}: {times[0]:.2f} ms eager fp32 -> {times[1]:.2f} ms per iteration (24 snapshots)")
