@@ -1,6 +1,7 @@
 """Data-parallel training check (run under torchrun, one rank per GPU):
 every rank trains the SAME small temporal model on ITS shard of a global batch with the CUDA path
-(sea_b200.parallel.train_step: backward -> NCCL all-reduce of the flat gradient buffer -> AdamW);
+(sea_b200.parallel.train_step: backward -> all-reduce of the gradient buckets (NCCL; gloo with SEA_DP_BACKEND=gloo,
+which also lets two ranks share one GPU) -> AdamW);
 rank 0 also trains the fp32 oracle on CPU on the WHOLE global batch and compares the loss curves.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
@@ -19,8 +20,11 @@ from oracle import sea_oracle as so  # noqa: E402
 from sea_b200 import parallel  # noqa: E402
 from sea_b200.temporal import TemporalModel  # noqa: E402
 
-rank, world, local = parallel.init_from_env()
-dev = torch.device("cuda", local)
+# SEA_DP_BACKEND=gloo: the ranks may SHARE a GPU (NCCL refuses two ranks on one device) — the CUDA backward with its
+# per-group events, the bucket planner, the bf16 twin and the twin-reading AdamW are exactly those of the NCCL run; only
+# the transport of the collective differs (gloo stages the CUDA buckets through pinned host memory)
+rank, world, local = parallel.init_from_env(os.environ.get("SEA_DP_BACKEND") or None)
+dev = torch.device("cuda", local % torch.cuda.device_count())
 torch.cuda.set_device(dev)
 E, nh, scale, V, T, steps = 128, 2, 2, 2, 12, 30
 LR = 1e-3

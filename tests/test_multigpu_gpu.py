@@ -30,6 +30,20 @@ def test_dp_training_matches_oracle_global_batch(cuda, ln, width, opt):
     assert r.returncode == 0 and "DP_TRAIN_OK" in r.stdout
 
 
+@pytest.mark.parametrize("ln,width,opt", [("adaln", "small", "torch"), ("ln", "small", "fused"), ("adaln", "full", "fused")])
+def test_dp_training_two_ranks_sharing_one_gpu(cuda, ln, width, opt):
+    """The same check on ANY box, a 1-GPU one included: two ranks share cuda:0 and exchange over gloo (NCCL refuses two
+    ranks on one device).  Everything on the device is the product path — backward with its per-group events, bucket
+    planner, overlapped side-stream exchange, bf16 gradient twin, twin-reading fused AdamW; only the collective's
+    transport differs from the NCCL cases above."""
+    env = dict(os.environ, SEA_LN=ln, SEA_DP_WIDTH=width, SEA_DP_OPT=opt, SEA_DP_BACKEND="gloo")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29521", "scripts/dp_train_check.py"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "DP_TRAIN_OK" in r.stdout
+
+
 def test_bench_two_gpus_weak_scaling_line(cuda):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
