@@ -74,7 +74,7 @@ class _Lazy:
             dll.sea_strerror.restype = C.c_char_p
             dll.sea_strerror.argtypes = [C.c_int]
             for fn in ("sea_temporal_cache_bytes", "sea_temporal_workspace_bytes", "sea_temporal_cond_cache_bytes",
-                       "sea_temporal_kv_cache_bytes"):
+                       "sea_temporal_kv_cache_bytes", "sea_spatial_cache_bytes"):
                 if hasattr(dll, fn):
                     getattr(dll, fn).restype = C.c_size_t
             if os.environ.get("SEA_B200_PDL", "1") == "0":   # A/B switch for programmatic dependent launch
