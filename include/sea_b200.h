@@ -633,6 +633,13 @@ int sea_last_launch_count(void);
 int sea_event_create(void** out_event);
 int sea_event_destroy(void* cuda_event);
 int sea_stream_wait_event(sea_stream_t stream, void* cuda_event);
+/* Strided device -> host copy for hosts without a runtime binding: `rows` rows of `row_bytes` bytes from a device buffer
+ * with row pitch `src_pitch` into PINNED host memory with row pitch `dst_pitch`, asynchronously on `stream` (one
+ * cudaMemcpy2DAsync).  The graphed rollout hands every finished group of steps to the host with it while the next group
+ * still runs (the results of utils/train_utils.py:209 `torch.cat(preds)` reach the host without a trailing copy).
+ * Returns 0 or a cudaError_t. */
+int sea_copy_rows_to_host(void* dst_host, size_t dst_pitch, const void* src_dev, size_t src_pitch, size_t row_bytes,
+                          size_t rows, sea_stream_t stream);
 
 /* Optional per-launch timing (CUDA events on the launching stream) for roofline accounting.
  * Between begin and end every executor launch is bracketed by an event pair; end synchronises on

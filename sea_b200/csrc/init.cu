@@ -91,6 +91,14 @@ extern "C" int sea_stream_wait_event(sea_stream_t stream, void* ev) {
   return static_cast<int>(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(ev), 0));
 }
 
+extern "C" int sea_copy_rows_to_host(void* dst_host, size_t dst_pitch, const void* src_dev, size_t src_pitch,
+                                     size_t row_bytes, size_t rows, sea_stream_t stream) {
+  if (!dst_host || !src_dev || row_bytes > dst_pitch || row_bytes > src_pitch) return SEA_ERR_INVALID;
+  if (rows == 0 || row_bytes == 0) return SEA_OK;
+  return static_cast<int>(cudaMemcpy2DAsync(dst_host, dst_pitch, src_dev, src_pitch, row_bytes, rows,
+                                            cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)));
+}
+
 extern "C" const char* sea_strerror(int code) {
   switch (code) {
     case SEA_OK: return "ok";

@@ -133,7 +133,8 @@ class RolloutPlan:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         pool = None
-        for t0, t1 in _graph_groups(1, self.steps, STEPS_PER_GRAPH):
+        self.groups = _graph_groups(1, self.steps, STEPS_PER_GRAPH)
+        for t0, t1 in self.groups:
             g = torch.cuda.CUDAGraph()
             n = 0
             with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode="relaxed"):
@@ -148,16 +149,49 @@ class RolloutPlan:
     def valid_for(self, eng) -> bool:
         return eng._cache is not None and self.key == _plan_key(eng)
 
+    def _host_copy_handles(self, out_host: torch.Tensor):
+        """(copy stream, one event per graph group) for streaming the predictions to `out_host`, after checking that it
+        is what cudaMemcpy2DAsync can fill asynchronously: pinned fp32 [B, steps, V, E] with contiguous trajectories."""
+        want = (self.B, self.steps, self.V, self.E)
+        if (out_host.is_cuda or out_host.dtype != torch.float32 or tuple(out_host.shape) != want
+                or not out_host.is_pinned() or out_host.stride(3) != 1 or out_host.stride(2) != self.E
+                or out_host.stride(1) != self.V * self.E or out_host.stride(0) < self.steps * self.V * self.E):
+            raise RuntimeError(f"out_host must be a pinned fp32 host tensor {want} with contiguous trajectories")
+        if getattr(self, "_copy", None) is None:
+            self._copy = (torch.cuda.Stream(device=self.seq.device), [torch.cuda.Event() for _ in self.graphs])
+        return self._copy
+
     @torch.no_grad()
-    def run(self, x0: torch.Tensor, ib: torch.Tensor) -> torch.Tensor:
+    def run(self, x0: torch.Tensor, ib: torch.Tensor, out_host: torch.Tensor | None = None) -> torch.Tensor:
         """x0 [B,1,V,E], ib [B,>=1,ib_num] (time-invariant) -> view [B,steps,V,E] of the plan's own
-        sequence buffer (overwritten by the next run)."""
+        sequence buffer (overwritten by the next run).  out_host (optional, pinned [B,steps,V,E]): every finished graph
+        group's predictions are copied to it on a side stream while the next group runs (one strided
+        cudaMemcpy2DAsync per group); the calling stream waits for the copies at the end of the call, so a stream
+        synchronize makes out_host readable and a following run cannot overwrite rows still in flight."""
         self.eng._ensure(False)
         self.seq[:, 0].copy_(x0[:, 0])
         self.ib1.copy_(ib[:, :1])
         self.ib2.copy_(ib[:, :1].expand(-1, 2, -1))
-        for g in self.graphs:
-            g.replay()
+        if out_host is None:
+            for g in self.graphs:
+                g.replay()
+        else:
+            copy_stream, events = self._host_copy_handles(out_host)
+            cur = torch.cuda.current_stream()
+            row = self.V * self.E * 4                           # bytes of one step of one trajectory
+            cs = C.c_void_p(copy_stream.cuda_stream)
+            for g, ev, (t0, t1) in zip(self.graphs, events, self.groups):
+                g.replay()
+                ev.record(cur)
+                copy_stream.wait_event(ev)
+                # seq[:, t0 : t1+1] (steps t0..t1 of every trajectory) -> out_host[:, t0-1 : t1]
+                check(lib.sea_copy_rows_to_host(C.c_void_p(out_host.data_ptr() + (t0 - 1) * row),
+                                                C.c_size_t(out_host.stride(0) * 4),
+                                                C.c_void_p(self.seq.data_ptr() + t0 * row),
+                                                C.c_size_t(self.seq.stride(0) * 4),
+                                                C.c_size_t((t1 - t0 + 1) * row), C.c_size_t(self.B), cs),
+                      "copy_rows_to_host")
+            cur.wait_stream(copy_stream)
         n = sum(self.launches)
         self.eng.last_launches = self.last_step_launches
         self.eng.total_launches += n
@@ -257,7 +291,7 @@ def _profiling() -> bool:
 @torch.no_grad()
 def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
             ib_time_invariant: bool | None = None, graphs: bool = True, cached: bool = False,
-            _view_ok: bool = False, splits: int | None = None) -> torch.Tensor:
+            _view_ok: bool = False, splits: int | None = None, out_host: torch.Tensor | None = None) -> torch.Tensor:
     """x0 [B,1,V,E], ib [B,>=steps,ib_num] -> predicted latents [B,steps,V,E].
 
     ``ib`` is the time-invariant physical parameter of a trajectory in the reference's data
@@ -267,7 +301,11 @@ def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
     the same inputs.
 
     ``cached=True`` (opt-in) runs the KV-cached incremental engine instead of recomputing the prefix:
-    same outputs up to rounding, O(1) instead of O(t) work per step (``CachedRolloutPlan``)."""
+    same outputs up to rounding, O(1) instead of O(t) work per step (``CachedRolloutPlan``).
+
+    ``out_host`` (optional, pinned fp32 [B,steps,V,E]): also deliver the predictions to the host, asynchronously on the
+    calling stream's timeline (synchronize the stream before reading it).  The graphed plan streams every finished
+    group of steps out while the next one runs; the other paths copy once at the end."""
     eng = _engine_of(model)
     if ib_time_invariant is None:
         ib_time_invariant = bool((ib[:, :steps] == ib[:, :1]).all().item())
@@ -284,6 +322,8 @@ def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
                 plans.clear()
             plan = plans[key] = CachedRolloutPlan(model, x0.shape[0], steps, x0.device, bool(ib_time_invariant), nsplit)
         out = plan.run(x0, ib)
+        if out_host is not None:
+            out_host.copy_(out, non_blocking=True)
         return out if _view_ok else out.clone()
     if graphs and eng is not None and ib_time_invariant and x0.is_cuda and not _profiling():
         eng._ensure(False)
@@ -295,7 +335,7 @@ def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
             if len(plans) >= 4:
                 plans.clear()
             plan = plans[key] = RolloutPlan(model, x0.shape[0], steps, x0.device, nsplit)
-        out = plan.run(x0, ib)
+        out = plan.run(x0, ib, out_host=out_host)
         return out if _view_ok else out.clone()   # the plan's buffer is overwritten by the next run
     prev = None
     if eng is not None:
@@ -314,16 +354,18 @@ def rollout(model, x0: torch.Tensor, ib: torch.Tensor, steps: int,
             eng.ib_time_invariant = prev
             eng.cond_reuse, eng._cond_valid = False, False
             eng.weights_frozen = False
+    if out_host is not None:
+        out_host.copy_(seq[:, 1:], non_blocking=True)
     return seq[:, 1:]
 
 
 def rollout_from_host(model, x0_host: torch.Tensor, ib_host: torch.Tensor, steps: int,
                       out_host: torch.Tensor, device) -> torch.Tensor:
-    """End-to-end variant: pinned host inputs -> device, rollout, predicted latents -> pinned host."""
+    """End-to-end variant: pinned host inputs -> device, rollout, predicted latents -> pinned host (streamed out group by
+    group behind the graphed plan, see ``RolloutPlan.run``)."""
     x0 = x0_host.to(device, non_blocking=True)
     ib = ib_host.to(device, non_blocking=True)
-    pred = rollout(model, x0, ib, steps, _view_ok=True)
-    out_host.copy_(pred, non_blocking=True)
+    rollout(model, x0, ib, steps, _view_ok=True, out_host=out_host)
     torch.cuda.current_stream().synchronize()
     return out_host
 

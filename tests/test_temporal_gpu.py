@@ -352,3 +352,31 @@ def test_micro_batched_rollout_plans_match_single_batch(cuda):
             out_c = rollout(m, x0, ib, 14, cached=True, splits=splits).clone()
             assert rel_l2(out.cpu(), ref.cpu()) < 1e-5, splits
             assert rel_l2(out_c.cpu(), ref_c.cpu()) < 1e-5, splits
+
+
+def test_rollout_streams_predictions_to_pinned_host(cuda):
+    """rollout(out_host=...): the graphed plan hands every finished group of steps to the pinned host buffer on a side
+    stream (sea_copy_rows_to_host, one strided copy per group) — same bytes as the device result, on repeated runs with
+    other trajectories, into a batch-strided host view, and through the paths that copy once at the end."""
+    from sea_b200.rollout import rollout
+    g, sd, cfg, m, x, ib, _, _ = build("small_adaln", "adaln", "bf16", cuda)
+    B, V, E = x.shape[0], x.shape[2], x.shape[3]
+    steps = 25                                              # three graph groups at 10 steps per graph: 10 + 10 + 5
+    ibc = ib[:, :1].expand(B, steps, 1).contiguous()
+    host = torch.empty(B, steps, V, E).pin_memory()
+    wide = torch.empty(B, steps + 3, V, E).pin_memory()      # a [B, steps] window of a longer host buffer
+    for trial in range(3):
+        x0 = x[:, trial:trial + 1].contiguous()
+        host.fill_(float("nan"))
+        dst = host if trial < 2 else wide[:, 2:2 + steps]
+        dev = rollout(m, x0, ibc, steps, out_host=dst)
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(dst, dev.cpu()), trial
+    assert torch.equal(dev.cpu(), rollout(m, x0, ibc, steps).cpu())          # the copies do not disturb the result
+    for kw in (dict(graphs=False), dict(cached=True)):
+        host.fill_(float("nan"))
+        dev = rollout(m, x0, ibc, steps, out_host=host, **kw)
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(host, dev.cpu()), kw
+    with pytest.raises(RuntimeError, match="pinned"):
+        rollout(m, x0, ibc, steps, out_host=torch.empty(B, steps, V, E))
