@@ -599,7 +599,6 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd_tc2_kernel(const __grid
       // only the P that feeds P.V is masked and rescaled
       const unsigned long long drop_row = DROP ? ((static_cast<unsigned long long>(b) * pp.n_heads + h) * pp.T + q) *
                                                      static_cast<unsigned long long>((pp.T + 1) & ~1) + kv0 : 0ull;
-#pragma unroll
       float nm = neg_m;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
